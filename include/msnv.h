@@ -1,0 +1,172 @@
+/* msnv.h -- C ABI of libmsnv_gpu.so: the B200 (sm_100a) implementation of metaSNV Part I's hot path.
+ *
+ * The reference has no library API for this path: the boundary is a process boundary
+ * (metaSNV.py:63-65 spawns `qaCompute`, metaSNV.py:160-176 pipes `samtools mpileup` into
+ * `snpCall`). The host programs that keep those command lines (metasnv_b200/csrc/bin) are thin:
+ * they decode BAM into the structure-of-arrays batches declared here and call these entry points,
+ * which are what a maintainer of the reference would bind instead of
+ *   - the per-line counting / calling loop of src/snpCaller/call_vC.cpp:466-668 together with the
+ *     column building that `samtools mpileup` does upstream of it (metaSNV.py:160-165), and
+ *   - the scatter / prefix-sum / histogram of src/qaTools/qaCompute.cpp:530-552 and :125-221.
+ *
+ * Conventions: every function returns 0 on success or a negative msnv_status; nothing throws.
+ * A context belongs to one device and one host thread at a time. Host buffers handed to
+ * msnv_shard_add_sample() are copied asynchronously on the context's stream (a DMA when they are
+ * pinned) and must stay valid until msnv_shard_sync() or msnv_shard_run() returns. Result pointers
+ * are owned by the context and stay valid until the next msnv_shard_begin() / msnv_destroy().
+ * There is no CPU implementation behind this ABI: without a CUDA device every call fails.
+ */
+#ifndef MSNV_H
+#define MSNV_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSNV_ABI_VERSION 1
+
+/* Positions per tile: contigs of a shard are laid out back to back in a "shard coordinate" space,
+ * each starting at a multiple of MSNV_TILE, so a tile never spans two contigs. */
+#define MSNV_TILE 512
+/* Limits of the tiled pileup kernel (longer reads are rejected with MSNV_E_LIMIT). */
+#define MSNV_MAX_READ_BASES 8192
+#define MSNV_MAX_READ_CIGAR 256
+
+typedef enum {
+    MSNV_OK = 0,
+    MSNV_E_CUDA = -1,      /* a CUDA call failed; see msnv_last_error() */
+    MSNV_E_ARG = -2,       /* invalid argument */
+    MSNV_E_STATE = -3,     /* call out of order */
+    MSNV_E_LIMIT = -4,     /* input exceeds a documented limit */
+    MSNV_E_NOMEM = -5
+} msnv_status;
+
+typedef struct msnv_ctx msnv_ctx;
+
+/* One sample's reads that take part in the pileup, in coordinate order. "Take part" = the read
+ * passed `samtools mpileup`'s default read filters and depth cap (SURVEY.md Annex A.1, A.3); that
+ * filtering is part of BAM decoding on the host. All offsets are prefix sums with n_reads+1 entries.
+ *   pos      shard coordinate of the first reference base the read covers
+ *   cig_off  first CIGAR word of the read in `cigar`
+ *   seg_off  number of M/=/X operations before this read (the kernel turns each into a segment)
+ *   q4_off   first 4-base group of the read in `seq2` (byte index) / `qual` (byte index * 4)
+ *   mate     index of the earlier mate this read overlaps per mpileup's overlap detection, else -1;
+ *            a read takes part in at most one pair
+ *   cigar    BAM encoding (len << 4 | op), op in MIDNSHP=X
+ *   seq2     2 bits per base, base k of a group in bits 2k..2k+1, A=0 C=1 G=2 T=3
+ *   qual     min(phred,127) per base; bit 7 set when the base is not A/C/G/T (N or IUPAC code)
+ *   max_span largest reference span (sum of M/D/N/=/X lengths) over the reads */
+typedef struct {
+    uint32_t        n_reads;
+    uint32_t        max_span;
+    uint32_t        n_pairs;   /* reads with mate >= 0 */
+    uint32_t        reserved;
+    const int32_t*  pos;
+    const uint32_t* cig_off;
+    const uint32_t* seg_off;
+    const uint32_t* q4_off;
+    const int32_t*  mate;
+    const uint32_t* pair_b;    /* [n_pairs] indices of the reads with mate >= 0, ascending */
+    const uint32_t* cigar;
+    const uint8_t*  seq2;
+    const uint8_t*  qual;
+} msnv_sample_reads;
+
+/* snpCall's thresholds (call_vC.cpp:26-36, options -c -t -p). */
+typedef struct {
+    int32_t min_coverage;       /* -c, default 4 */
+    int32_t calling_threshold;  /* -t, default 4 */
+    double  min_fraction;       /* -p, default 0.01 */
+} msnv_call_params;
+
+/* Called positions of a shard, ascending by position. Allele order in every mask/array is
+ * A, C, G, T (bit 0..3 / index 0..3). A position is listed when pop_mask | ind_mask != 0:
+ *   pop_mask  alleles passing the population test   (call_vC.cpp:588)  -> called_SNPs line
+ *   ind_mask  alleles passing only the individual test (call_vC.cpp:592-600) -> indiv_called line
+ *   cov       [n_hits][n_samples] per-sample coverage (the "c1|...|cS" column, call_vC.cpp:316-325)
+ *   allele    [n_hits][4][n_samples] per-sample count of each non-reference allele (0 for the
+ *             reference's own base, which mpileup renders as '.'/',')
+ *   total     [n_hits][5] population totals: coverage, then A, C, G, T */
+typedef struct {
+    uint32_t        n_hits;
+    uint32_t        n_samples;
+    const uint32_t* pos;
+    const uint8_t*  pop_mask;
+    const uint8_t*  ind_mask;
+    const uint16_t* cov;
+    const uint16_t* allele;
+    const uint32_t* total;
+} msnv_hits;
+
+/* Device-side timings of the last msnv_shard_run(), milliseconds (CUDA events on the context's
+ * stream), plus the work it did. */
+typedef struct {
+    float    ms_index, ms_overlap, ms_pileup, ms_call, ms_compact, ms_gather, ms_total;
+    uint64_t n_items;           /* active (sample, tile) pairs */
+    uint64_t n_reads;
+    uint64_t n_bases;           /* query bases resident for the shard */
+    uint32_t n_tiles;
+    uint32_t kernel_launches;
+} msnv_timings;
+
+int         msnv_abi_version(void);
+int         msnv_device_count(void);
+int         msnv_create(int device, msnv_ctx** out);
+void        msnv_destroy(msnv_ctx* ctx);
+const char* msnv_last_error(const msnv_ctx* ctx);
+
+/* ---- pileup + call (replaces `samtools mpileup ... | snpCall`, metaSNV.py:160-176) ---- */
+
+/* Start a shard of n_positions shard coordinates (a multiple of MSNV_TILE) seen by n_samples
+ * samples. `ref` holds one reference character per position exactly as mpileup would print it
+ * (FASTA case preserved, 'N' where the FASTA has no base); 0 marks a position that must not be
+ * called (padding between contigs, positions outside the -l BED, the first pileup line that
+ * call_vC.cpp:423 consumes). */
+int msnv_shard_begin(msnv_ctx* ctx, uint32_t n_samples, uint32_t n_positions, const uint8_t* ref);
+/* Copy one sample's reads to the device. Samples without reads need not be added. */
+int msnv_shard_add_sample(msnv_ctx* ctx, uint32_t sample, const msnv_sample_reads* reads);
+/* Mark one shard coordinate as not callable after msnv_shard_begin() (same effect as ref[pos] = 0). */
+int msnv_shard_mask_position(msnv_ctx* ctx, uint32_t pos);
+/* Wait until every copy queued by msnv_shard_add_sample() has completed. */
+int msnv_shard_sync(msnv_ctx* ctx);
+/* Run overlap correction, pileup, calling and compaction; fills *hits. May be called repeatedly
+ * (the per-base qualities are restored first), e.g. with different parameters. */
+int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* params, msnv_hits* hits);
+/* Test/inspection hook: per-position A,C,G,T,N counts ([n][5], uint16) of one sample after the last
+ * run, for shard coordinates [first, first+n). */
+int msnv_shard_counts(msnv_ctx* ctx, uint32_t sample, uint32_t first, uint32_t n, uint16_t* out);
+int msnv_get_timings(const msnv_ctx* ctx, msnv_timings* out);
+
+/* Classic mode: counts parsed by the host from `samtools mpileup` text (call_vC.cpp:503-535) for a
+ * batch of n_positions pileup lines (a multiple of MSNV_TILE; pad with ref = 0). Layout of both
+ * arrays: [tile][sample][MSNV_TILE]. acgt packs the letter counts a+A | c+C << 16 | g+G << 32 | t+T << 48,
+ * matches holds '.' + ','. Runs the same call / compaction / gather kernels as msnv_shard_run();
+ * hit positions index the batch's lines. Replaces any open shard. */
+int msnv_call_counts(msnv_ctx* ctx, uint32_t n_samples, uint32_t n_positions, const uint8_t* ref, const uint64_t* acgt,
+                     const uint16_t* matches, const msnv_call_params* params, msnv_hits* hits);
+
+/* ---- coverage (replaces the reductions of qaCompute, metaSNV.py:63-65) ---- */
+
+/* Coverage blocks of one BAM: for every read qaCompute counts (qaCompute.cpp:461-462,518,524-526)
+ * and every 'M' operation, the half-open index range [beg, end) of its contig's coverage array that
+ * the reference increments (qaCompute.cpp:530-552, including its 1-based shift and end clamp).
+ * Blocks are grouped by contig: blocks of contig k are blk_off[k] .. blk_off[k+1]; within a contig
+ * they are in file order (non-decreasing beg up to the span of one read). */
+typedef struct {
+    uint32_t        n_contigs;
+    const uint32_t* contig_len;   /* [n_contigs] chrSize */
+    const uint64_t* blk_off;      /* [n_contigs+1] */
+    const uint32_t* beg;          /* [blk_off[n_contigs]] */
+    const uint32_t* end;
+} msnv_cov_blocks;
+
+/* Per contig: cov_sum[k] = sum of coverage over indices [0, chrSize) and hist[k][c] for
+ * c = 0..max_cov = number of indices with min(coverage, max_cov) == c (qaCompute.cpp:142-165). */
+int msnv_cov_run(msnv_ctx* ctx, const msnv_cov_blocks* blocks, uint32_t max_cov, uint64_t* cov_sum, uint64_t* hist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSNV_H */

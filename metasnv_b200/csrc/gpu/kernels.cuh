@@ -1,0 +1,723 @@
+// kernels.cuh -- sm_100a kernels of the pileup + call path (device side of include/msnv.h).
+//
+// Data flow for one shard (all samples of one genome bin):
+//   index_kernel     (tile, sample) pairs that have reads  -> ordered work items (ballot compaction)
+//   overlap_*        mate-overlap base quality correction, in place (SURVEY.md Annex A.2)
+//   pileup_kernel    per item: stage reads (TMA bulk copies) -> CIGAR walk -> per-position gather
+//                    -> packed A/C/G/T/N counts, 10 B per sample-position      [dominant kernel]
+//   call_kernel      per tile: reduce over samples, snpCall thresholds (call_vC.cpp:545-601)
+//   compact_kernel   ordered stream compaction of called positions (warp ballot + block scan)
+//   gather_kernel    per hit: per-sample coverage / allele counts for the host formatter
+//
+// The reference computes the same quantities one text character at a time
+// (call_vC.cpp:503-535 over the columns rendered by `samtools mpileup`).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../../include/msnv.h"
+
+namespace msnv_gpu {
+
+constexpr int TILE = MSNV_TILE;                 // positions per tile == threads per pileup CTA
+constexpr int PILEUP_THREADS = TILE;
+constexpr int CHUNK_READS = 256;                // reads staged per chunk (at most)
+constexpr int CHUNK_Q4 = 4096;                  // 4-base groups staged per chunk (16384 bases)
+constexpr int CHUNK_CIGAR = 1024;               // CIGAR words staged per chunk
+constexpr int CHUNK_SEGS = 1024;                // aligned segments per chunk
+
+static_assert(MSNV_MAX_READ_BASES * 2 <= CHUNK_Q4 * 4, "one read must fit a chunk with room to spare");
+static_assert(MSNV_MAX_READ_CIGAR * 2 <= CHUNK_CIGAR, "one read's CIGAR must fit a chunk");
+
+struct SampleDev {
+    const int32_t*  pos;
+    const uint32_t* cig_off;
+    const uint32_t* seg_off;
+    const uint32_t* q4_off;
+    const int32_t*  mate;
+    const uint32_t* cigar;
+    const uint8_t*  seq2;
+    uint8_t*        qual;
+    const uint32_t* pair_b;      // [n_pairs] index of the later mate of each overlapping pair
+    const uint32_t* pair_bk;     // [n_pairs+1] byte offsets into `backup`
+    uint8_t*        backup;      // pristine qualities of every read that takes part in a pair
+    uint32_t        n_reads, max_span, n_pairs, pad_;
+};
+
+struct Item { uint32_t sample, tile, r_lo, r_hi; };   // reads [r_lo, r_hi) of `sample` may overlap `tile`
+
+// Per-position population result of call_kernel.
+struct CallParamsDev { int32_t min_cov; int32_t thr; double frac; };
+
+// ------------------------------------------------------------------------------------------------
+// small PTX helpers (mbarrier + 1-D TMA bulk copy), see blackwell_cuda_programming.md G3/G15
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy (TMA, SASS UBLKCP); dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// 1 << s for 64-bit with PTX clamping semantics (s >= 64 gives 0)
+__device__ __forceinline__ uint64_t shl1_clamped(uint32_t s)
+{
+    uint64_t r;
+    asm("shl.b64 %0, 1, %1;" : "=l"(r) : "r"(s));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t lower_bound_i32(const int32_t* __restrict__ a, uint32_t n, int64_t key)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if ((int64_t)__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Block-wide exclusive rank of `flag` among the block's threads (thread order) and the block total.
+// blockDim.x must be a multiple of 32 and at most 1024.
+__device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t* s_warp /*[33]*/, uint32_t& total)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    uint32_t bal = __ballot_sync(0xffffffffu, flag);
+    uint32_t r = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = lane < nwarp ? s_warp[lane] : 0;
+        uint32_t incl = v;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        s_warp[lane] = incl - v;
+        if (lane == 31) s_warp[32] = incl;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    uint32_t base = s_warp[warp];
+    __syncthreads();
+    return base + r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// index: which (tile, sample) pairs have reads. Pairs are enumerated tile-major so that the
+// compacted item list is grouped by tile (call_kernel reads one contiguous run of slots per tile).
+// Two passes over the same predicate: COUNT writes per-block totals, EMIT writes the items at the
+// scanned offsets (ordered stream compaction by warp ballot).
+// ------------------------------------------------------------------------------------------------
+template <bool EMIT>
+__global__ void __launch_bounds__(256) index_kernel(const SampleDev* __restrict__ samples, uint32_t n_samples,
+                                                    uint32_t n_tiles, uint32_t* __restrict__ block_sums,
+                                                    Item* __restrict__ items, uint32_t* __restrict__ tile_begin)
+{
+    __shared__ uint32_t s_warp[33];
+    const uint64_t pair = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    const uint64_t n_pairs = (uint64_t)n_tiles * n_samples;
+    bool active = false;
+    uint32_t s = 0, t = 0, r_lo = 0, r_hi = 0;
+    if (pair < n_pairs) {
+        t = (uint32_t)(pair / n_samples);
+        s = (uint32_t)(pair - (uint64_t)t * n_samples);
+        const uint32_t n = samples[s].n_reads;
+        if (n) {
+            const int32_t* pos = samples[s].pos;
+            const int64_t t0 = (int64_t)t * TILE;
+            r_lo = lower_bound_i32(pos, n, t0 - (int64_t)samples[s].max_span + 1);
+            r_hi = lower_bound_i32(pos, n, t0 + TILE);
+            active = r_hi > r_lo;
+        }
+    }
+    uint32_t total;
+    uint32_t rank = block_rank(active, s_warp, total);
+    if (!EMIT) {
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+    } else {
+        const uint32_t slot = block_sums[blockIdx.x] + rank;     // block_sums holds exclusive offsets now
+        if (active) items[slot] = Item{s, t, r_lo, r_hi};
+        if (pair < n_pairs && s == 0) tile_begin[t] = slot;
+    }
+}
+
+// Work items of dense count tiles handed in by the host (classic text mode): every sample on every tile.
+__global__ void dense_items_kernel(uint32_t n_samples, uint32_t n_tiles, Item* __restrict__ items, uint32_t* __restrict__ tile_begin)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t n = (uint64_t)n_samples * n_tiles;
+    if (i < n) {
+        const uint32_t t = (uint32_t)(i / n_samples), s = (uint32_t)(i - (uint64_t)t * n_samples);
+        items[i] = Item{s, t, 0u, 0u};
+        if (s == 0) tile_begin[t] = (uint32_t)i;
+    }
+    if (i == n) tile_begin[n_tiles] = (uint32_t)n;
+}
+
+// Exclusive scan of `v[0..n)` in place by one CTA; total to *total.
+__global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ v, uint32_t n, uint32_t* __restrict__ total)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t x = i < n ? v[i] : 0;
+        uint32_t incl = x;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane], wi = w;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        if (i < n) v[i] = carry + s_warp[warp] + incl - x;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[warp] + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mate-overlap quality correction (htslib tweak_overlap_quality as summarised in SURVEY.md A.2).
+// One thread per overlapping pair; both reads' CIGARs are walked in lock step. Qualities live in
+// 7 bits (bit 7 flags a non-ACGT base), so the 200 cap becomes 127: only "q >= 13" is ever used.
+// ------------------------------------------------------------------------------------------------
+struct CigarWalk {
+    const uint32_t* c; uint32_t n, k; int32_t x; uint32_t y;     // x: reference coordinate, y: query offset
+    __device__ void init(const uint32_t* cig, uint32_t n_ops, int32_t pos) { c = cig; n = n_ops; k = 0; x = pos; y = 0; }
+    // smallest aligned (M/=/X) reference coordinate >= want; false when the read is exhausted
+    __device__ bool seek(int32_t want, int32_t& ref, uint32_t& q)
+    {
+        while (k < n) {
+            const uint32_t w = __ldg(c + k), op = w & 0xf; const int32_t len = (int32_t)(w >> 4);
+            if (op == 0 || op == 7 || op == 8) {
+                if (want < x + len) { ref = want > x ? want : x; q = y + (uint32_t)(ref - x); return true; }
+                x += len; y += (uint32_t)len;
+            } else if (op == 2 || op == 3) x += len;
+            else if (op == 1 || op == 4) y += (uint32_t)len;
+            ++k;
+        }
+        return false;
+    }
+};
+
+__device__ __forceinline__ uint32_t base2_at(const uint8_t* seq2, uint32_t q)
+{
+    return (seq2[q >> 2] >> ((q & 3) * 2)) & 3;
+}
+
+// mode 0: save pristine qualities of both mates; 1: restore them; 2: apply the correction
+template <int MODE>
+__global__ void __launch_bounds__(128) overlap_kernel(const SampleDev* __restrict__ samples, const uint32_t* __restrict__ pair_base,
+                                                      uint32_t n_samples, uint64_t n_pairs_total)
+{
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_pairs_total) return;
+    // sample lookup: pair_base[s] <= g < pair_base[s+1]
+    uint32_t lo = 0, hi = n_samples;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (__ldg(pair_base + mid) <= g) lo = mid; else hi = mid; }
+    const SampleDev sd = samples[lo];
+    const uint32_t pi = (uint32_t)(g - __ldg(pair_base + lo));
+    const uint32_t b = __ldg(sd.pair_b + pi);
+    const uint32_t a = (uint32_t)__ldg(sd.mate + b);
+    const uint32_t qa0 = __ldg(sd.q4_off + a), qa1 = __ldg(sd.q4_off + a + 1);
+    const uint32_t qb0 = __ldg(sd.q4_off + b), qb1 = __ldg(sd.q4_off + b + 1);
+    uint8_t* aq = sd.qual + (size_t)qa0 * 4;
+    uint8_t* bq = sd.qual + (size_t)qb0 * 4;
+    if (MODE == 0 || MODE == 1) {
+        uint32_t* bk = (uint32_t*)(sd.backup + __ldg(sd.pair_bk + pi));
+        uint32_t* a4 = (uint32_t*)aq; uint32_t* b4 = (uint32_t*)bq;
+        const uint32_t na = qa1 - qa0, nb = qb1 - qb0;
+        if (MODE == 0) { for (uint32_t i = 0; i < na; ++i) bk[i] = a4[i]; for (uint32_t i = 0; i < nb; ++i) bk[na + i] = b4[i]; }
+        else           { for (uint32_t i = 0; i < na; ++i) a4[i] = bk[i]; for (uint32_t i = 0; i < nb; ++i) b4[i] = bk[na + i]; }
+        return;
+    }
+    const uint8_t* as = sd.seq2 + qa0;
+    const uint8_t* bs = sd.seq2 + qb0;
+    CigarWalk wa, wb;
+    const uint32_t ca = __ldg(sd.cig_off + a), cb = __ldg(sd.cig_off + b);
+    const int32_t pa = __ldg(sd.pos + a), pb = __ldg(sd.pos + b);
+    wa.init(sd.cigar + ca, __ldg(sd.cig_off + a + 1) - ca, pa);
+    wb.init(sd.cigar + cb, __ldg(sd.cig_off + b + 1) - cb, pb);
+    int32_t ref = pb;
+    for (;;) {
+        int32_t ra, rb; uint32_t ia, ib;
+        if (!wa.seek(ref, ra, ia)) break;
+        if (ra > ref) ref = ra;
+        if (!wb.seek(ref, rb, ib)) break;
+        if (rb > ref) { ref = rb; continue; }
+        const uint32_t va = aq[ia], vb = bq[ib];
+        const uint32_t fa = va & 0x80u, fb = vb & 0x80u;
+        const uint32_t q1 = va & 0x7fu, q2 = vb & 0x7fu;
+        // "same base" in htslib compares 4-bit codes; non-ACGT codes all collapse to the flag here
+        const bool same = (fa || fb) ? (fa && fb) : (base2_at(as, ia) == base2_at(bs, ib));
+        if (same) {
+            uint32_t q = q1 + q2; if (q > 127u) q = 127u;
+            aq[ia] = (uint8_t)(fa | q); bq[ib] = (uint8_t)fb;
+        } else if (q1 >= q2) {
+            aq[ia] = (uint8_t)(fa | (uint32_t)(0.8 * (double)q1)); bq[ib] = (uint8_t)fb;
+        } else {
+            bq[ib] = (uint8_t)(fb | (uint32_t)(0.8 * (double)q2)); aq[ia] = (uint8_t)fa;
+        }
+        ++ref;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pileup: one CTA per work item (sample, tile); thread i owns position tile*TILE + i.
+// Reads are staged chunk by chunk into shared memory with TMA bulk copies, their CIGARs are walked
+// into aligned segments, the per-base (2-bit base, quality) pairs are turned into 1-byte codes in
+// place, and every thread then gathers the codes of the segments that cover its own position. No
+// atomics: a position's counters live in the registers of exactly one thread, so deep coverage
+// costs instructions in proportion to bases and nothing for contention.
+//
+// Shared memory carve-up (dynamic), all regions 16-byte aligned:
+//   s_meta   4 x (CHUNK_READS+1) u32   pos | q4_off | cig_off | seg_off of the chunk's reads (+1 end)
+//   s_seq    CHUNK_Q4 + 32 bytes       2-bit bases           (TMA destination)
+//   s_qual   4*CHUNK_Q4 + 32 bytes     qualities -> codes    (TMA destination)
+//   s_cig    4*CHUNK_CIGAR + 32 bytes  CIGAR words           (TMA destination)
+//   s_seg    CHUNK_SEGS x 16 bytes     {ref begin, length, byte address of first code, read pos}
+// Codes: 0..3 = A,C,G,T with quality >= 13; 4 = non-ACGT base with quality >= 13; 7 = not counted.
+// ------------------------------------------------------------------------------------------------
+constexpr int META_STRIDE = CHUNK_READS + 4;
+constexpr size_t PILEUP_SMEM = 4 * META_STRIDE * 4 + (CHUNK_Q4 + 32) + (4 * CHUNK_Q4 + 32) + (4 * CHUNK_CIGAR + 32) + CHUNK_SEGS * 16 + 64;
+
+__global__ void __launch_bounds__(PILEUP_THREADS, 2)
+pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items,
+              uint64_t* __restrict__ acgt /*[n_items][TILE]*/, uint16_t* __restrict__ ncnt /*[n_items][TILE]*/,
+              int* __restrict__ err_flag)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t* s_pos = (uint32_t*)smem;
+    uint32_t* s_q4  = s_pos + META_STRIDE;
+    uint32_t* s_cgo = s_q4 + META_STRIDE;
+    uint32_t* s_sgo = s_cgo + META_STRIDE;
+    uint8_t*  s_seq  = (uint8_t*)(s_sgo + META_STRIDE);
+    uint8_t*  s_qual = s_seq + CHUNK_Q4 + 32;
+    uint8_t*  s_cig  = s_qual + 4 * CHUNK_Q4 + 32;
+    uint4*    s_seg  = (uint4*)(s_cig + 4 * CHUNK_CIGAR + 32);
+    uint64_t* s_bar  = (uint64_t*)(s_seg + CHUNK_SEGS);
+    uint32_t* s_misc = (uint32_t*)(s_bar + 1);        // [0] reads in chunk, [1] max span in chunk
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const Item it = items[blockIdx.x];
+    const SampleDev sd = samples[it.sample];
+    const int32_t p0 = (int32_t)(it.tile * TILE);
+    const int32_t my_pos = p0 + (int32_t)tid;
+    const int32_t warp_lo = p0 + (int32_t)(tid & ~31u);          // first position owned by this warp
+
+    if (tid == 0) { mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+
+    uint64_t acc = 0;       // A | C<<16 | G<<32 | T<<48
+    uint32_t acc_n = 0;
+    uint32_t parity = 0;
+
+    for (uint32_t c0 = it.r_lo; c0 < it.r_hi;) {
+        // ---- 1. read metadata of up to CHUNK_READS reads (+1 for the end offsets)
+        uint32_t n = it.r_hi - c0; if (n > CHUNK_READS) n = CHUNK_READS;
+        if (tid <= n) {
+            s_q4[tid]  = __ldg(sd.q4_off + c0 + tid);
+            s_cgo[tid] = __ldg(sd.cig_off + c0 + tid);
+            s_sgo[tid] = __ldg(sd.seg_off + c0 + tid);
+            if (tid < n) s_pos[tid] = (uint32_t)__ldg(sd.pos + c0 + tid);
+        }
+        if (tid == 0) { s_misc[0] = 0; s_misc[1] = 0; }
+        __syncthreads();
+        // how many of them fit the byte / cigar / segment budgets: the largest m with all prefix
+        // differences within budget (prefix sums are monotone, so the predicate is monotone in m)
+        if (tid >= 1 && tid <= n) {
+            const bool fits = s_q4[tid] - s_q4[0] <= CHUNK_Q4 && s_cgo[tid] - s_cgo[0] <= CHUNK_CIGAR &&
+                              s_sgo[tid] - s_sgo[0] <= CHUNK_SEGS;
+            if (fits) atomicMax(&s_misc[0], tid);
+        }
+        __syncthreads();
+        const uint32_t m = s_misc[0];
+        if (m == 0) {                       // a single read over the documented limits: host validation failed
+            if (tid == 0) atomicExch(err_flag, 1);
+            break;
+        }
+        const uint32_t q4_0 = s_q4[0], nq4 = s_q4[m] - q4_0;
+        const uint32_t cg_0 = s_cgo[0], ncg = s_cgo[m] - cg_0;
+        const uint32_t sg_0 = s_sgo[0], nsg = s_sgo[m] - sg_0;
+
+        // ---- 2. stage sequence, quality and CIGAR bytes: three bulk copies from 16-byte aligned
+        // addresses at or below the first byte needed; d_* is the offset of that byte in the buffer
+        const uint8_t* g_seq = sd.seq2 + q4_0;
+        const uint8_t* g_qual = sd.qual + (size_t)q4_0 * 4;
+        const uint8_t* g_cig = (const uint8_t*)(sd.cigar + cg_0);
+        const uint32_t d_seq = (uint32_t)((uintptr_t)g_seq & 15), d_qual = (uint32_t)((uintptr_t)g_qual & 15),
+                       d_cig = (uint32_t)((uintptr_t)g_cig & 15);
+        const uint32_t b_seq = (d_seq + nq4 + 15) & ~15u, b_qual = (d_qual + nq4 * 4 + 15) & ~15u,
+                       b_cig = (d_cig + ncg * 4 + 15) & ~15u;
+        if (tid == 0) {
+            fence_proxy_async();            // earlier generic-proxy accesses to these buffers are ordered before the copies
+            mbar_expect_tx(s_bar, b_seq + b_qual + b_cig);
+            if (b_seq)  tma_load_1d(s_seq, g_seq - d_seq, b_seq, s_bar);
+            if (b_qual) tma_load_1d(s_qual, g_qual - d_qual, b_qual, s_bar);
+            if (b_cig)  tma_load_1d(s_cig, g_cig - d_cig, b_cig, s_bar);
+        }
+        mbar_wait(s_bar, parity);
+        parity ^= 1;
+
+        // ---- 3a. CIGAR walk: one thread per read, one segment per M/=/X operation
+        if (tid < m) {
+            const uint32_t* cg = (const uint32_t*)(s_cig + d_cig) + (s_cgo[tid] - cg_0);
+            const uint32_t nops = s_cgo[tid + 1] - s_cgo[tid];
+            uint32_t k = s_sgo[tid] - sg_0;
+            const int32_t rpos = (int32_t)s_pos[tid];
+            int32_t x = rpos;
+            uint32_t y = d_qual + (s_q4[tid] - q4_0) * 4;        // byte address of the read's first base in s_qual
+            for (uint32_t o = 0; o < nops; ++o) {
+                const uint32_t w = cg[o], op = w & 0xf, len = w >> 4;
+                if (op == 0 || op == 7 || op == 8) {
+                    s_seg[k++] = make_uint4((uint32_t)x, len, y, (uint32_t)rpos);
+                    x += (int32_t)len; y += len;
+                } else if (op == 2 || op == 3) x += (int32_t)len;
+                else if (op == 1 || op == 4) y += len;
+            }
+            atomicMax(&s_misc[1], (uint32_t)(x - rpos));
+        }
+        // ---- 3b. (2-bit base, quality) -> code, in place over the quality bytes, 4 bases per step
+        {
+            uint32_t* q32 = (uint32_t*)(s_qual + d_qual);         // d_qual is a multiple of 4
+            const uint8_t* sq = s_seq + d_seq;
+            for (uint32_t g = tid; g < nq4; g += PILEUP_THREADS) {
+                const uint32_t q = q32[g];
+                const uint32_t b = sq[g];
+                uint32_t out = 0;
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t qb = (q >> (8 * j)) & 0xffu;
+                    uint32_t code = (b >> (2 * j)) & 3u;
+                    if (qb & 0x80u) code = 4u;
+                    if ((qb & 0x7fu) < 13u) code = 7u;
+                    out |= code << (8 * j);
+                }
+                q32[g] = out;
+            }
+        }
+        __syncthreads();
+
+        // ---- 4. gather. Segments are in read order, reads in position order: this warp only needs
+        // reads starting in (warp_lo - span, warp_lo + 32), located by counting with ballots.
+        {
+            const int64_t lo_key = (int64_t)warp_lo - (int64_t)s_misc[1];      // reads with pos <= lo_key cannot reach the warp
+            const int32_t hi_key = warp_lo + 32;
+            uint32_t r_first = 0, r_last = 0;
+            for (uint32_t base = 0; base < m; base += 32) {
+                const uint32_t i = base + lane;
+                const int32_t v = i < m ? (int32_t)s_pos[i] : 0x7fffffff;
+                r_first += __popc(__ballot_sync(0xffffffffu, (int64_t)v <= lo_key));
+                r_last  += __popc(__ballot_sync(0xffffffffu, v < hi_key));
+            }
+            const uint32_t j_lo = s_sgo[r_first] - sg_0, j_hi = s_sgo[r_last] - sg_0;
+            for (uint32_t j = j_lo; j < j_hi; ++j) {
+                const uint4 sg = s_seg[j];                        // same address in every lane: broadcast
+                const uint32_t idx = (uint32_t)(my_pos - (int32_t)sg.x);
+                if (idx < sg.y) {
+                    const uint32_t code = s_qual[sg.z + idx];
+                    acc += shl1_clamped(code * 16u);              // codes >= 4 shift out to 0
+                    acc_n += (code == 4u);
+                }
+            }
+        }
+        c0 += m;
+        __syncthreads();                    // everyone is done with the buffers before they are refilled
+    }
+
+    // ---- 5. flush: 8 B + 2 B per position, fully coalesced
+    const size_t o = (size_t)blockIdx.x * TILE + tid;
+    acgt[o] = acc;
+    ncnt[o] = (uint16_t)acc_n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// call: one CTA per tile, one thread per position. Sums the per-sample counts of the tile's items
+// and applies snpCall's tests (call_vC.cpp:545-601). Output: one flag byte per position
+// (low nibble: population mask, high nibble: individual mask, allele order A,C,G,T).
+// ------------------------------------------------------------------------------------------------
+// reference character -> channel of the base mpileup renders as '.'/',' (0..3 = A,C,G,T, 4 = N-like,
+// 5 = none: IUPAC ambiguity codes match no read base). Derived from SAMv1's nt16 coding, the table
+// mpileup's pileup_seq compares with (SURVEY.md Annex A.4).
+__device__ __forceinline__ uint32_t ref_channel(uint32_t c)
+{
+    switch (c) {
+        case 'A': case 'a': case '0': return 0;
+        case 'C': case 'c': case '1': return 1;
+        case 'G': case 'g': case '2': return 2;
+        case 'T': case 't': case '3': return 3;
+        case 'M': case 'm': case 'R': case 'r': case 'S': case 's': case 'V': case 'v': case 'W': case 'w':
+        case 'Y': case 'y': case 'H': case 'h': case 'K': case 'k': case 'D': case 'd': case 'B': case 'b':
+        case '=': return 5;
+        default: return 4;
+    }
+}
+
+__global__ void __launch_bounds__(TILE)
+call_kernel(const uint64_t* __restrict__ acgt, const uint16_t* __restrict__ ncnt, const uint32_t* __restrict__ tile_begin,
+            const uint8_t* __restrict__ ref, CallParamsDev prm, int text_mode, uint8_t* __restrict__ flags,
+            uint32_t* __restrict__ tile_hits)
+{
+    __shared__ uint32_t s_warp[33];
+    const uint32_t t = blockIdx.x, tid = threadIdx.x;
+    const uint32_t i0 = tile_begin[t], i1 = tile_begin[t + 1];
+    const size_t p = (size_t)t * TILE + tid;
+    const int32_t thr = prm.thr;
+    // any: bit a set when some sample has count[a] >= thr (samples without reads count 0, which only
+    // matters for the degenerate thr <= 0)
+    uint32_t sum[4] = {0, 0, 0, 0}, sum_n = 0, any = thr <= 0 ? 15u : 0u;
+    uint32_t i = i0;
+    for (; i + 4 <= i1; i += 4) {                              // 4 independent loads in flight per thread
+        uint64_t w[4]; uint32_t nn[4];
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) { w[u] = __ldg(acgt + (size_t)(i + u) * TILE + tid); nn[u] = __ldg(ncnt + (size_t)(i + u) * TILE + tid); }
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            #pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const uint32_t c = (uint32_t)(w[u] >> (16 * a)) & 0xffffu;
+                sum[a] += c;
+                any |= ((int32_t)c >= thr ? 1u : 0u) << a;
+            }
+            sum_n += nn[u];
+        }
+    }
+    for (; i < i1; ++i) {
+        const uint64_t w = __ldg(acgt + (size_t)i * TILE + tid);
+        #pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const uint32_t c = (uint32_t)(w >> (16 * a)) & 0xffffu;
+            sum[a] += c;
+            any |= ((int32_t)c >= thr ? 1u : 0u) << a;
+        }
+        sum_n += __ldg(ncnt + (size_t)i * TILE + tid);
+    }
+    uint32_t flag = 0;
+    const uint32_t rc = ref[p];
+    if (rc != 0 && i1 > i0) {
+        // text mode (counts parsed from mpileup text): letters are never the reference's own base and the
+        // fifth plane holds the '.'/',' matches, so nothing is masked (call_vC.cpp:545,550,583-584)
+        const uint32_t ch = text_mode ? 6u : ref_channel(rc);
+        const int64_t cov = (int64_t)sum[0] + sum[1] + sum[2] + sum[3] + ((ch == 4 || text_mode) ? sum_n : 0);
+        int64_t nonref = 0;
+        #pragma unroll
+        for (int a = 0; a < 4; ++a) if ((uint32_t)a != ch) nonref += sum[a];
+        // call_vC.cpp:547-552. (int) casts mirror the reference's `int cov`.
+        if (cov >= prm.min_cov && nonref >= thr) {
+            const double lim = __dmul_rn((double)cov, prm.frac);       // cov*calling_min_fraction, no FMA contraction
+            #pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                // call_vC.cpp:580: the allele is skipped only when the reference character is its lower-case letter
+                const uint32_t lower = a == 0 ? 'a' : a == 1 ? 'c' : a == 2 ? 'g' : 't';
+                if (rc == lower) continue;
+                const int64_t n = ((uint32_t)a == ch) ? 0 : (int64_t)sum[a];
+                if (n >= thr && (double)n >= lim) flag |= 1u << a;                       // population variant
+                else {
+                    const bool indiv = ((uint32_t)a == ch) ? (0 >= thr) : ((any >> a) & 1u);
+                    if (indiv) flag |= 16u << a;                                         // individual variant
+                }
+            }
+        }
+    }
+    flags[p] = (uint8_t)flag;
+    uint32_t total;
+    block_rank(flag != 0, s_warp, total);
+    if (tid == 0) tile_hits[t] = total;
+}
+
+// ordered compaction of the flagged positions: tile_hits holds exclusive offsets on entry
+__global__ void __launch_bounds__(TILE)
+compact_kernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ tile_hits, uint32_t* __restrict__ hit_pos,
+               uint8_t* __restrict__ hit_pop, uint8_t* __restrict__ hit_ind)
+{
+    __shared__ uint32_t s_warp[33];
+    const uint32_t t = blockIdx.x, tid = threadIdx.x;
+    const size_t p = (size_t)t * TILE + tid;
+    const uint32_t f = flags[p];
+    uint32_t total;
+    const uint32_t r = block_rank(f != 0, s_warp, total);
+    if (f) {
+        const uint32_t slot = tile_hits[t] + r;
+        hit_pos[slot] = (uint32_t)p;
+        hit_pop[slot] = (uint8_t)(f & 15u);
+        hit_ind[slot] = (uint8_t)(f >> 4);
+    }
+}
+
+// per hit: per-sample coverage and allele counts (zero for samples without an item on the tile)
+// plus population totals. One CTA of 128 threads per hit; outputs were zero-filled by the host side.
+__global__ void __launch_bounds__(128)
+gather_kernel(const uint64_t* __restrict__ acgt, const uint16_t* __restrict__ ncnt, const Item* __restrict__ items,
+              const uint32_t* __restrict__ tile_begin, const uint8_t* __restrict__ ref, const uint32_t* __restrict__ hit_pos,
+              uint32_t n_samples, int text_mode, uint16_t* __restrict__ cov, uint16_t* __restrict__ allele,
+              uint32_t* __restrict__ total)
+{
+    __shared__ uint32_t s_tot[5];
+    const uint32_t h = blockIdx.x, tid = threadIdx.x;
+    const uint32_t p = hit_pos[h];
+    const uint32_t t = p / TILE, off = p % TILE;
+    const uint32_t ch = text_mode ? 6u : ref_channel(ref[p]);
+    if (tid < 5) s_tot[tid] = 0;
+    __syncthreads();
+    uint32_t tc = 0, ta[4] = {0, 0, 0, 0};
+    for (uint32_t i = tile_begin[t] + tid; i < tile_begin[t + 1]; i += blockDim.x) {
+        const uint32_t s = items[i].sample;
+        const uint64_t w = __ldg(acgt + (size_t)i * TILE + off);
+        const uint32_t nn = __ldg(ncnt + (size_t)i * TILE + off);
+        uint32_t c[4], cv = (ch == 4 || text_mode) ? nn : 0;
+        #pragma unroll
+        for (int a = 0; a < 4; ++a) { c[a] = (uint32_t)(w >> (16 * a)) & 0xffffu; cv += c[a]; if ((uint32_t)a == ch) c[a] = 0; }
+        cov[(size_t)h * n_samples + s] = (uint16_t)cv;
+        #pragma unroll
+        for (int a = 0; a < 4; ++a) { allele[((size_t)h * 4 + a) * n_samples + s] = (uint16_t)c[a]; ta[a] += c[a]; }
+        tc += cv;
+    }
+    atomicAdd(&s_tot[0], tc);
+    #pragma unroll
+    for (int a = 0; a < 4; ++a) atomicAdd(&s_tot[1 + a], ta[a]);
+    __syncthreads();
+    if (tid < 5) total[(size_t)h * 5 + tid] = s_tot[tid];
+}
+
+// inspection hook: expand one sample's counts for a position range into [n][5] u16
+__global__ void counts_kernel(const uint64_t* __restrict__ acgt, const uint16_t* __restrict__ ncnt, const Item* __restrict__ items,
+                              const uint32_t* __restrict__ tile_begin, uint32_t sample, uint32_t first, uint32_t n,
+                              uint16_t* __restrict__ out)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t p = first + k, t = p / TILE, off = p % TILE;
+    uint16_t v[5] = {0, 0, 0, 0, 0};
+    for (uint32_t i = tile_begin[t]; i < tile_begin[t + 1]; ++i) {
+        if (items[i].sample != sample) continue;
+        const uint64_t w = acgt[(size_t)i * TILE + off];
+        for (int a = 0; a < 4; ++a) v[a] = (uint16_t)(w >> (16 * a));
+        v[4] = ncnt[(size_t)i * TILE + off];
+        break;
+    }
+    for (int a = 0; a < 5; ++a) out[(size_t)k * 5 + a] = v[a];
+}
+
+// ------------------------------------------------------------------------------------------------
+// coverage (qaCompute.cpp:530-552 scatter, :142-165 prefix sum + histogram).
+// Contigs that have reads are laid out in a "coverage coordinate" space, each starting at a multiple
+// of COV_CHUNK. A block [beg,end) contributes +1 at beg and -1 at end like the reference's
+// difference array, but every chunk it enters gets its own +1 at the chunk's first index, so each
+// chunk is prefix-summed independently by one CTA: no carries between CTAs, one pass over HBM.
+// ------------------------------------------------------------------------------------------------
+constexpr int COV_CHUNK = 4096;
+constexpr int COV_THREADS = 1024;
+constexpr int COV_MAX_BINS = 1024;
+
+__global__ void __launch_bounds__(256)
+cov_scatter_kernel(const uint32_t* __restrict__ beg, const uint32_t* __restrict__ end, const uint64_t* __restrict__ blk_off,
+                   const uint32_t* __restrict__ contig_chunk0, uint32_t n_contigs, uint64_t n_blocks, int32_t* __restrict__ diff)
+{
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_blocks) return;
+    uint32_t lo = 0, hi = n_contigs;                       // contig of this block: blk_off[lo] <= g < blk_off[lo+1]
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (__ldg(blk_off + mid) <= g) lo = mid; else hi = mid; }
+    const uint32_t b = __ldg(beg + g), e = __ldg(end + g);
+    if (e <= b) return;
+    int32_t* d = diff + (size_t)__ldg(contig_chunk0 + lo) * COV_CHUNK;
+    for (uint32_t c = b / COV_CHUNK; c <= (e - 1) / COV_CHUNK; ++c) {
+        const uint32_t c0 = c * COV_CHUNK;
+        atomicAdd(d + (b > c0 ? b : c0), 1);
+        if (e < c0 + COV_CHUNK) atomicAdd(d + e, -1);
+    }
+}
+
+__global__ void __launch_bounds__(COV_THREADS)
+cov_scan_kernel(const int32_t* __restrict__ diff, const uint32_t* __restrict__ chunk_contig, const uint32_t* __restrict__ contig_chunk0,
+                const uint32_t* __restrict__ contig_len, uint32_t max_cov, unsigned long long* __restrict__ cov_sum,
+                unsigned long long* __restrict__ hist /*[n_contigs][max_cov+1]*/)
+{
+    __shared__ int32_t s_warp[32];
+    __shared__ uint32_t s_hist[COV_MAX_BINS];
+    __shared__ unsigned long long s_sum;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t k = chunk_contig[blockIdx.x];
+    const uint32_t first = (blockIdx.x - contig_chunk0[k]) * COV_CHUNK;        // contig coordinate of the chunk's first index
+    const uint32_t len = contig_len[k];
+    for (uint32_t i = tid; i <= max_cov; i += COV_THREADS) s_hist[i] = 0;
+    if (tid == 0) s_sum = 0;
+    const int4 v = reinterpret_cast<const int4*>(diff + (size_t)blockIdx.x * COV_CHUNK)[tid];
+    int32_t c0 = v.x, c1 = c0 + v.y, c2 = c1 + v.z, c3 = c2 + v.w;
+    int32_t incl = c3;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int32_t w = s_warp[lane], wi = w;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int32_t o = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += o; }
+        s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    const int32_t base = s_warp[warp] + incl - c3;
+    int32_t cv[4] = {base + c0, base + c1, base + c2, base + c3};
+    unsigned long long local = 0;
+    #pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t p = first + tid * 4 + j;
+        const bool valid = p < len;
+        // negative coverage cannot occur for blocks that satisfy the ABI contract (beg < end)
+        uint32_t bin = cv[j] < 0 ? 0u : ((uint32_t)cv[j] > max_cov ? max_cov : (uint32_t)cv[j]);
+        if (!valid) bin = 0xffffffffu;
+        else local += (unsigned long long)(cv[j] < 0 ? 0 : cv[j]);
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[bin], (uint32_t)__popc(peers));
+    }
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) local += __shfl_down_sync(0xffffffffu, local, d);
+    if (lane == 0 && local) atomicAdd(&s_sum, local);
+    __syncthreads();
+    for (uint32_t i = tid; i <= max_cov; i += COV_THREADS)
+        if (s_hist[i]) atomicAdd(hist + (size_t)k * (max_cov + 1) + i, (unsigned long long)s_hist[i]);
+    if (tid == 0 && s_sum) atomicAdd(cov_sum + k, s_sum);
+}
+
+}  // namespace msnv_gpu

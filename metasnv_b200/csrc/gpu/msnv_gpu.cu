@@ -1,0 +1,525 @@
+// msnv_gpu.cu -- implementation of the C ABI in include/msnv.h (libmsnv_gpu.so).
+// Host-side orchestration only: device memory, the stream, kernel launches, result copies.
+// Kernels are in kernels.cuh. There is no CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace msnv_gpu;
+
+struct msnv_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // ---- shard state
+    bool open = false, quals_saved = false, has_run = false;
+    uint32_t S = 0, P = 0, n_tiles = 0;
+    std::vector<SampleDev> h_samples;
+    std::vector<uint32_t> pair_base;           // [S+1]
+    std::vector<void*> sample_allocs;
+    uint64_t n_reads = 0, n_bases = 0;
+    SampleDev* d_samples = nullptr;
+    uint32_t* d_pair_base = nullptr;
+    uint8_t* d_ref = nullptr;
+
+    // ---- work buffers (grown on demand, kept across shards)
+    Item* d_items = nullptr;        uint64_t cap_items = 0;
+    uint64_t* d_acgt = nullptr;     uint16_t* d_ncnt = nullptr;
+    uint32_t* d_tile_begin = nullptr; uint32_t* d_tile_hits = nullptr; uint8_t* d_flags = nullptr; uint64_t cap_tiles = 0;
+    uint32_t* d_block_sums = nullptr; uint64_t cap_blocks = 0;
+    uint32_t* d_scalar = nullptr;   int* d_err = nullptr;
+    uint32_t n_items = 0;
+
+    // ---- hits (device + pinned host mirrors)
+    uint64_t cap_hits = 0, cap_hits_S = 0;
+    uint32_t *d_hit_pos = nullptr, *d_hit_total = nullptr; uint8_t *d_hit_pop = nullptr, *d_hit_ind = nullptr;
+    uint16_t *d_hit_cov = nullptr, *d_hit_allele = nullptr;
+    uint32_t *h_hit_pos = nullptr, *h_hit_total = nullptr; uint8_t *h_hit_pop = nullptr, *h_hit_ind = nullptr;
+    uint16_t *h_hit_cov = nullptr, *h_hit_allele = nullptr;
+    uint32_t* h_scalar = nullptr;   // pinned, 4 words
+
+    cudaEvent_t ev[8] = {};
+    msnv_timings tm = {};
+};
+
+namespace {
+
+int fail(msnv_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(ctx, MSNV_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+int grow(msnv_ctx* ctx, T*& p, uint64_t n)
+{
+    if (p) { CU(cudaFree(p)); p = nullptr; }
+    CU(cudaMalloc((void**)&p, (size_t)(n ? n : 1) * sizeof(T)));
+    return 0;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void free_samples(msnv_ctx* ctx)
+{
+    for (void* p : ctx->sample_allocs) cudaFree(p);
+    ctx->sample_allocs.clear();
+}
+
+int ensure_hits(msnv_ctx* ctx, uint64_t n_hits)
+{
+    const uint64_t S = ctx->S;
+    if (n_hits <= ctx->cap_hits && n_hits * S <= ctx->cap_hits_S) return 0;
+    uint64_t cap = n_hits + n_hits / 4 + 1024;
+    cudaFree(ctx->d_hit_pos); cudaFree(ctx->d_hit_total); cudaFree(ctx->d_hit_pop); cudaFree(ctx->d_hit_ind);
+    cudaFree(ctx->d_hit_cov); cudaFree(ctx->d_hit_allele);
+    cudaFreeHost(ctx->h_hit_pos); cudaFreeHost(ctx->h_hit_total); cudaFreeHost(ctx->h_hit_pop); cudaFreeHost(ctx->h_hit_ind);
+    cudaFreeHost(ctx->h_hit_cov); cudaFreeHost(ctx->h_hit_allele);
+    ctx->d_hit_pos = ctx->d_hit_total = nullptr; ctx->d_hit_pop = ctx->d_hit_ind = nullptr; ctx->d_hit_cov = ctx->d_hit_allele = nullptr;
+    ctx->h_hit_pos = ctx->h_hit_total = nullptr; ctx->h_hit_pop = ctx->h_hit_ind = nullptr; ctx->h_hit_cov = ctx->h_hit_allele = nullptr;
+    ctx->cap_hits = ctx->cap_hits_S = 0;
+    CU(cudaMalloc((void**)&ctx->d_hit_pos, cap * 4));       CU(cudaMallocHost((void**)&ctx->h_hit_pos, cap * 4));
+    CU(cudaMalloc((void**)&ctx->d_hit_total, cap * 20));    CU(cudaMallocHost((void**)&ctx->h_hit_total, cap * 20));
+    CU(cudaMalloc((void**)&ctx->d_hit_pop, cap));           CU(cudaMallocHost((void**)&ctx->h_hit_pop, cap));
+    CU(cudaMalloc((void**)&ctx->d_hit_ind, cap));           CU(cudaMallocHost((void**)&ctx->h_hit_ind, cap));
+    CU(cudaMalloc((void**)&ctx->d_hit_cov, cap * S * 2));   CU(cudaMallocHost((void**)&ctx->h_hit_cov, cap * S * 2));
+    CU(cudaMalloc((void**)&ctx->d_hit_allele, cap * S * 8)); CU(cudaMallocHost((void**)&ctx->h_hit_allele, cap * S * 8));
+    ctx->cap_hits = cap; ctx->cap_hits_S = cap * S;
+    return 0;
+}
+
+}  // namespace
+
+
+// call -> ordered compaction -> per-hit gather -> copy back; shared by the BAM path and the text path.
+// Records events 4..6 (the caller records event 3 once the count tiles are final).
+static int run_call_phase(msnv_ctx* ctx, const msnv_call_params* prm, int text_mode, msnv_hits* hits, uint32_t& launches)
+{
+    cudaStream_t st = ctx->stream;
+    const uint32_t S = ctx->S, n_tiles = ctx->n_tiles;
+    CallParamsDev cp{prm->min_coverage, prm->calling_threshold, prm->min_fraction};
+    call_kernel<<<n_tiles, TILE, 0, st>>>(ctx->d_acgt, ctx->d_ncnt, ctx->d_tile_begin, ctx->d_ref, cp, text_mode, ctx->d_flags, ctx->d_tile_hits);
+    ++launches;
+    CU(cudaEventRecord(ctx->ev[4], st));
+
+    // ---- ordered compaction of the called positions
+    scan_kernel<<<1, 1024, 0, st>>>(ctx->d_tile_hits, n_tiles, ctx->d_scalar + 1);
+    ++launches;
+    CU(cudaMemcpyAsync(ctx->h_scalar + 1, ctx->d_scalar + 1, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_scalar + 2, ctx->d_err, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (ctx->h_scalar[2]) return fail(ctx, MSNV_E_LIMIT, "a read exceeds MSNV_MAX_READ_BASES / MSNV_MAX_READ_CIGAR");
+    const uint32_t n_hits = ctx->h_scalar[1];
+    if (ensure_hits(ctx, n_hits)) return MSNV_E_CUDA;
+    if (n_hits) {
+        compact_kernel<<<n_tiles, TILE, 0, st>>>(ctx->d_flags, ctx->d_tile_hits, ctx->d_hit_pos, ctx->d_hit_pop, ctx->d_hit_ind);
+        ++launches;
+    }
+    CU(cudaEventRecord(ctx->ev[5], st));
+
+    // ---- per-hit, per-sample numbers for the formatter
+    if (n_hits) {
+        CU(cudaMemsetAsync(ctx->d_hit_cov, 0, (size_t)n_hits * S * 2, st));
+        CU(cudaMemsetAsync(ctx->d_hit_allele, 0, (size_t)n_hits * S * 8, st));
+        gather_kernel<<<n_hits, 128, 0, st>>>(ctx->d_acgt, ctx->d_ncnt, ctx->d_items, ctx->d_tile_begin, ctx->d_ref, ctx->d_hit_pos, S,
+                                               text_mode, ctx->d_hit_cov, ctx->d_hit_allele, ctx->d_hit_total);
+        ++launches;
+    }
+    CU(cudaEventRecord(ctx->ev[6], st));
+    if (n_hits) {
+        CU(cudaMemcpyAsync(ctx->h_hit_pos, ctx->d_hit_pos, (size_t)n_hits * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_hit_total, ctx->d_hit_total, (size_t)n_hits * 20, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_hit_pop, ctx->d_hit_pop, n_hits, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_hit_ind, ctx->d_hit_ind, n_hits, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_hit_cov, ctx->d_hit_cov, (size_t)n_hits * S * 2, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_hit_allele, ctx->d_hit_allele, (size_t)n_hits * S * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    hits->n_hits = n_hits;
+    hits->n_samples = S;
+    hits->pos = ctx->h_hit_pos; hits->pop_mask = ctx->h_hit_pop; hits->ind_mask = ctx->h_hit_ind;
+    hits->cov = ctx->h_hit_cov; hits->allele = ctx->h_hit_allele; hits->total = ctx->h_hit_total;
+    return MSNV_OK;
+}
+
+static int ensure_items(msnv_ctx* ctx, uint64_t n_items)
+{
+    if (n_items <= ctx->cap_items) return 0;
+    const uint64_t cap = n_items + n_items / 8 + 64;
+    if (grow(ctx, ctx->d_items, cap)) return MSNV_E_CUDA;
+    cudaFree(ctx->d_acgt); cudaFree(ctx->d_ncnt); ctx->d_acgt = nullptr; ctx->d_ncnt = nullptr; ctx->cap_items = 0;
+    cudaError_t e1 = cudaMalloc((void**)&ctx->d_acgt, cap * TILE * 8);
+    cudaError_t e2 = cudaMalloc((void**)&ctx->d_ncnt, cap * TILE * 2);
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+        return fail(ctx, MSNV_E_NOMEM, "count tiles for %llu (sample,tile) items do not fit device memory", (unsigned long long)n_items);
+    ctx->cap_items = cap;
+    return 0;
+}
+
+extern "C" {
+
+int msnv_abi_version(void) { return MSNV_ABI_VERSION; }
+
+int msnv_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int msnv_create(int device, msnv_ctx** out)
+{
+    if (!out) return MSNV_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return MSNV_E_CUDA;
+    msnv_ctx* ctx = new msnv_ctx();
+    ctx->device = device;
+    *out = ctx;                                   // returned even on failure so the caller can read the error
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->ev) CU(cudaEventCreate(&e));
+    CU(cudaMalloc((void**)&ctx->d_scalar, 16));
+    CU(cudaMalloc((void**)&ctx->d_err, 4));
+    CU(cudaMallocHost((void**)&ctx->h_scalar, 16));
+    CU(cudaFuncSetAttribute(pileup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PILEUP_SMEM));
+    return MSNV_OK;
+}
+
+void msnv_destroy(msnv_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_samples(ctx);
+    cudaFree(ctx->d_samples); cudaFree(ctx->d_pair_base); cudaFree(ctx->d_ref);
+    cudaFree(ctx->d_items); cudaFree(ctx->d_acgt); cudaFree(ctx->d_ncnt);
+    cudaFree(ctx->d_tile_begin); cudaFree(ctx->d_tile_hits); cudaFree(ctx->d_flags); cudaFree(ctx->d_block_sums);
+    cudaFree(ctx->d_scalar); cudaFree(ctx->d_err);
+    cudaFree(ctx->d_hit_pos); cudaFree(ctx->d_hit_total); cudaFree(ctx->d_hit_pop); cudaFree(ctx->d_hit_ind);
+    cudaFree(ctx->d_hit_cov); cudaFree(ctx->d_hit_allele);
+    cudaFreeHost(ctx->h_hit_pos); cudaFreeHost(ctx->h_hit_total); cudaFreeHost(ctx->h_hit_pop); cudaFreeHost(ctx->h_hit_ind);
+    cudaFreeHost(ctx->h_hit_cov); cudaFreeHost(ctx->h_hit_allele); cudaFreeHost(ctx->h_scalar);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* msnv_last_error(const msnv_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
+
+int msnv_shard_begin(msnv_ctx* ctx, uint32_t n_samples, uint32_t n_positions, const uint8_t* ref)
+{
+    if (!ctx) return MSNV_E_ARG;
+    if (!ref || n_samples == 0 || n_positions == 0 || n_positions % TILE != 0)
+        return fail(ctx, MSNV_E_ARG, "msnv_shard_begin: n_samples and n_positions must be positive, n_positions a multiple of %d", TILE);
+    if (n_samples > 65535) return fail(ctx, MSNV_E_LIMIT, "msnv_shard_begin: at most 65535 samples (32-bit population sums)");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_samples(ctx);
+    ctx->S = n_samples; ctx->P = n_positions; ctx->n_tiles = n_positions / TILE;
+    ctx->h_samples.assign(n_samples, SampleDev{});
+    ctx->pair_base.assign(n_samples + 1, 0);
+    ctx->n_reads = ctx->n_bases = 0;
+    ctx->quals_saved = ctx->has_run = false;
+    cudaFree(ctx->d_samples); cudaFree(ctx->d_pair_base); cudaFree(ctx->d_ref);
+    ctx->d_samples = nullptr; ctx->d_pair_base = nullptr; ctx->d_ref = nullptr;
+    CU(cudaMalloc((void**)&ctx->d_samples, sizeof(SampleDev) * n_samples));
+    CU(cudaMalloc((void**)&ctx->d_pair_base, 4 * ((size_t)n_samples + 1)));
+    CU(cudaMalloc((void**)&ctx->d_ref, n_positions));
+    CU(cudaMemcpyAsync(ctx->d_ref, ref, n_positions, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->n_tiles + 1 > ctx->cap_tiles) {
+        if (grow(ctx, ctx->d_tile_begin, (uint64_t)ctx->n_tiles + 1)) return MSNV_E_CUDA;
+        if (grow(ctx, ctx->d_tile_hits, (uint64_t)ctx->n_tiles + 1)) return MSNV_E_CUDA;
+        if (grow(ctx, ctx->d_flags, (uint64_t)n_positions)) return MSNV_E_CUDA;
+        ctx->cap_tiles = (uint64_t)ctx->n_tiles + 1;
+    }
+    ctx->open = true;
+    return MSNV_OK;
+}
+
+int msnv_shard_add_sample(msnv_ctx* ctx, uint32_t sample, const msnv_sample_reads* r)
+{
+    if (!ctx || !r) return MSNV_E_ARG;
+    if (!ctx->open) return fail(ctx, MSNV_E_STATE, "msnv_shard_add_sample: no open shard");
+    if (sample >= ctx->S) return fail(ctx, MSNV_E_ARG, "msnv_shard_add_sample: sample %u out of range", sample);
+    if (ctx->h_samples[sample].n_reads) return fail(ctx, MSNV_E_STATE, "msnv_shard_add_sample: sample %u added twice", sample);
+    if (r->n_reads == 0) return MSNV_OK;
+    if (r->max_span > 8u * MSNV_MAX_READ_BASES) return fail(ctx, MSNV_E_LIMIT, "sample %u: reference span %u exceeds the limit", sample, r->max_span);
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = r->n_reads, n1 = n + 1;
+    const size_t n_cig = r->cig_off[n], n_q4 = r->q4_off[n], np = r->n_pairs;
+    // backup offsets of the overlapping pairs (bytes): qualities of both mates, 4-byte groups
+    std::vector<uint32_t> bk(np + 1, 0);
+    for (size_t i = 0; i < np; ++i) {
+        const uint32_t b = r->pair_b[i];
+        if (b >= n || r->mate[b] < 0 || (uint32_t)r->mate[b] >= b)
+            return fail(ctx, MSNV_E_ARG, "sample %u: pair_b[%zu] does not name a read with an earlier mate", sample, i);
+        const uint32_t a = (uint32_t)r->mate[b];
+        bk[i + 1] = bk[i] + 4u * ((r->q4_off[a + 1] - r->q4_off[a]) + (r->q4_off[b + 1] - r->q4_off[b]));
+    }
+    // one allocation per sample, sub-arrays 256-byte aligned, 32 spare bytes behind the byte arrays
+    // because the pileup kernel's bulk copies read whole 16-byte units
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes + 32, 256); return o; };
+    const size_t o_pos = take(n * 4), o_cgo = take(n1 * 4), o_sgo = take(n1 * 4), o_q4 = take(n1 * 4), o_mate = take(n * 4),
+                 o_pb = take(np * 4), o_pbk = take((np + 1) * 4), o_cig = take(n_cig * 4), o_seq = take(n_q4), o_qual = take(n_q4 * 4),
+                 o_bk = take(bk[np]);
+    uint8_t* base = nullptr;
+    cudaError_t e = cudaMalloc((void**)&base, off);
+    if (e != cudaSuccess) return fail(ctx, MSNV_E_NOMEM, "sample %u: cudaMalloc(%zu) failed: %s", sample, off, cudaGetErrorString(e));
+    ctx->sample_allocs.push_back(base);
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(base + o_pos, r->pos, n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_cgo, r->cig_off, n1 * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_sgo, r->seg_off, n1 * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_q4, r->q4_off, n1 * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_mate, r->mate, n * 4, cudaMemcpyHostToDevice, st));
+    if (np) CU(cudaMemcpyAsync(base + o_pb, r->pair_b, np * 4, cudaMemcpyHostToDevice, st));
+    // bk is a temporary: copy it synchronously with respect to the host (pageable source)
+    CU(cudaMemcpyAsync(base + o_pbk, bk.data(), (np + 1) * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    if (n_cig) CU(cudaMemcpyAsync(base + o_cig, r->cigar, n_cig * 4, cudaMemcpyHostToDevice, st));
+    if (n_q4) {
+        CU(cudaMemcpyAsync(base + o_seq, r->seq2, n_q4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(base + o_qual, r->qual, n_q4 * 4, cudaMemcpyHostToDevice, st));
+    }
+    SampleDev& d = ctx->h_samples[sample];
+    d.pos = (const int32_t*)(base + o_pos);     d.cig_off = (const uint32_t*)(base + o_cgo);
+    d.seg_off = (const uint32_t*)(base + o_sgo); d.q4_off = (const uint32_t*)(base + o_q4);
+    d.mate = (const int32_t*)(base + o_mate);   d.cigar = (const uint32_t*)(base + o_cig);
+    d.seq2 = base + o_seq;                      d.qual = base + o_qual;
+    d.pair_b = (const uint32_t*)(base + o_pb);  d.pair_bk = (const uint32_t*)(base + o_pbk);
+    d.backup = base + o_bk;
+    d.n_reads = r->n_reads; d.max_span = r->max_span ? r->max_span : 1; d.n_pairs = r->n_pairs; d.pad_ = 0;
+    ctx->n_reads += n; ctx->n_bases += 4ull * n_q4;
+    return MSNV_OK;
+}
+
+int msnv_shard_mask_position(msnv_ctx* ctx, uint32_t pos)
+{
+    if (!ctx) return MSNV_E_ARG;
+    if (!ctx->open || pos >= ctx->P) return fail(ctx, MSNV_E_ARG, "msnv_shard_mask_position: position out of range");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemsetAsync(ctx->d_ref + pos, 0, 1, ctx->stream));
+    return MSNV_OK;
+}
+
+int msnv_shard_sync(msnv_ctx* ctx)
+{
+    if (!ctx) return MSNV_E_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MSNV_OK;
+}
+
+int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
+{
+    if (!ctx || !prm || !hits) return MSNV_E_ARG;
+    if (!ctx->open) return fail(ctx, MSNV_E_STATE, "msnv_shard_run: no open shard");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t S = ctx->S, n_tiles = ctx->n_tiles;
+    uint32_t launches = 0;
+    memset(hits, 0, sizeof *hits);
+    hits->n_samples = S;
+
+    uint64_t pairs_total = 0;
+    for (uint32_t s = 0; s < S; ++s) { ctx->pair_base[s] = (uint32_t)pairs_total; pairs_total += ctx->h_samples[s].n_pairs; }
+    if (pairs_total > 0xffffffffull) return fail(ctx, MSNV_E_LIMIT, "more than 2^32 overlapping pairs in one shard");
+    ctx->pair_base[S] = (uint32_t)pairs_total;
+    CU(cudaMemcpyAsync(ctx->d_samples, ctx->h_samples.data(), sizeof(SampleDev) * S, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_pair_base, ctx->pair_base.data(), 4 * ((size_t)S + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(ctx->d_err, 0, 4, st));
+
+    CU(cudaEventRecord(ctx->ev[0], st));
+    // ---- index
+    const uint64_t n_pairs_idx = (uint64_t)n_tiles * S;
+    const uint64_t n_blocks = (n_pairs_idx + 255) / 256;
+    if (n_blocks > 0x7fffffffull) return fail(ctx, MSNV_E_LIMIT, "shard too large: %u tiles x %u samples", n_tiles, S);
+    if (n_blocks > ctx->cap_blocks) { if (grow(ctx, ctx->d_block_sums, n_blocks)) return MSNV_E_CUDA; ctx->cap_blocks = n_blocks; }
+    index_kernel<false><<<(unsigned)n_blocks, 256, 0, st>>>(ctx->d_samples, S, n_tiles, ctx->d_block_sums, nullptr, nullptr);
+    scan_kernel<<<1, 1024, 0, st>>>(ctx->d_block_sums, (uint32_t)n_blocks, ctx->d_scalar);
+    launches += 2;
+    CU(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint32_t n_items = ctx->h_scalar[0];
+    ctx->n_items = n_items;
+    if (int rc = ensure_items(ctx, n_items)) return rc;
+    index_kernel<true><<<(unsigned)n_blocks, 256, 0, st>>>(ctx->d_samples, S, n_tiles, ctx->d_block_sums, ctx->d_items, ctx->d_tile_begin);
+    ++launches;
+    CU(cudaMemcpyAsync(ctx->d_tile_begin + n_tiles, ctx->d_scalar, 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaEventRecord(ctx->ev[1], st));
+
+    // ---- mate-overlap quality correction (restores pristine qualities first on repeated runs)
+    if (pairs_total) {
+        const unsigned g = (unsigned)((pairs_total + 127) / 128);
+        if (!ctx->quals_saved) overlap_kernel<0><<<g, 128, 0, st>>>(ctx->d_samples, ctx->d_pair_base, S, pairs_total);
+        else                   overlap_kernel<1><<<g, 128, 0, st>>>(ctx->d_samples, ctx->d_pair_base, S, pairs_total);
+        overlap_kernel<2><<<g, 128, 0, st>>>(ctx->d_samples, ctx->d_pair_base, S, pairs_total);
+        ctx->quals_saved = true;
+        launches += 2;
+    }
+    CU(cudaEventRecord(ctx->ev[2], st));
+
+    // ---- pileup
+    if (n_items) {
+        pileup_kernel<<<n_items, PILEUP_THREADS, PILEUP_SMEM, st>>>(ctx->d_samples, ctx->d_items, n_items, ctx->d_acgt, ctx->d_ncnt, ctx->d_err);
+        ++launches;
+    }
+    CU(cudaEventRecord(ctx->ev[3], st));
+
+    // ---- call, compaction, gather, copy back
+    if (int rc = run_call_phase(ctx, prm, 0, hits, launches)) return rc;
+
+    msnv_timings& tm = ctx->tm;
+    cudaEventElapsedTime(&tm.ms_index, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&tm.ms_overlap, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&tm.ms_pileup, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&tm.ms_call, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&tm.ms_compact, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&tm.ms_gather, ctx->ev[5], ctx->ev[6]);
+    cudaEventElapsedTime(&tm.ms_total, ctx->ev[0], ctx->ev[6]);
+    tm.n_items = n_items; tm.n_reads = ctx->n_reads; tm.n_bases = ctx->n_bases; tm.n_tiles = n_tiles;
+    tm.kernel_launches = launches;
+    ctx->has_run = true;
+    return MSNV_OK;
+}
+
+int msnv_call_counts(msnv_ctx* ctx, uint32_t n_samples, uint32_t n_positions, const uint8_t* ref, const uint64_t* acgt,
+                     const uint16_t* matches, const msnv_call_params* prm, msnv_hits* hits)
+{
+    if (!ctx || !ref || !acgt || !matches || !prm || !hits) return MSNV_E_ARG;
+    if (int rc = msnv_shard_begin(ctx, n_samples, n_positions, ref)) return rc;
+    cudaStream_t st = ctx->stream;
+    const uint64_t n_items = (uint64_t)ctx->n_tiles * n_samples;
+    if (n_items > 0xffffffffull) return fail(ctx, MSNV_E_LIMIT, "msnv_call_counts: batch too large");
+    if (int rc = ensure_items(ctx, n_items)) return rc;
+    memset(hits, 0, sizeof *hits);
+    uint32_t launches = 0;
+    CU(cudaMemsetAsync(ctx->d_err, 0, 4, st));
+    CU(cudaEventRecord(ctx->ev[0], st));
+    CU(cudaMemcpyAsync(ctx->d_acgt, acgt, n_items * TILE * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_ncnt, matches, n_items * TILE * 2, cudaMemcpyHostToDevice, st));
+    dense_items_kernel<<<(unsigned)((n_items + 1 + 255) / 256), 256, 0, st>>>(n_samples, ctx->n_tiles, ctx->d_items, ctx->d_tile_begin);
+    ++launches;
+    ctx->n_items = (uint32_t)n_items;
+    for (int k = 1; k <= 3; ++k) CU(cudaEventRecord(ctx->ev[k], st));
+    if (int rc = run_call_phase(ctx, prm, 1, hits, launches)) return rc;
+    msnv_timings& tm = ctx->tm;
+    tm = msnv_timings{};
+    cudaEventElapsedTime(&tm.ms_call, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&tm.ms_compact, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&tm.ms_gather, ctx->ev[5], ctx->ev[6]);
+    cudaEventElapsedTime(&tm.ms_total, ctx->ev[0], ctx->ev[6]);
+    tm.n_items = n_items; tm.n_tiles = ctx->n_tiles; tm.kernel_launches = launches;
+    ctx->has_run = true;
+    return MSNV_OK;
+}
+
+int msnv_shard_counts(msnv_ctx* ctx, uint32_t sample, uint32_t first, uint32_t n, uint16_t* out)
+{
+    if (!ctx || !out) return MSNV_E_ARG;
+    if (!ctx->has_run) return fail(ctx, MSNV_E_STATE, "msnv_shard_counts: run the shard first");
+    if (sample >= ctx->S || (uint64_t)first + n > ctx->P) return fail(ctx, MSNV_E_ARG, "msnv_shard_counts: range out of bounds");
+    if (n == 0) return MSNV_OK;
+    CU(cudaSetDevice(ctx->device));
+    uint16_t* d = nullptr;
+    CU(cudaMalloc((void**)&d, (size_t)n * 10));
+    counts_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_acgt, ctx->d_ncnt, ctx->d_items, ctx->d_tile_begin, sample, first, n, d);
+    cudaError_t e = cudaMemcpyAsync(out, d, (size_t)n * 10, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, MSNV_E_CUDA, "msnv_shard_counts: %s", cudaGetErrorString(e));
+    return MSNV_OK;
+}
+
+int msnv_get_timings(const msnv_ctx* ctx, msnv_timings* out)
+{
+    if (!ctx || !out) return MSNV_E_ARG;
+    *out = ctx->tm;
+    return MSNV_OK;
+}
+
+int msnv_cov_run(msnv_ctx* ctx, const msnv_cov_blocks* b, uint32_t max_cov, uint64_t* cov_sum, uint64_t* hist)
+{
+    if (!ctx || !b || !cov_sum || !hist) return MSNV_E_ARG;
+    if (max_cov + 1 > (uint32_t)COV_MAX_BINS) return fail(ctx, MSNV_E_LIMIT, "msnv_cov_run: max_cov must be below %d", COV_MAX_BINS);
+    const uint32_t K = b->n_contigs;
+    if (K == 0) return MSNV_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t n_blocks = b->blk_off[K];
+    std::vector<uint32_t> chunk0(K + 1), chunk_contig;
+    uint64_t n_chunks = 0;
+    for (uint32_t k = 0; k < K; ++k) {
+        chunk0[k] = (uint32_t)n_chunks;
+        const uint64_t c = ((uint64_t)b->contig_len[k] + COV_CHUNK - 1) / COV_CHUNK;
+        n_chunks += c ? c : 1;
+        if (n_chunks > 0x7fffffffull) return fail(ctx, MSNV_E_LIMIT, "msnv_cov_run: too many positions in one call");
+    }
+    chunk0[K] = (uint32_t)n_chunks;
+    chunk_contig.resize(n_chunks);
+    for (uint32_t k = 0; k < K; ++k) for (uint32_t c = chunk0[k]; c < chunk0[k + 1]; ++c) chunk_contig[c] = k;
+
+    int32_t* d_diff = nullptr; uint32_t *d_beg = nullptr, *d_end = nullptr, *d_chunk0 = nullptr, *d_cc = nullptr, *d_len = nullptr;
+    uint64_t* d_off = nullptr; unsigned long long *d_sum = nullptr, *d_hist = nullptr;
+    int rc = MSNV_OK;
+    auto cleanup = [&]() {
+        cudaFree(d_diff); cudaFree(d_beg); cudaFree(d_end); cudaFree(d_chunk0); cudaFree(d_cc); cudaFree(d_len);
+        cudaFree(d_off); cudaFree(d_sum); cudaFree(d_hist);
+    };
+#define CUC(call)                                                                                                   \
+    do {                                                                                                            \
+        cudaError_t e_ = (call);                                                                                    \
+        if (e_ != cudaSuccess) { rc = fail(ctx, MSNV_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); cleanup(); return rc; } \
+    } while (0)
+    const size_t hist_n = (size_t)K * (max_cov + 1);
+    CUC(cudaMalloc((void**)&d_diff, n_chunks * COV_CHUNK * 4));
+    CUC(cudaMalloc((void**)&d_beg, (n_blocks ? n_blocks : 1) * 4));
+    CUC(cudaMalloc((void**)&d_end, (n_blocks ? n_blocks : 1) * 4));
+    CUC(cudaMalloc((void**)&d_chunk0, ((size_t)K + 1) * 4));
+    CUC(cudaMalloc((void**)&d_cc, n_chunks * 4));
+    CUC(cudaMalloc((void**)&d_len, (size_t)K * 4));
+    CUC(cudaMalloc((void**)&d_off, ((size_t)K + 1) * 8));
+    CUC(cudaMalloc((void**)&d_sum, (size_t)K * 8));
+    CUC(cudaMalloc((void**)&d_hist, hist_n * 8));
+    CUC(cudaMemsetAsync(d_diff, 0, n_chunks * COV_CHUNK * 4, st));
+    CUC(cudaMemsetAsync(d_sum, 0, (size_t)K * 8, st));
+    CUC(cudaMemsetAsync(d_hist, 0, hist_n * 8, st));
+    if (n_blocks) {
+        CUC(cudaMemcpyAsync(d_beg, b->beg, n_blocks * 4, cudaMemcpyHostToDevice, st));
+        CUC(cudaMemcpyAsync(d_end, b->end, n_blocks * 4, cudaMemcpyHostToDevice, st));
+    }
+    CUC(cudaMemcpyAsync(d_chunk0, chunk0.data(), ((size_t)K + 1) * 4, cudaMemcpyHostToDevice, st));
+    CUC(cudaMemcpyAsync(d_cc, chunk_contig.data(), n_chunks * 4, cudaMemcpyHostToDevice, st));
+    CUC(cudaMemcpyAsync(d_len, b->contig_len, (size_t)K * 4, cudaMemcpyHostToDevice, st));
+    CUC(cudaMemcpyAsync(d_off, b->blk_off, ((size_t)K + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_blocks)
+        cov_scatter_kernel<<<(unsigned)((n_blocks + 255) / 256), 256, 0, st>>>(d_beg, d_end, d_off, d_chunk0, K, n_blocks, d_diff);
+    cov_scan_kernel<<<(unsigned)n_chunks, COV_THREADS, 0, st>>>(d_diff, d_cc, d_chunk0, d_len, max_cov, d_sum, d_hist);
+    CUC(cudaMemcpyAsync(cov_sum, d_sum, (size_t)K * 8, cudaMemcpyDeviceToHost, st));
+    CUC(cudaMemcpyAsync(hist, d_hist, hist_n * 8, cudaMemcpyDeviceToHost, st));
+    CUC(cudaStreamSynchronize(st));
+    CUC(cudaGetLastError());
+#undef CUC
+    cleanup();
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,293 @@
+// pileup_input.cc -- see pileup_input.hpp.
+#include "pileup_input.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <queue>
+
+namespace msnv {
+
+// ------------------------------------------------------------------ FASTA / BED
+bool Fasta::load(const std::string& path, std::string& err)
+{
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) { err = "cannot open reference " + path; return false; }
+    char* line = nullptr; size_t cap = 0; ssize_t n;
+    int cur = -1;
+    while ((n = getline(&line, &cap, f)) > 0) {
+        while (n > 0 && (line[n - 1] == '\n' || line[n - 1] == '\r')) line[--n] = 0;
+        if (line[0] == '>') {
+            char* e = line + 1;
+            while (*e && !isspace((unsigned char)*e)) ++e;
+            std::string nm(line + 1, e);
+            cur = (int)names.size();
+            names.push_back(nm); seqs.emplace_back();
+            index.emplace(nm, cur);                 // keeps the first record of a duplicated name
+        } else if (cur >= 0) {
+            seqs[cur].append(line, (size_t)n);
+        }
+    }
+    free(line);
+    fclose(f);
+    return true;
+}
+
+bool Bed::load(const std::string& path, std::string& err)
+{
+    std::ifstream in(path);
+    if (!in) { err = "cannot open " + path; return false; }
+    std::string line;
+    while (std::getline(in, line)) {
+        if (line.empty() || line[0] == '#') continue;
+        char name[4096]; long long a = 0, b = 0;
+        int k = sscanf(line.c_str(), "%4095s %lld %lld", name, &a, &b);
+        if (k < 2) continue;
+        Iv iv;
+        if (k == 2) { iv.beg = a - 1; iv.end = a; } else { iv.beg = a; iv.end = b; }
+        by_name[name].push_back(iv);
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------ shard layout
+bool ShardLayout::build(const BamHeader& hdr, const Bed* b, std::string& err)
+{
+    ctgs.clear(); bed.clear();
+    slot_of_tid.assign(hdr.names.size(), -1);
+    has_bed = b != nullptr;
+    uint64_t off = 0;
+    for (size_t t = 0; t < hdr.names.size(); ++t) {
+        std::vector<Bed::Iv> ivs;
+        if (b) {
+            auto it = b->by_name.find(hdr.names[t]);
+            if (it == b->by_name.end()) continue;
+            ivs = it->second;
+            std::sort(ivs.begin(), ivs.end(), [](const Bed::Iv& x, const Bed::Iv& y) { return x.beg < y.beg; });
+            std::vector<Bed::Iv> merged;
+            for (const Bed::Iv& iv : ivs) {
+                if (iv.end <= iv.beg) continue;
+                if (!merged.empty() && iv.beg <= merged.back().end) merged.back().end = std::max(merged.back().end, iv.end);
+                else merged.push_back(iv);
+            }
+            ivs.swap(merged);
+            if (ivs.empty()) continue;
+        } else {
+            ivs.push_back(Bed::Iv{0, (int64_t)hdr.lens[t]});
+        }
+        Ctg c; c.tid = (int)t; c.len = hdr.lens[t]; c.offset = (uint32_t)off;
+        slot_of_tid[t] = (int)ctgs.size();
+        ctgs.push_back(c); bed.push_back(ivs);
+        off += ((uint64_t)hdr.lens[t] + MSNV_TILE - 1) / MSNV_TILE * MSNV_TILE;
+        if (hdr.lens[t] == 0) off += MSNV_TILE;
+        if (off > 0x7ff00000ull) { err = "shard larger than 2^31 positions; use more splits"; return false; }
+    }
+    n_positions = (uint32_t)off;
+    return true;
+}
+
+bool ShardLayout::overlaps(int slot, int64_t beg, int64_t end) const
+{
+    for (const Bed::Iv& iv : bed[slot]) if (iv.beg < end && beg < iv.end) return true;
+    return false;
+}
+
+int64_t ShardLayout::first_inside(int slot, int64_t beg, int64_t end) const
+{
+    for (const Bed::Iv& iv : bed[slot]) {                 // sorted, disjoint
+        if (iv.end <= beg) continue;
+        int64_t p = std::max(beg, iv.beg);
+        return p < end ? p : -1;
+    }
+    return -1;
+}
+
+std::vector<uint8_t> shard_reference(const ShardLayout& layout, const BamHeader& hdr, const Fasta& fa)
+{
+    std::vector<uint8_t> ref(layout.n_positions, 0);
+    for (size_t k = 0; k < layout.ctgs.size(); ++k) {
+        const ShardLayout::Ctg& c = layout.ctgs[k];
+        int fi = fa.find(hdr.names[c.tid]);
+        const std::string* seq = fi >= 0 ? &fa.seqs[fi] : nullptr;
+        for (const Bed::Iv& iv : layout.bed[k]) {
+            int64_t e = std::min<int64_t>(iv.end, c.len);
+            for (int64_t p = std::max<int64_t>(iv.beg, 0); p < e; ++p)
+                ref[c.offset + p] = (seq && p < (int64_t)seq->size()) ? (uint8_t)(*seq)[p] : (uint8_t)'N';
+        }
+    }
+    return ref;
+}
+
+// ------------------------------------------------------------------ SoA helpers
+msnv_sample_reads SampleReads::view() const
+{
+    msnv_sample_reads v;
+    memset(&v, 0, sizeof v);
+    v.n_reads = (uint32_t)pos.size();
+    v.max_span = max_span;
+    v.n_pairs = (uint32_t)pair_b.size();
+    v.pos = pos.data(); v.cig_off = cig_off.data(); v.seg_off = seg_off.data(); v.q4_off = q4_off.data();
+    v.mate = mate.data(); v.pair_b = pair_b.data(); v.cigar = cigar.data(); v.seq2 = seq2.data(); v.qual = qual.data();
+    return v;
+}
+
+size_t SampleReads::bytes() const
+{
+    return pos.size() * 4 + cig_off.size() * 4 + seg_off.size() * 4 + q4_off.size() * 4 + mate.size() * 4 + pair_b.size() * 4 +
+           cigar.size() * 4 + seq2.size() + qual.size();
+}
+
+namespace {
+
+// BAM 4-bit base code -> 2-bit code (A,C,G,T) or 4 for everything else
+const uint8_t kCode4to2[16] = {4, 0, 1, 4, 2, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4};
+
+inline uint64_t hash_qname(const char* s)
+{
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (; *s; ++s) { h ^= (unsigned char)*s; h *= 0x100000001b3ull; }
+    h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
+    return h;
+}
+
+struct Buffered { int32_t end; uint64_t qh; };
+struct ByEnd { bool operator()(const Buffered& a, const Buffered& b) const { return a.end > b.end; } };
+struct Stored { uint32_t index; int32_t end; };
+
+}  // namespace
+
+bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& layout, const std::vector<int64_t>& ref_len_of_tid,
+                              int inflate_threads, SampleReads& out, DecodeStats& st, std::string& err)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    BamReader rd;
+    if (!rd.open(bam_path, inflate_threads)) { err = rd.error(); return false; }
+    const int MAXCNT = 8000;                         // samtools mpileup -d default (>= 1.9), per file
+
+    // state of htslib's pileup iterator that the depth cap and the overlap hash depend on
+    int cur_tid = -1; int32_t last_pos = -1;
+    std::priority_queue<Buffered, std::vector<Buffered>, ByEnd> buffered;    // reads the iterator still holds
+    std::unordered_map<uint64_t, Stored> olap;                               // qname -> earlier mate waiting for its partner
+    bool warned_overhang = false, warned_iupac = false;
+
+    BamRecord r;
+    int rc;
+    while ((rc = rd.next(r)) > 0) {
+        ++st.records;
+        const BamCore& c = r.core;
+        // ---- mplp_func (SURVEY.md Annex A.1)
+        if (c.tid < 0 || (c.flag & FLAG_UNMAP)) continue;
+        if (c.flag & (FLAG_UNMAP | FLAG_SECONDARY | FLAG_QCFAIL | FLAG_DUP)) continue;
+        if ((size_t)c.tid >= layout.slot_of_tid.size()) continue;
+        int32_t rlen = 0; uint32_t n_seg = 0;
+        for (int i = 0; i < c.n_cigar; ++i) {
+            const uint32_t w = r.cigar_at(i), op = w & 0xf;
+            if (op == CIG_M || op == CIG_EQ || op == CIG_X) { rlen += (int32_t)(w >> 4); ++n_seg; }
+            else if (op == CIG_D || op == CIG_N) rlen += (int32_t)(w >> 4);
+        }
+        const int slot = layout.slot_of_tid[c.tid];
+        const int32_t end = c.pos + rlen;
+        if (layout.has_bed) {
+            if (slot < 0 || !layout.overlaps(slot, c.pos, c.pos + (rlen ? rlen : 1))) continue;
+        }
+        if (ref_len_of_tid[c.tid] >= 0 && ref_len_of_tid[c.tid] <= c.pos) continue;
+        if ((c.flag & FLAG_PAIRED) && !(c.flag & FLAG_PROPER_PAIR)) continue;
+        if (slot < 0) continue;
+        // ---- outside the contract of this implementation (documented in DESIGN.md)
+        if (rlen == 0) continue;                                   // no reference base: builds no column
+        if (c.pos < 0 || (uint32_t)end > layout.ctgs[slot].len) {
+            if (!warned_overhang) { fprintf(stderr, "[msnv] %s: read %s extends beyond its contig; such reads are skipped\n", bam_path.c_str(), r.qname); warned_overhang = true; }
+            continue;
+        }
+        if (c.l_seq > MSNV_MAX_READ_BASES || c.n_cigar > MSNV_MAX_READ_CIGAR) {
+            err = bam_path + ": read " + r.qname + " exceeds the supported length (" + std::to_string(MSNV_MAX_READ_BASES) +
+                  " bases / " + std::to_string(MSNV_MAX_READ_CIGAR) + " CIGAR operations)";
+            return false;
+        }
+
+        // ---- bam_plp_push: expiry of buffered reads, depth cap (Annex A.3)
+        if (c.tid != cur_tid) {
+            while (!buffered.empty()) buffered.pop();
+            olap.clear();
+            cur_tid = c.tid; last_pos = -1;
+        } else {
+            // columns < last_pos have been produced; they released every read ending at or before last_pos-1
+            while (!buffered.empty() && buffered.top().end <= last_pos - 1) {
+                olap.erase(buffered.top().qh);
+                buffered.pop();
+            }
+        }
+        const uint64_t qh = hash_qname(r.qname);
+        if (c.pos == last_pos && (int)buffered.size() + 1 > MAXCNT) {
+            olap.erase(qh);
+            ++st.dropped_by_cap;
+            continue;
+        }
+        last_pos = c.pos;
+        buffered.push(Buffered{end, qh});
+        if (buffered.size() > st.max_buffered) st.max_buffered = (uint32_t)buffered.size();
+
+        const uint32_t idx = (uint32_t)out.pos.size();
+        // ---- overlap_push (Annex A.2)
+        int32_t mate_idx = -1;
+        if (!(c.flag & FLAG_MUNMAP) && (c.flag & FLAG_PROPER_PAIR) &&
+            !((c.mtid >= 0 && c.tid != c.mtid) ||
+              ((c.tlen < 0 ? -(int64_t)c.tlen : (int64_t)c.tlen) >= 2 * (int64_t)c.l_seq && c.mpos >= end))) {
+            auto it = olap.find(qh);
+            if (it == olap.end()) {
+                if (c.mpos >= c.pos) olap.emplace(qh, Stored{idx, end});
+            } else {
+                if (it->second.end > c.pos) mate_idx = (int32_t)it->second.index;   // else: no common reference base
+                olap.erase(it);
+            }
+        }
+
+        // ---- append to the structure of arrays
+        const ShardLayout::Ctg& ctg = layout.ctgs[slot];
+        out.pos.push_back((int32_t)(ctg.offset + (uint32_t)c.pos));
+        out.mate.push_back(mate_idx);
+        if (mate_idx >= 0) { out.pair_b.push_back(idx); ++st.pairs; }
+        for (int i = 0; i < c.n_cigar; ++i) out.cigar.push_back(r.cigar_at(i));
+        out.cig_off.push_back((uint32_t)out.cigar.size());
+        out.seg_off.push_back(out.seg_off.back() + n_seg);
+        const size_t l = (size_t)c.l_seq, g = (l + 3) / 4, s0 = out.seq2.size(), q0 = out.qual.size();
+        out.seq2.resize(s0 + g, 0);
+        out.qual.resize(q0 + 4 * g, 0);
+        uint8_t* sq = out.seq2.data() + s0; uint8_t* ql = out.qual.data() + q0;
+        for (size_t i = 0; i < l; ++i) {
+            const uint8_t c4 = (r.seq[i >> 1] >> ((~i & 1) << 2)) & 0xf;
+            const uint8_t c2 = kCode4to2[c4];
+            uint8_t q = r.qual[i]; if (q > 127) q = 127;
+            if (c2 == 4) {
+                q |= 0x80;
+                if (c4 != 15 && !warned_iupac) {
+                    fprintf(stderr, "[msnv] %s: read %s has a base other than A/C/G/T/N; such bases are not counted\n", bam_path.c_str(), r.qname);
+                    warned_iupac = true;
+                }
+            } else sq[i >> 2] |= (uint8_t)(c2 << ((i & 3) * 2));
+            ql[i] = q;
+        }
+        if (out.q4_off.back() + g > 0xffffffffull) { err = bam_path + ": more than 2^34 bases in one shard of one sample"; return false; }
+        out.q4_off.push_back((uint32_t)(out.q4_off.back() + g));
+        if ((uint32_t)rlen > out.max_span) out.max_span = (uint32_t)rlen;
+        if (st.first_column < 0) {
+            int64_t p = layout.first_inside(slot, c.pos, end);
+            if (p >= 0) st.first_column = (int64_t)ctg.offset + p;
+        }
+        ++st.accepted;
+        for (int i = 0; i < c.n_cigar; ++i) {
+            const uint32_t w = r.cigar_at(i), op = w & 0xf;
+            if (op == CIG_M || op == CIG_EQ || op == CIG_X) st.aligned_bases += w >> 4;
+        }
+    }
+    if (rc < 0) { err = bam_path + ": " + rd.error(); return false; }
+    if (st.max_buffered + 64u > 65535u) { err = bam_path + ": pileup depth above 65535 is not supported"; return false; }
+    st.compressed_bytes = rd.compressed_size();
+    st.inflate_seconds = rd.inflate_seconds();
+    st.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return true;
+}
+
+}  // namespace msnv

@@ -1,0 +1,82 @@
+// pileup_input.hpp -- BAM -> structure-of-arrays read batches for the GPU pileup (include/msnv.h),
+// including everything `samtools mpileup` decides per read before it builds columns: the default
+// flag / orphan / BED / reference-length filters, the per-file depth cap and the mate-overlap
+// pairing (SURVEY.md Annex A.1-A.3; the reference reaches this code through metaSNV.py:160-165).
+// These are sequential, order-dependent per-file rules, so they run in the decoding thread; the
+// per-base work (overlap quality correction, CIGAR walk, counting) is done on the device.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../../include/msnv.h"
+#include "bam.hpp"
+
+namespace msnv {
+
+// Reference sequences by name (name = first word of the FASTA header, as faidx does).
+struct Fasta {
+    std::vector<std::string> names;
+    std::vector<std::string> seqs;
+    std::unordered_map<std::string, int> index;      // first record of a name wins
+    bool load(const std::string& path, std::string& err);
+    int find(const std::string& name) const { auto it = index.find(name); return it == index.end() ? -1 : it->second; }
+};
+
+// -l file: 3 columns = BED (0-based half open), 2 columns = 1-based position.
+struct Bed {
+    struct Iv { int64_t beg, end; };
+    std::unordered_map<std::string, std::vector<Iv>> by_name;
+    bool load(const std::string& path, std::string& err);
+};
+
+// Contigs of one shard in shard coordinates (each contig starts at a multiple of MSNV_TILE).
+struct ShardLayout {
+    struct Ctg { int tid; uint32_t len; uint32_t offset; };
+    std::vector<Ctg> ctgs;                    // ascending tid
+    std::vector<int> slot_of_tid;             // tid -> index into ctgs, or -1
+    std::vector<std::vector<Bed::Iv>> bed;    // per ctg: sorted intervals the shard covers ([0,len) without -l)
+    uint32_t n_positions = 0;
+    bool has_bed = false;
+    // All contigs of the header (no -l), or those named in the BED.
+    bool build(const BamHeader& hdr, const Bed* bed_or_null, std::string& err);
+    bool overlaps(int slot, int64_t beg, int64_t end) const;
+    // smallest position in [beg,end) covered by the shard's intervals, or -1
+    int64_t first_inside(int slot, int64_t beg, int64_t end) const;
+};
+
+// Growable host-side arrays of one sample, in the layout of msnv_sample_reads.
+struct SampleReads {
+    std::vector<int32_t>  pos;
+    std::vector<uint32_t> cig_off{0}, seg_off{0}, q4_off{0};
+    std::vector<int32_t>  mate;
+    std::vector<uint32_t> pair_b, cigar;
+    std::vector<uint8_t>  seq2, qual;
+    uint32_t max_span = 0;
+    msnv_sample_reads view() const;
+    size_t bytes() const;
+};
+
+struct DecodeStats {
+    uint64_t records = 0, accepted = 0, dropped_by_cap = 0, aligned_bases = 0, pairs = 0;
+    uint64_t compressed_bytes = 0;
+    double seconds = 0, inflate_seconds = 0;
+    // first pileup column this sample would emit (shard coordinate), or -1
+    int64_t first_column = -1;
+    uint32_t max_buffered = 0;
+};
+
+// Decode one BAM into `out` for the contigs of `layout`. `ref_len_of_tid[tid]` is the FASTA length
+// of the contig or -1 when the FASTA lacks it (mpileup then keeps every read). The BAM's header
+// is not compared with the shard's: like mpileup, the first file's header rules.
+bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& layout,
+                              const std::vector<int64_t>& ref_len_of_tid, int inflate_threads, SampleReads& out,
+                              DecodeStats& st, std::string& err);
+
+// Reference characters of the shard, one byte per shard coordinate: the FASTA character where the
+// contig has one and the position is inside the shard's intervals, 'N' inside the intervals but
+// beyond the FASTA, 0 elsewhere (padding, outside -l).
+std::vector<uint8_t> shard_reference(const ShardLayout& layout, const BamHeader& hdr, const Fasta& fa);
+
+}  // namespace msnv
