@@ -117,6 +117,11 @@ int         msnv_create(int device, msnv_ctx** out);
 void        msnv_destroy(msnv_ctx* ctx);
 const char* msnv_last_error(const msnv_ctx* ctx);
 
+/* Page-locked host memory for the batches handed to msnv_shard_add_sample() (cudaHostAlloc / cudaFreeHost);
+ * usable from any thread once a context exists. */
+void*       msnv_pinned_alloc(size_t bytes);
+void        msnv_pinned_free(void* p);
+
 /* ---- pileup + call (replaces `samtools mpileup ... | snpCall`, metaSNV.py:160-176) ---- */
 
 /* Start a shard of n_positions shard coordinates (a multiple of MSNV_TILE) seen by n_samples
@@ -146,6 +151,35 @@ int msnv_get_timings(const msnv_ctx* ctx, msnv_timings* out);
  * hit positions index the batch's lines. Replaces any open shard. */
 int msnv_call_counts(msnv_ctx* ctx, uint32_t n_samples, uint32_t n_positions, const uint8_t* ref, const uint64_t* acgt,
                      const uint16_t* matches, const msnv_call_params* params, msnv_hits* hits);
+
+/* ---- synthetic shards (benchmark / test input, no reference counterpart) ----
+ * Fills a shard on the device from the stateless read model of csrc/host/synth_model.h -- the same
+ * model `msnv_synth` writes BAM files from -- so the full BASELINE.json shapes can be benchmarked
+ * without materialising hundreds of GB of BAM. Equivalent to msnv_shard_begin() plus one
+ * msnv_shard_add_sample() per sample with what decoding those BAMs yields (only reads the mpileup
+ * filters accept; the model's filtered "junk" records do not exist here). */
+typedef struct {
+    uint64_t seed;
+    uint32_t n_samples, read_len, depth_x100, presence_ppm, paired_pct, site_ppm, err_ppm, nbase_ppm, refn_ppm;
+    uint32_t indel_pct_x10, clip_pct_x10, mapq0_pct_x10;
+    uint32_t n_contigs;
+    const uint32_t* contig_len;      /* [n_contigs], in header (tid) order */
+    const uint32_t* contig_genome;   /* [n_contigs] genome index of each contig */
+    uint32_t        n_genomes;
+    const uint32_t* genome_n_sub;    /* [n_genomes] number of subspecies clusters */
+} msnv_synth_desc;
+/* first_column (optional): shard coordinate of the first pileup column, i.e. what the caller would
+ * pass to msnv_shard_mask_position(); -1 when the shard has no reads. */
+int msnv_shard_synth(msnv_ctx* ctx, const msnv_synth_desc* desc, int64_t* first_column);
+
+/* Copy one sample of the open shard back to host arrays sized from *sizes (as returned by
+ * msnv_shard_sample_sizes): used to stage pinned host buffers for end-to-end timing. */
+typedef struct { uint32_t n_reads, n_pairs, max_span, reserved; uint64_t n_cigar, n_q4; } msnv_sample_sizes;
+int msnv_shard_sample_sizes(msnv_ctx* ctx, uint32_t sample, msnv_sample_sizes* sizes);
+int msnv_shard_export_sample(msnv_ctx* ctx, uint32_t sample, int32_t* pos, uint32_t* cig_off, uint32_t* seg_off, uint32_t* q4_off,
+                             int32_t* mate, uint32_t* pair_b, uint32_t* cigar, uint8_t* seq2, uint8_t* qual);
+/* Copy the shard's reference characters (n_positions bytes) back to the host. */
+int msnv_shard_export_ref(msnv_ctx* ctx, uint8_t* ref);
 
 /* ---- coverage (replaces the reductions of qaCompute, metaSNV.py:63-65) ---- */
 

@@ -180,6 +180,23 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     if (msnv_shard_run(ctx, &prm, &hits) != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); msnv_destroy(ctx); return 1; }
     const double t_run1 = now_s();
 
+    // test hook: per-sample, per-position A,C,G,T,N counts of the whole shard (msnv_shard_counts)
+    if (const char* dump = getenv("MSNV_DUMP_COUNTS")) {
+        FILE* f = fopen(dump, "wb");
+        FILE* g = fopen((std::string(dump) + ".layout").c_str(), "w");
+        if (f && g) {
+            std::vector<uint16_t> buf((size_t)layout.n_positions * 5);
+            for (uint32_t s = 0; s < S; ++s) {
+                if (msnv_shard_counts(ctx, s, 0, layout.n_positions, buf.data()) != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); break; }
+                fwrite(buf.data(), 2, buf.size(), f);
+            }
+            fprintf(g, "%u\t%u\t%lld\n", S, layout.n_positions, (long long)first_col);
+            for (const auto& c : layout.ctgs) fprintf(g, "%s\t%u\t%u\n", hdr.names[c.tid].c_str(), c.offset, c.len);
+        }
+        if (f) fclose(f);
+        if (g) fclose(g);
+    }
+
     HitWriter w;
     w.pop_out = stdout; w.indiv_out = indiv; w.ann = ann.active() ? &ann : nullptr;
     std::vector<HitWriter::Contig> ctgs;

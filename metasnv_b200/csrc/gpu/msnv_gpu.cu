@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "synth_kernels.cuh"
 
 using namespace msnv_gpu;
 
@@ -24,6 +25,7 @@ struct msnv_ctx {
     std::vector<SampleDev> h_samples;
     std::vector<uint32_t> pair_base;           // [S+1]
     std::vector<void*> sample_allocs;
+    std::vector<msnv_sample_sizes> sizes;      // [S]
     uint64_t n_reads = 0, n_bases = 0;
     SampleDev* d_samples = nullptr;
     uint32_t* d_pair_base = nullptr;
@@ -221,6 +223,15 @@ void msnv_destroy(msnv_ctx* ctx)
     delete ctx;
 }
 
+void* msnv_pinned_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void msnv_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
 const char* msnv_last_error(const msnv_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
 
 int msnv_shard_begin(msnv_ctx* ctx, uint32_t n_samples, uint32_t n_positions, const uint8_t* ref)
@@ -235,6 +246,7 @@ int msnv_shard_begin(msnv_ctx* ctx, uint32_t n_samples, uint32_t n_positions, co
     ctx->S = n_samples; ctx->P = n_positions; ctx->n_tiles = n_positions / TILE;
     ctx->h_samples.assign(n_samples, SampleDev{});
     ctx->pair_base.assign(n_samples + 1, 0);
+    ctx->sizes.assign(n_samples, msnv_sample_sizes{});
     ctx->n_reads = ctx->n_bases = 0;
     ctx->quals_saved = ctx->has_run = false;
     cudaFree(ctx->d_samples); cudaFree(ctx->d_pair_base); cudaFree(ctx->d_ref);
@@ -308,6 +320,7 @@ int msnv_shard_add_sample(msnv_ctx* ctx, uint32_t sample, const msnv_sample_read
     d.backup = base + o_bk;
     d.n_reads = r->n_reads; d.max_span = r->max_span ? r->max_span : 1; d.n_pairs = r->n_pairs; d.pad_ = 0;
     ctx->n_reads += n; ctx->n_bases += 4ull * n_q4;
+    ctx->sizes[sample] = msnv_sample_sizes{r->n_reads, r->n_pairs, d.max_span, 0, (uint64_t)n_cig, (uint64_t)n_q4};
     return MSNV_OK;
 }
 
@@ -429,6 +442,170 @@ int msnv_call_counts(msnv_ctx* ctx, uint32_t n_samples, uint32_t n_positions, co
     cudaEventElapsedTime(&tm.ms_total, ctx->ev[0], ctx->ev[6]);
     tm.n_items = n_items; tm.n_tiles = ctx->n_tiles; tm.kernel_launches = launches;
     ctx->has_run = true;
+    return MSNV_OK;
+}
+
+int msnv_shard_synth(msnv_ctx* ctx, const msnv_synth_desc* d, int64_t* first_column)
+{
+    if (!ctx || !d || !d->contig_len || !d->contig_genome || !d->genome_n_sub) return MSNV_E_ARG;
+    if (d->n_samples == 0 || d->n_contigs == 0 || d->read_len < 20 || d->read_len > 1000)
+        return fail(ctx, MSNV_E_ARG, "msnv_shard_synth: bad description");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    msnv::synth::Model m;
+    m.seed = d->seed; m.n_samples = (int32_t)d->n_samples; m.read_len = (int32_t)d->read_len; m.depth_x100 = d->depth_x100;
+    m.presence_ppm = d->presence_ppm; m.paired_pct = d->paired_pct; m.site_ppm = d->site_ppm; m.err_ppm = d->err_ppm;
+    m.nbase_ppm = d->nbase_ppm; m.refn_ppm = d->refn_ppm; m.indel_pct_x10 = d->indel_pct_x10; m.clip_pct_x10 = d->clip_pct_x10;
+    m.mapq0_pct_x10 = d->mapq0_pct_x10;
+    const uint32_t K = d->n_contigs, S = d->n_samples, L = d->read_len, q4 = (L + 3) / 4;
+    std::vector<uint32_t> off(K + 1);
+    uint64_t P = 0;
+    for (uint32_t k = 0; k < K; ++k) {
+        off[k] = (uint32_t)P;
+        P += ((uint64_t)d->contig_len[k] + TILE - 1) / TILE * TILE + (d->contig_len[k] == 0 ? TILE : 0);
+        if (P > 0x7ff00000ull) return fail(ctx, MSNV_E_LIMIT, "msnv_shard_synth: shard larger than 2^31 positions");
+    }
+    off[K] = (uint32_t)P;
+    // reference: generate on the device, begin the shard around it
+    std::vector<uint8_t> dummy(1, 'N');
+    {
+        // msnv_shard_begin wants a host reference; give it a zero page and overwrite on the device
+        std::vector<uint8_t> zero((size_t)P, 0);
+        if (int rc = msnv_shard_begin(ctx, S, (uint32_t)P, zero.data())) return rc;
+        CU(cudaStreamSynchronize(st));
+    }
+    uint32_t *d_off = nullptr, *d_len = nullptr;
+    CU(cudaMalloc((void**)&d_off, ((size_t)K + 1) * 4));
+    CU(cudaMalloc((void**)&d_len, (size_t)K * 4));
+    CU(cudaMemcpyAsync(d_off, off.data(), ((size_t)K + 1) * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_len, d->contig_len, (size_t)K * 4, cudaMemcpyHostToDevice, st));
+    synth_ref_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(m, d_off, d_len, K, (uint32_t)P, ctx->d_ref);
+    CU(cudaStreamSynchronize(st));
+    cudaFree(d_off); cudaFree(d_len);
+
+    int64_t first_col = -1;
+    std::vector<SynthSampleCtg> blocks;
+    std::vector<uint32_t> frag0;
+    for (uint32_t s = 0; s < S; ++s) {
+        const bool paired = msnv::synth::sample_paired(m, (int)s);
+        const int32_t D = paired ? msnv::synth::sample_mate_offset(m, (int)s) : 0;
+        const bool overlap = paired && D < (int32_t)L;
+        const uint32_t span = msnv::synth::frag_span(m, paired, D);
+        blocks.clear(); frag0.assign(1, 0);
+        uint64_t n_reads = 0, n_pairs = 0;
+        for (uint32_t k = 0; k < K; ++k) {
+            const uint32_t g = d->contig_genome[k];
+            if (g >= d->n_genomes) return fail(ctx, MSNV_E_ARG, "msnv_shard_synth: contig_genome out of range");
+            if (!msnv::synth::sample_has_genome(m, (int)s, (int)g) || d->contig_len[k] <= span) continue;
+            const uint32_t nf = msnv::synth::n_fragments(m, d->contig_len[k], paired);
+            if (!nf) continue;
+            SynthSampleCtg b{k, d->contig_len[k], off[k], g, d->genome_n_sub[g], nf, (uint32_t)n_reads, (uint32_t)n_pairs};
+            blocks.push_back(b);
+            frag0.push_back(frag0.back() + nf);
+            n_reads += (uint64_t)nf * (paired ? 2 : 1);
+            if (overlap) n_pairs += nf;
+            if (n_reads > 0x7fffffffull) return fail(ctx, MSNV_E_LIMIT, "msnv_shard_synth: more than 2^31 reads in one sample");
+        }
+        if (blocks.empty()) continue;
+        {   // first pileup column of this sample: first fragment of its first block
+            const SynthSampleCtg& b = blocks[0];
+            const int64_t c = (int64_t)b.offset + msnv::synth::frag_start(m, (int)s, b.ctg, b.len, span, b.n_frag, 0);
+            if (first_col < 0 || c < first_col) first_col = c;
+        }
+        const size_t n = (size_t)n_reads, n1 = n + 1, np = (size_t)n_pairs, nb = blocks.size(), nft = frag0.back();
+        // ---- phase 1: per-read metadata
+        size_t o = 0;
+        auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes + 32, 256); return r; };
+        const size_t o_pos = take(n * 4), o_cgo = take(n1 * 4), o_sgo = take(n1 * 4), o_q4 = take(n1 * 4), o_mate = take(n * 4),
+                     o_pb = take(np * 4), o_pbk = take((np + 1) * 4);
+        uint8_t* meta = nullptr;
+        if (cudaMalloc((void**)&meta, o) != cudaSuccess) return fail(ctx, MSNV_E_NOMEM, "msnv_shard_synth: out of device memory (sample %u)", s);
+        ctx->sample_allocs.push_back(meta);
+        SynthSampleCtg* d_blocks = nullptr; uint32_t *d_frag0 = nullptr, *d_nops = nullptr, *d_nsegs = nullptr, *d_for = nullptr;
+        CU(cudaMalloc((void**)&d_blocks, nb * sizeof(SynthSampleCtg)));
+        CU(cudaMalloc((void**)&d_frag0, (nb + 1) * 4));
+        CU(cudaMalloc((void**)&d_nops, n * 4));
+        CU(cudaMalloc((void**)&d_nsegs, n * 4));
+        CU(cudaMalloc((void**)&d_for, n * 4));
+        CU(cudaMemcpyAsync(d_blocks, blocks.data(), nb * sizeof(SynthSampleCtg), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_frag0, frag0.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, st));
+        synth_meta_kernel<<<(unsigned)((nft + 127) / 128), 128, 0, st>>>(m, (int)s, paired, D, overlap, d_blocks, d_frag0, (uint32_t)nb, (uint32_t)nft,
+            (int32_t*)(meta + o_pos), d_nops, d_nsegs, (uint32_t*)(meta + o_q4), (int32_t*)(meta + o_mate), (uint32_t*)(meta + o_pb),
+            (uint32_t*)(meta + o_pbk), d_for);
+        synth_tail_kernel<<<1, 1, 0, st>>>((uint32_t)n, q4, (uint32_t)np, (uint32_t*)(meta + o_q4), (uint32_t*)(meta + o_pbk));
+        synth_scan2_kernel<<<1, 1024, 0, st>>>(d_nops, d_nsegs, (uint32_t)n, (uint32_t*)(meta + o_cgo), (uint32_t*)(meta + o_sgo));
+        uint32_t n_cig = 0;
+        CU(cudaMemcpyAsync(&n_cig, meta + o_cgo + n * 4, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        // ---- phase 2: CIGARs, bases, qualities
+        const size_t n_q4 = n * q4;
+        o = 0;
+        const size_t o_cig = take((size_t)n_cig * 4), o_seq = take(n_q4), o_qual = take(n_q4 * 4), o_bk = take(np * 8 * q4);
+        uint8_t* data = nullptr;
+        if (cudaMalloc((void**)&data, o) != cudaSuccess) return fail(ctx, MSNV_E_NOMEM, "msnv_shard_synth: out of device memory (sample %u)", s);
+        ctx->sample_allocs.push_back(data);
+        synth_fill_kernel<<<(unsigned)((n_q4 + 255) / 256), 256, 0, st>>>(m, (int)s, paired, d_blocks, d_frag0, (uint32_t)nb, (uint32_t)n,
+            (const int32_t*)(meta + o_pos), (const uint32_t*)(meta + o_cgo), d_for, (uint32_t*)(data + o_cig), data + o_seq, data + o_qual);
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        cudaFree(d_blocks); cudaFree(d_frag0); cudaFree(d_nops); cudaFree(d_nsegs); cudaFree(d_for);
+        SampleDev& sd = ctx->h_samples[s];
+        sd.pos = (const int32_t*)(meta + o_pos);     sd.cig_off = (const uint32_t*)(meta + o_cgo);
+        sd.seg_off = (const uint32_t*)(meta + o_sgo); sd.q4_off = (const uint32_t*)(meta + o_q4);
+        sd.mate = (const int32_t*)(meta + o_mate);   sd.cigar = (const uint32_t*)(data + o_cig);
+        sd.seq2 = data + o_seq;                      sd.qual = data + o_qual;
+        sd.pair_b = (const uint32_t*)(meta + o_pb);  sd.pair_bk = (const uint32_t*)(meta + o_pbk);
+        sd.backup = data + o_bk;
+        sd.n_reads = (uint32_t)n; sd.max_span = L + 3; sd.n_pairs = (uint32_t)np; sd.pad_ = 0;
+        ctx->n_reads += n; ctx->n_bases += 4ull * n_q4;
+        ctx->sizes[s] = msnv_sample_sizes{(uint32_t)n, (uint32_t)np, L + 3, 0, (uint64_t)n_cig, (uint64_t)n_q4};
+    }
+    if (first_column) *first_column = first_col;
+    return MSNV_OK;
+}
+
+int msnv_shard_sample_sizes(msnv_ctx* ctx, uint32_t sample, msnv_sample_sizes* sizes)
+{
+    if (!ctx || !sizes) return MSNV_E_ARG;
+    if (!ctx->open || sample >= ctx->S) return fail(ctx, MSNV_E_ARG, "msnv_shard_sample_sizes: no such sample");
+    *sizes = ctx->sizes[sample];
+    return MSNV_OK;
+}
+
+int msnv_shard_export_sample(msnv_ctx* ctx, uint32_t sample, int32_t* pos, uint32_t* cig_off, uint32_t* seg_off, uint32_t* q4_off,
+                             int32_t* mate, uint32_t* pair_b, uint32_t* cigar, uint8_t* seq2, uint8_t* qual)
+{
+    if (!ctx) return MSNV_E_ARG;
+    if (!ctx->open || sample >= ctx->S) return fail(ctx, MSNV_E_ARG, "msnv_shard_export_sample: no such sample");
+    if (ctx->quals_saved) return fail(ctx, MSNV_E_STATE, "msnv_shard_export_sample: export before the first run (qualities are corrected in place)");
+    const msnv_sample_sizes z = ctx->sizes[sample];
+    if (z.n_reads == 0) return MSNV_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const SampleDev& d = ctx->h_samples[sample];
+    const size_t n = z.n_reads, n1 = n + 1;
+    CU(cudaMemcpyAsync(pos, d.pos, n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cig_off, d.cig_off, n1 * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(seg_off, d.seg_off, n1 * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(q4_off, d.q4_off, n1 * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(mate, d.mate, n * 4, cudaMemcpyDeviceToHost, st));
+    if (z.n_pairs) CU(cudaMemcpyAsync(pair_b, d.pair_b, (size_t)z.n_pairs * 4, cudaMemcpyDeviceToHost, st));
+    if (z.n_cigar) CU(cudaMemcpyAsync(cigar, d.cigar, (size_t)z.n_cigar * 4, cudaMemcpyDeviceToHost, st));
+    if (z.n_q4) {
+        CU(cudaMemcpyAsync(seq2, d.seq2, (size_t)z.n_q4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(qual, d.qual, (size_t)z.n_q4 * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return MSNV_OK;
+}
+
+int msnv_shard_export_ref(msnv_ctx* ctx, uint8_t* ref)
+{
+    if (!ctx || !ref) return MSNV_E_ARG;
+    if (!ctx->open) return fail(ctx, MSNV_E_STATE, "msnv_shard_export_ref: no open shard");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(ref, ctx->d_ref, ctx->P, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return MSNV_OK;
 }
 

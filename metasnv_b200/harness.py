@@ -36,6 +36,19 @@ def synth(out_dir, preset, scale=1.0, samples=0, seed=0, threads=0, depth=None, 
     return json.loads(out.strip().splitlines()[-1])
 
 
+def describe(preset, scale=1.0, samples=0, seed=0, depth=None):
+    """The synthetic configuration as a dict (input of abi.Context.shard_synth)."""
+    import json
+    cmd = [bin_path("msnv_synth"), "--preset", preset, "--scale", str(scale), "--describe"]
+    if samples:
+        cmd += ["--samples", str(samples)]
+    if seed:
+        cmd += ["--seed", str(seed)]
+    if depth is not None:
+        cmd += ["--depth", str(depth)]
+    return json.loads(subprocess.run(cmd, check=True, capture_output=True, text=True).stdout)
+
+
 def _pipe(producer, consumer, out_path, env=None):
     with open(out_path, "wb") as out:
         p1 = subprocess.Popen(producer, stdout=subprocess.PIPE, env=env)

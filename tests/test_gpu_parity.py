@@ -1,0 +1,221 @@
+"""Parity of the CUDA path with the oracle (B200 only: `pytest -m gpu`). Bit-exact for every output:
+called_SNPs, indiv_called, cov/*.cov, cov/*.cov.detail and the per-sample per-position counts."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from metasnv_b200 import harness as H
+from metasnv_b200.paths import bin_path
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(a, b):
+    d = H.first_diff(a, b)
+    assert not d, "%s vs %s: %s" % (a, b, d)
+
+
+@pytest.fixture(scope="module")
+def datasets(built, tmp_path_factory):
+    cache = {}
+    base = str(tmp_path_factory.mktemp("data"))
+
+    def get(preset, scale, samples, **kw):
+        key = (preset, scale, samples, tuple(sorted(kw.items())))
+        if key not in cache:
+            d = os.path.join(base, "%s_%d" % (preset, len(cache)))
+            H.synth(d, preset, scale, samples, **kw)
+            cache[key] = d
+        return cache[key]
+    return get
+
+
+# ---------------------------------------------------------------- committed golden fixtures
+@pytest.mark.parametrize("name", ["c1_tiny", "c5_tiny_annotated", "c4_tiny_deep"])
+def test_golden_fixture(name, datasets, tmp_path):
+    recipe = json.load(open(os.path.join(GOLDEN, name, "recipe.json")))
+    data = datasets(recipe["preset"], recipe["scale"], recipe["samples"], **recipe["extra"])
+    ann = os.path.join(data, "annotation.txt") if recipe["extra"].get("annotation") else None
+    bed = H.bed_header(data, os.path.join(data, "bed_header"))
+    for mode, b in (("unsplit", None), ("split", bed)):
+        out = str(tmp_path / ("gpu_" + mode))
+        rc, err = H.run_product_snpcall(data, out, bed=b, ann=ann)
+        assert rc == 0, err
+        for ext in (".called", ".indiv"):
+            _same(os.path.join(GOLDEN, name, mode + ext), out + ext)
+        out = str(tmp_path / ("txt_" + mode))
+        rc, err = H.run_product_snpcall_text(data, out, bed=b, ann=ann)      # classic text input, GPU call kernels
+        assert rc == 0, err
+        for ext in (".called", ".indiv"):
+            _same(os.path.join(GOLDEN, name, mode + ext), out + ext)
+    for i, bam in enumerate([l.strip() for l in open(os.path.join(data, "all_samples"))][:2]):
+        out = str(tmp_path / ("s%d.cov" % i))
+        r = H.run_qacompute(bin_path("qaCompute"), bam, out)
+        assert r.returncode == 0, r.stderr
+        for ext in ("", ".detail"):
+            _same(os.path.join(GOLDEN, name, "s%d.cov%s" % (i, ext)), out + ext)
+
+
+def test_hand_written_case(built, tmp_path):
+    """Edge cases in one small SAM: insertion, deletion, clips, N bases, lower-case / N reference, filtered flags,
+    orphan, overlapping mates that agree and disagree, low base quality, read starting at position 1."""
+    tmp = str(tmp_path)
+    bams = []
+    for s in ("s1", "s2"):
+        out = os.path.join(tmp, s + ".bam")
+        subprocess.run([bin_path("msnv_synth"), "--sam", os.path.join(GOLDEN, "hand", s + ".sam"), "--bam", out], check=True)
+        bams.append(out)
+    lst = os.path.join(tmp, "all_samples")
+    open(lst, "w").write("\n".join(bams) + "\n")
+    os.symlink(os.path.join(GOLDEN, "hand", "ref.fa"), os.path.join(tmp, "ref.fa"))
+    out = os.path.join(tmp, "gpu")
+    rc, err = H.run_product_snpcall(tmp, out, c=2, t=2)
+    assert rc == 0, err
+    _same(os.path.join(GOLDEN, "hand", "expected.called"), out + ".called")
+    _same(os.path.join(GOLDEN, "hand", "expected.indiv"), out + ".indiv")
+    for s, bam in zip(("s1", "s2"), bams):
+        o = os.path.join(tmp, s + ".cov")
+        assert H.run_qacompute(bin_path("qaCompute"), bam, o).returncode == 0
+        for ext in ("", ".detail"):
+            _same(os.path.join(GOLDEN, "hand", "expected_%s.cov%s" % (s, ext)), o + ext)
+
+
+# ---------------------------------------------------------------- live oracle on larger seeded inputs
+LIVE = [
+    ("c1", 0.2, 40, {}, dict()),
+    ("c1", 0.05, 12, {"seed": 7}, dict(c=10, t=2, p=0.2)),
+    ("c1", 0.05, 12, {"seed": 8}, dict(c=1, t=1, p=0.0)),
+    ("c3", 0.0005, 10, {}, dict()),
+    ("c4", 0.005, 3, {}, dict()),
+    ("c5", 0.004, 6, {"annotation": True}, dict()),
+    ("c2", 0.004, 160, {}, dict()),
+]
+
+
+@pytest.mark.parametrize("preset,scale,samples,kw,opts", LIVE, ids=["%s-%s-%d" % (p, s, n) for p, s, n, _, _ in LIVE])
+def test_live_parity(preset, scale, samples, kw, opts, datasets, tmp_path):
+    data = datasets(preset, scale, samples, **kw)
+    ann = os.path.join(data, "annotation.txt") if kw.get("annotation") else None
+    bed = H.bed_header(data, os.path.join(data, "bed_header"))
+    for mode, b in (("unsplit", None), ("split", bed)):
+        o, g = str(tmp_path / ("oracle_" + mode)), str(tmp_path / ("gpu_" + mode))
+        rc, err = H.run_oracle_snpcall(data, o, bed=b, ann=ann, **opts)
+        assert rc == 0, err
+        rc, err = H.run_product_snpcall(data, g, bed=b, ann=ann, **opts)
+        assert rc == 0, err
+        for ext in (".called", ".indiv"):
+            _same(o + ext, g + ext)
+    for i, bam in enumerate([l.strip() for l in open(os.path.join(data, "all_samples"))][:3]):
+        o, g = str(tmp_path / ("o%d.cov" % i)), str(tmp_path / ("g%d.cov" % i))
+        assert H.run_qacompute(H.oracle_bin("qacompute_oracle"), bam, o).returncode == 0
+        r = H.run_qacompute(bin_path("qaCompute"), bam, g)
+        assert r.returncode == 0, r.stderr
+        for ext in ("", ".detail"):
+            _same(o + ext, g + ext)
+
+
+def test_split_files_concatenate_to_whole(datasets, tmp_path):
+    """createOptimumSplit-style sharding: per-genome splits called independently (one process each, as metaSNV.py
+    does) equal the oracle on the same splits, and no call is lost or duplicated across shards."""
+    data = datasets("c1", 0.05, 12)
+    bed = H.bed_header(data, os.path.join(data, "bed_header"))
+    lines = open(bed).read().splitlines()
+    total = 0
+    for k, ln in enumerate(lines):                       # one genome (contig) per split
+        sp = str(tmp_path / ("best_split_%d" % k))
+        open(sp, "w").write(ln + "\n")
+        o, g = str(tmp_path / ("o%d" % k)), str(tmp_path / ("g%d" % k))
+        assert H.run_oracle_snpcall(data, o, bed=sp)[0] == 0
+        rc, err = H.run_product_snpcall(data, g, bed=sp)
+        assert rc == 0, err
+        _same(o + ".called", g + ".called")
+        _same(o + ".indiv", g + ".indiv")
+        total += sum(1 for _ in open(g + ".called"))
+    whole = str(tmp_path / "whole")
+    assert H.run_product_snpcall(data, whole, bed=bed)[0] == 0
+    # every split drops its own first pileup line, the single-process run only one: allow that difference
+    n_whole = sum(1 for _ in open(whole + ".called"))
+    assert n_whole - len(lines) <= total <= n_whole
+
+
+# ---------------------------------------------------------------- per-position counts (pileup kernel output)
+def _oracle_counts(pile_path, n_samples, layout):
+    """Parse mpileup text into [S][P][5] counts: a column's letters go to their base, '.'/',' to the reference's."""
+    off = {name: o for name, o, _ in layout}
+    P = max(o + ((l + 511) // 512) * 512 for _, o, l in layout)
+    cnt = np.zeros((n_samples, P, 5), np.uint16)
+    chan = {"A": 0, "C": 1, "G": 2, "T": 3, "a": 0, "c": 1, "g": 2, "t": 3}
+    for line in open(pile_path):
+        f = line.rstrip("\n").split("\t")
+        p = off[f[0]] + int(f[1]) - 1
+        r = f[2].upper()
+        rch = chan.get(r, 4)
+        for s in range(n_samples):
+            b = f[4 + 3 * s]
+            i = 0
+            while i < len(b):
+                ch = b[i]
+                if ch == "^":
+                    i += 2
+                    continue
+                if ch in "+-":
+                    j = i + 1
+                    while b[j].isdigit():
+                        j += 1
+                    i = j + int(b[i + 1:j])
+                    continue
+                if ch in ".,":
+                    cnt[s, p, rch] += 1
+                elif ch in chan:
+                    cnt[s, p, chan[ch]] += 1
+                elif ch in "Nn":
+                    cnt[s, p, 4] += 1
+                i += 1
+    return cnt
+
+
+@pytest.mark.parametrize("preset,scale,samples", [("c1", 0.03, 8), ("c4", 0.002, 2)])
+def test_pileup_counts_match_oracle_text(preset, scale, samples, datasets, tmp_path):
+    data = datasets(preset, scale, samples)
+    dump = str(tmp_path / "counts.bin")
+    rc, err = H.run_product_snpcall(data, str(tmp_path / "gpu"), env=dict(os.environ, MSNV_DUMP_COUNTS=dump))
+    assert rc == 0, err
+    lay = [l.rstrip("\n").split("\t") for l in open(dump + ".layout")]
+    S, P = int(lay[0][0]), int(lay[0][1])
+    layout = [(n, int(o), int(l)) for n, o, l in lay[1:]]
+    got = np.fromfile(dump, np.uint16).reshape(S, P, 5)
+    pile = str(tmp_path / "pile.txt")
+    with open(pile, "wb") as f:
+        subprocess.run([H.oracle_bin("mpileup_oracle"), "mpileup", "-f", os.path.join(data, "ref.fa"), "-B", "-b",
+                        os.path.join(data, "all_samples")], stdout=f, check=True)
+    want = _oracle_counts(pile, S, layout)
+    assert want.shape == got.shape
+    bad = np.argwhere(want != got)
+    assert bad.size == 0, "first mismatch (sample,pos,channel)=%s want %s got %s" % (bad[0], want[tuple(bad[0])], got[tuple(bad[0])])
+    assert int(got.sum()) > 0
+
+
+def test_empty_inputs(built, tmp_path):
+    """BAMs with a header but no reads, alone and next to a populated one."""
+    d = str(tmp_path)
+    sam = os.path.join(d, "e.sam")
+    open(sam, "w").write("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:ctgA\tLN:40\n@SQ\tSN:ctgB\tLN:40\n")
+    e1, e2 = os.path.join(d, "e1.bam"), os.path.join(d, "e2.bam")
+    for e in (e1, e2):
+        subprocess.run([bin_path("msnv_synth"), "--sam", sam, "--bam", e], check=True)
+    full = os.path.join(d, "s1.bam")
+    subprocess.run([bin_path("msnv_synth"), "--sam", os.path.join(GOLDEN, "hand", "s1.sam"), "--bam", full], check=True)
+    os.symlink(os.path.join(GOLDEN, "hand", "ref.fa"), os.path.join(d, "ref.fa"))
+    for name, bams in (("only_empty", [e1, e2]), ("mixed", [e1, full, e2])):
+        lst = os.path.join(d, name + ".list")
+        open(lst, "w").write("\n".join(bams) + "\n")
+        o, g = os.path.join(d, "o_" + name), os.path.join(d, "g_" + name)
+        assert H.run_oracle_snpcall(d, o, all_samples=lst, c=1, t=1)[0] == 0
+        rc, err = H.run_product_snpcall(d, g, all_samples=lst, c=1, t=1)
+        assert rc == 0, err
+        _same(o + ".called", g + ".called")
+        _same(o + ".indiv", g + ".indiv")

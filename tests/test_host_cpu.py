@@ -1,0 +1,109 @@
+"""Host-side checks that need no GPU: the C ABI library loads and exports what include/msnv.h declares,
+the drop-in programs keep the reference's command-line behaviour, BAM I/O round-trips, and the product
+refuses to run without a CUDA device (there is no CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+from metasnv_b200 import harness as H
+from metasnv_b200.paths import bin_path, lib_path
+
+
+def _no_gpu():
+    lib = ctypes.CDLL(lib_path())
+    lib.msnv_device_count.restype = ctypes.c_int
+    return lib.msnv_device_count() == 0
+
+
+def test_abi_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "msnv.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(msnv_[a-z_0-9]+)\s*\(", hdr))
+    assert {"msnv_create", "msnv_shard_begin", "msnv_shard_add_sample", "msnv_shard_run", "msnv_call_counts", "msnv_cov_run"} <= names
+    lib = ctypes.CDLL(lib_path())
+    for n in sorted(names):
+        assert hasattr(lib, n), "libmsnv_gpu.so does not export %s" % n
+    lib.msnv_abi_version.restype = ctypes.c_int
+    assert lib.msnv_abi_version() == 1
+
+
+def test_abi_python_binding_matches_struct_sizes(built):
+    from metasnv_b200 import abi
+    assert ctypes.sizeof(abi.SampleReads) == 16 + 9 * 8
+    assert ctypes.sizeof(abi.CallParams) == 16
+    assert ctypes.sizeof(abi.Hits) == 8 + 6 * 8
+    assert ctypes.sizeof(abi.CovBlocks) == 8 + 4 * 8
+
+
+def test_library_contains_sm100a_code_and_tma(built):
+    out = subprocess.run(["cuobjdump", "-lelf", lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", lib_path()], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass            # cp.async.bulk (TMA) in the pileup kernel
+
+
+def test_product_fails_loudly_without_gpu(built, tmp_path):
+    if not _no_gpu():
+        pytest.skip("a CUDA device is present")
+    d = str(tmp_path / "d")
+    H.synth(d, "c1", 0.02, 2)
+    rc, err = H.run_product_snpcall(d, str(tmp_path / "out"))
+    assert rc != 0 and "no usable CUDA device" in err
+    r = H.run_qacompute(bin_path("qaCompute"), open(os.path.join(d, "all_samples")).readline().strip(), str(tmp_path / "x.cov"))
+    assert r.returncode != 0 and "no usable CUDA device" in r.stderr
+    from metasnv_b200 import abi
+    with pytest.raises(abi.MsnvError):
+        abi.Context(0)
+
+
+def test_snpcall_cli_surface(built, tmp_path):
+    """Exit codes and messages of call_vC.cpp:346-416."""
+    sc = bin_path("snpCall")
+    r = subprocess.run([sc, "-h"], capture_output=True)
+    assert r.returncode == 255
+    r = subprocess.run([sc, "-f", "/nonexistent/ref.fa"], capture_output=True, text=True)
+    assert r.returncode == 255 and "Cannot open /nonexistent/ref.fa" in r.stderr
+    r = subprocess.run([sc, "stray"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == "Non-option argument stray\n"
+    r = subprocess.run([sc, "-z"], capture_output=True, text=True)
+    assert r.returncode == -6 and "Unknown option `-z'." in r.stderr          # abort()
+    r = subprocess.run([sc, "-f"], capture_output=True, text=True)
+    assert r.returncode == -6 and "requires a reference file" in r.stderr
+    ind = str(tmp_path / "i.txt")
+    r = subprocess.run([sc, "-i", ind], input=b"", capture_output=True)
+    assert r.returncode == 0 and r.stdout == b"" and os.path.getsize(ind) == 0 and b"Identified 0 samples" in r.stderr
+
+
+def test_qacompute_cli_surface(built, tmp_path):
+    qa = bin_path("qaCompute")
+    assert subprocess.run([qa], capture_output=True).returncode == 1
+    assert subprocess.run([qa, "-c", "10", "/nonexistent.bam", str(tmp_path / "o")], capture_output=True).returncode == 1
+    assert subprocess.run([qa, "-m", "a", "b"], capture_output=True).returncode == 255
+
+
+def test_samtools_standin(built, tmp_path):
+    st = bin_path("samtools")
+    r = subprocess.run([st, "mpileup", "-f", "ref.fa", "-l", "split", "-B", "-b", "list"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == "#MSNV1\tref.fa\tsplit\tlist\n"
+    r = subprocess.run([st, "mpileup", "-f", "ref.fa", "-B", "-b", "list"], capture_output=True, text=True)
+    assert r.stdout == "#MSNV1\tref.fa\t-\tlist\n"
+    assert subprocess.run([st, "sort", "x"], capture_output=True).returncode == 1
+
+
+def test_bam_roundtrip_product_writer_oracle_reader(built, tmp_path):
+    """BAMs written by the product's BGZF/BAM writer are read identically by the oracle's independent reader
+    (qaCompute restatement totals) and the header survives both readers."""
+    d = str(tmp_path / "d")
+    st = H.synth(d, "c1", 0.02, 3)
+    total = 0
+    for i, b in enumerate(l.strip() for l in open(os.path.join(d, "all_samples"))):
+        out = str(tmp_path / ("s%d.cov" % i))
+        assert H.run_qacompute(H.oracle_bin("qacompute_oracle"), b, out).returncode == 0
+        m = re.search(r"Total number of reads: (\d+)", open(out).read())
+        total += int(m.group(1))
+    assert total == st["reads"] + st["junk"] + st["unmapped"]
+    assert H.bed_header(d, str(tmp_path / "bed")) and open(str(tmp_path / "bed")).read().count("\n") == 3
