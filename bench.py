@@ -5,7 +5,7 @@ configuration "single 5 Mb genome, 1000 samples at ~10x" (configs[1], "c2").
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...     (N > 1)
 
-One "step" = one pass of index -> mate-overlap correction -> pileup -> call -> compaction -> gather
+One "step" = one pass of index -> pileup (with mate-overlap correction) -> call -> compaction -> gather
 over every read of the shard, inputs resident in HBM (`value`). `e2e` is the same pass through the
 C ABI with pinned HOST buffers: upload of all reads, the kernels, download of the hits.
 With N > 1 every rank owns one genome shard of the same shape (the sharding createOptimumSplit
@@ -226,7 +226,7 @@ def run_ours(a):
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = sum(t["ms_total"] for t in per) / a.steps
-    keys = ("ms_index", "ms_overlap", "ms_pileup", "ms_call", "ms_compact", "ms_gather")
+    keys = ("ms_index", "ms_pileup", "ms_call", "ms_compact", "ms_gather")
     kern = {k: sum(t[k] for t in per) / a.steps for k in keys}
     launches = sum(t["kernel_launches"] for t in per)
     items = per[-1]["n_items"]
@@ -262,13 +262,10 @@ def run_ours(a):
     # ---- reduce over ranks: time = max, work = sum
     step_ms, wall_ms = dev_ms, 1000.0 * wall / a.steps
     tot_aligned, tot_launch, tot_sp, e2e_max = aligned, launches, S * genome_len, e2e_ms or 0.0
+    from metasnv_b200.sharding import reduce_over_ranks
+    (step_ms, wall_ms, e2e_max), work = reduce_over_ranks(dist, "cuda", [step_ms, wall_ms, e2e_max], [tot_aligned, tot_launch, tot_sp])
+    tot_aligned, tot_launch, tot_sp = [int(x) for x in work]
     if dist is not None:
-        t = torch.tensor([step_ms, wall_ms, e2e_max], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms, wall_ms, e2e_max = t.tolist()
-        w = torch.tensor([tot_aligned, tot_launch, tot_sp], dtype=torch.float64, device="cuda")
-        dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        tot_aligned, tot_launch, tot_sp = [int(x) for x in w.tolist()]
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MSNV_ABI_VERSION 1
+#define MSNV_ABI_VERSION 2
 
 /* Positions per tile: contigs of a shard are laid out back to back in a "shard coordinate" space,
  * each starting at a multiple of MSNV_TILE, so a tile never spans two contigs. */
@@ -52,8 +52,8 @@ typedef struct msnv_ctx msnv_ctx;
  *   cig_off  first CIGAR word of the read in `cigar`
  *   seg_off  number of M/=/X operations before this read (the kernel turns each into a segment)
  *   q4_off   first 4-base group of the read in `seq2` (byte index) / `qual` (byte index * 4)
- *   mate     index of the earlier mate this read overlaps per mpileup's overlap detection, else -1;
- *            a read takes part in at most one pair
+ *   mate     index of the mate this read is paired with by mpileup's overlap detection (Annex A.2), else -1;
+ *            symmetric (mate[mate[i]] == i), a read takes part in at most one pair
  *   cigar    BAM encoding (len << 4 | op), op in MIDNSHP=X
  *   seq2     2 bits per base, base k of a group in bits 2k..2k+1, A=0 C=1 G=2 T=3
  *   qual     min(phred,127) per base; bit 7 set when the base is not A/C/G/T (N or IUPAC code)
@@ -61,14 +61,12 @@ typedef struct msnv_ctx msnv_ctx;
 typedef struct {
     uint32_t        n_reads;
     uint32_t        max_span;
-    uint32_t        n_pairs;   /* reads with mate >= 0 */
-    uint32_t        reserved;
+    uint32_t        reserved0, reserved1;
     const int32_t*  pos;
     const uint32_t* cig_off;
     const uint32_t* seg_off;
     const uint32_t* q4_off;
     const int32_t*  mate;
-    const uint32_t* pair_b;    /* [n_pairs] indices of the reads with mate >= 0, ascending */
     const uint32_t* cigar;
     const uint8_t*  seq2;
     const uint8_t*  qual;
@@ -103,7 +101,7 @@ typedef struct {
 /* Device-side timings of the last msnv_shard_run(), milliseconds (CUDA events on the context's
  * stream), plus the work it did. */
 typedef struct {
-    float    ms_index, ms_overlap, ms_pileup, ms_call, ms_compact, ms_gather, ms_total;
+    float    ms_index, ms_reserved, ms_pileup, ms_call, ms_compact, ms_gather, ms_total;
     uint64_t n_items;           /* active (sample, tile) pairs */
     uint64_t n_reads;
     uint64_t n_bases;           /* query bases resident for the shard */
@@ -136,8 +134,8 @@ int msnv_shard_add_sample(msnv_ctx* ctx, uint32_t sample, const msnv_sample_read
 int msnv_shard_mask_position(msnv_ctx* ctx, uint32_t pos);
 /* Wait until every copy queued by msnv_shard_add_sample() has completed. */
 int msnv_shard_sync(msnv_ctx* ctx);
-/* Run overlap correction, pileup, calling and compaction; fills *hits. May be called repeatedly
- * (the per-base qualities are restored first), e.g. with different parameters. */
+/* Run pileup (with mpileup's mate-overlap quality correction), calling and compaction; fills *hits.
+ * The uploaded reads are never modified, so it may be called repeatedly, e.g. with other parameters. */
 int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* params, msnv_hits* hits);
 /* Test/inspection hook: per-position A,C,G,T,N counts ([n][5], uint16) of one sample after the last
  * run, for shard coordinates [first, first+n). */
@@ -174,10 +172,10 @@ int msnv_shard_synth(msnv_ctx* ctx, const msnv_synth_desc* desc, int64_t* first_
 
 /* Copy one sample of the open shard back to host arrays sized from *sizes (as returned by
  * msnv_shard_sample_sizes): used to stage pinned host buffers for end-to-end timing. */
-typedef struct { uint32_t n_reads, n_pairs, max_span, reserved; uint64_t n_cigar, n_q4; } msnv_sample_sizes;
+typedef struct { uint32_t n_reads, n_mated, max_span, reserved; uint64_t n_cigar, n_q4; } msnv_sample_sizes;
 int msnv_shard_sample_sizes(msnv_ctx* ctx, uint32_t sample, msnv_sample_sizes* sizes);
 int msnv_shard_export_sample(msnv_ctx* ctx, uint32_t sample, int32_t* pos, uint32_t* cig_off, uint32_t* seg_off, uint32_t* q4_off,
-                             int32_t* mate, uint32_t* pair_b, uint32_t* cigar, uint8_t* seq2, uint8_t* qual);
+                             int32_t* mate, uint32_t* cigar, uint8_t* seq2, uint8_t* qual);
 /* Copy the shard's reference characters (n_positions bytes) back to the host. */
 int msnv_shard_export_ref(msnv_ctx* ctx, uint8_t* ref);
 

@@ -18,9 +18,9 @@ class MsnvError(RuntimeError):
 
 
 class SampleReads(C.Structure):
-    _fields_ = [("n_reads", C.c_uint32), ("max_span", C.c_uint32), ("n_pairs", C.c_uint32), ("reserved", C.c_uint32),
+    _fields_ = [("n_reads", C.c_uint32), ("max_span", C.c_uint32), ("reserved0", C.c_uint32), ("reserved1", C.c_uint32),
                 ("pos", C.c_void_p), ("cig_off", C.c_void_p), ("seg_off", C.c_void_p), ("q4_off", C.c_void_p),
-                ("mate", C.c_void_p), ("pair_b", C.c_void_p), ("cigar", C.c_void_p), ("seq2", C.c_void_p), ("qual", C.c_void_p)]
+                ("mate", C.c_void_p), ("cigar", C.c_void_p), ("seq2", C.c_void_p), ("qual", C.c_void_p)]
 
 
 class CallParams(C.Structure):
@@ -34,7 +34,7 @@ class Hits(C.Structure):
 
 
 class Timings(C.Structure):
-    _fields_ = [("ms_index", C.c_float), ("ms_overlap", C.c_float), ("ms_pileup", C.c_float), ("ms_call", C.c_float),
+    _fields_ = [("ms_index", C.c_float), ("ms_reserved", C.c_float), ("ms_pileup", C.c_float), ("ms_call", C.c_float),
                 ("ms_compact", C.c_float), ("ms_gather", C.c_float), ("ms_total", C.c_float),
                 ("n_items", C.c_uint64), ("n_reads", C.c_uint64), ("n_bases", C.c_uint64),
                 ("n_tiles", C.c_uint32), ("kernel_launches", C.c_uint32)]
@@ -52,7 +52,7 @@ class SynthDesc(C.Structure):
 
 
 class SampleSizes(C.Structure):
-    _fields_ = [("n_reads", C.c_uint32), ("n_pairs", C.c_uint32), ("max_span", C.c_uint32), ("reserved", C.c_uint32),
+    _fields_ = [("n_reads", C.c_uint32), ("n_mated", C.c_uint32), ("max_span", C.c_uint32), ("reserved", C.c_uint32),
                 ("n_cigar", C.c_uint64), ("n_q4", C.c_uint64)]
 
 
@@ -91,7 +91,7 @@ def load():
     lib.msnv_pinned_free.restype = None
     lib.msnv_shard_synth.argtypes = [C.c_void_p, C.POINTER(SynthDesc), C.POINTER(C.c_int64)]
     lib.msnv_shard_sample_sizes.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(SampleSizes)]
-    lib.msnv_shard_export_sample.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 9
+    lib.msnv_shard_export_sample.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 8
     lib.msnv_shard_export_ref.argtypes = [C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
@@ -177,14 +177,13 @@ class Context:
         self._check(self.lib.msnv_shard_begin(self.h, n_samples, ref.size, _ptr(ref)), "msnv_shard_begin")
 
     def shard_add_sample(self, sample, arrays):
-        """arrays: dict with pos, cig_off, seg_off, q4_off, mate, pair_b, cigar, seq2, qual (numpy), max_span."""
+        """arrays: dict with pos, cig_off, seg_off, q4_off, mate, cigar, seq2, qual (numpy), max_span."""
         a = {k: np.ascontiguousarray(v) for k, v in arrays.items() if k != "max_span"}
         self._keep.append(a)
         r = SampleReads()
         r.n_reads = a["pos"].size
         r.max_span = int(arrays["max_span"])
-        r.n_pairs = a["pair_b"].size
-        for k in ("pos", "cig_off", "seg_off", "q4_off", "mate", "pair_b", "cigar", "seq2", "qual"):
+        for k in ("pos", "cig_off", "seg_off", "q4_off", "mate", "cigar", "seq2", "qual"):
             setattr(r, k, _ptr(a[k]))
         self._check(self.lib.msnv_shard_add_sample(self.h, sample, C.byref(r)), "msnv_shard_add_sample")
 
@@ -219,7 +218,7 @@ class Context:
                 return np.empty(n, np.uint8)
         n, n1 = z.n_reads, z.n_reads + 1
         spec = [("pos", n, np.int32), ("cig_off", n1, np.uint32), ("seg_off", n1, np.uint32), ("q4_off", n1, np.uint32),
-                ("mate", n, np.int32), ("pair_b", z.n_pairs, np.uint32), ("cigar", z.n_cigar, np.uint32),
+                ("mate", n, np.int32), ("cigar", z.n_cigar, np.uint32),
                 ("seq2", z.n_q4, np.uint8), ("qual", z.n_q4 * 4, np.uint8)]
         out = {"max_span": z.max_span}
         for k, cnt, dt in spec:

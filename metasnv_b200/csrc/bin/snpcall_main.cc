@@ -214,13 +214,13 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
                     "\"aligned_bases\": %llu, \"pairs\": %llu, \"dropped_by_cap\": %llu, \"bam_bytes\": %llu, \"h2d_bytes\": %llu, \"hits\": %u, "
                     "\"decode_threads\": %d, \"decode_wall_s\": %.6f, \"decode_cpu_s\": %.6f, \"inflate_cpu_s\": %.6f, \"h2d_s\": %.6f, "
                     "\"gpu_run_wall_s\": %.6f, \"format_s\": %.6f, \"total_s\": %.6f, "
-                    "\"ms_index\": %.4f, \"ms_overlap\": %.4f, \"ms_pileup\": %.4f, \"ms_call\": %.4f, \"ms_compact\": %.4f, \"ms_gather\": %.4f, "
+                    "\"ms_index\": %.4f, \"ms_pileup\": %.4f, \"ms_call\": %.4f, \"ms_compact\": %.4f, \"ms_gather\": %.4f, "
                     "\"items\": %llu, \"launches\": %u}\n",
                     dev, S, layout.n_positions, (unsigned long long)tot.records, (unsigned long long)tot.accepted,
                     (unsigned long long)tot.aligned_bases, (unsigned long long)tot.pairs, (unsigned long long)tot.dropped_by_cap,
                     (unsigned long long)tot.compressed_bytes, (unsigned long long)h2d_bytes, hits.n_hits, n_threads * inflate_threads,
                     t_dec1 - t_dec0, tot.seconds, tot.inflate_seconds, t_h2d, t_run1 - t_run0, t_end - t_run1, t_end - t_start, tm.ms_index,
-                    tm.ms_overlap, tm.ms_pileup, tm.ms_call, tm.ms_compact, tm.ms_gather, (unsigned long long)tm.n_items, tm.kernel_launches);
+                    tm.ms_pileup, tm.ms_call, tm.ms_compact, tm.ms_gather, (unsigned long long)tm.n_items, tm.kernel_launches);
             fclose(f);
         }
     }

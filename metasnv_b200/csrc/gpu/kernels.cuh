@@ -2,8 +2,8 @@
 //
 // Data flow for one shard (all samples of one genome bin):
 //   index_kernel     (tile, sample) pairs that have reads  -> ordered work items (ballot compaction)
-//   overlap_*        mate-overlap base quality correction, in place (SURVEY.md Annex A.2)
-//   pileup_kernel    per item: stage reads (TMA bulk copies) -> CIGAR walk -> per-position gather
+//   pileup_kernel    per item: stage reads (TMA bulk copies) -> CIGAR walk + mate-overlap quality
+//                    correction (SURVEY.md Annex A.2) in shared memory -> per-position gather
 //                    -> packed A/C/G/T/N counts, 10 B per sample-position      [dominant kernel]
 //   call_kernel      per tile: reduce over samples, snpCall thresholds (call_vC.cpp:545-601)
 //   compact_kernel   ordered stream compaction of called positions (warp ballot + block scan)
@@ -21,7 +21,7 @@ namespace msnv_gpu {
 
 constexpr int TILE = MSNV_TILE;                 // positions per tile == threads per pileup CTA
 constexpr int PILEUP_THREADS = TILE;
-constexpr int CHUNK_READS = 256;                // reads staged per chunk (at most)
+constexpr int CHUNK_READS = 255;                // reads staged per chunk (at most; 8-bit per-chunk counters)
 constexpr int CHUNK_Q4 = 4096;                  // 4-base groups staged per chunk (16384 bases)
 constexpr int CHUNK_CIGAR = 1024;               // CIGAR words staged per chunk
 constexpr int CHUNK_SEGS = 1024;                // aligned segments per chunk
@@ -37,11 +37,8 @@ struct SampleDev {
     const int32_t*  mate;
     const uint32_t* cigar;
     const uint8_t*  seq2;
-    uint8_t*        qual;
-    const uint32_t* pair_b;      // [n_pairs] index of the later mate of each overlapping pair
-    const uint32_t* pair_bk;     // [n_pairs+1] byte offsets into `backup`
-    uint8_t*        backup;      // pristine qualities of every read that takes part in a pair
-    uint32_t        n_reads, max_span, n_pairs, pad_;
+    const uint8_t*  qual;
+    uint32_t        n_reads, max_span;
 };
 
 struct Item { uint32_t sample, tile, r_lo, r_hi; };   // reads [r_lo, r_hi) of `sample` may overlap `tile`
@@ -219,18 +216,16 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ v, ui
 }
 
 // ------------------------------------------------------------------------------------------------
-// mate-overlap quality correction (htslib tweak_overlap_quality as summarised in SURVEY.md A.2).
-// One thread per overlapping pair; both reads' CIGARs are walked in lock step. Qualities live in
-// 7 bits (bit 7 flags a non-ACGT base), so the 200 cap becomes 127: only "q >= 13" is ever used.
+// CIGAR cursor shared by the overlap correction: walks to aligned (M/=/X) reference coordinates.
 // ------------------------------------------------------------------------------------------------
 struct CigarWalk {
     const uint32_t* c; uint32_t n, k; int32_t x; uint32_t y;     // x: reference coordinate, y: query offset
     __device__ void init(const uint32_t* cig, uint32_t n_ops, int32_t pos) { c = cig; n = n_ops; k = 0; x = pos; y = 0; }
-    // smallest aligned (M/=/X) reference coordinate >= want; false when the read is exhausted
+    // smallest aligned reference coordinate >= want; false when the read is exhausted
     __device__ bool seek(int32_t want, int32_t& ref, uint32_t& q)
     {
         while (k < n) {
-            const uint32_t w = __ldg(c + k), op = w & 0xf; const int32_t len = (int32_t)(w >> 4);
+            const uint32_t w = c[k], op = w & 0xf; const int32_t len = (int32_t)(w >> 4);
             if (op == 0 || op == 7 || op == 8) {
                 if (want < x + len) { ref = want > x ? want : x; q = y + (uint32_t)(ref - x); return true; }
                 x += len; y += (uint32_t)len;
@@ -247,83 +242,40 @@ __device__ __forceinline__ uint32_t base2_at(const uint8_t* seq2, uint32_t q)
     return (seq2[q >> 2] >> ((q & 3) * 2)) & 3;
 }
 
-// mode 0: save pristine qualities of both mates; 1: restore them; 2: apply the correction
-template <int MODE>
-__global__ void __launch_bounds__(128) overlap_kernel(const SampleDev* __restrict__ samples, const uint32_t* __restrict__ pair_base,
-                                                      uint32_t n_samples, uint64_t n_pairs_total)
+// 1 << s with PTX clamping semantics (s >= 32 gives 0)
+__device__ __forceinline__ uint32_t shl1_clamped32(uint32_t s)
 {
-    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_pairs_total) return;
-    // sample lookup: pair_base[s] <= g < pair_base[s+1]
-    uint32_t lo = 0, hi = n_samples;
-    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (__ldg(pair_base + mid) <= g) lo = mid; else hi = mid; }
-    const SampleDev sd = samples[lo];
-    const uint32_t pi = (uint32_t)(g - __ldg(pair_base + lo));
-    const uint32_t b = __ldg(sd.pair_b + pi);
-    const uint32_t a = (uint32_t)__ldg(sd.mate + b);
-    const uint32_t qa0 = __ldg(sd.q4_off + a), qa1 = __ldg(sd.q4_off + a + 1);
-    const uint32_t qb0 = __ldg(sd.q4_off + b), qb1 = __ldg(sd.q4_off + b + 1);
-    uint8_t* aq = sd.qual + (size_t)qa0 * 4;
-    uint8_t* bq = sd.qual + (size_t)qb0 * 4;
-    if (MODE == 0 || MODE == 1) {
-        uint32_t* bk = (uint32_t*)(sd.backup + __ldg(sd.pair_bk + pi));
-        uint32_t* a4 = (uint32_t*)aq; uint32_t* b4 = (uint32_t*)bq;
-        const uint32_t na = qa1 - qa0, nb = qb1 - qb0;
-        if (MODE == 0) { for (uint32_t i = 0; i < na; ++i) bk[i] = a4[i]; for (uint32_t i = 0; i < nb; ++i) bk[na + i] = b4[i]; }
-        else           { for (uint32_t i = 0; i < na; ++i) a4[i] = bk[i]; for (uint32_t i = 0; i < nb; ++i) b4[i] = bk[na + i]; }
-        return;
-    }
-    const uint8_t* as = sd.seq2 + qa0;
-    const uint8_t* bs = sd.seq2 + qb0;
-    CigarWalk wa, wb;
-    const uint32_t ca = __ldg(sd.cig_off + a), cb = __ldg(sd.cig_off + b);
-    const int32_t pa = __ldg(sd.pos + a), pb = __ldg(sd.pos + b);
-    wa.init(sd.cigar + ca, __ldg(sd.cig_off + a + 1) - ca, pa);
-    wb.init(sd.cigar + cb, __ldg(sd.cig_off + b + 1) - cb, pb);
-    int32_t ref = pb;
-    for (;;) {
-        int32_t ra, rb; uint32_t ia, ib;
-        if (!wa.seek(ref, ra, ia)) break;
-        if (ra > ref) ref = ra;
-        if (!wb.seek(ref, rb, ib)) break;
-        if (rb > ref) { ref = rb; continue; }
-        const uint32_t va = aq[ia], vb = bq[ib];
-        const uint32_t fa = va & 0x80u, fb = vb & 0x80u;
-        const uint32_t q1 = va & 0x7fu, q2 = vb & 0x7fu;
-        // "same base" in htslib compares 4-bit codes; non-ACGT codes all collapse to the flag here
-        const bool same = (fa || fb) ? (fa && fb) : (base2_at(as, ia) == base2_at(bs, ib));
-        if (same) {
-            uint32_t q = q1 + q2; if (q > 127u) q = 127u;
-            aq[ia] = (uint8_t)(fa | q); bq[ib] = (uint8_t)fb;
-        } else if (q1 >= q2) {
-            aq[ia] = (uint8_t)(fa | (uint32_t)(0.8 * (double)q1)); bq[ib] = (uint8_t)fb;
-        } else {
-            bq[ib] = (uint8_t)(fb | (uint32_t)(0.8 * (double)q2)); aq[ia] = (uint8_t)fa;
-        }
-        ++ref;
-    }
+    uint32_t r;
+    asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"(s));
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------------
 // pileup: one CTA per work item (sample, tile); thread i owns position tile*TILE + i.
-// Reads are staged chunk by chunk into shared memory with TMA bulk copies, their CIGARs are walked
-// into aligned segments, the per-base (2-bit base, quality) pairs are turned into 1-byte codes in
-// place, and every thread then gathers the codes of the segments that cover its own position. No
-// atomics: a position's counters live in the registers of exactly one thread, so deep coverage
-// costs instructions in proportion to bases and nothing for contention.
+// Reads are staged chunk by chunk into shared memory with TMA bulk copies; then, per chunk:
+//   a. threads 0..m-1 walk one read's CIGAR each into aligned segments;
+//      threads 256..256+m-1 apply mpileup's mate-overlap quality correction (htslib
+//      tweak_overlap_quality, SURVEY.md Annex A.2) to their own read's staged qualities, reading the
+//      mate's pristine bases/qualities from global memory -- HBM copies are never modified;
+//   b. every (2-bit base, quality) pair becomes a 1-byte code in place;
+//   c. every thread gathers the codes of the segments that cover its own position.
+// No atomics on the counting path: a position's counters live in the registers of exactly one
+// thread, so deep coverage costs instructions in proportion to bases and nothing for contention.
 //
 // Shared memory carve-up (dynamic), all regions 16-byte aligned:
-//   s_meta   4 x (CHUNK_READS+1) u32   pos | q4_off | cig_off | seg_off of the chunk's reads (+1 end)
-//   s_seq    CHUNK_Q4 + 32 bytes       2-bit bases           (TMA destination)
-//   s_qual   4*CHUNK_Q4 + 32 bytes     qualities -> codes    (TMA destination)
-//   s_cig    4*CHUNK_CIGAR + 32 bytes  CIGAR words           (TMA destination)
-//   s_seg    CHUNK_SEGS x 16 bytes     {ref begin, length, byte address of first code, read pos}
-// Codes: 0..3 = A,C,G,T with quality >= 13; 4 = non-ACGT base with quality >= 13; 7 = not counted.
+//   s_meta   5 x META_STRIDE u32      pos | q4_off | cig_off | seg_off | mate of the chunk's reads
+//   s_seq    CHUNK_Q4 + 32 bytes      2-bit bases           (TMA destination)
+//   s_qual   4*CHUNK_Q4 + 32 bytes    qualities -> codes    (TMA destination)
+//   s_cig    4*CHUNK_CIGAR + 32 bytes CIGAR words           (TMA destination)
+//   s_seg    CHUNK_SEGS x 16 bytes    {ref begin, length, byte address of first code, read pos}
+// Codes are shift amounts: 0,8,16,24 = A,C,G,T with quality >= 13 (one byte lane each of the
+// per-chunk accumulator); 32 = non-ACGT base with quality >= 13; 64 = not counted.
 // ------------------------------------------------------------------------------------------------
-constexpr int META_STRIDE = CHUNK_READS + 4;
-constexpr size_t PILEUP_SMEM = 4 * META_STRIDE * 4 + (CHUNK_Q4 + 32) + (4 * CHUNK_Q4 + 32) + (4 * CHUNK_CIGAR + 32) + CHUNK_SEGS * 16 + 64;
+constexpr int META_STRIDE = 260;
+constexpr size_t PILEUP_SMEM = 5 * META_STRIDE * 4 + (CHUNK_Q4 + 32) + (4 * CHUNK_Q4 + 32) + (4 * CHUNK_CIGAR + 32) + CHUNK_SEGS * 16 + 64;
+constexpr uint32_t CODE_N = 32, CODE_SKIP = 64;
 
-__global__ void __launch_bounds__(PILEUP_THREADS, 2)
+__global__ void __launch_bounds__(PILEUP_THREADS, 3)
 pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items,
               uint64_t* __restrict__ acgt /*[n_items][TILE]*/, uint16_t* __restrict__ ncnt /*[n_items][TILE]*/,
               int* __restrict__ err_flag)
@@ -333,7 +285,8 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     uint32_t* s_q4  = s_pos + META_STRIDE;
     uint32_t* s_cgo = s_q4 + META_STRIDE;
     uint32_t* s_sgo = s_cgo + META_STRIDE;
-    uint8_t*  s_seq  = (uint8_t*)(s_sgo + META_STRIDE);
+    int32_t*  s_mate = (int32_t*)(s_sgo + META_STRIDE);
+    uint8_t*  s_seq  = (uint8_t*)(s_mate + META_STRIDE);
     uint8_t*  s_qual = s_seq + CHUNK_Q4 + 32;
     uint8_t*  s_cig  = s_qual + 4 * CHUNK_Q4 + 32;
     uint4*    s_seg  = (uint4*)(s_cig + 4 * CHUNK_CIGAR + 32);
@@ -361,7 +314,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
             s_q4[tid]  = __ldg(sd.q4_off + c0 + tid);
             s_cgo[tid] = __ldg(sd.cig_off + c0 + tid);
             s_sgo[tid] = __ldg(sd.seg_off + c0 + tid);
-            if (tid < n) s_pos[tid] = (uint32_t)__ldg(sd.pos + c0 + tid);
+            if (tid < n) { s_pos[tid] = (uint32_t)__ldg(sd.pos + c0 + tid); s_mate[tid] = __ldg(sd.mate + c0 + tid); }
         }
         if (tid == 0) { s_misc[0] = 0; s_misc[1] = 0; }
         __syncthreads();
@@ -380,7 +333,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
         }
         const uint32_t q4_0 = s_q4[0], nq4 = s_q4[m] - q4_0;
         const uint32_t cg_0 = s_cgo[0], ncg = s_cgo[m] - cg_0;
-        const uint32_t sg_0 = s_sgo[0], nsg = s_sgo[m] - sg_0;
+        const uint32_t sg_0 = s_sgo[0];
 
         // ---- 2. stage sequence, quality and CIGAR bytes: three bulk copies from 16-byte aligned
         // addresses at or below the first byte needed; d_* is the offset of that byte in the buffer
@@ -418,7 +371,51 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                 else if (op == 1 || op == 4) y += len;
             }
             atomicMax(&s_misc[1], (uint32_t)(x - rpos));
+        } else if (tid >= 256 && tid - 256 < m) {
+            // ---- 3a'. mate-overlap quality correction of this read's staged qualities, for the
+            // positions of this tile only (the others are counted by other CTAs). `a` is the mate that
+            // comes first in the file, `b` the later one; with pristine qualities qa, qb at a reference
+            // position both mates align to: same base -> a: min(qa+qb, cap), b: 0; different ->
+            // qa >= qb ? (a: 0.8*qa, b: 0) : (a: 0, b: 0.8*qb).
+            const uint32_t i = tid - 256;
+            const int32_t mt = s_mate[i];
+            if (mt >= 0) {
+                const uint32_t self = c0 + i;
+                const bool self_is_a = self < (uint32_t)mt;
+                const int32_t spos = (int32_t)s_pos[i], mpos = __ldg(sd.pos + mt);
+                const uint32_t mc0 = __ldg(sd.cig_off + mt), mq4 = __ldg(sd.q4_off + mt);
+                CigarWalk ws, wm;
+                ws.init((const uint32_t*)(s_cig + d_cig) + (s_cgo[i] - cg_0), s_cgo[i + 1] - s_cgo[i], spos);
+                wm.init(sd.cigar + mc0, __ldg(sd.cig_off + mt + 1) - mc0, mpos);
+                uint8_t* sq = s_qual + d_qual + (s_q4[i] - q4_0) * 4;
+                const uint8_t* ss = s_seq + d_seq + (s_q4[i] - q4_0);
+                const uint8_t* mq = sd.qual + (size_t)mq4 * 4;
+                const uint8_t* ms = sd.seq2 + mq4;
+                int32_t ref = spos > mpos ? spos : mpos;
+                if (ref < p0) ref = p0;
+                const int32_t ref_end = p0 + TILE;
+                while (ref < ref_end) {
+                    int32_t r1, r2; uint32_t i1, i2;
+                    if (!ws.seek(ref, r1, i1)) break;
+                    if (r1 > ref) ref = r1;
+                    if (!wm.seek(ref, r2, i2)) break;
+                    if (r2 > ref) { ref = r2; continue; }
+                    if (ref >= ref_end) break;
+                    const uint32_t vs = sq[i1], vm = mq[i2];
+                    const uint32_t fs = vs & 0x80u, fm = vm & 0x80u, qs = vs & 0x7fu, qm = vm & 0x7fu;
+                    // "same base" in htslib compares 4-bit codes; non-ACGT codes all collapse to the flag here
+                    const bool same = (fs || fm) ? (fs && fm) : (base2_at(ss, i1) == base2_at(ms, i2));
+                    const uint32_t qa = self_is_a ? qs : qm, qb = self_is_a ? qm : qs;
+                    uint32_t nq;
+                    if (same) { nq = qa + qb; if (nq > 127u) nq = 127u; if (!self_is_a) nq = 0; }
+                    else if (qa >= qb) nq = self_is_a ? (uint32_t)(0.8 * (double)qa) : 0u;
+                    else nq = self_is_a ? 0u : (uint32_t)(0.8 * (double)qb);
+                    sq[i1] = (uint8_t)(fs | nq);
+                    ++ref;
+                }
+            }
         }
+        __syncthreads();
         // ---- 3b. (2-bit base, quality) -> code, in place over the quality bytes, 4 bases per step
         {
             uint32_t* q32 = (uint32_t*)(s_qual + d_qual);         // d_qual is a multiple of 4
@@ -430,9 +427,9 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t qb = (q >> (8 * j)) & 0xffu;
-                    uint32_t code = (b >> (2 * j)) & 3u;
-                    if (qb & 0x80u) code = 4u;
-                    if ((qb & 0x7fu) < 13u) code = 7u;
+                    uint32_t code = ((b >> (2 * j)) & 3u) * 8u;
+                    if (qb & 0x80u) code = CODE_N;
+                    if ((qb & 0x7fu) < 13u) code = CODE_SKIP;
                     out |= code << (8 * j);
                 }
                 q32[g] = out;
@@ -453,15 +450,21 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                 r_last  += __popc(__ballot_sync(0xffffffffu, v < hi_key));
             }
             const uint32_t j_lo = s_sgo[r_first] - sg_0, j_hi = s_sgo[r_last] - sg_0;
+            // per-chunk accumulators: one byte lane per base (a position sees at most m <= 255 reads per
+            // chunk) and the non-ACGT count in units of CODE_N
+            uint32_t a8 = 0, n32 = 0;
+            #pragma unroll 4
             for (uint32_t j = j_lo; j < j_hi; ++j) {
                 const uint4 sg = s_seg[j];                        // same address in every lane: broadcast
                 const uint32_t idx = (uint32_t)(my_pos - (int32_t)sg.x);
-                if (idx < sg.y) {
-                    const uint32_t code = s_qual[sg.z + idx];
-                    acc += shl1_clamped(code * 16u);              // codes >= 4 shift out to 0
-                    acc_n += (code == 4u);
-                }
+                uint32_t code = CODE_SKIP;
+                if (idx < sg.y) code = s_qual[sg.z + idx];
+                a8 += shl1_clamped32(code);                       // codes >= 32 shift out to 0
+                n32 += code & CODE_N;
             }
+            acc += (uint64_t)(a8 & 0xffu) | (uint64_t)((a8 >> 8) & 0xffu) << 16 | (uint64_t)((a8 >> 16) & 0xffu) << 32 |
+                   (uint64_t)(a8 >> 24) << 48;
+            acc_n += n32 / CODE_N;
         }
         c0 += m;
         __syncthreads();                    // everyone is done with the buffers before they are refilled

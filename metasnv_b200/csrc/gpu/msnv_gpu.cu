@@ -20,15 +20,13 @@ struct msnv_ctx {
     std::string err;
 
     // ---- shard state
-    bool open = false, quals_saved = false, has_run = false;
+    bool open = false, has_run = false;
     uint32_t S = 0, P = 0, n_tiles = 0;
     std::vector<SampleDev> h_samples;
-    std::vector<uint32_t> pair_base;           // [S+1]
     std::vector<void*> sample_allocs;
     std::vector<msnv_sample_sizes> sizes;      // [S]
     uint64_t n_reads = 0, n_bases = 0;
     SampleDev* d_samples = nullptr;
-    uint32_t* d_pair_base = nullptr;
     uint8_t* d_ref = nullptr;
 
     // ---- work buffers (grown on demand, kept across shards)
@@ -210,7 +208,7 @@ void msnv_destroy(msnv_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_samples(ctx);
-    cudaFree(ctx->d_samples); cudaFree(ctx->d_pair_base); cudaFree(ctx->d_ref);
+    cudaFree(ctx->d_samples); cudaFree(ctx->d_ref);
     cudaFree(ctx->d_items); cudaFree(ctx->d_acgt); cudaFree(ctx->d_ncnt);
     cudaFree(ctx->d_tile_begin); cudaFree(ctx->d_tile_hits); cudaFree(ctx->d_flags); cudaFree(ctx->d_block_sums);
     cudaFree(ctx->d_scalar); cudaFree(ctx->d_err);
@@ -245,14 +243,12 @@ int msnv_shard_begin(msnv_ctx* ctx, uint32_t n_samples, uint32_t n_positions, co
     free_samples(ctx);
     ctx->S = n_samples; ctx->P = n_positions; ctx->n_tiles = n_positions / TILE;
     ctx->h_samples.assign(n_samples, SampleDev{});
-    ctx->pair_base.assign(n_samples + 1, 0);
     ctx->sizes.assign(n_samples, msnv_sample_sizes{});
     ctx->n_reads = ctx->n_bases = 0;
-    ctx->quals_saved = ctx->has_run = false;
-    cudaFree(ctx->d_samples); cudaFree(ctx->d_pair_base); cudaFree(ctx->d_ref);
-    ctx->d_samples = nullptr; ctx->d_pair_base = nullptr; ctx->d_ref = nullptr;
+    ctx->has_run = false;
+    cudaFree(ctx->d_samples); cudaFree(ctx->d_ref);
+    ctx->d_samples = nullptr; ctx->d_ref = nullptr;
     CU(cudaMalloc((void**)&ctx->d_samples, sizeof(SampleDev) * n_samples));
-    CU(cudaMalloc((void**)&ctx->d_pair_base, 4 * ((size_t)n_samples + 1)));
     CU(cudaMalloc((void**)&ctx->d_ref, n_positions));
     CU(cudaMemcpyAsync(ctx->d_ref, ref, n_positions, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->n_tiles + 1 > ctx->cap_tiles) {
@@ -275,23 +271,13 @@ int msnv_shard_add_sample(msnv_ctx* ctx, uint32_t sample, const msnv_sample_read
     if (r->max_span > 8u * MSNV_MAX_READ_BASES) return fail(ctx, MSNV_E_LIMIT, "sample %u: reference span %u exceeds the limit", sample, r->max_span);
     CU(cudaSetDevice(ctx->device));
     const size_t n = r->n_reads, n1 = n + 1;
-    const size_t n_cig = r->cig_off[n], n_q4 = r->q4_off[n], np = r->n_pairs;
-    // backup offsets of the overlapping pairs (bytes): qualities of both mates, 4-byte groups
-    std::vector<uint32_t> bk(np + 1, 0);
-    for (size_t i = 0; i < np; ++i) {
-        const uint32_t b = r->pair_b[i];
-        if (b >= n || r->mate[b] < 0 || (uint32_t)r->mate[b] >= b)
-            return fail(ctx, MSNV_E_ARG, "sample %u: pair_b[%zu] does not name a read with an earlier mate", sample, i);
-        const uint32_t a = (uint32_t)r->mate[b];
-        bk[i + 1] = bk[i] + 4u * ((r->q4_off[a + 1] - r->q4_off[a]) + (r->q4_off[b + 1] - r->q4_off[b]));
-    }
-    // one allocation per sample, sub-arrays 256-byte aligned, 32 spare bytes behind the byte arrays
+    const size_t n_cig = r->cig_off[n], n_q4 = r->q4_off[n];
+    // one allocation per sample, sub-arrays 256-byte aligned, 32 spare bytes behind every array
     // because the pileup kernel's bulk copies read whole 16-byte units
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes + 32, 256); return o; };
     const size_t o_pos = take(n * 4), o_cgo = take(n1 * 4), o_sgo = take(n1 * 4), o_q4 = take(n1 * 4), o_mate = take(n * 4),
-                 o_pb = take(np * 4), o_pbk = take((np + 1) * 4), o_cig = take(n_cig * 4), o_seq = take(n_q4), o_qual = take(n_q4 * 4),
-                 o_bk = take(bk[np]);
+                 o_cig = take(n_cig * 4), o_seq = take(n_q4), o_qual = take(n_q4 * 4);
     uint8_t* base = nullptr;
     cudaError_t e = cudaMalloc((void**)&base, off);
     if (e != cudaSuccess) return fail(ctx, MSNV_E_NOMEM, "sample %u: cudaMalloc(%zu) failed: %s", sample, off, cudaGetErrorString(e));
@@ -302,10 +288,6 @@ int msnv_shard_add_sample(msnv_ctx* ctx, uint32_t sample, const msnv_sample_read
     CU(cudaMemcpyAsync(base + o_sgo, r->seg_off, n1 * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_q4, r->q4_off, n1 * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_mate, r->mate, n * 4, cudaMemcpyHostToDevice, st));
-    if (np) CU(cudaMemcpyAsync(base + o_pb, r->pair_b, np * 4, cudaMemcpyHostToDevice, st));
-    // bk is a temporary: copy it synchronously with respect to the host (pageable source)
-    CU(cudaMemcpyAsync(base + o_pbk, bk.data(), (np + 1) * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));
     if (n_cig) CU(cudaMemcpyAsync(base + o_cig, r->cigar, n_cig * 4, cudaMemcpyHostToDevice, st));
     if (n_q4) {
         CU(cudaMemcpyAsync(base + o_seq, r->seq2, n_q4, cudaMemcpyHostToDevice, st));
@@ -316,11 +298,9 @@ int msnv_shard_add_sample(msnv_ctx* ctx, uint32_t sample, const msnv_sample_read
     d.seg_off = (const uint32_t*)(base + o_sgo); d.q4_off = (const uint32_t*)(base + o_q4);
     d.mate = (const int32_t*)(base + o_mate);   d.cigar = (const uint32_t*)(base + o_cig);
     d.seq2 = base + o_seq;                      d.qual = base + o_qual;
-    d.pair_b = (const uint32_t*)(base + o_pb);  d.pair_bk = (const uint32_t*)(base + o_pbk);
-    d.backup = base + o_bk;
-    d.n_reads = r->n_reads; d.max_span = r->max_span ? r->max_span : 1; d.n_pairs = r->n_pairs; d.pad_ = 0;
+    d.n_reads = r->n_reads; d.max_span = r->max_span ? r->max_span : 1;
     ctx->n_reads += n; ctx->n_bases += 4ull * n_q4;
-    ctx->sizes[sample] = msnv_sample_sizes{r->n_reads, r->n_pairs, d.max_span, 0, (uint64_t)n_cig, (uint64_t)n_q4};
+    ctx->sizes[sample] = msnv_sample_sizes{r->n_reads, 0, d.max_span, 0, (uint64_t)n_cig, (uint64_t)n_q4};
     return MSNV_OK;
 }
 
@@ -352,12 +332,7 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
     memset(hits, 0, sizeof *hits);
     hits->n_samples = S;
 
-    uint64_t pairs_total = 0;
-    for (uint32_t s = 0; s < S; ++s) { ctx->pair_base[s] = (uint32_t)pairs_total; pairs_total += ctx->h_samples[s].n_pairs; }
-    if (pairs_total > 0xffffffffull) return fail(ctx, MSNV_E_LIMIT, "more than 2^32 overlapping pairs in one shard");
-    ctx->pair_base[S] = (uint32_t)pairs_total;
     CU(cudaMemcpyAsync(ctx->d_samples, ctx->h_samples.data(), sizeof(SampleDev) * S, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->d_pair_base, ctx->pair_base.data(), 4 * ((size_t)S + 1), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(ctx->d_err, 0, 4, st));
 
     CU(cudaEventRecord(ctx->ev[0], st));
@@ -379,15 +354,6 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
     CU(cudaMemcpyAsync(ctx->d_tile_begin + n_tiles, ctx->d_scalar, 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaEventRecord(ctx->ev[1], st));
 
-    // ---- mate-overlap quality correction (restores pristine qualities first on repeated runs)
-    if (pairs_total) {
-        const unsigned g = (unsigned)((pairs_total + 127) / 128);
-        if (!ctx->quals_saved) overlap_kernel<0><<<g, 128, 0, st>>>(ctx->d_samples, ctx->d_pair_base, S, pairs_total);
-        else                   overlap_kernel<1><<<g, 128, 0, st>>>(ctx->d_samples, ctx->d_pair_base, S, pairs_total);
-        overlap_kernel<2><<<g, 128, 0, st>>>(ctx->d_samples, ctx->d_pair_base, S, pairs_total);
-        ctx->quals_saved = true;
-        launches += 2;
-    }
     CU(cudaEventRecord(ctx->ev[2], st));
 
     // ---- pileup
@@ -402,7 +368,7 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
 
     msnv_timings& tm = ctx->tm;
     cudaEventElapsedTime(&tm.ms_index, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&tm.ms_overlap, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&tm.ms_reserved, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&tm.ms_pileup, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&tm.ms_call, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&tm.ms_compact, ctx->ev[4], ctx->ev[5]);
@@ -492,18 +458,18 @@ int msnv_shard_synth(msnv_ctx* ctx, const msnv_synth_desc* d, int64_t* first_col
         const bool overlap = paired && D < (int32_t)L;
         const uint32_t span = msnv::synth::frag_span(m, paired, D);
         blocks.clear(); frag0.assign(1, 0);
-        uint64_t n_reads = 0, n_pairs = 0;
+        uint64_t n_reads = 0, n_mated = 0;
         for (uint32_t k = 0; k < K; ++k) {
             const uint32_t g = d->contig_genome[k];
             if (g >= d->n_genomes) return fail(ctx, MSNV_E_ARG, "msnv_shard_synth: contig_genome out of range");
             if (!msnv::synth::sample_has_genome(m, (int)s, (int)g) || d->contig_len[k] <= span) continue;
             const uint32_t nf = msnv::synth::n_fragments(m, d->contig_len[k], paired);
             if (!nf) continue;
-            SynthSampleCtg b{k, d->contig_len[k], off[k], g, d->genome_n_sub[g], nf, (uint32_t)n_reads, (uint32_t)n_pairs};
+            SynthSampleCtg b{k, d->contig_len[k], off[k], g, d->genome_n_sub[g], nf, (uint32_t)n_reads};
             blocks.push_back(b);
             frag0.push_back(frag0.back() + nf);
             n_reads += (uint64_t)nf * (paired ? 2 : 1);
-            if (overlap) n_pairs += nf;
+            if (overlap) n_mated += 2ull * nf;
             if (n_reads > 0x7fffffffull) return fail(ctx, MSNV_E_LIMIT, "msnv_shard_synth: more than 2^31 reads in one sample");
         }
         if (blocks.empty()) continue;
@@ -512,12 +478,11 @@ int msnv_shard_synth(msnv_ctx* ctx, const msnv_synth_desc* d, int64_t* first_col
             const int64_t c = (int64_t)b.offset + msnv::synth::frag_start(m, (int)s, b.ctg, b.len, span, b.n_frag, 0);
             if (first_col < 0 || c < first_col) first_col = c;
         }
-        const size_t n = (size_t)n_reads, n1 = n + 1, np = (size_t)n_pairs, nb = blocks.size(), nft = frag0.back();
+        const size_t n = (size_t)n_reads, n1 = n + 1, nb = blocks.size(), nft = frag0.back();
         // ---- phase 1: per-read metadata
         size_t o = 0;
         auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes + 32, 256); return r; };
-        const size_t o_pos = take(n * 4), o_cgo = take(n1 * 4), o_sgo = take(n1 * 4), o_q4 = take(n1 * 4), o_mate = take(n * 4),
-                     o_pb = take(np * 4), o_pbk = take((np + 1) * 4);
+        const size_t o_pos = take(n * 4), o_cgo = take(n1 * 4), o_sgo = take(n1 * 4), o_q4 = take(n1 * 4), o_mate = take(n * 4);
         uint8_t* meta = nullptr;
         if (cudaMalloc((void**)&meta, o) != cudaSuccess) return fail(ctx, MSNV_E_NOMEM, "msnv_shard_synth: out of device memory (sample %u)", s);
         ctx->sample_allocs.push_back(meta);
@@ -530,9 +495,8 @@ int msnv_shard_synth(msnv_ctx* ctx, const msnv_synth_desc* d, int64_t* first_col
         CU(cudaMemcpyAsync(d_blocks, blocks.data(), nb * sizeof(SynthSampleCtg), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_frag0, frag0.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, st));
         synth_meta_kernel<<<(unsigned)((nft + 127) / 128), 128, 0, st>>>(m, (int)s, paired, D, overlap, d_blocks, d_frag0, (uint32_t)nb, (uint32_t)nft,
-            (int32_t*)(meta + o_pos), d_nops, d_nsegs, (uint32_t*)(meta + o_q4), (int32_t*)(meta + o_mate), (uint32_t*)(meta + o_pb),
-            (uint32_t*)(meta + o_pbk), d_for);
-        synth_tail_kernel<<<1, 1, 0, st>>>((uint32_t)n, q4, (uint32_t)np, (uint32_t*)(meta + o_q4), (uint32_t*)(meta + o_pbk));
+            (int32_t*)(meta + o_pos), d_nops, d_nsegs, (uint32_t*)(meta + o_q4), (int32_t*)(meta + o_mate), d_for);
+        synth_tail_kernel<<<1, 1, 0, st>>>((uint32_t)n, q4, (uint32_t*)(meta + o_q4));
         synth_scan2_kernel<<<1, 1024, 0, st>>>(d_nops, d_nsegs, (uint32_t)n, (uint32_t*)(meta + o_cgo), (uint32_t*)(meta + o_sgo));
         uint32_t n_cig = 0;
         CU(cudaMemcpyAsync(&n_cig, meta + o_cgo + n * 4, 4, cudaMemcpyDeviceToHost, st));
@@ -540,7 +504,7 @@ int msnv_shard_synth(msnv_ctx* ctx, const msnv_synth_desc* d, int64_t* first_col
         // ---- phase 2: CIGARs, bases, qualities
         const size_t n_q4 = n * q4;
         o = 0;
-        const size_t o_cig = take((size_t)n_cig * 4), o_seq = take(n_q4), o_qual = take(n_q4 * 4), o_bk = take(np * 8 * q4);
+        const size_t o_cig = take((size_t)n_cig * 4), o_seq = take(n_q4), o_qual = take(n_q4 * 4);
         uint8_t* data = nullptr;
         if (cudaMalloc((void**)&data, o) != cudaSuccess) return fail(ctx, MSNV_E_NOMEM, "msnv_shard_synth: out of device memory (sample %u)", s);
         ctx->sample_allocs.push_back(data);
@@ -554,11 +518,9 @@ int msnv_shard_synth(msnv_ctx* ctx, const msnv_synth_desc* d, int64_t* first_col
         sd.seg_off = (const uint32_t*)(meta + o_sgo); sd.q4_off = (const uint32_t*)(meta + o_q4);
         sd.mate = (const int32_t*)(meta + o_mate);   sd.cigar = (const uint32_t*)(data + o_cig);
         sd.seq2 = data + o_seq;                      sd.qual = data + o_qual;
-        sd.pair_b = (const uint32_t*)(meta + o_pb);  sd.pair_bk = (const uint32_t*)(meta + o_pbk);
-        sd.backup = data + o_bk;
-        sd.n_reads = (uint32_t)n; sd.max_span = L + 3; sd.n_pairs = (uint32_t)np; sd.pad_ = 0;
+        sd.n_reads = (uint32_t)n; sd.max_span = L + 3;
         ctx->n_reads += n; ctx->n_bases += 4ull * n_q4;
-        ctx->sizes[s] = msnv_sample_sizes{(uint32_t)n, (uint32_t)np, L + 3, 0, (uint64_t)n_cig, (uint64_t)n_q4};
+        ctx->sizes[s] = msnv_sample_sizes{(uint32_t)n, (uint32_t)n_mated, L + 3, 0, (uint64_t)n_cig, (uint64_t)n_q4};
     }
     if (first_column) *first_column = first_col;
     return MSNV_OK;
@@ -573,11 +535,10 @@ int msnv_shard_sample_sizes(msnv_ctx* ctx, uint32_t sample, msnv_sample_sizes* s
 }
 
 int msnv_shard_export_sample(msnv_ctx* ctx, uint32_t sample, int32_t* pos, uint32_t* cig_off, uint32_t* seg_off, uint32_t* q4_off,
-                             int32_t* mate, uint32_t* pair_b, uint32_t* cigar, uint8_t* seq2, uint8_t* qual)
+                             int32_t* mate, uint32_t* cigar, uint8_t* seq2, uint8_t* qual)
 {
     if (!ctx) return MSNV_E_ARG;
     if (!ctx->open || sample >= ctx->S) return fail(ctx, MSNV_E_ARG, "msnv_shard_export_sample: no such sample");
-    if (ctx->quals_saved) return fail(ctx, MSNV_E_STATE, "msnv_shard_export_sample: export before the first run (qualities are corrected in place)");
     const msnv_sample_sizes z = ctx->sizes[sample];
     if (z.n_reads == 0) return MSNV_OK;
     CU(cudaSetDevice(ctx->device));
@@ -589,7 +550,6 @@ int msnv_shard_export_sample(msnv_ctx* ctx, uint32_t sample, int32_t* pos, uint3
     CU(cudaMemcpyAsync(seg_off, d.seg_off, n1 * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(q4_off, d.q4_off, n1 * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(mate, d.mate, n * 4, cudaMemcpyDeviceToHost, st));
-    if (z.n_pairs) CU(cudaMemcpyAsync(pair_b, d.pair_b, (size_t)z.n_pairs * 4, cudaMemcpyDeviceToHost, st));
     if (z.n_cigar) CU(cudaMemcpyAsync(cigar, d.cigar, (size_t)z.n_cigar * 4, cudaMemcpyDeviceToHost, st));
     if (z.n_q4) {
         CU(cudaMemcpyAsync(seq2, d.seq2, (size_t)z.n_q4, cudaMemcpyDeviceToHost, st));

@@ -19,7 +19,6 @@ struct SynthSampleCtg {          // one (sample, contig) block with reads
     uint32_t genome, n_sub;
     uint32_t n_frag;
     uint32_t read0;              // first read (rank) of the block within the sample
-    uint32_t pair0;              // first pair of the block within the sample
 };
 
 __device__ __forceinline__ uint32_t block_of(const uint32_t* __restrict__ starts, uint32_t n, uint32_t v)
@@ -57,8 +56,7 @@ __device__ __forceinline__ uint32_t count_starts_below(const Model& m, int sampl
 __global__ void synth_meta_kernel(Model m, int sample, bool paired, int32_t D, bool overlap, const SynthSampleCtg* __restrict__ blocks,
                                   const uint32_t* __restrict__ frag0 /*[n_blocks+1]*/, uint32_t n_blocks, uint32_t n_frag_total,
                                   int32_t* __restrict__ pos, uint32_t* __restrict__ n_ops, uint32_t* __restrict__ n_segs,
-                                  uint32_t* __restrict__ q4_off, int32_t* __restrict__ mate, uint32_t* __restrict__ pair_b,
-                                  uint32_t* __restrict__ pair_bk, uint32_t* __restrict__ frag_of_rank)
+                                  uint32_t* __restrict__ q4_off, int32_t* __restrict__ mate, uint32_t* __restrict__ frag_of_rank)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_frag_total) return;
@@ -82,19 +80,14 @@ __global__ void synth_meta_kernel(Model m, int sample, bool paired, int32_t D, b
         for (int o = 0; o < sh.n_ops; ++o) ns += (sh.ops[o] & 0xf) == 0;
         n_segs[r] = ns;
         q4_off[r] = r * q4;
-        mate[r] = (k == 1 && overlap) ? (int32_t)r1 : -1;
+        mate[r] = overlap ? (int32_t)(k == 1 ? r1 : r2) : -1;
         frag_of_rank[r] = (g << 1) | (uint32_t)k;
-    }
-    if (paired && overlap) {
-        pair_b[b.pair0 + f] = r2;
-        pair_bk[b.pair0 + f] = (b.pair0 + f) * (8u * q4);
     }
 }
 
-__global__ void synth_tail_kernel(uint32_t n_reads, uint32_t q4, uint32_t n_pairs, uint32_t* __restrict__ q4_off, uint32_t* __restrict__ pair_bk)
+__global__ void synth_tail_kernel(uint32_t n_reads, uint32_t q4, uint32_t* __restrict__ q4_off)
 {
     q4_off[n_reads] = n_reads * q4;
-    pair_bk[n_pairs] = n_pairs * 8u * q4;
 }
 
 // One thread per (read, 4-base group): bases, qualities and (group 0) the CIGAR words.

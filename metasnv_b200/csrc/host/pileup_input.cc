@@ -127,15 +127,14 @@ msnv_sample_reads SampleReads::view() const
     memset(&v, 0, sizeof v);
     v.n_reads = (uint32_t)pos.size();
     v.max_span = max_span;
-    v.n_pairs = (uint32_t)pair_b.size();
     v.pos = pos.data(); v.cig_off = cig_off.data(); v.seg_off = seg_off.data(); v.q4_off = q4_off.data();
-    v.mate = mate.data(); v.pair_b = pair_b.data(); v.cigar = cigar.data(); v.seq2 = seq2.data(); v.qual = qual.data();
+    v.mate = mate.data(); v.cigar = cigar.data(); v.seq2 = seq2.data(); v.qual = qual.data();
     return v;
 }
 
 size_t SampleReads::bytes() const
 {
-    return pos.size() * 4 + cig_off.size() * 4 + seg_off.size() * 4 + q4_off.size() * 4 + mate.size() * 4 + pair_b.size() * 4 +
+    return pos.size() * 4 + cig_off.size() * 4 + seg_off.size() * 4 + q4_off.size() * 4 + mate.size() * 4 +
            cigar.size() * 4 + seq2.size() + qual.size();
 }
 
@@ -248,7 +247,7 @@ bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& la
         const ShardLayout::Ctg& ctg = layout.ctgs[slot];
         out.pos.push_back((int32_t)(ctg.offset + (uint32_t)c.pos));
         out.mate.push_back(mate_idx);
-        if (mate_idx >= 0) { out.pair_b.push_back(idx); ++st.pairs; }
+        if (mate_idx >= 0) { out.mate[(size_t)mate_idx] = (int32_t)idx; ++st.pairs; }
         for (int i = 0; i < c.n_cigar; ++i) out.cigar.push_back(r.cigar_at(i));
         out.cig_off.push_back((uint32_t)out.cigar.size());
         out.seg_off.push_back(out.seg_off.back() + n_seg);

@@ -51,7 +51,7 @@ struct SampleReads {
     std::vector<int32_t>  pos;
     std::vector<uint32_t> cig_off{0}, seg_off{0}, q4_off{0};
     std::vector<int32_t>  mate;
-    std::vector<uint32_t> pair_b, cigar;
+    std::vector<uint32_t> cigar;
     std::vector<uint8_t>  seq2, qual;
     uint32_t max_span = 0;
     msnv_sample_reads view() const;

@@ -28,12 +28,12 @@ def test_abi_exports_every_declared_symbol(built):
     for n in sorted(names):
         assert hasattr(lib, n), "libmsnv_gpu.so does not export %s" % n
     lib.msnv_abi_version.restype = ctypes.c_int
-    assert lib.msnv_abi_version() == 1
+    assert lib.msnv_abi_version() == 2
 
 
 def test_abi_python_binding_matches_struct_sizes(built):
     from metasnv_b200 import abi
-    assert ctypes.sizeof(abi.SampleReads) == 16 + 9 * 8
+    assert ctypes.sizeof(abi.SampleReads) == 16 + 8 * 8
     assert ctypes.sizeof(abi.CallParams) == 16
     assert ctypes.sizeof(abi.Hits) == 8 + 6 * 8
     assert ctypes.sizeof(abi.CovBlocks) == 8 + 4 * 8
