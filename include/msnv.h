@@ -29,10 +29,12 @@ extern "C" {
 
 /* Positions per tile: contigs of a shard are laid out back to back in a "shard coordinate" space,
  * each starting at a multiple of MSNV_TILE, so a tile never spans two contigs. */
+#ifndef MSNV_TILE
 #define MSNV_TILE 512
+#endif
 /* Limits of the tiled pileup kernel (longer reads are rejected with MSNV_E_LIMIT). */
-#define MSNV_MAX_READ_BASES 8192
-#define MSNV_MAX_READ_CIGAR 256
+#define MSNV_MAX_READ_BASES 4096
+#define MSNV_MAX_READ_CIGAR 128
 
 typedef enum {
     MSNV_OK = 0,
@@ -110,6 +112,7 @@ typedef struct {
 } msnv_timings;
 
 int         msnv_abi_version(void);
+int         msnv_tile(void);              /* MSNV_TILE the library was built with */
 int         msnv_device_count(void);
 int         msnv_create(int device, msnv_ctx** out);
 void        msnv_destroy(msnv_ctx* ctx);

@@ -10,7 +10,7 @@ import numpy as np
 
 from .paths import lib_path
 
-TILE = 512
+TILE = 512          # replaced by the library's own value on load()
 
 
 class MsnvError(RuntimeError):
@@ -69,6 +69,9 @@ def load():
         raise MsnvError("%s is missing: run `python __graft_entry__.py` (build) first" % p)
     lib = C.CDLL(p)
     lib.msnv_abi_version.restype = C.c_int
+    lib.msnv_tile.restype = C.c_int
+    global TILE
+    TILE = lib.msnv_tile()
     lib.msnv_device_count.restype = C.c_int
     lib.msnv_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.msnv_destroy.argtypes = [C.c_void_p]

@@ -21,13 +21,13 @@ namespace msnv_gpu {
 
 constexpr int TILE = MSNV_TILE;                 // positions per tile == threads per pileup CTA
 constexpr int PILEUP_THREADS = TILE;
-constexpr int CHUNK_READS = 255;                // reads staged per chunk (at most; 8-bit per-chunk counters)
-constexpr int CHUNK_Q4 = 4096;                  // 4-base groups staged per chunk (16384 bases)
-constexpr int CHUNK_CIGAR = 1024;               // CIGAR words staged per chunk
-constexpr int CHUNK_SEGS = 1024;                // aligned segments per chunk
+constexpr int CHUNK_READS = TILE / 2 - 1 < 255 ? TILE / 2 - 1 : 255;   // reads staged per chunk (8-bit per-chunk counters;
+                                                                       // the second half of the CTA corrects mate overlaps)
+constexpr int CHUNK_Q4 = TILE * 8;              // 4-base groups staged per chunk (TILE*32 bases)
+constexpr int CHUNK_SEGS = TILE * 2;            // aligned segments per chunk
 
 static_assert(MSNV_MAX_READ_BASES * 2 <= CHUNK_Q4 * 4, "one read must fit a chunk with room to spare");
-static_assert(MSNV_MAX_READ_CIGAR * 2 <= CHUNK_CIGAR, "one read's CIGAR must fit a chunk");
+static_assert(MSNV_MAX_READ_CIGAR * 2 <= CHUNK_SEGS, "one read's segments must fit a chunk");
 
 struct SampleDev {
     const int32_t*  pos;
@@ -216,32 +216,8 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ v, ui
 }
 
 // ------------------------------------------------------------------------------------------------
-// CIGAR cursor shared by the overlap correction: walks to aligned (M/=/X) reference coordinates.
+// helpers of the pileup kernel
 // ------------------------------------------------------------------------------------------------
-struct CigarWalk {
-    const uint32_t* c; uint32_t n, k; int32_t x; uint32_t y;     // x: reference coordinate, y: query offset
-    __device__ void init(const uint32_t* cig, uint32_t n_ops, int32_t pos) { c = cig; n = n_ops; k = 0; x = pos; y = 0; }
-    // smallest aligned reference coordinate >= want; false when the read is exhausted
-    __device__ bool seek(int32_t want, int32_t& ref, uint32_t& q)
-    {
-        while (k < n) {
-            const uint32_t w = c[k], op = w & 0xf; const int32_t len = (int32_t)(w >> 4);
-            if (op == 0 || op == 7 || op == 8) {
-                if (want < x + len) { ref = want > x ? want : x; q = y + (uint32_t)(ref - x); return true; }
-                x += len; y += (uint32_t)len;
-            } else if (op == 2 || op == 3) x += len;
-            else if (op == 1 || op == 4) y += (uint32_t)len;
-            ++k;
-        }
-        return false;
-    }
-};
-
-__device__ __forceinline__ uint32_t base2_at(const uint8_t* seq2, uint32_t q)
-{
-    return (seq2[q >> 2] >> ((q & 3) * 2)) & 3;
-}
-
 // 1 << s with PTX clamping semantics (s >= 32 gives 0)
 __device__ __forceinline__ uint32_t shl1_clamped32(uint32_t s)
 {
@@ -250,32 +226,49 @@ __device__ __forceinline__ uint32_t shl1_clamped32(uint32_t s)
     return r;
 }
 
+constexpr uint32_t CODE_N = 32, CODE_SKIP = 64;
+
+// mpileup's mate-overlap rule (htslib tweak_overlap_quality, SURVEY.md Annex A.2) for one reference
+// position that both mates align to. va/vb: staged quality bytes (bit 7: non-ACGT base) of the mate
+// that comes first in the file (a) and of the later one (b); same: the two bases are equal.
+// Qualities live in 7 bits, so htslib's cap of 200 becomes 127: only "q >= 13" is ever used.
+__device__ __forceinline__ void overlap_rule(uint32_t va, uint32_t vb, bool same, uint32_t& na, uint32_t& nb)
+{
+    const uint32_t fa = va & 0x80u, fb = vb & 0x80u, qa = va & 0x7fu, qb = vb & 0x7fu;
+    if (same) { uint32_t q = qa + qb; if (q > 127u) q = 127u; na = fa | q; nb = fb; }
+    else if (qa >= qb) { na = fa | (uint32_t)(0.8 * (double)qa); nb = fb; }
+    else { na = fa; nb = fb | (uint32_t)(0.8 * (double)qb); }
+}
+
 // ------------------------------------------------------------------------------------------------
 // pileup: one CTA per work item (sample, tile); thread i owns position tile*TILE + i.
-// Reads are staged chunk by chunk into shared memory with TMA bulk copies; then, per chunk:
-//   a. threads 0..m-1 walk one read's CIGAR each into aligned segments;
-//      threads 256..256+m-1 apply mpileup's mate-overlap quality correction (htslib
-//      tweak_overlap_quality, SURVEY.md Annex A.2) to their own read's staged qualities, reading the
-//      mate's pristine bases/qualities from global memory -- HBM copies are never modified;
-//   b. every (2-bit base, quality) pair becomes a 1-byte code in place;
-//   c. every thread gathers the codes of the segments that cover its own position.
+// Per chunk of reads (<= CHUNK_READS reads, CHUNK_Q4*4 bases, CHUNK_SEGS aligned segments):
+//   1. metadata of the chunk's reads -> shared memory; __syncthreads_count sizes the chunk
+//   2. two TMA bulk copies (2-bit bases, qualities) are issued; while they fly,
+//   3. one thread per read walks its CIGAR (global, L2) into aligned segments
+//   4. mate-overlap quality correction in shared memory, one warp per pair, lanes over positions
+//      (mates staged in another chunk are read, pristine, from global memory)
+//   5. (2-bit base, quality) -> 1-byte code in place, four bases per word with SWAR arithmetic
+//   6. every thread gathers the codes of the segments that cover its own position
 // No atomics on the counting path: a position's counters live in the registers of exactly one
 // thread, so deep coverage costs instructions in proportion to bases and nothing for contention.
+// The reads in HBM are never modified.
 //
-// Shared memory carve-up (dynamic), all regions 16-byte aligned:
-//   s_meta   5 x META_STRIDE u32      pos | q4_off | cig_off | seg_off | mate of the chunk's reads
+// Shared memory (dynamic), regions 16-byte aligned:
+//   s_meta   4 x META_STRIDE u32      pos | q4_off | seg_off | mate of the chunk's reads
 //   s_seq    CHUNK_Q4 + 32 bytes      2-bit bases           (TMA destination)
 //   s_qual   4*CHUNK_Q4 + 32 bytes    qualities -> codes    (TMA destination)
-//   s_cig    4*CHUNK_CIGAR + 32 bytes CIGAR words           (TMA destination)
-//   s_seg    CHUNK_SEGS x 16 bytes    {ref begin, length, byte address of first code, read pos}
+//   s_seg    CHUNK_SEGS x 16 bytes    {ref begin, length, byte address of first code, read index}
 // Codes are shift amounts: 0,8,16,24 = A,C,G,T with quality >= 13 (one byte lane each of the
 // per-chunk accumulator); 32 = non-ACGT base with quality >= 13; 64 = not counted.
 // ------------------------------------------------------------------------------------------------
 constexpr int META_STRIDE = 260;
-constexpr size_t PILEUP_SMEM = 5 * META_STRIDE * 4 + (CHUNK_Q4 + 32) + (4 * CHUNK_Q4 + 32) + (4 * CHUNK_CIGAR + 32) + CHUNK_SEGS * 16 + 64;
-constexpr uint32_t CODE_N = 32, CODE_SKIP = 64;
+constexpr size_t PILEUP_SMEM = 4 * META_STRIDE * 4 + (CHUNK_Q4 + 32) + (4 * CHUNK_Q4 + 32) + CHUNK_SEGS * 16 + 64;
 
-__global__ void __launch_bounds__(PILEUP_THREADS, 3)
+#ifndef MSNV_PILEUP_MIN_CTAS
+#define MSNV_PILEUP_MIN_CTAS (TILE >= 512 ? 3 : 6)
+#endif
+__global__ void __launch_bounds__(PILEUP_THREADS, MSNV_PILEUP_MIN_CTAS)
 pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items,
               uint64_t* __restrict__ acgt /*[n_items][TILE]*/, uint16_t* __restrict__ ncnt /*[n_items][TILE]*/,
               int* __restrict__ err_flag)
@@ -283,17 +276,15 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* s_pos = (uint32_t*)smem;
     uint32_t* s_q4  = s_pos + META_STRIDE;
-    uint32_t* s_cgo = s_q4 + META_STRIDE;
-    uint32_t* s_sgo = s_cgo + META_STRIDE;
+    uint32_t* s_sgo = s_q4 + META_STRIDE;
     int32_t*  s_mate = (int32_t*)(s_sgo + META_STRIDE);
     uint8_t*  s_seq  = (uint8_t*)(s_mate + META_STRIDE);
     uint8_t*  s_qual = s_seq + CHUNK_Q4 + 32;
-    uint8_t*  s_cig  = s_qual + 4 * CHUNK_Q4 + 32;
-    uint4*    s_seg  = (uint4*)(s_cig + 4 * CHUNK_CIGAR + 32);
+    uint4*    s_seg  = (uint4*)(s_qual + 4 * CHUNK_Q4 + 32);
     uint64_t* s_bar  = (uint64_t*)(s_seg + CHUNK_SEGS);
-    uint32_t* s_misc = (uint32_t*)(s_bar + 1);        // [0] reads in chunk, [1] max span in chunk
+    uint32_t* s_misc = (uint32_t*)(s_bar + 1);        // [1] max span in chunk
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const Item it = items[blockIdx.x];
     const SampleDev sd = samples[it.sample];
     const int32_t p0 = (int32_t)(it.tile * TILE);
@@ -301,143 +292,154 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     const int32_t warp_lo = p0 + (int32_t)(tid & ~31u);          // first position owned by this warp
 
     if (tid == 0) { mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    __syncthreads();
 
     uint64_t acc = 0;       // A | C<<16 | G<<32 | T<<48
     uint32_t acc_n = 0;
     uint32_t parity = 0;
 
     for (uint32_t c0 = it.r_lo; c0 < it.r_hi;) {
-        // ---- 1. read metadata of up to CHUNK_READS reads (+1 for the end offsets)
+        // ---- 1. metadata of up to CHUNK_READS reads (+1 for the end offsets); the chunk takes the
+        // longest prefix within the byte and segment budgets (prefix sums: the predicate is monotone)
         uint32_t n = it.r_hi - c0; if (n > CHUNK_READS) n = CHUNK_READS;
+        const uint32_t q4_0 = __ldg(sd.q4_off + c0), sg_0 = __ldg(sd.seg_off + c0);
+        bool fits = false;
         if (tid <= n) {
-            s_q4[tid]  = __ldg(sd.q4_off + c0 + tid);
-            s_cgo[tid] = __ldg(sd.cig_off + c0 + tid);
-            s_sgo[tid] = __ldg(sd.seg_off + c0 + tid);
+            const uint32_t q = __ldg(sd.q4_off + c0 + tid), g = __ldg(sd.seg_off + c0 + tid);
+            s_q4[tid] = q; s_sgo[tid] = g;
+            fits = tid >= 1 && q - q4_0 <= CHUNK_Q4 && g - sg_0 <= CHUNK_SEGS;
             if (tid < n) { s_pos[tid] = (uint32_t)__ldg(sd.pos + c0 + tid); s_mate[tid] = __ldg(sd.mate + c0 + tid); }
         }
-        if (tid == 0) { s_misc[0] = 0; s_misc[1] = 0; }
-        __syncthreads();
-        // how many of them fit the byte / cigar / segment budgets: the largest m with all prefix
-        // differences within budget (prefix sums are monotone, so the predicate is monotone in m)
-        if (tid >= 1 && tid <= n) {
-            const bool fits = s_q4[tid] - s_q4[0] <= CHUNK_Q4 && s_cgo[tid] - s_cgo[0] <= CHUNK_CIGAR &&
-                              s_sgo[tid] - s_sgo[0] <= CHUNK_SEGS;
-            if (fits) atomicMax(&s_misc[0], tid);
-        }
-        __syncthreads();
-        const uint32_t m = s_misc[0];
+        if (tid == 0) s_misc[1] = 0;
+        const uint32_t m = (uint32_t)__syncthreads_count(fits);
         if (m == 0) {                       // a single read over the documented limits: host validation failed
             if (tid == 0) atomicExch(err_flag, 1);
             break;
         }
-        const uint32_t q4_0 = s_q4[0], nq4 = s_q4[m] - q4_0;
-        const uint32_t cg_0 = s_cgo[0], ncg = s_cgo[m] - cg_0;
-        const uint32_t sg_0 = s_sgo[0];
+        const uint32_t nq4 = s_q4[m] - q4_0;
 
-        // ---- 2. stage sequence, quality and CIGAR bytes: three bulk copies from 16-byte aligned
-        // addresses at or below the first byte needed; d_* is the offset of that byte in the buffer
+        // ---- 2. stage bases and qualities: two bulk copies from 16-byte aligned addresses at or
+        // below the first byte needed; d_* is the offset of that byte in the buffer
         const uint8_t* g_seq = sd.seq2 + q4_0;
         const uint8_t* g_qual = sd.qual + (size_t)q4_0 * 4;
-        const uint8_t* g_cig = (const uint8_t*)(sd.cigar + cg_0);
-        const uint32_t d_seq = (uint32_t)((uintptr_t)g_seq & 15), d_qual = (uint32_t)((uintptr_t)g_qual & 15),
-                       d_cig = (uint32_t)((uintptr_t)g_cig & 15);
-        const uint32_t b_seq = (d_seq + nq4 + 15) & ~15u, b_qual = (d_qual + nq4 * 4 + 15) & ~15u,
-                       b_cig = (d_cig + ncg * 4 + 15) & ~15u;
+        const uint32_t d_seq = (uint32_t)((uintptr_t)g_seq & 15), d_qual = (uint32_t)((uintptr_t)g_qual & 15);
+        const uint32_t b_seq = (d_seq + nq4 + 15) & ~15u, b_qual = (d_qual + nq4 * 4 + 15) & ~15u;
         if (tid == 0) {
             fence_proxy_async();            // earlier generic-proxy accesses to these buffers are ordered before the copies
-            mbar_expect_tx(s_bar, b_seq + b_qual + b_cig);
+            mbar_expect_tx(s_bar, b_seq + b_qual);
             if (b_seq)  tma_load_1d(s_seq, g_seq - d_seq, b_seq, s_bar);
             if (b_qual) tma_load_1d(s_qual, g_qual - d_qual, b_qual, s_bar);
-            if (b_cig)  tma_load_1d(s_cig, g_cig - d_cig, b_cig, s_bar);
         }
-        mbar_wait(s_bar, parity);
-        parity ^= 1;
 
-        // ---- 3a. CIGAR walk: one thread per read, one segment per M/=/X operation
+        // ---- 3. CIGAR walk while the copies are in flight: one thread per read, one segment per M/=/X
         if (tid < m) {
-            const uint32_t* cg = (const uint32_t*)(s_cig + d_cig) + (s_cgo[tid] - cg_0);
-            const uint32_t nops = s_cgo[tid + 1] - s_cgo[tid];
+            const uint32_t cg0 = __ldg(sd.cig_off + c0 + tid), nops = __ldg(sd.cig_off + c0 + tid + 1) - cg0;
             uint32_t k = s_sgo[tid] - sg_0;
             const int32_t rpos = (int32_t)s_pos[tid];
             int32_t x = rpos;
             uint32_t y = d_qual + (s_q4[tid] - q4_0) * 4;        // byte address of the read's first base in s_qual
             for (uint32_t o = 0; o < nops; ++o) {
-                const uint32_t w = cg[o], op = w & 0xf, len = w >> 4;
+                const uint32_t w = __ldg(sd.cigar + cg0 + o), op = w & 0xf, len = w >> 4;
                 if (op == 0 || op == 7 || op == 8) {
-                    s_seg[k++] = make_uint4((uint32_t)x, len, y, (uint32_t)rpos);
+                    s_seg[k++] = make_uint4((uint32_t)x, len, y, tid);
                     x += (int32_t)len; y += len;
                 } else if (op == 2 || op == 3) x += (int32_t)len;
                 else if (op == 1 || op == 4) y += len;
             }
             atomicMax(&s_misc[1], (uint32_t)(x - rpos));
-        } else if (tid >= 256 && tid - 256 < m) {
-            // ---- 3a'. mate-overlap quality correction of this read's staged qualities, for the
-            // positions of this tile only (the others are counted by other CTAs). `a` is the mate that
-            // comes first in the file, `b` the later one; with pristine qualities qa, qb at a reference
-            // position both mates align to: same base -> a: min(qa+qb, cap), b: 0; different ->
-            // qa >= qb ? (a: 0.8*qa, b: 0) : (a: 0, b: 0.8*qb).
-            const uint32_t i = tid - 256;
+        }
+        if (lane == 0) mbar_wait(s_bar, parity);
+        parity ^= 1;
+        __syncthreads();                    // segments written, copies landed
+
+        // ---- 4. mate-overlap quality correction, restricted to this tile's positions (other tiles
+        // are counted by other CTAs). Pairs with both mates in the chunk: the warp of the earlier mate
+        // rewrites both from pristine values. Mates outside the chunk (only when a tile needs several
+        // chunks): this read alone is rewritten, the mate's pristine data come from global memory.
+        for (uint32_t i = warp; i < m; i += PILEUP_THREADS / 32) {
             const int32_t mt = s_mate[i];
-            if (mt >= 0) {
-                const uint32_t self = c0 + i;
-                const bool self_is_a = self < (uint32_t)mt;
-                const int32_t spos = (int32_t)s_pos[i], mpos = __ldg(sd.pos + mt);
-                const uint32_t mc0 = __ldg(sd.cig_off + mt), mq4 = __ldg(sd.q4_off + mt);
-                CigarWalk ws, wm;
-                ws.init((const uint32_t*)(s_cig + d_cig) + (s_cgo[i] - cg_0), s_cgo[i + 1] - s_cgo[i], spos);
-                wm.init(sd.cigar + mc0, __ldg(sd.cig_off + mt + 1) - mc0, mpos);
-                uint8_t* sq = s_qual + d_qual + (s_q4[i] - q4_0) * 4;
-                const uint8_t* ss = s_seq + d_seq + (s_q4[i] - q4_0);
+            if (mt < 0) continue;
+            const uint32_t self = c0 + i;
+            const bool self_is_a = self < (uint32_t)mt;
+            const bool mate_here = (uint32_t)mt >= c0 && (uint32_t)mt < c0 + m;
+            if (mate_here && !self_is_a) continue;                 // done by the mate's warp
+            const uint32_t sa0 = s_sgo[i] - sg_0, sa1 = s_sgo[i + 1] - sg_0;
+            if (mate_here) {
+                const uint32_t j = (uint32_t)mt - c0;
+                const uint32_t sb0 = s_sgo[j] - sg_0, sb1 = s_sgo[j + 1] - sg_0;
+                for (uint32_t ka = sa0; ka < sa1; ++ka) {
+                    const uint4 A = s_seg[ka];
+                    for (uint32_t kb = sb0; kb < sb1; ++kb) {
+                        const uint4 B = s_seg[kb];
+                        int32_t lo = max(max((int32_t)A.x, (int32_t)B.x), p0);
+                        const int32_t hi = min(min((int32_t)(A.x + A.y), (int32_t)(B.x + B.y)), p0 + TILE);
+                        for (int32_t p = lo + (int32_t)lane; p < hi; p += 32) {
+                            const uint32_t za = A.z + (uint32_t)(p - (int32_t)A.x), zb = B.z + (uint32_t)(p - (int32_t)B.x);
+                            const uint32_t va = s_qual[za], vb = s_qual[zb];
+                            const uint32_t ia = za - d_qual, ib = zb - d_qual;     // base index inside the staged range
+                            const uint32_t ba = (s_seq[d_seq + (ia >> 2)] >> ((ia & 3) * 2)) & 3u;
+                            const uint32_t bb = (s_seq[d_seq + (ib >> 2)] >> ((ib & 3) * 2)) & 3u;
+                            const bool same = ((va | vb) & 0x80u) ? ((va & vb & 0x80u) != 0) : (ba == bb);
+                            uint32_t na, nb;
+                            overlap_rule(va, vb, same, na, nb);
+                            s_qual[za] = (uint8_t)na; s_qual[zb] = (uint8_t)nb;
+                        }
+                    }
+                }
+            } else {
+                // walk the mate's CIGAR from global memory (every lane the same way), lanes over positions
+                const uint32_t mc0 = __ldg(sd.cig_off + mt), mn = __ldg(sd.cig_off + mt + 1) - mc0;
+                const uint32_t mq4 = __ldg(sd.q4_off + mt);
                 const uint8_t* mq = sd.qual + (size_t)mq4 * 4;
                 const uint8_t* ms = sd.seq2 + mq4;
-                int32_t ref = spos > mpos ? spos : mpos;
-                if (ref < p0) ref = p0;
-                const int32_t ref_end = p0 + TILE;
-                while (ref < ref_end) {
-                    int32_t r1, r2; uint32_t i1, i2;
-                    if (!ws.seek(ref, r1, i1)) break;
-                    if (r1 > ref) ref = r1;
-                    if (!wm.seek(ref, r2, i2)) break;
-                    if (r2 > ref) { ref = r2; continue; }
-                    if (ref >= ref_end) break;
-                    const uint32_t vs = sq[i1], vm = mq[i2];
-                    const uint32_t fs = vs & 0x80u, fm = vm & 0x80u, qs = vs & 0x7fu, qm = vm & 0x7fu;
-                    // "same base" in htslib compares 4-bit codes; non-ACGT codes all collapse to the flag here
-                    const bool same = (fs || fm) ? (fs && fm) : (base2_at(ss, i1) == base2_at(ms, i2));
-                    const uint32_t qa = self_is_a ? qs : qm, qb = self_is_a ? qm : qs;
-                    uint32_t nq;
-                    if (same) { nq = qa + qb; if (nq > 127u) nq = 127u; if (!self_is_a) nq = 0; }
-                    else if (qa >= qb) nq = self_is_a ? (uint32_t)(0.8 * (double)qa) : 0u;
-                    else nq = self_is_a ? 0u : (uint32_t)(0.8 * (double)qb);
-                    sq[i1] = (uint8_t)(fs | nq);
-                    ++ref;
+                int32_t bx = __ldg(sd.pos + mt); uint32_t by = 0;
+                for (uint32_t o = 0; o < mn; ++o) {
+                    const uint32_t w = __ldg(sd.cigar + mc0 + o), op = w & 0xf, len = w >> 4;
+                    if (op == 0 || op == 7 || op == 8) {
+                        for (uint32_t ka = sa0; ka < sa1; ++ka) {
+                            const uint4 A = s_seg[ka];
+                            int32_t lo = max(max((int32_t)A.x, bx), p0);
+                            const int32_t hi = min(min((int32_t)(A.x + A.y), bx + (int32_t)len), p0 + TILE);
+                            for (int32_t p = lo + (int32_t)lane; p < hi; p += 32) {
+                                const uint32_t zs = A.z + (uint32_t)(p - (int32_t)A.x), im = by + (uint32_t)(p - bx);
+                                const uint32_t vs = s_qual[zs], vm = mq[im];
+                                const uint32_t is = zs - d_qual;
+                                const uint32_t bs = (s_seq[d_seq + (is >> 2)] >> ((is & 3) * 2)) & 3u;
+                                const uint32_t bm = (ms[im >> 2] >> ((im & 3) * 2)) & 3u;
+                                const bool same = ((vs | vm) & 0x80u) ? ((vs & vm & 0x80u) != 0) : (bs == bm);
+                                uint32_t na, nb;
+                                if (self_is_a) overlap_rule(vs, vm, same, na, nb); else overlap_rule(vm, vs, same, nb, na);
+                                s_qual[zs] = (uint8_t)na;
+                            }
+                        }
+                        bx += (int32_t)len; by += len;
+                    } else if (op == 2 || op == 3) bx += (int32_t)len;
+                    else if (op == 1 || op == 4) by += len;
                 }
             }
         }
         __syncthreads();
-        // ---- 3b. (2-bit base, quality) -> code, in place over the quality bytes, 4 bases per step
+
+        // ---- 5. (2-bit base, quality) -> code, in place over the quality bytes. Four bases per
+        // 32-bit word, all byte lanes at once (SWAR): no byte can carry into its neighbour.
         {
             uint32_t* q32 = (uint32_t*)(s_qual + d_qual);         // d_qual is a multiple of 4
             const uint8_t* sq = s_seq + d_seq;
             for (uint32_t g = tid; g < nq4; g += PILEUP_THREADS) {
                 const uint32_t q = q32[g];
-                const uint32_t b = sq[g];
-                uint32_t out = 0;
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t qb = (q >> (8 * j)) & 0xffu;
-                    uint32_t code = ((b >> (2 * j)) & 3u) * 8u;
-                    if (qb & 0x80u) code = CODE_N;
-                    if ((qb & 0x7fu) < 13u) code = CODE_SKIP;
-                    out |= code << (8 * j);
-                }
-                q32[g] = out;
+                uint32_t x = sq[g];
+                x = (x * 4097u) & 0x000f000fu;                    // two 2-bit pairs per half word
+                x = (x * 520u) & 0x18181818u;                     // base*8 in every byte lane
+                const uint32_t pass = (((q & 0x7f7f7f7fu) + 0x73737373u) >> 7) & 0x01010101u;   // 1 where (q & 127) >= 13
+                const uint32_t nflag = (q >> 7) & 0x01010101u;
+                const uint32_t pm = pass * 255u, nm = nflag * 255u;
+                x = (x & ~nm) | (0x20202020u & nm);               // CODE_N for non-ACGT bases
+                x = (x & pm) | (0x40404040u & ~pm);               // CODE_SKIP below the quality threshold
+                q32[g] = x;
             }
         }
         __syncthreads();
 
-        // ---- 4. gather. Segments are in read order, reads in position order: this warp only needs
+        // ---- 6. gather. Segments are in read order, reads in position order: this warp only needs
         // reads starting in (warp_lo - span, warp_lo + 32), located by counting with ballots.
         {
             const int64_t lo_key = (int64_t)warp_lo - (int64_t)s_misc[1];      // reads with pos <= lo_key cannot reach the warp
@@ -470,7 +472,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
         __syncthreads();                    // everyone is done with the buffers before they are refilled
     }
 
-    // ---- 5. flush: 8 B + 2 B per position, fully coalesced
+    // ---- 7. flush: 8 B + 2 B per position, fully coalesced
     const size_t o = (size_t)blockIdx.x * TILE + tid;
     acgt[o] = acc;
     ncnt[o] = (uint16_t)acc_n;

@@ -175,6 +175,7 @@ static int ensure_items(msnv_ctx* ctx, uint64_t n_items)
 extern "C" {
 
 int msnv_abi_version(void) { return MSNV_ABI_VERSION; }
+int msnv_tile(void) { return MSNV_TILE; }
 
 int msnv_device_count(void)
 {

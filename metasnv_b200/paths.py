@@ -8,6 +8,9 @@ ORACLE_DIR = os.path.join(REPO_ROOT, "oracle")
 
 
 def lib_path(name="libmsnv_gpu.so"):
+    # MSNV_LIB: alternative build of the same ABI (kernel experiments)
+    if name == "libmsnv_gpu.so" and os.environ.get("MSNV_LIB"):
+        return os.environ["MSNV_LIB"]
     return os.path.join(LIB_DIR, name)
 
 
