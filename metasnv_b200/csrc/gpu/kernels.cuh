@@ -24,7 +24,7 @@ constexpr int PILEUP_THREADS = TILE;
 constexpr int CHUNK_READS = TILE / 2 - 1 < 255 ? TILE / 2 - 1 : 255;   // reads staged per chunk (8-bit per-chunk counters;
                                                                        // the second half of the CTA corrects mate overlaps)
 constexpr int CHUNK_Q4 = TILE * 8;              // 4-base groups staged per chunk (TILE*32 bases)
-constexpr int CHUNK_SEGS = TILE * 2;            // aligned segments per chunk
+constexpr int CHUNK_SEGS = TILE;                // aligned segments per chunk
 
 static_assert(MSNV_MAX_READ_BASES * 2 <= CHUNK_Q4 * 4, "one read must fit a chunk with room to spare");
 static_assert(MSNV_MAX_READ_CIGAR * 2 <= CHUNK_SEGS, "one read's segments must fit a chunk");
@@ -134,7 +134,8 @@ __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t* s_warp /*[33
 template <bool EMIT>
 __global__ void __launch_bounds__(256) index_kernel(const SampleDev* __restrict__ samples, uint32_t n_samples,
                                                     uint32_t n_tiles, uint32_t* __restrict__ block_sums,
-                                                    Item* __restrict__ items, uint32_t* __restrict__ tile_begin)
+                                                    Item* __restrict__ items, uint32_t* __restrict__ tile_begin,
+                                                    uint2* __restrict__ range_cache /* [tiles*samples] or null: COUNT stores, EMIT reloads */)
 {
     __shared__ uint32_t s_warp[33];
     const uint64_t pair = (uint64_t)blockIdx.x * 256 + threadIdx.x;
@@ -144,14 +145,20 @@ __global__ void __launch_bounds__(256) index_kernel(const SampleDev* __restrict_
     if (pair < n_pairs) {
         t = (uint32_t)(pair / n_samples);
         s = (uint32_t)(pair - (uint64_t)t * n_samples);
-        const uint32_t n = samples[s].n_reads;
-        if (n) {
-            const int32_t* pos = samples[s].pos;
-            const int64_t t0 = (int64_t)t * TILE;
-            r_lo = lower_bound_i32(pos, n, t0 - (int64_t)samples[s].max_span + 1);
-            r_hi = lower_bound_i32(pos, n, t0 + TILE);
-            active = r_hi > r_lo;
+        if (EMIT && range_cache) {
+            const uint2 c = range_cache[pair];
+            r_lo = c.x; r_hi = c.y;
+        } else {
+            const uint32_t n = samples[s].n_reads;
+            if (n) {
+                const int32_t* pos = samples[s].pos;
+                const int64_t t0 = (int64_t)t * TILE;
+                r_lo = lower_bound_i32(pos, n, t0 - (int64_t)samples[s].max_span + 1);
+                r_hi = lower_bound_i32(pos, n, t0 + TILE);
+            }
+            if (!EMIT && range_cache) range_cache[pair] = make_uint2(r_lo, r_hi);
         }
+        active = r_hi > r_lo;
     }
     uint32_t total;
     uint32_t rank = block_rank(active, s_warp, total);
@@ -241,32 +248,43 @@ __device__ __forceinline__ void overlap_rule(uint32_t va, uint32_t vb, bool same
 }
 
 // ------------------------------------------------------------------------------------------------
-// pileup: one CTA per work item (sample, tile); thread i owns position tile*TILE + i.
+// pileup: one CTA per work item (sample, tile).
 // Per chunk of reads (<= CHUNK_READS reads, CHUNK_Q4*4 bases, CHUNK_SEGS aligned segments):
 //   1. metadata of the chunk's reads -> shared memory; __syncthreads_count sizes the chunk
 //   2. two TMA bulk copies (2-bit bases, qualities) are issued; while they fly,
-//   3. one thread per read walks its CIGAR (global, L2) into aligned segments
+//   3. one thread per read walks its CIGAR (global, L2) into aligned segments and a descriptor of
+//      its first segment clipped to the tile, and tags its 4-base groups with the read's index
 //   4. mate-overlap quality correction in shared memory, one warp per pair, lanes over positions
 //      (mates staged in another chunk are read, pristine, from global memory)
-//   5. (2-bit base, quality) -> 1-byte code in place, four bases per word with SWAR arithmetic
-//   6. every thread gathers the codes of the segments that cover its own position
-// No atomics on the counting path: a position's counters live in the registers of exactly one
-// thread, so deep coverage costs instructions in proportion to bases and nothing for contention.
+//   5. flat scatter: thread g takes the g-th 4-base group of the staged bytes, turns (2-bit base,
+//      quality) into four codes with SWAR arithmetic and adds each base that lies on the tile to
+//      its position's shared-memory counter (one byte lane per base letter) with ATOMS.ADD.
+//      Every staged base costs the same handful of instructions at full lane occupancy, whatever the
+//      depth; the counter words are XOR-swizzled so the stride-4 access of a warp is conflict free
+//      (measured: ~21 shared atomics per clock per SM, profiles/r01_microbench_shared_atomics.txt)
+//   6. thread i folds position i's byte lanes into its 16-bit packed registers and clears them
 // The reads in HBM are never modified.
 //
 // Shared memory (dynamic), regions 16-byte aligned:
 //   s_meta   4 x META_STRIDE u32      pos | q4_off | seg_off | mate of the chunk's reads
+//   s_rd     CHUNK_READS x 16 bytes   {first segment: p_rel - base index, lo, span; first seg | n segs << 16}
 //   s_seq    CHUNK_Q4 + 32 bytes      2-bit bases           (TMA destination)
-//   s_qual   4*CHUNK_Q4 + 32 bytes    qualities -> codes    (TMA destination)
-//   s_seg    CHUNK_SEGS x 16 bytes    {ref begin, length, byte address of first code, read index}
-// Codes are shift amounts: 0,8,16,24 = A,C,G,T with quality >= 13 (one byte lane each of the
-// per-chunk accumulator); 32 = non-ACGT base with quality >= 13; 64 = not counted.
+//   s_qual   4*CHUNK_Q4 + 32 bytes    qualities             (TMA destination)
+//   s_g2r    CHUNK_Q4 bytes           read index of every 4-base group
+//   s_seg    CHUNK_SEGS x 16 bytes    {ref begin, length, byte address of first quality, read index}
+//   s_cnt    2 x TILE u32             A|C|G|T byte lanes, non-ACGT count
+// Codes are shift amounts: 0,8,16,24 = A,C,G,T with quality >= 13; 32 = non-ACGT base with
+// quality >= 13; 64 = not counted.
 // ------------------------------------------------------------------------------------------------
 constexpr int META_STRIDE = 260;
-constexpr size_t PILEUP_SMEM = 4 * META_STRIDE * 4 + (CHUNK_Q4 + 32) + (4 * CHUNK_Q4 + 32) + CHUNK_SEGS * 16 + 64;
+constexpr size_t PILEUP_SMEM = 4 * META_STRIDE * 4 + 256 * 16 + (CHUNK_Q4 + 32) + (4 * CHUNK_Q4 + 32) + CHUNK_Q4 + CHUNK_SEGS * 16 +
+                               2 * TILE * 4 + 256 * 2 + 64;
+
+// counter word of tile-relative position p: XOR swizzle so that positions 4 apart fall in different banks
+__device__ __forceinline__ uint32_t cnt_slot(uint32_t p) { return p ^ ((p >> 5) & 3u); }
 
 #ifndef MSNV_PILEUP_MIN_CTAS
-#define MSNV_PILEUP_MIN_CTAS (TILE >= 512 ? 3 : 6)
+#define MSNV_PILEUP_MIN_CTAS (TILE >= 512 ? 4 : 8)
 #endif
 __global__ void __launch_bounds__(PILEUP_THREADS, MSNV_PILEUP_MIN_CTAS)
 pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items,
@@ -278,22 +296,26 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     uint32_t* s_q4  = s_pos + META_STRIDE;
     uint32_t* s_sgo = s_q4 + META_STRIDE;
     int32_t*  s_mate = (int32_t*)(s_sgo + META_STRIDE);
-    uint8_t*  s_seq  = (uint8_t*)(s_mate + META_STRIDE);
+    uint4*    s_rd   = (uint4*)(s_mate + META_STRIDE);
+    uint8_t*  s_seq  = (uint8_t*)(s_rd + 256);
     uint8_t*  s_qual = s_seq + CHUNK_Q4 + 32;
-    uint4*    s_seg  = (uint4*)(s_qual + 4 * CHUNK_Q4 + 32);
-    uint64_t* s_bar  = (uint64_t*)(s_seg + CHUNK_SEGS);
-    uint32_t* s_misc = (uint32_t*)(s_bar + 1);        // [1] max span in chunk
+    uint8_t*  s_g2r  = s_qual + 4 * CHUNK_Q4 + 32;
+    uint4*    s_seg  = (uint4*)(s_g2r + CHUNK_Q4);
+    uint32_t* s_cnt  = (uint32_t*)(s_seg + CHUNK_SEGS);
+    uint32_t* s_cntn = s_cnt + TILE;
+    uint16_t* s_pairs = (uint16_t*)(s_cntn + TILE);
+    uint64_t* s_bar  = (uint64_t*)(s_pairs + 256);
+    uint32_t* s_misc = (uint32_t*)(s_bar + 1);        // [0] number of overlap tasks of the chunk
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const Item it = items[blockIdx.x];
-    const SampleDev sd = samples[it.sample];
     const int32_t p0 = (int32_t)(it.tile * TILE);
-    const int32_t my_pos = p0 + (int32_t)tid;
-    const int32_t warp_lo = p0 + (int32_t)(tid & ~31u);          // first position owned by this warp
+    const SampleDev* __restrict__ sd = samples + it.sample;
 
     if (tid == 0) { mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    s_cnt[tid] = 0; s_cntn[tid] = 0;
 
-    uint64_t acc = 0;       // A | C<<16 | G<<32 | T<<48
+    uint64_t acc = 0;       // A | C<<16 | G<<32 | T<<48 of position p0 + tid
     uint32_t acc_n = 0;
     uint32_t parity = 0;
 
@@ -301,175 +323,201 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
         // ---- 1. metadata of up to CHUNK_READS reads (+1 for the end offsets); the chunk takes the
         // longest prefix within the byte and segment budgets (prefix sums: the predicate is monotone)
         uint32_t n = it.r_hi - c0; if (n > CHUNK_READS) n = CHUNK_READS;
-        const uint32_t q4_0 = __ldg(sd.q4_off + c0), sg_0 = __ldg(sd.seg_off + c0);
         bool fits = false;
         if (tid <= n) {
-            const uint32_t q = __ldg(sd.q4_off + c0 + tid), g = __ldg(sd.seg_off + c0 + tid);
+            const uint32_t* q4p = sd->q4_off + c0; const uint32_t* sgp = sd->seg_off + c0;
+            const uint32_t q = __ldg(q4p + tid), g = __ldg(sgp + tid);
             s_q4[tid] = q; s_sgo[tid] = g;
-            fits = tid >= 1 && q - q4_0 <= CHUNK_Q4 && g - sg_0 <= CHUNK_SEGS;
-            if (tid < n) { s_pos[tid] = (uint32_t)__ldg(sd.pos + c0 + tid); s_mate[tid] = __ldg(sd.mate + c0 + tid); }
+            fits = tid >= 1 && q - __ldg(q4p) <= CHUNK_Q4 && g - __ldg(sgp) <= CHUNK_SEGS;
+            if (tid < n) { s_pos[tid] = (uint32_t)__ldg(sd->pos + c0 + tid); s_mate[tid] = __ldg(sd->mate + c0 + tid); }
         }
-        if (tid == 0) s_misc[1] = 0;
+        if (tid == 0) s_misc[0] = 0;
         const uint32_t m = (uint32_t)__syncthreads_count(fits);
         if (m == 0) {                       // a single read over the documented limits: host validation failed
             if (tid == 0) atomicExch(err_flag, 1);
             break;
         }
-        const uint32_t nq4 = s_q4[m] - q4_0;
+        const uint32_t q4_0 = s_q4[0], sg_0 = s_sgo[0], nq4 = s_q4[m] - q4_0;
 
         // ---- 2. stage bases and qualities: two bulk copies from 16-byte aligned addresses at or
         // below the first byte needed; d_* is the offset of that byte in the buffer
-        const uint8_t* g_seq = sd.seq2 + q4_0;
-        const uint8_t* g_qual = sd.qual + (size_t)q4_0 * 4;
+        const uint8_t* g_seq = sd->seq2 + q4_0;
+        const uint8_t* g_qual = sd->qual + (size_t)q4_0 * 4;
         const uint32_t d_seq = (uint32_t)((uintptr_t)g_seq & 15), d_qual = (uint32_t)((uintptr_t)g_qual & 15);
-        const uint32_t b_seq = (d_seq + nq4 + 15) & ~15u, b_qual = (d_qual + nq4 * 4 + 15) & ~15u;
         if (tid == 0) {
+            const uint32_t b_seq = (d_seq + nq4 + 15) & ~15u, b_qual = (d_qual + nq4 * 4 + 15) & ~15u;
             fence_proxy_async();            // earlier generic-proxy accesses to these buffers are ordered before the copies
             mbar_expect_tx(s_bar, b_seq + b_qual);
             if (b_seq)  tma_load_1d(s_seq, g_seq - d_seq, b_seq, s_bar);
             if (b_qual) tma_load_1d(s_qual, g_qual - d_qual, b_qual, s_bar);
         }
 
-        // ---- 3. CIGAR walk while the copies are in flight: one thread per read, one segment per M/=/X
+        // ---- 3. CIGAR walk while the copies are in flight: one thread per read
         if (tid < m) {
-            const uint32_t cg0 = __ldg(sd.cig_off + c0 + tid), nops = __ldg(sd.cig_off + c0 + tid + 1) - cg0;
-            uint32_t k = s_sgo[tid] - sg_0;
-            const int32_t rpos = (int32_t)s_pos[tid];
-            int32_t x = rpos;
-            uint32_t y = d_qual + (s_q4[tid] - q4_0) * 4;        // byte address of the read's first base in s_qual
+            const uint32_t cg0 = __ldg(sd->cig_off + c0 + tid), nops = __ldg(sd->cig_off + c0 + tid + 1) - cg0;
+            const uint32_t k0 = s_sgo[tid] - sg_0;
+            uint32_t k = k0;
+            const uint32_t gq0 = s_q4[tid] - q4_0, gq1 = s_q4[tid + 1] - q4_0;
+            int32_t x = (int32_t)s_pos[tid];
+            uint32_t y = d_qual + gq0 * 4;                        // byte address of the read's first base in s_qual
             for (uint32_t o = 0; o < nops; ++o) {
-                const uint32_t w = __ldg(sd.cigar + cg0 + o), op = w & 0xf, len = w >> 4;
+                const uint32_t w = __ldg(sd->cigar + cg0 + o), op = w & 0xf, len = w >> 4;
                 if (op == 0 || op == 7 || op == 8) {
                     s_seg[k++] = make_uint4((uint32_t)x, len, y, tid);
                     x += (int32_t)len; y += len;
                 } else if (op == 2 || op == 3) x += (int32_t)len;
                 else if (op == 1 || op == 4) y += len;
             }
-            atomicMax(&s_misc[1], (uint32_t)(x - rpos));
-        }
-        if (lane == 0) mbar_wait(s_bar, parity);
-        parity ^= 1;
-        __syncthreads();                    // segments written, copies landed
-
-        // ---- 4. mate-overlap quality correction, restricted to this tile's positions (other tiles
-        // are counted by other CTAs). Pairs with both mates in the chunk: the warp of the earlier mate
-        // rewrites both from pristine values. Mates outside the chunk (only when a tile needs several
-        // chunks): this read alone is rewritten, the mate's pristine data come from global memory.
-        for (uint32_t i = warp; i < m; i += PILEUP_THREADS / 32) {
-            const int32_t mt = s_mate[i];
-            if (mt < 0) continue;
-            const uint32_t self = c0 + i;
-            const bool self_is_a = self < (uint32_t)mt;
-            const bool mate_here = (uint32_t)mt >= c0 && (uint32_t)mt < c0 + m;
-            if (mate_here && !self_is_a) continue;                 // done by the mate's warp
-            const uint32_t sa0 = s_sgo[i] - sg_0, sa1 = s_sgo[i + 1] - sg_0;
-            if (mate_here) {
-                const uint32_t j = (uint32_t)mt - c0;
-                const uint32_t sb0 = s_sgo[j] - sg_0, sb1 = s_sgo[j + 1] - sg_0;
-                for (uint32_t ka = sa0; ka < sa1; ++ka) {
-                    const uint4 A = s_seg[ka];
-                    for (uint32_t kb = sb0; kb < sb1; ++kb) {
-                        const uint4 B = s_seg[kb];
-                        int32_t lo = max(max((int32_t)A.x, (int32_t)B.x), p0);
-                        const int32_t hi = min(min((int32_t)(A.x + A.y), (int32_t)(B.x + B.y)), p0 + TILE);
-                        for (int32_t p = lo + (int32_t)lane; p < hi; p += 32) {
-                            const uint32_t za = A.z + (uint32_t)(p - (int32_t)A.x), zb = B.z + (uint32_t)(p - (int32_t)B.x);
-                            const uint32_t va = s_qual[za], vb = s_qual[zb];
-                            const uint32_t ia = za - d_qual, ib = zb - d_qual;     // base index inside the staged range
-                            const uint32_t ba = (s_seq[d_seq + (ia >> 2)] >> ((ia & 3) * 2)) & 3u;
-                            const uint32_t bb = (s_seq[d_seq + (ib >> 2)] >> ((ib & 3) * 2)) & 3u;
-                            const bool same = ((va | vb) & 0x80u) ? ((va & vb & 0x80u) != 0) : (ba == bb);
-                            uint32_t na, nb;
-                            overlap_rule(va, vb, same, na, nb);
-                            s_qual[za] = (uint8_t)na; s_qual[zb] = (uint8_t)nb;
-                        }
-                    }
-                }
-            } else {
-                // walk the mate's CIGAR from global memory (every lane the same way), lanes over positions
-                const uint32_t mc0 = __ldg(sd.cig_off + mt), mn = __ldg(sd.cig_off + mt + 1) - mc0;
-                const uint32_t mq4 = __ldg(sd.q4_off + mt);
-                const uint8_t* mq = sd.qual + (size_t)mq4 * 4;
-                const uint8_t* ms = sd.seq2 + mq4;
-                int32_t bx = __ldg(sd.pos + mt); uint32_t by = 0;
-                for (uint32_t o = 0; o < mn; ++o) {
-                    const uint32_t w = __ldg(sd.cigar + mc0 + o), op = w & 0xf, len = w >> 4;
-                    if (op == 0 || op == 7 || op == 8) {
-                        for (uint32_t ka = sa0; ka < sa1; ++ka) {
-                            const uint4 A = s_seg[ka];
-                            int32_t lo = max(max((int32_t)A.x, bx), p0);
-                            const int32_t hi = min(min((int32_t)(A.x + A.y), bx + (int32_t)len), p0 + TILE);
-                            for (int32_t p = lo + (int32_t)lane; p < hi; p += 32) {
-                                const uint32_t zs = A.z + (uint32_t)(p - (int32_t)A.x), im = by + (uint32_t)(p - bx);
-                                const uint32_t vs = s_qual[zs], vm = mq[im];
-                                const uint32_t is = zs - d_qual;
-                                const uint32_t bs = (s_seq[d_seq + (is >> 2)] >> ((is & 3) * 2)) & 3u;
-                                const uint32_t bm = (ms[im >> 2] >> ((im & 3) * 2)) & 3u;
-                                const bool same = ((vs | vm) & 0x80u) ? ((vs & vm & 0x80u) != 0) : (bs == bm);
-                                uint32_t na, nb;
-                                if (self_is_a) overlap_rule(vs, vm, same, na, nb); else overlap_rule(vm, vs, same, nb, na);
-                                s_qual[zs] = (uint8_t)na;
-                            }
-                        }
-                        bx += (int32_t)len; by += len;
-                    } else if (op == 2 || op == 3) bx += (int32_t)len;
-                    else if (op == 1 || op == 4) by += len;
-                }
+            // first segment clipped to the tile, in the coordinates the scatter uses: a base with staged
+            // index b (4*group + k) lies at tile-relative position rd.x + b if (rd.x + b - rd.y) < rd.z
+            uint4 rd = make_uint4(0u, 0u, 0u, k0 | (k - k0) << 16);
+            if (k > k0) {
+                const uint4 f = s_seg[k0];
+                const int32_t lo = max((int32_t)f.x - p0, 0), hi = min((int32_t)(f.x + f.y) - p0, (int32_t)TILE);
+                rd.x = (uint32_t)((int32_t)f.x - p0 - (int32_t)(f.z - d_qual));
+                rd.y = (uint32_t)lo;
+                rd.z = hi > lo ? (uint32_t)(hi - lo) : 0u;
+            }
+            s_rd[tid] = rd;
+            for (uint32_t g = gq0; g < gq1; ++g) s_g2r[g] = (uint8_t)tid;
+            const int32_t mt = s_mate[tid];
+            if (mt >= 0) {                                        // overlap task: once per pair when both mates are here
+                const bool mate_here = (uint32_t)mt >= c0 && (uint32_t)mt < c0 + m;
+                if (!mate_here || c0 + tid < (uint32_t)mt) s_pairs[atomicAdd(&s_misc[0], 1u)] = (uint16_t)tid;
             }
         }
-        __syncthreads();
+        if (tid == 0) mbar_wait(s_bar, parity);
+        parity ^= 1;
+        __syncthreads();                    // segments written, copies landed (thread 0 observed the barrier)
 
-        // ---- 5. (2-bit base, quality) -> code, in place over the quality bytes. Four bases per
-        // 32-bit word, all byte lanes at once (SWAR): no byte can carry into its neighbour.
+        // ---- 4. mate-overlap quality correction, restricted to this tile's positions (other tiles
+        // are counted by other CTAs). Pairs with both mates in the chunk: one warp rewrites both from
+        // pristine values. Mates outside the chunk (only when a tile needs several chunks): this read
+        // alone is rewritten, the mate's pristine data come from global memory.
+        const uint32_t n_tasks = s_misc[0];
+        if (n_tasks) {
+            for (uint32_t t = warp; t < n_tasks; t += PILEUP_THREADS / 32) {
+                const uint32_t i = s_pairs[t];
+                const int32_t mt = s_mate[i];
+                const bool self_is_a = c0 + i < (uint32_t)mt;
+                const bool mate_here = (uint32_t)mt >= c0 && (uint32_t)mt < c0 + m;
+                const uint32_t sa0 = s_sgo[i] - sg_0, sa1 = s_sgo[i + 1] - sg_0;
+                if (mate_here) {
+                    const uint32_t j = (uint32_t)mt - c0;
+                    const uint32_t sb0 = s_sgo[j] - sg_0, sb1 = s_sgo[j + 1] - sg_0;
+                    for (uint32_t ka = sa0; ka < sa1; ++ka) {
+                        const uint4 A = s_seg[ka];
+                        for (uint32_t kb = sb0; kb < sb1; ++kb) {
+                            const uint4 B = s_seg[kb];
+                            const int32_t lo = max(max((int32_t)A.x, (int32_t)B.x), p0);
+                            const int32_t hi = min(min((int32_t)(A.x + A.y), (int32_t)(B.x + B.y)), p0 + TILE);
+                            for (int32_t p = lo + (int32_t)lane; p < hi; p += 32) {
+                                const uint32_t za = A.z + (uint32_t)(p - (int32_t)A.x), zb = B.z + (uint32_t)(p - (int32_t)B.x);
+                                const uint32_t va = s_qual[za], vb = s_qual[zb];
+                                const uint32_t ia = za - d_qual, ib = zb - d_qual;     // base index inside the staged range
+                                const uint32_t ba = (s_seq[d_seq + (ia >> 2)] >> ((ia & 3) * 2)) & 3u;
+                                const uint32_t bb = (s_seq[d_seq + (ib >> 2)] >> ((ib & 3) * 2)) & 3u;
+                                const bool same = ((va | vb) & 0x80u) ? ((va & vb & 0x80u) != 0) : (ba == bb);
+                                uint32_t na, nb;
+                                overlap_rule(va, vb, same, na, nb);
+                                s_qual[za] = (uint8_t)na; s_qual[zb] = (uint8_t)nb;
+                            }
+                        }
+                    }
+                } else {
+                    // walk the mate's CIGAR from global memory (every lane the same way), lanes over positions
+                    const uint32_t mc0 = __ldg(sd->cig_off + mt), mn = __ldg(sd->cig_off + mt + 1) - mc0;
+                    const uint32_t mq4 = __ldg(sd->q4_off + mt);
+                    const uint8_t* mq = sd->qual + (size_t)mq4 * 4;
+                    const uint8_t* ms = sd->seq2 + mq4;
+                    int32_t bx = __ldg(sd->pos + mt); uint32_t by = 0;
+                    for (uint32_t o = 0; o < mn; ++o) {
+                        const uint32_t w = __ldg(sd->cigar + mc0 + o), op = w & 0xf, len = w >> 4;
+                        if (op == 0 || op == 7 || op == 8) {
+                            for (uint32_t ka = sa0; ka < sa1; ++ka) {
+                                const uint4 A = s_seg[ka];
+                                const int32_t lo = max(max((int32_t)A.x, bx), p0);
+                                const int32_t hi = min(min((int32_t)(A.x + A.y), bx + (int32_t)len), p0 + TILE);
+                                for (int32_t p = lo + (int32_t)lane; p < hi; p += 32) {
+                                    const uint32_t zs = A.z + (uint32_t)(p - (int32_t)A.x), im = by + (uint32_t)(p - bx);
+                                    const uint32_t vs = s_qual[zs], vm = mq[im];
+                                    const uint32_t is = zs - d_qual;
+                                    const uint32_t bs = (s_seq[d_seq + (is >> 2)] >> ((is & 3) * 2)) & 3u;
+                                    const uint32_t bm = (ms[im >> 2] >> ((im & 3) * 2)) & 3u;
+                                    const bool same = ((vs | vm) & 0x80u) ? ((vs & vm & 0x80u) != 0) : (bs == bm);
+                                    uint32_t na, nb;
+                                    if (self_is_a) overlap_rule(vs, vm, same, na, nb); else overlap_rule(vm, vs, same, nb, na);
+                                    s_qual[zs] = (uint8_t)na;
+                                }
+                            }
+                            bx += (int32_t)len; by += len;
+                        } else if (op == 2 || op == 3) bx += (int32_t)len;
+                        else if (op == 1 || op == 4) by += len;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- 5. flat scatter over the staged 4-base groups
         {
-            uint32_t* q32 = (uint32_t*)(s_qual + d_qual);         // d_qual is a multiple of 4
+            const uint32_t* q32 = (const uint32_t*)(s_qual + d_qual);     // d_qual is a multiple of 4
             const uint8_t* sq = s_seq + d_seq;
             for (uint32_t g = tid; g < nq4; g += PILEUP_THREADS) {
                 const uint32_t q = q32[g];
                 uint32_t x = sq[g];
+                const uint4 rd = s_rd[s_g2r[g]];
+                // four codes at once (SWAR): no byte lane can carry into its neighbour
                 x = (x * 4097u) & 0x000f000fu;                    // two 2-bit pairs per half word
                 x = (x * 520u) & 0x18181818u;                     // base*8 in every byte lane
                 const uint32_t pass = (((q & 0x7f7f7f7fu) + 0x73737373u) >> 7) & 0x01010101u;   // 1 where (q & 127) >= 13
-                const uint32_t nflag = (q >> 7) & 0x01010101u;
-                const uint32_t pm = pass * 255u, nm = nflag * 255u;
+                const uint32_t nm = ((q >> 7) & 0x01010101u) * 255u, pm = pass * 255u;
                 x = (x & ~nm) | (0x20202020u & nm);               // CODE_N for non-ACGT bases
                 x = (x & pm) | (0x40404040u & ~pm);               // CODE_SKIP below the quality threshold
-                q32[g] = x;
+                const uint32_t pr0 = rd.x + g * 4u;               // tile-relative position of the group's first base
+                const uint32_t t0 = pr0 - rd.y;
+                #pragma unroll
+                for (uint32_t k = 0; k < 4; ++k)
+                    if (t0 + k < rd.z) atomicAdd(&s_cnt[cnt_slot(pr0 + k)], shl1_clamped32((x >> (8 * k)) & 0xffu));
+                if (x & 0x20202020u) {                            // rare: non-ACGT bases count on their own plane
+                    #pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k)
+                        if (t0 + k < rd.z && ((x >> (8 * k)) & 0xffu) == CODE_N) atomicAdd(&s_cntn[pr0 + k], 1u);
+                }
+                if ((rd.w >> 16) > 1u) {                          // rare: further segments of a read with indels
+                    const uint32_t s1 = (rd.w & 0xffffu) + (rd.w >> 16);
+                    for (uint32_t sgi = (rd.w & 0xffffu) + 1u; sgi < s1; ++sgi) {
+                        const uint4 sg = s_seg[sgi];
+                        #pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k) {
+                            const uint32_t off = d_qual + g * 4u + k - sg.z;
+                            const uint32_t pr = (uint32_t)((int32_t)sg.x - p0) + off;
+                            if (off < sg.y && pr < (uint32_t)TILE) {
+                                const uint32_t code = (x >> (8 * k)) & 0xffu;
+                                atomicAdd(&s_cnt[cnt_slot(pr)], shl1_clamped32(code));
+                                if (code == CODE_N) atomicAdd(&s_cntn[pr], 1u);
+                            }
+                        }
+                    }
+                }
             }
         }
         __syncthreads();
 
-        // ---- 6. gather. Segments are in read order, reads in position order: this warp only needs
-        // reads starting in (warp_lo - span, warp_lo + 32), located by counting with ballots.
+        // ---- 6. fold this chunk's byte lanes (a position sees at most m <= 255 reads per chunk)
         {
-            const int64_t lo_key = (int64_t)warp_lo - (int64_t)s_misc[1];      // reads with pos <= lo_key cannot reach the warp
-            const int32_t hi_key = warp_lo + 32;
-            uint32_t r_first = 0, r_last = 0;
-            for (uint32_t base = 0; base < m; base += 32) {
-                const uint32_t i = base + lane;
-                const int32_t v = i < m ? (int32_t)s_pos[i] : 0x7fffffff;
-                r_first += __popc(__ballot_sync(0xffffffffu, (int64_t)v <= lo_key));
-                r_last  += __popc(__ballot_sync(0xffffffffu, v < hi_key));
+            const uint32_t sl = cnt_slot(tid);
+            const uint32_t a8 = s_cnt[sl];
+            if (a8) {
+                s_cnt[sl] = 0;
+                acc += (uint64_t)(a8 & 0xffu) | (uint64_t)((a8 >> 8) & 0xffu) << 16 | (uint64_t)((a8 >> 16) & 0xffu) << 32 |
+                       (uint64_t)(a8 >> 24) << 48;
             }
-            const uint32_t j_lo = s_sgo[r_first] - sg_0, j_hi = s_sgo[r_last] - sg_0;
-            // per-chunk accumulators: one byte lane per base (a position sees at most m <= 255 reads per
-            // chunk) and the non-ACGT count in units of CODE_N
-            uint32_t a8 = 0, n32 = 0;
-            #pragma unroll 4
-            for (uint32_t j = j_lo; j < j_hi; ++j) {
-                const uint4 sg = s_seg[j];                        // same address in every lane: broadcast
-                const uint32_t idx = (uint32_t)(my_pos - (int32_t)sg.x);
-                uint32_t code = CODE_SKIP;
-                if (idx < sg.y) code = s_qual[sg.z + idx];
-                a8 += shl1_clamped32(code);                       // codes >= 32 shift out to 0
-                n32 += code & CODE_N;
-            }
-            acc += (uint64_t)(a8 & 0xffu) | (uint64_t)((a8 >> 8) & 0xffu) << 16 | (uint64_t)((a8 >> 16) & 0xffu) << 32 |
-                   (uint64_t)(a8 >> 24) << 48;
-            acc_n += n32 / CODE_N;
+            const uint32_t cn = s_cntn[tid];
+            if (cn) { s_cntn[tid] = 0; acc_n += cn; }
         }
         c0 += m;
-        __syncthreads();                    // everyone is done with the buffers before they are refilled
+        // no barrier here: the next chunk only touches the counters again after two more barriers
     }
 
     // ---- 7. flush: 8 B + 2 B per position, fully coalesced

@@ -23,7 +23,8 @@ struct msnv_ctx {
     bool open = false, has_run = false;
     uint32_t S = 0, P = 0, n_tiles = 0;
     std::vector<SampleDev> h_samples;
-    std::vector<void*> sample_allocs;
+    std::vector<std::pair<void*, size_t>> sample_allocs;   // device blocks of the open shard
+    std::vector<std::pair<void*, size_t>> pool;            // blocks of the previous shard, reused by the next one
     std::vector<msnv_sample_sizes> sizes;      // [S]
     uint64_t n_reads = 0, n_bases = 0;
     SampleDev* d_samples = nullptr;
@@ -34,6 +35,7 @@ struct msnv_ctx {
     uint64_t* d_acgt = nullptr;     uint16_t* d_ncnt = nullptr;
     uint32_t* d_tile_begin = nullptr; uint32_t* d_tile_hits = nullptr; uint8_t* d_flags = nullptr; uint64_t cap_tiles = 0;
     uint32_t* d_block_sums = nullptr; uint64_t cap_blocks = 0;
+    uint2* d_range_cache = nullptr;   uint64_t cap_range = 0;
     uint32_t* d_scalar = nullptr;   int* d_err = nullptr;
     uint32_t n_items = 0;
 
@@ -75,10 +77,35 @@ int grow(msnv_ctx* ctx, T*& p, uint64_t n)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Blocks of a finished shard go to a pool: the next shard (e.g. the next genome bin of the same
+// sample set) reuses them instead of paying cudaFree (a device-wide sync) and cudaMalloc per sample.
 void free_samples(msnv_ctx* ctx)
 {
-    for (void* p : ctx->sample_allocs) cudaFree(p);
+    for (auto& b : ctx->pool) cudaFree(b.first);
+    ctx->pool.swap(ctx->sample_allocs);
     ctx->sample_allocs.clear();
+}
+
+void* take_block(msnv_ctx* ctx, size_t bytes)
+{
+    size_t best = (size_t)-1, bi = 0;
+    for (size_t i = 0; i < ctx->pool.size(); ++i)
+        if (ctx->pool[i].second >= bytes && ctx->pool[i].second < best) { best = ctx->pool[i].second; bi = i; }
+    void* p = nullptr;
+    if (best != (size_t)-1 && best <= bytes + bytes / 4 + (1u << 20)) {
+        p = ctx->pool[bi].first;
+        ctx->sample_allocs.push_back(ctx->pool[bi]);
+        ctx->pool[bi] = ctx->pool.back(); ctx->pool.pop_back();
+        return p;
+    }
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        for (auto& b : ctx->pool) cudaFree(b.first);         // give the pool back and retry once
+        ctx->pool.clear();
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    ctx->sample_allocs.push_back({p, bytes});
+    return p;
 }
 
 int ensure_hits(msnv_ctx* ctx, uint64_t n_hits)
@@ -209,9 +236,10 @@ void msnv_destroy(msnv_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_samples(ctx);
+    free_samples(ctx);                              // second call empties the pool as well
     cudaFree(ctx->d_samples); cudaFree(ctx->d_ref);
     cudaFree(ctx->d_items); cudaFree(ctx->d_acgt); cudaFree(ctx->d_ncnt);
-    cudaFree(ctx->d_tile_begin); cudaFree(ctx->d_tile_hits); cudaFree(ctx->d_flags); cudaFree(ctx->d_block_sums);
+    cudaFree(ctx->d_tile_begin); cudaFree(ctx->d_tile_hits); cudaFree(ctx->d_flags); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_range_cache);
     cudaFree(ctx->d_scalar); cudaFree(ctx->d_err);
     cudaFree(ctx->d_hit_pos); cudaFree(ctx->d_hit_total); cudaFree(ctx->d_hit_pop); cudaFree(ctx->d_hit_ind);
     cudaFree(ctx->d_hit_cov); cudaFree(ctx->d_hit_allele);
@@ -279,10 +307,8 @@ int msnv_shard_add_sample(msnv_ctx* ctx, uint32_t sample, const msnv_sample_read
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes + 32, 256); return o; };
     const size_t o_pos = take(n * 4), o_cgo = take(n1 * 4), o_sgo = take(n1 * 4), o_q4 = take(n1 * 4), o_mate = take(n * 4),
                  o_cig = take(n_cig * 4), o_seq = take(n_q4), o_qual = take(n_q4 * 4);
-    uint8_t* base = nullptr;
-    cudaError_t e = cudaMalloc((void**)&base, off);
-    if (e != cudaSuccess) return fail(ctx, MSNV_E_NOMEM, "sample %u: cudaMalloc(%zu) failed: %s", sample, off, cudaGetErrorString(e));
-    ctx->sample_allocs.push_back(base);
+    uint8_t* base = (uint8_t*)take_block(ctx, off);
+    if (!base) return fail(ctx, MSNV_E_NOMEM, "sample %u: cannot allocate %zu bytes of device memory", sample, off);
     cudaStream_t st = ctx->stream;
     CU(cudaMemcpyAsync(base + o_pos, r->pos, n * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_cgo, r->cig_off, n1 * 4, cudaMemcpyHostToDevice, st));
@@ -342,7 +368,13 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
     const uint64_t n_blocks = (n_pairs_idx + 255) / 256;
     if (n_blocks > 0x7fffffffull) return fail(ctx, MSNV_E_LIMIT, "shard too large: %u tiles x %u samples", n_tiles, S);
     if (n_blocks > ctx->cap_blocks) { if (grow(ctx, ctx->d_block_sums, n_blocks)) return MSNV_E_CUDA; ctx->cap_blocks = n_blocks; }
-    index_kernel<false><<<(unsigned)n_blocks, 256, 0, st>>>(ctx->d_samples, S, n_tiles, ctx->d_block_sums, nullptr, nullptr);
+    // the (r_lo, r_hi) of every pair found by the counting pass is kept for the emitting pass when it fits 1 GiB
+    uint2* cache = nullptr;
+    if (n_pairs_idx * 8 <= (1ull << 30)) {
+        if (n_pairs_idx > ctx->cap_range) { if (grow(ctx, ctx->d_range_cache, n_pairs_idx)) return MSNV_E_CUDA; ctx->cap_range = n_pairs_idx; }
+        cache = ctx->d_range_cache;
+    }
+    index_kernel<false><<<(unsigned)n_blocks, 256, 0, st>>>(ctx->d_samples, S, n_tiles, ctx->d_block_sums, nullptr, nullptr, cache);
     scan_kernel<<<1, 1024, 0, st>>>(ctx->d_block_sums, (uint32_t)n_blocks, ctx->d_scalar);
     launches += 2;
     CU(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, 4, cudaMemcpyDeviceToHost, st));
@@ -350,7 +382,7 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
     const uint32_t n_items = ctx->h_scalar[0];
     ctx->n_items = n_items;
     if (int rc = ensure_items(ctx, n_items)) return rc;
-    index_kernel<true><<<(unsigned)n_blocks, 256, 0, st>>>(ctx->d_samples, S, n_tiles, ctx->d_block_sums, ctx->d_items, ctx->d_tile_begin);
+    index_kernel<true><<<(unsigned)n_blocks, 256, 0, st>>>(ctx->d_samples, S, n_tiles, ctx->d_block_sums, ctx->d_items, ctx->d_tile_begin, cache);
     ++launches;
     CU(cudaMemcpyAsync(ctx->d_tile_begin + n_tiles, ctx->d_scalar, 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaEventRecord(ctx->ev[1], st));
@@ -484,9 +516,8 @@ int msnv_shard_synth(msnv_ctx* ctx, const msnv_synth_desc* d, int64_t* first_col
         size_t o = 0;
         auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes + 32, 256); return r; };
         const size_t o_pos = take(n * 4), o_cgo = take(n1 * 4), o_sgo = take(n1 * 4), o_q4 = take(n1 * 4), o_mate = take(n * 4);
-        uint8_t* meta = nullptr;
-        if (cudaMalloc((void**)&meta, o) != cudaSuccess) return fail(ctx, MSNV_E_NOMEM, "msnv_shard_synth: out of device memory (sample %u)", s);
-        ctx->sample_allocs.push_back(meta);
+        uint8_t* meta = (uint8_t*)take_block(ctx, o);
+        if (!meta) return fail(ctx, MSNV_E_NOMEM, "msnv_shard_synth: out of device memory (sample %u)", s);
         SynthSampleCtg* d_blocks = nullptr; uint32_t *d_frag0 = nullptr, *d_nops = nullptr, *d_nsegs = nullptr, *d_for = nullptr;
         CU(cudaMalloc((void**)&d_blocks, nb * sizeof(SynthSampleCtg)));
         CU(cudaMalloc((void**)&d_frag0, (nb + 1) * 4));
@@ -506,9 +537,8 @@ int msnv_shard_synth(msnv_ctx* ctx, const msnv_synth_desc* d, int64_t* first_col
         const size_t n_q4 = n * q4;
         o = 0;
         const size_t o_cig = take((size_t)n_cig * 4), o_seq = take(n_q4), o_qual = take(n_q4 * 4);
-        uint8_t* data = nullptr;
-        if (cudaMalloc((void**)&data, o) != cudaSuccess) return fail(ctx, MSNV_E_NOMEM, "msnv_shard_synth: out of device memory (sample %u)", s);
-        ctx->sample_allocs.push_back(data);
+        uint8_t* data = (uint8_t*)take_block(ctx, o);
+        if (!data) return fail(ctx, MSNV_E_NOMEM, "msnv_shard_synth: out of device memory (sample %u)", s);
         synth_fill_kernel<<<(unsigned)((n_q4 + 255) / 256), 256, 0, st>>>(m, (int)s, paired, d_blocks, d_frag0, (uint32_t)nb, (uint32_t)n,
             (const int32_t*)(meta + o_pos), (const uint32_t*)(meta + o_cgo), d_for, (uint32_t*)(data + o_cig), data + o_seq, data + o_qual);
         CU(cudaStreamSynchronize(st));

@@ -125,3 +125,53 @@ def bed_header(data_dir, out_path):
                 continue
             f.write(cols[1].replace("SN:", "") + "\t1\t" + cols[2].replace("LN:", "") + "\n")
     return out_path
+
+
+def stage_metasnv(tree, mode):
+    """Build a directory that looks like a metaSNV checkout to the reference's UNCHANGED metaSNV.py
+    (staged by oracle/Makefile into oracle/_ref/metaSNV): the scripts are symlinked, the three worker
+    programs are either the product's (mode 'gpu') or the oracle's (mode 'oracle').
+    Returns (path to metaSNV.py, env with PATH set so that `samtools` resolves to the chosen stand-in)."""
+    src = os.path.join(ORACLE_BIN, "metaSNV")
+    if not os.path.exists(os.path.join(src, "metaSNV.py")):
+        raise RuntimeError("oracle/_ref/metaSNV is missing: run `make -C oracle` where /root/reference exists")
+    if os.path.isdir(tree):
+        shutil.rmtree(tree)
+    os.makedirs(os.path.join(tree, "src", "qaTools"))
+    os.makedirs(os.path.join(tree, "src", "snpCaller"))
+    os.makedirs(os.path.join(tree, "shim"))
+    os.symlink(os.path.join(src, "metaSNV.py"), os.path.join(tree, "metaSNV.py"))
+    for f in ("computeGenomeCoverage.py", "collapse_coverages.py", "createOptimumSplit.py"):
+        os.symlink(os.path.join(src, "src", f), os.path.join(tree, "src", f))
+    if mode == "gpu":
+        os.symlink(bin_path("qaCompute"), os.path.join(tree, "src", "qaTools", "qaCompute"))
+        os.symlink(bin_path("snpCall"), os.path.join(tree, "src", "snpCaller", "snpCall"))
+        os.symlink(bin_path("samtools"), os.path.join(tree, "shim", "samtools"))
+    else:
+        qa = oracle_bin("qaCompute_ref") if os.path.exists(oracle_bin("qaCompute_ref")) else oracle_bin("qacompute_oracle")
+        sc = oracle_bin("snpCall_ref") if os.path.exists(oracle_bin("snpCall_ref")) else oracle_bin("snpcall_oracle")
+        os.symlink(qa, os.path.join(tree, "src", "qaTools", "qaCompute"))
+        os.symlink(sc, os.path.join(tree, "src", "snpCaller", "snpCall"))
+        os.symlink(oracle_bin("mpileup_oracle"), os.path.join(tree, "shim", "samtools"))
+    env = dict(os.environ)
+    env["PATH"] = os.path.join(tree, "shim") + os.pathsep + env.get("PATH", "")
+    return os.path.join(tree, "metaSNV.py"), env
+
+
+def run_metasnv(script, env, out_dir, all_samples, ref, threads=1, n_splits=1, db_ann=None):
+    import sys
+    if os.path.isdir(out_dir):
+        shutil.rmtree(out_dir)
+    cmd = [sys.executable, script, out_dir, all_samples, ref, "--threads", str(threads), "--n_splits", str(n_splits)]
+    if db_ann:
+        cmd += ["--db_ann", db_ann]
+    return subprocess.run(cmd, env=env, capture_output=True, text=True)
+
+
+def tree_files(root):
+    out = {}
+    for d, _, fs in os.walk(root):
+        for f in fs:
+            p = os.path.join(d, f)
+            out[os.path.relpath(p, root)] = p
+    return out

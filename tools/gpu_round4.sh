@@ -1,11 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 tools/microbench/atoms_bench.cu -o /tmp/atoms_bench && /tmp/atoms_bench > gpurun_out/atoms_bench.txt 2>&1
-cat gpurun_out/atoms_bench.txt
 timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -n 6 gpurun_out/pytest_gpu.log
 NV="nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared metasnv_b200/csrc/gpu/msnv_gpu.cu"
-$NV -DMSNV_PILEUP_MIN_CTAS=4 -o /tmp/lib_c4.so
+$NV -DMSNV_PILEUP_MIN_CTAS=3 -o /tmp/lib_c4.so
 $NV -DMSNV_PILEUP_MIN_CTAS=2 -o /tmp/lib_c2.so
 $NV -DMSNV_TILE=256 -o /tmp/lib_t256.so
 B="python bench.py --scale 0.1 --steps 3 --no-e2e --no-cpu-baseline"
