@@ -20,13 +20,13 @@
 namespace msnv_gpu {
 
 constexpr int TILE = MSNV_TILE;                 // positions per tile == threads per pileup CTA
-constexpr int PILEUP_THREADS = TILE;
-constexpr int CHUNK_READS = TILE / 2 - 1 < 255 ? TILE / 2 - 1 : 255;   // reads staged per chunk (8-bit per-chunk counters;
-                                                                       // the second half of the CTA corrects mate overlaps)
-constexpr int CHUNK_Q4 = TILE * 8;              // 4-base groups staged per chunk (TILE*32 bases)
-constexpr int CHUNK_SEGS = TILE;                // aligned segments per chunk
+constexpr int PILEUP_THREADS = 256;             // threads per pileup CTA (each folds TILE/256 positions)
+constexpr int CHUNK_READS = 255;                // reads staged per chunk (8-bit per-chunk counters, one walk thread per read)
+constexpr int CHUNK_Q4_MAX = 4096;              // upper bound of the 4-base groups staged per chunk (chosen per launch)
+constexpr int CHUNK_Q4_MIN = MSNV_MAX_READ_BASES / 4;   // a single read always fits
+constexpr int CHUNK_SEGS = 512;                 // aligned segments per chunk
 
-static_assert(MSNV_MAX_READ_BASES * 2 <= CHUNK_Q4 * 4, "one read must fit a chunk with room to spare");
+static_assert(TILE % PILEUP_THREADS == 0 && PILEUP_THREADS >= 256, "one walk thread per staged read");
 static_assert(MSNV_MAX_READ_CIGAR * 2 <= CHUNK_SEGS, "one read's segments must fit a chunk");
 
 struct SampleDev {
@@ -248,8 +248,8 @@ __device__ __forceinline__ void overlap_rule(uint32_t va, uint32_t vb, bool same
 }
 
 // ------------------------------------------------------------------------------------------------
-// pileup: one CTA per work item (sample, tile).
-// Per chunk of reads (<= CHUNK_READS reads, CHUNK_Q4*4 bases, CHUNK_SEGS aligned segments):
+// pileup: one CTA of PILEUP_THREADS threads per work item (sample, tile of TILE positions).
+// Per chunk of reads (<= CHUNK_READS reads, chunk_q4*4 bases, CHUNK_SEGS aligned segments):
 //   1. metadata of the chunk's reads -> shared memory; __syncthreads_count sizes the chunk
 //   2. two TMA bulk copies (2-bit bases, qualities) are issued; while they fly,
 //   3. one thread per read walks its CIGAR (global, L2) into aligned segments and a descriptor of
@@ -258,36 +258,47 @@ __device__ __forceinline__ void overlap_rule(uint32_t va, uint32_t vb, bool same
 //      (mates staged in another chunk are read, pristine, from global memory)
 //   5. flat scatter: thread g takes the g-th 4-base group of the staged bytes, turns (2-bit base,
 //      quality) into four codes with SWAR arithmetic and adds each base that lies on the tile to
-//      its position's shared-memory counter (one byte lane per base letter) with ATOMS.ADD.
-//      Every staged base costs the same handful of instructions at full lane occupancy, whatever the
-//      depth; the counter words are XOR-swizzled so the stride-4 access of a warp is conflict free
-//      (measured: ~21 shared atomics per clock per SM, profiles/r01_microbench_shared_atomics.txt)
-//   6. thread i folds position i's byte lanes into its 16-bit packed registers and clears them
-// The reads in HBM are never modified.
+//      its position's shared-memory counter (one byte lane per base letter) with a predicated
+//      red.shared.add. Every staged base costs the same handful of instructions at full lane
+//      occupancy, whatever the depth; the counter words are XOR-swizzled so the stride-4 access of
+//      a warp is conflict free (measured: >= 21 shared atomics per clock per SM,
+//      profiles/r01_microbench_shared_atomics.txt)
+//   6. each thread folds the byte lanes of its positions into 16-bit packed registers and clears them
+// The reads in HBM are never modified. CTAs are small (8 warps) and the staging buffers are sized
+// at launch from the mean work per item, so that 6-8 CTAs per SM overlap each other's barriers
+// and copy latency.
 //
-// Shared memory (dynamic), regions 16-byte aligned:
+// Shared memory (dynamic), regions 16-byte aligned; the counters are aligned to their own size:
 //   s_meta   4 x META_STRIDE u32      pos | q4_off | seg_off | mate of the chunk's reads
-//   s_rd     CHUNK_READS x 16 bytes   {first segment: p_rel - base index, lo, span; first seg | n segs << 16}
-//   s_seq    CHUNK_Q4 + 32 bytes      2-bit bases           (TMA destination)
-//   s_qual   4*CHUNK_Q4 + 32 bytes    qualities             (TMA destination)
-//   s_g2r    CHUNK_Q4 bytes           read index of every 4-base group
+//   s_rd     256 x 16 bytes           {first segment: p_rel - base index, lo, span; first seg | n segs << 16}
 //   s_seg    CHUNK_SEGS x 16 bytes    {ref begin, length, byte address of first quality, read index}
 //   s_cnt    2 x TILE u32             A|C|G|T byte lanes, non-ACGT count
+//   s_seq    chunk_q4 + 32 bytes      2-bit bases           (TMA destination)
+//   s_qual   4*chunk_q4 + 32 bytes    qualities             (TMA destination)
+//   s_g2r    chunk_q4 bytes           read index of every 4-base group
 // Codes are shift amounts: 0,8,16,24 = A,C,G,T with quality >= 13; 32 = non-ACGT base with
 // quality >= 13; 64 = not counted.
 // ------------------------------------------------------------------------------------------------
 constexpr int META_STRIDE = 260;
-constexpr size_t PILEUP_SMEM = 4 * META_STRIDE * 4 + 256 * 16 + (CHUNK_Q4 + 32) + (4 * CHUNK_Q4 + 32) + CHUNK_Q4 + CHUNK_SEGS * 16 +
-                               2 * TILE * 4 + 256 * 2 + 64;
+constexpr int PILEUP_POS_PER_THREAD = TILE / PILEUP_THREADS;
+constexpr size_t PILEUP_SMEM_FIXED = 4 * META_STRIDE * 4 + 256 * 16 + CHUNK_SEGS * 16 + 256 * 2 + 64 + (2 * TILE * 4) + TILE * 4 /*alignment slack*/;
+__host__ __device__ constexpr size_t pileup_smem_bytes(uint32_t chunk_q4) { return PILEUP_SMEM_FIXED + (chunk_q4 + 32) + (4 * (size_t)chunk_q4 + 32) + chunk_q4 + 32; }
 
 // counter word of tile-relative position p: XOR swizzle so that positions 4 apart fall in different banks
 __device__ __forceinline__ uint32_t cnt_slot(uint32_t p) { return p ^ ((p >> 5) & 3u); }
 
+// if (a < b) shared[addr] += val, without a branch
+__device__ __forceinline__ void red_shared_add_if_lt(uint32_t addr, uint32_t val, uint32_t a, uint32_t b)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %2, %3;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
+                 :: "r"(addr), "r"(val), "r"(a), "r"(b) : "memory");
+}
+
 #ifndef MSNV_PILEUP_MIN_CTAS
-#define MSNV_PILEUP_MIN_CTAS (TILE >= 512 ? 4 : 8)
+#define MSNV_PILEUP_MIN_CTAS 6
 #endif
 __global__ void __launch_bounds__(PILEUP_THREADS, MSNV_PILEUP_MIN_CTAS)
-pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items,
+pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items, uint32_t chunk_q4,
               uint64_t* __restrict__ acgt /*[n_items][TILE]*/, uint16_t* __restrict__ ncnt /*[n_items][TILE]*/,
               int* __restrict__ err_flag)
 {
@@ -297,15 +308,18 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     uint32_t* s_sgo = s_q4 + META_STRIDE;
     int32_t*  s_mate = (int32_t*)(s_sgo + META_STRIDE);
     uint4*    s_rd   = (uint4*)(s_mate + META_STRIDE);
-    uint8_t*  s_seq  = (uint8_t*)(s_rd + 256);
-    uint8_t*  s_qual = s_seq + CHUNK_Q4 + 32;
-    uint8_t*  s_g2r  = s_qual + 4 * CHUNK_Q4 + 32;
-    uint4*    s_seg  = (uint4*)(s_g2r + CHUNK_Q4);
-    uint32_t* s_cnt  = (uint32_t*)(s_seg + CHUNK_SEGS);
-    uint32_t* s_cntn = s_cnt + TILE;
-    uint16_t* s_pairs = (uint16_t*)(s_cntn + TILE);
+    uint4*    s_seg  = s_rd + 256;
+    uint16_t* s_pairs = (uint16_t*)(s_seg + CHUNK_SEGS);
     uint64_t* s_bar  = (uint64_t*)(s_pairs + 256);
     uint32_t* s_misc = (uint32_t*)(s_bar + 1);        // [0] number of overlap tasks of the chunk
+    // counters: aligned to TILE*4 bytes in the shared window so that base | offset == base + offset
+    const uint32_t after_fixed = smem_u32(s_misc) + 56;
+    const uint32_t cnt_base = (after_fixed + TILE * 4 - 1) & ~(uint32_t)(TILE * 4 - 1);
+    uint32_t* s_cnt  = (uint32_t*)(smem + (cnt_base - smem_u32(smem)));
+    uint32_t* s_cntn = s_cnt + TILE;
+    uint8_t*  s_seq  = (uint8_t*)(s_cntn + TILE);
+    uint8_t*  s_qual = s_seq + chunk_q4 + 32;
+    uint8_t*  s_g2r  = s_qual + 4 * chunk_q4 + 32;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const Item it = items[blockIdx.x];
@@ -313,10 +327,13 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     const SampleDev* __restrict__ sd = samples + it.sample;
 
     if (tid == 0) { mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    s_cnt[tid] = 0; s_cntn[tid] = 0;
+    #pragma unroll
+    for (int k = 0; k < PILEUP_POS_PER_THREAD; ++k) { s_cnt[tid + k * PILEUP_THREADS] = 0; s_cntn[tid + k * PILEUP_THREADS] = 0; }
 
-    uint64_t acc = 0;       // A | C<<16 | G<<32 | T<<48 of position p0 + tid
-    uint32_t acc_n = 0;
+    uint64_t acc[PILEUP_POS_PER_THREAD];      // A | C<<16 | G<<32 | T<<48 of positions p0 + tid + k*PILEUP_THREADS
+    uint32_t acc_n[PILEUP_POS_PER_THREAD];
+    #pragma unroll
+    for (int k = 0; k < PILEUP_POS_PER_THREAD; ++k) { acc[k] = 0; acc_n[k] = 0; }
     uint32_t parity = 0;
 
     for (uint32_t c0 = it.r_lo; c0 < it.r_hi;) {
@@ -328,7 +345,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
             const uint32_t* q4p = sd->q4_off + c0; const uint32_t* sgp = sd->seg_off + c0;
             const uint32_t q = __ldg(q4p + tid), g = __ldg(sgp + tid);
             s_q4[tid] = q; s_sgo[tid] = g;
-            fits = tid >= 1 && q - __ldg(q4p) <= CHUNK_Q4 && g - __ldg(sgp) <= CHUNK_SEGS;
+            fits = tid >= 1 && q - __ldg(q4p) <= chunk_q4 && g - __ldg(sgp) <= CHUNK_SEGS;
             if (tid < n) { s_pos[tid] = (uint32_t)__ldg(sd->pos + c0 + tid); s_mate[tid] = __ldg(sd->mate + c0 + tid); }
         }
         if (tid == 0) s_misc[0] = 0;
@@ -476,9 +493,12 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                 x = (x & pm) | (0x40404040u & ~pm);               // CODE_SKIP below the quality threshold
                 const uint32_t pr0 = rd.x + g * 4u;               // tile-relative position of the group's first base
                 const uint32_t t0 = pr0 - rd.y;
+                const uint32_t a0 = cnt_base + pr0 * 4u;          // == cnt_base | pr0*4 for positions on the tile
                 #pragma unroll
-                for (uint32_t k = 0; k < 4; ++k)
-                    if (t0 + k < rd.z) atomicAdd(&s_cnt[cnt_slot(pr0 + k)], shl1_clamped32((x >> (8 * k)) & 0xffu));
+                for (uint32_t k = 0; k < 4; ++k) {
+                    const uint32_t ak = a0 + 4u * k;
+                    red_shared_add_if_lt(ak ^ ((ak >> 5) & 12u), shl1_clamped32((x >> (8 * k)) & 0xffu), t0 + k, rd.z);
+                }
                 if (x & 0x20202020u) {                            // rare: non-ACGT bases count on their own plane
                     #pragma unroll
                     for (uint32_t k = 0; k < 4; ++k)
@@ -505,25 +525,30 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
         __syncthreads();
 
         // ---- 6. fold this chunk's byte lanes (a position sees at most m <= 255 reads per chunk)
-        {
-            const uint32_t sl = cnt_slot(tid);
+        #pragma unroll
+        for (int k = 0; k < PILEUP_POS_PER_THREAD; ++k) {
+            const uint32_t p = tid + k * PILEUP_THREADS;
+            const uint32_t sl = cnt_slot(p);
             const uint32_t a8 = s_cnt[sl];
             if (a8) {
                 s_cnt[sl] = 0;
-                acc += (uint64_t)(a8 & 0xffu) | (uint64_t)((a8 >> 8) & 0xffu) << 16 | (uint64_t)((a8 >> 16) & 0xffu) << 32 |
-                       (uint64_t)(a8 >> 24) << 48;
+                acc[k] += (uint64_t)(a8 & 0xffu) | (uint64_t)((a8 >> 8) & 0xffu) << 16 | (uint64_t)((a8 >> 16) & 0xffu) << 32 |
+                          (uint64_t)(a8 >> 24) << 48;
             }
-            const uint32_t cn = s_cntn[tid];
-            if (cn) { s_cntn[tid] = 0; acc_n += cn; }
+            const uint32_t cn = s_cntn[p];
+            if (cn) { s_cntn[p] = 0; acc_n[k] += cn; }
         }
         c0 += m;
         // no barrier here: the next chunk only touches the counters again after two more barriers
     }
 
     // ---- 7. flush: 8 B + 2 B per position, fully coalesced
-    const size_t o = (size_t)blockIdx.x * TILE + tid;
-    acgt[o] = acc;
-    ncnt[o] = (uint16_t)acc_n;
+    #pragma unroll
+    for (int k = 0; k < PILEUP_POS_PER_THREAD; ++k) {
+        const size_t o = (size_t)blockIdx.x * TILE + tid + k * PILEUP_THREADS;
+        acgt[o] = acc[k];
+        ncnt[o] = (uint16_t)acc_n[k];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -226,7 +227,7 @@ int msnv_create(int device, msnv_ctx** out)
     CU(cudaMalloc((void**)&ctx->d_scalar, 16));
     CU(cudaMalloc((void**)&ctx->d_err, 4));
     CU(cudaMallocHost((void**)&ctx->h_scalar, 16));
-    CU(cudaFuncSetAttribute(pileup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PILEUP_SMEM));
+    CU(cudaFuncSetAttribute(pileup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pileup_smem_bytes(CHUNK_Q4_MAX)));
     return MSNV_OK;
 }
 
@@ -391,7 +392,15 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
 
     // ---- pileup
     if (n_items) {
-        pileup_kernel<<<n_items, PILEUP_THREADS, PILEUP_SMEM, st>>>(ctx->d_samples, ctx->d_items, n_items, ctx->d_acgt, ctx->d_ncnt, ctx->d_err);
+        // staging buffers sized from the mean work per item (+25 %, at least one maximal read): smaller
+        // buffers let more CTAs share an SM; an item that does not fit simply takes another chunk
+        uint64_t mean_q4 = ctx->n_bases / 4 / n_items;
+        uint32_t chunk_q4 = (uint32_t)((mean_q4 * 3 / 2 + 255) / 256 * 256);
+        if (const char* e = getenv("MSNV_CHUNK_Q4")) chunk_q4 = (uint32_t)atoi(e) / 256 * 256;
+        if (chunk_q4 < (uint32_t)CHUNK_Q4_MIN) chunk_q4 = CHUNK_Q4_MIN;
+        if (chunk_q4 > (uint32_t)CHUNK_Q4_MAX) chunk_q4 = CHUNK_Q4_MAX;
+        pileup_kernel<<<n_items, PILEUP_THREADS, pileup_smem_bytes(chunk_q4), st>>>(ctx->d_samples, ctx->d_items, n_items, chunk_q4, ctx->d_acgt,
+                                                                                     ctx->d_ncnt, ctx->d_err);
         ++launches;
     }
     CU(cudaEventRecord(ctx->ev[3], st));
