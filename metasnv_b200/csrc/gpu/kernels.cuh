@@ -295,7 +295,7 @@ __device__ __forceinline__ void red_shared_add_if_lt(uint32_t addr, uint32_t val
 }
 
 #ifndef MSNV_PILEUP_MIN_CTAS
-#define MSNV_PILEUP_MIN_CTAS 6
+#define MSNV_PILEUP_MIN_CTAS 5
 #endif
 __global__ void __launch_bounds__(PILEUP_THREADS, MSNV_PILEUP_MIN_CTAS)
 pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items, uint32_t chunk_q4,
@@ -313,9 +313,10 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     uint64_t* s_bar  = (uint64_t*)(s_pairs + 256);
     uint32_t* s_misc = (uint32_t*)(s_bar + 1);        // [0] number of overlap tasks of the chunk
     // counters: aligned to TILE*4 bytes in the shared window so that base | offset == base + offset
+    const uint32_t smem_base = smem_u32(smem);
     const uint32_t after_fixed = smem_u32(s_misc) + 56;
     const uint32_t cnt_base = (after_fixed + TILE * 4 - 1) & ~(uint32_t)(TILE * 4 - 1);
-    uint32_t* s_cnt  = (uint32_t*)(smem + (cnt_base - smem_u32(smem)));
+    uint32_t* s_cnt  = (uint32_t*)(smem + (cnt_base - smem_base));
     uint32_t* s_cntn = s_cnt + TILE;
     uint8_t*  s_seq  = (uint8_t*)(s_cntn + TILE);
     uint8_t*  s_qual = s_seq + chunk_q4 + 32;
@@ -413,8 +414,10 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
         // alone is rewritten, the mate's pristine data come from global memory.
         const uint32_t n_tasks = s_misc[0];
         if (n_tasks) {
-            for (uint32_t t = warp; t < n_tasks; t += PILEUP_THREADS / 32) {
-                const uint32_t i = s_pairs[t];
+            // one thread per task: the work per pair is a few dozen shared-memory bytes, far too little to
+            // spread over a warp (a warp per pair spent ~200 instructions per pair on set-up alone)
+            if (tid < n_tasks) {
+                const uint32_t i = s_pairs[tid];
                 const int32_t mt = s_mate[i];
                 const bool self_is_a = c0 + i < (uint32_t)mt;
                 const bool mate_here = (uint32_t)mt >= c0 && (uint32_t)mt < c0 + m;
@@ -428,8 +431,8 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                             const uint4 B = s_seg[kb];
                             const int32_t lo = max(max((int32_t)A.x, (int32_t)B.x), p0);
                             const int32_t hi = min(min((int32_t)(A.x + A.y), (int32_t)(B.x + B.y)), p0 + TILE);
-                            for (int32_t p = lo + (int32_t)lane; p < hi; p += 32) {
-                                const uint32_t za = A.z + (uint32_t)(p - (int32_t)A.x), zb = B.z + (uint32_t)(p - (int32_t)B.x);
+                            uint32_t za = A.z + (uint32_t)(lo - (int32_t)A.x), zb = B.z + (uint32_t)(lo - (int32_t)B.x);
+                            for (int32_t p = lo; p < hi; ++p, ++za, ++zb) {
                                 const uint32_t va = s_qual[za], vb = s_qual[zb];
                                 const uint32_t ia = za - d_qual, ib = zb - d_qual;     // base index inside the staged range
                                 const uint32_t ba = (s_seq[d_seq + (ia >> 2)] >> ((ia & 3) * 2)) & 3u;
@@ -442,7 +445,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                         }
                     }
                 } else {
-                    // walk the mate's CIGAR from global memory (every lane the same way), lanes over positions
+                    // the mate is staged in another chunk: walk its CIGAR and read its pristine bytes from global memory
                     const uint32_t mc0 = __ldg(sd->cig_off + mt), mn = __ldg(sd->cig_off + mt + 1) - mc0;
                     const uint32_t mq4 = __ldg(sd->q4_off + mt);
                     const uint8_t* mq = sd->qual + (size_t)mq4 * 4;
@@ -455,7 +458,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                                 const uint4 A = s_seg[ka];
                                 const int32_t lo = max(max((int32_t)A.x, bx), p0);
                                 const int32_t hi = min(min((int32_t)(A.x + A.y), bx + (int32_t)len), p0 + TILE);
-                                for (int32_t p = lo + (int32_t)lane; p < hi; p += 32) {
+                                for (int32_t p = lo; p < hi; ++p) {
                                     const uint32_t zs = A.z + (uint32_t)(p - (int32_t)A.x), im = by + (uint32_t)(p - bx);
                                     const uint32_t vs = s_qual[zs], vm = mq[im];
                                     const uint32_t is = zs - d_qual;
@@ -493,11 +496,15 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                 x = (x & pm) | (0x40404040u & ~pm);               // CODE_SKIP below the quality threshold
                 const uint32_t pr0 = rd.x + g * 4u;               // tile-relative position of the group's first base
                 const uint32_t t0 = pr0 - rd.y;
-                const uint32_t a0 = cnt_base + pr0 * 4u;          // == cnt_base | pr0*4 for positions on the tile
+                // unconditional atomics: a base off the tile (or outside the first segment) adds 0 to a
+                // clamped address, which is cheaper than a divergent branch around every ATOMS
+                const uint32_t a0 = cnt_base | ((pr0 * 4u) & (uint32_t)(TILE * 4 - 1));
                 #pragma unroll
                 for (uint32_t k = 0; k < 4; ++k) {
-                    const uint32_t ak = a0 + 4u * k;
-                    red_shared_add_if_lt(ak ^ ((ak >> 5) & 12u), shl1_clamped32((x >> (8 * k)) & 0xffu), t0 + k, rd.z);
+                    const uint32_t ak = (a0 + 4u * k) & ~(uint32_t)(TILE * 4);      // stays inside the counter array
+                    uint32_t inc = shl1_clamped32((x >> (8 * k)) & 0xffu);
+                    if (t0 + k >= rd.z) inc = 0;
+                    atomicAdd((uint32_t*)(smem + ((ak ^ ((ak >> 5) & 12u)) - smem_base)), inc);
                 }
                 if (x & 0x20202020u) {                            // rare: non-ACGT bases count on their own plane
                     #pragma unroll
