@@ -498,10 +498,10 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                 const uint32_t t0 = pr0 - rd.y;
                 // unconditional atomics: a base off the tile (or outside the first segment) adds 0 to a
                 // clamped address, which is cheaper than a divergent branch around every ATOMS
-                const uint32_t a0 = cnt_base | ((pr0 * 4u) & (uint32_t)(TILE * 4 - 1));
+                const uint32_t o0 = pr0 * 4u;
                 #pragma unroll
                 for (uint32_t k = 0; k < 4; ++k) {
-                    const uint32_t ak = (a0 + 4u * k) & ~(uint32_t)(TILE * 4);      // stays inside the counter array
+                    const uint32_t ak = cnt_base | ((o0 + 4u * k) & (uint32_t)(TILE * 4 - 1));   // wraps inside the counter array
                     uint32_t inc = shl1_clamped32((x >> (8 * k)) & 0xffu);
                     if (t0 + k >= rd.z) inc = 0;
                     atomicAdd((uint32_t*)(smem + ((ak ^ ((ak >> 5) & 12u)) - smem_base)), inc);
