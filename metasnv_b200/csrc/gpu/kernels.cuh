@@ -21,10 +21,16 @@ namespace msnv_gpu {
 
 constexpr int TILE = MSNV_TILE;                 // positions per tile == threads per pileup CTA
 constexpr int PILEUP_THREADS = 256;             // threads per pileup CTA (each folds TILE/256 positions)
-constexpr int CHUNK_READS = 255;                // reads staged per chunk (8-bit per-chunk counters, one walk thread per read)
+#ifndef MSNV_CHUNK_READS
+#define MSNV_CHUNK_READS 255
+#endif
+constexpr int CHUNK_READS = MSNV_CHUNK_READS;   // reads staged per chunk (<= 255: 8-bit per-chunk counters, one walk thread per read)
 constexpr int CHUNK_Q4_MAX = 4096;              // upper bound of the 4-base groups staged per chunk (chosen per launch)
 constexpr int CHUNK_Q4_MIN = MSNV_MAX_READ_BASES / 4;   // a single read always fits
-constexpr int CHUNK_SEGS = 512;                 // aligned segments per chunk
+#ifndef MSNV_CHUNK_SEGS
+#define MSNV_CHUNK_SEGS 512
+#endif
+constexpr int CHUNK_SEGS = MSNV_CHUNK_SEGS;     // aligned segments per chunk
 
 static_assert(TILE % PILEUP_THREADS == 0 && PILEUP_THREADS >= 256, "one walk thread per staged read");
 static_assert(MSNV_MAX_READ_CIGAR * 2 <= CHUNK_SEGS, "one read's segments must fit a chunk");
@@ -279,9 +285,10 @@ __device__ __forceinline__ void overlap_rule(uint32_t va, uint32_t vb, bool same
 // Codes are shift amounts: 0,8,16,24 = A,C,G,T with quality >= 13; 32 = non-ACGT base with
 // quality >= 13; 64 = not counted.
 // ------------------------------------------------------------------------------------------------
-constexpr int META_STRIDE = 260;
+constexpr int META_STRIDE = (CHUNK_READS + 1 + 3) / 4 * 4;
+constexpr int RD_SLOTS = (CHUNK_READS + 1 + 3) / 4 * 4;
 constexpr int PILEUP_POS_PER_THREAD = TILE / PILEUP_THREADS;
-constexpr size_t PILEUP_SMEM_FIXED = 4 * META_STRIDE * 4 + 256 * 16 + CHUNK_SEGS * 16 + 256 * 2 + 64 + (2 * TILE * 4) + TILE * 4 /*alignment slack*/;
+constexpr size_t PILEUP_SMEM_FIXED = 4 * META_STRIDE * 4 + RD_SLOTS * 16 + CHUNK_SEGS * 16 + RD_SLOTS * 2 + 64 + (2 * TILE * 4) + TILE * 4 /*alignment slack*/;
 __host__ __device__ constexpr size_t pileup_smem_bytes(uint32_t chunk_q4) { return PILEUP_SMEM_FIXED + (chunk_q4 + 32) + (4 * (size_t)chunk_q4 + 32) + chunk_q4 + 32; }
 
 // counter word of tile-relative position p: XOR swizzle so that positions 4 apart fall in different banks
@@ -308,9 +315,9 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     uint32_t* s_sgo = s_q4 + META_STRIDE;
     int32_t*  s_mate = (int32_t*)(s_sgo + META_STRIDE);
     uint4*    s_rd   = (uint4*)(s_mate + META_STRIDE);
-    uint4*    s_seg  = s_rd + 256;
+    uint4*    s_seg  = s_rd + RD_SLOTS;
     uint16_t* s_pairs = (uint16_t*)(s_seg + CHUNK_SEGS);
-    uint64_t* s_bar  = (uint64_t*)(s_pairs + 256);
+    uint64_t* s_bar  = (uint64_t*)(s_pairs + RD_SLOTS);
     uint32_t* s_misc = (uint32_t*)(s_bar + 1);        // [0] number of overlap tasks of the chunk
     // counters: aligned to TILE*4 bytes in the shared window so that base | offset == base + offset
     const uint32_t smem_base = smem_u32(smem);
