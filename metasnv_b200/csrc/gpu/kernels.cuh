@@ -21,19 +21,16 @@ namespace msnv_gpu {
 
 constexpr int TILE = MSNV_TILE;                 // positions per tile == threads per pileup CTA
 constexpr int PILEUP_THREADS = 256;             // threads per pileup CTA (each folds TILE/256 positions)
-#ifndef MSNV_CHUNK_READS
-#define MSNV_CHUNK_READS 255
-#endif
-constexpr int CHUNK_READS = MSNV_CHUNK_READS;   // reads staged per chunk (<= 255: 8-bit per-chunk counters, one walk thread per read)
+// reads staged per chunk: <= 255 (8-bit per-chunk counters, one walk thread per read). Two
+// instantiations of the pileup kernel: a small one for shallow data (8 CTAs per SM) and a large
+// one for deep data (fewer, longer chunks per tile)
+constexpr int CHUNK_READS_SMALL = 127, CHUNK_READS_LARGE = 255;
 constexpr int CHUNK_Q4_MAX = 4096;              // upper bound of the 4-base groups staged per chunk (chosen per launch)
 constexpr int CHUNK_Q4_MIN = MSNV_MAX_READ_BASES / 4;   // a single read always fits
-#ifndef MSNV_CHUNK_SEGS
-#define MSNV_CHUNK_SEGS 512
-#endif
-constexpr int CHUNK_SEGS = MSNV_CHUNK_SEGS;     // aligned segments per chunk
+constexpr int CHUNK_SEGS_SMALL = 256, CHUNK_SEGS_LARGE = 512;   // aligned segments per chunk
 
 static_assert(TILE % PILEUP_THREADS == 0 && PILEUP_THREADS >= 256, "one walk thread per staged read");
-static_assert(MSNV_MAX_READ_CIGAR * 2 <= CHUNK_SEGS, "one read's segments must fit a chunk");
+static_assert(MSNV_MAX_READ_CIGAR * 2 <= CHUNK_SEGS_SMALL, "one read's segments must fit a chunk");
 
 struct SampleDev {
     const int32_t*  pos;
@@ -285,11 +282,13 @@ __device__ __forceinline__ void overlap_rule(uint32_t va, uint32_t vb, bool same
 // Codes are shift amounts: 0,8,16,24 = A,C,G,T with quality >= 13; 32 = non-ACGT base with
 // quality >= 13; 64 = not counted.
 // ------------------------------------------------------------------------------------------------
-constexpr int META_STRIDE = (CHUNK_READS + 1 + 3) / 4 * 4;
-constexpr int RD_SLOTS = (CHUNK_READS + 1 + 3) / 4 * 4;
 constexpr int PILEUP_POS_PER_THREAD = TILE / PILEUP_THREADS;
-constexpr size_t PILEUP_SMEM_FIXED = 4 * META_STRIDE * 4 + RD_SLOTS * 16 + CHUNK_SEGS * 16 + RD_SLOTS * 2 + 64 + (2 * TILE * 4) + TILE * 4 /*alignment slack*/;
-__host__ __device__ constexpr size_t pileup_smem_bytes(uint32_t chunk_q4) { return PILEUP_SMEM_FIXED + (chunk_q4 + 32) + (4 * (size_t)chunk_q4 + 32) + chunk_q4 + 32; }
+__host__ __device__ constexpr size_t pileup_smem_bytes(int chunk_reads, int chunk_segs, uint32_t chunk_q4)
+{
+    return (size_t)(4 * ((chunk_reads + 4) / 4 * 4) * 4 + ((chunk_reads + 4) / 4 * 4) * 16 + chunk_segs * 16 + ((chunk_reads + 4) / 4 * 4) * 2 + 64 +
+                    (2 * TILE * 4) + TILE * 4 /*alignment slack*/) +
+           (chunk_q4 + 32) + (4 * (size_t)chunk_q4 + 32) + chunk_q4 + 32;
+}
 
 // counter word of tile-relative position p: XOR swizzle so that positions 4 apart fall in different banks
 __device__ __forceinline__ uint32_t cnt_slot(uint32_t p) { return p ^ ((p >> 5) & 3u); }
@@ -301,14 +300,13 @@ __device__ __forceinline__ void red_shared_add_if_lt(uint32_t addr, uint32_t val
                  :: "r"(addr), "r"(val), "r"(a), "r"(b) : "memory");
 }
 
-#ifndef MSNV_PILEUP_MIN_CTAS
-#define MSNV_PILEUP_MIN_CTAS 5
-#endif
-__global__ void __launch_bounds__(PILEUP_THREADS, MSNV_PILEUP_MIN_CTAS)
+template <int CHUNK_READS, int CHUNK_SEGS, int MIN_CTAS>
+__global__ void __launch_bounds__(PILEUP_THREADS, MIN_CTAS)
 pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items, uint32_t chunk_q4,
               uint64_t* __restrict__ acgt /*[n_items][TILE]*/, uint16_t* __restrict__ ncnt /*[n_items][TILE]*/,
               int* __restrict__ err_flag)
 {
+    constexpr int META_STRIDE = (CHUNK_READS + 4) / 4 * 4, RD_SLOTS = META_STRIDE;
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* s_pos = (uint32_t*)smem;
     uint32_t* s_q4  = s_pos + META_STRIDE;

@@ -227,7 +227,10 @@ int msnv_create(int device, msnv_ctx** out)
     CU(cudaMalloc((void**)&ctx->d_scalar, 16));
     CU(cudaMalloc((void**)&ctx->d_err, 4));
     CU(cudaMallocHost((void**)&ctx->h_scalar, 16));
-    CU(cudaFuncSetAttribute(pileup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pileup_smem_bytes(CHUNK_Q4_MAX)));
+    CU(cudaFuncSetAttribute(pileup_kernel<CHUNK_READS_SMALL, CHUNK_SEGS_SMALL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)pileup_smem_bytes(CHUNK_READS_SMALL, CHUNK_SEGS_SMALL, CHUNK_Q4_MAX)));
+    CU(cudaFuncSetAttribute(pileup_kernel<CHUNK_READS_LARGE, CHUNK_SEGS_LARGE, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)pileup_smem_bytes(CHUNK_READS_LARGE, CHUNK_SEGS_LARGE, CHUNK_Q4_MAX)));
     return MSNV_OK;
 }
 
@@ -399,8 +402,16 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
         if (const char* e = getenv("MSNV_CHUNK_Q4")) chunk_q4 = (uint32_t)atoi(e) / 256 * 256;
         if (chunk_q4 < (uint32_t)CHUNK_Q4_MIN) chunk_q4 = CHUNK_Q4_MIN;
         if (chunk_q4 > (uint32_t)CHUNK_Q4_MAX) chunk_q4 = CHUNK_Q4_MAX;
-        pileup_kernel<<<n_items, PILEUP_THREADS, pileup_smem_bytes(chunk_q4), st>>>(ctx->d_samples, ctx->d_items, n_items, chunk_q4, ctx->d_acgt,
-                                                                                     ctx->d_ncnt, ctx->d_err);
+        // shallow data (a tile's reads fit one small chunk): small buffers, 8 CTAs per SM; deep data: larger chunks
+        const uint64_t mean_reads = ctx->n_reads / n_items;
+        bool small = mean_reads * 2 <= (uint64_t)CHUNK_READS_SMALL;
+        if (const char* e = getenv("MSNV_PILEUP_VARIANT")) small = e[0] == 's';
+        if (small)
+            pileup_kernel<CHUNK_READS_SMALL, CHUNK_SEGS_SMALL, 8><<<n_items, PILEUP_THREADS, pileup_smem_bytes(CHUNK_READS_SMALL, CHUNK_SEGS_SMALL, chunk_q4), st>>>(
+                ctx->d_samples, ctx->d_items, n_items, chunk_q4, ctx->d_acgt, ctx->d_ncnt, ctx->d_err);
+        else
+            pileup_kernel<CHUNK_READS_LARGE, CHUNK_SEGS_LARGE, 5><<<n_items, PILEUP_THREADS, pileup_smem_bytes(CHUNK_READS_LARGE, CHUNK_SEGS_LARGE, chunk_q4), st>>>(
+                ctx->d_samples, ctx->d_items, n_items, chunk_q4, ctx->d_acgt, ctx->d_ncnt, ctx->d_err);
         ++launches;
     }
     CU(cudaEventRecord(ctx->ev[3], st));

@@ -1,0 +1,42 @@
+"""The reference's UNCHANGED orchestrator (metaSNV.py + its three helper scripts, staged by oracle/Makefile into
+oracle/_ref/metaSNV) drives the product binaries exactly as it drives its own: qaCompute per BAM, `samtools view -H`,
+createOptimumSplit, one `samtools mpileup | snpCall` pipe per split. Every file of the project directory must be
+byte-identical to the run with the oracle's binaries."""
+import os
+
+import pytest
+
+from metasnv_b200 import harness as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("threads,splits,ann", [(3, 3, False), (1, 1, False), (2, 2, True)])
+def test_metasnv_py_drives_the_gpu_path(threads, splits, ann, built, tmp_path):
+    if not os.path.exists(os.path.join(H.ORACLE_BIN, "metaSNV", "metaSNV.py")):
+        pytest.skip("oracle/_ref/metaSNV not staged (needs /root/reference at build time)")
+    data = str(tmp_path / "data")
+    if ann:
+        H.synth(data, "c5", 0.002, 5, annotation=True)
+    else:
+        H.synth(data, "c1", 0.03, 9)
+    lst, ref = os.path.join(data, "all_samples"), os.path.join(data, "ref.fa")
+    db_ann = os.path.join(data, "annotation.txt") if ann else None
+    outs = {}
+    for mode in ("oracle", "gpu"):
+        script, env = H.stage_metasnv(str(tmp_path / ("tree_" + mode)), mode)
+        out = str(tmp_path / "proj")          # same project name in both runs: it appears in file names
+        r = H.run_metasnv(script, env, out, lst, ref, threads=threads, n_splits=splits, db_ann=db_ann)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        keep = str(tmp_path / ("proj_" + mode))
+        os.rename(out, keep)
+        outs[mode] = H.tree_files(keep)
+    assert sorted(outs["oracle"]) == sorted(outs["gpu"])
+    assert any(f.startswith("snpCaller/called_SNPs") for f in outs["gpu"])
+    n_lines = 0
+    for rel in sorted(outs["oracle"]):
+        d = H.first_diff(outs["oracle"][rel], outs["gpu"][rel])
+        assert not d, "%s: %s" % (rel, d)
+        if rel.startswith("snpCaller/called_SNPs"):
+            n_lines += sum(1 for _ in open(outs["gpu"][rel]))
+    assert n_lines > 0
