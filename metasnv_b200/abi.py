@@ -105,26 +105,36 @@ def _ptr(a):
 
 
 class PinnedArena:
-    """Page-locked host memory from the library (exact sizes; freed on close())."""
+    """Page-locked host memory from the library, carved out of 1 GiB slabs (cudaHostAlloc is slow per call)."""
+    SLAB = 1 << 30
 
     def __init__(self):
         self.lib = load()
-        self.ptrs = []
+        self.slabs = []          # (ptr, size)
+        self.cur = None          # numpy view of the current slab
+        self.off = 0
         self.bytes = 0
 
     def alloc(self, nbytes):
-        n = max(1, int(nbytes))
-        p = self.lib.msnv_pinned_alloc(n)
-        if not p:
-            raise MsnvError("msnv_pinned_alloc(%d) failed" % n)
-        self.ptrs.append(p)
+        n = (max(1, int(nbytes)) + 255) // 256 * 256
+        if self.cur is None or self.off + n > self.cur.size:
+            size = max(self.SLAB, n)
+            p = self.lib.msnv_pinned_alloc(size)
+            if not p:
+                raise MsnvError("msnv_pinned_alloc(%d) failed" % size)
+            self.slabs.append((p, size))
+            self.cur = np.ctypeslib.as_array((C.c_uint8 * size).from_address(p))
+            self.off = 0
+        v = self.cur[self.off:self.off + n]
+        self.off += n
         self.bytes += n
-        return np.ctypeslib.as_array((C.c_uint8 * n).from_address(p))
+        return v
 
     def close(self):
-        for p in self.ptrs:
+        self.cur = None
+        for p, _ in self.slabs:
             self.lib.msnv_pinned_free(p)
-        self.ptrs = []
+        self.slabs = []
 
 
 class HitsView:
