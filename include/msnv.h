@@ -30,7 +30,7 @@ extern "C" {
 /* Positions per tile: contigs of a shard are laid out back to back in a "shard coordinate" space,
  * each starting at a multiple of MSNV_TILE, so a tile never spans two contigs. */
 #ifndef MSNV_TILE
-#define MSNV_TILE 512
+#define MSNV_TILE 1024
 #endif
 /* Limits of the tiled pileup kernel (longer reads are rejected with MSNV_E_LIMIT). */
 #define MSNV_MAX_READ_BASES 4096

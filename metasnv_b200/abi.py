@@ -10,7 +10,7 @@ import numpy as np
 
 from .paths import lib_path
 
-TILE = 512          # replaced by the library's own value on load()
+TILE = 1024         # replaced by the library's own value on load()
 
 
 class MsnvError(RuntimeError):

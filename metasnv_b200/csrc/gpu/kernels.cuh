@@ -25,6 +25,7 @@ constexpr int PILEUP_THREADS = 256;             // threads per pileup CTA (each 
 // instantiations of the pileup kernel: a small one for shallow data (8 CTAs per SM) and a large
 // one for deep data (fewer, longer chunks per tile)
 constexpr int CHUNK_READS_SMALL = 127, CHUNK_READS_LARGE = 255;
+constexpr int PILEUP_CTAS_SMALL = TILE >= 1024 ? 6 : 8, PILEUP_CTAS_LARGE = TILE >= 1024 ? 4 : 5;   // launch-bound targets (register budget)
 constexpr int CHUNK_Q4_MAX = 4096;              // upper bound of the 4-base groups staged per chunk (chosen per launch)
 constexpr int CHUNK_Q4_MIN = MSNV_MAX_READ_BASES / 4;   // a single read always fits
 constexpr int CHUNK_SEGS_SMALL = 256, CHUNK_SEGS_LARGE = 512;   // aligned segments per chunk
@@ -419,10 +420,12 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
         // alone is rewritten, the mate's pristine data come from global memory.
         const uint32_t n_tasks = s_misc[0];
         if (n_tasks) {
-            // one thread per task: the work per pair is a few dozen shared-memory bytes, far too little to
-            // spread over a warp (a warp per pair spent ~200 instructions per pair on set-up alone)
-            if (tid < n_tasks) {
-                const uint32_t i = s_pairs[tid];
+            // eight lanes per task (four tasks per warp): the work per pair is a few dozen shared-memory
+            // bytes -- a whole warp per pair wastes ~200 instructions on set-up, one thread per pair
+            // serialises ~50 dependent read-modify-writes
+            const uint32_t l8 = lane & 7u;
+            for (uint32_t t = tid >> 3; t < n_tasks; t += PILEUP_THREADS / 8) {
+                const uint32_t i = s_pairs[t];
                 const int32_t mt = s_mate[i];
                 const bool self_is_a = c0 + i < (uint32_t)mt;
                 const bool mate_here = (uint32_t)mt >= c0 && (uint32_t)mt < c0 + m;
@@ -436,8 +439,8 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                             const uint4 B = s_seg[kb];
                             const int32_t lo = max(max((int32_t)A.x, (int32_t)B.x), p0);
                             const int32_t hi = min(min((int32_t)(A.x + A.y), (int32_t)(B.x + B.y)), p0 + TILE);
-                            uint32_t za = A.z + (uint32_t)(lo - (int32_t)A.x), zb = B.z + (uint32_t)(lo - (int32_t)B.x);
-                            for (int32_t p = lo; p < hi; ++p, ++za, ++zb) {
+                            for (int32_t p = lo + (int32_t)l8; p < hi; p += 8) {
+                                const uint32_t za = A.z + (uint32_t)(p - (int32_t)A.x), zb = B.z + (uint32_t)(p - (int32_t)B.x);
                                 const uint32_t va = s_qual[za], vb = s_qual[zb];
                                 const uint32_t ia = za - d_qual, ib = zb - d_qual;     // base index inside the staged range
                                 const uint32_t ba = (s_seq[d_seq + (ia >> 2)] >> ((ia & 3) * 2)) & 3u;
@@ -463,7 +466,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                                 const uint4 A = s_seg[ka];
                                 const int32_t lo = max(max((int32_t)A.x, bx), p0);
                                 const int32_t hi = min(min((int32_t)(A.x + A.y), bx + (int32_t)len), p0 + TILE);
-                                for (int32_t p = lo; p < hi; ++p) {
+                                for (int32_t p = lo + (int32_t)l8; p < hi; p += 8) {
                                     const uint32_t zs = A.z + (uint32_t)(p - (int32_t)A.x), im = by + (uint32_t)(p - bx);
                                     const uint32_t vs = s_qual[zs], vm = mq[im];
                                     const uint32_t is = zs - d_qual;
@@ -585,7 +588,7 @@ __device__ __forceinline__ uint32_t ref_channel(uint32_t c)
     }
 }
 
-__global__ void __launch_bounds__(TILE)
+__global__ void __launch_bounds__(TILE, 2048 / TILE)
 call_kernel(const uint64_t* __restrict__ acgt, const uint16_t* __restrict__ ncnt, const uint32_t* __restrict__ tile_begin,
             const uint8_t* __restrict__ ref, CallParamsDev prm, int text_mode, uint8_t* __restrict__ flags,
             uint32_t* __restrict__ tile_hits)

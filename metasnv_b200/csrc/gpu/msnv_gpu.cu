@@ -227,9 +227,9 @@ int msnv_create(int device, msnv_ctx** out)
     CU(cudaMalloc((void**)&ctx->d_scalar, 16));
     CU(cudaMalloc((void**)&ctx->d_err, 4));
     CU(cudaMallocHost((void**)&ctx->h_scalar, 16));
-    CU(cudaFuncSetAttribute(pileup_kernel<CHUNK_READS_SMALL, CHUNK_SEGS_SMALL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(pileup_kernel<CHUNK_READS_SMALL, CHUNK_SEGS_SMALL, PILEUP_CTAS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)pileup_smem_bytes(CHUNK_READS_SMALL, CHUNK_SEGS_SMALL, CHUNK_Q4_MAX)));
-    CU(cudaFuncSetAttribute(pileup_kernel<CHUNK_READS_LARGE, CHUNK_SEGS_LARGE, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(pileup_kernel<CHUNK_READS_LARGE, CHUNK_SEGS_LARGE, PILEUP_CTAS_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)pileup_smem_bytes(CHUNK_READS_LARGE, CHUNK_SEGS_LARGE, CHUNK_Q4_MAX)));
     return MSNV_OK;
 }
@@ -407,10 +407,10 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
         bool small = mean_reads * 2 <= (uint64_t)CHUNK_READS_SMALL;
         if (const char* e = getenv("MSNV_PILEUP_VARIANT")) small = e[0] == 's';
         if (small)
-            pileup_kernel<CHUNK_READS_SMALL, CHUNK_SEGS_SMALL, 8><<<n_items, PILEUP_THREADS, pileup_smem_bytes(CHUNK_READS_SMALL, CHUNK_SEGS_SMALL, chunk_q4), st>>>(
+            pileup_kernel<CHUNK_READS_SMALL, CHUNK_SEGS_SMALL, PILEUP_CTAS_SMALL><<<n_items, PILEUP_THREADS, pileup_smem_bytes(CHUNK_READS_SMALL, CHUNK_SEGS_SMALL, chunk_q4), st>>>(
                 ctx->d_samples, ctx->d_items, n_items, chunk_q4, ctx->d_acgt, ctx->d_ncnt, ctx->d_err);
         else
-            pileup_kernel<CHUNK_READS_LARGE, CHUNK_SEGS_LARGE, 5><<<n_items, PILEUP_THREADS, pileup_smem_bytes(CHUNK_READS_LARGE, CHUNK_SEGS_LARGE, chunk_q4), st>>>(
+            pileup_kernel<CHUNK_READS_LARGE, CHUNK_SEGS_LARGE, PILEUP_CTAS_LARGE><<<n_items, PILEUP_THREADS, pileup_smem_bytes(CHUNK_READS_LARGE, CHUNK_SEGS_LARGE, chunk_q4), st>>>(
                 ctx->d_samples, ctx->d_items, n_items, chunk_q4, ctx->d_acgt, ctx->d_ncnt, ctx->d_err);
         ++launches;
     }

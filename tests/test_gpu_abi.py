@@ -9,7 +9,6 @@ import pytest
 from metasnv_b200 import harness as H
 
 pytestmark = pytest.mark.gpu
-TILE = 512
 
 
 def _text_from_counts(cnt, match, ref):
@@ -44,6 +43,8 @@ def _expected_lines(h, ref, kind):
 @pytest.mark.parametrize("S,L,seed,opts", [(3, 700, 1, (4, 4, 0.01)), (17, 1500, 2, (4, 4, 0.01)), (5, 512, 3, (10, 2, 0.3)), (1, 100, 4, (1, 1, 0.0))])
 def test_call_counts_matches_snpcall_oracle(S, L, seed, opts, built, tmp_path):
     from metasnv_b200 import abi
+    abi.load()
+    TILE = abi.TILE
     rng = np.random.default_rng(seed)
     cnt = rng.poisson(0.6, (L, S, 4)).astype(np.uint64) * (rng.random((L, S, 4)) < 0.3)
     cnt[rng.random((L, S, 4)) < 0.01] = 40

@@ -143,10 +143,9 @@ def test_split_files_concatenate_to_whole(datasets, tmp_path):
 
 
 # ---------------------------------------------------------------- per-position counts (pileup kernel output)
-def _oracle_counts(pile_path, n_samples, layout):
+def _oracle_counts(pile_path, n_samples, layout, P):
     """Parse mpileup text into [S][P][5] counts: a column's letters go to their base, '.'/',' to the reference's."""
     off = {name: o for name, o, _ in layout}
-    P = max(o + ((l + 511) // 512) * 512 for _, o, l in layout)
     cnt = np.zeros((n_samples, P, 5), np.uint16)
     chan = {"A": 0, "C": 1, "G": 2, "T": 3, "a": 0, "c": 1, "g": 2, "t": 3}
     for line in open(pile_path):
@@ -192,7 +191,7 @@ def test_pileup_counts_match_oracle_text(preset, scale, samples, datasets, tmp_p
     with open(pile, "wb") as f:
         subprocess.run([H.oracle_bin("mpileup_oracle"), "mpileup", "-f", os.path.join(data, "ref.fa"), "-B", "-b",
                         os.path.join(data, "all_samples")], stdout=f, check=True)
-    want = _oracle_counts(pile, S, layout)
+    want = _oracle_counts(pile, S, layout, P)
     assert want.shape == got.shape
     bad = np.argwhere(want != got)
     assert bad.size == 0, "first mismatch (sample,pos,channel)=%s want %s got %s" % (bad[0], want[tuple(bad[0])], got[tuple(bad[0])])
