@@ -291,6 +291,18 @@ __host__ __device__ constexpr size_t pileup_smem_bytes(int chunk_reads, int chun
            (chunk_q4 + 32) + (4 * (size_t)chunk_q4 + 32) + chunk_q4 + 32;
 }
 
+// explicit shared-window accesses (32-bit addresses): the compiler otherwise rebuilds generic
+// pointers from the CTA's shared base in every iteration of the scatter loop
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void red_shared_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+
 // counter word of tile-relative position p: XOR swizzle so that positions 4 apart fall in different banks
 __device__ __forceinline__ uint32_t cnt_slot(uint32_t p) { return p ^ ((p >> 5) & 3u); }
 
@@ -489,12 +501,13 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
 
         // ---- 5. flat scatter over the staged 4-base groups
         {
-            const uint32_t* q32 = (const uint32_t*)(s_qual + d_qual);     // d_qual is a multiple of 4
-            const uint8_t* sq = s_seq + d_seq;
+            const uint32_t a_q = smem_u32(s_qual) + d_qual;               // d_qual is a multiple of 4
+            const uint32_t a_s = smem_u32(s_seq) + d_seq, a_g = smem_u32(s_g2r), a_rd = smem_u32(s_rd);
+            const uint32_t a_n = smem_u32(s_cntn);
             for (uint32_t g = tid; g < nq4; g += PILEUP_THREADS) {
-                const uint32_t q = q32[g];
-                uint32_t x = sq[g];
-                const uint4 rd = s_rd[s_g2r[g]];
+                const uint32_t q = lds_u32(a_q + g * 4u);
+                uint32_t x = lds_u8(a_s + g);
+                const uint4 rd = lds_v4(a_rd + lds_u8(a_g + g) * 16u);
                 // four codes at once (SWAR): no byte lane can carry into its neighbour
                 x = (x * 4097u) & 0x000f000fu;                    // two 2-bit pairs per half word
                 x = (x * 520u) & 0x18181818u;                     // base*8 in every byte lane
@@ -504,33 +517,45 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                 x = (x & pm) | (0x40404040u & ~pm);               // CODE_SKIP below the quality threshold
                 const uint32_t pr0 = rd.x + g * 4u;               // tile-relative position of the group's first base
                 const uint32_t t0 = pr0 - rd.y;
-                // unconditional atomics: a base off the tile (or outside the first segment) adds 0 to a
-                // clamped address, which is cheaper than a divergent branch around every ATOMS
                 const uint32_t o0 = pr0 * 4u;
-                #pragma unroll
-                for (uint32_t k = 0; k < 4; ++k) {
-                    const uint32_t ak = cnt_base | ((o0 + 4u * k) & (uint32_t)(TILE * 4 - 1));   // wraps inside the counter array
-                    uint32_t inc = shl1_clamped32((x >> (8 * k)) & 0xffu);
-                    if (t0 + k >= rd.z) inc = 0;
-                    atomicAdd((uint32_t*)(smem + ((ak ^ ((ak >> 5) & 12u)) - smem_base)), inc);
-                }
-                if (x & 0x20202020u) {                            // rare: non-ACGT bases count on their own plane
+                if (t0 + 3u < rd.z) {
+                    // all four bases lie on the tile inside the read's first segment (the common case):
+                    // no clamping, no per-base validity test
                     #pragma unroll
-                    for (uint32_t k = 0; k < 4; ++k)
-                        if (t0 + k < rd.z && ((x >> (8 * k)) & 0xffu) == CODE_N) atomicAdd(&s_cntn[pr0 + k], 1u);
+                    for (uint32_t k = 0; k < 4; ++k) {
+                        const uint32_t ak = cnt_base + o0 + 4u * k;
+                        red_shared_add(ak ^ ((ak >> 5) & 12u), shl1_clamped32((x >> (8 * k)) & 0xffu));
+                    }
+                } else {
+                    // a base off the tile (or outside the first segment) adds 0 to a clamped address, which
+                    // is cheaper than a divergent branch around every atomic
+                    #pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k) {
+                        const uint32_t ak = cnt_base | ((o0 + 4u * k) & (uint32_t)(TILE * 4 - 1));   // wraps inside the counter array
+                        uint32_t inc = shl1_clamped32((x >> (8 * k)) & 0xffu);
+                        if (t0 + k >= rd.z) inc = 0;
+                        red_shared_add(ak ^ ((ak >> 5) & 12u), inc);
+                    }
                 }
-                if ((rd.w >> 16) > 1u) {                          // rare: further segments of a read with indels
-                    const uint32_t s1 = (rd.w & 0xffffu) + (rd.w >> 16);
-                    for (uint32_t sgi = (rd.w & 0xffffu) + 1u; sgi < s1; ++sgi) {
-                        const uint4 sg = s_seg[sgi];
+                if ((x & 0x20202020u) | (rd.w & 0xfffe0000u)) {   // rare: non-ACGT bases, reads with indels
+                    if (x & 0x20202020u) {                        // non-ACGT bases count on their own plane
                         #pragma unroll
-                        for (uint32_t k = 0; k < 4; ++k) {
-                            const uint32_t off = d_qual + g * 4u + k - sg.z;
-                            const uint32_t pr = (uint32_t)((int32_t)sg.x - p0) + off;
-                            if (off < sg.y && pr < (uint32_t)TILE) {
-                                const uint32_t code = (x >> (8 * k)) & 0xffu;
-                                atomicAdd(&s_cnt[cnt_slot(pr)], shl1_clamped32(code));
-                                if (code == CODE_N) atomicAdd(&s_cntn[pr], 1u);
+                        for (uint32_t k = 0; k < 4; ++k)
+                            if (t0 + k < rd.z && ((x >> (8 * k)) & 0xffu) == CODE_N) red_shared_add(a_n + (pr0 + k) * 4u, 1u);
+                    }
+                    if ((rd.w >> 16) > 1u) {                      // further segments of a read with indels
+                        const uint32_t s1 = (rd.w & 0xffffu) + (rd.w >> 16);
+                        for (uint32_t sgi = (rd.w & 0xffffu) + 1u; sgi < s1; ++sgi) {
+                            const uint4 sg = s_seg[sgi];
+                            #pragma unroll
+                            for (uint32_t k = 0; k < 4; ++k) {
+                                const uint32_t off = d_qual + g * 4u + k - sg.z;
+                                const uint32_t pr = (uint32_t)((int32_t)sg.x - p0) + off;
+                                if (off < sg.y && pr < (uint32_t)TILE) {
+                                    const uint32_t code = (x >> (8 * k)) & 0xffu;
+                                    atomicAdd(&s_cnt[cnt_slot(pr)], shl1_clamped32(code));
+                                    if (code == CODE_N) atomicAdd(&s_cntn[pr], 1u);
+                                }
                             }
                         }
                     }
