@@ -518,7 +518,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                 const uint32_t pr0 = rd.x + g * 4u;               // tile-relative position of the group's first base
                 const uint32_t t0 = pr0 - rd.y;
                 const uint32_t o0 = pr0 * 4u;
-                if (t0 + 3u < rd.z) {
+                if (t0 < rd.z && t0 + 3u < rd.z) {              // (t0 may have wrapped below zero: test both ends)
                     // all four bases lie on the tile inside the read's first segment (the common case):
                     // no clamping, no per-base validity test
                     #pragma unroll
