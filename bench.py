@@ -33,6 +33,9 @@ WORKLOADS = {
     "c2": ("c2", "single 5 Mb genome, 1000 samples at ~10x, population + individual calling (BASELINE.json configs[1])"),
     "c1": ("c1", "tutorial shape: 3 genomes, 160 samples (BASELINE.json configs[0])"),
     "c4": ("c4", "deep coverage: one 3 Mb genome, 20 samples at ~2000x without the >8000x spikes (BASELINE.json configs[3])"),
+    "c3": ("c3", "ProGenomes2 scale: 1000 genomes x 4 Mb in 50 contigs each, 500 samples carrying ~10% of the genomes at 5x; one shard of 8 "
+                 "(createOptimumSplit over 8 GPUs) per GPU is selected with --scale 0.125 (BASELINE.json configs[2])"),
+    "c5": ("c5", "50 genomes x 3 Mb, 200 samples at ~10x (BASELINE.json configs[4], pileup + call part)"),
 }
 
 
@@ -117,8 +120,8 @@ def cpu_sample(workload, work, samples, scale):
 
 def cpu_baseline(workload, work, steps=1, scale=None, samples=None):
     # about 3e8 aligned bases: 10-30 s of the CPU pipe
-    samples = samples or {"c2": 1000, "c1": 160, "c4": 20}[workload]
-    scale = scale or {"c2": 0.003, "c1": 0.12, "c4": 0.0012}[workload]
+    samples = samples or {"c2": 1000, "c1": 160, "c4": 20, "c3": 500, "c5": 200}[workload]
+    scale = scale or {"c2": 0.003, "c1": 0.12, "c4": 0.0012, "c3": 0.0004, "c5": 0.0012}[workload]
     data, st = cpu_sample(workload, work, samples, scale)
     times = []
     caller = ""

@@ -57,11 +57,14 @@ bool synth_preset(const std::string& name, double scale, int n_samples, uint64_t
         int S = n_samples > 0 ? n_samples : 500;
         cfg.model = default_model(seed ? seed : 20211126, S);
         cfg.model.depth_x100 = 500; cfg.model.presence_ppm = 100000;
-        int NG = (int)std::max(8.0, std::floor(1000 * std::min(1.0, scale * 50)));
+        // scale >= 0.01: that fraction of the 1000 genomes at full size (0.125 = one of 8 createOptimumSplit shards);
+        // smaller scales (tests): a handful of short genomes
+        const bool full = scale >= 0.01;
+        int NG = full ? (int)std::max(2.0, std::floor(1000 * scale + 0.5)) : (int)std::max(8.0, std::floor(1000 * std::min(1.0, scale * 50)));
         for (int g = 0; g < NG; ++g) {
             SynthGenome G; G.taxid = 300001 + g; G.n_sub = 1 + g % 3;
-            int nc = scale < 0.02 ? 5 : 50;
-            for (int c = 0; c < nc; ++c) G.contig_lens.push_back(scaled(4e6 / nc, std::min(1.0, scale * 20), 1500));
+            int nc = full ? 50 : 5;
+            for (int c = 0; c < nc; ++c) G.contig_lens.push_back(full ? 80000u : scaled(4e6 / nc, std::min(1.0, scale * 20), 1500));
             cfg.genomes.push_back(G);
         }
     } else if (name == "c4") {              // deep coverage: one 3 Mb genome, 20 samples at 2000x + spikes
