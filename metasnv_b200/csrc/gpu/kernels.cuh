@@ -135,11 +135,29 @@ __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t* s_warp /*[33
 // Two passes over the same predicate: COUNT writes per-block totals, EMIT writes the items at the
 // scanned offsets (ordered stream compaction by warp ballot).
 // ------------------------------------------------------------------------------------------------
+// Occupancy bitmap for sparse shards (most (tile, sample) pairs have no reads at all, e.g. a sample that
+// carries 10 % of the genomes of its bin): one bit per (sample, tile), set for the tile a read starts in.
+// index_kernel then skips the two binary searches of every pair whose tile and the tiles a read could
+// reach it from are all clear.
+__global__ void __launch_bounds__(256) mark_kernel(const SampleDev* __restrict__ samples, uint32_t words_per_sample,
+                                                   uint32_t* __restrict__ bitmap)
+{
+    const SampleDev sd = samples[blockIdx.y];
+    uint32_t* bm = bitmap + (size_t)blockIdx.y * words_per_sample;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < sd.n_reads; i += gridDim.x * blockDim.x) {
+        const uint32_t t = (uint32_t)__ldg(sd.pos + i) / TILE;
+        // consecutive reads mostly share a tile: one atomic per (warp, tile)
+        const uint32_t peers = __match_any_sync(__activemask(), t);
+        if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicOr(bm + (t >> 5), 1u << (t & 31));
+    }
+}
+
 template <bool EMIT>
 __global__ void __launch_bounds__(256) index_kernel(const SampleDev* __restrict__ samples, uint32_t n_samples,
                                                     uint32_t n_tiles, uint32_t* __restrict__ block_sums,
                                                     Item* __restrict__ items, uint32_t* __restrict__ tile_begin,
-                                                    uint2* __restrict__ range_cache /* [tiles*samples] or null: COUNT stores, EMIT reloads */)
+                                                    uint2* __restrict__ range_cache /* [tiles*samples] or null: COUNT stores, EMIT reloads */,
+                                                    const uint32_t* __restrict__ bitmap /* mark_kernel's, or null */, uint32_t words_per_sample)
 {
     __shared__ uint32_t s_warp[33];
     const uint64_t pair = (uint64_t)blockIdx.x * 256 + threadIdx.x;
@@ -154,7 +172,14 @@ __global__ void __launch_bounds__(256) index_kernel(const SampleDev* __restrict_
             r_lo = c.x; r_hi = c.y;
         } else {
             const uint32_t n = samples[s].n_reads;
-            if (n) {
+            bool maybe = n != 0;
+            if (maybe && bitmap) {                       // any read starting in a tile that can reach tile t?
+                const uint32_t back = (samples[s].max_span + TILE - 2) / TILE;      // tiles a read can reach back from
+                const uint32_t* bm = bitmap + (size_t)s * words_per_sample;
+                maybe = false;
+                for (uint32_t u = t >= back ? t - back : 0; u <= t && !maybe; ++u) maybe = (__ldg(bm + (u >> 5)) >> (u & 31)) & 1u;
+            }
+            if (maybe) {
                 const int32_t* pos = samples[s].pos;
                 const int64_t t0 = (int64_t)t * TILE;
                 r_lo = lower_bound_i32(pos, n, t0 - (int64_t)samples[s].max_span + 1);

@@ -37,6 +37,7 @@ struct msnv_ctx {
     uint32_t* d_tile_begin = nullptr; uint32_t* d_tile_hits = nullptr; uint8_t* d_flags = nullptr; uint64_t cap_tiles = 0;
     uint32_t* d_block_sums = nullptr; uint64_t cap_blocks = 0;
     uint2* d_range_cache = nullptr;   uint64_t cap_range = 0;
+    uint32_t* d_bitmap = nullptr;     uint64_t cap_bitmap = 0;
     uint32_t* d_scalar = nullptr;   int* d_err = nullptr;
     uint32_t n_items = 0;
 
@@ -243,7 +244,7 @@ void msnv_destroy(msnv_ctx* ctx)
     free_samples(ctx);                              // second call empties the pool as well
     cudaFree(ctx->d_samples); cudaFree(ctx->d_ref);
     cudaFree(ctx->d_items); cudaFree(ctx->d_acgt); cudaFree(ctx->d_ncnt);
-    cudaFree(ctx->d_tile_begin); cudaFree(ctx->d_tile_hits); cudaFree(ctx->d_flags); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_range_cache);
+    cudaFree(ctx->d_tile_begin); cudaFree(ctx->d_tile_hits); cudaFree(ctx->d_flags); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_range_cache); cudaFree(ctx->d_bitmap);
     cudaFree(ctx->d_scalar); cudaFree(ctx->d_err);
     cudaFree(ctx->d_hit_pos); cudaFree(ctx->d_hit_total); cudaFree(ctx->d_hit_pop); cudaFree(ctx->d_hit_ind);
     cudaFree(ctx->d_hit_cov); cudaFree(ctx->d_hit_allele);
@@ -378,7 +379,23 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
         if (n_pairs_idx > ctx->cap_range) { if (grow(ctx, ctx->d_range_cache, n_pairs_idx)) return MSNV_E_CUDA; ctx->cap_range = n_pairs_idx; }
         cache = ctx->d_range_cache;
     }
-    index_kernel<false><<<(unsigned)n_blocks, 256, 0, st>>>(ctx->d_samples, S, n_tiles, ctx->d_block_sums, nullptr, nullptr, cache);
+    // sparse shards (fewer than ~1/3 of the pairs can be active): occupancy bitmap first
+    uint32_t* bitmap = nullptr;
+    const uint32_t words_per_sample = (n_tiles + 31) / 32;
+    const bool sparse = getenv("MSNV_INDEX_BITMAP") ? atoi(getenv("MSNV_INDEX_BITMAP")) != 0
+                                                     : ctx->n_reads / 4 < n_pairs_idx;      // < 0.25 reads per (tile, sample) pair
+    if (sparse) {
+        const uint64_t words = (uint64_t)words_per_sample * S;
+        if (words > ctx->cap_bitmap) { if (grow(ctx, ctx->d_bitmap, words)) return MSNV_E_CUDA; ctx->cap_bitmap = words; }
+        CU(cudaMemsetAsync(ctx->d_bitmap, 0, words * 4, st));
+        uint64_t max_reads = 0;
+        for (uint32_t s = 0; s < S; ++s) if (ctx->h_samples[s].n_reads > max_reads) max_reads = ctx->h_samples[s].n_reads;
+        unsigned gx = (unsigned)((max_reads + 256 * 8 - 1) / (256 * 8)); if (gx < 1) gx = 1; if (gx > 1024) gx = 1024;
+        mark_kernel<<<dim3(gx, S), 256, 0, st>>>(ctx->d_samples, words_per_sample, ctx->d_bitmap);
+        ++launches;
+        bitmap = ctx->d_bitmap;
+    }
+    index_kernel<false><<<(unsigned)n_blocks, 256, 0, st>>>(ctx->d_samples, S, n_tiles, ctx->d_block_sums, nullptr, nullptr, cache, bitmap, words_per_sample);
     scan_kernel<<<1, 1024, 0, st>>>(ctx->d_block_sums, (uint32_t)n_blocks, ctx->d_scalar);
     launches += 2;
     CU(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, 4, cudaMemcpyDeviceToHost, st));
@@ -386,7 +403,8 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
     const uint32_t n_items = ctx->h_scalar[0];
     ctx->n_items = n_items;
     if (int rc = ensure_items(ctx, n_items)) return rc;
-    index_kernel<true><<<(unsigned)n_blocks, 256, 0, st>>>(ctx->d_samples, S, n_tiles, ctx->d_block_sums, ctx->d_items, ctx->d_tile_begin, cache);
+    index_kernel<true><<<(unsigned)n_blocks, 256, 0, st>>>(ctx->d_samples, S, n_tiles, ctx->d_block_sums, ctx->d_items, ctx->d_tile_begin, cache, bitmap,
+                                                           words_per_sample);
     ++launches;
     CU(cudaMemcpyAsync(ctx->d_tile_begin + n_tiles, ctx->d_scalar, 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaEventRecord(ctx->ev[1], st));

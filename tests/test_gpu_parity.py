@@ -218,3 +218,18 @@ def test_empty_inputs(built, tmp_path):
         assert rc == 0, err
         _same(o + ".called", g + ".called")
         _same(o + ".indiv", g + ".indiv")
+
+
+@pytest.mark.parametrize("env", [{"MSNV_INDEX_BITMAP": "1"}, {"MSNV_INDEX_BITMAP": "0"}, {"MSNV_PILEUP_VARIANT": "s"}, {"MSNV_PILEUP_VARIANT": "l"},
+                                 {"MSNV_CHUNK_Q4": "1024"}], ids=lambda e: "-".join("%s=%s" % kv for kv in e.items()))
+def test_kernel_variants_give_identical_output(env, datasets, tmp_path):
+    """Every launch-time choice of the library (occupancy bitmap for sparse shards, small/large chunk instantiation of
+    the pileup kernel, staging budget) must produce the same bytes."""
+    for name in ("c1_tiny", "c4_tiny_deep"):
+        recipe = json.load(open(os.path.join(GOLDEN, name, "recipe.json")))
+        data = datasets(recipe["preset"], recipe["scale"], recipe["samples"], **recipe["extra"])
+        out = str(tmp_path / ("gpu_" + name))
+        rc, err = H.run_product_snpcall(data, out, env=dict(os.environ, **env))
+        assert rc == 0, err
+        for ext in (".called", ".indiv"):
+            _same(os.path.join(GOLDEN, name, "unsplit" + ext), out + ext)
