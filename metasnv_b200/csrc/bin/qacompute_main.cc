@@ -8,6 +8,7 @@
 // (msnv_cov_run). The modes metaSNV never uses (-m median, -p profile, -s span coverage, -x regions,
 // -a subsampling, -h alternative header) are parsed and refused.
 #include <getopt.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -160,7 +161,7 @@ int main(int argc, char* argv[])
             msnv_destroy(ctx);
             return 1;
         }
-        msnv_destroy(ctx);
+        if (getenv("MSNV_CLEAN_EXIT")) msnv_destroy(ctx);      // otherwise left to process exit (see snpcall_main.cc)
     }
 
     // ---- text output, in header order (qaCompute.cpp:214-217,226-263,439,600-602)
@@ -224,5 +225,7 @@ int main(int argc, char* argv[])
     fprintf(outputFile, "Percentage of proper pairs: %3.5f\n", procOfProperPaires);
     fclose(outputFile);
     if (detailed) fclose(detailed);
+    fflush(stdout); fflush(stderr);
+    if (!getenv("MSNV_CLEAN_EXIT")) _exit(0);
     return 0;
 }

@@ -46,7 +46,12 @@ static int print_usage()
     return 1;
 }
 
+static bool verbose() { static int v = getenv("MSNV_VERBOSE") ? 1 : 0; return v != 0; }
+static double g_t0 = 0;
+static void stage(const char* what);
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static void stage(const char* what) { if (verbose()) fprintf(stderr, "[msnv %8.3f s] %s\n", now_s() - g_t0, what); }
 
 static int pick_device(const std::string& indiv_path)
 {
@@ -100,6 +105,7 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
         fprintf(stderr, "Genomes loaded!\n");
     }
 
+    stage("reference and annotation loaded");
     const int dev = pick_device(indiv_path);
     msnv_ctx* ctx = nullptr;
     if (dev < 0 || msnv_create(dev, &ctx) != MSNV_OK) {
@@ -107,6 +113,7 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
         msnv_destroy(ctx);
         return 1;
     }
+    stage("CUDA context created");
     if (msnv_shard_begin(ctx, S, layout.n_positions, ref.data()) != MSNV_OK) {
         fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); msnv_destroy(ctx); return 1;
     }
@@ -157,6 +164,7 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     }
     for (auto& th : pool) th.join();
     const double t_dec1 = now_s();
+    stage("BAMs decoded and uploaded");
     if (failed) {
         if (!first_err.empty()) fprintf(stderr, "snpCall: %s\n", first_err.c_str());
         msnv_destroy(ctx);
@@ -179,6 +187,7 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     const double t_run0 = now_s();
     if (msnv_shard_run(ctx, &prm, &hits) != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); msnv_destroy(ctx); return 1; }
     const double t_run1 = now_s();
+    stage("kernels done");
 
     // test hook: per-sample, per-position A,C,G,T,N counts of the whole shard (msnv_shard_counts)
     if (const char* dump = getenv("MSNV_DUMP_COUNTS")) {
@@ -224,12 +233,16 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
             fclose(f);
         }
     }
-    msnv_destroy(ctx);
+    stage("output written");
+    // the process is about to exit: the driver reclaims the device; freeing every block one by one
+    // (each cudaFree is a device-wide synchronisation) would only add seconds
+    if (getenv("MSNV_CLEAN_EXIT")) msnv_destroy(ctx);
     return 0;
 }
 
 int main(int argc, char** argv)
 {
+    g_t0 = now_s();
     FILE* individualFile = NULL;
     std::string fasta_opt, genes_opt, indiv_path;
     msnv_call_params prm; prm.min_coverage = 4; prm.calling_threshold = 4; prm.min_fraction = 0.01;
@@ -279,5 +292,8 @@ int main(int argc, char** argv)
         rc = run_text_mode(first, stdin, prm, fasta_opt, genes_opt, individualFile, pick_device(indiv_path));
     }
     if (individualFile) fclose(individualFile);
+    fflush(stdout); fflush(stderr);
+    stage("exit");
+    if (!getenv("MSNV_CLEAN_EXIT")) _exit(rc & 0xff);      // skip static destructors / CUDA runtime teardown
     return rc;
 }

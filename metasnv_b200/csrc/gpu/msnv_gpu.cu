@@ -383,7 +383,7 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
     uint32_t* bitmap = nullptr;
     const uint32_t words_per_sample = (n_tiles + 31) / 32;
     const bool sparse = getenv("MSNV_INDEX_BITMAP") ? atoi(getenv("MSNV_INDEX_BITMAP")) != 0
-                                                     : ctx->n_reads / 4 < n_pairs_idx;      // < 0.25 reads per (tile, sample) pair
+                                                     : ctx->n_reads / 20 < n_pairs_idx;     // < 20 reads per (tile, sample) pair on average
     if (sparse) {
         const uint64_t words = (uint64_t)words_per_sample * S;
         if (words > ctx->cap_bitmap) { if (grow(ctx, ctx->d_bitmap, words)) return MSNV_E_CUDA; ctx->cap_bitmap = words; }
