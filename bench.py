@@ -190,14 +190,13 @@ def run_ours(a):
     t0 = time.perf_counter()
     arena = abi.PinnedArena()
     host_samples = []
-    n_reads = aligned = h2d_bytes = extra_ops = 0
+    n_reads = aligned = h2d_bytes = n_segs = 0
     e2e_on = not a.no_e2e
     for s in range(S):
         e = ctx.export_sample(s, arena.alloc if e2e_on else None)
-        cig = e["cigar"]
-        aligned += int((cig[(cig & 0xf) == 0] >> 4).sum())
+        aligned += int(e["seg_len"].sum(dtype=np.uint64))
         n_reads += e["pos"].size
-        extra_ops += cig.size - e["pos"].size
+        n_segs += e["seg_len"].size
         h2d_bytes += sum(v.nbytes for k, v in e.items() if k != "max_span")
         if e2e_on:
             host_samples.append(e)
@@ -276,9 +275,10 @@ def run_ours(a):
 
     peak, peak_src = measured_peak()
     sp_active = items * abi.TILE                      # sample-positions whose count tiles are written / read
-    # algorithmic bytes: pileup reads 1.25 B per query base + 20 B per read (+4 per extra
-    # CIGAR op) and writes 10 B per active sample-position; the call kernel reads those 10 B again plus 1 B of reference.
-    pile_bytes = 1.25 * aligned + 20.0 * n_reads + 4.0 * extra_ops + 10.0 * sp_active
+    # algorithmic bytes: pileup reads 1.25 B per aligned base (the padding of the position-aligned
+    # layout is NOT counted) + 12 B per read + 6 B per segment and writes 10 B per active sample-position; the call kernel
+    # reads those 10 B again plus 1 B of reference.
+    pile_bytes = 1.25 * aligned + 12.0 * n_reads + 6.0 * n_segs + 10.0 * sp_active
     path_bytes = pile_bytes + 10.0 * sp_active + n_pos + n_hits * (8 + 10 * S)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "pileup_traffic.json")

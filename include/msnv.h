@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MSNV_ABI_VERSION 2
+#define MSNV_ABI_VERSION 3
 
 /* Positions per tile: contigs of a shard are laid out back to back in a "shard coordinate" space,
  * each starting at a multiple of MSNV_TILE, so a tile never spans two contigs. */
@@ -34,7 +34,7 @@ extern "C" {
 #endif
 /* Limits of the tiled pileup kernel (longer reads are rejected with MSNV_E_LIMIT). */
 #define MSNV_MAX_READ_BASES 4096
-#define MSNV_MAX_READ_CIGAR 128
+#define MSNV_MAX_READ_SEGMENTS 128
 
 typedef enum {
     MSNV_OK = 0,
@@ -49,27 +49,37 @@ typedef struct msnv_ctx msnv_ctx;
 
 /* One sample's reads that take part in the pileup, in coordinate order. "Take part" = the read
  * passed `samtools mpileup`'s default read filters and depth cap (SURVEY.md Annex A.1, A.3); that
- * filtering is part of BAM decoding on the host. All offsets are prefix sums with n_reads+1 entries.
+ * filtering is part of BAM decoding on the host, and so is the CIGAR: the device sees a read as its
+ * ALIGNED SEGMENTS (one per M/=/X operation), stored position-aligned. Inserted and clipped bases
+ * never reach a pileup column that snpCall counts (call_vC.cpp:503-535 skips "+n..."), so they are
+ * not stored. Offsets are prefix sums with n_reads+1 entries.
  *   pos      shard coordinate of the first reference base the read covers
- *   cig_off  first CIGAR word of the read in `cigar`
- *   seg_off  number of M/=/X operations before this read (the kernel turns each into a segment)
- *   q4_off   first 4-base group of the read in `seq2` (byte index) / `qual` (byte index * 4)
+ *   seg_off  first segment of the read in seg_pos / seg_len
+ *   q4_off   first 4-position group ("quad") of the read in `seq2` (byte index) / `qual` (byte index * 4)
  *   mate     index of the mate this read is paired with by mpileup's overlap detection (Annex A.2), else -1;
  *            symmetric (mate[mate[i]] == i), a read takes part in at most one pair
- *   cigar    BAM encoding (len << 4 | op), op in MIDNSHP=X
- *   seq2     2 bits per base, base k of a group in bits 2k..2k+1, A=0 C=1 G=2 T=3
- *   qual     min(phred,127) per base; bit 7 set when the base is not A/C/G/T (N or IUPAC code)
- *   max_span largest reference span (sum of M/D/N/=/X lengths) over the reads */
+ *   seg_pos  shard coordinate of the segment's first base; ascending within a read, segments of a
+ *            read do not overlap
+ *   seg_len  its length in bases (>= 1)
+ *   qual     segment k of a read owns nq(k) = ((seg_pos & 3) + seg_len + 3) / 4 quads, right behind
+ *            the quads of segment k-1 (the first segment starts at q4_off). Byte i of those 4*nq(k)
+ *            bytes belongs to shard coordinate (seg_pos & ~3) + i: the bytes of a quad are four
+ *            consecutive positions starting at a multiple of four. Value: min(phred,127), bit 7 set
+ *            when the base is not A/C/G/T (N or IUPAC code); the padding bytes in front of and behind
+ *            the segment are 0
+ *   seq2     same geometry, 2 bits per position: position k of a quad in bits 2k..2k+1 of the quad's
+ *            byte, A=0 C=1 G=2 T=3 (0 for non-ACGT bases and padding)
+ *   max_span largest reference span (last covered position - pos + 1) over the reads */
 typedef struct {
     uint32_t        n_reads;
     uint32_t        max_span;
     uint32_t        reserved0, reserved1;
     const int32_t*  pos;
-    const uint32_t* cig_off;
     const uint32_t* seg_off;
     const uint32_t* q4_off;
     const int32_t*  mate;
-    const uint32_t* cigar;
+    const int32_t*  seg_pos;
+    const uint16_t* seg_len;
     const uint8_t*  seq2;
     const uint8_t*  qual;
 } msnv_sample_reads;
@@ -106,7 +116,7 @@ typedef struct {
     float    ms_index, ms_reserved, ms_pileup, ms_call, ms_compact, ms_gather, ms_total;
     uint64_t n_items;           /* active (sample, tile) pairs */
     uint64_t n_reads;
-    uint64_t n_bases;           /* query bases resident for the shard */
+    uint64_t n_bases;           /* staged base slots resident for the shard (4 x quads, padding included) */
     uint32_t n_tiles;
     uint32_t kernel_launches;
 } msnv_timings;
@@ -175,10 +185,10 @@ int msnv_shard_synth(msnv_ctx* ctx, const msnv_synth_desc* desc, int64_t* first_
 
 /* Copy one sample of the open shard back to host arrays sized from *sizes (as returned by
  * msnv_shard_sample_sizes): used to stage pinned host buffers for end-to-end timing. */
-typedef struct { uint32_t n_reads, n_mated, max_span, reserved; uint64_t n_cigar, n_q4; } msnv_sample_sizes;
+typedef struct { uint32_t n_reads, n_mated, max_span, reserved; uint64_t n_segs, n_q4; } msnv_sample_sizes;
 int msnv_shard_sample_sizes(msnv_ctx* ctx, uint32_t sample, msnv_sample_sizes* sizes);
-int msnv_shard_export_sample(msnv_ctx* ctx, uint32_t sample, int32_t* pos, uint32_t* cig_off, uint32_t* seg_off, uint32_t* q4_off,
-                             int32_t* mate, uint32_t* cigar, uint8_t* seq2, uint8_t* qual);
+int msnv_shard_export_sample(msnv_ctx* ctx, uint32_t sample, int32_t* pos, uint32_t* seg_off, uint32_t* q4_off, int32_t* mate,
+                             int32_t* seg_pos, uint16_t* seg_len, uint8_t* seq2, uint8_t* qual);
 /* Copy the shard's reference characters (n_positions bytes) back to the host. */
 int msnv_shard_export_ref(msnv_ctx* ctx, uint8_t* ref);
 

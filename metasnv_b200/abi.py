@@ -17,10 +17,13 @@ class MsnvError(RuntimeError):
     pass
 
 
+SAMPLE_ARRAYS = ("pos", "seg_off", "q4_off", "mate", "seg_pos", "seg_len", "seq2", "qual")   # order of msnv_sample_reads
+
+
 class SampleReads(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("max_span", C.c_uint32), ("reserved0", C.c_uint32), ("reserved1", C.c_uint32),
-                ("pos", C.c_void_p), ("cig_off", C.c_void_p), ("seg_off", C.c_void_p), ("q4_off", C.c_void_p),
-                ("mate", C.c_void_p), ("cigar", C.c_void_p), ("seq2", C.c_void_p), ("qual", C.c_void_p)]
+                ("pos", C.c_void_p), ("seg_off", C.c_void_p), ("q4_off", C.c_void_p), ("mate", C.c_void_p),
+                ("seg_pos", C.c_void_p), ("seg_len", C.c_void_p), ("seq2", C.c_void_p), ("qual", C.c_void_p)]
 
 
 class CallParams(C.Structure):
@@ -53,7 +56,7 @@ class SynthDesc(C.Structure):
 
 class SampleSizes(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_mated", C.c_uint32), ("max_span", C.c_uint32), ("reserved", C.c_uint32),
-                ("n_cigar", C.c_uint64), ("n_q4", C.c_uint64)]
+                ("n_segs", C.c_uint64), ("n_q4", C.c_uint64)]
 
 
 _lib = None
@@ -190,13 +193,13 @@ class Context:
         self._check(self.lib.msnv_shard_begin(self.h, n_samples, ref.size, _ptr(ref)), "msnv_shard_begin")
 
     def shard_add_sample(self, sample, arrays):
-        """arrays: dict with pos, cig_off, seg_off, q4_off, mate, cigar, seq2, qual (numpy), max_span."""
+        """arrays: dict with pos, seg_off, q4_off, mate, seg_pos, seg_len, seq2, qual (numpy), max_span."""
         a = {k: np.ascontiguousarray(v) for k, v in arrays.items() if k != "max_span"}
         self._keep.append(a)
         r = SampleReads()
         r.n_reads = a["pos"].size
         r.max_span = int(arrays["max_span"])
-        for k in ("pos", "cig_off", "seg_off", "q4_off", "mate", "cigar", "seq2", "qual"):
+        for k in SAMPLE_ARRAYS:
             setattr(r, k, _ptr(a[k]))
         self._check(self.lib.msnv_shard_add_sample(self.h, sample, C.byref(r)), "msnv_shard_add_sample")
 
@@ -230,8 +233,8 @@ class Context:
             def alloc(n):
                 return np.empty(n, np.uint8)
         n, n1 = z.n_reads, z.n_reads + 1
-        spec = [("pos", n, np.int32), ("cig_off", n1, np.uint32), ("seg_off", n1, np.uint32), ("q4_off", n1, np.uint32),
-                ("mate", n, np.int32), ("cigar", z.n_cigar, np.uint32),
+        spec = [("pos", n, np.int32), ("seg_off", n1, np.uint32), ("q4_off", n1, np.uint32), ("mate", n, np.int32),
+                ("seg_pos", z.n_segs, np.int32), ("seg_len", z.n_segs, np.uint16),
                 ("seq2", z.n_q4, np.uint8), ("qual", z.n_q4 * 4, np.uint8)]
         out = {"max_span": z.max_span}
         for k, cnt, dt in spec:

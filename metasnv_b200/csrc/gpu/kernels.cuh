@@ -2,8 +2,9 @@
 //
 // Data flow for one shard (all samples of one genome bin):
 //   index_kernel     (tile, sample) pairs that have reads  -> ordered work items (ballot compaction)
-//   pileup_kernel    per item: stage reads (TMA bulk copies) -> CIGAR walk + mate-overlap quality
-//                    correction (SURVEY.md Annex A.2) in shared memory -> per-position gather
+//   pileup_kernel    per item: stage the reads' position-aligned segments (TMA bulk copies) ->
+//                    mate-overlap quality correction (SURVEY.md Annex A.2) in shared memory ->
+//                    four positions per thread scattered into byte-lane counters
 //                    -> packed A/C/G/T/N counts, 10 B per sample-position      [dominant kernel]
 //   call_kernel      per tile: reduce over samples, snpCall thresholds (call_vC.cpp:545-601)
 //   compact_kernel   ordered stream compaction of called positions (warp ballot + block scan)
@@ -19,27 +20,27 @@
 
 namespace msnv_gpu {
 
-constexpr int TILE = MSNV_TILE;                 // positions per tile == threads per pileup CTA
+constexpr int TILE = MSNV_TILE;                 // positions per tile
 constexpr int PILEUP_THREADS = 256;             // threads per pileup CTA (each folds TILE/256 positions)
 // reads staged per chunk: <= 255 (8-bit per-chunk counters, one walk thread per read). Two
 // instantiations of the pileup kernel: a small one for shallow data (8 CTAs per SM) and a large
 // one for deep data (fewer, longer chunks per tile)
 constexpr int CHUNK_READS_SMALL = 127, CHUNK_READS_LARGE = 255;
 constexpr int PILEUP_CTAS_SMALL = TILE >= 1024 ? 6 : 8, PILEUP_CTAS_LARGE = TILE >= 1024 ? 4 : 5;   // launch-bound targets (register budget)
-constexpr int CHUNK_Q4_MAX = 4096;              // upper bound of the 4-base groups staged per chunk (chosen per launch)
-constexpr int CHUNK_Q4_MIN = MSNV_MAX_READ_BASES / 4;   // a single read always fits
+constexpr int CHUNK_Q4_MAX = 4096;              // upper bound of the quads staged per chunk (chosen per launch)
+constexpr int CHUNK_Q4_MIN = MSNV_MAX_READ_BASES / 4 + 2 * MSNV_MAX_READ_SEGMENTS;   // a single read always fits
 constexpr int CHUNK_SEGS_SMALL = 256, CHUNK_SEGS_LARGE = 512;   // aligned segments per chunk
 
 static_assert(TILE % PILEUP_THREADS == 0 && PILEUP_THREADS >= 256, "one walk thread per staged read");
-static_assert(MSNV_MAX_READ_CIGAR * 2 <= CHUNK_SEGS_SMALL, "one read's segments must fit a chunk");
+static_assert(MSNV_MAX_READ_SEGMENTS <= CHUNK_SEGS_SMALL, "one read's segments must fit a chunk");
 
 struct SampleDev {
     const int32_t*  pos;
-    const uint32_t* cig_off;
     const uint32_t* seg_off;
     const uint32_t* q4_off;
     const int32_t*  mate;
-    const uint32_t* cigar;
+    const int32_t*  seg_pos;
+    const uint16_t* seg_len;
     const uint8_t*  seq2;
     const uint8_t*  qual;
     uint32_t        n_reads, max_span;
@@ -254,16 +255,6 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ v, ui
 // ------------------------------------------------------------------------------------------------
 // helpers of the pileup kernel
 // ------------------------------------------------------------------------------------------------
-// 1 << s with PTX clamping semantics (s >= 32 gives 0)
-__device__ __forceinline__ uint32_t shl1_clamped32(uint32_t s)
-{
-    uint32_t r;
-    asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"(s));
-    return r;
-}
-
-constexpr uint32_t CODE_N = 32, CODE_SKIP = 64;
-
 // mpileup's mate-overlap rule (htslib tweak_overlap_quality, SURVEY.md Annex A.2) for one reference
 // position that both mates align to. va/vb: staged quality bytes (bit 7: non-ACGT base) of the mate
 // that comes first in the file (a) and of the later one (b); same: the two bases are equal.
@@ -278,65 +269,52 @@ __device__ __forceinline__ void overlap_rule(uint32_t va, uint32_t vb, bool same
 
 // ------------------------------------------------------------------------------------------------
 // pileup: one CTA of PILEUP_THREADS threads per work item (sample, tile of TILE positions).
-// Per chunk of reads (<= CHUNK_READS reads, chunk_q4*4 bases, CHUNK_SEGS aligned segments):
+// Reads arrive as position-aligned segments (include/msnv.h): a staged quad holds four consecutive
+// positions starting at a multiple of four, so a quad is either on the tile or off it, and the four
+// bases of a quad are counted with byte-lane (SWAR) arithmetic, never one at a time.
+// Per chunk of reads (<= CHUNK_READS reads, chunk_q4 quads, CHUNK_SEGS segments):
 //   1. metadata of the chunk's reads -> shared memory; __syncthreads_count sizes the chunk
 //   2. two TMA bulk copies (2-bit bases, qualities) are issued; while they fly,
-//   3. one thread per read walks its CIGAR (global, L2) into aligned segments and a descriptor of
-//      its first segment clipped to the tile, and tags its 4-base groups with the read's index
-//   4. mate-overlap quality correction in shared memory, one warp per pair, lanes over positions
+//   3. one thread per read loads its segment records, derives for every segment the tile-relative
+//      quad index of its first staged quad, and tags the read's quads with their segment
+//   4. mate-overlap quality correction in shared memory, eight lanes per pair
 //      (mates staged in another chunk are read, pristine, from global memory)
-//   5. flat scatter: thread g takes the g-th 4-base group of the staged bytes, turns (2-bit base,
-//      quality) into four codes with SWAR arithmetic and adds each base that lies on the tile to
-//      its position's shared-memory counter (one byte lane per base letter) with a predicated
-//      red.shared.add. Every staged base costs the same handful of instructions at full lane
-//      occupancy, whatever the depth; the counter words are XOR-swizzled so the stride-4 access of
-//      a warp is conflict free (measured: >= 21 shared atomics per clock per SM,
-//      profiles/r01_microbench_shared_atomics.txt)
-//   6. each thread folds the byte lanes of its positions into 16-bit packed registers and clears them
+//   5. flat scatter: thread g takes the g-th staged quad: quality test and base decoding for the
+//      four positions at once, then ONE shared-memory atomic per base letter. Plane X of the
+//      counters holds, per quad of the tile, a word with one byte lane per position; lanes of a
+//      warp hit consecutive words (no bank conflicts, no swizzle) and the plane offsets are
+//      immediates. Padding bytes carry quality 0 and fail the threshold like any poor base.
+//   6. thread t folds the byte lanes of quad t into 16-bit lanes held in registers and clears them
 // The reads in HBM are never modified. CTAs are small (8 warps) and the staging buffers are sized
-// at launch from the mean work per item, so that 6-8 CTAs per SM overlap each other's barriers
+// at launch from the mean work per item, so that several CTAs per SM overlap each other's barriers
 // and copy latency.
 //
-// Shared memory (dynamic), regions 16-byte aligned; the counters are aligned to their own size:
-//   s_meta   4 x META_STRIDE u32      pos | q4_off | seg_off | mate of the chunk's reads
-//   s_rd     256 x 16 bytes           {first segment: p_rel - base index, lo, span; first seg | n segs << 16}
-//   s_seg    CHUNK_SEGS x 16 bytes    {ref begin, length, byte address of first quality, read index}
-//   s_cnt    2 x TILE u32             A|C|G|T byte lanes, non-ACGT count
+// Shared memory (dynamic), regions 16-byte aligned:
+//   s_meta   3 x META_STRIDE u32      q4_off | seg_off | mate of the chunk's reads
+//   s_seg    CHUNK_SEGS x 16 bytes    {first position, length, byte index of its first quality,
+//                                      tile-relative quad index of staged quad 0 as seen from this segment}
+//   s_cnt    5 x TILE bytes           planes A, C, G, T, non-ACGT: one byte per position
 //   s_seq    chunk_q4 + 32 bytes      2-bit bases           (TMA destination)
 //   s_qual   4*chunk_q4 + 32 bytes    qualities             (TMA destination)
-//   s_g2r    chunk_q4 bytes           read index of every 4-base group
-// Codes are shift amounts: 0,8,16,24 = A,C,G,T with quality >= 13; 32 = non-ACGT base with
-// quality >= 13; 64 = not counted.
+//   s_g2s    chunk_q4 u16             segment of every staged quad
 // ------------------------------------------------------------------------------------------------
-constexpr int PILEUP_POS_PER_THREAD = TILE / PILEUP_THREADS;
+constexpr int TILE_QUADS = TILE / 4;
+constexpr int QUADS_PER_THREAD = TILE_QUADS / PILEUP_THREADS;
+static_assert(TILE_QUADS % PILEUP_THREADS == 0 && QUADS_PER_THREAD >= 1, "each thread folds whole quads");
+
 __host__ __device__ constexpr size_t pileup_smem_bytes(int chunk_reads, int chunk_segs, uint32_t chunk_q4)
 {
-    return (size_t)(4 * ((chunk_reads + 4) / 4 * 4) * 4 + ((chunk_reads + 4) / 4 * 4) * 16 + chunk_segs * 16 + ((chunk_reads + 4) / 4 * 4) * 2 + 64 +
-                    (2 * TILE * 4) + TILE * 4 /*alignment slack*/) +
-           (chunk_q4 + 32) + (4 * (size_t)chunk_q4 + 32) + chunk_q4 + 32;
+    return (size_t)(3 * ((chunk_reads + 4) / 4 * 4) * 4 + chunk_segs * 16 + ((chunk_reads + 4) / 4 * 4) * 2 + 64 + 5 * TILE) +
+           (chunk_q4 + 32) + (4 * (size_t)chunk_q4 + 32) + 2 * (size_t)chunk_q4 + 32;
 }
 
 // explicit shared-window accesses (32-bit addresses): the compiler otherwise rebuilds generic
 // pointers from the CTA's shared base in every iteration of the scatter loop
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint4 lds_v4(uint32_t a)
-{
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void red_shared_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-
-// counter word of tile-relative position p: XOR swizzle so that positions 4 apart fall in different banks
-__device__ __forceinline__ uint32_t cnt_slot(uint32_t p) { return p ^ ((p >> 5) & 3u); }
-
-// if (a < b) shared[addr] += val, without a branch
-__device__ __forceinline__ void red_shared_add_if_lt(uint32_t addr, uint32_t val, uint32_t a, uint32_t b)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %2, %3;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
-                 :: "r"(addr), "r"(val), "r"(a), "r"(b) : "memory");
-}
+template <int OFF>
+__device__ __forceinline__ void red_shared_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0+%2], %1;" :: "r"(a), "r"(v), "n"(OFF) : "memory"); }
 
 template <int CHUNK_READS, int CHUNK_SEGS, int MIN_CTAS>
 __global__ void __launch_bounds__(PILEUP_THREADS, MIN_CTAS)
@@ -344,45 +322,39 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
               uint64_t* __restrict__ acgt /*[n_items][TILE]*/, uint16_t* __restrict__ ncnt /*[n_items][TILE]*/,
               int* __restrict__ err_flag)
 {
-    constexpr int META_STRIDE = (CHUNK_READS + 4) / 4 * 4, RD_SLOTS = META_STRIDE;
+    constexpr int META_STRIDE = (CHUNK_READS + 4) / 4 * 4;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint32_t* s_pos = (uint32_t*)smem;
-    uint32_t* s_q4  = s_pos + META_STRIDE;
-    uint32_t* s_sgo = s_q4 + META_STRIDE;
+    uint32_t* s_q4   = (uint32_t*)smem;
+    uint32_t* s_sgo  = s_q4 + META_STRIDE;
     int32_t*  s_mate = (int32_t*)(s_sgo + META_STRIDE);
-    uint4*    s_rd   = (uint4*)(s_mate + META_STRIDE);
-    uint4*    s_seg  = s_rd + RD_SLOTS;
+    uint4*    s_seg  = (uint4*)(s_mate + META_STRIDE);
     uint16_t* s_pairs = (uint16_t*)(s_seg + CHUNK_SEGS);
-    uint64_t* s_bar  = (uint64_t*)(s_pairs + RD_SLOTS);
+    uint64_t* s_bar  = (uint64_t*)(s_pairs + META_STRIDE);
     uint32_t* s_misc = (uint32_t*)(s_bar + 1);        // [0] number of overlap tasks of the chunk
-    // counters: aligned to TILE*4 bytes in the shared window so that base | offset == base + offset
-    const uint32_t smem_base = smem_u32(smem);
-    const uint32_t after_fixed = smem_u32(s_misc) + 56;
-    const uint32_t cnt_base = (after_fixed + TILE * 4 - 1) & ~(uint32_t)(TILE * 4 - 1);
-    uint32_t* s_cnt  = (uint32_t*)(smem + (cnt_base - smem_base));
-    uint32_t* s_cntn = s_cnt + TILE;
-    uint8_t*  s_seq  = (uint8_t*)(s_cntn + TILE);
+    uint32_t* s_cnt  = s_misc + 14;                   // 5 planes of TILE_QUADS words
+    uint8_t*  s_seq  = (uint8_t*)(s_cnt + 5 * TILE_QUADS);
     uint8_t*  s_qual = s_seq + chunk_q4 + 32;
-    uint8_t*  s_g2r  = s_qual + 4 * chunk_q4 + 32;
+    uint16_t* s_g2s  = (uint16_t*)(s_qual + 4 * chunk_q4 + 32);
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
     const Item it = items[blockIdx.x];
     const int32_t p0 = (int32_t)(it.tile * TILE);
     const SampleDev* __restrict__ sd = samples + it.sample;
 
     if (tid == 0) { mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    #pragma unroll
-    for (int k = 0; k < PILEUP_POS_PER_THREAD; ++k) { s_cnt[tid + k * PILEUP_THREADS] = 0; s_cntn[tid + k * PILEUP_THREADS] = 0; }
+    for (int k = tid; k < 5 * TILE_QUADS; k += PILEUP_THREADS) s_cnt[k] = 0;
 
-    uint64_t acc[PILEUP_POS_PER_THREAD];      // A | C<<16 | G<<32 | T<<48 of positions p0 + tid + k*PILEUP_THREADS
-    uint32_t acc_n[PILEUP_POS_PER_THREAD];
+    // per letter and quad: 16-bit lanes, [0] = positions 0 and 2 of the quad, [1] = positions 1 and 3
+    uint32_t acc[QUADS_PER_THREAD][5][2];
     #pragma unroll
-    for (int k = 0; k < PILEUP_POS_PER_THREAD; ++k) { acc[k] = 0; acc_n[k] = 0; }
+    for (int k = 0; k < QUADS_PER_THREAD; ++k)
+        #pragma unroll
+        for (int c = 0; c < 5; ++c) { acc[k][c][0] = 0; acc[k][c][1] = 0; }
     uint32_t parity = 0;
 
     for (uint32_t c0 = it.r_lo; c0 < it.r_hi;) {
         // ---- 1. metadata of up to CHUNK_READS reads (+1 for the end offsets); the chunk takes the
-        // longest prefix within the byte and segment budgets (prefix sums: the predicate is monotone)
+        // longest prefix within the quad and segment budgets (prefix sums: the predicate is monotone)
         uint32_t n = it.r_hi - c0; if (n > CHUNK_READS) n = CHUNK_READS;
         bool fits = false;
         if (tid <= n) {
@@ -390,7 +362,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
             const uint32_t q = __ldg(q4p + tid), g = __ldg(sgp + tid);
             s_q4[tid] = q; s_sgo[tid] = g;
             fits = tid >= 1 && q - __ldg(q4p) <= chunk_q4 && g - __ldg(sgp) <= CHUNK_SEGS;
-            if (tid < n) { s_pos[tid] = (uint32_t)__ldg(sd->pos + c0 + tid); s_mate[tid] = __ldg(sd->mate + c0 + tid); }
+            if (tid < n) s_mate[tid] = __ldg(sd->mate + c0 + tid);
         }
         if (tid == 0) s_misc[0] = 0;
         const uint32_t m = (uint32_t)__syncthreads_count(fits);
@@ -413,34 +385,25 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
             if (b_qual) tma_load_1d(s_qual, g_qual - d_qual, b_qual, s_bar);
         }
 
-        // ---- 3. CIGAR walk while the copies are in flight: one thread per read
+        // ---- 3. segment records while the copies are in flight: one thread per read
         if (tid < m) {
-            const uint32_t cg0 = __ldg(sd->cig_off + c0 + tid), nops = __ldg(sd->cig_off + c0 + tid + 1) - cg0;
-            const uint32_t k0 = s_sgo[tid] - sg_0;
-            uint32_t k = k0;
-            const uint32_t gq0 = s_q4[tid] - q4_0, gq1 = s_q4[tid + 1] - q4_0;
-            int32_t x = (int32_t)s_pos[tid];
-            uint32_t y = d_qual + gq0 * 4;                        // byte address of the read's first base in s_qual
-            for (uint32_t o = 0; o < nops; ++o) {
-                const uint32_t w = __ldg(sd->cigar + cg0 + o), op = w & 0xf, len = w >> 4;
-                if (op == 0 || op == 7 || op == 8) {
-                    s_seg[k++] = make_uint4((uint32_t)x, len, y, tid);
-                    x += (int32_t)len; y += len;
-                } else if (op == 2 || op == 3) x += (int32_t)len;
-                else if (op == 1 || op == 4) y += len;
+            const uint32_t k0 = s_sgo[tid] - sg_0, k1 = s_sgo[tid + 1] - sg_0;
+            uint32_t q = s_q4[tid] - q4_0;                        // first staged quad of the next segment
+            const uint32_t q_end = s_q4[tid + 1] - q4_0;
+            for (uint32_t k = k0; k < k1; ++k) {
+                const int32_t p = __ldg(sd->seg_pos + sg_0 + k);
+                const uint32_t len = __ldg(sd->seg_len + sg_0 + k);
+                const uint32_t a = (uint32_t)p & 3u, nq = (a + len + 3u) >> 2;
+                // staged quad g of this segment covers tile-relative quad g + w
+                s_seg[k] = make_uint4((uint32_t)p, len, d_qual + q * 4u + a, (uint32_t)((p - (int32_t)a - p0) >> 2) - q);
+                uint32_t e = q + nq; if (e > q_end) e = q_end;
+                for (uint32_t g = q; g < e; ++g) s_g2s[g] = (uint16_t)k;
+                q += nq;
             }
-            // first segment clipped to the tile, in the coordinates the scatter uses: a base with staged
-            // index b (4*group + k) lies at tile-relative position rd.x + b if (rd.x + b - rd.y) < rd.z
-            uint4 rd = make_uint4(0u, 0u, 0u, k0 | (k - k0) << 16);
-            if (k > k0) {
-                const uint4 f = s_seg[k0];
-                const int32_t lo = max((int32_t)f.x - p0, 0), hi = min((int32_t)(f.x + f.y) - p0, (int32_t)TILE);
-                rd.x = (uint32_t)((int32_t)f.x - p0 - (int32_t)(f.z - d_qual));
-                rd.y = (uint32_t)lo;
-                rd.z = hi > lo ? (uint32_t)(hi - lo) : 0u;
+            if (q != q_end) {                                     // offsets and segments disagree: refuse, stay in bounds
+                atomicExch(err_flag, 2);
+                for (uint32_t g = s_q4[tid] - q4_0; g < q_end; ++g) s_g2s[g] = 0;
             }
-            s_rd[tid] = rd;
-            for (uint32_t g = gq0; g < gq1; ++g) s_g2r[g] = (uint8_t)tid;
             const int32_t mt = s_mate[tid];
             if (mt >= 0) {                                        // overlap task: once per pair when both mates are here
                 const bool mate_here = (uint32_t)mt >= c0 && (uint32_t)mt < c0 + m;
@@ -452,7 +415,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
         __syncthreads();                    // segments written, copies landed (thread 0 observed the barrier)
 
         // ---- 4. mate-overlap quality correction, restricted to this tile's positions (other tiles
-        // are counted by other CTAs). Pairs with both mates in the chunk: one warp rewrites both from
+        // are counted by other CTAs). Pairs with both mates in the chunk: both are rewritten from
         // pristine values. Mates outside the chunk (only when a tile needs several chunks): this read
         // alone is rewritten, the mate's pristine data come from global memory.
         const uint32_t n_tasks = s_misc[0];
@@ -479,9 +442,9 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                             for (int32_t p = lo + (int32_t)l8; p < hi; p += 8) {
                                 const uint32_t za = A.z + (uint32_t)(p - (int32_t)A.x), zb = B.z + (uint32_t)(p - (int32_t)B.x);
                                 const uint32_t va = s_qual[za], vb = s_qual[zb];
-                                const uint32_t ia = za - d_qual, ib = zb - d_qual;     // base index inside the staged range
-                                const uint32_t ba = (s_seq[d_seq + (ia >> 2)] >> ((ia & 3) * 2)) & 3u;
-                                const uint32_t bb = (s_seq[d_seq + (ib >> 2)] >> ((ib & 3) * 2)) & 3u;
+                                const uint32_t sh = ((uint32_t)p & 3u) * 2u;           // storage is position aligned
+                                const uint32_t ba = (s_seq[d_seq + ((za - d_qual) >> 2)] >> sh) & 3u;
+                                const uint32_t bb = (s_seq[d_seq + ((zb - d_qual) >> 2)] >> sh) & 3u;
                                 const bool same = ((va | vb) & 0x80u) ? ((va & vb & 0x80u) != 0) : (ba == bb);
                                 uint32_t na, nb;
                                 overlap_rule(va, vb, same, na, nb);
@@ -490,100 +453,59 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                         }
                     }
                 } else {
-                    // the mate is staged in another chunk: walk its CIGAR and read its pristine bytes from global memory
-                    const uint32_t mc0 = __ldg(sd->cig_off + mt), mn = __ldg(sd->cig_off + mt + 1) - mc0;
-                    const uint32_t mq4 = __ldg(sd->q4_off + mt);
-                    const uint8_t* mq = sd->qual + (size_t)mq4 * 4;
-                    const uint8_t* ms = sd->seq2 + mq4;
-                    int32_t bx = __ldg(sd->pos + mt); uint32_t by = 0;
-                    for (uint32_t o = 0; o < mn; ++o) {
-                        const uint32_t w = __ldg(sd->cigar + mc0 + o), op = w & 0xf, len = w >> 4;
-                        if (op == 0 || op == 7 || op == 8) {
-                            for (uint32_t ka = sa0; ka < sa1; ++ka) {
-                                const uint4 A = s_seg[ka];
-                                const int32_t lo = max(max((int32_t)A.x, bx), p0);
-                                const int32_t hi = min(min((int32_t)(A.x + A.y), bx + (int32_t)len), p0 + TILE);
-                                for (int32_t p = lo + (int32_t)l8; p < hi; p += 8) {
-                                    const uint32_t zs = A.z + (uint32_t)(p - (int32_t)A.x), im = by + (uint32_t)(p - bx);
-                                    const uint32_t vs = s_qual[zs], vm = mq[im];
-                                    const uint32_t is = zs - d_qual;
-                                    const uint32_t bs = (s_seq[d_seq + (is >> 2)] >> ((is & 3) * 2)) & 3u;
-                                    const uint32_t bm = (ms[im >> 2] >> ((im & 3) * 2)) & 3u;
-                                    const bool same = ((vs | vm) & 0x80u) ? ((vs & vm & 0x80u) != 0) : (bs == bm);
-                                    uint32_t na, nb;
-                                    if (self_is_a) overlap_rule(vs, vm, same, na, nb); else overlap_rule(vm, vs, same, nb, na);
-                                    s_qual[zs] = (uint8_t)na;
-                                }
+                    // the mate is staged in another chunk: read its segments and pristine bytes from global memory
+                    const uint32_t ms0 = __ldg(sd->seg_off + mt), ms1 = __ldg(sd->seg_off + mt + 1);
+                    uint32_t mq = __ldg(sd->q4_off + mt);                  // first quad of the mate's next segment
+                    for (uint32_t ks = ms0; ks < ms1; ++ks) {
+                        const int32_t bx = __ldg(sd->seg_pos + ks);
+                        const uint32_t bl = __ldg(sd->seg_len + ks), ba0 = (uint32_t)bx & 3u;
+                        const uint8_t* mqual = sd->qual + (size_t)mq * 4 + ba0;      // quality of the segment's first base
+                        const uint8_t* mseq = sd->seq2 + mq;
+                        for (uint32_t ka = sa0; ka < sa1; ++ka) {
+                            const uint4 A = s_seg[ka];
+                            const int32_t lo = max(max((int32_t)A.x, bx), p0);
+                            const int32_t hi = min(min((int32_t)(A.x + A.y), bx + (int32_t)bl), p0 + TILE);
+                            for (int32_t p = lo + (int32_t)l8; p < hi; p += 8) {
+                                const uint32_t zs = A.z + (uint32_t)(p - (int32_t)A.x), im = (uint32_t)(p - bx);
+                                const uint32_t vs = s_qual[zs], vm = mqual[im];
+                                const uint32_t sh = ((uint32_t)p & 3u) * 2u;
+                                const uint32_t bs = (s_seq[d_seq + ((zs - d_qual) >> 2)] >> sh) & 3u;
+                                const uint32_t bm = (mseq[(ba0 + im) >> 2] >> sh) & 3u;
+                                const bool same = ((vs | vm) & 0x80u) ? ((vs & vm & 0x80u) != 0) : (bs == bm);
+                                uint32_t na, nb;
+                                if (self_is_a) overlap_rule(vs, vm, same, na, nb); else overlap_rule(vm, vs, same, nb, na);
+                                s_qual[zs] = (uint8_t)na;
                             }
-                            bx += (int32_t)len; by += len;
-                        } else if (op == 2 || op == 3) bx += (int32_t)len;
-                        else if (op == 1 || op == 4) by += len;
+                        }
+                        mq += (ba0 + bl + 3u) >> 2;
                     }
                 }
             }
             __syncthreads();
         }
 
-        // ---- 5. flat scatter over the staged 4-base groups
+        // ---- 5. flat scatter over the staged quads
         {
             const uint32_t a_q = smem_u32(s_qual) + d_qual;               // d_qual is a multiple of 4
-            const uint32_t a_s = smem_u32(s_seq) + d_seq, a_g = smem_u32(s_g2r), a_rd = smem_u32(s_rd);
-            const uint32_t a_n = smem_u32(s_cntn);
+            const uint32_t a_s = smem_u32(s_seq) + d_seq, a_g = smem_u32(s_g2s), a_w = smem_u32(s_seg) + 12u;
+            const uint32_t a_c = smem_u32(s_cnt);
             for (uint32_t g = tid; g < nq4; g += PILEUP_THREADS) {
                 const uint32_t q = lds_u32(a_q + g * 4u);
                 uint32_t x = lds_u8(a_s + g);
-                const uint4 rd = lds_v4(a_rd + lds_u8(a_g + g) * 16u);
-                // four codes at once (SWAR): no byte lane can carry into its neighbour
-                x = (x * 4097u) & 0x000f000fu;                    // two 2-bit pairs per half word
-                x = (x * 520u) & 0x18181818u;                     // base*8 in every byte lane
-                const uint32_t pass = (((q & 0x7f7f7f7fu) + 0x73737373u) >> 7) & 0x01010101u;   // 1 where (q & 127) >= 13
-                const uint32_t nm = ((q >> 7) & 0x01010101u) * 255u, pm = pass * 255u;
-                x = (x & ~nm) | (0x20202020u & nm);               // CODE_N for non-ACGT bases
-                x = (x & pm) | (0x40404040u & ~pm);               // CODE_SKIP below the quality threshold
-                const uint32_t pr0 = rd.x + g * 4u;               // tile-relative position of the group's first base
-                const uint32_t t0 = pr0 - rd.y;
-                const uint32_t o0 = pr0 * 4u;
-                if (t0 < rd.z && t0 + 3u < rd.z) {              // (t0 may have wrapped below zero: test both ends)
-                    // all four bases lie on the tile inside the read's first segment (the common case):
-                    // no clamping, no per-base validity test
-                    #pragma unroll
-                    for (uint32_t k = 0; k < 4; ++k) {
-                        const uint32_t ak = cnt_base + o0 + 4u * k;
-                        red_shared_add(ak ^ ((ak >> 5) & 12u), shl1_clamped32((x >> (8 * k)) & 0xffu));
-                    }
-                } else {
-                    // a base off the tile (or outside the first segment) adds 0 to a clamped address, which
-                    // is cheaper than a divergent branch around every atomic
-                    #pragma unroll
-                    for (uint32_t k = 0; k < 4; ++k) {
-                        const uint32_t ak = cnt_base | ((o0 + 4u * k) & (uint32_t)(TILE * 4 - 1));   // wraps inside the counter array
-                        uint32_t inc = shl1_clamped32((x >> (8 * k)) & 0xffu);
-                        if (t0 + k >= rd.z) inc = 0;
-                        red_shared_add(ak ^ ((ak >> 5) & 12u), inc);
-                    }
-                }
-                if ((x & 0x20202020u) | (rd.w & 0xfffe0000u)) {   // rare: non-ACGT bases, reads with indels
-                    if (x & 0x20202020u) {                        // non-ACGT bases count on their own plane
-                        #pragma unroll
-                        for (uint32_t k = 0; k < 4; ++k)
-                            if (t0 + k < rd.z && ((x >> (8 * k)) & 0xffu) == CODE_N) red_shared_add(a_n + (pr0 + k) * 4u, 1u);
-                    }
-                    if ((rd.w >> 16) > 1u) {                      // further segments of a read with indels
-                        const uint32_t s1 = (rd.w & 0xffffu) + (rd.w >> 16);
-                        for (uint32_t sgi = (rd.w & 0xffffu) + 1u; sgi < s1; ++sgi) {
-                            const uint4 sg = s_seg[sgi];
-                            #pragma unroll
-                            for (uint32_t k = 0; k < 4; ++k) {
-                                const uint32_t off = d_qual + g * 4u + k - sg.z;
-                                const uint32_t pr = (uint32_t)((int32_t)sg.x - p0) + off;
-                                if (off < sg.y && pr < (uint32_t)TILE) {
-                                    const uint32_t code = (x >> (8 * k)) & 0xffu;
-                                    atomicAdd(&s_cnt[cnt_slot(pr)], shl1_clamped32(code));
-                                    if (code == CODE_N) atomicAdd(&s_cntn[pr], 1u);
-                                }
-                            }
-                        }
-                    }
+                const uint32_t j = lds_u32(a_w + lds_u16(a_g + g * 2u) * 16u) + g;     // tile-relative quad
+                if (j < (uint32_t)TILE_QUADS) {
+                    x = (x * 4097u) & 0x000f000fu;                        // two 2-bit pairs per half word
+                    x = (x * 65u) & 0x03030303u;                          // one base per byte lane
+                    const uint32_t v = (q & 0x7f7f7f7fu) + 0x73737373u;   // bit 7 of a lane: quality >= 13
+                    const uint32_t ok = ((v & ~q) >> 7) & 0x01010101u;    // ... and the base is A/C/G/T
+                    const uint32_t hi = x >> 1;
+                    const uint32_t a = a_c + j * 4u;
+                    red_shared_add<0>(a, ok & ~x & ~hi);
+                    red_shared_add<TILE>(a, ok & x & ~hi);
+                    red_shared_add<2 * TILE>(a, ok & ~x & hi);
+                    red_shared_add<3 * TILE>(a, ok & x & hi);
+                    const uint32_t nn = v & q & 0x80808080u;              // rare: counted non-ACGT bases
+                    if (nn) red_shared_add<4 * TILE>(a, nn >> 7);
                 }
             }
         }
@@ -591,28 +513,41 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
 
         // ---- 6. fold this chunk's byte lanes (a position sees at most m <= 255 reads per chunk)
         #pragma unroll
-        for (int k = 0; k < PILEUP_POS_PER_THREAD; ++k) {
-            const uint32_t p = tid + k * PILEUP_THREADS;
-            const uint32_t sl = cnt_slot(p);
-            const uint32_t a8 = s_cnt[sl];
-            if (a8) {
-                s_cnt[sl] = 0;
-                acc[k] += (uint64_t)(a8 & 0xffu) | (uint64_t)((a8 >> 8) & 0xffu) << 16 | (uint64_t)((a8 >> 16) & 0xffu) << 32 |
-                          (uint64_t)(a8 >> 24) << 48;
+        for (int k = 0; k < QUADS_PER_THREAD; ++k) {
+            #pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                const uint32_t slot = c * TILE_QUADS + k * PILEUP_THREADS + tid;
+                const uint32_t w = s_cnt[slot];
+                if (w) {
+                    s_cnt[slot] = 0;
+                    acc[k][c][0] += w & 0x00ff00ffu;
+                    acc[k][c][1] += (w >> 8) & 0x00ff00ffu;
+                }
             }
-            const uint32_t cn = s_cntn[p];
-            if (cn) { s_cntn[p] = 0; acc_n[k] += cn; }
         }
         c0 += m;
         // no barrier here: the next chunk only touches the counters again after two more barriers
     }
 
-    // ---- 7. flush: 8 B + 2 B per position, fully coalesced
+    // ---- 7. flush: 8 B + 2 B per position; a thread owns four consecutive positions
     #pragma unroll
-    for (int k = 0; k < PILEUP_POS_PER_THREAD; ++k) {
-        const size_t o = (size_t)blockIdx.x * TILE + tid + k * PILEUP_THREADS;
-        acgt[o] = acc[k];
-        ncnt[o] = (uint16_t)acc_n[k];
+    for (int k = 0; k < QUADS_PER_THREAD; ++k) {
+        const size_t o = (size_t)blockIdx.x * TILE + 4u * (k * PILEUP_THREADS + tid);
+        uint32_t w[4][2], nw[2];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            // position i of the quad sits in lane (i >> 1) of acc[..][i & 1]
+            const uint32_t sh = 16u * (uint32_t)(i >> 1);
+            const uint32_t A = (acc[k][0][i & 1] >> sh) & 0xffffu, C = (acc[k][1][i & 1] >> sh) & 0xffffu;
+            const uint32_t G = (acc[k][2][i & 1] >> sh) & 0xffffu, T = (acc[k][3][i & 1] >> sh) & 0xffffu;
+            w[i][0] = A | C << 16; w[i][1] = G | T << 16;
+        }
+        nw[0] = ((acc[k][4][0]) & 0xffffu) | (acc[k][4][1] & 0xffffu) << 16;
+        nw[1] = (acc[k][4][0] >> 16) | (acc[k][4][1] >> 16) << 16;
+        uint4* dst = reinterpret_cast<uint4*>(acgt + o);
+        dst[0] = make_uint4(w[0][0], w[0][1], w[1][0], w[1][1]);
+        dst[1] = make_uint4(w[2][0], w[2][1], w[3][0], w[3][1]);
+        *reinterpret_cast<uint2*>(ncnt + o) = make_uint2(nw[0], nw[1]);
     }
 }
 

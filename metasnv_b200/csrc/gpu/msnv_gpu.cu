@@ -152,7 +152,7 @@ static int run_call_phase(msnv_ctx* ctx, const msnv_call_params* prm, int text_m
     CU(cudaMemcpyAsync(ctx->h_scalar + 1, ctx->d_scalar + 1, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(ctx->h_scalar + 2, ctx->d_err, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (ctx->h_scalar[2]) return fail(ctx, MSNV_E_LIMIT, "a read exceeds MSNV_MAX_READ_BASES / MSNV_MAX_READ_CIGAR");
+    if (ctx->h_scalar[2]) return fail(ctx, MSNV_E_LIMIT, "a read exceeds MSNV_MAX_READ_BASES / MSNV_MAX_READ_SEGMENTS, or its offsets and segments disagree");
     const uint32_t n_hits = ctx->h_scalar[1];
     if (ensure_hits(ctx, n_hits)) return MSNV_E_CUDA;
     if (n_hits) {
@@ -305,34 +305,34 @@ int msnv_shard_add_sample(msnv_ctx* ctx, uint32_t sample, const msnv_sample_read
     if (r->max_span > 8u * MSNV_MAX_READ_BASES) return fail(ctx, MSNV_E_LIMIT, "sample %u: reference span %u exceeds the limit", sample, r->max_span);
     CU(cudaSetDevice(ctx->device));
     const size_t n = r->n_reads, n1 = n + 1;
-    const size_t n_cig = r->cig_off[n], n_q4 = r->q4_off[n];
+    const size_t n_seg = r->seg_off[n], n_q4 = r->q4_off[n];
+    if (n_seg < n || n_q4 < n_seg) return fail(ctx, MSNV_E_ARG, "sample %u: inconsistent offsets (%zu reads, %zu segments, %zu quads)", sample, n, n_seg, n_q4);
     // one allocation per sample, sub-arrays 256-byte aligned, 32 spare bytes behind every array
     // because the pileup kernel's bulk copies read whole 16-byte units
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes + 32, 256); return o; };
-    const size_t o_pos = take(n * 4), o_cgo = take(n1 * 4), o_sgo = take(n1 * 4), o_q4 = take(n1 * 4), o_mate = take(n * 4),
-                 o_cig = take(n_cig * 4), o_seq = take(n_q4), o_qual = take(n_q4 * 4);
+    const size_t o_pos = take(n * 4), o_sgo = take(n1 * 4), o_q4 = take(n1 * 4), o_mate = take(n * 4),
+                 o_sp = take(n_seg * 4), o_sl = take(n_seg * 2), o_seq = take(n_q4), o_qual = take(n_q4 * 4);
     uint8_t* base = (uint8_t*)take_block(ctx, off);
     if (!base) return fail(ctx, MSNV_E_NOMEM, "sample %u: cannot allocate %zu bytes of device memory", sample, off);
     cudaStream_t st = ctx->stream;
     CU(cudaMemcpyAsync(base + o_pos, r->pos, n * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_cgo, r->cig_off, n1 * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_sgo, r->seg_off, n1 * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_q4, r->q4_off, n1 * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_mate, r->mate, n * 4, cudaMemcpyHostToDevice, st));
-    if (n_cig) CU(cudaMemcpyAsync(base + o_cig, r->cigar, n_cig * 4, cudaMemcpyHostToDevice, st));
-    if (n_q4) {
-        CU(cudaMemcpyAsync(base + o_seq, r->seq2, n_q4, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(base + o_qual, r->qual, n_q4 * 4, cudaMemcpyHostToDevice, st));
-    }
+    CU(cudaMemcpyAsync(base + o_sp, r->seg_pos, n_seg * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_sl, r->seg_len, n_seg * 2, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_seq, r->seq2, n_q4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_qual, r->qual, n_q4 * 4, cudaMemcpyHostToDevice, st));
     SampleDev& d = ctx->h_samples[sample];
-    d.pos = (const int32_t*)(base + o_pos);     d.cig_off = (const uint32_t*)(base + o_cgo);
+    d.pos = (const int32_t*)(base + o_pos);
     d.seg_off = (const uint32_t*)(base + o_sgo); d.q4_off = (const uint32_t*)(base + o_q4);
-    d.mate = (const int32_t*)(base + o_mate);   d.cigar = (const uint32_t*)(base + o_cig);
+    d.mate = (const int32_t*)(base + o_mate);
+    d.seg_pos = (const int32_t*)(base + o_sp);   d.seg_len = (const uint16_t*)(base + o_sl);
     d.seq2 = base + o_seq;                      d.qual = base + o_qual;
     d.n_reads = r->n_reads; d.max_span = r->max_span ? r->max_span : 1;
     ctx->n_reads += n; ctx->n_bases += 4ull * n_q4;
-    ctx->sizes[sample] = msnv_sample_sizes{r->n_reads, 0, d.max_span, 0, (uint64_t)n_cig, (uint64_t)n_q4};
+    ctx->sizes[sample] = msnv_sample_sizes{r->n_reads, 0, d.max_span, 0, (uint64_t)n_seg, (uint64_t)n_q4};
     return MSNV_OK;
 }
 
@@ -550,46 +550,49 @@ int msnv_shard_synth(msnv_ctx* ctx, const msnv_synth_desc* d, int64_t* first_col
             if (first_col < 0 || c < first_col) first_col = c;
         }
         const size_t n = (size_t)n_reads, n1 = n + 1, nb = blocks.size(), nft = frag0.back();
-        // ---- phase 1: per-read metadata
+        // ---- phase 1: per-read metadata (segments and quads per read, then their prefix sums)
         size_t o = 0;
         auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes + 32, 256); return r; };
-        const size_t o_pos = take(n * 4), o_cgo = take(n1 * 4), o_sgo = take(n1 * 4), o_q4 = take(n1 * 4), o_mate = take(n * 4);
+        const size_t o_pos = take(n * 4), o_sgo = take(n1 * 4), o_q4 = take(n1 * 4), o_mate = take(n * 4);
         uint8_t* meta = (uint8_t*)take_block(ctx, o);
         if (!meta) return fail(ctx, MSNV_E_NOMEM, "msnv_shard_synth: out of device memory (sample %u)", s);
-        SynthSampleCtg* d_blocks = nullptr; uint32_t *d_frag0 = nullptr, *d_nops = nullptr, *d_nsegs = nullptr, *d_for = nullptr;
+        SynthSampleCtg* d_blocks = nullptr; uint32_t *d_frag0 = nullptr, *d_nq = nullptr, *d_nsegs = nullptr, *d_for = nullptr;
         CU(cudaMalloc((void**)&d_blocks, nb * sizeof(SynthSampleCtg)));
         CU(cudaMalloc((void**)&d_frag0, (nb + 1) * 4));
-        CU(cudaMalloc((void**)&d_nops, n * 4));
+        CU(cudaMalloc((void**)&d_nq, n * 4));
         CU(cudaMalloc((void**)&d_nsegs, n * 4));
         CU(cudaMalloc((void**)&d_for, n * 4));
         CU(cudaMemcpyAsync(d_blocks, blocks.data(), nb * sizeof(SynthSampleCtg), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_frag0, frag0.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, st));
         synth_meta_kernel<<<(unsigned)((nft + 127) / 128), 128, 0, st>>>(m, (int)s, paired, D, overlap, d_blocks, d_frag0, (uint32_t)nb, (uint32_t)nft,
-            (int32_t*)(meta + o_pos), d_nops, d_nsegs, (uint32_t*)(meta + o_q4), (int32_t*)(meta + o_mate), d_for);
-        synth_tail_kernel<<<1, 1, 0, st>>>((uint32_t)n, q4, (uint32_t*)(meta + o_q4));
-        synth_scan2_kernel<<<1, 1024, 0, st>>>(d_nops, d_nsegs, (uint32_t)n, (uint32_t*)(meta + o_cgo), (uint32_t*)(meta + o_sgo));
-        uint32_t n_cig = 0;
-        CU(cudaMemcpyAsync(&n_cig, meta + o_cgo + n * 4, 4, cudaMemcpyDeviceToHost, st));
+            (int32_t*)(meta + o_pos), d_nsegs, d_nq, (int32_t*)(meta + o_mate), d_for);
+        synth_scan2_kernel<<<1, 1024, 0, st>>>(d_nsegs, d_nq, (uint32_t)n, (uint32_t*)(meta + o_sgo), (uint32_t*)(meta + o_q4));
+        uint32_t n_seg = 0, n_q4_u = 0;
+        CU(cudaMemcpyAsync(&n_seg, meta + o_sgo + n * 4, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&n_q4_u, meta + o_q4 + n * 4, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        // ---- phase 2: CIGARs, bases, qualities
-        const size_t n_q4 = n * q4;
+        // ---- phase 2: segment records, bases, qualities
+        const size_t n_q4 = n_q4_u;
+        const uint32_t q_slots = q4 + 4;          // upper bound of the quads of one read (two segments)
         o = 0;
-        const size_t o_cig = take((size_t)n_cig * 4), o_seq = take(n_q4), o_qual = take(n_q4 * 4);
+        const size_t o_sp = take((size_t)n_seg * 4), o_sl = take((size_t)n_seg * 2), o_seq = take(n_q4), o_qual = take(n_q4 * 4);
         uint8_t* data = (uint8_t*)take_block(ctx, o);
         if (!data) return fail(ctx, MSNV_E_NOMEM, "msnv_shard_synth: out of device memory (sample %u)", s);
-        synth_fill_kernel<<<(unsigned)((n_q4 + 255) / 256), 256, 0, st>>>(m, (int)s, paired, d_blocks, d_frag0, (uint32_t)nb, (uint32_t)n,
-            (const int32_t*)(meta + o_pos), (const uint32_t*)(meta + o_cgo), d_for, (uint32_t*)(data + o_cig), data + o_seq, data + o_qual);
+        synth_fill_kernel<<<(unsigned)((n * q_slots + 255) / 256), 256, 0, st>>>(m, (int)s, paired, d_blocks, d_frag0, (uint32_t)nb, (uint32_t)n, q_slots,
+            (const int32_t*)(meta + o_pos), (const uint32_t*)(meta + o_sgo), (const uint32_t*)(meta + o_q4), d_for,
+            (int32_t*)(data + o_sp), (uint16_t*)(data + o_sl), data + o_seq, data + o_qual);
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
-        cudaFree(d_blocks); cudaFree(d_frag0); cudaFree(d_nops); cudaFree(d_nsegs); cudaFree(d_for);
+        cudaFree(d_blocks); cudaFree(d_frag0); cudaFree(d_nq); cudaFree(d_nsegs); cudaFree(d_for);
         SampleDev& sd = ctx->h_samples[s];
-        sd.pos = (const int32_t*)(meta + o_pos);     sd.cig_off = (const uint32_t*)(meta + o_cgo);
+        sd.pos = (const int32_t*)(meta + o_pos);
         sd.seg_off = (const uint32_t*)(meta + o_sgo); sd.q4_off = (const uint32_t*)(meta + o_q4);
-        sd.mate = (const int32_t*)(meta + o_mate);   sd.cigar = (const uint32_t*)(data + o_cig);
+        sd.mate = (const int32_t*)(meta + o_mate);
+        sd.seg_pos = (const int32_t*)(data + o_sp);  sd.seg_len = (const uint16_t*)(data + o_sl);
         sd.seq2 = data + o_seq;                      sd.qual = data + o_qual;
         sd.n_reads = (uint32_t)n; sd.max_span = L + 3;
         ctx->n_reads += n; ctx->n_bases += 4ull * n_q4;
-        ctx->sizes[s] = msnv_sample_sizes{(uint32_t)n, (uint32_t)n_mated, L + 3, 0, (uint64_t)n_cig, (uint64_t)n_q4};
+        ctx->sizes[s] = msnv_sample_sizes{(uint32_t)n, (uint32_t)n_mated, L + 3, 0, (uint64_t)n_seg, (uint64_t)n_q4};
     }
     if (first_column) *first_column = first_col;
     return MSNV_OK;
@@ -603,8 +606,8 @@ int msnv_shard_sample_sizes(msnv_ctx* ctx, uint32_t sample, msnv_sample_sizes* s
     return MSNV_OK;
 }
 
-int msnv_shard_export_sample(msnv_ctx* ctx, uint32_t sample, int32_t* pos, uint32_t* cig_off, uint32_t* seg_off, uint32_t* q4_off,
-                             int32_t* mate, uint32_t* cigar, uint8_t* seq2, uint8_t* qual)
+int msnv_shard_export_sample(msnv_ctx* ctx, uint32_t sample, int32_t* pos, uint32_t* seg_off, uint32_t* q4_off, int32_t* mate,
+                             int32_t* seg_pos, uint16_t* seg_len, uint8_t* seq2, uint8_t* qual)
 {
     if (!ctx) return MSNV_E_ARG;
     if (!ctx->open || sample >= ctx->S) return fail(ctx, MSNV_E_ARG, "msnv_shard_export_sample: no such sample");
@@ -615,11 +618,13 @@ int msnv_shard_export_sample(msnv_ctx* ctx, uint32_t sample, int32_t* pos, uint3
     const SampleDev& d = ctx->h_samples[sample];
     const size_t n = z.n_reads, n1 = n + 1;
     CU(cudaMemcpyAsync(pos, d.pos, n * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(cig_off, d.cig_off, n1 * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(seg_off, d.seg_off, n1 * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(q4_off, d.q4_off, n1 * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(mate, d.mate, n * 4, cudaMemcpyDeviceToHost, st));
-    if (z.n_cigar) CU(cudaMemcpyAsync(cigar, d.cigar, (size_t)z.n_cigar * 4, cudaMemcpyDeviceToHost, st));
+    if (z.n_segs) {
+        CU(cudaMemcpyAsync(seg_pos, d.seg_pos, (size_t)z.n_segs * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(seg_len, d.seg_len, (size_t)z.n_segs * 2, cudaMemcpyDeviceToHost, st));
+    }
     if (z.n_q4) {
         CU(cudaMemcpyAsync(seq2, d.seq2, (size_t)z.n_q4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(qual, d.qual, (size_t)z.n_q4 * 4, cudaMemcpyDeviceToHost, st));

@@ -52,11 +52,11 @@ __device__ __forceinline__ uint32_t count_starts_below(const Model& m, int sampl
     return lo;
 }
 
-// One thread per fragment: ranks of its read(s), positions, op / segment counts, mate links.
+// One thread per fragment: ranks of its read(s), positions, segment / quad counts, mate links.
 __global__ void synth_meta_kernel(Model m, int sample, bool paired, int32_t D, bool overlap, const SynthSampleCtg* __restrict__ blocks,
                                   const uint32_t* __restrict__ frag0 /*[n_blocks+1]*/, uint32_t n_blocks, uint32_t n_frag_total,
-                                  int32_t* __restrict__ pos, uint32_t* __restrict__ n_ops, uint32_t* __restrict__ n_segs,
-                                  uint32_t* __restrict__ q4_off, int32_t* __restrict__ mate, uint32_t* __restrict__ frag_of_rank)
+                                  int32_t* __restrict__ pos, uint32_t* __restrict__ n_segs, uint32_t* __restrict__ n_quads,
+                                  int32_t* __restrict__ mate, uint32_t* __restrict__ frag_of_rank)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_frag_total) return;
@@ -65,7 +65,6 @@ __global__ void synth_meta_kernel(Model m, int sample, bool paired, int32_t D, b
     const uint32_t f = g - frag0[bi];
     const uint32_t span = msnv::synth::frag_span(m, paired, D);
     const uint32_t x = msnv::synth::frag_start(m, sample, b.ctg, b.len, span, b.n_frag, f);
-    const uint32_t q4 = (uint32_t)(m.read_len + 3) / 4;
     uint32_t r1 = b.read0 + f, r2 = 0;
     if (paired) {
         r1 = b.read0 + f + count_starts_below(m, sample, b, span, (int64_t)x - D, false);     // second mates strictly before
@@ -74,33 +73,35 @@ __global__ void synth_meta_kernel(Model m, int sample, bool paired, int32_t D, b
     for (int k = 0; k < (paired ? 2 : 1); ++k) {
         const uint32_t r = k == 0 ? r1 : r2;
         const msnv::synth::ReadShape sh = msnv::synth::read_shape(m, sample, b.ctg, f, k, paired);
-        pos[r] = (int32_t)(b.offset + x + (k ? (uint32_t)D : 0u));
-        n_ops[r] = (uint32_t)sh.n_ops;
-        uint32_t ns = 0;
-        for (int o = 0; o < sh.n_ops; ++o) ns += (sh.ops[o] & 0xf) == 0;
+        const uint32_t p = b.offset + x + (k ? (uint32_t)D : 0u);
+        pos[r] = (int32_t)p;
+        uint32_t ns = 0, nq = 0, rx = p;
+        for (int o = 0; o < sh.n_ops; ++o) {
+            const uint32_t op = sh.ops[o] & 0xf, len = sh.ops[o] >> 4;
+            if (op == 0) { ++ns; nq += ((rx & 3u) + len + 3u) >> 2; rx += len; }
+            else if (op == 2) rx += len;
+        }
         n_segs[r] = ns;
-        q4_off[r] = r * q4;
+        n_quads[r] = nq;
         mate[r] = overlap ? (int32_t)(k == 1 ? r1 : r2) : -1;
         frag_of_rank[r] = (g << 1) | (uint32_t)k;
     }
 }
 
-__global__ void synth_tail_kernel(uint32_t n_reads, uint32_t q4, uint32_t* __restrict__ q4_off)
-{
-    q4_off[n_reads] = n_reads * q4;
-}
-
-// One thread per (read, 4-base group): bases, qualities and (group 0) the CIGAR words.
+// One thread per (read, quad slot): the quad's bases and qualities in the position-aligned layout
+// of include/msnv.h; slot 0 also writes the read's segment records.
 __global__ void synth_fill_kernel(Model m, int sample, bool paired, const SynthSampleCtg* __restrict__ blocks,
-                                  const uint32_t* __restrict__ frag0, uint32_t n_blocks, uint32_t n_reads,
-                                  const int32_t* __restrict__ pos, const uint32_t* __restrict__ cig_off,
-                                  const uint32_t* __restrict__ frag_of_rank, uint32_t* __restrict__ cigar,
+                                  const uint32_t* __restrict__ frag0, uint32_t n_blocks, uint32_t n_reads, uint32_t q_slots,
+                                  const int32_t* __restrict__ pos, const uint32_t* __restrict__ seg_off,
+                                  const uint32_t* __restrict__ q4_off, const uint32_t* __restrict__ frag_of_rank,
+                                  int32_t* __restrict__ seg_pos, uint16_t* __restrict__ seg_len,
                                   uint8_t* __restrict__ seq2, uint8_t* __restrict__ qual)
 {
-    const uint32_t q4 = (uint32_t)(m.read_len + 3) / 4;
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (uint64_t)n_reads * q4) return;
-    const uint32_t r = (uint32_t)(t / q4), grp = (uint32_t)(t - (uint64_t)r * q4);
+    if (t >= (uint64_t)n_reads * q_slots) return;
+    const uint32_t r = (uint32_t)(t / q_slots), slot = (uint32_t)(t - (uint64_t)r * q_slots);
+    const uint32_t q0 = q4_off[r], nq_read = q4_off[r + 1] - q0;
+    if (slot >= nq_read && slot != 0) return;
     const uint32_t fr = frag_of_rank[r];
     const uint32_t g = fr >> 1; const int k = (int)(fr & 1);
     const uint32_t bi = block_of(frag0, n_blocks, g);
@@ -108,28 +109,35 @@ __global__ void synth_fill_kernel(Model m, int sample, bool paired, const SynthS
     const uint32_t f = g - frag0[bi];
     const msnv::synth::ReadShape sh = msnv::synth::read_shape(m, sample, b.ctg, f, k, paired);
     const uint64_t rid = (uint64_t)f * 2 + (uint64_t)k;
-    const int64_t rpos = (int64_t)pos[r] - (int64_t)b.offset;
-    if (grp == 0) for (int o = 0; o < sh.n_ops; ++o) cigar[cig_off[r] + o] = sh.ops[o];
+    // walk the aligned segments: rx = shard coordinate, qy = query index of the segment's first base
+    uint32_t rx = (uint32_t)pos[r], qy = 0, quads_before = 0, seg = 0;
     uint32_t sbyte = 0, qword = 0;
-    for (int j4 = 0; j4 < 4; ++j4) {
-        const int j = (int)grp * 4 + j4;
-        if (j >= m.read_len) break;
-        // reference position of query base j (or -1 inside an insertion / clip)
-        int64_t refp = -1; int qy = 0; int64_t rx = rpos;
-        for (int o = 0; o < sh.n_ops; ++o) {
-            const int op = (int)(sh.ops[o] & 0xf), len = (int)(sh.ops[o] >> 4);
-            if (op == 0) { if (j < qy + len) { refp = rx + (j - qy); break; } qy += len; rx += len; }
-            else if (op == 1 || op == 4) { if (j < qy + len) { refp = -1; break; } qy += len; }
-            else if (op == 2) rx += len;
-        }
-        const char c = msnv::synth::read_base(m, sample, (int)b.genome, (int)b.n_sub, b.ctg, rid, j, refp);
-        uint32_t q = msnv::synth::read_qual(m, sample, b.ctg, rid, j);
-        const int code = msnv::synth::base_code(c);
-        if (code < 0) q |= 0x80u; else sbyte |= (uint32_t)code << (2 * j4);
-        qword |= q << (8 * j4);
+    for (int o = 0; o < sh.n_ops; ++o) {
+        const uint32_t op = sh.ops[o] & 0xf, len = sh.ops[o] >> 4;
+        if (op == 0) {
+            const uint32_t a = rx & 3u, nq = (a + len + 3u) >> 2;
+            if (slot == 0) { seg_pos[seg_off[r] + seg] = (int32_t)rx; seg_len[seg_off[r] + seg] = (uint16_t)len; }
+            if (slot >= quads_before && slot < quads_before + nq) {
+                const uint32_t first = (rx - a) + 4u * (slot - quads_before);       // shard coordinate of the quad's first position
+                for (uint32_t j4 = 0; j4 < 4; ++j4) {
+                    const uint32_t p = first + j4;
+                    if (p < rx || p >= rx + len) continue;                        // padding: quality 0, base bits 0
+                    const int j = (int)(qy + (p - rx));
+                    const char c = msnv::synth::read_base(m, sample, (int)b.genome, (int)b.n_sub, b.ctg, rid, j, (int64_t)p - (int64_t)b.offset);
+                    uint32_t q = msnv::synth::read_qual(m, sample, b.ctg, rid, j);
+                    const int code = msnv::synth::base_code(c);
+                    if (code < 0) q |= 0x80u; else sbyte |= (uint32_t)code << (2 * j4);
+                    qword |= q << (8 * j4);
+                }
+            }
+            quads_before += nq; ++seg; qy += len; rx += len;
+        } else if (op == 1 || op == 4) qy += len;
+        else if (op == 2) rx += len;
     }
-    seq2[(size_t)r * q4 + grp] = (uint8_t)sbyte;
-    reinterpret_cast<uint32_t*>(qual)[(size_t)r * q4 + grp] = qword;
+    if (slot < nq_read) {
+        seq2[(size_t)q0 + slot] = (uint8_t)sbyte;
+        reinterpret_cast<uint32_t*>(qual)[(size_t)q0 + slot] = qword;
+    }
 }
 
 // exclusive scans of two u32 arrays of one sample by one CTA (n up to 2^31); writes n+1 entries

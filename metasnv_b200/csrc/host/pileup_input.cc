@@ -127,15 +127,15 @@ msnv_sample_reads SampleReads::view() const
     memset(&v, 0, sizeof v);
     v.n_reads = (uint32_t)pos.size();
     v.max_span = max_span;
-    v.pos = pos.data(); v.cig_off = cig_off.data(); v.seg_off = seg_off.data(); v.q4_off = q4_off.data();
-    v.mate = mate.data(); v.cigar = cigar.data(); v.seq2 = seq2.data(); v.qual = qual.data();
+    v.pos = pos.data(); v.seg_off = seg_off.data(); v.q4_off = q4_off.data(); v.mate = mate.data();
+    v.seg_pos = seg_pos.data(); v.seg_len = seg_len.data(); v.seq2 = seq2.data(); v.qual = qual.data();
     return v;
 }
 
 size_t SampleReads::bytes() const
 {
-    return pos.size() * 4 + cig_off.size() * 4 + seg_off.size() * 4 + q4_off.size() * 4 + mate.size() * 4 +
-           cigar.size() * 4 + seq2.size() + qual.size();
+    return pos.size() * 4 + seg_off.size() * 4 + q4_off.size() * 4 + mate.size() * 4 + seg_pos.size() * 4 +
+           seg_len.size() * 2 + seq2.size() + qual.size();
 }
 
 namespace {
@@ -183,7 +183,7 @@ bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& la
         int32_t rlen = 0; uint32_t n_seg = 0;
         for (int i = 0; i < c.n_cigar; ++i) {
             const uint32_t w = r.cigar_at(i), op = w & 0xf;
-            if (op == CIG_M || op == CIG_EQ || op == CIG_X) { rlen += (int32_t)(w >> 4); ++n_seg; }
+            if (op == CIG_M || op == CIG_EQ || op == CIG_X) { rlen += (int32_t)(w >> 4); n_seg += (w >> 4) != 0; }
             else if (op == CIG_D || op == CIG_N) rlen += (int32_t)(w >> 4);
         }
         const int slot = layout.slot_of_tid[c.tid];
@@ -200,9 +200,9 @@ bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& la
             if (!warned_overhang) { fprintf(stderr, "[msnv] %s: read %s extends beyond its contig; such reads are skipped\n", bam_path.c_str(), r.qname); warned_overhang = true; }
             continue;
         }
-        if (c.l_seq > MSNV_MAX_READ_BASES || c.n_cigar > MSNV_MAX_READ_CIGAR) {
+        if (c.l_seq > MSNV_MAX_READ_BASES || n_seg > MSNV_MAX_READ_SEGMENTS) {
             err = bam_path + ": read " + r.qname + " exceeds the supported length (" + std::to_string(MSNV_MAX_READ_BASES) +
-                  " bases / " + std::to_string(MSNV_MAX_READ_CIGAR) + " CIGAR operations)";
+                  " bases / " + std::to_string(MSNV_MAX_READ_SEGMENTS) + " aligned segments)";
             return false;
         }
 
@@ -248,38 +248,55 @@ bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& la
         out.pos.push_back((int32_t)(ctg.offset + (uint32_t)c.pos));
         out.mate.push_back(mate_idx);
         if (mate_idx >= 0) { out.mate[(size_t)mate_idx] = (int32_t)idx; ++st.pairs; }
-        for (int i = 0; i < c.n_cigar; ++i) out.cigar.push_back(r.cigar_at(i));
-        out.cig_off.push_back((uint32_t)out.cigar.size());
         out.seg_off.push_back(out.seg_off.back() + n_seg);
-        const size_t l = (size_t)c.l_seq, g = (l + 3) / 4, s0 = out.seq2.size(), q0 = out.qual.size();
-        out.seq2.resize(s0 + g, 0);
-        out.qual.resize(q0 + 4 * g, 0);
-        uint8_t* sq = out.seq2.data() + s0; uint8_t* ql = out.qual.data() + q0;
-        for (size_t i = 0; i < l; ++i) {
-            const uint8_t c4 = (r.seq[i >> 1] >> ((~i & 1) << 2)) & 0xf;
-            const uint8_t c2 = kCode4to2[c4];
-            uint8_t q = r.qual[i]; if (q > 127) q = 127;
-            if (c2 == 4) {
-                q |= 0x80;
-                if (c4 != 15 && !warned_iupac) {
-                    fprintf(stderr, "[msnv] %s: read %s has a base other than A/C/G/T/N; such bases are not counted\n", bam_path.c_str(), r.qname);
-                    warned_iupac = true;
-                }
-            } else sq[i >> 2] |= (uint8_t)(c2 << ((i & 3) * 2));
-            ql[i] = q;
+        // every M/=/X operation becomes a segment stored position-aligned (include/msnv.h): byte i of its
+        // quads belongs to shard coordinate (first & ~3) + i; inserted and clipped bases are dropped
+        size_t quads = 0;
+        {
+            uint32_t rx = ctg.offset + (uint32_t)c.pos;           // shard coordinate
+            size_t qy = 0;                                        // query index
+            for (int i = 0; i < c.n_cigar; ++i) {
+                const uint32_t w = r.cigar_at(i), op = w & 0xf, len = w >> 4;
+                if (op == CIG_M || op == CIG_EQ || op == CIG_X) {
+                    if (len) {
+                        if (qy + len > (size_t)c.l_seq) { err = bam_path + ": read " + r.qname + ": CIGAR longer than the sequence"; return false; }
+                        const uint32_t a = rx & 3u; const size_t nq = (a + len + 3u) >> 2;
+                        const size_t s0 = out.seq2.size(), q0 = out.qual.size();
+                        out.seq2.resize(s0 + nq, 0);
+                        out.qual.resize(q0 + 4 * nq, 0);
+                        uint8_t* sq = out.seq2.data() + s0; uint8_t* ql = out.qual.data() + q0;
+                        for (uint32_t k = 0; k < len; ++k) {
+                            const size_t i2 = qy + k, o = a + k;
+                            const uint8_t c4 = (r.seq[i2 >> 1] >> ((~i2 & 1) << 2)) & 0xf;
+                            const uint8_t c2 = kCode4to2[c4];
+                            uint8_t q = r.qual[i2]; if (q > 127) q = 127;
+                            if (c2 == 4) {
+                                q |= 0x80;
+                                if (c4 != 15 && !warned_iupac) {
+                                    fprintf(stderr, "[msnv] %s: read %s has a base other than A/C/G/T/N; such bases are not counted\n", bam_path.c_str(), r.qname);
+                                    warned_iupac = true;
+                                }
+                            } else sq[o >> 2] |= (uint8_t)(c2 << ((o & 3) * 2));
+                            ql[o] = q;
+                        }
+                        out.seg_pos.push_back((int32_t)rx);
+                        out.seg_len.push_back((uint16_t)len);
+                        quads += nq;
+                        st.aligned_bases += len;
+                    }
+                    rx += len; qy += len;
+                } else if (op == CIG_D || op == CIG_N) rx += len;
+                else if (op == CIG_I || op == CIG_S) qy += len;
+            }
         }
-        if (out.q4_off.back() + g > 0xffffffffull) { err = bam_path + ": more than 2^34 bases in one shard of one sample"; return false; }
-        out.q4_off.push_back((uint32_t)(out.q4_off.back() + g));
+        if (out.q4_off.back() + quads > 0xffffffffull) { err = bam_path + ": more than 2^34 bases in one shard of one sample"; return false; }
+        out.q4_off.push_back((uint32_t)(out.q4_off.back() + quads));
         if ((uint32_t)rlen > out.max_span) out.max_span = (uint32_t)rlen;
         if (st.first_column < 0) {
             int64_t p = layout.first_inside(slot, c.pos, end);
             if (p >= 0) st.first_column = (int64_t)ctg.offset + p;
         }
         ++st.accepted;
-        for (int i = 0; i < c.n_cigar; ++i) {
-            const uint32_t w = r.cigar_at(i), op = w & 0xf;
-            if (op == CIG_M || op == CIG_EQ || op == CIG_X) st.aligned_bases += w >> 4;
-        }
     }
     if (rc < 0) { err = bam_path + ": " + rd.error(); return false; }
     if (st.max_buffered + 64u > 65535u) { err = bam_path + ": pileup depth above 65535 is not supported"; return false; }

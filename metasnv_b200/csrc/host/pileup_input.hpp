@@ -49,9 +49,10 @@ struct ShardLayout {
 // Growable host-side arrays of one sample, in the layout of msnv_sample_reads.
 struct SampleReads {
     std::vector<int32_t>  pos;
-    std::vector<uint32_t> cig_off{0}, seg_off{0}, q4_off{0};
+    std::vector<uint32_t> seg_off{0}, q4_off{0};
     std::vector<int32_t>  mate;
-    std::vector<uint32_t> cigar;
+    std::vector<int32_t>  seg_pos;
+    std::vector<uint16_t> seg_len;
     std::vector<uint8_t>  seq2, qual;
     uint32_t max_span = 0;
     msnv_sample_reads view() const;
