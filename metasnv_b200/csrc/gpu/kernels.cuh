@@ -17,22 +17,20 @@
 #include <stdint.h>
 
 #include "../../../include/msnv.h"
+#include "overlap_rule.h"
 
 namespace msnv_gpu {
 
 constexpr int TILE = MSNV_TILE;                 // positions per tile
-constexpr int PILEUP_THREADS = 256;             // threads per pileup CTA (each folds TILE/256 positions)
-// reads staged per chunk: <= 255 (8-bit per-chunk counters, one walk thread per read). Two
-// instantiations of the pileup kernel: a small one for shallow data (8 CTAs per SM) and a large
-// one for deep data (fewer, longer chunks per tile)
-constexpr int CHUNK_READS_SMALL = 127, CHUNK_READS_LARGE = 255;
-constexpr int PILEUP_CTAS_SMALL = TILE >= 1024 ? 6 : 8, PILEUP_CTAS_LARGE = TILE >= 1024 ? 4 : 5;   // launch-bound targets (register budget)
+// CTA shapes of the pileup kernel (threads, reads staged per chunk <= threads - 1: one thread per read in the
+// per-read steps; at most 255 so that 8-bit per-chunk counters cannot overflow). A CTA's life is a sequence of
+// short dependent steps, so many small CTAs per SM keep the SM busy better than few large ones; deep data gets
+// the larger shape (fewer chunks per tile).
 constexpr int CHUNK_Q4_MAX = 4096;              // upper bound of the quads staged per chunk (chosen per launch)
 constexpr int CHUNK_Q4_MIN = MSNV_MAX_READ_BASES / 4 + 2 * MSNV_MAX_READ_SEGMENTS;   // a single read always fits
-constexpr int CHUNK_SEGS_SMALL = 256, CHUNK_SEGS_LARGE = 512;   // aligned segments per chunk
+constexpr int CHUNK_SEGS = 256;                 // aligned segments per chunk (<= 256: one byte tags a quad)
 
-static_assert(TILE % PILEUP_THREADS == 0 && PILEUP_THREADS >= 256, "one walk thread per staged read");
-static_assert(MSNV_MAX_READ_SEGMENTS <= CHUNK_SEGS_SMALL, "one read's segments must fit a chunk");
+static_assert(MSNV_MAX_READ_SEGMENTS <= CHUNK_SEGS, "one read's segments must fit a chunk");
 
 struct SampleDev {
     const int32_t*  pos;
@@ -46,7 +44,9 @@ struct SampleDev {
     uint32_t        n_reads, max_span;
 };
 
-struct Item { uint32_t sample, tile, r_lo, r_hi; };   // reads [r_lo, r_hi) of `sample` may overlap `tile`
+// reads [r_lo, r_hi) of `sample` may overlap `tile`; q4_* / sg_* = q4_off / seg_off at r_lo and r_hi, which lets a
+// CTA prefetch a later item's data without first loading that item's offsets
+struct __align__(16) Item { uint32_t sample, tile, r_lo, r_hi, q4_lo, sg_lo, q4_hi, sg_hi; };
 
 // Per-position population result of call_kernel.
 struct CallParamsDev { int32_t min_cov; int32_t thr; double frac; };
@@ -196,7 +196,10 @@ __global__ void __launch_bounds__(256) index_kernel(const SampleDev* __restrict_
         if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
     } else {
         const uint32_t slot = block_sums[blockIdx.x] + rank;     // block_sums holds exclusive offsets now
-        if (active) items[slot] = Item{s, t, r_lo, r_hi};
+        if (active) {
+            const uint32_t* qo = samples[s].q4_off; const uint32_t* so = samples[s].seg_off;
+            items[slot] = Item{s, t, r_lo, r_hi, __ldg(qo + r_lo), __ldg(so + r_lo), __ldg(qo + r_hi), __ldg(so + r_hi)};
+        }
         if (pair < n_pairs && s == 0) tile_begin[t] = slot;
     }
 }
@@ -208,7 +211,7 @@ __global__ void dense_items_kernel(uint32_t n_samples, uint32_t n_tiles, Item* _
     const uint64_t n = (uint64_t)n_samples * n_tiles;
     if (i < n) {
         const uint32_t t = (uint32_t)(i / n_samples), s = (uint32_t)(i - (uint64_t)t * n_samples);
-        items[i] = Item{s, t, 0u, 0u};
+        items[i] = Item{s, t, 0u, 0u, 0u, 0u, 0u, 0u};
         if (s == 0) tile_begin[t] = (uint32_t)i;
     }
     if (i == n) tile_begin[n_tiles] = (uint32_t)n;
@@ -255,39 +258,32 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ v, ui
 // ------------------------------------------------------------------------------------------------
 // helpers of the pileup kernel
 // ------------------------------------------------------------------------------------------------
-// mpileup's mate-overlap rule (htslib tweak_overlap_quality, SURVEY.md Annex A.2) for one reference
-// position that both mates align to. va/vb: staged quality bytes (bit 7: non-ACGT base) of the mate
-// that comes first in the file (a) and of the later one (b); same: the two bases are equal.
-// Qualities live in 7 bits, so htslib's cap of 200 becomes 127: only "q >= 13" is ever used.
-__device__ __forceinline__ void overlap_rule(uint32_t va, uint32_t vb, bool same, uint32_t& na, uint32_t& nb)
-{
-    const uint32_t fa = va & 0x80u, fb = vb & 0x80u, qa = va & 0x7fu, qb = vb & 0x7fu;
-    if (same) { uint32_t q = qa + qb; if (q > 127u) q = 127u; na = fa | q; nb = fb; }
-    else if (qa >= qb) { na = fa | (uint32_t)(0.8 * (double)qa); nb = fb; }
-    else { na = fa; nb = fb | (uint32_t)(0.8 * (double)qb); }
-}
-
 // ------------------------------------------------------------------------------------------------
-// pileup: one CTA of PILEUP_THREADS threads per work item (sample, tile of TILE positions).
+// pileup: one CTA (128 or 256 threads, see the variant table in msnv_gpu.cu) per work item
+// (sample, tile of TILE positions).
 // Reads arrive as position-aligned segments (include/msnv.h): a staged quad holds four consecutive
 // positions starting at a multiple of four, so a quad is either on the tile or off it, and the four
-// bases of a quad are counted with byte-lane (SWAR) arithmetic, never one at a time.
+// bases of a quad are handled with byte-lane (SWAR) arithmetic, never one at a time.
 // Per chunk of reads (<= CHUNK_READS reads, chunk_q4 quads, CHUNK_SEGS segments):
-//   1. metadata of the chunk's reads -> shared memory; __syncthreads_count sizes the chunk
+//   1. offsets and mates of the chunk's reads -> shared memory; __syncthreads_count sizes the chunk
 //   2. two TMA bulk copies (2-bit bases, qualities) are issued; while they fly,
-//   3. one thread per read loads its segment records, derives for every segment the tile-relative
-//      quad index of its first staged quad, and tags the read's quads with their segment
-//   4. mate-overlap quality correction in shared memory, eight lanes per pair
-//      (mates staged in another chunk are read, pristine, from global memory)
+//   3. one thread per read loads its segment records, derives for every segment where its quads
+//      lie in the staging buffer and on the tile, and tags those quads with the segment's index
+//      (word-wide stores)
+//   4. mate-overlap quality correction in shared memory (overlap_rule.h), eight lanes per pair, a
+//      quad of both mates per lane and step (mates staged in another chunk are read, pristine,
+//      from global memory)
 //   5. flat scatter: thread g takes the g-th staged quad: quality test and base decoding for the
 //      four positions at once, then ONE shared-memory atomic per base letter. Plane X of the
-//      counters holds, per quad of the tile, a word with one byte lane per position; lanes of a
-//      warp hit consecutive words (no bank conflicts, no swizzle) and the plane offsets are
-//      immediates. Padding bytes carry quality 0 and fail the threshold like any poor base.
-//   6. thread t folds the byte lanes of quad t into 16-bit lanes held in registers and clears them
-// The reads in HBM are never modified. CTAs are small (8 warps) and the staging buffers are sized
-// at launch from the mean work per item, so that several CTAs per SM overlap each other's barriers
-// and copy latency.
+//      counters holds, per quad of the tile, a word with one byte lane per position; the plane
+//      offsets are immediates. Padding bytes carry quality 0 and fail the threshold like any poor
+//      base.
+//   6. thread t folds the byte lanes of its quads into 16-bit lanes held in registers and clears them
+// The reads in HBM are never modified. Lane 0 of the last warp asks L2 for the first chunk of the
+// item PILEUP_PREFETCH_DISTANCE further on (the Item record carries the offsets that needs).
+// What bounds the kernel is the length of this chain of short dependent steps, not HBM: CTAs are
+// kept small and the staging buffers are sized at launch from the mean work per item so that 7-8
+// CTAs per SM overlap each other's barriers and latencies.
 //
 // Shared memory (dynamic), regions 16-byte aligned:
 //   s_meta   3 x META_STRIDE u32      q4_off | seg_off | mate of the chunk's reads
@@ -296,32 +292,44 @@ __device__ __forceinline__ void overlap_rule(uint32_t va, uint32_t vb, bool same
 //   s_cnt    5 x TILE bytes           planes A, C, G, T, non-ACGT: one byte per position
 //   s_seq    chunk_q4 + 32 bytes      2-bit bases           (TMA destination)
 //   s_qual   4*chunk_q4 + 32 bytes    qualities             (TMA destination)
-//   s_g2s    chunk_q4 u16             segment of every staged quad
+//   s_g2s    chunk_q4 bytes           segment of every staged quad
 // ------------------------------------------------------------------------------------------------
 constexpr int TILE_QUADS = TILE / 4;
-constexpr int QUADS_PER_THREAD = TILE_QUADS / PILEUP_THREADS;
-static_assert(TILE_QUADS % PILEUP_THREADS == 0 && QUADS_PER_THREAD >= 1, "each thread folds whole quads");
 
-__host__ __device__ constexpr size_t pileup_smem_bytes(int chunk_reads, int chunk_segs, uint32_t chunk_q4)
+__host__ __device__ constexpr size_t pileup_smem_bytes(int chunk_reads, uint32_t chunk_q4)
 {
-    return (size_t)(3 * ((chunk_reads + 4) / 4 * 4) * 4 + chunk_segs * 16 + ((chunk_reads + 4) / 4 * 4) * 2 + 64 + 5 * TILE) +
-           (chunk_q4 + 32) + (4 * (size_t)chunk_q4 + 32) + 2 * (size_t)chunk_q4 + 32;
+    return (size_t)(3 * ((chunk_reads + 4) / 4 * 4) * 4 + CHUNK_SEGS * 16 + ((chunk_reads + 4) / 4 * 4) * 2 + 64 + 5 * TILE) +
+           (chunk_q4 + 32) + (4 * (size_t)chunk_q4 + 32) + (size_t)chunk_q4 + 32;
 }
 
 // explicit shared-window accesses (32-bit addresses): the compiler otherwise rebuilds generic
 // pointers from the CTA's shared base in every iteration of the scatter loop
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 template <int OFF>
 __device__ __forceinline__ void red_shared_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0+%2], %1;" :: "r"(a), "r"(v), "n"(OFF) : "memory"); }
 
-template <int CHUNK_READS, int CHUNK_SEGS, int MIN_CTAS>
-__global__ void __launch_bounds__(PILEUP_THREADS, MIN_CTAS)
+// L2 prefetch of [p, p + bytes): whole 16-byte units around the range (the arrays carry 32 spare bytes)
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes)
+{
+    const uintptr_t a = (uintptr_t)p & ~(uintptr_t)15;
+    const uint32_t n = (uint32_t)((uintptr_t)p - a + bytes + 15u) & ~15u;
+    if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a), "r"(n) : "memory");
+}
+
+// Items this far ahead of a CTA's own are prefetched into L2 by it (about two waves of resident CTAs):
+// a CTA's life is a chain of dependent loads (item -> offsets -> segment records / bases / qualities),
+// which then hit L2 instead of HBM.
+constexpr uint32_t PILEUP_PREFETCH_DISTANCE = 148 * 6 * 2;     // overridable: MSNV_PF_DIST (0 switches prefetching off)
+
+template <int THREADS, int CHUNK_READS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
 pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items, uint32_t chunk_q4,
               uint64_t* __restrict__ acgt /*[n_items][TILE]*/, uint16_t* __restrict__ ncnt /*[n_items][TILE]*/,
-              int* __restrict__ err_flag)
+              int* __restrict__ err_flag, uint32_t pf_dist)
 {
+    static_assert(CHUNK_SEGS <= 256 && CHUNK_READS < THREADS && TILE_QUADS % THREADS == 0, "one thread per staged read; each thread folds whole quads");
+    constexpr int QUADS_PER_THREAD = TILE_QUADS / THREADS;
     constexpr int META_STRIDE = (CHUNK_READS + 4) / 4 * 4;
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* s_q4   = (uint32_t*)smem;
@@ -334,7 +342,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     uint32_t* s_cnt  = s_misc + 14;                   // 5 planes of TILE_QUADS words
     uint8_t*  s_seq  = (uint8_t*)(s_cnt + 5 * TILE_QUADS);
     uint8_t*  s_qual = s_seq + chunk_q4 + 32;
-    uint16_t* s_g2s  = (uint16_t*)(s_qual + 4 * chunk_q4 + 32);
+    uint8_t*  s_g2s  = s_qual + 4 * chunk_q4 + 32;                // 4-byte aligned
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const Item it = items[blockIdx.x];
@@ -342,7 +350,22 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     const SampleDev* __restrict__ sd = samples + it.sample;
 
     if (tid == 0) { mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    for (int k = tid; k < 5 * TILE_QUADS; k += PILEUP_THREADS) s_cnt[k] = 0;
+    if (tid == THREADS - 32 && blockIdx.x + pf_dist < n_items && pf_dist) {
+        // the last warp is the one least needed for the first chunk's metadata: its lane 0 follows the chain
+        // of a later item and asks L2 for that item's first chunk
+        const Item f = items[blockIdx.x + pf_dist];
+        const SampleDev* __restrict__ fd = samples + f.sample;
+        uint32_t fn = f.r_hi - f.r_lo; if (fn > CHUNK_READS) fn = CHUNK_READS;
+        prefetch_l2(fd->q4_off + f.r_lo, (fn + 1) * 4u);
+        prefetch_l2(fd->seg_off + f.r_lo, (fn + 1) * 4u);
+        prefetch_l2(fd->mate + f.r_lo, fn * 4u);
+        const uint32_t fs = min(f.sg_hi - f.sg_lo, (uint32_t)CHUNK_SEGS), fq = min(f.q4_hi - f.q4_lo, chunk_q4);
+        prefetch_l2(fd->seg_pos + f.sg_lo, fs * 4u);
+        prefetch_l2(fd->seg_len + f.sg_lo, fs * 2u);
+        prefetch_l2(fd->seq2 + f.q4_lo, fq);
+        prefetch_l2(fd->qual + (size_t)f.q4_lo * 4, fq * 4u);
+    }
+    for (int k = tid; k < 5 * TILE_QUADS; k += THREADS) s_cnt[k] = 0;
 
     // per letter and quad: 16-bit lanes, [0] = positions 0 and 2 of the quad, [1] = positions 1 and 3
     uint32_t acc[QUADS_PER_THREAD][5][2];
@@ -397,7 +420,12 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                 // staged quad g of this segment covers tile-relative quad g + w
                 s_seg[k] = make_uint4((uint32_t)p, len, d_qual + q * 4u + a, (uint32_t)((p - (int32_t)a - p0) >> 2) - q);
                 uint32_t e = q + nq; if (e > q_end) e = q_end;
-                for (uint32_t g = q; g < e; ++g) s_g2s[g] = (uint16_t)k;
+                {   // tag the segment's quads: bytes up to a word boundary, whole words, trailing bytes
+                    uint32_t g = q;
+                    for (; (g & 3u) && g < e; ++g) s_g2s[g] = (uint8_t)k;
+                    for (; g + 4u <= e; g += 4u) *reinterpret_cast<uint32_t*>(s_g2s + g) = k * 0x01010101u;
+                    for (; g < e; ++g) s_g2s[g] = (uint8_t)k;
+                }
                 q += nq;
             }
             if (q != q_end) {                                     // offsets and segments disagree: refuse, stay in bounds
@@ -424,7 +452,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
             // bytes -- a whole warp per pair wastes ~200 instructions on set-up, one thread per pair
             // serialises ~50 dependent read-modify-writes
             const uint32_t l8 = lane & 7u;
-            for (uint32_t t = tid >> 3; t < n_tasks; t += PILEUP_THREADS / 8) {
+            for (uint32_t t = tid >> 3; t < n_tasks; t += THREADS / 8) {
                 const uint32_t i = s_pairs[t];
                 const int32_t mt = s_mate[i];
                 const bool self_is_a = c0 + i < (uint32_t)mt;
@@ -439,16 +467,18 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                             const uint4 B = s_seg[kb];
                             const int32_t lo = max(max((int32_t)A.x, (int32_t)B.x), p0);
                             const int32_t hi = min(min((int32_t)(A.x + A.y), (int32_t)(B.x + B.y)), p0 + TILE);
-                            for (int32_t p = lo + (int32_t)l8; p < hi; p += 8) {
-                                const uint32_t za = A.z + (uint32_t)(p - (int32_t)A.x), zb = B.z + (uint32_t)(p - (int32_t)B.x);
-                                const uint32_t va = s_qual[za], vb = s_qual[zb];
-                                const uint32_t sh = ((uint32_t)p & 3u) * 2u;           // storage is position aligned
-                                const uint32_t ba = (s_seq[d_seq + ((za - d_qual) >> 2)] >> sh) & 3u;
-                                const uint32_t bb = (s_seq[d_seq + ((zb - d_qual) >> 2)] >> sh) & 3u;
-                                const bool same = ((va | vb) & 0x80u) ? ((va & vb & 0x80u) != 0) : (ba == bb);
+                            if (lo >= hi) continue;
+                            // four positions per lane and step: both mates are stored position-aligned, so the
+                            // quads of the common range line up word for word
+                            const uint32_t za0 = A.z - (A.x & 3u) - 4u * (A.x >> 2), zb0 = B.z - (B.x & 3u) - 4u * (B.x >> 2);
+                            for (int32_t P = (lo >> 2) + (int32_t)l8; P < ((hi + 3) >> 2); P += 8) {
+                                const uint32_t za = za0 + 4u * (uint32_t)P, zb = zb0 + 4u * (uint32_t)P;   // byte index of the quad in s_qual
+                                const uint32_t va = *reinterpret_cast<const uint32_t*>(s_qual + za), vb = *reinterpret_cast<const uint32_t*>(s_qual + zb);
+                                const uint32_t xa = msnv_spread_bases(s_seq[d_seq + ((za - d_qual) >> 2)]);
+                                const uint32_t xb = msnv_spread_bases(s_seq[d_seq + ((zb - d_qual) >> 2)]);
                                 uint32_t na, nb;
-                                overlap_rule(va, vb, same, na, nb);
-                                s_qual[za] = (uint8_t)na; s_qual[zb] = (uint8_t)nb;
+                                msnv_overlap_rule4(va, vb, xa, xb, msnv_quad_mask(P << 2, lo, hi), na, nb);
+                                *reinterpret_cast<uint32_t*>(s_qual + za) = na; *reinterpret_cast<uint32_t*>(s_qual + zb) = nb;
                             }
                         }
                     }
@@ -459,22 +489,22 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                     for (uint32_t ks = ms0; ks < ms1; ++ks) {
                         const int32_t bx = __ldg(sd->seg_pos + ks);
                         const uint32_t bl = __ldg(sd->seg_len + ks), ba0 = (uint32_t)bx & 3u;
-                        const uint8_t* mqual = sd->qual + (size_t)mq * 4 + ba0;      // quality of the segment's first base
+                        const uint32_t* mqual4 = reinterpret_cast<const uint32_t*>(sd->qual) + mq;   // the segment's first quad
                         const uint8_t* mseq = sd->seq2 + mq;
                         for (uint32_t ka = sa0; ka < sa1; ++ka) {
                             const uint4 A = s_seg[ka];
                             const int32_t lo = max(max((int32_t)A.x, bx), p0);
                             const int32_t hi = min(min((int32_t)(A.x + A.y), bx + (int32_t)bl), p0 + TILE);
-                            for (int32_t p = lo + (int32_t)l8; p < hi; p += 8) {
-                                const uint32_t zs = A.z + (uint32_t)(p - (int32_t)A.x), im = (uint32_t)(p - bx);
-                                const uint32_t vs = s_qual[zs], vm = mqual[im];
-                                const uint32_t sh = ((uint32_t)p & 3u) * 2u;
-                                const uint32_t bs = (s_seq[d_seq + ((zs - d_qual) >> 2)] >> sh) & 3u;
-                                const uint32_t bm = (mseq[(ba0 + im) >> 2] >> sh) & 3u;
-                                const bool same = ((vs | vm) & 0x80u) ? ((vs & vm & 0x80u) != 0) : (bs == bm);
+                            if (lo >= hi) continue;
+                            const uint32_t zs0 = A.z - (A.x & 3u) - 4u * (A.x >> 2);
+                            for (int32_t P = (lo >> 2) + (int32_t)l8; P < ((hi + 3) >> 2); P += 8) {
+                                const uint32_t zs = zs0 + 4u * (uint32_t)P, im = (uint32_t)(P - (bx >> 2));   // the mate's quad index
+                                const uint32_t vs = *reinterpret_cast<const uint32_t*>(s_qual + zs), vm = __ldg(mqual4 + im);
+                                const uint32_t xs = msnv_spread_bases(s_seq[d_seq + ((zs - d_qual) >> 2)]), xm = msnv_spread_bases(__ldg(mseq + im));
+                                const uint32_t msk = msnv_quad_mask(P << 2, lo, hi);
                                 uint32_t na, nb;
-                                if (self_is_a) overlap_rule(vs, vm, same, na, nb); else overlap_rule(vm, vs, same, nb, na);
-                                s_qual[zs] = (uint8_t)na;
+                                if (self_is_a) msnv_overlap_rule4(vs, vm, xs, xm, msk, na, nb); else msnv_overlap_rule4(vm, vs, xm, xs, msk, nb, na);
+                                *reinterpret_cast<uint32_t*>(s_qual + zs) = na;
                             }
                         }
                         mq += (ba0 + bl + 3u) >> 2;
@@ -489,10 +519,10 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
             const uint32_t a_q = smem_u32(s_qual) + d_qual;               // d_qual is a multiple of 4
             const uint32_t a_s = smem_u32(s_seq) + d_seq, a_g = smem_u32(s_g2s), a_w = smem_u32(s_seg) + 12u;
             const uint32_t a_c = smem_u32(s_cnt);
-            for (uint32_t g = tid; g < nq4; g += PILEUP_THREADS) {
+            for (uint32_t g = tid; g < nq4; g += THREADS) {
                 const uint32_t q = lds_u32(a_q + g * 4u);
                 uint32_t x = lds_u8(a_s + g);
-                const uint32_t j = lds_u32(a_w + lds_u16(a_g + g * 2u) * 16u) + g;     // tile-relative quad
+                const uint32_t j = lds_u32(a_w + lds_u8(a_g + g) * 16u) + g;           // tile-relative quad
                 if (j < (uint32_t)TILE_QUADS) {
                     x = (x * 4097u) & 0x000f000fu;                        // two 2-bit pairs per half word
                     x = (x * 65u) & 0x03030303u;                          // one base per byte lane
@@ -516,7 +546,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
         for (int k = 0; k < QUADS_PER_THREAD; ++k) {
             #pragma unroll
             for (int c = 0; c < 5; ++c) {
-                const uint32_t slot = c * TILE_QUADS + k * PILEUP_THREADS + tid;
+                const uint32_t slot = c * TILE_QUADS + k * THREADS + tid;
                 const uint32_t w = s_cnt[slot];
                 if (w) {
                     s_cnt[slot] = 0;
@@ -532,7 +562,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     // ---- 7. flush: 8 B + 2 B per position; a thread owns four consecutive positions
     #pragma unroll
     for (int k = 0; k < QUADS_PER_THREAD; ++k) {
-        const size_t o = (size_t)blockIdx.x * TILE + 4u * (k * PILEUP_THREADS + tid);
+        const size_t o = (size_t)blockIdx.x * TILE + 4u * (k * THREADS + tid);
         uint32_t w[4][2], nw[2];
         #pragma unroll
         for (int i = 0; i < 4; ++i) {

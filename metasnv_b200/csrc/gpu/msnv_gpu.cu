@@ -213,6 +213,37 @@ int msnv_device_count(void)
     return n;
 }
 
+// The instantiations of the pileup kernel: threads per CTA, reads staged per chunk, and the CTAs per SM the
+// register allocation aims at. Chosen per launch from the mean number of reads per (sample, tile) item;
+// MSNV_PILEUP_VARIANT=<index> overrides the choice (tuning hook, see tools/variant_sweep.py).
+#define MSNV_PILEUP_VARIANTS(X) \
+    X(0, 128, 127, 8) /* shallow: a tile's reads fill half a chunk or less */ \
+    X(1, 128, 127, 7) /* standard */ \
+    X(2, 256, 255, 5) /* deep: several chunks per tile */ \
+    X(3, 128, 127, 6) \
+    X(4, 256, 255, 4)
+constexpr int N_PILEUP_VARIANTS = 5, PILEUP_VARIANT_SHALLOW = 0, PILEUP_VARIANT_STANDARD = 1, PILEUP_VARIANT_DEEP = 2;
+
+static cudaError_t pileup_variant_prepare(int v)
+{
+    switch (v) {
+#define X(I, T, R, C) case I: return cudaFuncSetAttribute(pileup_kernel<T, R, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pileup_smem_bytes(R, CHUNK_Q4_MAX));
+        MSNV_PILEUP_VARIANTS(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+
+static void pileup_variant_launch(int v, uint32_t n_items, uint32_t chunk_q4, uint32_t pf_dist, cudaStream_t st, const SampleDev* samples,
+                                  const Item* items, uint64_t* acgt, uint16_t* ncnt, int* err)
+{
+    switch (v) {
+#define X(I, T, R, C) case I: pileup_kernel<T, R, C><<<n_items, T, pileup_smem_bytes(R, chunk_q4), st>>>(samples, items, n_items, chunk_q4, acgt, ncnt, err, pf_dist); break;
+        MSNV_PILEUP_VARIANTS(X)
+#undef X
+    }
+}
+
 int msnv_create(int device, msnv_ctx** out)
 {
     if (!out) return MSNV_E_ARG;
@@ -228,10 +259,7 @@ int msnv_create(int device, msnv_ctx** out)
     CU(cudaMalloc((void**)&ctx->d_scalar, 16));
     CU(cudaMalloc((void**)&ctx->d_err, 4));
     CU(cudaMallocHost((void**)&ctx->h_scalar, 16));
-    CU(cudaFuncSetAttribute(pileup_kernel<CHUNK_READS_SMALL, CHUNK_SEGS_SMALL, PILEUP_CTAS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)pileup_smem_bytes(CHUNK_READS_SMALL, CHUNK_SEGS_SMALL, CHUNK_Q4_MAX)));
-    CU(cudaFuncSetAttribute(pileup_kernel<CHUNK_READS_LARGE, CHUNK_SEGS_LARGE, PILEUP_CTAS_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)pileup_smem_bytes(CHUNK_READS_LARGE, CHUNK_SEGS_LARGE, CHUNK_Q4_MAX)));
+    for (int v = 0; v < N_PILEUP_VARIANTS; ++v) CU(pileup_variant_prepare(v));
     return MSNV_OK;
 }
 
@@ -413,23 +441,18 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
 
     // ---- pileup
     if (n_items) {
-        // staging buffers sized from the mean work per item (+25 %, at least one maximal read): smaller
+        // staging buffers sized from the mean work per item (+15 %, at least one maximal read): smaller
         // buffers let more CTAs share an SM; an item that does not fit simply takes another chunk
-        uint64_t mean_q4 = ctx->n_bases / 4 / n_items;
-        uint32_t chunk_q4 = (uint32_t)((mean_q4 * 3 / 2 + 255) / 256 * 256);
+        const uint64_t mean_q4 = ctx->n_bases / 4 / n_items, mean_reads = ctx->n_reads / n_items;
+        int variant = mean_reads > 160 ? PILEUP_VARIANT_DEEP : mean_reads <= 64 ? PILEUP_VARIANT_SHALLOW : PILEUP_VARIANT_STANDARD;
+        if (const char* e = getenv("MSNV_PILEUP_VARIANT"))
+            if (e[0] >= '0' && e[0] <= '9' && atoi(e) < N_PILEUP_VARIANTS) variant = atoi(e);
+        uint32_t chunk_q4 = variant == PILEUP_VARIANT_DEEP ? (uint32_t)CHUNK_Q4_MAX : (uint32_t)((mean_q4 * 23 / 20 + 255) / 256 * 256);
         if (const char* e = getenv("MSNV_CHUNK_Q4")) chunk_q4 = (uint32_t)atoi(e) / 256 * 256;
         if (chunk_q4 < (uint32_t)CHUNK_Q4_MIN) chunk_q4 = CHUNK_Q4_MIN;
         if (chunk_q4 > (uint32_t)CHUNK_Q4_MAX) chunk_q4 = CHUNK_Q4_MAX;
-        // shallow data (a tile's reads fit one small chunk): small buffers, 8 CTAs per SM; deep data: larger chunks
-        const uint64_t mean_reads = ctx->n_reads / n_items;
-        bool small = mean_reads * 2 <= (uint64_t)CHUNK_READS_SMALL;
-        if (const char* e = getenv("MSNV_PILEUP_VARIANT")) small = e[0] == 's';
-        if (small)
-            pileup_kernel<CHUNK_READS_SMALL, CHUNK_SEGS_SMALL, PILEUP_CTAS_SMALL><<<n_items, PILEUP_THREADS, pileup_smem_bytes(CHUNK_READS_SMALL, CHUNK_SEGS_SMALL, chunk_q4), st>>>(
-                ctx->d_samples, ctx->d_items, n_items, chunk_q4, ctx->d_acgt, ctx->d_ncnt, ctx->d_err);
-        else
-            pileup_kernel<CHUNK_READS_LARGE, CHUNK_SEGS_LARGE, PILEUP_CTAS_LARGE><<<n_items, PILEUP_THREADS, pileup_smem_bytes(CHUNK_READS_LARGE, CHUNK_SEGS_LARGE, chunk_q4), st>>>(
-                ctx->d_samples, ctx->d_items, n_items, chunk_q4, ctx->d_acgt, ctx->d_ncnt, ctx->d_err);
+        const uint32_t pf_dist = getenv("MSNV_PF_DIST") ? (uint32_t)atoi(getenv("MSNV_PF_DIST")) : PILEUP_PREFETCH_DISTANCE;
+        pileup_variant_launch(variant, n_items, chunk_q4, pf_dist, st, ctx->d_samples, ctx->d_items, ctx->d_acgt, ctx->d_ncnt, ctx->d_err);
         ++launches;
     }
     CU(cudaEventRecord(ctx->ev[3], st));

@@ -1,0 +1,42 @@
+#include <cstdio>
+#include <cstdlib>
+#include "overlap_rule.h"
+int main() {
+    long bad = 0;
+    // exhaustive per lane: every (va, vb, base a, base b), in every lane position, with the other lanes random
+    uint64_t rng = 88172645463325252ull;
+    auto rnd = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return (uint32_t)(rng >> 16); };
+    for (int lane = 0; lane < 4; ++lane)
+        for (uint32_t a = 0; a < 256; ++a)
+            for (uint32_t b = 0; b < 256; ++b)
+                for (uint32_t ba = 0; ba < 4; ++ba)
+                    for (uint32_t bb = 0; bb < 4; ++bb) {
+                        uint32_t va = rnd(), vb = rnd(), sa = rnd() & 0xff, sb = rnd() & 0xff, m = 0;
+                        for (int k = 0; k < 4; ++k) if (rnd() & 1) m |= 0xffu << (8 * k);
+                        m |= 0xffu << (8 * lane);
+                        va = (va & ~(0xffu << (8 * lane))) | a << (8 * lane);
+                        vb = (vb & ~(0xffu << (8 * lane))) | b << (8 * lane);
+                        sa = (sa & ~(3u << (2 * lane))) | ba << (2 * lane);
+                        sb = (sb & ~(3u << (2 * lane))) | bb << (2 * lane);
+                        uint32_t oa, ob;
+                        msnv_overlap_rule4(va, vb, msnv_spread_bases(sa), msnv_spread_bases(sb), m, oa, ob);
+                        for (int k = 0; k < 4; ++k) {
+                            uint32_t xa = (va >> (8 * k)) & 0xff, xb = (vb >> (8 * k)) & 0xff, ea = xa, eb = xb;
+                            if ((m >> (8 * k)) & 0xff) {
+                                uint32_t ca = (sa >> (2 * k)) & 3, cb = (sb >> (2 * k)) & 3;
+                                bool same = ((xa | xb) & 0x80u) ? ((xa & xb & 0x80u) != 0) : (ca == cb);
+                                msnv_overlap_rule(xa, xb, same, ea, eb);
+                            }
+                            if (((oa >> (8 * k)) & 0xff) != ea || ((ob >> (8 * k)) & 0xff) != eb) ++bad;
+                        }
+                    }
+    for (uint32_t q = 0; q < 256; ++q) if (msnv_q08(q) != (uint32_t)(0.8 * (double)q)) ++bad;
+    for (int p0 = 0; p0 < 16; p0 += 4) for (int lo = 0; lo < 20; ++lo) for (int hi = lo + 1; hi < 24; ++hi) {
+        if (hi <= p0 || lo >= p0 + 4) continue;
+        uint32_t m = msnv_quad_mask(p0, lo, hi), e = 0;
+        for (int k = 0; k < 4; ++k) if (p0 + k >= lo && p0 + k < hi) e |= 0xffu << (8 * k);
+        if (m != e) ++bad;
+    }
+    printf("mismatches: %ld\n", bad);
+    return bad != 0;
+}

@@ -107,3 +107,15 @@ def test_bam_roundtrip_product_writer_oracle_reader(built, tmp_path):
         total += int(m.group(1))
     assert total == st["reads"] + st["junk"] + st["unmapped"]
     assert H.bed_header(d, str(tmp_path / "bed")) and open(str(tmp_path / "bed")).read().count("\n") == 3
+
+
+def test_overlap_rule_four_lane_form_matches_scalar_rule(tmp_path):
+    """csrc/gpu/overlap_rule.h (host + device): the byte-lane form the pileup kernel uses equals the scalar
+    restatement of htslib's tweak_overlap_quality (SURVEY.md Annex A.2) for every (quality, quality, base, base)
+    in every lane, (q * 205) >> 8 equals (int)(0.8 * q) for every byte, and the quad masks are right.
+    The checker is tests/overlap_rule_check.cc (exhaustive, ~1 s)."""
+    exe = str(tmp_path / "overlap_rule_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "metasnv_b200", "csrc", "gpu"),
+                    os.path.join(ROOT, "tests", "overlap_rule_check.cc"), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "mismatches: 0" in r.stdout, r.stdout + r.stderr
