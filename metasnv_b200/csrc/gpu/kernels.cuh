@@ -44,9 +44,7 @@ struct SampleDev {
     uint32_t        n_reads, max_span;
 };
 
-// reads [r_lo, r_hi) of `sample` may overlap `tile`; q4_* / sg_* = q4_off / seg_off at r_lo and r_hi, which lets a
-// CTA prefetch a later item's data without first loading that item's offsets
-struct __align__(16) Item { uint32_t sample, tile, r_lo, r_hi, q4_lo, sg_lo, q4_hi, sg_hi; };
+struct Item { uint32_t sample, tile, r_lo, r_hi; };   // reads [r_lo, r_hi) of `sample` may overlap `tile`
 
 // Per-position population result of call_kernel.
 struct CallParamsDev { int32_t min_cov; int32_t thr; double frac; };
@@ -196,10 +194,7 @@ __global__ void __launch_bounds__(256) index_kernel(const SampleDev* __restrict_
         if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
     } else {
         const uint32_t slot = block_sums[blockIdx.x] + rank;     // block_sums holds exclusive offsets now
-        if (active) {
-            const uint32_t* qo = samples[s].q4_off; const uint32_t* so = samples[s].seg_off;
-            items[slot] = Item{s, t, r_lo, r_hi, __ldg(qo + r_lo), __ldg(so + r_lo), __ldg(qo + r_hi), __ldg(so + r_hi)};
-        }
+        if (active) items[slot] = Item{s, t, r_lo, r_hi};
         if (pair < n_pairs && s == 0) tile_begin[t] = slot;
     }
 }
@@ -211,7 +206,7 @@ __global__ void dense_items_kernel(uint32_t n_samples, uint32_t n_tiles, Item* _
     const uint64_t n = (uint64_t)n_samples * n_tiles;
     if (i < n) {
         const uint32_t t = (uint32_t)(i / n_samples), s = (uint32_t)(i - (uint64_t)t * n_samples);
-        items[i] = Item{s, t, 0u, 0u, 0u, 0u, 0u, 0u};
+        items[i] = Item{s, t, 0u, 0u};
         if (s == 0) tile_begin[t] = (uint32_t)i;
     }
     if (i == n) tile_begin[n_tiles] = (uint32_t)n;
@@ -279,8 +274,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ v, ui
 //      offsets are immediates. Padding bytes carry quality 0 and fail the threshold like any poor
 //      base.
 //   6. thread t folds the byte lanes of its quads into 16-bit lanes held in registers and clears them
-// The reads in HBM are never modified. Lane 0 of the last warp asks L2 for the first chunk of the
-// item PILEUP_PREFETCH_DISTANCE further on (the Item record carries the offsets that needs).
+// The reads in HBM are never modified.
 // What bounds the kernel is the length of this chain of short dependent steps, not HBM: CTAs are
 // kept small and the staging buffers are sized at launch from the mean work per item so that 7-8
 // CTAs per SM overlap each other's barriers and latencies.
@@ -309,24 +303,11 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volati
 template <int OFF>
 __device__ __forceinline__ void red_shared_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0+%2], %1;" :: "r"(a), "r"(v), "n"(OFF) : "memory"); }
 
-// L2 prefetch of [p, p + bytes): whole 16-byte units around the range (the arrays carry 32 spare bytes)
-__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes)
-{
-    const uintptr_t a = (uintptr_t)p & ~(uintptr_t)15;
-    const uint32_t n = (uint32_t)((uintptr_t)p - a + bytes + 15u) & ~15u;
-    if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a), "r"(n) : "memory");
-}
-
-// Items this far ahead of a CTA's own are prefetched into L2 by it (about two waves of resident CTAs):
-// a CTA's life is a chain of dependent loads (item -> offsets -> segment records / bases / qualities),
-// which then hit L2 instead of HBM.
-constexpr uint32_t PILEUP_PREFETCH_DISTANCE = 148 * 6 * 2;     // overridable: MSNV_PF_DIST (0 switches prefetching off)
-
 template <int THREADS, int CHUNK_READS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items, uint32_t chunk_q4,
               uint64_t* __restrict__ acgt /*[n_items][TILE]*/, uint16_t* __restrict__ ncnt /*[n_items][TILE]*/,
-              int* __restrict__ err_flag, uint32_t pf_dist)
+              int* __restrict__ err_flag)
 {
     static_assert(CHUNK_SEGS <= 256 && CHUNK_READS < THREADS && TILE_QUADS % THREADS == 0, "one thread per staged read; each thread folds whole quads");
     constexpr int QUADS_PER_THREAD = TILE_QUADS / THREADS;
@@ -350,21 +331,6 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     const SampleDev* __restrict__ sd = samples + it.sample;
 
     if (tid == 0) { mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    if (tid == THREADS - 32 && blockIdx.x + pf_dist < n_items && pf_dist) {
-        // the last warp is the one least needed for the first chunk's metadata: its lane 0 follows the chain
-        // of a later item and asks L2 for that item's first chunk
-        const Item f = items[blockIdx.x + pf_dist];
-        const SampleDev* __restrict__ fd = samples + f.sample;
-        uint32_t fn = f.r_hi - f.r_lo; if (fn > CHUNK_READS) fn = CHUNK_READS;
-        prefetch_l2(fd->q4_off + f.r_lo, (fn + 1) * 4u);
-        prefetch_l2(fd->seg_off + f.r_lo, (fn + 1) * 4u);
-        prefetch_l2(fd->mate + f.r_lo, fn * 4u);
-        const uint32_t fs = min(f.sg_hi - f.sg_lo, (uint32_t)CHUNK_SEGS), fq = min(f.q4_hi - f.q4_lo, chunk_q4);
-        prefetch_l2(fd->seg_pos + f.sg_lo, fs * 4u);
-        prefetch_l2(fd->seg_len + f.sg_lo, fs * 2u);
-        prefetch_l2(fd->seq2 + f.q4_lo, fq);
-        prefetch_l2(fd->qual + (size_t)f.q4_lo * 4, fq * 4u);
-    }
     for (int k = tid; k < 5 * TILE_QUADS; k += THREADS) s_cnt[k] = 0;
 
     // per letter and quad: 16-bit lanes, [0] = positions 0 and 2 of the quad, [1] = positions 1 and 3

@@ -234,11 +234,11 @@ static cudaError_t pileup_variant_prepare(int v)
     return cudaErrorInvalidValue;
 }
 
-static void pileup_variant_launch(int v, uint32_t n_items, uint32_t chunk_q4, uint32_t pf_dist, cudaStream_t st, const SampleDev* samples,
+static void pileup_variant_launch(int v, uint32_t n_items, uint32_t chunk_q4, cudaStream_t st, const SampleDev* samples,
                                   const Item* items, uint64_t* acgt, uint16_t* ncnt, int* err)
 {
     switch (v) {
-#define X(I, T, R, C) case I: pileup_kernel<T, R, C><<<n_items, T, pileup_smem_bytes(R, chunk_q4), st>>>(samples, items, n_items, chunk_q4, acgt, ncnt, err, pf_dist); break;
+#define X(I, T, R, C) case I: pileup_kernel<T, R, C><<<n_items, T, pileup_smem_bytes(R, chunk_q4), st>>>(samples, items, n_items, chunk_q4, acgt, ncnt, err); break;
         MSNV_PILEUP_VARIANTS(X)
 #undef X
     }
@@ -451,8 +451,7 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
         if (const char* e = getenv("MSNV_CHUNK_Q4")) chunk_q4 = (uint32_t)atoi(e) / 256 * 256;
         if (chunk_q4 < (uint32_t)CHUNK_Q4_MIN) chunk_q4 = CHUNK_Q4_MIN;
         if (chunk_q4 > (uint32_t)CHUNK_Q4_MAX) chunk_q4 = CHUNK_Q4_MAX;
-        const uint32_t pf_dist = getenv("MSNV_PF_DIST") ? (uint32_t)atoi(getenv("MSNV_PF_DIST")) : PILEUP_PREFETCH_DISTANCE;
-        pileup_variant_launch(variant, n_items, chunk_q4, pf_dist, st, ctx->d_samples, ctx->d_items, ctx->d_acgt, ctx->d_ncnt, ctx->d_err);
+        pileup_variant_launch(variant, n_items, chunk_q4, st, ctx->d_samples, ctx->d_items, ctx->d_acgt, ctx->d_ncnt, ctx->d_err);
         ++launches;
     }
     CU(cudaEventRecord(ctx->ev[3], st));

@@ -220,7 +220,7 @@ def test_empty_inputs(built, tmp_path):
         _same(o + ".indiv", g + ".indiv")
 
 
-@pytest.mark.parametrize("env", [{"MSNV_INDEX_BITMAP": "1"}, {"MSNV_INDEX_BITMAP": "0"}, {"MSNV_PILEUP_VARIANT": "0"}, {"MSNV_PILEUP_VARIANT": "1"}, {"MSNV_PILEUP_VARIANT": "2"}, {"MSNV_PF_DIST": "0"}, {"MSNV_PF_DIST": "3"},
+@pytest.mark.parametrize("env", [{"MSNV_INDEX_BITMAP": "1"}, {"MSNV_INDEX_BITMAP": "0"}, {"MSNV_PILEUP_VARIANT": "0"}, {"MSNV_PILEUP_VARIANT": "1"}, {"MSNV_PILEUP_VARIANT": "2"},
                                  {"MSNV_CHUNK_Q4": "1280"}], ids=lambda e: "-".join("%s=%s" % kv for kv in e.items()))
 def test_kernel_variants_give_identical_output(env, datasets, tmp_path):
     """Every launch-time choice of the library (occupancy bitmap for sparse shards, small/large chunk instantiation of

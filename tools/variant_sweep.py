@@ -7,7 +7,7 @@ from metasnv_b200 import abi, harness as H
 ap = argparse.ArgumentParser()
 ap.add_argument("--preset", default="c2"); ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--samples", type=int, default=0); ap.add_argument("--steps", type=int, default=3)
-ap.add_argument("--settings", default="default,0,1,2,3,4", help="comma list of <variant|default>[:chunk_q4[:prefetch distance]]")
+ap.add_argument("--settings", default="default,0,1,2,3,4", help="comma list of <variant|default>[:chunk_q4]")
 a = ap.parse_args()
 desc = H.describe(a.preset, a.scale, a.samples)
 ctx = abi.Context(0)
@@ -17,11 +17,8 @@ if first >= 0:
 ref_hits = None
 for setting in a.settings.split(","):
     v, _, q = setting.partition(":")
-    q, _, pf = q.partition(":")
-    for k in ("MSNV_PILEUP_VARIANT", "MSNV_CHUNK_Q4", "MSNV_PF_DIST"):
+    for k in ("MSNV_PILEUP_VARIANT", "MSNV_CHUNK_Q4"):
         os.environ.pop(k, None)
-    if pf:
-        os.environ["MSNV_PF_DIST"] = pf
     if v != "default":
         os.environ["MSNV_PILEUP_VARIANT"] = v
     if q:
