@@ -106,6 +106,18 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     }
 
     stage("reference and annotation loaded");
+    const int dev = pick_device(indiv_path);
+    msnv_ctx* ctx = nullptr;
+    if (dev < 0 || msnv_create(dev, &ctx) != MSNV_OK) {
+        fprintf(stderr, "snpCall: no usable CUDA device (%s); this build has no CPU calling path\n", msnv_last_error(ctx));
+        msnv_destroy(ctx);
+        return 1;
+    }
+    stage("CUDA context created");
+    if (msnv_shard_begin(ctx, S, layout.n_positions, ref.data()) != MSNV_OK) {
+        fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); msnv_destroy(ctx); return 1;
+    }
+
     // ---- decode all BAMs (one thread per file at a time), upload each as soon as it is ready
     int n_threads = (int)std::thread::hardware_concurrency();
     if (const char* e = getenv("MSNV_THREADS")) n_threads = atoi(e);
@@ -135,20 +147,6 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
                 done[s] = 1;
             }
         });
-    // creating the CUDA context takes about as long as decoding a small data set: do it while the decoders run
-    auto abort_decoders = [&]() { failed = true; for (auto& th : pool) th.join(); };
-    const int dev = pick_device(indiv_path);
-    msnv_ctx* ctx = nullptr;
-    if (dev < 0 || msnv_create(dev, &ctx) != MSNV_OK) {
-        fprintf(stderr, "snpCall: no usable CUDA device (%s); this build has no CPU calling path\n", msnv_last_error(ctx));
-        abort_decoders();
-        msnv_destroy(ctx);
-        return 1;
-    }
-    stage("CUDA context created");
-    if (msnv_shard_begin(ctx, S, layout.n_positions, ref.data()) != MSNV_OK) {
-        fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); abort_decoders(); msnv_destroy(ctx); return 1;
-    }
     // the context is single-threaded: uploads happen here, in sample order
     double t_h2d = 0; uint64_t h2d_bytes = 0;
     int rc = 0;
