@@ -109,6 +109,28 @@ HAND_SAM = [
     "u1\t4\t*\t0\t0\t*\t*\t0\t0\tACGT\tIIII",
 ]
 
+# CIGAR operations and shapes the synthetic model never produces: =/X, padding, hard + soft clips around indels,
+# zero-length operations, one-base segments, mates whose overlap contains an insertion and a deletion,
+# a reference skip inside a pair. Checked as per-position counts (tests/test_gpu_parity.py) against the
+# restatement's text, which is pinned here.
+HAND_OPS = [
+    "@HD\tVN:1.6\tSO:coordinate", "@SQ\tSN:ctgA\tLN:40", "@SQ\tSN:ctgB\tLN:40",
+    "x1\t0\tctgA\t1\t60\t5=1X4=\t*\t0\t0\tACGTAAGTAC\tIIIIIIIIII",
+    "x2\t0\tctgA\t2\t60\t3M1P1I3M\t*\t0\t0\tCGTTACG\tIIIIIII",
+    "x3\t16\tctgA\t3\t60\t2H2S3M1I2M1D3M2S\t*\t0\t0\tTTGTATCGACGGG\tIIIIIIIIIIIII",
+    "x4\t0\tctgA\t4\t60\t4M0I4M\t*\t0\t0\tTACGTACG\tIIIIIIII",
+    "q1\t99\tctgA\t8\t60\t4M2D6M\t=\t12\t14\tTACGCGTNCG\tIIIIIIIIII",
+    "q1\t147\tctgA\t12\t60\t3M1I6M\t=\t8\t-14\tACGTTNCGAA\t5555555555",
+    "q2\t99\tctgA\t20\t60\t10M\t=\t22\t10\tACGTACGTAC\t((((((((((",
+    "q2\t147\tctgA\t22\t60\t2S8M\t=\t20\t-10\tGGGTTCGTAC\tIIIIIIIIII",
+    "q3\t99\tctgA\t26\t60\t3M3N3M\t=\t30\t10\tGTAGTA\tIIIIII",
+    "q3\t147\tctgA\t30\t60\t6M\t=\t26\t-10\tCCTACG\tIIIIII",
+    "x6\t0\tctgA\t33\t60\t2=2X2=\t*\t0\t0\tACAAAC\tIIIIII",
+    "y1\t0\tctgB\t1\t60\t10M\t*\t0\t0\tTTTTTTTTTA\tIIIIIIIIII",
+    "y2\t16\tctgB\t5\t60\t1M1I1M1I1M1D1M1I1M\t*\t0\t0\tTATCTGGAG\tIIIIIIIII",
+    "y3\t0\tctgB\t31\t60\t10M\t*\t0\t0\tAAAAACAAAA\tIIIIIIIIII",
+]
+
 
 def hand_case(work):
     d = os.path.join(HERE, "hand")
@@ -120,8 +142,13 @@ def hand_case(work):
     open(os.path.join(d, "s1.sam"), "w").write("\n".join(l for l in HAND_SAM if not l.startswith("s4\t")) + "\n")
     open(os.path.join(d, "s2.sam"), "w").write("\n".join(l for l in HAND_SAM if l[0] == "@" or l[0] in "su" and not l.startswith("s4\t")) + "\n")
     open(os.path.join(d, "s3_refskip.sam"), "w").write("\n".join(HAND_SAM) + "\n")
-    for s in ("s1", "s2", "s3_refskip"):
+    open(os.path.join(d, "s4_ops.sam"), "w").write("\n".join(HAND_OPS) + "\n")
+    for s in ("s1", "s2", "s3_refskip", "s4_ops"):
         subprocess.run([bin_path("msnv_synth"), "--sam", os.path.join(d, s + ".sam"), "--bam", os.path.join(work, s + ".bam")], check=True)
+    lst4 = os.path.join(work, "hand_list4")
+    open(lst4, "w").write("%s\n%s\n" % (os.path.join(work, "s4_ops.bam"), os.path.join(work, "s1.bam")))
+    txt4 = subprocess.check_output([H.oracle_bin("mpileup_oracle"), "mpileup", "-f", os.path.join(d, "ref.fa"), "-B", "-b", lst4])
+    open(os.path.join(d, "expected_ops.pileup"), "wb").write(txt4)
     lst = os.path.join(work, "hand_list")
     open(lst, "w").write("%s\n%s\n" % (os.path.join(work, "s1.bam"), os.path.join(work, "s2.bam")))
     txt = subprocess.check_output([H.oracle_bin("mpileup_oracle"), "mpileup", "-f", os.path.join(d, "ref.fa"), "-B", "-b", lst])

@@ -198,6 +198,31 @@ def test_pileup_counts_match_oracle_text(preset, scale, samples, datasets, tmp_p
     assert int(got.sum()) > 0
 
 
+def test_exotic_cigar_operations_counts_match_pinned_oracle_text(built, tmp_path):
+    """tests/golden/hand/s4_ops.sam: =/X, padding, hard and soft clips around indels, zero-length operations,
+    one-base segments, mates whose overlap contains an insertion and a deletion, a reference skip inside a pair.
+    The device counts of every position must equal the counts of the restatement's (pinned) pileup text."""
+    tmp = str(tmp_path)
+    bams = []
+    for s in ("s4_ops", "s1"):
+        out = os.path.join(tmp, s + ".bam")
+        subprocess.run([bin_path("msnv_synth"), "--sam", os.path.join(GOLDEN, "hand", s + ".sam"), "--bam", out], check=True)
+        bams.append(out)
+    open(os.path.join(tmp, "all_samples"), "w").write("\n".join(bams) + "\n")
+    os.symlink(os.path.join(GOLDEN, "hand", "ref.fa"), os.path.join(tmp, "ref.fa"))
+    dump = os.path.join(tmp, "counts.bin")
+    rc, err = H.run_product_snpcall(tmp, os.path.join(tmp, "gpu"), c=2, t=2, env=dict(os.environ, MSNV_DUMP_COUNTS=dump))
+    assert rc == 0, err
+    lay = [l.rstrip("\n").split("\t") for l in open(dump + ".layout")]
+    S, P = int(lay[0][0]), int(lay[0][1])
+    layout = [(n, int(o), int(l)) for n, o, l in lay[1:]]
+    got = np.fromfile(dump, np.uint16).reshape(S, P, 5)
+    want = _oracle_counts(os.path.join(GOLDEN, "hand", "expected_ops.pileup"), S, layout, P)
+    bad = np.argwhere(want != got)
+    assert bad.size == 0, "first mismatch (sample,pos,channel)=%s want %s got %s" % (bad[0], want[tuple(bad[0])], got[tuple(bad[0])])
+    assert int(got[0].sum()) > 60
+
+
 def test_empty_inputs(built, tmp_path):
     """BAMs with a header but no reads, alone and next to a populated one."""
     d = str(tmp_path)

@@ -75,6 +75,14 @@ def test_mpileup_restatement_hand_case(built, tmp_path):
     assert lines[16].startswith("ctgA\t17\tN\t1\t.\t]\t")                # N read base matches N reference; disagreeing pair p2 keeps 0.8*10 < 13
     assert lines[23].startswith("ctgA\t24\tT\t0\t*\t*\t")                # covered only by a filtered base: line with depth 0
     assert lines[40].startswith("ctgB\t6\tT\t3\tAAa\tIII\t3\tAAa\tIII")  # strand case of mismatches
+    # exotic CIGAR operations (=, X, P, H+S around indels, zero-length, one-base segments, indels inside a mate overlap)
+    lst4 = os.path.join(tmp, "list4")
+    open(lst4, "w").write("%s\n%s\n" % (_bam_from_sam("s4_ops", tmp), _bam_from_sam("s1", tmp)))
+    txt4 = subprocess.check_output([H.oracle_bin("mpileup_oracle"), "mpileup", "-f", ref, "-B", "-b", lst4])
+    assert txt4 == open(os.path.join(GOLDEN, "hand", "expected_ops.pileup"), "rb").read()
+    l4 = txt4.decode().split("\n")
+    assert l4[5].startswith("ctgA\t6\tC\t4\tA.,.\t")                  # the X of 5=1X4= is a mismatch like any other
+    assert l4[11].startswith("ctgA\t12\tt\t2\t*^]a\tA5\t")             # q1's deletion meets its mate's first base: no overlap rule on '*'
     # N operations render '>' / '<'
     lst3 = os.path.join(tmp, "list3")
     open(lst3, "w").write("%s\n" % _bam_from_sam("s3_refskip", tmp))
