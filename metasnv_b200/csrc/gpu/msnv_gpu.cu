@@ -24,8 +24,12 @@ struct msnv_ctx {
     bool open = false, has_run = false;
     uint32_t S = 0, P = 0, n_tiles = 0;
     std::vector<SampleDev> h_samples;
-    std::vector<std::pair<void*, size_t>> sample_allocs;   // device blocks of the open shard
-    std::vector<std::pair<void*, size_t>> pool;            // blocks of the previous shard, reused by the next one
+    struct Block { void* p; size_t bytes; bool in_slab; };
+    struct Slab { uint8_t* base; size_t size, used; };
+    std::vector<Block> sample_allocs;   // device blocks of the open shard
+    std::vector<Block> pool;            // blocks of the previous shard, reused by the next one
+    std::vector<Slab> slabs;            // small blocks are carved out of large allocations
+    size_t slab_live = 0;               // carved blocks in sample_allocs + pool
     std::vector<msnv_sample_sizes> sizes;      // [S]
     uint64_t n_reads = 0, n_bases = 0;
     SampleDev* d_samples = nullptr;
@@ -81,9 +85,20 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Blocks of a finished shard go to a pool: the next shard (e.g. the next genome bin of the same
 // sample set) reuses them instead of paying cudaFree (a device-wide sync) and cudaMalloc per sample.
+// Blocks below SLAB_BYTES / 4 are carved out of SLAB_BYTES allocations: a job with hundreds of small
+// samples would otherwise make hundreds of cudaMalloc calls while the decoder threads fault pages in,
+// and the two contend for the process's address-space lock (measured: 0.7 s vs 3.4 s for 400 samples).
+constexpr size_t SLAB_BYTES = 256u << 20;
+
+void release_block(msnv_ctx* ctx, const msnv_ctx::Block& b)
+{
+    if (!b.in_slab) { cudaFree(b.p); return; }
+    if (--ctx->slab_live == 0) for (auto& sl : ctx->slabs) sl.used = 0;      // nothing carved is alive: start over
+}
+
 void free_samples(msnv_ctx* ctx)
 {
-    for (auto& b : ctx->pool) cudaFree(b.first);
+    for (auto& b : ctx->pool) release_block(ctx, b);
     ctx->pool.swap(ctx->sample_allocs);
     ctx->sample_allocs.clear();
 }
@@ -92,21 +107,37 @@ void* take_block(msnv_ctx* ctx, size_t bytes)
 {
     size_t best = (size_t)-1, bi = 0;
     for (size_t i = 0; i < ctx->pool.size(); ++i)
-        if (ctx->pool[i].second >= bytes && ctx->pool[i].second < best) { best = ctx->pool[i].second; bi = i; }
-    void* p = nullptr;
+        if (ctx->pool[i].bytes >= bytes && ctx->pool[i].bytes < best) { best = ctx->pool[i].bytes; bi = i; }
     if (best != (size_t)-1 && best <= bytes + bytes / 4 + (1u << 20)) {
-        p = ctx->pool[bi].first;
+        void* p = ctx->pool[bi].p;
         ctx->sample_allocs.push_back(ctx->pool[bi]);
         ctx->pool[bi] = ctx->pool.back(); ctx->pool.pop_back();
         return p;
     }
+    if (bytes <= SLAB_BYTES / 4) {
+        const size_t need = align_up(bytes, 256);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            for (auto& sl : ctx->slabs)
+                if (sl.size - sl.used >= need) {
+                    void* p = sl.base + sl.used;
+                    sl.used += need;
+                    ++ctx->slab_live;
+                    ctx->sample_allocs.push_back({p, bytes, true});
+                    return p;
+                }
+            void* base = nullptr;
+            if (attempt || cudaMalloc(&base, SLAB_BYTES) != cudaSuccess) { cudaGetLastError(); break; }   // fall through to a plain block
+            ctx->slabs.push_back({(uint8_t*)base, SLAB_BYTES, 0});
+        }
+    }
+    void* p = nullptr;
     if (cudaMalloc(&p, bytes) != cudaSuccess) {
         cudaGetLastError();
-        for (auto& b : ctx->pool) cudaFree(b.first);         // give the pool back and retry once
+        for (auto& b : ctx->pool) release_block(ctx, b);     // give the pool back and retry once
         ctx->pool.clear();
         if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     }
-    ctx->sample_allocs.push_back({p, bytes});
+    ctx->sample_allocs.push_back({p, bytes, false});
     return p;
 }
 
@@ -270,6 +301,7 @@ void msnv_destroy(msnv_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_samples(ctx);
     free_samples(ctx);                              // second call empties the pool as well
+    for (auto& sl : ctx->slabs) cudaFree(sl.base);
     cudaFree(ctx->d_samples); cudaFree(ctx->d_ref);
     cudaFree(ctx->d_items); cudaFree(ctx->d_acgt); cudaFree(ctx->d_ncnt);
     cudaFree(ctx->d_tile_begin); cudaFree(ctx->d_tile_hits); cudaFree(ctx->d_flags); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_range_cache); cudaFree(ctx->d_bitmap);
