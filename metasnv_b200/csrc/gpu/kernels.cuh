@@ -101,6 +101,36 @@ __device__ __forceinline__ uint32_t lower_bound_i32(const int32_t* __restrict__ 
     return lo;
 }
 
+// lower_bound_i32 when the answer is expected near `guess`: gallop away from the guess in doubling steps,
+// then bisect the bracket. A good guess costs ~8 probes that share one or two cache lines instead of
+// log2(n) scattered ones; a bad one costs 2*log2(error).
+__device__ __forceinline__ uint32_t lower_bound_near_i32(const int32_t* __restrict__ a, uint32_t n, int64_t key, uint32_t guess)
+{
+    uint32_t lo, hi, cur = guess < n ? guess : n, step = 16;
+    if (cur < n && (int64_t)__ldg(a + cur) < key) {            // the answer lies above the guess
+        lo = cur + 1;
+        for (;;) {
+            const uint32_t c = cur + step;
+            if (c >= n) { hi = n; break; }
+            if ((int64_t)__ldg(a + c) >= key) { hi = c; break; }
+            lo = c + 1; cur = c; step <<= 1;
+        }
+    } else {                                                   // at or below it
+        hi = cur;
+        for (;;) {
+            if (cur < step) { lo = 0; break; }
+            const uint32_t c = cur - step;
+            if ((int64_t)__ldg(a + c) < key) { lo = c + 1; break; }
+            hi = c; cur = c; step <<= 1;
+        }
+    }
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((int64_t)__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 // Block-wide exclusive rank of `flag` among the block's threads (thread order) and the block total.
 // blockDim.x must be a multiple of 32 and at most 1024.
 __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t* s_warp /*[33]*/, uint32_t& total)
@@ -180,9 +210,19 @@ __global__ void __launch_bounds__(256) index_kernel(const SampleDev* __restrict_
             }
             if (maybe) {
                 const int32_t* pos = samples[s].pos;
-                const int64_t t0 = (int64_t)t * TILE;
-                r_lo = lower_bound_i32(pos, n, t0 - (int64_t)samples[s].max_span + 1);
-                r_hi = lower_bound_i32(pos, n, t0 + TILE);
+                const int64_t t0 = (int64_t)t * TILE, k_lo = t0 - (int64_t)samples[s].max_span + 1;
+                if (bitmap) {
+                    // sparse shard: the sample covers a few contigs of many, its read density is anything but even
+                    r_lo = lower_bound_i32(pos, n, k_lo);
+                    r_hi = lower_bound_near_i32(pos, n, t0 + TILE, r_lo + 32);          // ... but the end is close to the start
+                } else {
+                    // reads are spread fairly evenly over what the sample covers: interpolate, then search near the guess
+                    const int64_t first = __ldg(pos), extent = (int64_t)__ldg(pos + n - 1) - first + 1;
+                    const int64_t g = k_lo <= first ? 0 : (k_lo - first) * (int64_t)n / extent;
+                    r_lo = lower_bound_near_i32(pos, n, k_lo, (uint32_t)(g < (int64_t)n ? g : (int64_t)n));
+                    const int64_t w = ((int64_t)TILE + samples[s].max_span) * (int64_t)n / extent;
+                    r_hi = lower_bound_near_i32(pos, n, t0 + TILE, r_lo + (uint32_t)(w < (int64_t)n ? w : (int64_t)n));
+                }
             }
             if (!EMIT && range_cache) range_cache[pair] = make_uint2(r_lo, r_hi);
         }
