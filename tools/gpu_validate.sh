@@ -1,5 +1,6 @@
 #!/bin/bash
-# final validation + measurement of the round
+# One gpurun session that validates and measures the whole path (what the round-end numbers in profiles/ come from):
+#   /usr/local/graft/bin/gpurun --timeout 2300 -- "bash tools/gpu_validate.sh"
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -n 4 gpurun_out/pytest_gpu.log
