@@ -303,16 +303,17 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ v, ui
 //   1. offsets and mates of the chunk's reads -> shared memory; __syncthreads_count sizes the chunk
 //   2. two TMA bulk copies (2-bit bases, qualities) are issued; while they fly,
 //   3. one thread per read loads its segment records, derives for every segment where its quads
-//      lie in the staging buffer and on the tile, and tags those quads with the segment's index
-//      (word-wide stores)
+//      lie in the staging buffer and on the tile, and tags every quad with (the low byte of) its
+//      tile-relative index, four tags per store; after the copies have landed the same threads zero
+//      the qualities of the few quads that lie off the tile
 //   4. mate-overlap quality correction in shared memory (overlap_rule.h), eight lanes per pair, a
 //      quad of both mates per lane and step (mates staged in another chunk are read, pristine,
 //      from global memory)
 //   5. flat scatter: thread g takes the g-th staged quad: quality test and base decoding for the
 //      four positions at once, then ONE shared-memory atomic per base letter. Plane X of the
 //      counters holds, per quad of the tile, a word with one byte lane per position; the plane
-//      offsets are immediates. Padding bytes carry quality 0 and fail the threshold like any poor
-//      base.
+//      offsets are immediates. Padding bytes and quads off the tile carry quality 0 and fail the
+//      threshold like any poor base: the loop has no bounds test and no table look-up.
 //   6. thread t folds the byte lanes of its quads into 16-bit lanes held in registers and clears them
 // The reads in HBM are never modified.
 // What bounds the kernel is the length of this chain of short dependent steps, not HBM: CTAs are
@@ -322,11 +323,11 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ v, ui
 // Shared memory (dynamic), regions 16-byte aligned:
 //   s_meta   3 x META_STRIDE u32      q4_off | seg_off | mate of the chunk's reads
 //   s_seg    CHUNK_SEGS x 16 bytes    {first position, length, byte index of its first quality,
-//                                      tile-relative quad index of staged quad 0 as seen from this segment}
+//                                      tile-relative index of its first quad}
 //   s_cnt    5 x TILE bytes           planes A, C, G, T, non-ACGT: one byte per position
 //   s_seq    chunk_q4 + 32 bytes      2-bit bases           (TMA destination)
 //   s_qual   4*chunk_q4 + 32 bytes    qualities             (TMA destination)
-//   s_g2s    chunk_q4 bytes           segment of every staged quad
+//   s_g2s    chunk_q4 bytes           tile-relative index of every staged quad (low byte)
 // ------------------------------------------------------------------------------------------------
 constexpr int TILE_QUADS = TILE / 4;
 
@@ -349,7 +350,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
               uint64_t* __restrict__ acgt /*[n_items][TILE]*/, uint16_t* __restrict__ ncnt /*[n_items][TILE]*/,
               int* __restrict__ err_flag)
 {
-    static_assert(CHUNK_SEGS <= 256 && CHUNK_READS < THREADS && TILE_QUADS % THREADS == 0, "one thread per staged read; each thread folds whole quads");
+    static_assert(TILE_QUADS == 256 && CHUNK_READS < THREADS && TILE_QUADS % THREADS == 0, "one thread per staged read; each thread folds whole quads");
     constexpr int QUADS_PER_THREAD = TILE_QUADS / THREADS;
     constexpr int META_STRIDE = (CHUNK_READS + 4) / 4 * 4;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -423,14 +424,22 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                 const int32_t p = __ldg(sd->seg_pos + sg_0 + k);
                 const uint32_t len = __ldg(sd->seg_len + sg_0 + k);
                 const uint32_t a = (uint32_t)p & 3u, nq = (a + len + 3u) >> 2;
-                // staged quad g of this segment covers tile-relative quad g + w
-                s_seg[k] = make_uint4((uint32_t)p, len, d_qual + q * 4u + a, (uint32_t)((p - (int32_t)a - p0) >> 2) - q);
+                const int32_t jw = (p - (int32_t)a - p0) >> 2;    // tile-relative index of the segment's first quad (may be off the tile)
+                // (a segment whose quads run past the read's - inconsistent input, flagged below - gets length 0,
+                // which keeps it out of the overlap step and of the zeroing in step 4a)
+                s_seg[k] = make_uint4((uint32_t)p, q + nq <= q_end ? len : 0u, d_qual + q * 4u + a, (uint32_t)jw);
                 uint32_t e = q + nq; if (e > q_end) e = q_end;
-                {   // tag the segment's quads: bytes up to a word boundary, whole words, trailing bytes
-                    uint32_t g = q;
-                    for (; (g & 3u) && g < e; ++g) s_g2s[g] = (uint8_t)k;
-                    for (; g + 4u <= e; g += 4u) *reinterpret_cast<uint32_t*>(s_g2s + g) = k * 0x01010101u;
-                    for (; g < e; ++g) s_g2s[g] = (uint8_t)k;
+                {   // tag every quad with the low byte of its tile-relative index (TILE_QUADS == 256: a quad ON the tile
+                    // is tagged exactly; quads off the tile get their qualities zeroed in step 4 and may carry any tag):
+                    // bytes up to a word boundary, whole words of four consecutive tags, trailing bytes
+                    uint32_t g = q, t = (uint32_t)jw;
+                    for (; (g & 3u) && g < e; ++g, ++t) s_g2s[g] = (uint8_t)t;
+                    for (; g + 4u <= e; g += 4u, t += 4u) {
+                        const uint32_t t0 = t & 0xffu;
+                        if (t0 <= 252u) *reinterpret_cast<uint32_t*>(s_g2s + g) = t0 * 0x01010101u + 0x03020100u;
+                        else { s_g2s[g] = (uint8_t)t; s_g2s[g + 1] = (uint8_t)(t + 1); s_g2s[g + 2] = (uint8_t)(t + 2); s_g2s[g + 3] = (uint8_t)(t + 3); }
+                    }
+                    for (; g < e; ++g, ++t) s_g2s[g] = (uint8_t)t;
                 }
                 q += nq;
             }
@@ -447,6 +456,24 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
         if (tid == 0) mbar_wait(s_bar, parity);
         parity ^= 1;
         __syncthreads();                    // segments written, copies landed (thread 0 observed the barrier)
+
+        // ---- 4a. quads off the tile (front of reads that start before it, tail of reads that run past it) must not
+        // count: their qualities are zeroed, which the scatter's threshold test then rejects like any poor base
+        if (tid < m) {
+            const uint32_t k0 = s_sgo[tid] - sg_0, k1 = s_sgo[tid + 1] - sg_0;
+            for (uint32_t k = k0; k < k1; ++k) {
+                const uint4 sg = s_seg[k];
+                if (!sg.y) continue;
+                const int32_t jw = (int32_t)sg.w;
+                const uint32_t a = sg.x & 3u;
+                const int32_t nq = (int32_t)((a + sg.y + 3u) >> 2);
+                if (jw >= 0 && jw + nq <= TILE_QUADS) continue;                    // wholly on the tile: the common case
+                uint32_t* qw = reinterpret_cast<uint32_t*>(s_qual + (sg.z - a));    // the segment's first quad
+                const int32_t lead = min(max(-jw, 0), nq), tail = min(max(TILE_QUADS - jw, 0), nq);
+                for (int32_t i = 0; i < lead; ++i) qw[i] = 0;
+                for (int32_t i = tail; i < nq; ++i) qw[i] = 0;
+            }
+        }
 
         // ---- 4. mate-overlap quality correction, restricted to this tile's positions (other tiles
         // are counted by other CTAs). Pairs with both mates in the chunk: both are rewritten from
@@ -517,32 +544,30 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                     }
                 }
             }
-            __syncthreads();
         }
+        __syncthreads();                    // qualities are final (steps 4a and 4 wrote disjoint quads)
 
         // ---- 5. flat scatter over the staged quads
         {
             const uint32_t a_q = smem_u32(s_qual) + d_qual;               // d_qual is a multiple of 4
-            const uint32_t a_s = smem_u32(s_seq) + d_seq, a_g = smem_u32(s_g2s), a_w = smem_u32(s_seg) + 12u;
+            const uint32_t a_s = smem_u32(s_seq) + d_seq, a_g = smem_u32(s_g2s);
             const uint32_t a_c = smem_u32(s_cnt);
             for (uint32_t g = tid; g < nq4; g += THREADS) {
                 const uint32_t q = lds_u32(a_q + g * 4u);
                 uint32_t x = lds_u8(a_s + g);
-                const uint32_t j = lds_u32(a_w + lds_u8(a_g + g) * 16u) + g;           // tile-relative quad
-                if (j < (uint32_t)TILE_QUADS) {
-                    x = (x * 4097u) & 0x000f000fu;                        // two 2-bit pairs per half word
-                    x = (x * 65u) & 0x03030303u;                          // one base per byte lane
-                    const uint32_t v = (q & 0x7f7f7f7fu) + 0x73737373u;   // bit 7 of a lane: quality >= 13
-                    const uint32_t ok = ((v & ~q) >> 7) & 0x01010101u;    // ... and the base is A/C/G/T
-                    const uint32_t hi = x >> 1;
-                    const uint32_t a = a_c + j * 4u;
-                    red_shared_add<0>(a, ok & ~x & ~hi);
-                    red_shared_add<TILE>(a, ok & x & ~hi);
-                    red_shared_add<2 * TILE>(a, ok & ~x & hi);
-                    red_shared_add<3 * TILE>(a, ok & x & hi);
-                    const uint32_t nn = v & q & 0x80808080u;              // rare: counted non-ACGT bases
-                    if (nn) red_shared_add<4 * TILE>(a, nn >> 7);
-                }
+                const uint32_t j = lds_u8(a_g + g);                           // tile-relative quad
+                x = (x * 4097u) & 0x000f000fu;                                // two 2-bit pairs per half word
+                x = (x * 65u) & 0x03030303u;                                  // one base per byte lane
+                const uint32_t v = (q & 0x7f7f7f7fu) + 0x73737373u;           // bit 7 of a lane: quality >= 13
+                const uint32_t ok = ((v & ~q) >> 7) & 0x01010101u;            // ... and the base is A/C/G/T
+                const uint32_t hi = x >> 1;
+                const uint32_t a = a_c + j * 4u;
+                red_shared_add<0>(a, ok & ~x & ~hi);
+                red_shared_add<TILE>(a, ok & x & ~hi);
+                red_shared_add<2 * TILE>(a, ok & ~x & hi);
+                red_shared_add<3 * TILE>(a, ok & x & hi);
+                const uint32_t nn = v & q & 0x80808080u;                      // rare: counted non-ACGT bases
+                if (nn) red_shared_add<4 * TILE>(a, nn >> 7);
             }
         }
         __syncthreads();
