@@ -83,14 +83,6 @@ __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// 1 << s for 64-bit with PTX clamping semantics (s >= 64 gives 0)
-__device__ __forceinline__ uint64_t shl1_clamped(uint32_t s)
-{
-    uint64_t r;
-    asm("shl.b64 %0, 1, %1;" : "=l"(r) : "r"(s));
-    return r;
-}
-
 __device__ __forceinline__ uint32_t lower_bound_i32(const int32_t* __restrict__ a, uint32_t n, int64_t key)
 {
     uint32_t lo = 0, hi = n;
