@@ -3,10 +3,13 @@ oracle/_ref/metaSNV) drives the product binaries exactly as it drives its own: q
 createOptimumSplit, one `samtools mpileup | snpCall` pipe per split. Every file of the project directory must be
 byte-identical to the run with the oracle's binaries."""
 import os
+import subprocess
+import sys
 
 import pytest
 
 from metasnv_b200 import harness as H
+from metasnv_b200.paths import bin_path
 
 pytestmark = pytest.mark.gpu
 
@@ -40,3 +43,21 @@ def test_metasnv_py_drives_the_gpu_path(threads, splits, ann, built, tmp_path):
         if rel.startswith("snpCaller/called_SNPs"):
             n_lines += sum(1 for _ in open(outs["gpu"][rel]))
     assert n_lines > 0
+    # Part II's first step on both trees: the reference's metaSNV_Filtering.py on the oracle tree, the product's
+    # bin/metaSNV_Filtering on the GPU tree -> identical filtered/pop/*.freq
+    ref_filter = os.path.join(H.ORACLE_BIN, "metaSNV", "metaSNV_Filtering.py")
+    if os.path.exists(ref_filter):
+        a, b = str(tmp_path / "proj_oracle"), str(tmp_path / "proj_gpu")
+        # same project name for both (it is part of the coverage table names)
+        os.rename(a, str(tmp_path / "proj"))
+        r1 = subprocess.run([sys.executable, ref_filter, str(tmp_path / "proj"), "-m", "2"], capture_output=True, text=True)
+        assert r1.returncode == 0, r1.stderr
+        os.rename(str(tmp_path / "proj"), a)
+        os.rename(b, str(tmp_path / "proj"))
+        r2 = subprocess.run([bin_path("metaSNV_Filtering"), str(tmp_path / "proj"), "-m", "2"], capture_output=True, text=True)
+        assert r2.returncode == 0, r2.stderr
+        os.rename(str(tmp_path / "proj"), b)
+        fa, fb = H.tree_files(os.path.join(a, "filtered")), H.tree_files(os.path.join(b, "filtered"))
+        assert sorted(fa) == sorted(fb) and len(fa) > 0
+        for rel in fa:
+            assert not H.first_diff(fa[rel], fb[rel]), rel
