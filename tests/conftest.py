@@ -50,3 +50,20 @@ def snpcall_checkers(built):
 
 def run(cmd, **kw):
     return subprocess.run(cmd, capture_output=True, **kw)
+
+
+@pytest.fixture(scope="module")
+def datasets(built, tmp_path_factory):
+    """Seeded synthetic BAM sets (bin/msnv_synth), generated once per test module and configuration."""
+    from metasnv_b200 import harness as H
+    cache = {}
+    base = str(tmp_path_factory.mktemp("data"))
+
+    def get(preset, scale, samples, **kw):
+        key = (preset, scale, samples, tuple(sorted(kw.items())))
+        if key not in cache:
+            d = os.path.join(base, "%s_%d" % (preset, len(cache)))
+            H.synth(d, preset, scale, samples, **kw)
+            cache[key] = d
+        return cache[key]
+    return get

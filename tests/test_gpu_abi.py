@@ -152,3 +152,49 @@ def test_device_synth_equals_bam_pipeline(preset, scale, samples, built, tmp_pat
     for a in ("pos", "pop_mask", "ind_mask", "cov", "allele", "total"):
         assert np.array_equal(getattr(h, a), getattr(h2, a)), a
         assert np.array_equal(getattr(h, a), getattr(h3, a)), a
+
+
+def test_full_size_shard_counts_recount_with_numpy(built):
+    """BASELINE.json's headline shape at FULL size (5 Mb genome, 1000 samples at ~10x: 5e8 reads, 125 GB resident):
+    the oracle cannot run at this size, so the device counts of whole samples are checked against the independent
+    numpy recount of the same batches (tests/pileup_counts.py, itself pinned to the oracle on the CPU in
+    tests/test_decode_cpu.py): one sample without overlapping mates, one with; plus size-independent properties:
+    a second run is bit-identical, and every called position is covered where it says it is."""
+    from metasnv_b200 import abi
+    from pileup_counts import check_layout, numpy_counts
+    desc = H.describe("c2", 1.0, 0)
+    S = desc["n_samples"]
+    assert S == 1000 and sum(desc["contig_len"]) == 5000000
+    with abi.Context(0) as ctx:
+        P, first = ctx.shard_synth(desc)
+        ctx.shard_mask_position(first)
+        h = ctx.shard_run()
+        t = ctx.timings()
+        assert t["n_reads"] >= 4.9e8 and t["n_items"] > 4.8e6
+        picked = {}
+        for s in range(S):
+            z = ctx.sample_sizes(s)
+            kind = "paired" if z.n_mated else "unpaired"
+            if kind not in picked and z.n_reads:
+                picked[kind] = s
+            if len(picked) == 2:
+                break
+        assert set(picked) == {"paired", "unpaired"}
+        for kind, s in picked.items():
+            e = ctx.export_sample(s)
+            assert (e["mate"] >= 0).any() == (kind == "paired")
+            check_layout(e)
+            want = numpy_counts(e, P)
+            got = ctx.shard_counts(s, 0, P)
+            bad = np.argwhere(got != want)
+            assert bad.size == 0, "%s sample %d: first mismatch (pos, channel) %s: device %s, numpy %s" % (kind, s, bad[0], got[tuple(bad[0])], want[tuple(bad[0])])
+            assert int(got.sum()) > 3e7
+            # hits report this sample's coverage = counts of the four letters (+ N where the reference is N-like)
+            cov = got[h.pos.astype(np.int64), :4].sum(axis=1)
+            ref = ctx.export_ref(P)[h.pos.astype(np.int64)]
+            acgt_ref = np.isin(ref, np.frombuffer(b"ACGTacgt", np.uint8))
+            assert np.array_equal(h.cov[acgt_ref, s], cov[acgt_ref].astype(h.cov.dtype))
+        h2 = ctx.shard_run()
+        for a in ("pos", "pop_mask", "ind_mask", "cov", "allele", "total"):
+            assert np.array_equal(getattr(h, a), getattr(h2, a)), a
+        assert h.n_hits > 10000

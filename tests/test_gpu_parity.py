@@ -19,21 +19,6 @@ def _same(a, b):
     assert not d, "%s vs %s: %s" % (a, b, d)
 
 
-@pytest.fixture(scope="module")
-def datasets(built, tmp_path_factory):
-    cache = {}
-    base = str(tmp_path_factory.mktemp("data"))
-
-    def get(preset, scale, samples, **kw):
-        key = (preset, scale, samples, tuple(sorted(kw.items())))
-        if key not in cache:
-            d = os.path.join(base, "%s_%d" % (preset, len(cache)))
-            H.synth(d, preset, scale, samples, **kw)
-            cache[key] = d
-        return cache[key]
-    return get
-
-
 # ---------------------------------------------------------------- committed golden fixtures
 @pytest.mark.parametrize("name", ["c1_tiny", "c5_tiny_annotated", "c4_tiny_deep"])
 def test_golden_fixture(name, datasets, tmp_path):
@@ -143,38 +128,7 @@ def test_split_files_concatenate_to_whole(datasets, tmp_path):
 
 
 # ---------------------------------------------------------------- per-position counts (pileup kernel output)
-def _oracle_counts(pile_path, n_samples, layout, P):
-    """Parse mpileup text into [S][P][5] counts: a column's letters go to their base, '.'/',' to the reference's."""
-    off = {name: o for name, o, _ in layout}
-    cnt = np.zeros((n_samples, P, 5), np.uint16)
-    chan = {"A": 0, "C": 1, "G": 2, "T": 3, "a": 0, "c": 1, "g": 2, "t": 3}
-    for line in open(pile_path):
-        f = line.rstrip("\n").split("\t")
-        p = off[f[0]] + int(f[1]) - 1
-        r = f[2].upper()
-        rch = chan.get(r, 4)
-        for s in range(n_samples):
-            b = f[4 + 3 * s]
-            i = 0
-            while i < len(b):
-                ch = b[i]
-                if ch == "^":
-                    i += 2
-                    continue
-                if ch in "+-":
-                    j = i + 1
-                    while b[j].isdigit():
-                        j += 1
-                    i = j + int(b[i + 1:j])
-                    continue
-                if ch in ".,":
-                    cnt[s, p, rch] += 1
-                elif ch in chan:
-                    cnt[s, p, chan[ch]] += 1
-                elif ch in "Nn":
-                    cnt[s, p, 4] += 1
-                i += 1
-    return cnt
+from pileup_counts import oracle_counts as _oracle_counts  # noqa: E402
 
 
 @pytest.mark.parametrize("preset,scale,samples", [("c1", 0.03, 8), ("c4", 0.002, 2)])
