@@ -119,3 +119,27 @@ def test_overlap_rule_four_lane_form_matches_scalar_rule(tmp_path):
                     os.path.join(ROOT, "tests", "overlap_rule_check.cc"), "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "mismatches: 0" in r.stdout, r.stdout + r.stderr
+
+
+def test_bench_contract_on_cpu(built):
+    """bench.py without a GPU: the product arm refuses loudly (no CPU fallback to time), the reference arm prints
+    the contract's JSON line from rank 0 only."""
+    import json
+    import sys
+    bench = os.path.join(ROOT, "bench.py")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, bench, "--steps", "1"], capture_output=True, text=True, env=env)
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+    r = subprocess.run([sys.executable, bench, "--impl", "reference", "--workload", "c1", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["metric"] == "aligned_bases_per_s" and line["value"] > 1e6
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    r = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
+    assert r.returncode == 0 and r.stdout.strip() == ""
