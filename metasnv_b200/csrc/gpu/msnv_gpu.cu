@@ -227,7 +227,7 @@ static int ensure_items(msnv_ctx* ctx, uint64_t n_items)
     cudaError_t e1 = cudaMalloc((void**)&ctx->d_acgt, cap * TILE * 8);
     cudaError_t e2 = cudaMalloc((void**)&ctx->d_ncnt, cap * TILE * 2);
     if (e1 != cudaSuccess || e2 != cudaSuccess)
-        return fail(ctx, MSNV_E_NOMEM, "count tiles for %llu (sample,tile) items do not fit device memory", (unsigned long long)n_items);
+        return fail(ctx, MSNV_E_NOMEM, "count tiles for %llu (sample,tile) items do not fit device memory; run smaller shards (metaSNV.py --n_splits bins the genomes)", (unsigned long long)n_items);
     ctx->cap_items = cap;
     return 0;
 }
@@ -374,7 +374,7 @@ int msnv_shard_add_sample(msnv_ctx* ctx, uint32_t sample, const msnv_sample_read
     const size_t o_pos = take(n * 4), o_sgo = take(n1 * 4), o_q4 = take(n1 * 4), o_mate = take(n * 4),
                  o_sp = take(n_seg * 4), o_sl = take(n_seg * 2), o_seq = take(n_q4), o_qual = take(n_q4 * 4);
     uint8_t* base = (uint8_t*)take_block(ctx, off);
-    if (!base) return fail(ctx, MSNV_E_NOMEM, "sample %u: cannot allocate %zu bytes of device memory", sample, off);
+    if (!base) return fail(ctx, MSNV_E_NOMEM, "sample %u: cannot allocate %zu bytes of device memory; run smaller shards (metaSNV.py --n_splits bins the genomes)", sample, off);
     cudaStream_t st = ctx->stream;
     CU(cudaMemcpyAsync(base + o_pos, r->pos, n * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_sgo, r->seg_off, n1 * 4, cudaMemcpyHostToDevice, st));
