@@ -173,6 +173,7 @@ def run_ours(a):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     preset = WORKLOADS[a.workload][0]
@@ -192,6 +193,26 @@ def run_ours(a):
     host_samples = []
     n_reads = aligned = h2d_bytes = n_segs = 0
     e2e_on = not a.no_e2e
+    e2e_skipped = None
+    if e2e_on:
+        # The end-to-end leg keeps a host copy of the whole shard (75 GB for the headline shape) per rank. Never drive
+        # the box out of memory for it: all ranks agree (min over ranks) on whether the node has room.
+        import psutil
+        need = 0
+        for s in range(S):
+            z = ctx.sample_sizes(s)
+            need += z.n_reads * 16 + 8 + z.n_segs * 6 + z.n_q4 * 5 + 8 * 256
+        if dist is not None:
+            dist.barrier()
+        ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        room = psutil.virtual_memory().available >= need * ranks_here * 1.1 + 16e9
+        if dist is not None:
+            flag = torch.tensor([1 if room else 0], device="cuda", dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            room = bool(flag.item())
+        if not room:
+            e2e_on = False
+            e2e_skipped = "host memory: %.0f GB per rank x %d ranks needed for the host copies of the shards" % (need / 1e9, ranks_here)
     for s in range(S):
         e = ctx.export_sample(s, arena.alloc if e2e_on else None)
         aligned += int(e["seg_len"].sum(dtype=np.uint64))
@@ -258,6 +279,7 @@ def run_ours(a):
                 e2e_times.append(dt)
         e2e_ms = 1000.0 * sum(e2e_times) / len(e2e_times)
     host_samples = None
+    pageable_bytes = arena.pageable_bytes
     arena.close()
     ctx.close()
 
@@ -310,10 +332,14 @@ def run_ours(a):
                                     "frac": path_bytes / (dev_ms / 1000.0) / 1e9 / peak}},
         "setup_s": {"device_synth": t_synth, "export_to_pinned_host": t_export},
     }
+    if e2e_skipped:
+        line["e2e"] = {"value": None, "unit": "aligned bases/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                       "skipped": e2e_skipped}
     if e2e_on:
         line["e2e"] = {"value": tot_aligned / (e2e_max / 1000.0), "unit": "aligned bases/s", "h2d_bytes_per_step": h2d_bytes,
                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_max, "steps": a.e2e_steps,
-                       "what": "msnv_shard_begin + msnv_shard_add_sample x samples from pinned host arrays + msnv_shard_run (hits copied back)"}
+                       "what": "msnv_shard_begin + msnv_shard_add_sample x samples from pinned host arrays + msnv_shard_run (hits copied back)",
+                       "pageable_host_bytes": pageable_bytes}
     if world == 1 and not a.no_cpu_baseline:
         work = tempfile.mkdtemp(prefix="msnv_bench_cpu_")
         try:

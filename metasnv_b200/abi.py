@@ -108,25 +108,35 @@ def _ptr(a):
 
 
 class PinnedArena:
-    """Page-locked host memory from the library, carved out of 1 GiB slabs (cudaHostAlloc is slow per call)."""
+    """Page-locked host memory from the library, carved out of 1 GiB slabs (cudaHostAlloc is slow per call).
+    When the driver refuses to pin more, further slabs are ordinary (pageable) memory: copies from them are slower
+    but still correct; `pageable_bytes` says how much that was."""
     SLAB = 1 << 30
 
     def __init__(self):
         self.lib = load()
         self.slabs = []          # (ptr, size)
+        self.plain = []          # pageable slabs (numpy owns them)
         self.cur = None          # numpy view of the current slab
         self.off = 0
         self.bytes = 0
+        self.pageable_bytes = 0
 
     def alloc(self, nbytes):
         n = (max(1, int(nbytes)) + 255) // 256 * 256
         if self.cur is None or self.off + n > self.cur.size:
             size = max(self.SLAB, n)
-            p = self.lib.msnv_pinned_alloc(size)
-            if not p:
-                raise MsnvError("msnv_pinned_alloc(%d) failed" % size)
-            self.slabs.append((p, size))
-            self.cur = np.ctypeslib.as_array((C.c_uint8 * size).from_address(p))
+            p = None if self.plain else self.lib.msnv_pinned_alloc(size)      # once pinning failed, do not retry per slab
+            if p:
+                self.slabs.append((p, size))
+                self.cur = np.ctypeslib.as_array((C.c_uint8 * size).from_address(p))
+            else:
+                try:
+                    self.cur = np.empty(size, np.uint8)
+                except MemoryError:
+                    raise MsnvError("no host memory for another %d-byte staging slab" % size)
+                self.plain.append(self.cur)
+                self.pageable_bytes += size
             self.off = 0
         v = self.cur[self.off:self.off + n]
         self.off += n
@@ -138,6 +148,7 @@ class PinnedArena:
         for p, _ in self.slabs:
             self.lib.msnv_pinned_free(p)
         self.slabs = []
+        self.plain = []
 
 
 class HitsView:
