@@ -151,7 +151,7 @@ def run_reference(a):
                 "dtype": "u16", "data": "synthetic", "config": {"workload": WORKLOADS[a.workload][1], "sample": base["sample"]},
                 "cpu_baseline": base,
                 "e2e": {"value": value, "unit": "aligned bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
     finally:
         shutil.rmtree(work, ignore_errors=True)
     return 0
@@ -173,7 +173,6 @@ def run_ours(a):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     preset = WORKLOADS[a.workload][0]
@@ -346,8 +345,28 @@ def run_ours(a):
             line["cpu_baseline"], _, _ = cpu_baseline(a.workload, work)
         finally:
             shutil.rmtree(work, ignore_errors=True)
-    print(json.dumps(line))
+    emit(line)
     return 0
+
+
+_json_out = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner with
+    printf, ignoring NCCL_DEBUG_FILE): keep a private handle to the real stdout for the JSON line and point file
+    descriptor 1 at stderr for everybody else."""
+    global _json_out
+    if _json_out is None:
+        sys.stdout.flush()
+        _json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _json_out or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -368,6 +387,7 @@ def main():
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "ours":
         a.warmup = 3
+    claim_stdout()
     if a.impl == "reference":
         return run_reference(a)
     return run_ours(a)

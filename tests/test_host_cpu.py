@@ -133,7 +133,8 @@ def test_bench_contract_on_cpu(built):
     r = subprocess.run([sys.executable, bench, "--impl", "reference", "--workload", "c1", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr
-    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert len(r.stdout.strip().splitlines()) == 1, "exactly one line on stdout"
+    line = json.loads(r.stdout.strip())
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in line, k
@@ -143,3 +144,8 @@ def test_bench_contract_on_cpu(built):
     r = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
     assert r.returncode == 0 and r.stdout.strip() == ""
+    # anything a library prints to file descriptor 1 (NCCL's version banner does) must not reach stdout
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.claim_stdout(); os.system('echo banner from a library'); "
+            "print('python print'); bench.emit({'a': 1})" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == '{"a": 1}\n' and "banner from a library" in r.stderr and "python print" in r.stderr
