@@ -28,7 +28,9 @@ extern "C" {
 #define MSNV_ABI_VERSION 3
 
 /* Positions per tile: contigs of a shard are laid out back to back in a "shard coordinate" space,
- * each starting at a multiple of MSNV_TILE, so a tile never spans two contigs. */
+ * each starting at a multiple of MSNV_TILE, so a tile never spans two contigs. The kernels are written
+ * for 1024 (256 quads per tile: the pileup kernel tags a staged quad with one byte); the library
+ * refuses to compile for another value. */
 #ifndef MSNV_TILE
 #define MSNV_TILE 1024
 #endif
