@@ -109,6 +109,18 @@ def test_bam_roundtrip_product_writer_oracle_reader(built, tmp_path):
     assert H.bed_header(d, str(tmp_path / "bed")) and open(str(tmp_path / "bed")).read().count("\n") == 3
 
 
+def test_fast_inflate_agrees_with_zlib(tmp_path):
+    """csrc/host/fast_inflate.cc (the BGZF reader's own DEFLATE decoder) against zlib on ~2900 streams: stored, fixed
+    and dynamic blocks, multi-block streams, every size up to 64 KiB, truncated and bit-flipped input, wrong expected
+    sizes; guard bytes around the output buffer. The checker is tests/fast_inflate_check.cc."""
+    exe = str(tmp_path / "fast_inflate_check")
+    host = os.path.join(ROOT, "metasnv_b200", "csrc", "host")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", host, os.path.join(ROOT, "tests", "fast_inflate_check.cc"),
+                    os.path.join(host, "fast_inflate.cc"), "-lz", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "mismatches: 0" in r.stdout, r.stdout + r.stderr[-2000:]
+
+
 def test_overlap_rule_four_lane_form_matches_scalar_rule(tmp_path):
     """csrc/gpu/overlap_rule.h (host + device): the byte-lane form the pileup kernel uses equals the scalar
     restatement of htslib's tweak_overlap_quality (SURVEY.md Annex A.2) for every (quality, quality, base, base)
