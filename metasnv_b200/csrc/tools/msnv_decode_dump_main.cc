@@ -57,9 +57,10 @@ int main(int argc, char** argv)
             fprintf(stderr, "msnv_decode_dump: cannot write to %s\n", out.c_str()); return 1;
         }
         fprintf(js, "%s{\"n_reads\": %zu, \"n_segs\": %zu, \"n_q4\": %zu, \"max_span\": %u, \"first_column\": %lld, \"records\": %llu, \"accepted\": %llu, "
-                    "\"dropped_by_cap\": %llu, \"aligned_bases\": %llu, \"pairs\": %llu}",
+                    "\"dropped_by_cap\": %llu, \"aligned_bases\": %llu, \"pairs\": %llu, \"decode_s\": %.6f, \"inflate_s\": %.6f}",
                 s ? ", " : "", r.pos.size(), r.seg_pos.size(), r.seq2.size(), r.max_span, (long long)st.first_column, (unsigned long long)st.records,
-                (unsigned long long)st.accepted, (unsigned long long)st.dropped_by_cap, (unsigned long long)st.aligned_bases, (unsigned long long)st.pairs);
+                (unsigned long long)st.accepted, (unsigned long long)st.dropped_by_cap, (unsigned long long)st.aligned_bases, (unsigned long long)st.pairs,
+                st.seconds, st.inflate_seconds);
     }
     fprintf(js, "]}\n");
     fclose(js);
