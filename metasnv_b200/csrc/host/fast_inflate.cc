@@ -10,18 +10,20 @@ namespace {
 // bits 0..4   code bits to consume (for a link: the primary table's width)
 // bits 5..8   extra bits that follow the code (lengths: 0..5, distances: 0..13; for a link: subtable index bits)
 // bits 9..10  kind
+// bit  11     (literals) the entry carries TWO literals: value = first | second << 8, the bit count covers both codes
 // bits 16..31 literal byte | length or distance base | 0 = end of block, 1 = invalid symbol | subtable offset
 // Bit patterns no code maps to hold INVALID (a "special" entry), so the hot loop tests the kind only.
 enum : uint32_t { K_LITERAL = 0, K_BASE = 1, K_SPECIAL = 2, K_LINK = 3 };
 constexpr uint32_t entry(uint32_t nbits, uint32_t extra, uint32_t kind, uint32_t value) { return nbits | extra << 5 | kind << 9 | value << 16; }
 constexpr uint32_t INVALID = entry(1, 0, K_SPECIAL, 1);
+constexpr uint32_t DOUBLE = 1u << 11;
 inline uint32_t e_bits(uint32_t e) { return e & 31u; }
 inline uint32_t e_extra(uint32_t e) { return (e >> 5) & 15u; }
 inline uint32_t e_kind(uint32_t e) { return (e >> 9) & 3u; }
 inline uint32_t e_value(uint32_t e) { return e >> 16; }
 
-constexpr int LL_PRIMARY = 10, D_PRIMARY = 8, CL_PRIMARY = 7;
-constexpr int LL_SIZE = 2048, D_SIZE = 1024;          // primary + subtables; build_table refuses to overflow them
+constexpr int LL_PRIMARY = 11, D_PRIMARY = 8, CL_PRIMARY = 7;
+constexpr int LL_SIZE = 2048 + 1024, D_SIZE = 1024;          // primary + subtables; build_table refuses to overflow them
 
 const uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
 const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -70,6 +72,7 @@ bool build_table(Alphabet a, const uint8_t* lens, int n, int primary, uint32_t* 
     const int psize = 1 << primary;
     for (int i = 0; i < psize; ++i) table[i] = INVALID;
     // widest code behind every primary prefix that needs a subtable
+    static_assert(LL_PRIMARY >= D_PRIMARY && LL_PRIMARY >= CL_PRIMARY, "scratch arrays are sized for the widest primary table");
     uint8_t sub_bits[1 << LL_PRIMARY];
     memset(sub_bits, 0, (size_t)psize);
     uint32_t codes[288];
@@ -102,6 +105,21 @@ bool build_table(Alphabet a, const uint8_t* lens, int n, int primary, uint32_t* 
             const uint32_t e = symbol_entry(a, (uint32_t)s, (uint32_t)(l - primary));
             const uint32_t size = 1u << e_extra(link);
             for (uint32_t i = codes[s] >> primary; i < size; i += 1u << (l - primary)) table[e_value(link) + i] = e;
+        }
+    }
+    if (a == LITLEN) {
+        // two short literal codes that fit the primary index together become one entry: BAM payload is literal-heavy
+        // (qualities, packed bases) with codes of 2-6 bits, and a table look-up per symbol is what bounds the decoder
+        uint32_t single[1 << LL_PRIMARY];
+        memcpy(single, table, sizeof(uint32_t) * (size_t)psize);
+        for (int i = 0; i < psize; ++i) {
+            const uint32_t e1 = single[i];
+            if (e_kind(e1) != K_LITERAL) continue;
+            const uint32_t l1 = e_bits(e1);
+            if ((int)l1 >= primary) continue;
+            const uint32_t e2 = single[(uint32_t)i >> l1];             // the index bits behind the first code, zero-extended
+            if (e_kind(e2) != K_LITERAL || l1 + e_bits(e2) > (uint32_t)primary) continue;
+            table[i] = entry(l1 + e_bits(e2), 0, K_LITERAL, e_value(e1) | e_value(e2) << 8) | DOUBLE;
         }
     }
     return true;
@@ -212,25 +230,28 @@ bool fast_inflate(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len
         } else return false;
 
         // ---- symbols of one Huffman block
-        // Fast loop while there is slack on both sides (no bounds tests inside): up to three literals per refill
-        // of the bit buffer, then at most one match (258 bytes + 8 of copy slack).
+        // Fast loop while there is slack on both sides (no bounds tests inside): up to three literal entries (six
+        // literals) per refill of the bit buffer, then at most one match (258 bytes + 8 of copy slack).
         bool block_done = false;
-        while (out_end - out >= 3 + 258 + 8 && b.end - b.in >= 8) {
+        while (out_end - out >= 6 + 258 + 8 && b.end - b.in >= 8) {
             b.refill();
             uint32_t e = ll[b.peek(LL_PRIMARY)];
+            // an entry of the primary table holds one literal or two: both bytes are stored, the pointer moves by 1 or 2
+#define MSNV_PUT_LITERALS(e) do { b.consume((int)e_bits(e)); out[0] = (uint8_t)e_value(e); out[1] = (uint8_t)(e_value(e) >> 8); out += 1 + (((e) >> 11) & 1u); } while (0)
             if (e_kind(e) == K_LITERAL) {
-                b.consume((int)e_bits(e)); *out++ = (uint8_t)e_value(e);
+                MSNV_PUT_LITERALS(e);
                 e = ll[b.peek(LL_PRIMARY)];
                 if (e_kind(e) == K_LITERAL) {
-                    b.consume((int)e_bits(e)); *out++ = (uint8_t)e_value(e);
+                    MSNV_PUT_LITERALS(e);
                     e = ll[b.peek(LL_PRIMARY)];
-                    if (e_kind(e) == K_LITERAL) { b.consume((int)e_bits(e)); *out++ = (uint8_t)e_value(e); continue; }
+                    if (e_kind(e) == K_LITERAL) { MSNV_PUT_LITERALS(e); continue; }
                 }
                 b.refill();                                 // keeps the low bits: `e` still describes the next symbol
             }
+#undef MSNV_PUT_LITERALS
             if (e_kind(e) == K_LINK) { b.consume(LL_PRIMARY); e = ll[e_value(e) + b.peek((int)e_extra(e))]; }
             b.consume((int)e_bits(e));
-            if (e_kind(e) == K_LITERAL) { *out++ = (uint8_t)e_value(e); continue; }
+            if (e_kind(e) == K_LITERAL) { *out++ = (uint8_t)e_value(e); continue; }           // (subtable entries are single)
             if (e_kind(e) == K_SPECIAL) {
                 if (e_value(e) != 0) return false;
                 block_done = true;
@@ -262,6 +283,10 @@ bool fast_inflate(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len
             if (e_kind(e) == K_LITERAL) {
                 if (out >= out_end) return false;
                 *out++ = (uint8_t)e_value(e);
+                if (e & DOUBLE) {
+                    if (out >= out_end) return false;
+                    *out++ = (uint8_t)(e_value(e) >> 8);
+                }
                 continue;
             }
             if (e_kind(e) == K_SPECIAL) {
