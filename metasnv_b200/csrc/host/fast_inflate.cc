@@ -49,12 +49,10 @@ inline uint32_t symbol_entry(Alphabet a, uint32_t sym, uint32_t nbits)
     }
 }
 
-inline uint32_t reverse_bits(uint32_t v, int n)
-{
-    uint32_t r = 0;
-    for (int i = 0; i < n; ++i) { r = r << 1 | (v & 1u); v >>= 1; }
-    return r;
-}
+struct Reverse8 { uint8_t t[256]; constexpr Reverse8() : t() { for (int i = 0; i < 256; ++i) { int r = 0; for (int k = 0; k < 8; ++k) r |= ((i >> k) & 1) << (7 - k); t[i] = (uint8_t)r; } } };
+constexpr Reverse8 kReverse8;
+// the low n (<= 15) bits of v in reverse order
+inline uint32_t reverse_bits(uint32_t v, int n) { return ((uint32_t)kReverse8.t[v & 0xff] << 8 | kReverse8.t[(v >> 8) & 0xff]) >> (16 - n); }
 
 // Canonical Huffman code of `lens[0..n)` (0 = unused symbol) -> look-up table indexed by the next
 // `primary` input bits (LSB first). Over-subscribed codes are refused; incomplete ones are accepted
