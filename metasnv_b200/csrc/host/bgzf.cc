@@ -1,5 +1,6 @@
 // bgzf.cc -- see bgzf.hpp.
 #include "bgzf.hpp"
+#include "crc32_fold.hpp"
 #include "fast_inflate.hpp"
 
 #include <fcntl.h>
@@ -121,7 +122,7 @@ bool inflate_member(const uint8_t* src, const Member& m, uint8_t* dst)
     // the path's own decoder first (fast_inflate.hpp); zlib only for what it refuses. The CRC is checked either way.
     static const bool use_zlib_only = getenv("MSNV_ZLIB_INFLATE") != nullptr;      // A/B switch for tests and timing
     if (!use_zlib_only && fast_inflate(src + m.coff, m.clen, dst + m.ooff, m.isize))
-        return (uint32_t)crc32(crc32(0L, nullptr, 0), dst + m.ooff, m.isize) == m.crc;
+        return crc32_member(dst + m.ooff, m.isize) == m.crc;
     z_stream zs; memset(&zs, 0, sizeof zs);
     if (inflateInit2(&zs, -15) != Z_OK) return false;
     zs.next_in = (Bytef*)(src + m.coff); zs.avail_in = m.clen;
@@ -129,7 +130,7 @@ bool inflate_member(const uint8_t* src, const Member& m, uint8_t* dst)
     int zr = inflate(&zs, Z_FINISH);
     inflateEnd(&zs);
     if (zr != Z_STREAM_END || zs.total_out != m.isize) return false;
-    return (uint32_t)crc32(crc32(0L, nullptr, 0), dst + m.ooff, m.isize) == m.crc;
+    return crc32_member(dst + m.ooff, m.isize) == m.crc;
 }
 }  // namespace
 

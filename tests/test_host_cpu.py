@@ -121,6 +121,16 @@ def test_fast_inflate_agrees_with_zlib(tmp_path):
     assert r.returncode == 0 and "mismatches: 0" in r.stdout, r.stdout + r.stderr[-2000:]
 
 
+def test_folded_crc32_agrees_with_zlib(tmp_path):
+    """csrc/host/crc32_fold.cc (carry-less-multiply CRC-32 of a BGZF member, zlib for the tail and on other CPUs)."""
+    exe = str(tmp_path / "crc32_fold_check")
+    host = os.path.join(ROOT, "metasnv_b200", "csrc", "host")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", host, os.path.join(ROOT, "tests", "crc32_fold_check.cc"),
+                    os.path.join(host, "crc32_fold.cc"), "-lz", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "mismatches: 0" in r.stdout, r.stdout + r.stderr[-2000:]
+
+
 def test_overlap_rule_four_lane_form_matches_scalar_rule(tmp_path):
     """csrc/gpu/overlap_rule.h (host + device): the byte-lane form the pileup kernel uses equals the scalar
     restatement of htslib's tweak_overlap_quality (SURVEY.md Annex A.2) for every (quality, quality, base, base)
