@@ -140,8 +140,8 @@ size_t SampleReads::bytes() const
 
 namespace {
 
-// BAM 4-bit base code -> 2-bit code (A,C,G,T) or 4 for everything else
-const uint8_t kCode4to2[16] = {4, 0, 1, 4, 2, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4};
+// BAM 4-bit base code -> 2-bit code (A,C,G,T), or 0x80 (flag, code bits 0) for everything else
+const uint8_t kCode4to2f[16] = {0x80, 0, 1, 0x80, 2, 0x80, 0x80, 0x80, 3, 0x80, 0x80, 0x80, 0x80, 0x80, 0x80, 0x80};
 
 inline uint64_t hash_qname(const char* s)
 {
@@ -265,19 +265,39 @@ bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& la
                         out.seq2.resize(s0 + nq, 0);
                         out.qual.resize(q0 + 4 * nq, 0);
                         uint8_t* sq = out.seq2.data() + s0; uint8_t* ql = out.qual.data() + q0;
+                        // three plain passes instead of one branchy loop: (1) nibbles -> 2-bit code or the "other base"
+                        // flag 0x80, two per sequence byte; (2) qualities capped at 127 plus the flag; (3) four codes per byte
+                        uint8_t cf[MSNV_MAX_READ_BASES + 2];
+                        {
+                            uint32_t k = 0; size_t i2 = qy;
+                            if (i2 & 1) { cf[k++] = kCode4to2f[r.seq[i2 >> 1] & 0xf]; ++i2; }
+                            for (; k + 2 <= len; k += 2, i2 += 2) { const uint8_t b = r.seq[i2 >> 1]; cf[k] = kCode4to2f[b >> 4]; cf[k + 1] = kCode4to2f[b & 0xf]; }
+                            if (k < len) cf[k] = kCode4to2f[r.seq[i2 >> 1] >> 4];
+                        }
+                        const uint8_t* qin = r.qual + qy;
+                        uint8_t any = 0;
                         for (uint32_t k = 0; k < len; ++k) {
-                            const size_t i2 = qy + k, o = a + k;
-                            const uint8_t c4 = (r.seq[i2 >> 1] >> ((~i2 & 1) << 2)) & 0xf;
-                            const uint8_t c2 = kCode4to2[c4];
-                            uint8_t q = r.qual[i2]; if (q > 127) q = 127;
-                            if (c2 == 4) {
-                                q |= 0x80;
-                                if (c4 != 15 && !warned_iupac) {
+                            const uint8_t q = qin[k] < 127 ? qin[k] : 127;
+                            ql[a + k] = (uint8_t)(q | (cf[k] & 0x80));
+                            any |= cf[k];
+                        }
+                        {
+                            uint32_t k = 0, o = a;
+                            for (; (o & 3) && k < len; ++k, ++o) sq[o >> 2] |= (uint8_t)((cf[k] & 3) << ((o & 3) * 2));
+                            for (; k + 4 <= len; k += 4, o += 4)
+                                sq[o >> 2] = (uint8_t)((cf[k] & 3) | (cf[k + 1] & 3) << 2 | (cf[k + 2] & 3) << 4 | (cf[k + 3] & 3) << 6);
+                            for (; k < len; ++k, ++o) sq[o >> 2] |= (uint8_t)((cf[k] & 3) << ((o & 3) * 2));
+                        }
+                        if ((any & 0x80) && !warned_iupac) {           // rare: is one of the flagged bases something other than N?
+                            for (uint32_t k = 0; k < len; ++k) {
+                                const size_t i2 = qy + k;
+                                const uint8_t c4 = (r.seq[i2 >> 1] >> ((~i2 & 1) << 2)) & 0xf;
+                                if ((cf[k] & 0x80) && c4 != 15) {
                                     fprintf(stderr, "[msnv] %s: read %s has a base other than A/C/G/T/N; such bases are not counted\n", bam_path.c_str(), r.qname);
                                     warned_iupac = true;
+                                    break;
                                 }
-                            } else sq[o >> 2] |= (uint8_t)(c2 << ((o & 3) * 2));
-                            ql[o] = q;
+                            }
                         }
                         out.seg_pos.push_back((int32_t)rx);
                         out.seg_len.push_back((uint16_t)len);
