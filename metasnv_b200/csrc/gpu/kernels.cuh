@@ -2,10 +2,10 @@
 //
 // Data flow for one shard (all samples of one genome bin):
 //   index_kernel     (tile, sample) pairs that have reads  -> ordered work items (ballot compaction)
-//   pileup_kernel    per item: stage the reads' position-aligned segments (TMA bulk copies) ->
-//                    mate-overlap quality correction (SURVEY.md Annex A.2) in shared memory ->
-//                    four positions per thread scattered into byte-lane counters
-//                    -> packed A/C/G/T/N counts, 10 B per sample-position      [dominant kernel]
+//   pileup_kernel    persistent CTAs: a producer warp stages the items' position-aligned reads through a
+//                    ring of TMA bulk copies; consumer warps apply the mate-overlap quality correction
+//                    (SURVEY.md Annex A.2) in shared memory and scatter sixteen positions per thread and
+//                    step into byte-lane count planes -> 6 B per sample-position     [dominant kernel]
 //   call_kernel      per tile: reduce over samples, snpCall thresholds (call_vC.cpp:545-601)
 //   compact_kernel   ordered stream compaction of called positions (warp ballot + block scan)
 //   gather_kernel    per hit: per-sample coverage / allele counts for the host formatter
@@ -22,15 +22,6 @@
 namespace msnv_gpu {
 
 constexpr int TILE = MSNV_TILE;                 // positions per tile
-// CTA shapes of the pileup kernel (threads, reads staged per chunk <= threads - 1: one thread per read in the
-// per-read steps; at most 255 so that 8-bit per-chunk counters cannot overflow). A CTA's life is a sequence of
-// short dependent steps, so many small CTAs per SM keep the SM busy better than few large ones; deep data gets
-// the larger shape (fewer chunks per tile).
-constexpr int CHUNK_Q4_MAX = 4096;              // upper bound of the quads staged per chunk (chosen per launch)
-constexpr int CHUNK_Q4_MIN = MSNV_MAX_READ_BASES / 4 + 2 * MSNV_MAX_READ_SEGMENTS;   // a single read always fits
-constexpr int CHUNK_SEGS = 256;                 // aligned segments per chunk (<= 256: one byte tags a quad)
-
-static_assert(MSNV_MAX_READ_SEGMENTS <= CHUNK_SEGS, "one read's segments must fit a chunk");
 
 struct SampleDev {
     const int32_t*  pos;
@@ -173,12 +164,21 @@ __global__ void __launch_bounds__(256) mark_kernel(const SampleDev* __restrict__
     }
 }
 
+// The index searches every sample's `pos`: refuse samples whose reads are not in coordinate order (err_flag = 3).
+__global__ void __launch_bounds__(256) order_check_kernel(const SampleDev* __restrict__ samples, int* __restrict__ err_flag)
+{
+    const SampleDev sd = samples[blockIdx.y];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i + 1 < sd.n_reads; i += gridDim.x * blockDim.x)
+        if (__ldg(sd.pos + i) > __ldg(sd.pos + i + 1)) atomicExch(err_flag, 3);
+}
+
 template <bool EMIT>
 __global__ void __launch_bounds__(256) index_kernel(const SampleDev* __restrict__ samples, uint32_t n_samples,
                                                     uint32_t n_tiles, uint32_t* __restrict__ block_sums,
                                                     Item* __restrict__ items, uint32_t* __restrict__ tile_begin,
                                                     uint2* __restrict__ range_cache /* [tiles*samples] or null: COUNT stores, EMIT reloads */,
-                                                    const uint32_t* __restrict__ bitmap /* mark_kernel's, or null */, uint32_t words_per_sample)
+                                                    const uint32_t* __restrict__ bitmap /* mark_kernel's, or null */, uint32_t words_per_sample,
+                                                    unsigned long long* __restrict__ item_reads /* COUNT: sum of r_hi - r_lo over the items */)
 {
     __shared__ uint32_t s_warp[33];
     const uint64_t pair = (uint64_t)blockIdx.x * 256 + threadIdx.x;
@@ -224,6 +224,11 @@ __global__ void __launch_bounds__(256) index_kernel(const SampleDev* __restrict_
     uint32_t rank = block_rank(active, s_warp, total);
     if (!EMIT) {
         if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+        // reads staged over all items: sizes the pileup kernel's staging buffers
+        uint32_t nr = active ? r_hi - r_lo : 0u;
+        #pragma unroll
+        for (int d = 16; d > 0; d >>= 1) nr += __shfl_down_sync(0xffffffffu, nr, d);
+        if ((threadIdx.x & 31) == 0 && nr) atomicAdd(item_reads, (unsigned long long)nr);
     } else {
         const uint32_t slot = block_sums[blockIdx.x] + rank;     // block_sums holds exclusive offsets now
         if (active) items[slot] = Item{s, t, r_lo, r_hi};
@@ -238,7 +243,7 @@ __global__ void dense_items_kernel(uint32_t n_samples, uint32_t n_tiles, Item* _
     const uint64_t n = (uint64_t)n_samples * n_tiles;
     if (i < n) {
         const uint32_t t = (uint32_t)(i / n_samples), s = (uint32_t)(i - (uint64_t)t * n_samples);
-        items[i] = Item{s, t, 0u, 0u};
+        items[i] = Item{s, t, 0u, 0xffffffffu};             // "wide": the planes handed in are 16-bit
         if (s == 0) tile_begin[t] = (uint32_t)i;
     }
     if (i == n) tile_begin[n_tiles] = (uint32_t)n;
@@ -283,201 +288,359 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ v, ui
 }
 
 // ------------------------------------------------------------------------------------------------
-// helpers of the pileup kernel
-// ------------------------------------------------------------------------------------------------
-// ------------------------------------------------------------------------------------------------
-// pileup: one CTA (128 or 256 threads, see the variant table in msnv_gpu.cu) per work item
-// (sample, tile of TILE positions).
-// Reads arrive as position-aligned segments (include/msnv.h): a staged quad holds four consecutive
-// positions starting at a multiple of four, so a quad is either on the tile or off it, and the four
-// bases of a quad are handled with byte-lane (SWAR) arithmetic, never one at a time.
-// Per chunk of reads (<= CHUNK_READS reads, chunk_q4 quads, CHUNK_SEGS segments):
-//   1. offsets and mates of the chunk's reads -> shared memory; __syncthreads_count sizes the chunk
-//   2. two TMA bulk copies (2-bit bases, qualities) are issued; while they fly,
-//   3. one thread per read loads its segment records, derives for every segment where its quads
-//      lie in the staging buffer and on the tile, and tags every quad with (the low byte of) its
-//      tile-relative index, four tags per store; after the copies have landed the same threads zero
-//      the qualities of the few quads that lie off the tile
-//   4. mate-overlap quality correction in shared memory (overlap_rule.h), eight lanes per pair, a
-//      quad of both mates per lane and step (mates staged in another chunk are read, pristine,
-//      from global memory)
-//   5. flat scatter: thread g takes the g-th staged quad: quality test and base decoding for the
-//      four positions at once, then ONE shared-memory atomic per base letter. Plane X of the
-//      counters holds, per quad of the tile, a word with one byte lane per position; the plane
-//      offsets are immediates. Padding bytes and quads off the tile carry quality 0 and fail the
-//      threshold like any poor base: the loop has no bounds test and no table look-up.
-//   6. thread t folds the byte lanes of its quads into 16-bit lanes held in registers and clears them
-// The reads in HBM are never modified.
-// What bounds the kernel is the length of this chain of short dependent steps, not HBM: CTAs are
-// kept small and the staging buffers are sized at launch from the mean work per item so that 7-8
-// CTAs per SM overlap each other's barriers and latencies.
-//
-// Shared memory (dynamic), regions 16-byte aligned:
-//   s_meta   3 x META_STRIDE u32      q4_off | seg_off | mate of the chunk's reads
-//   s_seg    CHUNK_SEGS x 16 bytes    {first position, length, byte index of its first quality,
-//                                      tile-relative index of its first quad}
-//   s_cnt    5 x TILE bytes           planes A, C, G, T, non-ACGT: one byte per position
-//   s_seq    chunk_q4 + 32 bytes      2-bit bases           (TMA destination)
-//   s_qual   4*chunk_q4 + 32 bytes    qualities             (TMA destination)
-//   s_g2s    chunk_q4 bytes           tile-relative index of every staged quad (low byte)
+// count tiles: what the pileup kernel writes and the call / gather kernels read.
+// Every work item (sample, tile) owns a slot of SLOT_BYTES in HBM holding six count planes of
+// TILE positions:
+//   D   bases counted at the position (quality >= 13 after the mate-overlap correction, base A/C/G/T)
+//   A, C, G, T   those of them that DIFFER from the position's expected letter e (expect[]: the
+//       reference base, A where the reference is not A/C/G/T); the plane of letter e stays 0
+//   N   counted bases that are not A/C/G/T
+// so count[e] = D - (A + C + G + T) and count[x != e] = plane x. Nearly every aligned base equals the
+// reference, so the pileup does ONE shared-memory atomic per four positions instead of four.
+// Narrow items (at most 255 reads touch the tile: no counter can pass 255) store the planes as
+// bytes (6 B per sample-position), wide items (deep coverage) as 16-bit values (12 B).
 // ------------------------------------------------------------------------------------------------
 constexpr int TILE_QUADS = TILE / 4;
+constexpr int N_PLANES = 6;
+constexpr int PLANE_D = 0, PLANE_A = 1, PLANE_N = 5;
+constexpr uint32_t NARROW_MAX_READS = 255;
+constexpr size_t SLOT_BYTES = 2 * N_PLANES * TILE;
+static_assert(TILE_QUADS == 256, "a staged quad is tagged with one byte");
 
-__host__ __device__ constexpr size_t pileup_smem_bytes(int chunk_reads, uint32_t chunk_q4)
+__host__ __device__ __forceinline__ bool item_is_wide(uint32_t r_lo, uint32_t r_hi) { return r_hi - r_lo > NARROW_MAX_READS; }
+
+// expected letter per position (0..3 = A,C,G,T) from the reference characters
+__global__ void expect_kernel(const uint8_t* __restrict__ ref, uint32_t n, uint8_t* __restrict__ expect)
 {
-    return (size_t)(3 * ((chunk_reads + 4) / 4 * 4) * 4 + CHUNK_SEGS * 16 + ((chunk_reads + 4) / 4 * 4) * 2 + 64 + 5 * TILE) +
-           (chunk_q4 + 32) + (4 * (size_t)chunk_q4 + 32) + (size_t)chunk_q4 + 32;
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t e = 0;
+    switch (ref[p]) {
+        case 'C': case 'c': e = 1; break;
+        case 'G': case 'g': e = 2; break;
+        case 'T': case 't': e = 3; break;
+        default: break;
+    }
+    expect[p] = (uint8_t)e;
 }
 
-// explicit shared-window accesses (32-bit addresses): the compiler otherwise rebuilds generic
-// pointers from the CTA's shared base in every iteration of the scatter loop
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-template <int OFF>
-__device__ __forceinline__ void red_shared_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0+%2], %1;" :: "r"(a), "r"(v), "n"(OFF) : "memory"); }
+// ------------------------------------------------------------------------------------------------
+// pileup: persistent CTAs, one producer warp + four consumer warps each, walking the work items
+// blockIdx.x, blockIdx.x + gridDim.x, ... (items are tile-major, so the CTAs resident at any time
+// work on neighbouring tiles and the reads of a sample stream through L2 once).
+//
+// Producer warp. Item records and the four offsets that size an item are fetched 32 items at a time
+// (one per lane: the dependent global loads of 32 items overlap). An item whose reads fit one stage
+// (the common case) becomes one chunk; otherwise the warp searches the longest prefix of reads that
+// fits (32 probes at a time) and sends several chunks. For a chunk the warp waits for a free stage of
+// the ring, writes a header and issues eight TMA bulk copies (UBLKCP) that complete on the stage's
+// mbarrier: the reads' offsets and mate links, the segment records, the 2-bit bases, the qualities
+// and the tile's expected letters. Consumers therefore never wait for HBM, only for the barrier.
+//
+// Consumer warps, per chunk (reads arrive as position-aligned segments, include/msnv.h: a staged
+// quad holds four consecutive positions starting at a multiple of four, so a quad is either on the
+// tile or off it and its four bases are handled with byte-lane arithmetic):
+//   1. one thread per read: segment geometry -> s_seg; every staged quad that lies on the tile is
+//      tagged with its tile-relative index (four tags per store), the qualities of the few quads off
+//      the tile are zeroed (the scatter's threshold test then rejects them like any poor base);
+//      reads with an overlapping mate are queued
+//   2. mate-overlap quality correction on the staged qualities (overlap_rule.h, SURVEY.md Annex
+//      A.2), eight lanes per pair, one quad of both mates per lane and step; a mate staged in
+//      another chunk is read, pristine, from global memory. The reads in HBM are never modified.
+//   3. scatter: a thread takes FOUR consecutive staged quads per step (one 128-bit load of the
+//      qualities, one word of bases, one word of tags). Per quad: quality test on four byte lanes,
+//      one shared-memory atomic into plane D, and a compare with the expected letters; only lanes
+//      that hold a mismatch loop over their set bits and add to a letter plane.
+//   4. last chunk of an item: narrow items copy the byte planes to HBM (6 KB, 128-bit stores) and
+//      clear them; wide items fold every chunk into 16-bit lanes held in registers (a chunk stages
+//      at most 255 reads) and store those.
+//
+// Shared memory (dynamic, see pileup_smem_layout): mbarriers | 6 count planes | s_seg | overlap
+// queue | quad tags | PL_STAGES x { header, q4_off, seg_off, mate, seg_pos, seg_len, expected
+// letters, bases, qualities }. Every TMA destination is 16-byte aligned; sources are the 16-byte
+// aligned addresses at or below the first element needed (the arrays are 256-byte aligned and have
+// 32 spare bytes behind them), so a stage holds a few elements in front of and behind the chunk.
+// ------------------------------------------------------------------------------------------------
+constexpr int PL_CONSUMERS = 128;
+constexpr int PL_THREADS = PL_CONSUMERS + 32;
+constexpr int PL_STAGES = 2;
+constexpr uint32_t CHUNK_Q4_MIN = MSNV_MAX_READ_BASES / 4 + 2 * MSNV_MAX_READ_SEGMENTS;   // a single read always fits
+constexpr uint32_t CHUNK_SEGS_MIN = MSNV_MAX_READ_SEGMENTS;
+constexpr uint32_t CHUNK_FIRST = 1u, CHUNK_LAST = 2u, CHUNK_WIDE = 4u, CHUNK_STOP = 8u;
 
-template <int THREADS, int CHUNK_READS, int MIN_CTAS>
-__global__ void __launch_bounds__(THREADS, MIN_CTAS)
-pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items, uint32_t chunk_q4,
-              uint64_t* __restrict__ acgt /*[n_items][TILE]*/, uint16_t* __restrict__ ncnt /*[n_items][TILE]*/,
-              int* __restrict__ err_flag)
+// limits of one staged chunk, chosen per launch from the shape of the shard
+struct PileupShape { uint32_t max_reads, max_segs, chunk_q4; };
+
+struct ChunkHdr { uint32_t m, nq4, q4_0, sg_0, nseg, c0, item, sample, tile, flags, pad[6]; };
+static_assert(sizeof(ChunkHdr) == 64, "header is one 64-byte block");
+
+struct PileupSmem {
+    uint32_t bar, misc, cnt, seg, pairs, tags, stage0, stage_bytes;              // byte offsets
+    uint32_t o_hdr, o_q4, o_sg, o_mt, o_sp, o_sl, o_exp, o_seq, o_qual;         // within a stage
+    uint32_t total;
+};
+
+__host__ __device__ constexpr uint32_t up_to(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ inline PileupSmem pileup_smem_layout(const PileupShape sh)
 {
-    static_assert(TILE_QUADS == 256 && CHUNK_READS < THREADS && TILE_QUADS % THREADS == 0, "one thread per staged read; each thread folds whole quads");
-    constexpr int QUADS_PER_THREAD = TILE_QUADS / THREADS;
-    constexpr int META_STRIDE = (CHUNK_READS + 4) / 4 * 4;
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint32_t* s_q4   = (uint32_t*)smem;
-    uint32_t* s_sgo  = s_q4 + META_STRIDE;
-    int32_t*  s_mate = (int32_t*)(s_sgo + META_STRIDE);
-    uint4*    s_seg  = (uint4*)(s_mate + META_STRIDE);
-    uint16_t* s_pairs = (uint16_t*)(s_seg + CHUNK_SEGS);
-    uint64_t* s_bar  = (uint64_t*)(s_pairs + META_STRIDE);
-    uint32_t* s_misc = (uint32_t*)(s_bar + 1);        // [0] number of overlap tasks of the chunk
-    uint32_t* s_cnt  = s_misc + 14;                   // 5 planes of TILE_QUADS words
-    uint8_t*  s_seq  = (uint8_t*)(s_cnt + 5 * TILE_QUADS);
-    uint8_t*  s_qual = s_seq + chunk_q4 + 32;
-    uint8_t*  s_g2s  = s_qual + 4 * chunk_q4 + 32;                // 4-byte aligned
+    PileupSmem L{};
+    uint32_t o = 0;
+    L.bar = o;   o += 64;
+    L.misc = o;  o += 64;
+    L.cnt = o;   o += N_PLANES * TILE;
+    L.seg = o;   o += up_to(sh.max_segs, 4) * 16;
+    L.pairs = o; o += up_to(sh.max_reads * 2, 16);
+    L.tags = o;  o += up_to(sh.chunk_q4, 16) + 16;
+    L.stage0 = up_to(o, 128);
+    uint32_t s = 0;
+    const uint32_t mw = up_to(sh.max_reads + 1, 4) + 8;
+    L.o_hdr = s;  s += 64;
+    L.o_q4 = s;   s += mw * 4;
+    L.o_sg = s;   s += mw * 4;
+    L.o_mt = s;   s += mw * 4;
+    L.o_sp = s;   s += (up_to(sh.max_segs, 4) + 8) * 4;
+    L.o_sl = s;   s += (up_to(sh.max_segs, 8) + 16) * 2;
+    L.o_exp = s;  s += TILE;
+    L.o_seq = s;  s += up_to(sh.chunk_q4, 16) + 32;
+    L.o_qual = s; s += 4 * up_to(sh.chunk_q4, 16) + 32;
+    L.stage_bytes = up_to(s, 128);
+    L.total = L.stage0 + PL_STAGES * L.stage_bytes;
+    return L;
+}
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
-    const Item it = items[blockIdx.x];
-    const int32_t p0 = (int32_t)(it.tile * TILE);
-    const SampleDev* __restrict__ sd = samples + it.sample;
+// explicit shared-window accesses (32-bit addresses) for the scatter loop
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void red_shared_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// barrier among the consumer warps only (the producer warp never joins it)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PL_CONSUMERS) : "memory"); }
 
-    if (tid == 0) { mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    for (int k = tid; k < 5 * TILE_QUADS; k += THREADS) s_cnt[k] = 0;
+// ---- producer: one chunk into the next stage of the ring (whole warp; lane 0 writes and issues)
+__device__ __forceinline__ void pileup_issue_chunk(uint8_t* smem, const PileupSmem& L, uint32_t& chunk_no, const SampleDev* __restrict__ sd,
+                                                   const uint8_t* __restrict__ expect, uint32_t item, uint32_t sample, uint32_t tile, uint32_t c0,
+                                                   uint32_t m, uint32_t q4_0, uint32_t nq4, uint32_t sg_0, uint32_t nseg, uint32_t flags)
+{
+    uint64_t* full = (uint64_t*)(smem + L.bar);
+    uint64_t* empty = full + PL_STAGES;
+    const uint32_t s = chunk_no % PL_STAGES, ph = (chunk_no / PL_STAGES) & 1u;
+    mbar_wait(empty + s, ph ^ 1u);
+    if ((threadIdx.x & 31) == 0) {
+        uint8_t* stage = smem + L.stage0 + s * L.stage_bytes;
+        ChunkHdr* h = (ChunkHdr*)(stage + L.o_hdr);
+        h->m = m; h->nq4 = nq4; h->q4_0 = q4_0; h->sg_0 = sg_0; h->nseg = nseg; h->c0 = c0;
+        h->item = item; h->sample = sample; h->tile = tile; h->flags = flags;
+        const uint32_t dm = c0 & 3u, ds = sg_0 & 3u, dl = sg_0 & 7u, dq = q4_0 & 3u, d16 = q4_0 & 15u;
+        const uint32_t b_q4 = up_to(dm + m + 1u, 4) * 4u, b_mt = up_to(dm + m, 4) * 4u;
+        const uint32_t b_sp = up_to(ds + nseg, 4) * 4u, b_sl = up_to(dl + nseg, 8) * 2u;
+        const uint32_t b_seq = up_to(d16 + nq4, 16), b_qual = up_to(dq + nq4, 4) * 4u;
+        fence_proxy_async();
+        mbar_expect_tx(full + s, 2u * b_q4 + b_mt + b_sp + b_sl + b_seq + b_qual + (uint32_t)TILE);
+        tma_load_1d(stage + L.o_q4, sd->q4_off + (c0 - dm), b_q4, full + s);
+        tma_load_1d(stage + L.o_sg, sd->seg_off + (c0 - dm), b_q4, full + s);
+        if (b_mt) tma_load_1d(stage + L.o_mt, sd->mate + (c0 - dm), b_mt, full + s);
+        if (b_sp) tma_load_1d(stage + L.o_sp, sd->seg_pos + (sg_0 - ds), b_sp, full + s);
+        if (b_sl) tma_load_1d(stage + L.o_sl, sd->seg_len + (sg_0 - dl), b_sl, full + s);
+        tma_load_1d(stage + L.o_exp, expect + (size_t)tile * TILE, TILE, full + s);
+        if (b_seq) tma_load_1d(stage + L.o_seq, sd->seq2 + (q4_0 - d16), b_seq, full + s);
+        if (b_qual) tma_load_1d(stage + L.o_qual, sd->qual + 4u * (size_t)(q4_0 - dq), b_qual, full + s);
+    }
+    __syncwarp();
+    ++chunk_no;
+}
 
-    // per letter and quad: 16-bit lanes, [0] = positions 0 and 2 of the quad, [1] = positions 1 and 3
-    uint32_t acc[QUADS_PER_THREAD][5][2];
-    #pragma unroll
-    for (int k = 0; k < QUADS_PER_THREAD; ++k)
-        #pragma unroll
-        for (int c = 0; c < 5; ++c) { acc[k][c][0] = 0; acc[k][c][1] = 0; }
-    uint32_t parity = 0;
-
-    for (uint32_t c0 = it.r_lo; c0 < it.r_hi;) {
-        // ---- 1. metadata of up to CHUNK_READS reads (+1 for the end offsets); the chunk takes the
-        // longest prefix within the quad and segment budgets (prefix sums: the predicate is monotone)
-        uint32_t n = it.r_hi - c0; if (n > CHUNK_READS) n = CHUNK_READS;
-        bool fits = false;
-        if (tid <= n) {
-            const uint32_t* q4p = sd->q4_off + c0; const uint32_t* sgp = sd->seg_off + c0;
-            const uint32_t q = __ldg(q4p + tid), g = __ldg(sgp + tid);
-            s_q4[tid] = q; s_sgo[tid] = g;
-            fits = tid >= 1 && q - __ldg(q4p) <= chunk_q4 && g - __ldg(sgp) <= CHUNK_SEGS;
-            if (tid < n) s_mate[tid] = __ldg(sd->mate + c0 + tid);
+__device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem& L, const PileupShape sh, const SampleDev* __restrict__ samples,
+                                                const Item* __restrict__ items, uint32_t n_items, const uint8_t* __restrict__ expect,
+                                                int* __restrict__ err_flag)
+{
+    const uint32_t lane = threadIdx.x & 31, G = gridDim.x;
+    uint32_t chunk_no = 0;
+    for (uint64_t base = blockIdx.x; base < n_items; base += 32ull * G) {
+        // ---- 32 upcoming items of this CTA, one per lane: item record and the offsets that size it
+        const uint64_t mine = base + (uint64_t)lane * G;
+        uint4 it = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t q_lo = 0, q_hi = 0, g_lo = 0, g_hi = 0;
+        if (mine < n_items) {
+            it = __ldg(reinterpret_cast<const uint4*>(items) + mine);
+            const SampleDev* sd = samples + it.x;
+            const uint32_t* q4p = sd->q4_off; const uint32_t* sgp = sd->seg_off;
+            q_lo = __ldg(q4p + it.z); q_hi = __ldg(q4p + it.w);
+            g_lo = __ldg(sgp + it.z); g_hi = __ldg(sgp + it.w);
         }
-        if (tid == 0) s_misc[0] = 0;
-        const uint32_t m = (uint32_t)__syncthreads_count(fits);
-        if (m == 0) {                       // a single read over the documented limits: host validation failed
-            if (tid == 0) atomicExch(err_flag, 1);
-            break;
-        }
-        const uint32_t q4_0 = s_q4[0], sg_0 = s_sgo[0], nq4 = s_q4[m] - q4_0;
-
-        // ---- 2. stage bases and qualities: two bulk copies from 16-byte aligned addresses at or
-        // below the first byte needed; d_* is the offset of that byte in the buffer
-        const uint8_t* g_seq = sd->seq2 + q4_0;
-        const uint8_t* g_qual = sd->qual + (size_t)q4_0 * 4;
-        const uint32_t d_seq = (uint32_t)((uintptr_t)g_seq & 15), d_qual = (uint32_t)((uintptr_t)g_qual & 15);
-        if (tid == 0) {
-            const uint32_t b_seq = (d_seq + nq4 + 15) & ~15u, b_qual = (d_qual + nq4 * 4 + 15) & ~15u;
-            fence_proxy_async();            // earlier generic-proxy accesses to these buffers are ordered before the copies
-            mbar_expect_tx(s_bar, b_seq + b_qual);
-            if (b_seq)  tma_load_1d(s_seq, g_seq - d_seq, b_seq, s_bar);
-            if (b_qual) tma_load_1d(s_qual, g_qual - d_qual, b_qual, s_bar);
-        }
-
-        // ---- 3. segment records while the copies are in flight: one thread per read
-        if (tid < m) {
-            const uint32_t k0 = s_sgo[tid] - sg_0, k1 = s_sgo[tid + 1] - sg_0;
-            uint32_t q = s_q4[tid] - q4_0;                        // first staged quad of the next segment
-            const uint32_t q_end = s_q4[tid + 1] - q4_0;
-            for (uint32_t k = k0; k < k1; ++k) {
-                const int32_t p = __ldg(sd->seg_pos + sg_0 + k);
-                const uint32_t len = __ldg(sd->seg_len + sg_0 + k);
-                const uint32_t a = (uint32_t)p & 3u, nq = (a + len + 3u) >> 2;
-                const int32_t jw = (p - (int32_t)a - p0) >> 2;    // tile-relative index of the segment's first quad (may be off the tile)
-                // (a segment whose quads run past the read's - inconsistent input, flagged below - gets length 0,
-                // which keeps it out of the overlap step and of the zeroing in step 4a)
-                s_seg[k] = make_uint4((uint32_t)p, q + nq <= q_end ? len : 0u, d_qual + q * 4u + a, (uint32_t)jw);
-                uint32_t e = q + nq; if (e > q_end) e = q_end;
-                {   // tag every quad with the low byte of its tile-relative index (TILE_QUADS == 256: a quad ON the tile
-                    // is tagged exactly; quads off the tile get their qualities zeroed in step 4 and may carry any tag):
-                    // bytes up to a word boundary, whole words of four consecutive tags, trailing bytes
-                    uint32_t g = q, t = (uint32_t)jw;
-                    for (; (g & 3u) && g < e; ++g, ++t) s_g2s[g] = (uint8_t)t;
-                    for (; g + 4u <= e; g += 4u, t += 4u) {
-                        const uint32_t t0 = t & 0xffu;
-                        if (t0 <= 252u) *reinterpret_cast<uint32_t*>(s_g2s + g) = t0 * 0x01010101u + 0x03020100u;
-                        else { s_g2s[g] = (uint8_t)t; s_g2s[g + 1] = (uint8_t)(t + 1); s_g2s[g + 2] = (uint8_t)(t + 2); s_g2s[g + 3] = (uint8_t)(t + 3); }
-                    }
-                    for (; g < e; ++g, ++t) s_g2s[g] = (uint8_t)t;
+        for (uint32_t k = 0; k < 32u; ++k) {
+            const uint64_t idx = base + (uint64_t)k * G;
+            if (idx >= n_items) break;
+            const uint32_t sample = __shfl_sync(0xffffffffu, it.x, k), tile = __shfl_sync(0xffffffffu, it.y, k);
+            const uint32_t r_lo = __shfl_sync(0xffffffffu, it.z, k), r_hi = __shfl_sync(0xffffffffu, it.w, k);
+            const uint32_t ql = __shfl_sync(0xffffffffu, q_lo, k), qh = __shfl_sync(0xffffffffu, q_hi, k);
+            const uint32_t gl = __shfl_sync(0xffffffffu, g_lo, k), gh = __shfl_sync(0xffffffffu, g_hi, k);
+            const SampleDev* sd = samples + sample;
+            const uint32_t n = r_hi - r_lo;
+            const uint32_t wide = item_is_wide(r_lo, r_hi) ? CHUNK_WIDE : 0u;
+            if (n <= sh.max_reads && qh - ql <= sh.chunk_q4 && gh - gl <= sh.max_segs) {
+                pileup_issue_chunk(smem, L, chunk_no, sd, expect, (uint32_t)idx, sample, tile, r_lo, n, ql, qh - ql, gl, gh - gl,
+                                   CHUNK_FIRST | CHUNK_LAST | wide);
+                continue;
+            }
+            // ---- the item needs several chunks: longest prefix of the remaining reads within the three limits
+            const uint32_t* q4p = sd->q4_off; const uint32_t* sgp = sd->seg_off;
+            uint32_t c0 = r_lo, qc = ql, gc = gl, first = CHUNK_FIRST;
+            while (c0 < r_hi) {
+                const uint32_t cap = min(sh.max_reads, r_hi - c0), step = (cap + 31u) / 32u;
+                const uint32_t pi = min((lane + 1u) * step, cap);
+                bool fit = __ldg(q4p + c0 + pi) - qc <= sh.chunk_q4 && __ldg(sgp + c0 + pi) - gc <= sh.max_segs;
+                const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, fit));
+                uint32_t m = cap;
+                if (cnt < 32u) {                     // lanes 0..cnt-1 fit, lane cnt does not: refine between the two probes
+                    const uint32_t b0 = cnt * step, pj = b0 + lane + 1u;
+                    fit = false;
+                    if (lane + 1u < step && pj <= cap) fit = __ldg(q4p + c0 + pj) - qc <= sh.chunk_q4 && __ldg(sgp + c0 + pj) - gc <= sh.max_segs;
+                    m = b0 + __popc(__ballot_sync(0xffffffffu, fit));
                 }
-                q += nq;
-            }
-            if (q != q_end) {                                     // offsets and segments disagree: refuse, stay in bounds
-                atomicExch(err_flag, 2);
-                for (uint32_t g = s_q4[tid] - q4_0; g < q_end; ++g) s_g2s[g] = 0;
-            }
-            const int32_t mt = s_mate[tid];
-            if (mt >= 0) {                                        // overlap task: once per pair when both mates are here
-                const bool mate_here = (uint32_t)mt >= c0 && (uint32_t)mt < c0 + m;
-                if (!mate_here || c0 + tid < (uint32_t)mt) s_pairs[atomicAdd(&s_misc[0], 1u)] = (uint16_t)tid;
+                if (m == 0) {                        // a single read over the documented limits: host validation failed
+                    if (lane == 0) atomicExch(err_flag, 1);
+                    pileup_issue_chunk(smem, L, chunk_no, sd, expect, (uint32_t)idx, sample, tile, c0, 0u, qc, 0u, gc, 0u, first | CHUNK_LAST | wide);
+                    break;
+                }
+                const uint32_t qn = __ldg(q4p + c0 + m), gn = __ldg(sgp + c0 + m);
+                pileup_issue_chunk(smem, L, chunk_no, sd, expect, (uint32_t)idx, sample, tile, c0, m, qc, qn - qc, gc, gn - gc,
+                                   first | (c0 + m == r_hi ? CHUNK_LAST : 0u) | wide);
+                c0 += m; qc = qn; gc = gn; first = 0u;
             }
         }
-        if (tid == 0) mbar_wait(s_bar, parity);
-        parity ^= 1;
-        __syncthreads();                    // segments written, copies landed (thread 0 observed the barrier)
+    }
+    // ---- no more items: tell the consumers
+    uint64_t* full = (uint64_t*)(smem + L.bar);
+    uint64_t* empty = full + PL_STAGES;
+    const uint32_t s = chunk_no % PL_STAGES, ph = (chunk_no / PL_STAGES) & 1u;
+    mbar_wait(empty + s, ph ^ 1u);
+    if (lane == 0) {
+        ((ChunkHdr*)(smem + L.stage0 + s * L.stage_bytes + L.o_hdr))->flags = CHUNK_STOP;
+        mbar_arrive(full + s);
+    }
+}
 
-        // ---- 4a. quads off the tile (front of reads that start before it, tail of reads that run past it) must not
-        // count: their qualities are zeroed, which the scatter's threshold test then rejects like any poor base
-        if (tid < m) {
-            const uint32_t k0 = s_sgo[tid] - sg_0, k1 = s_sgo[tid + 1] - sg_0;
+__global__ void __launch_bounds__(PL_THREADS, 4)
+pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items, const PileupShape sh,
+              const uint8_t* __restrict__ expect, uint8_t* __restrict__ tiles /*[n_items][SLOT_BYTES]*/, int* __restrict__ err_flag)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const PileupSmem L = pileup_smem_layout(sh);
+    uint64_t* full = (uint64_t*)(smem + L.bar);
+    uint64_t* empty = full + PL_STAGES;
+    uint32_t* s_misc = (uint32_t*)(smem + L.misc);
+    uint32_t* s_cnt = (uint32_t*)(smem + L.cnt);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PL_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        s_misc[0] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (uint32_t k = threadIdx.x; k < (uint32_t)(N_PLANES * TILE_QUADS); k += PL_THREADS) s_cnt[k] = 0;
+    __syncthreads();
+
+    if (threadIdx.x >= PL_CONSUMERS) {
+        pileup_producer(smem, L, sh, samples, items, n_items, expect, err_flag);
+        return;
+    }
+
+    // ------------------------------------------------------------------------------------ consumers
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    uint4* s_seg = (uint4*)(smem + L.seg);
+    uint16_t* s_pairs = (uint16_t*)(smem + L.pairs);
+    uint8_t* s_tags = smem + L.tags;
+    // wide items: per plane and owned quad (2 * tid, 2 * tid + 1), 16-bit lanes: [0] = positions 0 and 2, [1] = positions 1 and 3
+    uint32_t acc[N_PLANES][2][2];
+    #pragma unroll
+    for (int c = 0; c < N_PLANES; ++c) { acc[c][0][0] = acc[c][0][1] = acc[c][1][0] = acc[c][1][1] = 0; }
+
+    for (uint32_t chunk_no = 0;; ++chunk_no) {
+        const uint32_t st = chunk_no % PL_STAGES, ph = (chunk_no / PL_STAGES) & 1u;
+        uint8_t* stage = smem + L.stage0 + st * L.stage_bytes;
+        mbar_wait(full + st, ph);
+        const ChunkHdr* h = (const ChunkHdr*)(stage + L.o_hdr);
+        const uint32_t flags = h->flags;
+        if (flags & CHUNK_STOP) break;
+        const uint32_t m = h->m, nq4 = h->nq4, q4_0 = h->q4_0, sg_0 = h->sg_0, nseg = h->nseg, c0 = h->c0, item = h->item;
+        const int32_t p0 = (int32_t)(h->tile * TILE);
+        const SampleDev* __restrict__ sd = samples + h->sample;
+        const uint32_t dm = c0 & 3u, dq = q4_0 & 3u, c12 = q4_0 & 12u;
+        const uint32_t* s_q4 = (const uint32_t*)(stage + L.o_q4) + dm;          // s_q4[t] = q4_off[c0 + t], t <= m
+        const uint32_t* s_sgo = (const uint32_t*)(stage + L.o_sg) + dm;
+        const int32_t* s_mate = (const int32_t*)(stage + L.o_mt) + dm;
+        const int32_t* s_sp = (const int32_t*)(stage + L.o_sp) + (sg_0 & 3u);   // s_sp[k] = seg_pos[sg_0 + k], k < nseg
+        const uint16_t* s_sl = (const uint16_t*)(stage + L.o_sl) + (sg_0 & 7u);
+        uint8_t* s_seq = stage + L.o_seq + c12;                                 // s_seq[B]: bases of buffer quad B
+        uint8_t* s_qual = stage + L.o_qual;                                     // qualities of buffer quad B at byte 4 * B
+        uint32_t* s_qw = (uint32_t*)s_qual;
+        const uint32_t nbq = dq + nq4, ngroups = (nbq + 3u) >> 2;               // staged quad g is buffer quad g + dq
+
+        // ---- 1. one thread per read: segment geometry, tags of the quads on the tile, zeroed qualities off it
+        for (uint32_t t = tid; t < m; t += PL_CONSUMERS) {
+            const uint32_t k0 = s_sgo[t] - sg_0, k1 = s_sgo[t + 1] - sg_0;
+            uint32_t B = s_q4[t] - q4_0 + dq;                                   // first buffer quad of the next segment
+            const uint32_t B_end = s_q4[t + 1] - q4_0 + dq;
+            if (k1 < k0 || k1 > nseg || B_end < B || B_end > nbq) { atomicExch(err_flag, 2); continue; }   // offsets not prefix sums
             for (uint32_t k = k0; k < k1; ++k) {
-                const uint4 sg = s_seg[k];
-                if (!sg.y) continue;
-                const int32_t jw = (int32_t)sg.w;
-                const uint32_t a = sg.x & 3u;
-                const int32_t nq = (int32_t)((a + sg.y + 3u) >> 2);
-                if (jw >= 0 && jw + nq <= TILE_QUADS) continue;                    // wholly on the tile: the common case
-                uint32_t* qw = reinterpret_cast<uint32_t*>(s_qual + (sg.z - a));    // the segment's first quad
-                const int32_t lead = min(max(-jw, 0), nq), tail = min(max(TILE_QUADS - jw, 0), nq);
-                for (int32_t i = 0; i < lead; ++i) qw[i] = 0;
-                for (int32_t i = tail; i < nq; ++i) qw[i] = 0;
+                const int32_t p = s_sp[k];
+                const uint32_t len = s_sl[k];
+                const uint32_t a = (uint32_t)p & 3u;
+                const int32_t nq = (int32_t)((a + len + 3u) >> 2);
+                const int32_t jw = (p - (int32_t)a - p0) >> 2;                  // tile-relative index of the segment's first quad
+                if (B + (uint32_t)nq > B_end) {                                 // segments and offsets disagree: refuse, stay in bounds
+                    atomicExch(err_flag, 2);
+                    for (uint32_t kk = k; kk < k1; ++kk) s_seg[kk] = make_uint4(0u, 0u, 0u, 0u);
+                    for (uint32_t g = B; g < B_end; ++g) s_qw[g] = 0;
+                    B = B_end;
+                    break;
+                }
+                s_seg[k] = make_uint4((uint32_t)p, len, 4u * B + a, (uint32_t)jw);
+                int32_t i_lo = jw < 0 ? -jw : 0; if (i_lo > nq) i_lo = nq;
+                int32_t i_hi = TILE_QUADS - jw; if (i_hi > nq) i_hi = nq; if (i_hi < i_lo) i_hi = i_lo;
+                for (int32_t i = 0; i < i_lo; ++i) s_qw[B + i] = 0;
+                for (int32_t i = i_hi; i < nq; ++i) s_qw[B + i] = 0;
+                uint32_t g = B + (uint32_t)i_lo, tv = (uint32_t)(jw + i_lo);
+                const uint32_t e = B + (uint32_t)i_hi;                          // tags tv .. tv + (e - g) - 1 are within 0..255
+                for (; (g & 3u) && g < e; ++g, ++tv) s_tags[g] = (uint8_t)tv;
+                for (; g + 4u <= e; g += 4u, tv += 4u) *reinterpret_cast<uint32_t*>(s_tags + g) = tv * 0x01010101u + 0x03020100u;
+                for (; g < e; ++g, ++tv) s_tags[g] = (uint8_t)tv;
+                B += (uint32_t)nq;
+            }
+            if (B != B_end) {                                                   // quads no segment owns: keep them out of the counts
+                atomicExch(err_flag, 2);
+                for (uint32_t g = B; g < B_end; ++g) s_qw[g] = 0;
+            }
+            const int32_t mt = s_mate[t];
+            if (mt >= 0) {                                                      // overlap task: once per pair when both mates are here
+                const bool mate_here = (uint32_t)mt >= c0 && (uint32_t)mt < c0 + m;
+                if (!mate_here || c0 + t < (uint32_t)mt) s_pairs[atomicAdd(&s_misc[0], 1u)] = (uint16_t)t;
             }
         }
+        if (tid == PL_CONSUMERS - 1) {                                          // elements in front of and behind the chunk in the buffer
+            for (uint32_t g = 0; g < dq; ++g) s_qw[g] = 0;
+            for (uint32_t g = nbq; g < 4u * ngroups; ++g) s_qw[g] = 0;
+        }
+        consumer_sync();
 
-        // ---- 4. mate-overlap quality correction, restricted to this tile's positions (other tiles
-        // are counted by other CTAs). Pairs with both mates in the chunk: both are rewritten from
-        // pristine values. Mates outside the chunk (only when a tile needs several chunks): this read
-        // alone is rewritten, the mate's pristine data come from global memory.
+        // ---- 2. mate-overlap quality correction, restricted to this tile's positions (other tiles are counted by other
+        // items). Pairs with both mates in the chunk: both are rewritten from pristine values. Mates outside the chunk (only
+        // when a tile needs several chunks): this read alone is rewritten, the mate's pristine data come from global memory.
         const uint32_t n_tasks = s_misc[0];
         if (n_tasks) {
-            // eight lanes per task (four tasks per warp): the work per pair is a few dozen shared-memory
-            // bytes -- a whole warp per pair wastes ~200 instructions on set-up, one thread per pair
-            // serialises ~50 dependent read-modify-writes
-            const uint32_t l8 = lane & 7u;
-            for (uint32_t t = tid >> 3; t < n_tasks; t += THREADS / 8) {
+            // eight lanes per task (four tasks per warp). Two segment combinations of one pair can touch the same quality
+            // word (segments of one mate that are adjacent inside a segment of the other): the group's lanes re-converge
+            // between combinations.
+            const uint32_t l8 = lane & 7u, gmask = 0xffu << (lane & 24u);
+            for (uint32_t t = tid >> 3; t < n_tasks; t += PL_CONSUMERS / 8) {
                 const uint32_t i = s_pairs[t];
                 const int32_t mt = s_mate[i];
                 const bool self_is_a = c0 + i < (uint32_t)mt;
@@ -489,22 +652,23 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                     for (uint32_t ka = sa0; ka < sa1; ++ka) {
                         const uint4 A = s_seg[ka];
                         for (uint32_t kb = sb0; kb < sb1; ++kb) {
-                            const uint4 B = s_seg[kb];
-                            const int32_t lo = max(max((int32_t)A.x, (int32_t)B.x), p0);
-                            const int32_t hi = min(min((int32_t)(A.x + A.y), (int32_t)(B.x + B.y)), p0 + TILE);
-                            if (lo >= hi) continue;
-                            // four positions per lane and step: both mates are stored position-aligned, so the
-                            // quads of the common range line up word for word
-                            const uint32_t za0 = A.z - (A.x & 3u) - 4u * (A.x >> 2), zb0 = B.z - (B.x & 3u) - 4u * (B.x >> 2);
-                            for (int32_t P = (lo >> 2) + (int32_t)l8; P < ((hi + 3) >> 2); P += 8) {
-                                const uint32_t za = za0 + 4u * (uint32_t)P, zb = zb0 + 4u * (uint32_t)P;   // byte index of the quad in s_qual
-                                const uint32_t va = *reinterpret_cast<const uint32_t*>(s_qual + za), vb = *reinterpret_cast<const uint32_t*>(s_qual + zb);
-                                const uint32_t xa = msnv_spread_bases(s_seq[d_seq + ((za - d_qual) >> 2)]);
-                                const uint32_t xb = msnv_spread_bases(s_seq[d_seq + ((zb - d_qual) >> 2)]);
-                                uint32_t na, nb;
-                                msnv_overlap_rule4(va, vb, xa, xb, msnv_quad_mask(P << 2, lo, hi), na, nb);
-                                *reinterpret_cast<uint32_t*>(s_qual + za) = na; *reinterpret_cast<uint32_t*>(s_qual + zb) = nb;
+                            const uint4 Bs = s_seg[kb];
+                            const int32_t lo = max(max((int32_t)A.x, (int32_t)Bs.x), p0);
+                            const int32_t hi = min(min((int32_t)(A.x + A.y), (int32_t)(Bs.x + Bs.y)), p0 + TILE);
+                            if (lo < hi) {
+                                // four positions per lane and step: both mates are stored position-aligned, so the quads of the
+                                // common range line up word for word
+                                const uint32_t za0 = A.z - (A.x & 3u) - 4u * (A.x >> 2), zb0 = Bs.z - (Bs.x & 3u) - 4u * (Bs.x >> 2);
+                                for (int32_t P = (lo >> 2) + (int32_t)l8; P < ((hi + 3) >> 2); P += 8) {
+                                    const uint32_t za = za0 + 4u * (uint32_t)P, zb = zb0 + 4u * (uint32_t)P;   // byte index of the quad in s_qual
+                                    const uint32_t va = *reinterpret_cast<const uint32_t*>(s_qual + za), vb = *reinterpret_cast<const uint32_t*>(s_qual + zb);
+                                    const uint32_t xa = msnv_spread_bases(s_seq[za >> 2]), xb = msnv_spread_bases(s_seq[zb >> 2]);
+                                    uint32_t na, nb;
+                                    msnv_overlap_rule4(va, vb, xa, xb, msnv_quad_mask(P << 2, lo, hi), na, nb);
+                                    *reinterpret_cast<uint32_t*>(s_qual + za) = na; *reinterpret_cast<uint32_t*>(s_qual + zb) = nb;
+                                }
                             }
+                            __syncwarp(gmask);
                         }
                     }
                 } else {
@@ -520,87 +684,107 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                             const uint4 A = s_seg[ka];
                             const int32_t lo = max(max((int32_t)A.x, bx), p0);
                             const int32_t hi = min(min((int32_t)(A.x + A.y), bx + (int32_t)bl), p0 + TILE);
-                            if (lo >= hi) continue;
-                            const uint32_t zs0 = A.z - (A.x & 3u) - 4u * (A.x >> 2);
-                            for (int32_t P = (lo >> 2) + (int32_t)l8; P < ((hi + 3) >> 2); P += 8) {
-                                const uint32_t zs = zs0 + 4u * (uint32_t)P, im = (uint32_t)(P - (bx >> 2));   // the mate's quad index
-                                const uint32_t vs = *reinterpret_cast<const uint32_t*>(s_qual + zs), vm = __ldg(mqual4 + im);
-                                const uint32_t xs = msnv_spread_bases(s_seq[d_seq + ((zs - d_qual) >> 2)]), xm = msnv_spread_bases(__ldg(mseq + im));
-                                const uint32_t msk = msnv_quad_mask(P << 2, lo, hi);
-                                uint32_t na, nb;
-                                if (self_is_a) msnv_overlap_rule4(vs, vm, xs, xm, msk, na, nb); else msnv_overlap_rule4(vm, vs, xm, xs, msk, nb, na);
-                                *reinterpret_cast<uint32_t*>(s_qual + zs) = na;
+                            if (lo < hi) {
+                                const uint32_t zs0 = A.z - (A.x & 3u) - 4u * (A.x >> 2);
+                                for (int32_t P = (lo >> 2) + (int32_t)l8; P < ((hi + 3) >> 2); P += 8) {
+                                    const uint32_t zs = zs0 + 4u * (uint32_t)P, im = (uint32_t)(P - (bx >> 2));   // the mate's quad index
+                                    const uint32_t vs = *reinterpret_cast<const uint32_t*>(s_qual + zs), vm = __ldg(mqual4 + im);
+                                    const uint32_t xs = msnv_spread_bases(s_seq[zs >> 2]), xm = msnv_spread_bases(__ldg(mseq + im));
+                                    const uint32_t msk = msnv_quad_mask(P << 2, lo, hi);
+                                    uint32_t na, nb;
+                                    if (self_is_a) msnv_overlap_rule4(vs, vm, xs, xm, msk, na, nb); else msnv_overlap_rule4(vm, vs, xm, xs, msk, nb, na);
+                                    *reinterpret_cast<uint32_t*>(s_qual + zs) = na;
+                                }
                             }
+                            __syncwarp(gmask);
                         }
                         mq += (ba0 + bl + 3u) >> 2;
                     }
                 }
             }
+            consumer_sync();                // qualities are final
+            if (tid == 0) s_misc[0] = 0;    // every thread has read the count; the next chunk queues after one more barrier
         }
-        __syncthreads();                    // qualities are final (steps 4a and 4 wrote disjoint quads)
 
-        // ---- 5. flat scatter over the staged quads
+        // ---- 3. scatter: four consecutive buffer quads per thread and step
         {
-            const uint32_t a_q = smem_u32(s_qual) + d_qual;               // d_qual is a multiple of 4
-            const uint32_t a_s = smem_u32(s_seq) + d_seq, a_g = smem_u32(s_g2s);
-            const uint32_t a_c = smem_u32(s_cnt);
-            for (uint32_t g = tid; g < nq4; g += THREADS) {
-                const uint32_t q = lds_u32(a_q + g * 4u);
-                uint32_t x = lds_u8(a_s + g);
-                const uint32_t j = lds_u8(a_g + g);                           // tile-relative quad
-                x = (x * 4097u) & 0x000f000fu;                                // two 2-bit pairs per half word
-                x = (x * 65u) & 0x03030303u;                                  // one base per byte lane
-                const uint32_t v = (q & 0x7f7f7f7fu) + 0x73737373u;           // bit 7 of a lane: quality >= 13
-                const uint32_t ok = ((v & ~q) >> 7) & 0x01010101u;            // ... and the base is A/C/G/T
-                const uint32_t hi = x >> 1;
-                const uint32_t a = a_c + j * 4u;
-                red_shared_add<0>(a, ok & ~x & ~hi);
-                red_shared_add<TILE>(a, ok & x & ~hi);
-                red_shared_add<2 * TILE>(a, ok & ~x & hi);
-                red_shared_add<3 * TILE>(a, ok & x & hi);
-                const uint32_t nn = v & q & 0x80808080u;                      // rare: counted non-ACGT bases
-                if (nn) red_shared_add<4 * TILE>(a, nn >> 7);
-            }
-        }
-        __syncthreads();
-
-        // ---- 6. fold this chunk's byte lanes (a position sees at most m <= 255 reads per chunk)
-        #pragma unroll
-        for (int k = 0; k < QUADS_PER_THREAD; ++k) {
-            #pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                const uint32_t slot = c * TILE_QUADS + k * THREADS + tid;
-                const uint32_t w = s_cnt[slot];
-                if (w) {
-                    s_cnt[slot] = 0;
-                    acc[k][c][0] += w & 0x00ff00ffu;
-                    acc[k][c][1] += (w >> 8) & 0x00ff00ffu;
+            const uint32_t a_q = smem_u32(s_qual), a_s = smem_u32(s_seq), a_g = smem_u32(s_tags);
+            const uint32_t a_c = smem_u32(s_cnt), a_e = smem_u32(stage + L.o_exp);
+            for (uint32_t u = tid; u < ngroups; u += PL_CONSUMERS) {
+                const uint4 qv = lds_v4(a_q + 16u * u);
+                const uint32_t sw = lds_u32(a_s + 4u * u), tw = lds_u32(a_g + 4u * u);
+                const uint32_t qa[4] = {qv.x, qv.y, qv.z, qv.w};
+                uint32_t xs[4], mm[4], ac[4], nn_any = 0, mm_any = 0;
+                #pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t q = qa[k];
+                    const uint32_t j = __byte_perm(tw, 0u, 0x4440u + k);                // tile-relative quad
+                    ac[k] = a_c + 4u * j;                                               // its word in plane D
+                    xs[k] = msnv_spread_bases(__byte_perm(sw, 0u, 0x4440u + k));        // one 2-bit base per byte lane
+                    const uint32_t v = (q & 0x7f7f7f7fu) + 0x73737373u;                 // bit 7 of a lane: quality >= 13
+                    const uint32_t ok = (v & ~q & 0x80808080u) >> 7;                    // ... and the base is A/C/G/T
+                    const uint32_t d = xs[k] ^ lds_u32(a_e + 4u * j);                   // differs from the expected letter?
+                    red_shared_add(ac[k], ok);
+                    mm[k] = (d | (d >> 1)) & ok;
+                    mm_any |= mm[k];
+                    nn_any |= v & q;
+                }
+                if (mm_any) {                                                           // counted bases that are not the expected letter:
+                    #pragma unroll                                                      // only the lanes that hold one loop over their set bits
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t r = mm[k];
+                        while (r) {
+                            const uint32_t b = (uint32_t)__ffs((int)r) - 1u;            // 0, 8, 16 or 24
+                            red_shared_add(ac[k] + (PLANE_A + ((xs[k] >> b) & 3u)) * (uint32_t)TILE, 1u << b);
+                            r &= r - 1u;
+                        }
+                    }
+                }
+                if (nn_any & 0x80808080u) {                                             // rare: counted non-ACGT bases
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t q = qa[k];
+                        const uint32_t nn = ((q & 0x7f7f7f7fu) + 0x73737373u) & q & 0x80808080u;
+                        if (nn) red_shared_add(ac[k] + PLANE_N * (uint32_t)TILE, nn >> 7);
+                    }
                 }
             }
         }
-        c0 += m;
-        // no barrier here: the next chunk only touches the counters again after two more barriers
-    }
+        fence_proxy_async();                // this thread's writes to the stage are ordered before the copies that refill it
+        consumer_sync();
+        if (tid == 0) mbar_arrive(empty + st);
 
-    // ---- 7. flush: 8 B + 2 B per position; a thread owns four consecutive positions
-    #pragma unroll
-    for (int k = 0; k < QUADS_PER_THREAD; ++k) {
-        const size_t o = (size_t)blockIdx.x * TILE + 4u * (k * THREADS + tid);
-        uint32_t w[4][2], nw[2];
-        #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            // position i of the quad sits in lane (i >> 1) of acc[..][i & 1]
-            const uint32_t sh = 16u * (uint32_t)(i >> 1);
-            const uint32_t A = (acc[k][0][i & 1] >> sh) & 0xffffu, C = (acc[k][1][i & 1] >> sh) & 0xffffu;
-            const uint32_t G = (acc[k][2][i & 1] >> sh) & 0xffffu, T = (acc[k][3][i & 1] >> sh) & 0xffffu;
-            w[i][0] = A | C << 16; w[i][1] = G | T << 16;
+        // ---- 4. counts of the chunk
+        if (flags & CHUNK_WIDE) {
+            uint2* cnt2 = reinterpret_cast<uint2*>(s_cnt);
+            #pragma unroll
+            for (int c = 0; c < N_PLANES; ++c) {
+                const uint2 w = cnt2[c * (TILE_QUADS / 2) + tid];
+                cnt2[c * (TILE_QUADS / 2) + tid] = make_uint2(0u, 0u);
+                acc[c][0][0] += w.x & 0x00ff00ffu; acc[c][0][1] += (w.x >> 8) & 0x00ff00ffu;
+                acc[c][1][0] += w.y & 0x00ff00ffu; acc[c][1][1] += (w.y >> 8) & 0x00ff00ffu;
+            }
+            if (flags & CHUNK_LAST) {
+                uint4* dst = reinterpret_cast<uint4*>(tiles + (size_t)item * SLOT_BYTES);
+                #pragma unroll
+                for (int c = 0; c < N_PLANES; ++c) {
+                    // 16-bit plane c, positions 8 * tid .. 8 * tid + 7
+                    dst[c * (TILE / 8) + tid] = make_uint4((acc[c][0][0] & 0xffffu) | (acc[c][0][1] << 16), (acc[c][0][0] >> 16) | (acc[c][0][1] & 0xffff0000u),
+                                                           (acc[c][1][0] & 0xffffu) | (acc[c][1][1] << 16), (acc[c][1][0] >> 16) | (acc[c][1][1] & 0xffff0000u));
+                    acc[c][0][0] = acc[c][0][1] = acc[c][1][0] = acc[c][1][1] = 0;
+                }
+            }
+        } else if (flags & CHUNK_LAST) {
+            uint4* cnt4 = reinterpret_cast<uint4*>(s_cnt);
+            uint4* dst = reinterpret_cast<uint4*>(tiles + (size_t)item * SLOT_BYTES);
+            #pragma unroll
+            for (int i = 0; i < N_PLANES * TILE / 16 / PL_CONSUMERS; ++i) {
+                const uint4 w = cnt4[i * PL_CONSUMERS + tid];
+                cnt4[i * PL_CONSUMERS + tid] = make_uint4(0u, 0u, 0u, 0u);
+                dst[i * PL_CONSUMERS + tid] = w;
+            }
         }
-        nw[0] = ((acc[k][4][0]) & 0xffffu) | (acc[k][4][1] & 0xffffu) << 16;
-        nw[1] = (acc[k][4][0] >> 16) | (acc[k][4][1] >> 16) << 16;
-        uint4* dst = reinterpret_cast<uint4*>(acgt + o);
-        dst[0] = make_uint4(w[0][0], w[0][1], w[1][0], w[1][1]);
-        dst[1] = make_uint4(w[2][0], w[2][1], w[3][0], w[3][1]);
-        *reinterpret_cast<uint2*>(ncnt + o) = make_uint2(nw[0], nw[1]);
+        // no barrier here: the next chunk touches the counters again only after its own barriers
     }
 }
 
@@ -626,78 +810,164 @@ __device__ __forceinline__ uint32_t ref_channel(uint32_t c)
     }
 }
 
-__global__ void __launch_bounds__(TILE, 2048 / TILE)
-call_kernel(const uint64_t* __restrict__ acgt, const uint16_t* __restrict__ ncnt, const uint32_t* __restrict__ tile_begin,
-            const uint8_t* __restrict__ ref, CallParamsDev prm, int text_mode, uint8_t* __restrict__ flags,
-            uint32_t* __restrict__ tile_hits)
+// Per-position verdict from the population sums of a position (call_vC.cpp:545-601).
+//   sum[a]   population count of letter a (A,C,G,T), extra = what else counts as coverage (N bases under an N-like
+//   reference; the '.'/',' matches in text mode), any = bit a set when some sample has count[a] >= thr
+// Returns the flag byte: low nibble population mask, high nibble individual mask.
+__device__ __forceinline__ uint32_t call_position(uint32_t rc, uint32_t ch, const uint32_t sum[4], uint32_t extra, uint32_t any,
+                                                  const CallParamsDev& prm)
 {
-    __shared__ uint32_t s_warp[33];
-    const uint32_t t = blockIdx.x, tid = threadIdx.x;
-    const uint32_t i0 = tile_begin[t], i1 = tile_begin[t + 1];
-    const size_t p = (size_t)t * TILE + tid;
     const int32_t thr = prm.thr;
-    // any: bit a set when some sample has count[a] >= thr (samples without reads count 0, which only
-    // matters for the degenerate thr <= 0)
-    uint32_t sum[4] = {0, 0, 0, 0}, sum_n = 0, any = thr <= 0 ? 15u : 0u;
-    uint32_t i = i0;
-    for (; i + 4 <= i1; i += 4) {                              // 4 independent loads in flight per thread
-        uint64_t w[4]; uint32_t nn[4];
-        #pragma unroll
-        for (int u = 0; u < 4; ++u) { w[u] = __ldg(acgt + (size_t)(i + u) * TILE + tid); nn[u] = __ldg(ncnt + (size_t)(i + u) * TILE + tid); }
-        #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const uint32_t c = (uint32_t)(w[u] >> (16 * a)) & 0xffffu;
-                sum[a] += c;
-                any |= ((int32_t)c >= thr ? 1u : 0u) << a;
-            }
-            sum_n += nn[u];
-        }
-    }
-    for (; i < i1; ++i) {
-        const uint64_t w = __ldg(acgt + (size_t)i * TILE + tid);
+    uint32_t flag = 0;
+    const int64_t cov = (int64_t)sum[0] + sum[1] + sum[2] + sum[3] + extra;
+    int64_t nonref = 0;
+    #pragma unroll
+    for (int a = 0; a < 4; ++a) if ((uint32_t)a != ch) nonref += sum[a];
+    // call_vC.cpp:547-552
+    if (cov >= prm.min_cov && nonref >= thr) {
+        const double lim = __dmul_rn((double)cov, prm.frac);       // cov*calling_min_fraction, no FMA contraction
         #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            const uint32_t c = (uint32_t)(w >> (16 * a)) & 0xffffu;
-            sum[a] += c;
-            any |= ((int32_t)c >= thr ? 1u : 0u) << a;
+            // call_vC.cpp:580: the allele is skipped only when the reference character is its lower-case letter
+            const uint32_t lower = a == 0 ? 'a' : a == 1 ? 'c' : a == 2 ? 'g' : 't';
+            if (rc == lower) continue;
+            const int64_t n = ((uint32_t)a == ch) ? 0 : (int64_t)sum[a];
+            if (n >= thr && (double)n >= lim) flag |= 1u << a;                       // population variant
+            else {
+                const bool indiv = ((uint32_t)a == ch) ? (0 >= thr) : ((any >> a) & 1u);
+                if (indiv) flag |= 16u << a;                                         // individual variant
+            }
         }
-        sum_n += __ldg(ncnt + (size_t)i * TILE + tid);
     }
-    uint32_t flag = 0;
-    const uint32_t rc = ref[p];
-    if (rc != 0 && i1 > i0) {
-        // text mode (counts parsed from mpileup text): letters are never the reference's own base and the
-        // fifth plane holds the '.'/',' matches, so nothing is masked (call_vC.cpp:545,550,583-584)
-        const uint32_t ch = text_mode ? 6u : ref_channel(rc);
-        const int64_t cov = (int64_t)sum[0] + sum[1] + sum[2] + sum[3] + ((ch == 4 || text_mode) ? sum_n : 0);
-        int64_t nonref = 0;
+    return flag;
+}
+
+// ------------------------------------------------------------------------------------------------
+// call: one CTA per tile, one thread per quad of four positions. Sums the count planes of the
+// tile's items over the samples (byte lanes -> 16-bit lanes -> 32 bits), tracks per letter whether
+// some sample reaches the threshold, and applies snpCall's tests (call_vC.cpp:545-601).
+// Output: one flag byte per position (low nibble: population mask, high nibble: individual mask,
+// allele order A,C,G,T) and the number of flagged positions of the tile.
+// HI_THR: the calling threshold lies in 129..255 (the byte-lane ">= thr" test needs a different
+// combination); thresholds above 255 can only be met by wide items, which are compared as integers.
+// ------------------------------------------------------------------------------------------------
+constexpr int CALL_THREADS = TILE_QUADS;
+
+template <bool HI_THR>
+__global__ void __launch_bounds__(CALL_THREADS)
+call_kernel(const uint8_t* __restrict__ tiles, const Item* __restrict__ items, const uint32_t* __restrict__ tile_begin,
+            const uint8_t* __restrict__ ref, const uint8_t* __restrict__ expect, CallParamsDev prm, int text_mode,
+            uint8_t* __restrict__ flags, uint32_t* __restrict__ tile_hits)
+{
+    __shared__ uint32_t s_hits;
+    const uint32_t t = blockIdx.x, tid = threadIdx.x;
+    const uint32_t i0 = tile_begin[t], i1 = tile_begin[t + 1];
+    const int32_t thr = prm.thr;
+    if (tid == 0) s_hits = 0;
+    // byte-lane test "lane >= thr": bit 7 of ((x & 0x7f) + tb) combined with bit 7 of x (OR for thr <= 128, AND above)
+    const uint32_t tb = (HI_THR ? (thr <= 255 ? 256u - (uint32_t)thr : 0u) : (thr >= 1 ? 128u - (uint32_t)thr : 0u)) * 0x01010101u;
+    uint32_t s32[N_PLANES][4];
+    #pragma unroll
+    for (int c = 0; c < N_PLANES; ++c) { s32[c][0] = s32[c][1] = s32[c][2] = s32[c][3] = 0; }
+    uint32_t any7[5] = {0, 0, 0, 0, 0};            // bit 7 of lane p: some sample has >= thr of A, C, G, T, expected letter at position p
+    const size_t lane_off = 4u * (size_t)tid;
+
+    for (uint32_t i = i0; i < i1;) {
+        const uint32_t blk_end = min(i1, i + 256u);   // 16-bit lanes hold the sums of 256 narrow items
+        uint32_t s16[N_PLANES][2];
         #pragma unroll
-        for (int a = 0; a < 4; ++a) if ((uint32_t)a != ch) nonref += sum[a];
-        // call_vC.cpp:547-552. (int) casts mirror the reference's `int cov`.
-        if (cov >= prm.min_cov && nonref >= thr) {
-            const double lim = __dmul_rn((double)cov, prm.frac);       // cov*calling_min_fraction, no FMA contraction
+        for (int c = 0; c < N_PLANES; ++c) { s16[c][0] = s16[c][1] = 0; }
+        for (; i < blk_end; i += 4) {
+            uint4 it[4]; uint32_t w[4][N_PLANES];
             #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                // call_vC.cpp:580: the allele is skipped only when the reference character is its lower-case letter
-                const uint32_t lower = a == 0 ? 'a' : a == 1 ? 'c' : a == 2 ? 'g' : 't';
-                if (rc == lower) continue;
-                const int64_t n = ((uint32_t)a == ch) ? 0 : (int64_t)sum[a];
-                if (n >= thr && (double)n >= lim) flag |= 1u << a;                       // population variant
-                else {
-                    const bool indiv = ((uint32_t)a == ch) ? (0 >= thr) : ((any >> a) & 1u);
-                    if (indiv) flag |= 16u << a;                                         // individual variant
+            for (int u = 0; u < 4; ++u)
+                it[u] = i + u < blk_end ? __ldg(reinterpret_cast<const uint4*>(items) + (i + u)) : make_uint4(0u, 0u, 0u, 0u);
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool live = i + u < blk_end && !item_is_wide(it[u].z, it[u].w);
+                const uint8_t* base = tiles + (size_t)(i + u) * SLOT_BYTES + lane_off;
+                #pragma unroll
+                for (int c = 0; c < N_PLANES; ++c) w[u][c] = live ? __ldg(reinterpret_cast<const uint32_t*>(base + c * TILE)) : 0u;
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t R = w[u][0] - (w[u][1] + w[u][2] + w[u][3] + w[u][4]);     // lane-wise: D >= A + C + G + T
+                #pragma unroll
+                for (int a = 0; a < 5; ++a) {
+                    const uint32_t x = a < 4 ? w[u][1 + a] : R;
+                    const uint32_t g = (x & 0x7f7f7f7fu) + tb;
+                    any7[a] |= HI_THR ? (g & x) : (g | x);
+                }
+                #pragma unroll
+                for (int c = 0; c < N_PLANES; ++c) { s16[c][0] += w[u][c] & 0x00ff00ffu; s16[c][1] += (w[u][c] >> 8) & 0x00ff00ffu; }
+                if (i + u < blk_end && item_is_wide(it[u].z, it[u].w)) {                  // deep coverage: 16-bit planes, compared as integers
+                    const uint8_t* base = tiles + (size_t)(i + u) * SLOT_BYTES + 2u * lane_off;
+                    uint32_t v[N_PLANES][4];
+                    #pragma unroll
+                    for (int c = 0; c < N_PLANES; ++c) {
+                        const uint2 ww = __ldg(reinterpret_cast<const uint2*>(base + c * 2 * TILE));
+                        v[c][0] = ww.x & 0xffffu; v[c][1] = ww.x >> 16; v[c][2] = ww.y & 0xffffu; v[c][3] = ww.y >> 16;
+                    }
+                    #pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const uint32_t Rp = v[0][p] - (v[1][p] + v[2][p] + v[3][p] + v[4][p]);
+                        #pragma unroll
+                        for (int a = 0; a < 5; ++a) {
+                            const uint32_t x = a < 4 ? v[1 + a][p] : Rp;
+                            if ((int64_t)x >= (int64_t)thr) any7[a] |= 0x80u << (8 * p);
+                        }
+                        #pragma unroll
+                        for (int c = 0; c < N_PLANES; ++c) s32[c][p] += v[c][p];
+                    }
                 }
             }
         }
+        i = blk_end;
+        #pragma unroll
+        for (int c = 0; c < N_PLANES; ++c) {
+            s32[c][0] += s16[c][0] & 0xffffu; s32[c][2] += s16[c][0] >> 16;
+            s32[c][1] += s16[c][1] & 0xffffu; s32[c][3] += s16[c][1] >> 16;
+        }
     }
-    flags[p] = (uint8_t)flag;
-    uint32_t total;
-    block_rank(flag != 0, s_warp, total);
-    if (tid == 0) tile_hits[t] = total;
-}
 
+    uint32_t out = 0, n_flagged = 0;
+    if (i1 > i0) {
+        const size_t p4 = (size_t)t * TILE + lane_off;
+        const uint32_t rw = *reinterpret_cast<const uint32_t*>(ref + p4), ew = *reinterpret_cast<const uint32_t*>(expect + p4);
+        #pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const uint32_t rc = (rw >> (8 * p)) & 0xffu, e = (ew >> (8 * p)) & 3u;
+            if (rc == 0) continue;
+            uint32_t sum[4] = {s32[1][p], s32[2][p], s32[3][p], s32[4][p]};
+            const uint32_t rest = s32[0][p] - (sum[0] + sum[1] + sum[2] + sum[3]);      // bases equal to the expected letter / text mode: '.' and ','
+            uint32_t any = 0;
+            #pragma unroll
+            for (int a = 0; a < 4; ++a) any |= ((any7[a] >> (8 * p + 7)) & 1u) << a;
+            uint32_t ch, extra;
+            if (text_mode) {
+                // counts parsed from mpileup text: letters are never the reference's own base and `rest` holds the
+                // '.'/',' matches, so nothing is masked (call_vC.cpp:545,550,583-584)
+                ch = 6u; extra = rest;
+            } else {
+                #pragma unroll
+                for (int a = 0; a < 4; ++a) if ((uint32_t)a == e) { sum[a] += rest; any |= ((any7[4] >> (8 * p + 7)) & 1u) << a; }
+                ch = ref_channel(rc);
+                extra = ch == 4u ? s32[PLANE_N][p] : 0u;
+            }
+            if (thr <= 0) any = 15u;
+            const uint32_t f = call_position(rc, ch, sum, extra, any, prm);
+            out |= f << (8 * p);
+            n_flagged += f != 0;
+        }
+    }
+    *reinterpret_cast<uint32_t*>(flags + (size_t)t * TILE + lane_off) = out;
+    __syncthreads();
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_flagged += __shfl_down_sync(0xffffffffu, n_flagged, d);
+    if ((tid & 31) == 0 && n_flagged) atomicAdd(&s_hits, n_flagged);
+    __syncthreads();
+    if (tid == 0) tile_hits[t] = s_hits;
+}
 // ordered compaction of the flagged positions: tile_hits holds exclusive offsets on entry
 __global__ void __launch_bounds__(TILE)
 compact_kernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ tile_hits, uint32_t* __restrict__ hit_pos,
@@ -717,32 +987,48 @@ compact_kernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ t
     }
 }
 
+// the six plane values of one position of one item (bytes for narrow items, 16-bit values for wide ones)
+__device__ __forceinline__ void load_planes(const uint8_t* __restrict__ tiles, uint32_t item, bool wide, uint32_t off, uint32_t v[N_PLANES])
+{
+    const uint8_t* base = tiles + (size_t)item * SLOT_BYTES;
+    #pragma unroll
+    for (int c = 0; c < N_PLANES; ++c)
+        v[c] = wide ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(base) + c * TILE + off) : (uint32_t)__ldg(base + c * TILE + off);
+}
+
 // per hit: per-sample coverage and allele counts (zero for samples without an item on the tile)
 // plus population totals. One CTA of 128 threads per hit; outputs were zero-filled by the host side.
 __global__ void __launch_bounds__(128)
-gather_kernel(const uint64_t* __restrict__ acgt, const uint16_t* __restrict__ ncnt, const Item* __restrict__ items,
-              const uint32_t* __restrict__ tile_begin, const uint8_t* __restrict__ ref, const uint32_t* __restrict__ hit_pos,
-              uint32_t n_samples, int text_mode, uint16_t* __restrict__ cov, uint16_t* __restrict__ allele,
-              uint32_t* __restrict__ total)
+gather_kernel(const uint8_t* __restrict__ tiles, const Item* __restrict__ items, const uint32_t* __restrict__ tile_begin,
+              const uint8_t* __restrict__ ref, const uint8_t* __restrict__ expect, const uint32_t* __restrict__ hit_pos,
+              uint32_t n_samples, int text_mode, uint16_t* __restrict__ cov, uint16_t* __restrict__ allele, uint32_t* __restrict__ total)
 {
     __shared__ uint32_t s_tot[5];
     const uint32_t h = blockIdx.x, tid = threadIdx.x;
     const uint32_t p = hit_pos[h];
     const uint32_t t = p / TILE, off = p % TILE;
     const uint32_t ch = text_mode ? 6u : ref_channel(ref[p]);
+    const uint32_t e = expect[p] & 3u;
     if (tid < 5) s_tot[tid] = 0;
     __syncthreads();
     uint32_t tc = 0, ta[4] = {0, 0, 0, 0};
     for (uint32_t i = tile_begin[t] + tid; i < tile_begin[t + 1]; i += blockDim.x) {
-        const uint32_t s = items[i].sample;
-        const uint64_t w = __ldg(acgt + (size_t)i * TILE + off);
-        const uint32_t nn = __ldg(ncnt + (size_t)i * TILE + off);
-        uint32_t c[4], cv = (ch == 4 || text_mode) ? nn : 0;
+        const uint4 it = __ldg(reinterpret_cast<const uint4*>(items) + i);
+        uint32_t v[N_PLANES];
+        load_planes(tiles, i, item_is_wide(it.z, it.w), off, v);
+        const uint32_t rest = v[0] - (v[1] + v[2] + v[3] + v[4]);
+        uint32_t c[4] = {v[1], v[2], v[3], v[4]}, cv;
+        if (text_mode) cv = rest;
+        else {
+            #pragma unroll
+            for (int a = 0; a < 4; ++a) if ((uint32_t)a == e) c[a] += rest;
+            cv = ch == 4u ? v[PLANE_N] : 0u;
+        }
         #pragma unroll
-        for (int a = 0; a < 4; ++a) { c[a] = (uint32_t)(w >> (16 * a)) & 0xffffu; cv += c[a]; if ((uint32_t)a == ch) c[a] = 0; }
-        cov[(size_t)h * n_samples + s] = (uint16_t)cv;
+        for (int a = 0; a < 4; ++a) { cv += c[a]; if ((uint32_t)a == ch) c[a] = 0; }
+        cov[(size_t)h * n_samples + it.x] = (uint16_t)cv;
         #pragma unroll
-        for (int a = 0; a < 4; ++a) { allele[((size_t)h * 4 + a) * n_samples + s] = (uint16_t)c[a]; ta[a] += c[a]; }
+        for (int a = 0; a < 4; ++a) { allele[((size_t)h * 4 + a) * n_samples + it.x] = (uint16_t)c[a]; ta[a] += c[a]; }
         tc += cv;
     }
     atomicAdd(&s_tot[0], tc);
@@ -752,23 +1038,42 @@ gather_kernel(const uint64_t* __restrict__ acgt, const uint16_t* __restrict__ nc
     if (tid < 5) total[(size_t)h * 5 + tid] = s_tot[tid];
 }
 
-// inspection hook: expand one sample's counts for a position range into [n][5] u16
-__global__ void counts_kernel(const uint64_t* __restrict__ acgt, const uint16_t* __restrict__ ncnt, const Item* __restrict__ items,
-                              const uint32_t* __restrict__ tile_begin, uint32_t sample, uint32_t first, uint32_t n,
-                              uint16_t* __restrict__ out)
+// inspection hook: one sample's counts for a position range as [n][5] u16 (A, C, G, T, non-ACGT)
+__global__ void counts_kernel(const uint8_t* __restrict__ tiles, const Item* __restrict__ items, const uint32_t* __restrict__ tile_begin,
+                              const uint8_t* __restrict__ expect, uint32_t sample, uint32_t first, uint32_t n, uint16_t* __restrict__ out)
 {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const uint32_t p = first + k, t = p / TILE, off = p % TILE;
-    uint16_t v[5] = {0, 0, 0, 0, 0};
+    uint32_t r[5] = {0, 0, 0, 0, 0};
     for (uint32_t i = tile_begin[t]; i < tile_begin[t + 1]; ++i) {
-        if (items[i].sample != sample) continue;
-        const uint64_t w = acgt[(size_t)i * TILE + off];
-        for (int a = 0; a < 4; ++a) v[a] = (uint16_t)(w >> (16 * a));
-        v[4] = ncnt[(size_t)i * TILE + off];
+        const uint4 it = __ldg(reinterpret_cast<const uint4*>(items) + i);
+        if (it.x != sample) continue;
+        uint32_t v[N_PLANES];
+        load_planes(tiles, i, item_is_wide(it.z, it.w), off, v);
+        const uint32_t e = expect[p] & 3u;
+        for (int a = 0; a < 4; ++a) r[a] = v[1 + a] + ((uint32_t)a == e ? v[0] - (v[1] + v[2] + v[3] + v[4]) : 0u);
+        r[4] = v[PLANE_N];
         break;
     }
-    for (int a = 0; a < 5; ++a) out[(size_t)k * 5 + a] = v[a];
+    for (int a = 0; a < 5; ++a) out[(size_t)k * 5 + a] = (uint16_t)r[a];
+}
+
+// classic text mode: counts parsed by the host from mpileup text ([item][TILE]: packed letter counts and '.'/','
+// matches) -> wide count planes. D holds everything counted, so "D - letters" gives the matches back.
+__global__ void text_tiles_kernel(const uint64_t* __restrict__ acgt, const uint16_t* __restrict__ matches, uint64_t n_cells,
+                                  uint8_t* __restrict__ tiles)
+{
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_cells) return;
+    const uint64_t item = g / TILE; const uint32_t off = (uint32_t)(g % TILE);
+    const uint64_t w = acgt[g];
+    uint32_t c[4], sum = matches[g];
+    for (int a = 0; a < 4; ++a) { c[a] = (uint32_t)(w >> (16 * a)) & 0xffffu; sum += c[a]; }
+    uint16_t* base = reinterpret_cast<uint16_t*>(tiles + item * SLOT_BYTES);
+    base[off] = (uint16_t)(sum > 0xffffu ? 0xffffu : sum);
+    for (int a = 0; a < 4; ++a) base[(1 + a) * TILE + off] = (uint16_t)c[a];
+    base[PLANE_N * TILE + off] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -852,3 +1157,5 @@ cov_scan_kernel(const int32_t* __restrict__ diff, const uint32_t* __restrict__ c
 }
 
 }  // namespace msnv_gpu
+
+

@@ -31,13 +31,16 @@ struct msnv_ctx {
     std::vector<Slab> slabs;            // small blocks are carved out of large allocations
     size_t slab_live = 0;               // carved blocks in sample_allocs + pool
     std::vector<msnv_sample_sizes> sizes;      // [S]
-    uint64_t n_reads = 0, n_bases = 0;
+    uint64_t n_reads = 0, n_bases = 0, n_segs = 0;
     SampleDev* d_samples = nullptr;
     uint8_t* d_ref = nullptr;
 
     // ---- work buffers (grown on demand, kept across shards)
     Item* d_items = nullptr;        uint64_t cap_items = 0;
-    uint64_t* d_acgt = nullptr;     uint16_t* d_ncnt = nullptr;
+    uint8_t* d_tiles = nullptr;     // count planes, SLOT_BYTES per item
+    uint8_t* d_expect = nullptr;    // expected letter per position (derived from d_ref)
+    uint64_t* d_text_acgt = nullptr; uint16_t* d_text_match = nullptr; uint64_t cap_text = 0;   // classic text mode staging
+    int sm_count = 0;
     uint32_t* d_tile_begin = nullptr; uint32_t* d_tile_hits = nullptr; uint8_t* d_flags = nullptr; uint64_t cap_tiles = 0;
     uint32_t* d_block_sums = nullptr; uint64_t cap_blocks = 0;
     uint2* d_range_cache = nullptr;   uint64_t cap_range = 0;
@@ -55,6 +58,7 @@ struct msnv_ctx {
 
     cudaEvent_t ev[8] = {};
     msnv_timings tm = {};
+    PileupShape tm_shape = {}; int tm_ctas = 0;   // what the last pileup launch used (MSNV_VERBOSE)
 };
 
 namespace {
@@ -173,7 +177,12 @@ static int run_call_phase(msnv_ctx* ctx, const msnv_call_params* prm, int text_m
     cudaStream_t st = ctx->stream;
     const uint32_t S = ctx->S, n_tiles = ctx->n_tiles;
     CallParamsDev cp{prm->min_coverage, prm->calling_threshold, prm->min_fraction};
-    call_kernel<<<n_tiles, TILE, 0, st>>>(ctx->d_acgt, ctx->d_ncnt, ctx->d_tile_begin, ctx->d_ref, cp, text_mode, ctx->d_flags, ctx->d_tile_hits);
+    if (cp.thr > 128)
+        call_kernel<true><<<n_tiles, CALL_THREADS, 0, st>>>(ctx->d_tiles, ctx->d_items, ctx->d_tile_begin, ctx->d_ref, ctx->d_expect, cp, text_mode,
+                                                            ctx->d_flags, ctx->d_tile_hits);
+    else
+        call_kernel<false><<<n_tiles, CALL_THREADS, 0, st>>>(ctx->d_tiles, ctx->d_items, ctx->d_tile_begin, ctx->d_ref, ctx->d_expect, cp, text_mode,
+                                                             ctx->d_flags, ctx->d_tile_hits);
     ++launches;
     CU(cudaEventRecord(ctx->ev[4], st));
 
@@ -196,7 +205,7 @@ static int run_call_phase(msnv_ctx* ctx, const msnv_call_params* prm, int text_m
     if (n_hits) {
         CU(cudaMemsetAsync(ctx->d_hit_cov, 0, (size_t)n_hits * S * 2, st));
         CU(cudaMemsetAsync(ctx->d_hit_allele, 0, (size_t)n_hits * S * 8, st));
-        gather_kernel<<<n_hits, 128, 0, st>>>(ctx->d_acgt, ctx->d_ncnt, ctx->d_items, ctx->d_tile_begin, ctx->d_ref, ctx->d_hit_pos, S,
+        gather_kernel<<<n_hits, 128, 0, st>>>(ctx->d_tiles, ctx->d_items, ctx->d_tile_begin, ctx->d_ref, ctx->d_expect, ctx->d_hit_pos, S,
                                                text_mode, ctx->d_hit_cov, ctx->d_hit_allele, ctx->d_hit_total);
         ++launches;
     }
@@ -223,10 +232,8 @@ static int ensure_items(msnv_ctx* ctx, uint64_t n_items)
     if (n_items <= ctx->cap_items) return 0;
     const uint64_t cap = n_items + n_items / 8 + 64;
     if (grow(ctx, ctx->d_items, cap)) return MSNV_E_CUDA;
-    cudaFree(ctx->d_acgt); cudaFree(ctx->d_ncnt); ctx->d_acgt = nullptr; ctx->d_ncnt = nullptr; ctx->cap_items = 0;
-    cudaError_t e1 = cudaMalloc((void**)&ctx->d_acgt, cap * TILE * 8);
-    cudaError_t e2 = cudaMalloc((void**)&ctx->d_ncnt, cap * TILE * 2);
-    if (e1 != cudaSuccess || e2 != cudaSuccess)
+    cudaFree(ctx->d_tiles); ctx->d_tiles = nullptr; ctx->cap_items = 0;
+    if (cudaMalloc((void**)&ctx->d_tiles, cap * SLOT_BYTES) != cudaSuccess)
         return fail(ctx, MSNV_E_NOMEM, "count tiles for %llu (sample,tile) items do not fit device memory; run smaller shards (metaSNV.py --n_splits bins the genomes)", (unsigned long long)n_items);
     ctx->cap_items = cap;
     return 0;
@@ -244,35 +251,50 @@ int msnv_device_count(void)
     return n;
 }
 
-// The instantiations of the pileup kernel: threads per CTA, reads staged per chunk, and the CTAs per SM the
-// register allocation aims at. Chosen per launch from the mean number of reads per (sample, tile) item;
-// MSNV_PILEUP_VARIANT=<index> overrides the choice (tuning hook, see tools/variant_sweep.py).
-#define MSNV_PILEUP_VARIANTS(X) \
-    X(0, 128, 127, 8) /* shallow: a tile's reads fill half a chunk or less */ \
-    X(1, 128, 127, 7) /* standard */ \
-    X(2, 256, 255, 5) /* deep: several chunks per tile */ \
-    X(3, 128, 127, 6) \
-    X(4, 256, 255, 4)
-constexpr int N_PILEUP_VARIANTS = 5, PILEUP_VARIANT_SHALLOW = 0, PILEUP_VARIANT_STANDARD = 1, PILEUP_VARIANT_DEEP = 2;
+// Staging limits of the pileup kernel for a shard (PileupShape) and the CTAs per SM they allow. A stage should hold
+// a whole item in the common case: the limits follow the mean number of reads per item (measured by the index pass)
+// with head-room for its spread; what is left of the SM's shared memory after fitting `ctas` CTAs goes into larger
+// quad buffers. MSNV_MAX_READS / MSNV_CHUNK_Q4 / MSNV_PILEUP_CTAS override the choice (tuning hooks).
+constexpr size_t SMEM_PER_SM = 233472, SMEM_PER_CTA_MAX = 232448, SMEM_CTA_RESERVED = 1024;
+constexpr uint32_t CHUNK_Q4_CAP = 16384;
 
-static cudaError_t pileup_variant_prepare(int v)
+static PileupShape choose_pileup_shape(const msnv_ctx* ctx, uint64_t n_items, uint64_t item_reads, int& ctas)
 {
-    switch (v) {
-#define X(I, T, R, C) case I: return cudaFuncSetAttribute(pileup_kernel<T, R, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pileup_smem_bytes(R, CHUNK_Q4_MAX));
-        MSNV_PILEUP_VARIANTS(X)
-#undef X
+    const double reads_per_item = (double)item_reads / (double)(n_items ? n_items : 1);
+    const double q4_per_read = (double)ctx->n_bases / 4.0 / (double)(ctx->n_reads ? ctx->n_reads : 1);
+    const double segs_per_read = (double)ctx->n_segs / (double)(ctx->n_reads ? ctx->n_reads : 1);
+    PileupShape sh;
+    uint32_t mr = (uint32_t)(reads_per_item * 1.3 + 24.0);
+    if (const char* e = getenv("MSNV_MAX_READS")) mr = (uint32_t)atoi(e);
+    if (mr < 16) mr = 16;
+    if (mr > NARROW_MAX_READS) mr = NARROW_MAX_READS;
+    sh.max_reads = mr;
+    uint32_t ms = (uint32_t)(mr * segs_per_read * 1.1 + 16.0);
+    if (ms < CHUNK_SEGS_MIN) ms = CHUNK_SEGS_MIN;
+    sh.max_segs = up_to(ms, 8);
+    const double want_reads = reads_per_item < (double)mr ? reads_per_item * 1.25 + 4.0 : (double)mr;
+    uint32_t cq = (uint32_t)(want_reads * q4_per_read) + 64u;
+    if (const char* e = getenv("MSNV_CHUNK_Q4")) cq = (uint32_t)atoi(e);
+    if (cq < CHUNK_Q4_MIN) cq = CHUNK_Q4_MIN;
+    if (cq > CHUNK_Q4_CAP) cq = CHUNK_Q4_CAP;
+    sh.chunk_q4 = up_to(cq, 16);
+    while (pileup_smem_layout(sh).total > SMEM_PER_CTA_MAX && sh.chunk_q4 > CHUNK_Q4_MIN) sh.chunk_q4 -= 16;
+    ctas = (int)(SMEM_PER_SM / (pileup_smem_layout(sh).total + SMEM_CTA_RESERVED));
+    if (ctas < 1) ctas = 1;
+    if (ctas > 6) ctas = 6;
+    if (const char* e = getenv("MSNV_PILEUP_CTAS")) { const int v = atoi(e); if (v >= 1 && v < ctas) ctas = v; }
+    if (!getenv("MSNV_CHUNK_Q4")) {
+        // spend the rest of the SM's shared memory on the quad buffers (fewer items need a second chunk)
+        const size_t budget = SMEM_PER_SM / ctas - SMEM_CTA_RESERVED;
+        const size_t per_q4 = 5 * PL_STAGES + 1;             // bytes per staged quad: bases + qualities per stage, one tag
+        const size_t have = pileup_smem_layout(sh).total;
+        if (budget > have + 256) {
+            uint32_t extra = (uint32_t)((budget - have - 256) / per_q4) / 16 * 16;
+            if (sh.chunk_q4 + extra > CHUNK_Q4_CAP) extra = CHUNK_Q4_CAP - sh.chunk_q4;
+            sh.chunk_q4 += extra;
+        }
     }
-    return cudaErrorInvalidValue;
-}
-
-static void pileup_variant_launch(int v, uint32_t n_items, uint32_t chunk_q4, cudaStream_t st, const SampleDev* samples,
-                                  const Item* items, uint64_t* acgt, uint16_t* ncnt, int* err)
-{
-    switch (v) {
-#define X(I, T, R, C) case I: pileup_kernel<T, R, C><<<n_items, T, pileup_smem_bytes(R, chunk_q4), st>>>(samples, items, n_items, chunk_q4, acgt, ncnt, err); break;
-        MSNV_PILEUP_VARIANTS(X)
-#undef X
-    }
+    return sh;
 }
 
 int msnv_create(int device, msnv_ctx** out)
@@ -287,10 +309,11 @@ int msnv_create(int device, msnv_ctx** out)
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto& e : ctx->ev) CU(cudaEventCreate(&e));
-    CU(cudaMalloc((void**)&ctx->d_scalar, 16));
+    CU(cudaMalloc((void**)&ctx->d_scalar, 32));
     CU(cudaMalloc((void**)&ctx->d_err, 4));
-    CU(cudaMallocHost((void**)&ctx->h_scalar, 16));
-    for (int v = 0; v < N_PILEUP_VARIANTS; ++v) CU(pileup_variant_prepare(v));
+    CU(cudaMallocHost((void**)&ctx->h_scalar, 32));
+    CU(cudaFuncSetAttribute(pileup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PER_CTA_MAX));
+    CU(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     return MSNV_OK;
 }
 
@@ -303,7 +326,7 @@ void msnv_destroy(msnv_ctx* ctx)
     free_samples(ctx);                              // second call empties the pool as well
     for (auto& sl : ctx->slabs) cudaFree(sl.base);
     cudaFree(ctx->d_samples); cudaFree(ctx->d_ref);
-    cudaFree(ctx->d_items); cudaFree(ctx->d_acgt); cudaFree(ctx->d_ncnt);
+    cudaFree(ctx->d_items); cudaFree(ctx->d_tiles); cudaFree(ctx->d_expect); cudaFree(ctx->d_text_acgt); cudaFree(ctx->d_text_match);
     cudaFree(ctx->d_tile_begin); cudaFree(ctx->d_tile_hits); cudaFree(ctx->d_flags); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_range_cache); cudaFree(ctx->d_bitmap);
     cudaFree(ctx->d_scalar); cudaFree(ctx->d_err);
     cudaFree(ctx->d_hit_pos); cudaFree(ctx->d_hit_total); cudaFree(ctx->d_hit_pop); cudaFree(ctx->d_hit_ind);
@@ -338,12 +361,13 @@ int msnv_shard_begin(msnv_ctx* ctx, uint32_t n_samples, uint32_t n_positions, co
     ctx->S = n_samples; ctx->P = n_positions; ctx->n_tiles = n_positions / TILE;
     ctx->h_samples.assign(n_samples, SampleDev{});
     ctx->sizes.assign(n_samples, msnv_sample_sizes{});
-    ctx->n_reads = ctx->n_bases = 0;
+    ctx->n_reads = ctx->n_bases = ctx->n_segs = 0;
     ctx->has_run = false;
-    cudaFree(ctx->d_samples); cudaFree(ctx->d_ref);
-    ctx->d_samples = nullptr; ctx->d_ref = nullptr;
+    cudaFree(ctx->d_samples); cudaFree(ctx->d_ref); cudaFree(ctx->d_expect);
+    ctx->d_samples = nullptr; ctx->d_ref = nullptr; ctx->d_expect = nullptr;
     CU(cudaMalloc((void**)&ctx->d_samples, sizeof(SampleDev) * n_samples));
     CU(cudaMalloc((void**)&ctx->d_ref, n_positions));
+    CU(cudaMalloc((void**)&ctx->d_expect, n_positions));
     CU(cudaMemcpyAsync(ctx->d_ref, ref, n_positions, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->n_tiles + 1 > ctx->cap_tiles) {
         if (grow(ctx, ctx->d_tile_begin, (uint64_t)ctx->n_tiles + 1)) return MSNV_E_CUDA;
@@ -391,7 +415,7 @@ int msnv_shard_add_sample(msnv_ctx* ctx, uint32_t sample, const msnv_sample_read
     d.seg_pos = (const int32_t*)(base + o_sp);   d.seg_len = (const uint16_t*)(base + o_sl);
     d.seq2 = base + o_seq;                      d.qual = base + o_qual;
     d.n_reads = r->n_reads; d.max_span = r->max_span ? r->max_span : 1;
-    ctx->n_reads += n; ctx->n_bases += 4ull * n_q4;
+    ctx->n_reads += n; ctx->n_bases += 4ull * n_q4; ctx->n_segs += n_seg;
     ctx->sizes[sample] = msnv_sample_sizes{r->n_reads, 0, d.max_span, 0, (uint64_t)n_seg, (uint64_t)n_q4};
     return MSNV_OK;
 }
@@ -426,6 +450,10 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
 
     CU(cudaMemcpyAsync(ctx->d_samples, ctx->h_samples.data(), sizeof(SampleDev) * S, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(ctx->d_err, 0, 4, st));
+    CU(cudaMemsetAsync(ctx->d_scalar, 0, 32, st));
+    // expected letter per position (msnv_shard_mask_position may have changed the reference since the last run)
+    expect_kernel<<<(ctx->P + 255) / 256, 256, 0, st>>>(ctx->d_ref, ctx->P, ctx->d_expect);
+    ++launches;
 
     CU(cudaEventRecord(ctx->ev[0], st));
     // ---- index
@@ -438,6 +466,13 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
     if (n_pairs_idx * 8 <= (1ull << 30)) {
         if (n_pairs_idx > ctx->cap_range) { if (grow(ctx, ctx->d_range_cache, n_pairs_idx)) return MSNV_E_CUDA; ctx->cap_range = n_pairs_idx; }
         cache = ctx->d_range_cache;
+    }
+    {   // the index and the pileup rely on coordinate order within a sample; checked on the device (0.3 ms for 5e8 reads)
+        uint64_t max_reads = 0;
+        for (uint32_t s = 0; s < S; ++s) if (ctx->h_samples[s].n_reads > max_reads) max_reads = ctx->h_samples[s].n_reads;
+        unsigned gx = (unsigned)((max_reads + 256 * 8 - 1) / (256 * 8)); if (gx < 1) gx = 1; if (gx > 1024) gx = 1024;
+        order_check_kernel<<<dim3(gx, S), 256, 0, st>>>(ctx->d_samples, ctx->d_err);
+        ++launches;
     }
     // sparse shards (fewer than ~1/3 of the pairs can be active): occupancy bitmap first
     uint32_t* bitmap = nullptr;
@@ -455,36 +490,44 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* prm, msnv_hits* hits)
         ++launches;
         bitmap = ctx->d_bitmap;
     }
-    index_kernel<false><<<(unsigned)n_blocks, 256, 0, st>>>(ctx->d_samples, S, n_tiles, ctx->d_block_sums, nullptr, nullptr, cache, bitmap, words_per_sample);
+    unsigned long long* d_item_reads = reinterpret_cast<unsigned long long*>(ctx->d_scalar + 2);
+    index_kernel<false><<<(unsigned)n_blocks, 256, 0, st>>>(ctx->d_samples, S, n_tiles, ctx->d_block_sums, nullptr, nullptr, cache, bitmap, words_per_sample,
+                                                            d_item_reads);
     scan_kernel<<<1, 1024, 0, st>>>(ctx->d_block_sums, (uint32_t)n_blocks, ctx->d_scalar);
     launches += 2;
-    CU(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_scalar + 4, ctx->d_err, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (ctx->h_scalar[4] == 3) return fail(ctx, MSNV_E_ARG, "the reads of a sample are not in coordinate order (pos must be ascending)");
     const uint32_t n_items = ctx->h_scalar[0];
+    const uint64_t item_reads = (uint64_t)ctx->h_scalar[2] | (uint64_t)ctx->h_scalar[3] << 32;
     ctx->n_items = n_items;
     if (int rc = ensure_items(ctx, n_items)) return rc;
     index_kernel<true><<<(unsigned)n_blocks, 256, 0, st>>>(ctx->d_samples, S, n_tiles, ctx->d_block_sums, ctx->d_items, ctx->d_tile_begin, cache, bitmap,
-                                                           words_per_sample);
+                                                           words_per_sample, nullptr);
     ++launches;
     CU(cudaMemcpyAsync(ctx->d_tile_begin + n_tiles, ctx->d_scalar, 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaEventRecord(ctx->ev[1], st));
 
     CU(cudaEventRecord(ctx->ev[2], st));
 
-    // ---- pileup
+    // ---- pileup: persistent CTAs, as many per SM as the staging buffers allow
     if (n_items) {
-        // staging buffers sized from the mean work per item (+15 %, at least one maximal read): smaller
-        // buffers let more CTAs share an SM; an item that does not fit simply takes another chunk
-        const uint64_t mean_q4 = ctx->n_bases / 4 / n_items, mean_reads = ctx->n_reads / n_items;
-        int variant = mean_reads > 160 ? PILEUP_VARIANT_DEEP : mean_reads <= 64 ? PILEUP_VARIANT_SHALLOW : PILEUP_VARIANT_STANDARD;
-        if (const char* e = getenv("MSNV_PILEUP_VARIANT"))
-            if (e[0] >= '0' && e[0] <= '9' && atoi(e) < N_PILEUP_VARIANTS) variant = atoi(e);
-        uint32_t chunk_q4 = variant == PILEUP_VARIANT_DEEP ? (uint32_t)CHUNK_Q4_MAX : (uint32_t)((mean_q4 * 23 / 20 + 255) / 256 * 256);
-        if (const char* e = getenv("MSNV_CHUNK_Q4")) chunk_q4 = (uint32_t)atoi(e) / 256 * 256;
-        if (chunk_q4 < (uint32_t)CHUNK_Q4_MIN) chunk_q4 = CHUNK_Q4_MIN;
-        if (chunk_q4 > (uint32_t)CHUNK_Q4_MAX) chunk_q4 = CHUNK_Q4_MAX;
-        pileup_variant_launch(variant, n_items, chunk_q4, st, ctx->d_samples, ctx->d_items, ctx->d_acgt, ctx->d_ncnt, ctx->d_err);
+        int ctas = 1;
+        const PileupShape sh = choose_pileup_shape(ctx, n_items, item_reads, ctas);
+        const size_t smem = pileup_smem_layout(sh).total;
+        int fit = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, pileup_kernel, PL_THREADS, smem));
+        if (fit < 1) return fail(ctx, MSNV_E_CUDA, "pileup kernel does not fit an SM (%zu bytes of shared memory)", smem);
+        if (fit < ctas) ctas = fit;
+        uint64_t grid = (uint64_t)ctas * (uint64_t)ctx->sm_count;
+        if (grid > n_items) grid = n_items;
+        pileup_kernel<<<(unsigned)grid, PL_THREADS, smem, st>>>(ctx->d_samples, ctx->d_items, n_items, sh, ctx->d_expect, ctx->d_tiles, ctx->d_err);
         ++launches;
+        ctx->tm_shape = sh; ctx->tm_ctas = ctas;
+        if (getenv("MSNV_VERBOSE"))
+            fprintf(stderr, "msnv: pileup %u items (%.1f reads each), %u CTAs (%d per SM) x %d threads, stage limits %u reads / %u segments / %u quads, %zu B shared memory\n",
+                    n_items, (double)item_reads / n_items, (unsigned)grid, ctas, PL_THREADS, sh.max_reads, sh.max_segs, sh.chunk_q4, smem);
     }
     CU(cudaEventRecord(ctx->ev[3], st));
 
@@ -518,8 +561,16 @@ int msnv_call_counts(msnv_ctx* ctx, uint32_t n_samples, uint32_t n_positions, co
     uint32_t launches = 0;
     CU(cudaMemsetAsync(ctx->d_err, 0, 4, st));
     CU(cudaEventRecord(ctx->ev[0], st));
-    CU(cudaMemcpyAsync(ctx->d_acgt, acgt, n_items * TILE * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->d_ncnt, matches, n_items * TILE * 2, cudaMemcpyHostToDevice, st));
+    if (n_items > ctx->cap_text) {
+        if (grow(ctx, ctx->d_text_acgt, n_items * TILE)) return MSNV_E_CUDA;
+        if (grow(ctx, ctx->d_text_match, n_items * TILE)) return MSNV_E_CUDA;
+        ctx->cap_text = n_items;
+    }
+    CU(cudaMemcpyAsync(ctx->d_text_acgt, acgt, n_items * TILE * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_text_match, matches, n_items * TILE * 2, cudaMemcpyHostToDevice, st));
+    expect_kernel<<<(ctx->P + 255) / 256, 256, 0, st>>>(ctx->d_ref, ctx->P, ctx->d_expect);
+    text_tiles_kernel<<<(unsigned)((n_items * TILE + 255) / 256), 256, 0, st>>>(ctx->d_text_acgt, ctx->d_text_match, n_items * TILE, ctx->d_tiles);
+    launches += 2;
     dense_items_kernel<<<(unsigned)((n_items + 1 + 255) / 256), 256, 0, st>>>(n_samples, ctx->n_tiles, ctx->d_items, ctx->d_tile_begin);
     ++launches;
     ctx->n_items = (uint32_t)n_items;
@@ -645,7 +696,7 @@ int msnv_shard_synth(msnv_ctx* ctx, const msnv_synth_desc* d, int64_t* first_col
         sd.seg_pos = (const int32_t*)(data + o_sp);  sd.seg_len = (const uint16_t*)(data + o_sl);
         sd.seq2 = data + o_seq;                      sd.qual = data + o_qual;
         sd.n_reads = (uint32_t)n; sd.max_span = L + 3;
-        ctx->n_reads += n; ctx->n_bases += 4ull * n_q4;
+        ctx->n_reads += n; ctx->n_bases += 4ull * n_q4; ctx->n_segs += n_seg;
         ctx->sizes[s] = msnv_sample_sizes{(uint32_t)n, (uint32_t)n_mated, L + 3, 0, (uint64_t)n_seg, (uint64_t)n_q4};
     }
     if (first_column) *first_column = first_col;
@@ -706,7 +757,7 @@ int msnv_shard_counts(msnv_ctx* ctx, uint32_t sample, uint32_t first, uint32_t n
     CU(cudaSetDevice(ctx->device));
     uint16_t* d = nullptr;
     CU(cudaMalloc((void**)&d, (size_t)n * 10));
-    counts_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_acgt, ctx->d_ncnt, ctx->d_items, ctx->d_tile_begin, sample, first, n, d);
+    counts_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_tiles, ctx->d_items, ctx->d_tile_begin, ctx->d_expect, sample, first, n, d);
     cudaError_t e = cudaMemcpyAsync(out, d, (size_t)n * 10, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d);

@@ -145,10 +145,12 @@ bool BgzfReader::fill()
         const uint8_t* h = map_ + cpos_;
         if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { err_ = "not a BGZF member"; return false; }
         uint32_t xlen = h[10] | h[11] << 8;
+        if (size_ - cpos_ < 12 + (uint64_t)xlen) { err_ = "truncated BGZF extra field"; return false; }
         int bsize = -1;
-        for (uint32_t off = 0; off + 4 <= xlen && cpos_ + 12 + off + 4 <= size_;) {
+        for (uint32_t off = 0; off + 4 <= xlen;) {
             const uint8_t* x = h + 12 + off;
             uint32_t slen = x[2] | x[3] << 8;
+            if (off + 4 + slen > xlen) break;                     // sub-field runs past the extra field: malformed
             if (x[0] == 'B' && x[1] == 'C' && slen == 2) bsize = x[4] | x[5] << 8;
             off += 4 + slen;
         }

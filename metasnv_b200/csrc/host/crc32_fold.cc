@@ -8,57 +8,72 @@
 
 namespace {
 
-__attribute__((target("pclmul,sse4.1")))
-uint32_t crc32_clmul(const uint8_t* buf, size_t len /* >= 64, multiple of 16 */, uint32_t crc /* register value: ~crc of the bytes before */)
+// ---- fold constants, derived at start-up from the polynomial itself
+// x^n mod P over GF(2) for the CRC-32 polynomial P = x^32 + 0x04C11DB7 (most significant bit = highest power)
+constexpr uint32_t kPolyLow = 0x04C11DB7u;
+uint32_t x_pow_mod_p(unsigned n)
 {
-    alignas(16) static const uint64_t k1k2[2] = {0x0154442bd4ull, 0x01c6e41596ull};   // x^(4*128+32) mod P, x^(4*128-32) mod P (reflected)
-    alignas(16) static const uint64_t k3k4[2] = {0x01751997d0ull, 0x00ccaa009eull};   // x^(128+32) mod P, x^(128-32) mod P
-    alignas(16) static const uint64_t k5k0[2] = {0x0163cd6124ull, 0x0000000000ull};   // x^64 mod P
-    alignas(16) static const uint64_t poly[2] = {0x01db710641ull, 0x01f7011641ull};   // P and floor(x^64 / P)
-    __m128i x0, x1, x2, x3, x4, x5, x6, x7, x8, y5, y6, y7, y8;
-    x1 = _mm_loadu_si128((const __m128i*)(buf + 0x00));
-    x2 = _mm_loadu_si128((const __m128i*)(buf + 0x10));
-    x3 = _mm_loadu_si128((const __m128i*)(buf + 0x20));
-    x4 = _mm_loadu_si128((const __m128i*)(buf + 0x30));
-    x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)crc));
-    x0 = _mm_load_si128((const __m128i*)k1k2);
-    buf += 64; len -= 64;
-    while (len >= 64) {                                   // four independent 128-bit lanes, each folded over 512 bits
-        x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
-        x7 = _mm_clmulepi64_si128(x3, x0, 0x00); x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
-        x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
-        x3 = _mm_clmulepi64_si128(x3, x0, 0x11); x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
-        y5 = _mm_loadu_si128((const __m128i*)(buf + 0x00)); y6 = _mm_loadu_si128((const __m128i*)(buf + 0x10));
-        y7 = _mm_loadu_si128((const __m128i*)(buf + 0x20)); y8 = _mm_loadu_si128((const __m128i*)(buf + 0x30));
-        x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), y5); x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), y6);
-        x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), y7); x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), y8);
-        buf += 64; len -= 64;
+    uint32_t r = 1;                         // x^0
+    for (unsigned i = 0; i < n; ++i) {
+        const bool carry = r & 0x80000000u;
+        r <<= 1;
+        if (carry) r ^= kPolyLow;
     }
-    x0 = _mm_load_si128((const __m128i*)k3k4);            // the four lanes into one
-    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
-    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
-    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
-    while (len >= 16) {                                   // remaining whole 16-byte blocks
-        x2 = _mm_loadu_si128((const __m128i*)buf);
-        x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
-        buf += 16; len -= 16;
-    }
-    x2 = _mm_clmulepi64_si128(x1, x0, 0x10);              // 128 -> 64 bits
-    x3 = _mm_setr_epi32(~0, 0, ~0, 0);
-    x1 = _mm_srli_si128(x1, 8);
-    x1 = _mm_xor_si128(x1, x2);
-    x0 = _mm_loadl_epi64((const __m128i*)k5k0);
-    x2 = _mm_srli_si128(x1, 4);
-    x1 = _mm_and_si128(x1, x3);
-    x1 = _mm_clmulepi64_si128(x1, x0, 0x00);
-    x1 = _mm_xor_si128(x1, x2);
-    x0 = _mm_load_si128((const __m128i*)poly);            // Barrett reduction 64 -> 32 bits
-    x2 = _mm_and_si128(x1, x3);
-    x2 = _mm_clmulepi64_si128(x2, x0, 0x10);
-    x2 = _mm_and_si128(x2, x3);
-    x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
-    x1 = _mm_xor_si128(x1, x2);
-    return (uint32_t)_mm_extract_epi32(x1, 1);
+    return r;
+}
+// gzip's CRC is bit-reflected; a carry-less product of two reflected 64-bit operands comes out one bit short of its
+// own reflection, which the constant absorbs: constant = reflect32(x^n mod P) << 1
+uint64_t fold_constant(unsigned n)
+{
+    const uint32_t v = x_pow_mod_p(n);
+    uint32_t r = 0;
+    for (int b = 0; b < 32; ++b) if (v & (1u << b)) r |= 0x80000000u >> b;
+    return (uint64_t)r << 1;
+}
+
+struct FoldKeys { __m128i by512, by128; };
+
+__attribute__((target("pclmul,sse4.1")))
+const FoldKeys& fold_keys()
+{
+    // moving a 128-bit lane D bits towards the end of the message multiplies its low half by x^(D+32) and its high
+    // half by x^(D-32) (all mod P); D = 512 while four lanes run side by side, D = 128 when they are merged
+    static const FoldKeys k = {
+        _mm_set_epi64x((long long)fold_constant(512 - 32), (long long)fold_constant(512 + 32)),
+        _mm_set_epi64x((long long)fold_constant(128 - 32), (long long)fold_constant(128 + 32)),
+    };
+    return k;
+}
+
+// lane * x^D mod P (as a 128-bit value congruent to it), xor the data that sits D bits further on
+__attribute__((target("pclmul,sse4.1")))
+inline __m128i fold_onto(__m128i lane, __m128i key, __m128i next)
+{
+    const __m128i lo = _mm_clmulepi64_si128(lane, key, 0x00), hi = _mm_clmulepi64_si128(lane, key, 0x11);
+    return _mm_xor_si128(_mm_xor_si128(lo, hi), next);
+}
+
+// CRC register after `len` bytes (len >= 64, a multiple of 16), starting from register value `reg`.
+// Invariant of the loop: (lanes || unread bytes) has the same remainder as (reg-adjusted message read so far ||
+// unread bytes). At the end one 16-byte lane is left; its remainder is taken by zlib as if it were message bytes
+// under a zero register, so there is no reduction code here.
+__attribute__((target("pclmul,sse4.1")))
+uint32_t crc32_fold_bulk(const uint8_t* p, size_t len, uint32_t reg)
+{
+    const FoldKeys& k = fold_keys();
+    __m128i lane[4];
+    for (int i = 0; i < 4; ++i) lane[i] = _mm_loadu_si128((const __m128i*)(p + 16 * i));
+    lane[0] = _mm_xor_si128(lane[0], _mm_cvtsi32_si128((int)reg));       // the register lines up with the first four bytes
+    p += 64; len -= 64;
+    for (; len >= 64; p += 64, len -= 64)
+        for (int i = 0; i < 4; ++i) lane[i] = fold_onto(lane[i], k.by512, _mm_loadu_si128((const __m128i*)(p + 16 * i)));
+    __m128i acc = lane[0];
+    for (int i = 1; i < 4; ++i) acc = fold_onto(acc, k.by128, lane[i]);
+    for (; len >= 16; p += 16, len -= 16) acc = fold_onto(acc, k.by128, _mm_loadu_si128((const __m128i*)p));
+    alignas(16) uint8_t rest[16];
+    _mm_store_si128((__m128i*)rest, acc);
+    // zlib's crc32(c, buf) is ~remainder(register = ~c, buf): a zero register is c = ~0, and the result is inverted back
+    return ~(uint32_t)crc32(0xffffffffu, rest, 16);
 }
 
 bool have_clmul() { static const bool ok = __builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1"); return ok; }
@@ -73,7 +88,7 @@ uint32_t crc32_member(const uint8_t* data, size_t n)
 #if defined(__x86_64__)
     if (n >= 64 && have_clmul()) {
         const size_t bulk = n & ~(size_t)15;
-        const uint32_t reg = crc32_clmul(data, bulk, 0xffffffffu);        // zlib's crc32(0, ...) starts from register ~0
+        const uint32_t reg = crc32_fold_bulk(data, bulk, 0xffffffffu);    // zlib's crc32(0, ...) starts from register ~0
         // hand the register to zlib for the tail: crc32(c, ...) works on ~c
         return (uint32_t)crc32((uLong)(~reg), data + bulk, (uInt)(n - bulk));
     }

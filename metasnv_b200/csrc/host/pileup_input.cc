@@ -164,6 +164,14 @@ bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& la
     BamReader rd;
     if (!rd.open(bam_path, inflate_threads)) { err = rd.error(); return false; }
     const int MAXCNT = 8000;                         // samtools mpileup -d default (>= 1.9), per file
+    // mpileup takes the contigs from the first file's header and trusts the others to agree; a file whose header
+    // differs would be piled up against the wrong coordinates, so it is refused here instead
+    {
+        const BamHeader& h = rd.header();
+        if (h.lens.size() != layout.slot_of_tid.size()) { err = bam_path + ": its header lists " + std::to_string(h.lens.size()) + " contigs, the first file's " + std::to_string(layout.slot_of_tid.size()); return false; }
+        for (const ShardLayout::Ctg& c : layout.ctgs)
+            if (h.lens[c.tid] != c.len) { err = bam_path + ": contig " + h.names[c.tid] + " has another length than in the first file's header"; return false; }
+    }
 
     // state of htslib's pileup iterator that the depth cap and the overlap hash depend on
     int cur_tid = -1; int32_t last_pos = -1;
@@ -206,7 +214,13 @@ bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& la
             return false;
         }
 
-        // ---- bam_plp_push: expiry of buffered reads, depth cap (Annex A.3)
+        // ---- bam_plp_push: the input must be coordinate sorted (htslib stops with "the input is not sorted"); the
+        // device-side index searches the positions and relies on it
+        if (c.tid < cur_tid || (c.tid == cur_tid && c.pos < last_pos)) {
+            err = bam_path + " is not coordinate sorted (read " + r.qname + ")";
+            return false;
+        }
+        // ---- expiry of buffered reads, depth cap (Annex A.3)
         if (c.tid != cur_tid) {
             while (!buffered.empty()) buffered.pop();
             olap.clear();

@@ -136,6 +136,9 @@ int run_text_mode(const std::string& first_line, FILE* in, const msnv_call_param
                 if (s < S) {
                     uint32_t c[5] = {0, 0, 0, 0, 0};
                     count_column(tok.c_str(), tok.size(), c);
+                    // 16-bit count lanes; a column is at most kTokLimit characters wide (call_vC.cpp:92-111 truncates
+                    // there), so this only guards the packing below against a change of that limit
+                    static_assert(kTokLimit <= 65535, "column counts are packed into 16-bit lanes");
                     const size_t o = ((size_t)tile * S + s) * MSNV_TILE + off;
                     acgt[o] = (uint64_t)c[0] | (uint64_t)c[1] << 16 | (uint64_t)c[2] << 32 | (uint64_t)c[3] << 48;
                     match[o] = (uint16_t)c[4];

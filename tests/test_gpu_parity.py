@@ -199,11 +199,13 @@ def test_empty_inputs(built, tmp_path):
         _same(o + ".indiv", g + ".indiv")
 
 
-@pytest.mark.parametrize("env", [{"MSNV_INDEX_BITMAP": "1"}, {"MSNV_INDEX_BITMAP": "0"}, {"MSNV_PILEUP_VARIANT": "0"}, {"MSNV_PILEUP_VARIANT": "1"}, {"MSNV_PILEUP_VARIANT": "2"},
-                                 {"MSNV_CHUNK_Q4": "1280"}], ids=lambda e: "-".join("%s=%s" % kv for kv in e.items()))
+@pytest.mark.parametrize("env", [{"MSNV_INDEX_BITMAP": "1"}, {"MSNV_INDEX_BITMAP": "0"}, {"MSNV_MAX_READS": "16"}, {"MSNV_MAX_READS": "255"},
+                                 {"MSNV_CHUNK_Q4": "1280"}, {"MSNV_CHUNK_Q4": "16384"}, {"MSNV_PILEUP_CTAS": "1"},
+                                 {"MSNV_MAX_READS": "40", "MSNV_CHUNK_Q4": "1280", "MSNV_PILEUP_CTAS": "2"}],
+                         ids=lambda e: "-".join("%s=%s" % kv for kv in e.items()))
 def test_kernel_variants_give_identical_output(env, datasets, tmp_path):
-    """Every launch-time choice of the library (occupancy bitmap for sparse shards, small/large chunk instantiation of
-    the pileup kernel, staging budget) must produce the same bytes."""
+    """Every launch-time choice of the library (occupancy bitmap for sparse shards; reads, quads per staged chunk of the
+    pileup kernel and therefore how many chunks an item takes; CTAs per SM) must produce the same bytes."""
     for name in ("c1_tiny", "c4_tiny_deep"):
         recipe = json.load(open(os.path.join(GOLDEN, name, "recipe.json")))
         data = datasets(recipe["preset"], recipe["scale"], recipe["samples"], **recipe["extra"])

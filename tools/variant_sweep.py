@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Tuning aid: one device-generated shard, msnv_shard_run under several MSNV_PILEUP_VARIANT / MSNV_CHUNK_Q4 settings."""
+"""Tuning aid: one device-generated shard, msnv_shard_run under several staging settings of the pileup kernel
+(MSNV_PILEUP_CTAS : MSNV_CHUNK_Q4 : MSNV_MAX_READS, empty = the library's own choice)."""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from metasnv_b200 import abi, harness as H
@@ -7,7 +8,7 @@ from metasnv_b200 import abi, harness as H
 ap = argparse.ArgumentParser()
 ap.add_argument("--preset", default="c2"); ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--samples", type=int, default=0); ap.add_argument("--steps", type=int, default=3)
-ap.add_argument("--settings", default="default,0,1,2,3,4", help="comma list of <variant|default>[:chunk_q4]")
+ap.add_argument("--settings", default="::,2::,3::,4::,5::", help="comma list of <ctas per SM>:<chunk_q4>:<max_reads>, empty fields = default")
 a = ap.parse_args()
 desc = H.describe(a.preset, a.scale, a.samples)
 ctx = abi.Context(0)
@@ -16,13 +17,11 @@ if first >= 0:
     ctx.shard_mask_position(first)
 ref_hits = None
 for setting in a.settings.split(","):
-    v, _, q = setting.partition(":")
-    for k in ("MSNV_PILEUP_VARIANT", "MSNV_CHUNK_Q4"):
+    fields = (setting.split(":") + ["", "", ""])[:3]
+    for k, v in zip(("MSNV_PILEUP_CTAS", "MSNV_CHUNK_Q4", "MSNV_MAX_READS"), fields):
         os.environ.pop(k, None)
-    if v != "default":
-        os.environ["MSNV_PILEUP_VARIANT"] = v
-    if q:
-        os.environ["MSNV_CHUNK_Q4"] = q
+        if v:
+            os.environ[k] = v
     ctx.shard_run(copy=False)
     ms = []
     for _ in range(a.steps):
