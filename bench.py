@@ -2,17 +2,24 @@
 """Benchmark of the hot path: pileup + call throughput in aligned bases/s on the BASELINE.json
 configuration "single 5 Mb genome, 1000 samples at ~10x" (configs[1], "c2").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1..c5|cov]
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...     (N > 1)
 
 One "step" = one pass of index -> pileup (with mate-overlap correction) -> call -> compaction -> gather
-over every read of the shard, inputs resident in HBM (`value`). `e2e` is the same pass through the
-C ABI with pinned HOST buffers: upload of all reads, the kernels, download of the hits.
-With N > 1 every rank owns one genome shard of the same shape (the sharding createOptimumSplit
-produces for N equal genomes); there is no collective on the data path (weak scaling).
+over every read of the shard, inputs resident in HBM (`value`; the copy of the hits to the host is timed and
+reported beside it). Shards that do not fit the device (c3 per-GPU shard, c5 at full size) are processed
+window by window (groups of contigs, msnv_window_*): `value` then sums the windows' kernel times.
+`e2e` is measured FROM BAM FILES through the drop-in programs (`samtools` stand-in | `snpCall`): BGZF inflate
+and BAM decode on the host cores, upload, kernels, text output - the same boundary the reference arm is
+timed at; host decode time is broken out. `e2e_h2d` is the same pass through the C ABI from pinned host
+arrays (upload + kernels + hits), which is what the host link allows.
+With N > 1 every rank owns one genome shard of the same shape (the sharding createOptimumSplit produces for
+N equal genomes; for c3 the N bins of its LPT assignment); there is no collective on the data path (weak
+scaling).
 The reference arm (`--impl reference`) and the `cpu_baseline` object time the CPU pipe
-`mpileup (oracle restatement) | snpCall (unmodified reference build)` on a bounded sample of the
-same workload; upstream samtools is not available in this image.
+`mpileup (oracle restatement) | snpCall (unmodified reference build)` on a bounded sample of the same
+workload; for workloads with several genomes the unchanged metaSNV.py drives it with --threads = host cores.
+Upstream samtools is not available in this image.
 """
 import argparse
 import json

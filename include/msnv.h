@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MSNV_ABI_VERSION 3
+#define MSNV_ABI_VERSION 4
 
 /* Positions per tile: contigs of a shard are laid out back to back in a "shard coordinate" space,
  * each starting at a multiple of MSNV_TILE, so a tile never spans two contigs. The kernels are written
@@ -115,12 +115,16 @@ typedef struct {
 /* Device-side timings of the last msnv_shard_run(), milliseconds (CUDA events on the context's
  * stream), plus the work it did. */
 typedef struct {
-    float    ms_index, ms_reserved, ms_pileup, ms_call, ms_compact, ms_gather, ms_total;
+    float    ms_index, ms_d2h /* copy of the hits to the host, not part of ms_total */;
+    float    ms_pileup /* mate-overlap pass + pileup kernel */, ms_call, ms_compact, ms_gather;
+    float    ms_total;          /* index + pileup + call + compact + gather */
     uint64_t n_items;           /* active (sample, tile) pairs */
     uint64_t n_reads;
-    uint64_t n_bases;           /* staged base slots resident for the shard (4 x quads, padding included) */
+    uint64_t n_bases;           /* staged base slots resident for the window (4 x quads, padding included) */
     uint32_t n_tiles;
     uint32_t kernel_launches;
+    uint32_t n_ranges;          /* ranges of tiles the run was split into to fit the tile budget (1 = none) */
+    float    ms_mate;           /* the mate-overlap pass alone (included in ms_pileup) */
 } msnv_timings;
 
 int         msnv_abi_version(void);
@@ -152,6 +156,21 @@ int msnv_shard_sync(msnv_ctx* ctx);
 /* Run pileup (with mpileup's mate-overlap quality correction), calling and compaction; fills *hits.
  * The uploaded reads are never modified, so it may be called repeatedly, e.g. with other parameters. */
 int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* params, msnv_hits* hits);
+/* ---- shards larger than device memory: position windows ----
+ * A shard may be processed as a sequence of windows [pos_lo, pos_hi) of shard coordinates (multiples of MSNV_TILE,
+ * ascending, disjoint), the way the reference streams through its input with O(samples) memory (call_vC.cpp:466-479).
+ * For each window the caller hands in, per sample, the reads that overlap it (pos < pos_hi and last covered position
+ * >= pos_lo; a read that straddles a boundary is given to both windows, mate links are window-local) and gets the
+ * called positions inside it. The context has two window slots: queue the uploads of window k+1 (slot (k+1) & 1)
+ * before calling msnv_window_run() for window k and the copies overlap its kernels. msnv_window_run() returns
+ * when the hits are on the host; the slot's host buffers may be reused then.
+ * msnv_shard_begin() opens the whole shard as one window in slot 0, which is what msnv_shard_add_sample() and
+ * msnv_shard_run() operate on. Whatever the window, count planes are produced for ranges of tiles that fit the
+ * free device memory (MSNV_TILE_BUDGET_MB overrides), so neither reads nor counts of a shard must fit the device. */
+int msnv_window_begin(msnv_ctx* ctx, uint32_t slot, uint32_t pos_lo, uint32_t pos_hi);
+int msnv_window_add_sample(msnv_ctx* ctx, uint32_t slot, uint32_t sample, const msnv_sample_reads* reads);
+int msnv_window_run(msnv_ctx* ctx, uint32_t slot, const msnv_call_params* params, msnv_hits* hits);
+
 /* Test/inspection hook: per-position A,C,G,T,N counts ([n][5], uint16) of one sample after the last
  * run, for shard coordinates [first, first+n). */
 int msnv_shard_counts(msnv_ctx* ctx, uint32_t sample, uint32_t first, uint32_t n, uint16_t* out);
@@ -184,11 +203,17 @@ typedef struct {
 /* first_column (optional): shard coordinate of the first pileup column, i.e. what the caller would
  * pass to msnv_shard_mask_position(); -1 when the shard has no reads. */
 int msnv_shard_synth(msnv_ctx* ctx, const msnv_synth_desc* desc, int64_t* first_column);
+/* The same in two steps, for shards that do not fit the device: msnv_shard_synth_ref() begins the shard and generates its
+ * reference; msnv_window_synth() then opens the window that covers contigs [ctg_lo, ctg_hi) in `slot` and fills it with
+ * their reads (msnv_window_run() processes it). msnv_shard_synth() = the reference + one window with every contig. */
+int msnv_shard_synth_ref(msnv_ctx* ctx, const msnv_synth_desc* desc, int64_t* first_column);
+int msnv_window_synth(msnv_ctx* ctx, uint32_t slot, const msnv_synth_desc* desc, uint32_t ctg_lo, uint32_t ctg_hi);
 
 /* Copy one sample of the open shard back to host arrays sized from *sizes (as returned by
  * msnv_shard_sample_sizes): used to stage pinned host buffers for end-to-end timing. */
-typedef struct { uint32_t n_reads, n_mated, max_span, reserved; uint64_t n_segs, n_q4; } msnv_sample_sizes;
-int msnv_shard_sample_sizes(msnv_ctx* ctx, uint32_t sample, msnv_sample_sizes* sizes);
+typedef struct { uint32_t n_reads, n_mated, max_span, reserved; uint64_t n_segs, n_q4, n_aligned /* sum of seg_len */; } msnv_sample_sizes;
+int msnv_shard_sample_sizes(msnv_ctx* ctx, uint32_t sample, msnv_sample_sizes* sizes);                  /* window slot 0 */
+int msnv_window_sample_sizes(msnv_ctx* ctx, uint32_t slot, uint32_t sample, msnv_sample_sizes* sizes);
 int msnv_shard_export_sample(msnv_ctx* ctx, uint32_t sample, int32_t* pos, uint32_t* seg_off, uint32_t* q4_off, int32_t* mate,
                              int32_t* seg_pos, uint16_t* seg_len, uint8_t* seq2, uint8_t* qual);
 /* Copy the shard's reference characters (n_positions bytes) back to the host. */

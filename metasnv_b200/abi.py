@@ -37,10 +37,10 @@ class Hits(C.Structure):
 
 
 class Timings(C.Structure):
-    _fields_ = [("ms_index", C.c_float), ("ms_reserved", C.c_float), ("ms_pileup", C.c_float), ("ms_call", C.c_float),
+    _fields_ = [("ms_index", C.c_float), ("ms_d2h", C.c_float), ("ms_pileup", C.c_float), ("ms_call", C.c_float),
                 ("ms_compact", C.c_float), ("ms_gather", C.c_float), ("ms_total", C.c_float),
                 ("n_items", C.c_uint64), ("n_reads", C.c_uint64), ("n_bases", C.c_uint64),
-                ("n_tiles", C.c_uint32), ("kernel_launches", C.c_uint32)]
+                ("n_tiles", C.c_uint32), ("kernel_launches", C.c_uint32), ("n_ranges", C.c_uint32), ("ms_mate", C.c_float)]
 
 
 class CovBlocks(C.Structure):
@@ -56,7 +56,7 @@ class SynthDesc(C.Structure):
 
 class SampleSizes(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_mated", C.c_uint32), ("max_span", C.c_uint32), ("reserved", C.c_uint32),
-                ("n_segs", C.c_uint64), ("n_q4", C.c_uint64)]
+                ("n_segs", C.c_uint64), ("n_q4", C.c_uint64), ("n_aligned", C.c_uint64)]
 
 
 _lib = None
@@ -86,6 +86,9 @@ def load():
     lib.msnv_shard_mask_position.argtypes = [C.c_void_p, C.c_uint32]
     lib.msnv_shard_sync.argtypes = [C.c_void_p]
     lib.msnv_shard_run.argtypes = [C.c_void_p, C.POINTER(CallParams), C.POINTER(Hits)]
+    lib.msnv_window_begin.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.msnv_window_add_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(SampleReads)]
+    lib.msnv_window_run.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(CallParams), C.POINTER(Hits)]
     lib.msnv_shard_counts.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.msnv_get_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
     lib.msnv_call_counts.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -97,6 +100,9 @@ def load():
     lib.msnv_pinned_free.restype = None
     lib.msnv_shard_synth.argtypes = [C.c_void_p, C.POINTER(SynthDesc), C.POINTER(C.c_int64)]
     lib.msnv_shard_sample_sizes.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(SampleSizes)]
+    lib.msnv_window_sample_sizes.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(SampleSizes)]
+    lib.msnv_shard_synth_ref.argtypes = [C.c_void_p, C.POINTER(SynthDesc), C.POINTER(C.c_int64)]
+    lib.msnv_window_synth.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(SynthDesc), C.c_uint32, C.c_uint32]
     lib.msnv_shard_export_sample.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 8
     lib.msnv_shard_export_ref.argtypes = [C.c_void_p, C.c_void_p]
     _lib = lib
@@ -214,8 +220,31 @@ class Context:
             setattr(r, k, _ptr(a[k]))
         self._check(self.lib.msnv_shard_add_sample(self.h, sample, C.byref(r)), "msnv_shard_add_sample")
 
-    def shard_synth(self, desc):
-        """desc: the JSON dict printed by `msnv_synth --describe`. Returns (n_positions, first_column)."""
+    # ---- position windows (shards larger than device memory)
+    def window_begin(self, slot, pos_lo, pos_hi):
+        self._keep_win = getattr(self, "_keep_win", {})
+        self._keep_win[slot] = []
+        self._check(self.lib.msnv_window_begin(self.h, slot, pos_lo, pos_hi), "msnv_window_begin")
+
+    def window_add_sample(self, slot, sample, arrays):
+        a = {k: np.ascontiguousarray(v) for k, v in arrays.items() if k != "max_span"}
+        self._keep_win[slot].append(a)
+        r = SampleReads()
+        r.n_reads = a["pos"].size
+        r.max_span = int(arrays["max_span"])
+        for k in SAMPLE_ARRAYS:
+            setattr(r, k, _ptr(a[k]))
+        self._check(self.lib.msnv_window_add_sample(self.h, slot, sample, C.byref(r)), "msnv_window_add_sample")
+
+    def window_run(self, slot, min_coverage=4, calling_threshold=4, min_fraction=0.01, copy=True):
+        p = CallParams(min_coverage, calling_threshold, min_fraction)
+        h = Hits()
+        self._check(self.lib.msnv_window_run(self.h, slot, C.byref(p), C.byref(h)), "msnv_window_run")
+        return HitsView(h) if copy else h
+
+    def shard_synth(self, desc, ref_only=False):
+        """desc: the JSON dict printed by `msnv_synth --describe`. Returns (n_positions, first_column).
+        ref_only: begin the shard and generate its reference; the reads come window by window (window_synth)."""
         cl = np.ascontiguousarray(desc["contig_len"], np.uint32)
         cg = np.ascontiguousarray(desc["contig_genome"], np.uint32)
         gs = np.ascontiguousarray(desc["genome_n_sub"], np.uint32)
@@ -227,10 +256,23 @@ class Context:
         d.n_contigs = cl.size
         d.contig_len, d.contig_genome, d.n_genomes, d.genome_n_sub = _ptr(cl), _ptr(cg), gs.size, _ptr(gs)
         first = C.c_int64(-1)
-        self._check(self.lib.msnv_shard_synth(self.h, C.byref(d), C.byref(first)), "msnv_shard_synth")
+        self._synth = (d, cl, cg, gs)
+        if ref_only:
+            self._check(self.lib.msnv_shard_synth_ref(self.h, C.byref(d), C.byref(first)), "msnv_shard_synth_ref")
+        else:
+            self._check(self.lib.msnv_shard_synth(self.h, C.byref(d), C.byref(first)), "msnv_shard_synth")
         n_pos = int(sum((int(x) + TILE - 1) // TILE * TILE for x in cl))
         self.n_positions = n_pos
         return n_pos, first.value
+
+    def window_synth(self, slot, ctg_lo, ctg_hi):
+        """Reads of contigs [ctg_lo, ctg_hi) of the description given to shard_synth(ref_only=True) into a window slot."""
+        self._check(self.lib.msnv_window_synth(self.h, slot, C.byref(self._synth[0]), ctg_lo, ctg_hi), "msnv_window_synth")
+
+    def window_sample_sizes(self, slot, sample):
+        z = SampleSizes()
+        self._check(self.lib.msnv_window_sample_sizes(self.h, slot, sample, C.byref(z)), "msnv_window_sample_sizes")
+        return z
 
     def sample_sizes(self, sample):
         z = SampleSizes()
@@ -304,3 +346,24 @@ class Context:
         hist = np.zeros((k, max_cov + 1), np.uint64)
         self._check(self.lib.msnv_cov_run(self.h, C.byref(b), max_cov, _ptr(cov_sum), _ptr(hist)), "msnv_cov_run")
         return cov_sum, hist
+
+
+def window_slice(arrays, pos_lo, pos_hi):
+    """The reads of one sample (dict as returned by Context.export_sample) that a window [pos_lo, pos_hi) needs, as a
+    new dict in the same layout: every read with pos < pos_hi that can reach pos_lo (pos + max_span > pos_lo), a
+    contiguous run of the coordinate-sorted reads; offsets re-based to 0, mate links re-based to the run (links that
+    leave it are dropped: such mates share no position inside the window)."""
+    pos = arrays["pos"]
+    span = int(arrays["max_span"])
+    lo = int(np.searchsorted(pos, pos_lo - span + 1, side="left"))
+    hi = int(np.searchsorted(pos, pos_hi, side="left"))
+    if hi <= lo:
+        return None
+    s0, s1 = int(arrays["seg_off"][lo]), int(arrays["seg_off"][hi])
+    q0, q1 = int(arrays["q4_off"][lo]), int(arrays["q4_off"][hi])
+    mate = arrays["mate"][lo:hi].astype(np.int64) - lo
+    mate[(mate < 0) | (mate >= hi - lo)] = -1
+    return {"max_span": span, "pos": pos[lo:hi].copy(), "seg_off": (arrays["seg_off"][lo:hi + 1] - s0).astype(np.uint32),
+            "q4_off": (arrays["q4_off"][lo:hi + 1] - q0).astype(np.uint32), "mate": mate.astype(np.int32),
+            "seg_pos": arrays["seg_pos"][s0:s1].copy(), "seg_len": arrays["seg_len"][s0:s1].copy(),
+            "seq2": arrays["seq2"][q0:q1].copy(), "qual": arrays["qual"][4 * q0:4 * q1].copy()}

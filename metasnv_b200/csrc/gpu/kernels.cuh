@@ -32,6 +32,7 @@ struct SampleDev {
     const uint16_t* seg_len;
     const uint8_t*  seq2;
     const uint8_t*  qual;
+    uint8_t*        fix;          // samples with mate links: per quad, the verdict of the mate-overlap rule (mate_kernel), else null
     uint32_t        n_reads, max_span;
 };
 
@@ -53,16 +54,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+// hint_ns > 0: the hardware may park the thread for up to that long between polls (fewer issue slots spent spinning)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 0)
 {
     uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
+    if (hint_ns) {
+        do {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
+        } while (!done);
+    } else {
+        do {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        } while (!done);
+    }
 }
 // global -> shared bulk copy (TMA, SASS UBLKCP); dst/src 16-byte aligned, bytes a multiple of 16
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
@@ -152,12 +164,16 @@ __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t* s_warp /*[33
 // index_kernel then skips the two binary searches of every pair whose tile and the tiles a read could
 // reach it from are all clear.
 __global__ void __launch_bounds__(256) mark_kernel(const SampleDev* __restrict__ samples, uint32_t words_per_sample,
-                                                   uint32_t* __restrict__ bitmap)
+                                                   uint32_t tile0, uint32_t n_tiles, uint32_t* __restrict__ bitmap)
 {
     const SampleDev sd = samples[blockIdx.y];
     uint32_t* bm = bitmap + (size_t)blockIdx.y * words_per_sample;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < sd.n_reads; i += gridDim.x * blockDim.x) {
-        const uint32_t t = (uint32_t)__ldg(sd.pos + i) / TILE;
+        // tile of the window the read starts in; reads that start in front of the window (they reach into it) count for its
+        // first tile, reads behind it for none
+        const int64_t ta = (int64_t)__ldg(sd.pos + i) / TILE - (int64_t)tile0;
+        if (ta >= (int64_t)n_tiles) continue;
+        const uint32_t t = ta < 0 ? 0u : (uint32_t)ta;
         // consecutive reads mostly share a tile: one atomic per (warp, tile)
         const uint32_t peers = __match_any_sync(__activemask(), t);
         if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicOr(bm + (t >> 5), 1u << (t & 31));
@@ -174,11 +190,12 @@ __global__ void __launch_bounds__(256) order_check_kernel(const SampleDev* __res
 
 template <bool EMIT>
 __global__ void __launch_bounds__(256) index_kernel(const SampleDev* __restrict__ samples, uint32_t n_samples,
-                                                    uint32_t n_tiles, uint32_t* __restrict__ block_sums,
+                                                    uint32_t tile0 /* first tile of the window */, uint32_t n_tiles /* tiles of the window */,
+                                                    uint32_t* __restrict__ block_sums,
                                                     Item* __restrict__ items, uint32_t* __restrict__ tile_begin,
                                                     uint2* __restrict__ range_cache /* [tiles*samples] or null: COUNT stores, EMIT reloads */,
                                                     const uint32_t* __restrict__ bitmap /* mark_kernel's, or null */, uint32_t words_per_sample,
-                                                    unsigned long long* __restrict__ item_reads /* COUNT: sum of r_hi - r_lo over the items */)
+                                                    unsigned long long* __restrict__ item_reads /* COUNT: [0] sum, [1] maximum of r_hi - r_lo over the items */)
 {
     __shared__ uint32_t s_warp[33];
     const uint64_t pair = (uint64_t)blockIdx.x * 256 + threadIdx.x;
@@ -202,7 +219,7 @@ __global__ void __launch_bounds__(256) index_kernel(const SampleDev* __restrict_
             }
             if (maybe) {
                 const int32_t* pos = samples[s].pos;
-                const int64_t t0 = (int64_t)t * TILE, k_lo = t0 - (int64_t)samples[s].max_span + 1;
+                const int64_t t0 = (int64_t)(tile0 + t) * TILE, k_lo = t0 - (int64_t)samples[s].max_span + 1;
                 if (bitmap) {
                     // sparse shard: the sample covers a few contigs of many, its read density is anything but even
                     r_lo = lower_bound_i32(pos, n, k_lo);
@@ -225,14 +242,14 @@ __global__ void __launch_bounds__(256) index_kernel(const SampleDev* __restrict_
     if (!EMIT) {
         if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
         // reads staged over all items: sizes the pileup kernel's staging buffers
-        uint32_t nr = active ? r_hi - r_lo : 0u;
+        uint32_t nr = active ? r_hi - r_lo : 0u, nmax = nr;
         #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) nr += __shfl_down_sync(0xffffffffu, nr, d);
-        if ((threadIdx.x & 31) == 0 && nr) atomicAdd(item_reads, (unsigned long long)nr);
+        for (int d = 16; d > 0; d >>= 1) { nr += __shfl_down_sync(0xffffffffu, nr, d); nmax = max(nmax, __shfl_down_sync(0xffffffffu, nmax, d)); }
+        if ((threadIdx.x & 31) == 0 && nr) { atomicAdd(item_reads, (unsigned long long)nr); atomicMax(item_reads + 1, (unsigned long long)nmax); }
     } else {
         const uint32_t slot = block_sums[blockIdx.x] + rank;     // block_sums holds exclusive offsets now
-        if (active) items[slot] = Item{s, t, r_lo, r_hi};
-        if (pair < n_pairs && s == 0) tile_begin[t] = slot;
+        if (active) items[slot] = Item{s, tile0 + t, r_lo, r_hi};
+        if (pair < n_pairs && s == 0) tile_begin[t] = slot;          // tile_begin is indexed by the window's tiles
     }
 }
 
@@ -288,6 +305,76 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ v, ui
 }
 
 // ------------------------------------------------------------------------------------------------
+// mate overlap (htslib tweak_overlap_quality, SURVEY.md Annex A.2): for every pair the host linked, at every
+// reference position both mates align a base to, the rule decides which of the two bases is still counted
+// (overlap_rule.h: a corrected quality is only ever compared with the threshold, so its verdict is one bit).
+// The uploaded reads are never modified: the verdicts go to a side array `fix`, one byte per quad of the
+// sample - low nibble: positions the rule overrides, high nibble: whether the base passes there - which the
+// pileup kernel stages next to the bases. Cleared and rebuilt by every run (fix_clear_kernel, mate_kernel).
+// One thread per pair: the two mates are a few reads apart in a shallow sample and thousands apart in a deep
+// one; either way every load is an independent global access and millions of pairs are in flight.
+// ------------------------------------------------------------------------------------------------
+// bit 0 of the four byte lanes -> a nibble, and back
+__device__ __forceinline__ uint32_t lanes_to_nibble(uint32_t x) { return ((x & 0x01010101u) * 0x01020408u) >> 24; }
+__device__ __forceinline__ uint32_t nibble_to_lanes(uint32_t n) { return ((n & 0xfu) * 0x00204081u) & 0x01010101u; }
+
+__global__ void __launch_bounds__(256) fix_clear_kernel(const SampleDev* __restrict__ samples)
+{
+    const SampleDev sd = samples[blockIdx.y];
+    if (!sd.fix || sd.n_reads == 0) return;
+    const uint32_t n16 = (__ldg(sd.q4_off + sd.n_reads) + 15u) / 16u;        // the array has spare bytes behind it
+    uint4* f = reinterpret_cast<uint4*>(sd.fix);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) f[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+__global__ void __launch_bounds__(256) mate_kernel(const SampleDev* __restrict__ samples)
+{
+    const SampleDev sd = samples[blockIdx.y];
+    if (!sd.fix) return;
+    const uint32_t* __restrict__ qual32 = reinterpret_cast<const uint32_t*>(sd.qual);
+    uint32_t* __restrict__ fix32 = reinterpret_cast<uint32_t*>(sd.fix);
+    const uint32_t nq_total = sd.n_reads ? __ldg(sd.q4_off + sd.n_reads) : 0u;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < sd.n_reads; r += gridDim.x * blockDim.x) {
+        const int32_t mt = __ldg(sd.mate + r);
+        if (mt <= (int32_t)r || (uint32_t)mt >= sd.n_reads) continue;         // the earlier mate (a) handles the pair
+        const uint32_t sa0 = __ldg(sd.seg_off + r), sa1 = __ldg(sd.seg_off + r + 1), sb0 = __ldg(sd.seg_off + mt), sb1 = __ldg(sd.seg_off + mt + 1);
+        uint32_t qa = __ldg(sd.q4_off + r);                                   // first quad of a's next segment
+        const uint32_t qb0 = __ldg(sd.q4_off + mt);
+        for (uint32_t ka = sa0; ka < sa1; ++ka) {
+            const int32_t ax = __ldg(sd.seg_pos + ka);
+            const uint32_t al = __ldg(sd.seg_len + ka);
+            uint32_t qb = qb0;
+            for (uint32_t kb = sb0; kb < sb1; ++kb) {
+                const int32_t bx = __ldg(sd.seg_pos + kb);
+                const uint32_t bl = __ldg(sd.seg_len + kb);
+                const int32_t lo = max(ax, bx), hi = min(ax + (int32_t)al, bx + (int32_t)bl);
+                #pragma unroll 4
+                for (int32_t P = lo >> 2; P < ((hi + 3) >> 2); ++P) {         // (empty when the segments share no position)
+                    const uint32_t ia = qa + (uint32_t)(P - (ax >> 2)), ib = qb + (uint32_t)(P - (bx >> 2));
+                    if (ia >= nq_total || ib >= nq_total) continue;           // segments and offsets disagree (the pileup kernel reports it)
+                    const uint32_t va = __ldg(qual32 + ia), vb = __ldg(qual32 + ib);
+                    const uint32_t d = msnv_spread_bases((uint32_t)__ldg(sd.seq2 + ia) ^ (uint32_t)__ldg(sd.seq2 + ib));
+                    const uint32_t msk = ((P << 2) >= lo && (P << 2) + 4 <= hi) ? 0xffffffffu : msnv_quad_mask(P << 2, lo, hi);
+                    uint32_t na, nb;
+                    msnv_overlap_pass4(va, vb, d, msk, na, nb);               // masked lanes: flag | 16 (passes) or flag | 0
+                    const uint32_t ovr = lanes_to_nibble(msk);
+                    const uint32_t fa = ovr | (lanes_to_nibble(na >> 4) & ovr) << 4, fb = ovr | (lanes_to_nibble(nb >> 4) & ovr) << 4;
+                    // a quad the rule covers whole belongs to this segment combination alone: plain byte stores. Two
+                    // combinations can meet in a quad at their ends (with disjoint positions): OR into the byte there.
+                    if (msk == 0xffffffffu) { sd.fix[ia] = (uint8_t)fa; sd.fix[ib] = (uint8_t)fb; }
+                    else {
+                        atomicOr(fix32 + (ia >> 2), fa << (8u * (ia & 3u)));
+                        atomicOr(fix32 + (ib >> 2), fb << (8u * (ib & 3u)));
+                    }
+                }
+                qb += (((uint32_t)bx & 3u) + bl + 3u) >> 2;
+            }
+            qa += (((uint32_t)ax & 3u) + al + 3u) >> 2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // count tiles: what the pileup kernel writes and the call / gather kernels read.
 // Every work item (sample, tile) owns a slot of SLOT_BYTES in HBM holding six count planes of
 // TILE positions:
@@ -340,43 +427,40 @@ __global__ void expect_kernel(const uint8_t* __restrict__ ref, uint32_t n, uint8
 // Consumer warps, per chunk (reads arrive as position-aligned segments, include/msnv.h: a staged
 // quad holds four consecutive positions starting at a multiple of four, so a quad is either on the
 // tile or off it and its four bases are handled with byte-lane arithmetic):
-//   1. one thread per read: segment geometry -> s_seg; every staged quad that lies on the tile is
-//      tagged with its tile-relative index (four tags per store), the qualities of the few quads off
-//      the tile are zeroed (the scatter's threshold test then rejects them like any poor base);
-//      reads with an overlapping mate are queued
-//   2. mate-overlap quality correction on the staged qualities (overlap_rule.h, SURVEY.md Annex
-//      A.2), eight lanes per pair, one quad of both mates per lane and step; a mate staged in
-//      another chunk is read, pristine, from global memory. The reads in HBM are never modified.
-//   3. scatter: a thread takes FOUR consecutive staged quads per step (one 128-bit load of the
-//      qualities, one word of bases, one word of tags). Per quad: quality test on four byte lanes,
-//      one shared-memory atomic into plane D, and a compare with the expected letters; only lanes
-//      that hold a mismatch loop over their set bits and add to a letter plane.
-//   4. last chunk of an item: narrow items copy the byte planes to HBM (6 KB, 128-bit stores) and
+//   1. one thread per read: every staged quad that lies on the tile is tagged with its tile-relative
+//      index (four tags per store), the qualities of the few quads off the tile are zeroed (the
+//      scatter's threshold test then rejects them like any poor base)
+//   2. scatter: a thread takes FOUR consecutive staged quads per step (one 128-bit load of the
+//      qualities, one word each of bases, tags and - for samples with mates - overlap verdicts).
+//      Per quad: quality test on four byte lanes (overridden where mate_kernel left a verdict), one
+//      shared-memory atomic into plane D, and a compare with the expected letters; only lanes that
+//      hold a mismatch loop over their set bits and add to a letter plane.
+//   3. last chunk of an item: narrow items copy the byte planes to HBM (6 KB, 128-bit stores) and
 //      clear them; wide items fold every chunk into 16-bit lanes held in registers (a chunk stages
 //      at most 255 reads) and store those.
+// The mate-overlap rule itself runs before this kernel (mate_kernel): no read ever waits for its mate here.
 //
-// Shared memory (dynamic, see pileup_smem_layout): mbarriers | 6 count planes | s_seg | overlap
-// queue | quad tags | PL_STAGES x { header, q4_off, seg_off, mate, seg_pos, seg_len, expected
-// letters, bases, qualities }. Every TMA destination is 16-byte aligned; sources are the 16-byte
+// Shared memory (dynamic, see pileup_smem_layout): mbarriers | 6 count planes | quad tags |
+// PL_STAGES x { header, q4_off, seg_off, seg_pos, seg_len, expected letters, bases, overlap
+// verdicts, qualities }. Every TMA destination is 16-byte aligned; sources are the 16-byte
 // aligned addresses at or below the first element needed (the arrays are 256-byte aligned and have
 // 32 spare bytes behind them), so a stage holds a few elements in front of and behind the chunk.
 // ------------------------------------------------------------------------------------------------
-constexpr int PL_CONSUMERS = 128;
-constexpr int PL_THREADS = PL_CONSUMERS + 32;
+// consumer threads per CTA: a template parameter of the kernel (128 or 256; the CTA has one more warp, the producer)
 constexpr int PL_STAGES = 2;
 constexpr uint32_t CHUNK_Q4_MIN = MSNV_MAX_READ_BASES / 4 + 2 * MSNV_MAX_READ_SEGMENTS;   // a single read always fits
 constexpr uint32_t CHUNK_SEGS_MIN = MSNV_MAX_READ_SEGMENTS;
-constexpr uint32_t CHUNK_FIRST = 1u, CHUNK_LAST = 2u, CHUNK_WIDE = 4u, CHUNK_STOP = 8u;
+constexpr uint32_t CHUNK_FIRST = 1u, CHUNK_LAST = 2u, CHUNK_WIDE = 4u, CHUNK_STOP = 8u, CHUNK_FIX = 16u /* the sample has mate verdicts */;
 
 // limits of one staged chunk, chosen per launch from the shape of the shard
-struct PileupShape { uint32_t max_reads, max_segs, chunk_q4; };
+struct PileupShape { uint32_t max_reads, max_segs, chunk_q4, has_fix /* some sample carries mate verdicts */, wait_hint_ns, ablate /* measurement only: phases to skip */; };
 
 struct ChunkHdr { uint32_t m, nq4, q4_0, sg_0, nseg, c0, item, sample, tile, flags, pad[6]; };
 static_assert(sizeof(ChunkHdr) == 64, "header is one 64-byte block");
 
 struct PileupSmem {
-    uint32_t bar, misc, cnt, seg, pairs, tags, stage0, stage_bytes;              // byte offsets
-    uint32_t o_hdr, o_q4, o_sg, o_mt, o_sp, o_sl, o_exp, o_seq, o_qual;         // within a stage
+    uint32_t bar, cnt, tags, stage0, stage_bytes;                               // byte offsets
+    uint32_t o_hdr, o_q4, o_sg, o_sp, o_sl, o_exp, o_seq, o_fix, o_qual;        // within a stage
     uint32_t total;
 };
 
@@ -386,11 +470,8 @@ __host__ __device__ inline PileupSmem pileup_smem_layout(const PileupShape sh)
 {
     PileupSmem L{};
     uint32_t o = 0;
-    L.bar = o;   o += 64;
-    L.misc = o;  o += 64;
+    L.bar = o;   o += 128;
     L.cnt = o;   o += N_PLANES * TILE;
-    L.seg = o;   o += up_to(sh.max_segs, 4) * 16;
-    L.pairs = o; o += up_to(sh.max_reads * 2, 16);
     L.tags = o;  o += up_to(sh.chunk_q4, 16) + 16;
     L.stage0 = up_to(o, 128);
     uint32_t s = 0;
@@ -398,11 +479,11 @@ __host__ __device__ inline PileupSmem pileup_smem_layout(const PileupShape sh)
     L.o_hdr = s;  s += 64;
     L.o_q4 = s;   s += mw * 4;
     L.o_sg = s;   s += mw * 4;
-    L.o_mt = s;   s += mw * 4;
     L.o_sp = s;   s += (up_to(sh.max_segs, 4) + 8) * 4;
     L.o_sl = s;   s += (up_to(sh.max_segs, 8) + 16) * 2;
     L.o_exp = s;  s += TILE;
     L.o_seq = s;  s += up_to(sh.chunk_q4, 16) + 32;
+    L.o_fix = s;  s += sh.has_fix ? up_to(sh.chunk_q4, 16) + 32 : 0;
     L.o_qual = s; s += 4 * up_to(sh.chunk_q4, 16) + 32;
     L.stage_bytes = up_to(s, 128);
     L.total = L.stage0 + PL_STAGES * L.stage_bytes;
@@ -423,40 +504,81 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // barrier among the consumer warps only (the producer warp never joins it)
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PL_CONSUMERS) : "memory"); }
+template <int CONSUMERS>
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory"); }
 
-// ---- producer: one chunk into the next stage of the ring (whole warp; lane 0 writes and issues)
-__device__ __forceinline__ void pileup_issue_chunk(uint8_t* smem, const PileupSmem& L, uint32_t& chunk_no, const SampleDev* __restrict__ sd,
+// the arrays of one sample the producer copies from
+struct SrcPtrs {
+    const uint32_t* q4_off; const uint32_t* seg_off; const int32_t* seg_pos; const uint16_t* seg_len;
+    const uint8_t* seq2; const uint8_t* qual; const uint8_t* fix;
+};
+__device__ __forceinline__ SrcPtrs load_src_ptrs(const SampleDev* __restrict__ sd)
+{
+    SrcPtrs p;
+    p.q4_off = sd->q4_off; p.seg_off = sd->seg_off; p.seg_pos = sd->seg_pos; p.seg_len = sd->seg_len;
+    p.seq2 = sd->seq2; p.qual = sd->qual; p.fix = sd->fix;
+    return p;
+}
+
+// source address and size of the seven bulk copies of a chunk (16-byte aligned addresses at or below the first element
+// needed, sizes rounded up to 16 bytes)
+struct ChunkCopies { const void* src[7]; uint32_t bytes[7]; };
+__device__ __forceinline__ ChunkCopies chunk_copies(const SrcPtrs& p, uint32_t c0, uint32_t m, uint32_t q4_0, uint32_t nq4, uint32_t sg_0, uint32_t nseg)
+{
+    const uint32_t dm = c0 & 3u, ds = sg_0 & 3u, dl = sg_0 & 7u, dq = q4_0 & 3u, d16 = q4_0 & 15u;
+    ChunkCopies c;
+    c.src[0] = p.q4_off + (c0 - dm);             c.bytes[0] = up_to(dm + m + 1u, 4) * 4u;
+    c.src[1] = p.seg_off + (c0 - dm);            c.bytes[1] = c.bytes[0];
+    c.src[2] = p.fix ? p.fix + (q4_0 - d16) : nullptr; c.bytes[2] = p.fix ? up_to(d16 + nq4, 16) : 0u;   // same geometry as the bases
+    c.src[3] = p.seg_pos + (sg_0 - ds);          c.bytes[3] = up_to(ds + nseg, 4) * 4u;
+    c.src[4] = p.seg_len + (sg_0 - dl);          c.bytes[4] = up_to(dl + nseg, 8) * 2u;
+    c.src[5] = p.seq2 + (q4_0 - d16);            c.bytes[5] = up_to(d16 + nq4, 16);
+    c.src[6] = p.qual + 4u * (size_t)(q4_0 - dq); c.bytes[6] = up_to(dq + nq4, 4) * 4u;
+    return c;
+}
+__device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+// bring a chunk's source bytes into L2 ahead of the copy that stages them (the copy then takes an L2 round trip
+// instead of an HBM one: with two stages per CTA the time from "stage free" to "stage full" bounds the CTA's rate)
+__device__ __forceinline__ void prefetch_chunk(const SrcPtrs& p, uint32_t c0, uint32_t m, uint32_t q4_0, uint32_t nq4, uint32_t sg_0, uint32_t nseg)
+{
+    const ChunkCopies c = chunk_copies(p, c0, m, q4_0, nq4, sg_0, nseg);
+    #pragma unroll
+    for (int i = 2; i < 7; ++i) if (c.bytes[i]) prefetch_l2(c.src[i], c.bytes[i]);      // the offsets were touched when the item was sized
+}
+
+// ---- producer: one chunk into the next stage of the ring (whole warp waits; lane `issuer` writes the header and issues)
+__device__ __forceinline__ void pileup_issue_chunk(uint8_t* smem, const PileupSmem& L, const PileupShape& sh, uint32_t& chunk_no, uint32_t issuer, const SrcPtrs& src,
                                                    const uint8_t* __restrict__ expect, uint32_t item, uint32_t sample, uint32_t tile, uint32_t c0,
                                                    uint32_t m, uint32_t q4_0, uint32_t nq4, uint32_t sg_0, uint32_t nseg, uint32_t flags)
 {
     uint64_t* full = (uint64_t*)(smem + L.bar);
     uint64_t* empty = full + PL_STAGES;
     const uint32_t s = chunk_no % PL_STAGES, ph = (chunk_no / PL_STAGES) & 1u;
-    mbar_wait(empty + s, ph ^ 1u);
-    if ((threadIdx.x & 31) == 0) {
+    mbar_wait(empty + s, ph ^ 1u, sh.wait_hint_ns);
+    if ((threadIdx.x & 31) == issuer) {
         uint8_t* stage = smem + L.stage0 + s * L.stage_bytes;
         ChunkHdr* h = (ChunkHdr*)(stage + L.o_hdr);
         h->m = m; h->nq4 = nq4; h->q4_0 = q4_0; h->sg_0 = sg_0; h->nseg = nseg; h->c0 = c0;
-        h->item = item; h->sample = sample; h->tile = tile; h->flags = flags;
-        const uint32_t dm = c0 & 3u, ds = sg_0 & 3u, dl = sg_0 & 7u, dq = q4_0 & 3u, d16 = q4_0 & 15u;
-        const uint32_t b_q4 = up_to(dm + m + 1u, 4) * 4u, b_mt = up_to(dm + m, 4) * 4u;
-        const uint32_t b_sp = up_to(ds + nseg, 4) * 4u, b_sl = up_to(dl + nseg, 8) * 2u;
-        const uint32_t b_seq = up_to(d16 + nq4, 16), b_qual = up_to(dq + nq4, 4) * 4u;
+        h->item = item; h->sample = sample; h->tile = tile; h->flags = flags | (src.fix ? CHUNK_FIX : 0u);
+        const ChunkCopies c = chunk_copies(src, c0, m, q4_0, nq4, sg_0, nseg);
+        const uint32_t dst[7] = {L.o_q4, L.o_sg, L.o_fix, L.o_sp, L.o_sl, L.o_seq, L.o_qual};
+        uint32_t total = (uint32_t)TILE;
+        #pragma unroll
+        for (int i = 0; i < 7; ++i) total += c.bytes[i];
         fence_proxy_async();
-        mbar_expect_tx(full + s, 2u * b_q4 + b_mt + b_sp + b_sl + b_seq + b_qual + (uint32_t)TILE);
-        tma_load_1d(stage + L.o_q4, sd->q4_off + (c0 - dm), b_q4, full + s);
-        tma_load_1d(stage + L.o_sg, sd->seg_off + (c0 - dm), b_q4, full + s);
-        if (b_mt) tma_load_1d(stage + L.o_mt, sd->mate + (c0 - dm), b_mt, full + s);
-        if (b_sp) tma_load_1d(stage + L.o_sp, sd->seg_pos + (sg_0 - ds), b_sp, full + s);
-        if (b_sl) tma_load_1d(stage + L.o_sl, sd->seg_len + (sg_0 - dl), b_sl, full + s);
+        mbar_expect_tx(full + s, total);
+        #pragma unroll
+        for (int i = 0; i < 7; ++i) if (c.bytes[i]) tma_load_1d(stage + dst[i], c.src[i], c.bytes[i], full + s);
         tma_load_1d(stage + L.o_exp, expect + (size_t)tile * TILE, TILE, full + s);
-        if (b_seq) tma_load_1d(stage + L.o_seq, sd->seq2 + (q4_0 - d16), b_seq, full + s);
-        if (b_qual) tma_load_1d(stage + L.o_qual, sd->qual + 4u * (size_t)(q4_0 - dq), b_qual, full + s);
     }
     __syncwarp();
     ++chunk_no;
 }
+
+constexpr uint32_t PREFETCH_AHEAD = 4;       // items between a chunk's L2 prefetch and its copy
 
 __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem& L, const PileupShape sh, const SampleDev* __restrict__ samples,
                                                 const Item* __restrict__ items, uint32_t n_items, const uint8_t* __restrict__ expect,
@@ -465,56 +587,84 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
     const uint32_t lane = threadIdx.x & 31, G = gridDim.x;
     uint32_t chunk_no = 0;
     for (uint64_t base = blockIdx.x; base < n_items; base += 32ull * G) {
-        // ---- 32 upcoming items of this CTA, one per lane: item record and the offsets that size it
+        // ---- 32 upcoming items of this CTA, one per lane: item record, source arrays and the offsets that size the item
         const uint64_t mine = base + (uint64_t)lane * G;
         uint4 it = make_uint4(0u, 0u, 0u, 0u);
         uint32_t q_lo = 0, q_hi = 0, g_lo = 0, g_hi = 0;
+        SrcPtrs src{};
+        bool whole = false;                  // the item fits one stage
         if (mine < n_items) {
             it = __ldg(reinterpret_cast<const uint4*>(items) + mine);
-            const SampleDev* sd = samples + it.x;
-            const uint32_t* q4p = sd->q4_off; const uint32_t* sgp = sd->seg_off;
-            q_lo = __ldg(q4p + it.z); q_hi = __ldg(q4p + it.w);
-            g_lo = __ldg(sgp + it.z); g_hi = __ldg(sgp + it.w);
+            src = load_src_ptrs(samples + it.x);
+            q_lo = __ldg(src.q4_off + it.z); q_hi = __ldg(src.q4_off + it.w);
+            g_lo = __ldg(src.seg_off + it.z); g_hi = __ldg(src.seg_off + it.w);
+            whole = it.w - it.z <= sh.max_reads && q_hi - q_lo <= sh.chunk_q4 && g_hi - g_lo <= sh.max_segs;
+            if (whole && lane < PREFETCH_AHEAD) prefetch_chunk(src, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo, g_hi - g_lo);
         }
         for (uint32_t k = 0; k < 32u; ++k) {
             const uint64_t idx = base + (uint64_t)k * G;
             if (idx >= n_items) break;
-            const uint32_t sample = __shfl_sync(0xffffffffu, it.x, k), tile = __shfl_sync(0xffffffffu, it.y, k);
-            const uint32_t r_lo = __shfl_sync(0xffffffffu, it.z, k), r_hi = __shfl_sync(0xffffffffu, it.w, k);
-            const uint32_t ql = __shfl_sync(0xffffffffu, q_lo, k), qh = __shfl_sync(0xffffffffu, q_hi, k);
-            const uint32_t gl = __shfl_sync(0xffffffffu, g_lo, k), gh = __shfl_sync(0xffffffffu, g_hi, k);
-            const SampleDev* sd = samples + sample;
-            const uint32_t n = r_hi - r_lo;
-            const uint32_t wide = item_is_wide(r_lo, r_hi) ? CHUNK_WIDE : 0u;
-            if (n <= sh.max_reads && qh - ql <= sh.chunk_q4 && gh - gl <= sh.max_segs) {
-                pileup_issue_chunk(smem, L, chunk_no, sd, expect, (uint32_t)idx, sample, tile, r_lo, n, ql, qh - ql, gl, gh - gl,
-                                   CHUNK_FIRST | CHUNK_LAST | wide);
+            if (lane == k + PREFETCH_AHEAD && whole) prefetch_chunk(src, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo, g_hi - g_lo);
+            if (__shfl_sync(0xffffffffu, (int)whole, k)) {                   // the lane that owns the item issues it from its own registers
+                pileup_issue_chunk(smem, L, sh, chunk_no, k, src, expect, (uint32_t)mine, it.x, it.y, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo,
+                                   g_hi - g_lo, CHUNK_FIRST | CHUNK_LAST | (item_is_wide(it.z, it.w) ? CHUNK_WIDE : 0u));
                 continue;
             }
             // ---- the item needs several chunks: longest prefix of the remaining reads within the three limits
-            const uint32_t* q4p = sd->q4_off; const uint32_t* sgp = sd->seg_off;
-            uint32_t c0 = r_lo, qc = ql, gc = gl, first = CHUNK_FIRST;
+            const uint32_t sample = __shfl_sync(0xffffffffu, it.x, k), tile = __shfl_sync(0xffffffffu, it.y, k);
+            const uint32_t r_lo = __shfl_sync(0xffffffffu, it.z, k), r_hi = __shfl_sync(0xffffffffu, it.w, k);
+            const uint32_t ql = __shfl_sync(0xffffffffu, q_lo, k), gl = __shfl_sync(0xffffffffu, g_lo, k);
+            const SrcPtrs sp = load_src_ptrs(samples + sample);
+            const uint32_t* q4p = sp.q4_off; const uint32_t* sgp = sp.seg_off;
+            const uint32_t wide = item_is_wide(r_lo, r_hi) ? CHUNK_WIDE : 0u;
+            uint32_t c0 = r_lo, qc = ql, gc = gl;
             while (c0 < r_hi) {
+                // Optimistic sizing of the next 32 chunks at once: max_reads reads each, one probe per lane (the stage is
+                // sized so that this many reads normally fit). A deep item takes hundreds of chunks; sizing them one by one
+                // would put two or three dependent global round trips between any two copies.
+                const uint32_t b_l = min(c0 + lane * sh.max_reads, r_hi), e_l = min(b_l + sh.max_reads, r_hi);
+                const uint32_t qe = __ldg(q4p + e_l), ge = __ldg(sgp + e_l);
+                uint32_t qb = __shfl_up_sync(0xffffffffu, qe, 1), gb = __shfl_up_sync(0xffffffffu, ge, 1);
+                if (lane == 0) { qb = qc; gb = gc; }
+                const bool fit = e_l == b_l || (qe - qb <= sh.chunk_q4 && ge - gb <= sh.max_segs);
+                const uint32_t okmask = __ballot_sync(0xffffffffu, fit);
+                const uint32_t n_ok = okmask == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~okmask) - 1u;      // leading chunks that fit
+                if (n_ok) {
+                    const uint32_t fl = (b_l == r_lo ? CHUNK_FIRST : 0u) | (e_l == r_hi ? CHUNK_LAST : 0u) | wide;
+                    if (lane < PREFETCH_AHEAD && lane < n_ok && e_l > b_l) prefetch_chunk(sp, b_l, e_l - b_l, qb, qe - qb, gb, ge - gb);
+                    uint32_t done_to = c0, done_q = qc, done_g = gc;
+                    for (uint32_t kk = 0; kk < n_ok; ++kk) {
+                        const uint32_t bk = __shfl_sync(0xffffffffu, b_l, kk), ek = __shfl_sync(0xffffffffu, e_l, kk);
+                        if (ek == bk) break;                                             // past the end of the item
+                        if (lane == kk + PREFETCH_AHEAD && lane < n_ok && e_l > b_l) prefetch_chunk(sp, b_l, e_l - b_l, qb, qe - qb, gb, ge - gb);
+                        pileup_issue_chunk(smem, L, sh, chunk_no, kk, sp, expect, (uint32_t)idx, sample, tile, b_l, e_l - b_l, qb, qe - qb, gb, ge - gb, fl);
+                        done_to = ek; done_q = __shfl_sync(0xffffffffu, qe, kk); done_g = __shfl_sync(0xffffffffu, ge, kk);
+                    }
+                    c0 = done_to; qc = done_q; gc = done_g;
+                    continue;
+                }
+                // the first of them does not fit (long reads, many segments): longest prefix of reads within the three limits
                 const uint32_t cap = min(sh.max_reads, r_hi - c0), step = (cap + 31u) / 32u;
                 const uint32_t pi = min((lane + 1u) * step, cap);
-                bool fit = __ldg(q4p + c0 + pi) - qc <= sh.chunk_q4 && __ldg(sgp + c0 + pi) - gc <= sh.max_segs;
-                const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, fit));
+                bool fits = __ldg(q4p + c0 + pi) - qc <= sh.chunk_q4 && __ldg(sgp + c0 + pi) - gc <= sh.max_segs;
+                const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, fits));
                 uint32_t m = cap;
                 if (cnt < 32u) {                     // lanes 0..cnt-1 fit, lane cnt does not: refine between the two probes
                     const uint32_t b0 = cnt * step, pj = b0 + lane + 1u;
-                    fit = false;
-                    if (lane + 1u < step && pj <= cap) fit = __ldg(q4p + c0 + pj) - qc <= sh.chunk_q4 && __ldg(sgp + c0 + pj) - gc <= sh.max_segs;
-                    m = b0 + __popc(__ballot_sync(0xffffffffu, fit));
+                    fits = false;
+                    if (lane + 1u < step && pj <= cap) fits = __ldg(q4p + c0 + pj) - qc <= sh.chunk_q4 && __ldg(sgp + c0 + pj) - gc <= sh.max_segs;
+                    m = b0 + __popc(__ballot_sync(0xffffffffu, fits));
                 }
+                const uint32_t first = c0 == r_lo ? CHUNK_FIRST : 0u;
                 if (m == 0) {                        // a single read over the documented limits: host validation failed
                     if (lane == 0) atomicExch(err_flag, 1);
-                    pileup_issue_chunk(smem, L, chunk_no, sd, expect, (uint32_t)idx, sample, tile, c0, 0u, qc, 0u, gc, 0u, first | CHUNK_LAST | wide);
+                    pileup_issue_chunk(smem, L, sh, chunk_no, 0u, sp, expect, (uint32_t)idx, sample, tile, c0, 0u, qc, 0u, gc, 0u, first | CHUNK_LAST | wide);
                     break;
                 }
                 const uint32_t qn = __ldg(q4p + c0 + m), gn = __ldg(sgp + c0 + m);
-                pileup_issue_chunk(smem, L, chunk_no, sd, expect, (uint32_t)idx, sample, tile, c0, m, qc, qn - qc, gc, gn - gc,
+                pileup_issue_chunk(smem, L, sh, chunk_no, 0u, sp, expect, (uint32_t)idx, sample, tile, c0, m, qc, qn - qc, gc, gn - gc,
                                    first | (c0 + m == r_hi ? CHUNK_LAST : 0u) | wide);
-                c0 += m; qc = qn; gc = gn; first = 0u;
+                c0 += m; qc = qn; gc = gn;
             }
         }
     }
@@ -522,14 +672,18 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
     uint64_t* full = (uint64_t*)(smem + L.bar);
     uint64_t* empty = full + PL_STAGES;
     const uint32_t s = chunk_no % PL_STAGES, ph = (chunk_no / PL_STAGES) & 1u;
-    mbar_wait(empty + s, ph ^ 1u);
+    mbar_wait(empty + s, ph ^ 1u, sh.wait_hint_ns);
     if (lane == 0) {
         ((ChunkHdr*)(smem + L.stage0 + s * L.stage_bytes + L.o_hdr))->flags = CHUNK_STOP;
         mbar_arrive(full + s);
     }
 }
 
-__global__ void __launch_bounds__(PL_THREADS, 4)
+// CONSUMERS: consumer threads (128: four CTAs per SM at the standard shape; 256: three larger ones).
+// HAS_WIDE: the shard has items with more than 255 reads (deep coverage); without them the 16-bit accumulators and
+// their registers do not exist.
+template <int CONSUMERS, bool HAS_WIDE>
+__global__ void __launch_bounds__(CONSUMERS + 32, CONSUMERS == 128 ? 4 : 3)
 pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items, const PileupShape sh,
               const uint8_t* __restrict__ expect, uint8_t* __restrict__ tiles /*[n_items][SLOT_BYTES]*/, int* __restrict__ err_flag)
 {
@@ -537,55 +691,54 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     const PileupSmem L = pileup_smem_layout(sh);
     uint64_t* full = (uint64_t*)(smem + L.bar);
     uint64_t* empty = full + PL_STAGES;
-    uint32_t* s_misc = (uint32_t*)(smem + L.misc);
     uint32_t* s_cnt = (uint32_t*)(smem + L.cnt);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < PL_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        s_misc[0] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (uint32_t k = threadIdx.x; k < (uint32_t)(N_PLANES * TILE_QUADS); k += PL_THREADS) s_cnt[k] = 0;
+    for (uint32_t k = threadIdx.x; k < (uint32_t)(N_PLANES * TILE_QUADS); k += CONSUMERS + 32) s_cnt[k] = 0;
     __syncthreads();
 
-    if (threadIdx.x >= PL_CONSUMERS) {
+    if (threadIdx.x >= CONSUMERS) {
         pileup_producer(smem, L, sh, samples, items, n_items, expect, err_flag);
         return;
     }
 
     // ------------------------------------------------------------------------------------ consumers
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
-    uint4* s_seg = (uint4*)(smem + L.seg);
-    uint16_t* s_pairs = (uint16_t*)(smem + L.pairs);
+    const uint32_t tid = threadIdx.x;
     uint8_t* s_tags = smem + L.tags;
-    // wide items: per plane and owned quad (2 * tid, 2 * tid + 1), 16-bit lanes: [0] = positions 0 and 2, [1] = positions 1 and 3
-    uint32_t acc[N_PLANES][2][2];
+    // wide items: per plane and owned quad (QPT * tid + k), 16-bit lanes: [0] = positions 0 and 2, [1] = positions 1 and 3
+    constexpr int QPT = TILE_QUADS / CONSUMERS;                 // quads a thread folds (2 or 1)
+    uint32_t acc[HAS_WIDE ? N_PLANES : 1][QPT][2];
     #pragma unroll
-    for (int c = 0; c < N_PLANES; ++c) { acc[c][0][0] = acc[c][0][1] = acc[c][1][0] = acc[c][1][1] = 0; }
+    for (int c = 0; c < (HAS_WIDE ? N_PLANES : 1); ++c)
+        #pragma unroll
+        for (int k = 0; k < QPT; ++k) acc[c][k][0] = acc[c][k][1] = 0;
 
     for (uint32_t chunk_no = 0;; ++chunk_no) {
         const uint32_t st = chunk_no % PL_STAGES, ph = (chunk_no / PL_STAGES) & 1u;
         uint8_t* stage = smem + L.stage0 + st * L.stage_bytes;
-        mbar_wait(full + st, ph);
+        mbar_wait(full + st, ph, sh.wait_hint_ns);
         const ChunkHdr* h = (const ChunkHdr*)(stage + L.o_hdr);
         const uint32_t flags = h->flags;
         if (flags & CHUNK_STOP) break;
         const uint32_t m = h->m, nq4 = h->nq4, q4_0 = h->q4_0, sg_0 = h->sg_0, nseg = h->nseg, c0 = h->c0, item = h->item;
         const int32_t p0 = (int32_t)(h->tile * TILE);
-        const SampleDev* __restrict__ sd = samples + h->sample;
         const uint32_t dm = c0 & 3u, dq = q4_0 & 3u, c12 = q4_0 & 12u;
         const uint32_t* s_q4 = (const uint32_t*)(stage + L.o_q4) + dm;          // s_q4[t] = q4_off[c0 + t], t <= m
         const uint32_t* s_sgo = (const uint32_t*)(stage + L.o_sg) + dm;
-        const int32_t* s_mate = (const int32_t*)(stage + L.o_mt) + dm;
         const int32_t* s_sp = (const int32_t*)(stage + L.o_sp) + (sg_0 & 3u);   // s_sp[k] = seg_pos[sg_0 + k], k < nseg
         const uint16_t* s_sl = (const uint16_t*)(stage + L.o_sl) + (sg_0 & 7u);
-        uint8_t* s_seq = stage + L.o_seq + c12;                                 // s_seq[B]: bases of buffer quad B
-        uint8_t* s_qual = stage + L.o_qual;                                     // qualities of buffer quad B at byte 4 * B
-        uint32_t* s_qw = (uint32_t*)s_qual;
+        uint32_t* s_qw = (uint32_t*)(stage + L.o_qual);                         // qualities of buffer quad B in word B
+        uint8_t* s_fx = stage + L.o_fix + c12;                                  // overlap verdicts of buffer quad B (samples with mates)
+        const bool has_fix = (flags & CHUNK_FIX) != 0;
         const uint32_t nbq = dq + nq4, ngroups = (nbq + 3u) >> 2;               // staged quad g is buffer quad g + dq
+        // a quad that must not count (off the tile, in front of or behind the chunk): no quality passes and no verdict overrides
+        auto mute = [&](uint32_t g) { s_qw[g] = 0; if (has_fix) s_fx[g] = 0; };
 
-        // ---- 1. one thread per read: segment geometry, tags of the quads on the tile, zeroed qualities off it
-        for (uint32_t t = tid; t < m; t += PL_CONSUMERS) {
+        // ---- 1. one thread per read: tags of the quads on the tile, zeroed qualities off it
+        for (uint32_t t = tid; t < m; t += CONSUMERS) {
             const uint32_t k0 = s_sgo[t] - sg_0, k1 = s_sgo[t + 1] - sg_0;
             uint32_t B = s_q4[t] - q4_0 + dq;                                   // first buffer quad of the next segment
             const uint32_t B_end = s_q4[t + 1] - q4_0 + dq;
@@ -596,140 +749,96 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                 const uint32_t a = (uint32_t)p & 3u;
                 const int32_t nq = (int32_t)((a + len + 3u) >> 2);
                 const int32_t jw = (p - (int32_t)a - p0) >> 2;                  // tile-relative index of the segment's first quad
-                if (B + (uint32_t)nq > B_end) {                                 // segments and offsets disagree: refuse, stay in bounds
-                    atomicExch(err_flag, 2);
-                    for (uint32_t kk = k; kk < k1; ++kk) s_seg[kk] = make_uint4(0u, 0u, 0u, 0u);
-                    for (uint32_t g = B; g < B_end; ++g) s_qw[g] = 0;
-                    B = B_end;
-                    break;
-                }
-                s_seg[k] = make_uint4((uint32_t)p, len, 4u * B + a, (uint32_t)jw);
+                if (B + (uint32_t)nq > B_end) break;                            // segments and offsets disagree: flagged below
                 int32_t i_lo = jw < 0 ? -jw : 0; if (i_lo > nq) i_lo = nq;
                 int32_t i_hi = TILE_QUADS - jw; if (i_hi > nq) i_hi = nq; if (i_hi < i_lo) i_hi = i_lo;
-                for (int32_t i = 0; i < i_lo; ++i) s_qw[B + i] = 0;
-                for (int32_t i = i_hi; i < nq; ++i) s_qw[B + i] = 0;
+                for (int32_t i = 0; i < i_lo; ++i) mute(B + (uint32_t)i);
+                for (int32_t i = i_hi; i < nq; ++i) mute(B + (uint32_t)i);
                 uint32_t g = B + (uint32_t)i_lo, tv = (uint32_t)(jw + i_lo);
                 const uint32_t e = B + (uint32_t)i_hi;                          // tags tv .. tv + (e - g) - 1 are within 0..255
-                for (; (g & 3u) && g < e; ++g, ++tv) s_tags[g] = (uint8_t)tv;
-                for (; g + 4u <= e; g += 4u, tv += 4u) *reinterpret_cast<uint32_t*>(s_tags + g) = tv * 0x01010101u + 0x03020100u;
-                for (; g < e; ++g, ++tv) s_tags[g] = (uint8_t)tv;
+                if (!(sh.ablate & 2u)) {   // up to three single tags to a word boundary, words of four consecutive tags, up to three single tags
+                    uint32_t hn = (0u - g) & 3u; if (hn > e - g) hn = e - g;
+                    if (hn > 0u) s_tags[g] = (uint8_t)tv;
+                    if (hn > 1u) s_tags[g + 1] = (uint8_t)(tv + 1u);
+                    if (hn > 2u) s_tags[g + 2] = (uint8_t)(tv + 2u);
+                    g += hn; tv += hn;
+                    uint32_t wv = tv * 0x01010101u + 0x03020100u;                   // no lane passes 255: all four quads are on the tile
+                    uint32_t* tw = reinterpret_cast<uint32_t*>(s_tags + g);
+                    const uint32_t nw = (e - g) >> 2;
+                    uint32_t w = 0;
+                    for (; w + 2u <= nw; w += 2u, wv += 0x08080808u) { tw[w] = wv; tw[w + 1] = wv + 0x04040404u; }
+                    if (w < nw) { tw[w] = wv; ++w; }
+                    g += 4u * nw; tv += 4u * nw;
+                    const uint32_t tn = e - g;
+                    if (tn > 0u) s_tags[g] = (uint8_t)tv;
+                    if (tn > 1u) s_tags[g + 1] = (uint8_t)(tv + 1u);
+                    if (tn > 2u) s_tags[g + 2] = (uint8_t)(tv + 2u);
+                }
                 B += (uint32_t)nq;
             }
             if (B != B_end) {                                                   // quads no segment owns: keep them out of the counts
                 atomicExch(err_flag, 2);
-                for (uint32_t g = B; g < B_end; ++g) s_qw[g] = 0;
-            }
-            const int32_t mt = s_mate[t];
-            if (mt >= 0) {                                                      // overlap task: once per pair when both mates are here
-                const bool mate_here = (uint32_t)mt >= c0 && (uint32_t)mt < c0 + m;
-                if (!mate_here || c0 + t < (uint32_t)mt) s_pairs[atomicAdd(&s_misc[0], 1u)] = (uint16_t)t;
+                for (uint32_t g = B; g < B_end; ++g) mute(g);
             }
         }
-        if (tid == PL_CONSUMERS - 1) {                                          // elements in front of and behind the chunk in the buffer
-            for (uint32_t g = 0; g < dq; ++g) s_qw[g] = 0;
-            for (uint32_t g = nbq; g < 4u * ngroups; ++g) s_qw[g] = 0;
+        if (tid == CONSUMERS - 1) {                                             // elements in front of and behind the chunk in the buffer
+            for (uint32_t g = 0; g < dq; ++g) mute(g);
+            for (uint32_t g = nbq; g < 4u * ngroups; ++g) mute(g);
         }
-        consumer_sync();
+        consumer_sync<CONSUMERS>();
 
-        // ---- 2. mate-overlap quality correction, restricted to this tile's positions (other tiles are counted by other
-        // items). Pairs with both mates in the chunk: both are rewritten from pristine values. Mates outside the chunk (only
-        // when a tile needs several chunks): this read alone is rewritten, the mate's pristine data come from global memory.
-        const uint32_t n_tasks = s_misc[0];
-        if (n_tasks) {
-            // eight lanes per task (four tasks per warp). Two segment combinations of one pair can touch the same quality
-            // word (segments of one mate that are adjacent inside a segment of the other): the group's lanes re-converge
-            // between combinations.
-            const uint32_t l8 = lane & 7u, gmask = 0xffu << (lane & 24u);
-            for (uint32_t t = tid >> 3; t < n_tasks; t += PL_CONSUMERS / 8) {
-                const uint32_t i = s_pairs[t];
-                const int32_t mt = s_mate[i];
-                const bool self_is_a = c0 + i < (uint32_t)mt;
-                const bool mate_here = (uint32_t)mt >= c0 && (uint32_t)mt < c0 + m;
-                const uint32_t sa0 = s_sgo[i] - sg_0, sa1 = s_sgo[i + 1] - sg_0;
-                if (mate_here) {
-                    const uint32_t j = (uint32_t)mt - c0;
-                    const uint32_t sb0 = s_sgo[j] - sg_0, sb1 = s_sgo[j + 1] - sg_0;
-                    for (uint32_t ka = sa0; ka < sa1; ++ka) {
-                        const uint4 A = s_seg[ka];
-                        for (uint32_t kb = sb0; kb < sb1; ++kb) {
-                            const uint4 Bs = s_seg[kb];
-                            const int32_t lo = max(max((int32_t)A.x, (int32_t)Bs.x), p0);
-                            const int32_t hi = min(min((int32_t)(A.x + A.y), (int32_t)(Bs.x + Bs.y)), p0 + TILE);
-                            if (lo < hi) {
-                                // four positions per lane and step: both mates are stored position-aligned, so the quads of the
-                                // common range line up word for word
-                                const uint32_t za0 = A.z - (A.x & 3u) - 4u * (A.x >> 2), zb0 = Bs.z - (Bs.x & 3u) - 4u * (Bs.x >> 2);
-                                for (int32_t P = (lo >> 2) + (int32_t)l8; P < ((hi + 3) >> 2); P += 8) {
-                                    const uint32_t za = za0 + 4u * (uint32_t)P, zb = zb0 + 4u * (uint32_t)P;   // byte index of the quad in s_qual
-                                    const uint32_t va = *reinterpret_cast<const uint32_t*>(s_qual + za), vb = *reinterpret_cast<const uint32_t*>(s_qual + zb);
-                                    const uint32_t xa = msnv_spread_bases(s_seq[za >> 2]), xb = msnv_spread_bases(s_seq[zb >> 2]);
-                                    uint32_t na, nb;
-                                    msnv_overlap_rule4(va, vb, xa, xb, msnv_quad_mask(P << 2, lo, hi), na, nb);
-                                    *reinterpret_cast<uint32_t*>(s_qual + za) = na; *reinterpret_cast<uint32_t*>(s_qual + zb) = nb;
-                                }
-                            }
-                            __syncwarp(gmask);
-                        }
-                    }
-                } else {
-                    // the mate is staged in another chunk: read its segments and pristine bytes from global memory
-                    const uint32_t ms0 = __ldg(sd->seg_off + mt), ms1 = __ldg(sd->seg_off + mt + 1);
-                    uint32_t mq = __ldg(sd->q4_off + mt);                  // first quad of the mate's next segment
-                    for (uint32_t ks = ms0; ks < ms1; ++ks) {
-                        const int32_t bx = __ldg(sd->seg_pos + ks);
-                        const uint32_t bl = __ldg(sd->seg_len + ks), ba0 = (uint32_t)bx & 3u;
-                        const uint32_t* mqual4 = reinterpret_cast<const uint32_t*>(sd->qual) + mq;   // the segment's first quad
-                        const uint8_t* mseq = sd->seq2 + mq;
-                        for (uint32_t ka = sa0; ka < sa1; ++ka) {
-                            const uint4 A = s_seg[ka];
-                            const int32_t lo = max(max((int32_t)A.x, bx), p0);
-                            const int32_t hi = min(min((int32_t)(A.x + A.y), bx + (int32_t)bl), p0 + TILE);
-                            if (lo < hi) {
-                                const uint32_t zs0 = A.z - (A.x & 3u) - 4u * (A.x >> 2);
-                                for (int32_t P = (lo >> 2) + (int32_t)l8; P < ((hi + 3) >> 2); P += 8) {
-                                    const uint32_t zs = zs0 + 4u * (uint32_t)P, im = (uint32_t)(P - (bx >> 2));   // the mate's quad index
-                                    const uint32_t vs = *reinterpret_cast<const uint32_t*>(s_qual + zs), vm = __ldg(mqual4 + im);
-                                    const uint32_t xs = msnv_spread_bases(s_seq[zs >> 2]), xm = msnv_spread_bases(__ldg(mseq + im));
-                                    const uint32_t msk = msnv_quad_mask(P << 2, lo, hi);
-                                    uint32_t na, nb;
-                                    if (self_is_a) msnv_overlap_rule4(vs, vm, xs, xm, msk, na, nb); else msnv_overlap_rule4(vm, vs, xm, xs, msk, nb, na);
-                                    *reinterpret_cast<uint32_t*>(s_qual + zs) = na;
-                                }
-                            }
-                            __syncwarp(gmask);
-                        }
-                        mq += (ba0 + bl + 3u) >> 2;
-                    }
-                }
-            }
-            consumer_sync();                // qualities are final
-            if (tid == 0) s_misc[0] = 0;    // every thread has read the count; the next chunk queues after one more barrier
-        }
-
-        // ---- 3. scatter: four consecutive buffer quads per thread and step
+        // ---- 2. scatter: four consecutive buffer quads per thread and step
         {
-            const uint32_t a_q = smem_u32(s_qual), a_s = smem_u32(s_seq), a_g = smem_u32(s_tags);
+            const uint32_t a_q = smem_u32(s_qw), a_s = smem_u32(stage + L.o_seq) + c12, a_f = smem_u32(stage + L.o_fix) + c12, a_g = smem_u32(s_tags);
             const uint32_t a_c = smem_u32(s_cnt), a_e = smem_u32(stage + L.o_exp);
-            for (uint32_t u = tid; u < ngroups; u += PL_CONSUMERS) {
+            for (uint32_t u = tid; u < ((sh.ablate & 1u) ? 0u : ngroups); u += CONSUMERS) {
                 const uint4 qv = lds_v4(a_q + 16u * u);
                 const uint32_t sw = lds_u32(a_s + 4u * u), tw = lds_u32(a_g + 4u * u);
                 const uint32_t qa[4] = {qv.x, qv.y, qv.z, qv.w};
-                uint32_t xs[4], mm[4], ac[4], nn_any = 0, mm_any = 0;
-                #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t q = qa[k];
-                    const uint32_t j = __byte_perm(tw, 0u, 0x4440u + k);                // tile-relative quad
-                    ac[k] = a_c + 4u * j;                                               // its word in plane D
-                    xs[k] = msnv_spread_bases(__byte_perm(sw, 0u, 0x4440u + k));        // one 2-bit base per byte lane
-                    const uint32_t v = (q & 0x7f7f7f7fu) + 0x73737373u;                 // bit 7 of a lane: quality >= 13
-                    const uint32_t ok = (v & ~q & 0x80808080u) >> 7;                    // ... and the base is A/C/G/T
-                    const uint32_t d = xs[k] ^ lds_u32(a_e + 4u * j);                   // differs from the expected letter?
-                    red_shared_add(ac[k], ok);
-                    mm[k] = (d | (d >> 1)) & ok;
-                    mm_any |= mm[k];
-                    nn_any |= v & q;
+                uint32_t xs[4], mm[4], ac[4], nn[4], nn_any = 0, mm_any = 0;
+                if (!has_fix) {
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t q = qa[k];
+                        const uint32_t j = __byte_perm(tw, 0u, 0x4440u + k);                // tile-relative quad
+                        ac[k] = a_c + 4u * j;                                               // its word in plane D
+                        xs[k] = msnv_spread_bases(__byte_perm(sw, 0u, 0x4440u + k));        // one 2-bit base per byte lane
+                        const uint32_t v = (q & 0x7f7f7f7fu) + 0x73737373u;                 // bit 7 of a lane: quality >= 13
+                        uint32_t ok;                                                        // ... and the base is A/C/G/T
+                        asm("lop3.b32 %0, %1, %2, 0x80808080, 0x20;" : "=r"(ok) : "r"(v), "r"(q));    // v & ~q & 0x80808080
+                        ok >>= 7;
+                        const uint32_t d = xs[k] ^ lds_u32(a_e + 4u * j);                   // differs from the expected letter?
+                        red_shared_add(ac[k], ok);
+                        mm[k] = (d | (d >> 1)) & ok;
+                        mm_any |= mm[k];
+                        nn[k] = v & q;                                                      // bit 7: counted base that is not A/C/G/T
+                        nn_any |= nn[k];
+                    }
+                } else {
+                    // the sample has mate verdicts: where the overlap rule spoke (low nibble of the quad's fix byte) its verdict
+                    // (high nibble) replaces the quality test
+                    const uint32_t fw = lds_u32(a_f + 4u * u);
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t q = qa[k];
+                        const uint32_t j = __byte_perm(tw, 0u, 0x4440u + k);
+                        ac[k] = a_c + 4u * j;
+                        xs[k] = msnv_spread_bases(__byte_perm(sw, 0u, 0x4440u + k));
+                        const uint32_t f = __byte_perm(fw, 0u, 0x4440u + k);
+                        const uint32_t ovr = nibble_to_lanes(f), val = nibble_to_lanes(f >> 4);
+                        const uint32_t qp = (((q & 0x7f7f7f7fu) + 0x73737373u) >> 7) & 0x01010101u;   // quality >= 13
+                        const uint32_t pass = (qp & ~ovr) | (val & ovr);
+                        const uint32_t fl = (q >> 7) & 0x01010101u;                         // the base is not A/C/G/T
+                        const uint32_t ok = pass & ~fl;
+                        const uint32_t d = xs[k] ^ lds_u32(a_e + 4u * j);
+                        red_shared_add(ac[k], ok);
+                        mm[k] = (d | (d >> 1)) & ok;
+                        mm_any |= mm[k];
+                        nn[k] = (pass & fl) << 7;
+                        nn_any |= nn[k];
+                    }
                 }
-                if (mm_any) {                                                           // counted bases that are not the expected letter:
+                if (mm_any && !(sh.ablate & 32u)) {                                     // counted bases that are not the expected letter:
                     #pragma unroll                                                      // only the lanes that hold one loop over their set bits
                     for (int k = 0; k < 4; ++k) {
                         uint32_t r = mm[k];
@@ -743,45 +852,45 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                 if (nn_any & 0x80808080u) {                                             // rare: counted non-ACGT bases
                     #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint32_t q = qa[k];
-                        const uint32_t nn = ((q & 0x7f7f7f7fu) + 0x73737373u) & q & 0x80808080u;
-                        if (nn) red_shared_add(ac[k] + PLANE_N * (uint32_t)TILE, nn >> 7);
+                        const uint32_t n7 = nn[k] & 0x80808080u;
+                        if (n7) red_shared_add(ac[k] + PLANE_N * (uint32_t)TILE, n7 >> 7);
                     }
                 }
             }
         }
         fence_proxy_async();                // this thread's writes to the stage are ordered before the copies that refill it
-        consumer_sync();
+        consumer_sync<CONSUMERS>();
         if (tid == 0) mbar_arrive(empty + st);
 
         // ---- 4. counts of the chunk
-        if (flags & CHUNK_WIDE) {
-            uint2* cnt2 = reinterpret_cast<uint2*>(s_cnt);
+        if (HAS_WIDE && (flags & CHUNK_WIDE)) {
             #pragma unroll
-            for (int c = 0; c < N_PLANES; ++c) {
-                const uint2 w = cnt2[c * (TILE_QUADS / 2) + tid];
-                cnt2[c * (TILE_QUADS / 2) + tid] = make_uint2(0u, 0u);
-                acc[c][0][0] += w.x & 0x00ff00ffu; acc[c][0][1] += (w.x >> 8) & 0x00ff00ffu;
-                acc[c][1][0] += w.y & 0x00ff00ffu; acc[c][1][1] += (w.y >> 8) & 0x00ff00ffu;
-            }
-            if (flags & CHUNK_LAST) {
-                uint4* dst = reinterpret_cast<uint4*>(tiles + (size_t)item * SLOT_BYTES);
+            for (int c = 0; c < (HAS_WIDE ? N_PLANES : 1); ++c)
                 #pragma unroll
-                for (int c = 0; c < N_PLANES; ++c) {
-                    // 16-bit plane c, positions 8 * tid .. 8 * tid + 7
-                    dst[c * (TILE / 8) + tid] = make_uint4((acc[c][0][0] & 0xffffu) | (acc[c][0][1] << 16), (acc[c][0][0] >> 16) | (acc[c][0][1] & 0xffff0000u),
-                                                           (acc[c][1][0] & 0xffffu) | (acc[c][1][1] << 16), (acc[c][1][0] >> 16) | (acc[c][1][1] & 0xffff0000u));
-                    acc[c][0][0] = acc[c][0][1] = acc[c][1][0] = acc[c][1][1] = 0;
+                for (int k = 0; k < QPT; ++k) {
+                    const uint32_t slot = c * TILE_QUADS + QPT * tid + k;
+                    const uint32_t w = s_cnt[slot];
+                    s_cnt[slot] = 0;
+                    acc[c][k][0] += w & 0x00ff00ffu; acc[c][k][1] += (w >> 8) & 0x00ff00ffu;
                 }
+            if (flags & CHUNK_LAST) {
+                uint2* dst = reinterpret_cast<uint2*>(tiles + (size_t)item * SLOT_BYTES);
+                #pragma unroll
+                for (int c = 0; c < (HAS_WIDE ? N_PLANES : 1); ++c)
+                    #pragma unroll
+                    for (int k = 0; k < QPT; ++k) {
+                        // 16-bit plane c, positions 4 * (QPT * tid + k) .. + 3
+                        dst[c * (TILE / 4) + QPT * tid + k] = make_uint2((acc[c][k][0] & 0xffffu) | (acc[c][k][1] << 16), (acc[c][k][0] >> 16) | (acc[c][k][1] & 0xffff0000u));
+                        acc[c][k][0] = acc[c][k][1] = 0;
+                    }
             }
-        } else if (flags & CHUNK_LAST) {
+        } else if ((flags & CHUNK_LAST) && !(sh.ablate & 8u)) {
             uint4* cnt4 = reinterpret_cast<uint4*>(s_cnt);
             uint4* dst = reinterpret_cast<uint4*>(tiles + (size_t)item * SLOT_BYTES);
-            #pragma unroll
-            for (int i = 0; i < N_PLANES * TILE / 16 / PL_CONSUMERS; ++i) {
-                const uint4 w = cnt4[i * PL_CONSUMERS + tid];
-                cnt4[i * PL_CONSUMERS + tid] = make_uint4(0u, 0u, 0u, 0u);
-                dst[i * PL_CONSUMERS + tid] = w;
+            for (uint32_t i = tid; i < (uint32_t)(N_PLANES * TILE / 16); i += CONSUMERS) {
+                const uint4 w = cnt4[i];
+                cnt4[i] = make_uint4(0u, 0u, 0u, 0u);
+                dst[i] = w;
             }
         }
         // no barrier here: the next chunk touches the counters again only after its own barriers
@@ -855,9 +964,10 @@ constexpr int CALL_THREADS = TILE_QUADS;
 
 template <bool HI_THR>
 __global__ void __launch_bounds__(CALL_THREADS)
-call_kernel(const uint8_t* __restrict__ tiles, const Item* __restrict__ items, const uint32_t* __restrict__ tile_begin,
+call_kernel(const uint8_t* __restrict__ tiles /* slot of item `item0` first */, const Item* __restrict__ items, uint32_t item0,
+            const uint32_t* __restrict__ tile_begin /* of this launch's first tile */, uint32_t tile_abs0 /* its shard tile index */,
             const uint8_t* __restrict__ ref, const uint8_t* __restrict__ expect, CallParamsDev prm, int text_mode,
-            uint8_t* __restrict__ flags, uint32_t* __restrict__ tile_hits)
+            uint8_t* __restrict__ flags /* of this launch's first tile */, uint32_t* __restrict__ tile_hits)
 {
     __shared__ uint32_t s_hits;
     const uint32_t t = blockIdx.x, tid = threadIdx.x;
@@ -885,7 +995,7 @@ call_kernel(const uint8_t* __restrict__ tiles, const Item* __restrict__ items, c
             #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const bool live = i + u < blk_end && !item_is_wide(it[u].z, it[u].w);
-                const uint8_t* base = tiles + (size_t)(i + u) * SLOT_BYTES + lane_off;
+                const uint8_t* base = tiles + (size_t)(i + u - item0) * SLOT_BYTES + lane_off;
                 #pragma unroll
                 for (int c = 0; c < N_PLANES; ++c) w[u][c] = live ? __ldg(reinterpret_cast<const uint32_t*>(base + c * TILE)) : 0u;
             }
@@ -901,7 +1011,7 @@ call_kernel(const uint8_t* __restrict__ tiles, const Item* __restrict__ items, c
                 #pragma unroll
                 for (int c = 0; c < N_PLANES; ++c) { s16[c][0] += w[u][c] & 0x00ff00ffu; s16[c][1] += (w[u][c] >> 8) & 0x00ff00ffu; }
                 if (i + u < blk_end && item_is_wide(it[u].z, it[u].w)) {                  // deep coverage: 16-bit planes, compared as integers
-                    const uint8_t* base = tiles + (size_t)(i + u) * SLOT_BYTES + 2u * lane_off;
+                    const uint8_t* base = tiles + (size_t)(i + u - item0) * SLOT_BYTES + 2u * lane_off;
                     uint32_t v[N_PLANES][4];
                     #pragma unroll
                     for (int c = 0; c < N_PLANES; ++c) {
@@ -932,7 +1042,7 @@ call_kernel(const uint8_t* __restrict__ tiles, const Item* __restrict__ items, c
 
     uint32_t out = 0, n_flagged = 0;
     if (i1 > i0) {
-        const size_t p4 = (size_t)t * TILE + lane_off;
+        const size_t p4 = (size_t)(tile_abs0 + t) * TILE + lane_off;
         const uint32_t rw = *reinterpret_cast<const uint32_t*>(ref + p4), ew = *reinterpret_cast<const uint32_t*>(expect + p4);
         #pragma unroll
         for (int p = 0; p < 4; ++p) {
@@ -970,13 +1080,13 @@ call_kernel(const uint8_t* __restrict__ tiles, const Item* __restrict__ items, c
 }
 // ordered compaction of the flagged positions: tile_hits holds exclusive offsets on entry
 __global__ void __launch_bounds__(TILE)
-compact_kernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ tile_hits, uint32_t* __restrict__ hit_pos,
+compact_kernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ tile_hits, uint32_t tile_abs0, uint32_t* __restrict__ hit_pos,
                uint8_t* __restrict__ hit_pop, uint8_t* __restrict__ hit_ind)
 {
     __shared__ uint32_t s_warp[33];
     const uint32_t t = blockIdx.x, tid = threadIdx.x;
-    const size_t p = (size_t)t * TILE + tid;
-    const uint32_t f = flags[p];
+    const size_t p = (size_t)(tile_abs0 + t) * TILE + tid;        // shard coordinate; flags and tile_hits are this launch's
+    const uint32_t f = flags[(size_t)t * TILE + tid];
     uint32_t total;
     const uint32_t r = block_rank(f != 0, s_warp, total);
     if (f) {
@@ -999,14 +1109,14 @@ __device__ __forceinline__ void load_planes(const uint8_t* __restrict__ tiles, u
 // per hit: per-sample coverage and allele counts (zero for samples without an item on the tile)
 // plus population totals. One CTA of 128 threads per hit; outputs were zero-filled by the host side.
 __global__ void __launch_bounds__(128)
-gather_kernel(const uint8_t* __restrict__ tiles, const Item* __restrict__ items, const uint32_t* __restrict__ tile_begin,
-              const uint8_t* __restrict__ ref, const uint8_t* __restrict__ expect, const uint32_t* __restrict__ hit_pos,
+gather_kernel(const uint8_t* __restrict__ tiles, const Item* __restrict__ items, uint32_t item0,
+              const uint32_t* __restrict__ tile_begin /* of the window's first tile */, uint32_t win_tile0, const uint8_t* __restrict__ ref, const uint8_t* __restrict__ expect, const uint32_t* __restrict__ hit_pos,
               uint32_t n_samples, int text_mode, uint16_t* __restrict__ cov, uint16_t* __restrict__ allele, uint32_t* __restrict__ total)
 {
     __shared__ uint32_t s_tot[5];
     const uint32_t h = blockIdx.x, tid = threadIdx.x;
     const uint32_t p = hit_pos[h];
-    const uint32_t t = p / TILE, off = p % TILE;
+    const uint32_t t = p / TILE - win_tile0, off = p % TILE;
     const uint32_t ch = text_mode ? 6u : ref_channel(ref[p]);
     const uint32_t e = expect[p] & 3u;
     if (tid < 5) s_tot[tid] = 0;
@@ -1015,7 +1125,7 @@ gather_kernel(const uint8_t* __restrict__ tiles, const Item* __restrict__ items,
     for (uint32_t i = tile_begin[t] + tid; i < tile_begin[t + 1]; i += blockDim.x) {
         const uint4 it = __ldg(reinterpret_cast<const uint4*>(items) + i);
         uint32_t v[N_PLANES];
-        load_planes(tiles, i, item_is_wide(it.z, it.w), off, v);
+        load_planes(tiles, i - item0, item_is_wide(it.z, it.w), off, v);
         const uint32_t rest = v[0] - (v[1] + v[2] + v[3] + v[4]);
         uint32_t c[4] = {v[1], v[2], v[3], v[4]}, cv;
         if (text_mode) cv = rest;
@@ -1039,18 +1149,19 @@ gather_kernel(const uint8_t* __restrict__ tiles, const Item* __restrict__ items,
 }
 
 // inspection hook: one sample's counts for a position range as [n][5] u16 (A, C, G, T, non-ACGT)
-__global__ void counts_kernel(const uint8_t* __restrict__ tiles, const Item* __restrict__ items, const uint32_t* __restrict__ tile_begin,
+__global__ void counts_kernel(const uint8_t* __restrict__ tiles, const Item* __restrict__ items, uint32_t item0,
+                              const uint32_t* __restrict__ tile_begin /* of the window's first tile */, uint32_t win_tile0,
                               const uint8_t* __restrict__ expect, uint32_t sample, uint32_t first, uint32_t n, uint16_t* __restrict__ out)
 {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const uint32_t p = first + k, t = p / TILE, off = p % TILE;
+    const uint32_t p = first + k, t = p / TILE - win_tile0, off = p % TILE;
     uint32_t r[5] = {0, 0, 0, 0, 0};
     for (uint32_t i = tile_begin[t]; i < tile_begin[t + 1]; ++i) {
         const uint4 it = __ldg(reinterpret_cast<const uint4*>(items) + i);
         if (it.x != sample) continue;
         uint32_t v[N_PLANES];
-        load_planes(tiles, i, item_is_wide(it.z, it.w), off, v);
+        load_planes(tiles, i - item0, item_is_wide(it.z, it.w), off, v);
         const uint32_t e = expect[p] & 3u;
         for (int a = 0; a < 4; ++a) r[a] = v[1 + a] + ((uint32_t)a == e ? v[0] - (v[1] + v[2] + v[3] + v[4]) : 0u);
         r[4] = v[PLANE_N];

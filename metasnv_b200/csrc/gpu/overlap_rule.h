@@ -62,6 +62,28 @@ MSNV_RULE_HD void msnv_overlap_rule4(uint32_t va, uint32_t vb, uint32_t xa, uint
     ob = (vb & ~m) | (nb & m);
 }
 
+// The same rule reduced to what the pileup consumes: a corrected quality is only ever compared with the threshold 13
+// (mpileup -Q default; nothing else reads it), so it is enough to know per base whether it still passes:
+//   bases equal  : a passes iff qa + qb >= 13, b never
+//   bases differ : the better one (a on ties) passes iff its quality is >= 17 (0.8 * 17 = 13.6 -> 13, 0.8 * 16 -> 12), the other never
+// d: XOR of the two mates' bases (msnv_spread_bases of the XOR of their seq2 bytes). In the lanes of m the outputs carry
+// the input's flag bit and quality 16 (passes) or 0 (fails); other lanes pass through unchanged.
+MSNV_RULE_HD void msnv_overlap_pass4(uint32_t va, uint32_t vb, uint32_t d, uint32_t m, uint32_t& oa, uint32_t& ob)
+{
+    const uint32_t H = 0x80808080u;
+    const uint32_t fa = va & H, fb = vb & H, qa = va & ~H, qb = vb & ~H;
+    const uint32_t diff7 = (d | (d << 1)) << 6;                                  // bit 7: the 2-bit codes differ
+    const uint32_t same7 = (fa & fb) | ~(fa | fb | diff7);                       // bit 7: "bases equal"
+    const uint32_t sum = qa + qb;                                                // <= 254 per lane: no carry between lanes
+    const uint32_t s13 = ((sum & ~H) + 0x73737373u) | sum;                       // bit 7: qa + qb >= 13
+    const uint32_t ge7 = (qa | H) - qb;                                          // bit 7: qa >= qb (no borrow between lanes)
+    const uint32_t a17 = qa + 0x6f6f6f6fu, b17 = qb + 0x6f6f6f6fu;               // bit 7: quality >= 17
+    const uint32_t pa = ((same7 & s13) | (~same7 & ge7 & a17)) & H;
+    const uint32_t pb = ~same7 & ~ge7 & b17 & H;
+    oa = (va & ~m) | ((fa | (pa >> 3)) & m);
+    ob = (vb & ~m) | ((fb | (pb >> 3)) & m);
+}
+
 // byte-lane mask of the positions p0 .. p0+3 that lie in [lo, hi); the quad must intersect the range
 MSNV_RULE_HD uint32_t msnv_quad_mask(int32_t p0, int32_t lo, int32_t hi)
 {

@@ -28,6 +28,16 @@ __device__ __forceinline__ uint32_t block_of(const uint32_t* __restrict__ starts
     return lo;
 }
 
+// sum of a u16 array (aligned bases of a sample = sum of its segment lengths)
+__global__ void sum_u16_kernel(const uint16_t* __restrict__ v, uint32_t n, unsigned long long* __restrict__ out)
+{
+    unsigned long long acc = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += v[i];
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 __global__ void synth_ref_kernel(Model m, const uint32_t* __restrict__ ctg_off, const uint32_t* __restrict__ ctg_len,
                                  uint32_t n_ctg, uint32_t n_pos, uint8_t* __restrict__ ref)
 {

@@ -1,6 +1,9 @@
 // bam.cc -- see bam.hpp.
 #include "bam.hpp"
 
+#include <unistd.h>
+
+#include <cstdio>
 #include <cstring>
 
 namespace msnv {
@@ -52,6 +55,79 @@ int BamReader::next(BamRecord& rec)
     rec.seq = rec.cigar + 4 * (size_t)c->n_cigar;
     rec.qual = rec.seq + (c->l_seq + 1) / 2;
     return 1;
+}
+
+// ---- tid index
+namespace {
+const char kTidxMagic[8] = {'M', 'S', 'N', 'V', 'T', 'I', 'X', '1'};
+}
+
+bool TidIndex::save(const std::string& path, uint64_t bam_bytes) const
+{
+    const std::string tmp = path + ".tmp" + std::to_string((unsigned long long)getpid());
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return false;
+    const uint64_t n = first.size();
+    bool ok = fwrite(kTidxMagic, 1, 8, f) == 8 && fwrite(&bam_bytes, 8, 1, f) == 1 && fwrite(&n, 8, 1, f) == 1 &&
+              (n == 0 || fwrite(first.data(), 8, n, f) == n);
+    ok = fclose(f) == 0 && ok;
+    if (ok) ok = rename(tmp.c_str(), path.c_str()) == 0;          // concurrent writers: last complete file wins
+    if (!ok) remove(tmp.c_str());
+    return ok;
+}
+
+bool TidIndex::load_sidecar(const std::string& path, uint64_t bam_bytes, size_t n_ref)
+{
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    char magic[8]; uint64_t size = 0, n = 0;
+    bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, kTidxMagic, 8) == 0 && fread(&size, 8, 1, f) == 1 && fread(&n, 8, 1, f) == 1 &&
+              size == bam_bytes && n == n_ref;
+    std::vector<uint64_t> v;
+    if (ok) { v.resize(n); ok = n == 0 || fread(v.data(), 8, n, f) == n; }
+    fclose(f);
+    if (ok) first.swap(v);
+    return ok;
+}
+
+bool TidIndex::load_bai(const std::string& path, size_t n_ref)
+{
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    auto rd = [&](void* p, size_t n) { return fread(p, 1, n, f) == n; };
+    char magic[4]; int32_t n = 0;
+    bool ok = rd(magic, 4) && memcmp(magic, "BAI\1", 4) == 0 && rd(&n, 4) && n >= 0 && (size_t)n == n_ref;
+    std::vector<uint64_t> v(ok ? n_ref : 0, NONE);
+    for (int32_t r = 0; ok && r < n; ++r) {
+        int32_t n_bin = 0;
+        ok = rd(&n_bin, 4) && n_bin >= 0;
+        uint64_t lo = NONE;
+        for (int32_t b = 0; ok && b < n_bin; ++b) {
+            uint32_t bin = 0; int32_t n_chunk = 0;
+            ok = rd(&bin, 4) && rd(&n_chunk, 4) && n_chunk >= 0;
+            for (int32_t c = 0; ok && c < n_chunk; ++c) {
+                uint64_t cb = 0, ce = 0;
+                ok = rd(&cb, 8) && rd(&ce, 8);
+                if (ok && bin != 37450 && cb < lo) lo = cb;           // 37450: the pseudo-bin with the read counts
+            }
+        }
+        int32_t n_intv = 0;
+        ok = ok && rd(&n_intv, 4) && n_intv >= 0;
+        for (int32_t i = 0; ok && i < n_intv; ++i) { uint64_t io = 0; ok = rd(&io, 8); }
+        if (ok) v[r] = lo;
+    }
+    fclose(f);
+    if (ok) first.swap(v);
+    return ok;
+}
+
+bool TidIndex::find_for(const std::string& bam_path, const std::string& extra, uint64_t bam_bytes, size_t n_ref)
+{
+    if (load_sidecar(bam_path + ".tidx", bam_bytes, n_ref)) return true;
+    if (!extra.empty() && load_sidecar(extra, bam_bytes, n_ref)) return true;
+    if (load_bai(bam_path + ".bai", n_ref)) return true;
+    if (bam_path.size() > 4 && bam_path.compare(bam_path.size() - 4, 4, ".bam") == 0 && load_bai(bam_path.substr(0, bam_path.size() - 4) + ".bai", n_ref)) return true;
+    return false;
 }
 
 int reg2bin(int64_t beg, int64_t end)

@@ -53,6 +53,10 @@ public:
     const std::string& error() const { return err_; }
     double inflate_seconds() const { return bg_.inflate_seconds(); }
     uint64_t compressed_size() const { return bg_.compressed_size(); }
+    uint64_t compressed_bytes_read() const { return bg_.compressed_bytes_read(); }
+    // virtual offset of the record the next call to next() returns / jump to a record boundary
+    uint64_t tell() const { return bg_.tell(); }
+    bool seek(uint64_t virtual_offset) { if (!bg_.seek(virtual_offset)) { err_ = bg_.error(); return false; } return true; }
 private:
     BgzfReader bg_;
     BamHeader hdr_;
@@ -70,6 +74,23 @@ public:
 private:
     BgzfWriter bg_;
     std::vector<uint8_t> rec_;
+};
+
+// Where the records of every reference sequence start in a coordinate-sorted BAM: lets a reader that needs a few
+// contigs (one genome bin of createOptimumSplit.py:43-60) seek to them instead of inflating the whole file, which
+// is what `samtools mpileup -l` - and round 1 of this build - did once per split (metaSNV.py:157-165).
+// Sources, in order: "<bam>.tidx" / a caller-given sidecar written by this repository's qaCompute during the coverage
+// pass (one scan of every BAM that metaSNV.py runs anyway, metaSNV.py:58-69), else the linear index of a standard
+// "<bam>.bai" (SAMv1 5.2). A sidecar records the size of the BAM it was made for and is ignored when that differs.
+struct TidIndex {
+    static constexpr uint64_t NONE = ~0ull;
+    std::vector<uint64_t> first;          // [n_ref] virtual offset of the first record of the tid, NONE = no record
+    bool valid() const { return !first.empty(); }
+    bool save(const std::string& path, uint64_t bam_bytes) const;
+    bool load_sidecar(const std::string& path, uint64_t bam_bytes, size_t n_ref);
+    bool load_bai(const std::string& path, size_t n_ref);
+    // "<bam>.tidx", `extra` (may be empty), "<bam>.bai", "<bam without .bam>.bai"
+    bool find_for(const std::string& bam_path, const std::string& extra, uint64_t bam_bytes, size_t n_ref);
 };
 
 // SAM header text for a list of contigs (@HD + @SQ lines), the form `samtools view -H` prints.

@@ -140,6 +140,7 @@ bool BgzfReader::fill()
     const size_t kBatchBytes = threads_ > 1 ? ((size_t)8 << 20) : ((size_t)512 << 10);
     std::vector<Member> ms;
     uint64_t total = 0;
+    batch_.clear();
     while (cpos_ < size_ && total < kBatchBytes) {
         if (size_ - cpos_ < 18) { err_ = "truncated BGZF member header"; return false; }
         const uint8_t* h = map_ + cpos_;
@@ -164,9 +165,11 @@ bool BgzfReader::fill()
         memcpy(&m.isize, map_ + cpos_ + msize - 4, 4);
         if (m.isize > (1u << 16)) { err_ = "BGZF member larger than 64 KiB"; return false; }
         m.ooff = total;
+        batch_.push_back(BatchMember{cpos_, total});
         total += m.isize;
         ms.push_back(m);
         cpos_ += msize;
+        cread_ += msize;
     }
     if (ms.empty()) return false;
     auto t0 = std::chrono::steady_clock::now();
@@ -191,6 +194,25 @@ bool BgzfReader::fill()
     if (!ok) { err_ = "BGZF inflate/CRC failure"; return false; }
     opos_ = 0; olen_ = total;
     if (total == 0) return cpos_ < size_ ? fill() : false;   // only empty members (EOF marker)
+    return true;
+}
+
+uint64_t BgzfReader::tell() const
+{
+    if (opos_ >= olen_) return cpos_ << 16;                       // the next byte is the first of the next member
+    size_t lo = 0, hi = batch_.size();                            // last member that starts at or before opos_
+    while (hi - lo > 1) { const size_t mid = (lo + hi) / 2; if (batch_[mid].ooff <= opos_) lo = mid; else hi = mid; }
+    return batch_[lo].cstart << 16 | (uint64_t)(opos_ - batch_[lo].ooff);
+}
+
+bool BgzfReader::seek(uint64_t voff)
+{
+    const uint64_t c = voff >> 16, u = voff & 0xffff;
+    if (c > size_) { err_ = "seek beyond the end of the file"; return false; }
+    cpos_ = c; opos_ = olen_ = 0; batch_.clear(); err_.clear();
+    if (u == 0) return true;
+    if (!fill() || u > olen_) { if (err_.empty()) err_ = "seek into a truncated BGZF member"; return false; }
+    opos_ = u;
     return true;
 }
 

@@ -52,9 +52,17 @@ public:
     const uint8_t* fetch(size_t n);
     const std::string& error() const { return err_; }
     uint64_t compressed_size() const { return size_; }
+    uint64_t compressed_bytes_read() const { return cread_; }     // members actually inflated (less than the file after a seek)
     double inflate_seconds() const { return inflate_s_; }
+    // BGZF virtual file offset (SAMv1 4.1.1: compressed offset of the member << 16 | offset inside its data) of
+    // the next byte read() would deliver, and repositioning to one.
+    uint64_t tell() const;
+    bool seek(uint64_t virtual_offset);
 private:
     bool fill();             // inflate the next batch; false at EOF or error
+    struct BatchMember { uint64_t cstart; uint64_t ooff; };
+    std::vector<BatchMember> batch_;  // members of the current batch: where each starts in the file and in out_
+    uint64_t cread_ = 0;
     int fd_ = -1;
     const uint8_t* map_ = nullptr;
     uint64_t size_ = 0, cpos_ = 0;

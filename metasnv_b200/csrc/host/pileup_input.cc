@@ -153,36 +153,132 @@ inline uint64_t hash_qname(const char* s)
 
 struct Buffered { int32_t end; uint64_t qh; };
 struct ByEnd { bool operator()(const Buffered& a, const Buffered& b) const { return a.end > b.end; } };
-struct Stored { uint32_t index; int32_t end; };
+struct Stored { uint64_t ordinal; int32_t end; };
 
 }  // namespace
 
-bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& layout, const std::vector<int64_t>& ref_len_of_tid,
-                              int inflate_threads, SampleReads& out, DecodeStats& st, std::string& err)
-{
-    auto t0 = std::chrono::steady_clock::now();
+// ------------------------------------------------------------------ resumable decoder
+struct SampleDecoderState {
+    std::string path;
+    const ShardLayout* layout = nullptr;
+    const std::vector<int64_t>* ref_len = nullptr;
     BamReader rd;
-    if (!rd.open(bam_path, inflate_threads)) { err = rd.error(); return false; }
-    const int MAXCNT = 8000;                         // samtools mpileup -d default (>= 1.9), per file
-    // mpileup takes the contigs from the first file's header and trusts the others to agree; a file whose header
-    // differs would be piled up against the wrong coordinates, so it is refused here instead
-    {
-        const BamHeader& h = rd.header();
-        if (h.lens.size() != layout.slot_of_tid.size()) { err = bam_path + ": its header lists " + std::to_string(h.lens.size()) + " contigs, the first file's " + std::to_string(layout.slot_of_tid.size()); return false; }
-        for (const ShardLayout::Ctg& c : layout.ctgs)
-            if (h.lens[c.tid] != c.len) { err = bam_path + ": contig " + h.names[c.tid] + " has another length than in the first file's header"; return false; }
-    }
-
+    DecodeStats st;
+    bool eof = false;
+    // one record read ahead (it belongs to a later window): kept as a private copy of its bytes
+    bool have_pending = false;
+    BamRecord pending; std::vector<uint8_t> pending_bytes;
     // state of htslib's pileup iterator that the depth cap and the overlap hash depend on
     int cur_tid = -1; int32_t last_pos = -1;
     std::priority_queue<Buffered, std::vector<Buffered>, ByEnd> buffered;    // reads the iterator still holds
-    std::unordered_map<uint64_t, Stored> olap;                               // qname -> earlier mate waiting for its partner
+    std::unordered_map<uint64_t, Stored> olap;                               // qname -> earlier mate waiting for its partner (index = ordinal)
     bool warned_overhang = false, warned_iupac = false;
+    uint64_t n_emitted = 0;                      // ordinal of the next accepted read over the whole file
+    uint64_t base = 0;                           // ordinal of the first read of the window batch being built
+    // index-driven reading: runs of consecutive tids of the shard, visited in order
+    TidIndex index;
+    std::vector<std::pair<int, int>> runs;       // [first tid, last tid]
+    size_t run_i = 0; bool in_run = false;
+    std::chrono::steady_clock::time_point t_open;
+};
+
+SampleDecoder::SampleDecoder() : st_(new SampleDecoderState()) {}
+SampleDecoder::~SampleDecoder() { delete st_; }
+const DecodeStats& SampleDecoder::stats() const { return st_->st; }
+bool SampleDecoder::used_index() const { return st_->index.valid() && !st_->runs.empty(); }
+
+bool SampleDecoder::open(const std::string& bam_path, const ShardLayout& layout, const std::vector<int64_t>& ref_len_of_tid, int inflate_threads,
+                         const std::string& index_hint, std::string& err)
+{
+    SampleDecoderState& S = *st_;
+    S.path = bam_path; S.layout = &layout; S.ref_len = &ref_len_of_tid;
+    if (!S.rd.open(bam_path, inflate_threads)) { err = S.rd.error(); return false; }
+    // mpileup takes the contigs from the first file's header and trusts the others to agree; a file whose header
+    // differs would be piled up against the wrong coordinates, so it is refused here instead
+    const BamHeader& h = S.rd.header();
+    if (h.lens.size() != layout.slot_of_tid.size()) { err = bam_path + ": its header lists " + std::to_string(h.lens.size()) + " contigs, the first file's " + std::to_string(layout.slot_of_tid.size()); return false; }
+    for (const ShardLayout::Ctg& c : layout.ctgs)
+        if (h.lens[c.tid] != c.len) { err = bam_path + ": contig " + h.names[c.tid] + " has another length than in the first file's header"; return false; }
+    // a split (-l) names a few contigs: with an index, read only the runs of the file that hold them
+    if (layout.has_bed && !getenv("MSNV_NO_INDEX") && S.index.find_for(bam_path, index_hint, S.rd.compressed_size(), h.lens.size())) {
+        for (const ShardLayout::Ctg& c : layout.ctgs) {
+            if (!S.runs.empty() && S.runs.back().second + 1 == c.tid) S.runs.back().second = c.tid;
+            else S.runs.emplace_back(c.tid, c.tid);
+        }
+    }
+    return true;
+}
+
+// next record of the shard's part of the file: 1 = delivered, 0 = no more, -1 = error
+static int next_record(SampleDecoderState& S, BamRecord& r)
+{
+    if (S.runs.empty()) return S.rd.next(r);
+    for (;;) {
+        if (!S.in_run) {
+            // start of the next run: the first of its tids that has records
+            uint64_t off = TidIndex::NONE;
+            while (S.run_i < S.runs.size() && off == TidIndex::NONE) {
+                for (int t = S.runs[S.run_i].first; t <= S.runs[S.run_i].second && off == TidIndex::NONE; ++t) off = S.index.first[(size_t)t];
+                if (off == TidIndex::NONE) ++S.run_i;
+            }
+            if (S.run_i >= S.runs.size()) return 0;
+            if (!S.rd.seek(off)) return -1;
+            S.in_run = true;
+        }
+        const int rc = S.rd.next(r);
+        if (rc <= 0) return rc;
+        if (r.core.tid >= 0 && r.core.tid <= S.runs[S.run_i].second) return 1;     // (an index entry may point a little before the tid: earlier tids are filtered by the caller)
+        S.in_run = false; ++S.run_i;                                                // past the run: on to the next one
+    }
+}
+
+bool SampleDecoder::window(uint32_t pos_lo, uint32_t pos_hi, const SampleReads* prev, SampleReads& out, std::string& err)
+{
+    SampleDecoderState& S = *st_;
+    const ShardLayout& layout = *S.layout;
+    const std::vector<int64_t>& ref_len_of_tid = *S.ref_len;
+    DecodeStats& st = S.st;
+    const std::string& bam_path = S.path;
+    auto t0 = std::chrono::steady_clock::now();
+    const int MAXCNT = 8000;                         // samtools mpileup -d default (>= 1.9), per file
+
+    // ---- the previous window's reads that reach this one: a contiguous tail of its batch
+    out = SampleReads();
+    if (prev && !prev->pos.empty()) {
+        const size_t n = prev->pos.size();
+        size_t first = n;
+        for (size_t i = n; i-- > 0;) {
+            if ((int64_t)prev->pos[i] + (int64_t)prev->max_span <= (int64_t)pos_lo) break;      // no earlier read can reach the window either
+            const uint32_t k = prev->seg_off[i + 1] - 1;                                         // its last segment
+            if ((int64_t)prev->seg_pos[k] + prev->seg_len[k] > (int64_t)pos_lo) first = i;
+        }
+        if (first < n) {
+            const uint32_t s0 = prev->seg_off[first], q0 = prev->q4_off[first];
+            out.pos.assign(prev->pos.begin() + first, prev->pos.end());
+            out.seg_off.resize(n - first + 1); out.q4_off.resize(n - first + 1); out.mate.resize(n - first);
+            for (size_t i = first; i <= n; ++i) { out.seg_off[i - first] = prev->seg_off[i] - s0; out.q4_off[i - first] = prev->q4_off[i] - q0; }
+            for (size_t i = first; i < n; ++i) { const int64_t m = (int64_t)prev->mate[i] - (int64_t)first; out.mate[i - first] = m >= 0 ? (int32_t)m : -1; }
+            out.seg_pos.assign(prev->seg_pos.begin() + s0, prev->seg_pos.end());
+            out.seg_len.assign(prev->seg_len.begin() + s0, prev->seg_len.end());
+            out.seq2.assign(prev->seq2.begin() + q0, prev->seq2.end());
+            out.qual.assign(prev->qual.begin() + 4 * (size_t)q0, prev->qual.end());
+            out.max_span = prev->max_span;
+        }
+        S.base = S.n_emitted - (n - first);
+    } else {
+        S.base = S.n_emitted;
+    }
 
     BamRecord r;
-    int rc;
-    while ((rc = rd.next(r)) > 0) {
-        ++st.records;
+    for (;;) {
+        if (S.have_pending) { r = S.pending; S.have_pending = false; }
+        else {
+            if (S.eof) break;
+            const int rc = next_record(S, r);
+            if (rc < 0) { err = bam_path + ": " + S.rd.error(); return false; }
+            if (rc == 0) { S.eof = true; break; }
+            ++st.records;
+        }
         const BamCore& c = r.core;
         // ---- mplp_func (SURVEY.md Annex A.1)
         if (c.tid < 0 || (c.flag & FLAG_UNMAP)) continue;
@@ -205,7 +301,7 @@ bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& la
         // ---- outside the contract of this implementation (documented in DESIGN.md)
         if (rlen == 0) continue;                                   // no reference base: builds no column
         if (c.pos < 0 || (uint32_t)end > layout.ctgs[slot].len) {
-            if (!warned_overhang) { fprintf(stderr, "[msnv] %s: read %s extends beyond its contig; such reads are skipped\n", bam_path.c_str(), r.qname); warned_overhang = true; }
+            if (!S.warned_overhang) { fprintf(stderr, "[msnv] %s: read %s extends beyond its contig; such reads are skipped\n", bam_path.c_str(), r.qname); S.warned_overhang = true; }
             continue;
         }
         if (c.l_seq > MSNV_MAX_READ_BASES || n_seg > MSNV_MAX_READ_SEGMENTS) {
@@ -213,52 +309,70 @@ bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& la
                   " bases / " + std::to_string(MSNV_MAX_READ_SEGMENTS) + " aligned segments)";
             return false;
         }
+        const ShardLayout::Ctg& ctg = layout.ctgs[slot];
+        // ---- a read of a later window: keep it for the next call (its bytes live in the reader's buffer only until the next record)
+        if ((uint64_t)ctg.offset + (uint32_t)c.pos >= pos_hi) {
+            const size_t nb = 32 + (size_t)c.l_read_name + 4 * (size_t)c.n_cigar + (size_t)((c.l_seq + 1) / 2) + (size_t)c.l_seq;
+            const uint8_t* src = (const uint8_t*)r.qname - 32;
+            if (!S.pending_bytes.empty() && src == S.pending_bytes.data()) { S.pending = r; S.have_pending = true; break; }   // it was the pending one already
+            std::vector<uint8_t> copy(nb);
+            memcpy(copy.data() + 32, src + 32, nb - 32);
+            S.pending_bytes.swap(copy);
+            S.pending = r;
+            const uint8_t* p = S.pending_bytes.data();
+            S.pending.qname = (const char*)(p + 32);
+            S.pending.cigar = p + 32 + c.l_read_name;
+            S.pending.seq = S.pending.cigar + 4 * (size_t)c.n_cigar;
+            S.pending.qual = S.pending.seq + (c.l_seq + 1) / 2;
+            S.have_pending = true;
+            break;
+        }
 
         // ---- bam_plp_push: the input must be coordinate sorted (htslib stops with "the input is not sorted"); the
         // device-side index searches the positions and relies on it
-        if (c.tid < cur_tid || (c.tid == cur_tid && c.pos < last_pos)) {
+        if (c.tid < S.cur_tid || (c.tid == S.cur_tid && c.pos < S.last_pos)) {
             err = bam_path + " is not coordinate sorted (read " + r.qname + ")";
             return false;
         }
         // ---- expiry of buffered reads, depth cap (Annex A.3)
-        if (c.tid != cur_tid) {
-            while (!buffered.empty()) buffered.pop();
-            olap.clear();
-            cur_tid = c.tid; last_pos = -1;
+        if (c.tid != S.cur_tid) {
+            while (!S.buffered.empty()) S.buffered.pop();
+            S.olap.clear();
+            S.cur_tid = c.tid; S.last_pos = -1;
         } else {
             // columns < last_pos have been produced; they released every read ending at or before last_pos-1
-            while (!buffered.empty() && buffered.top().end <= last_pos - 1) {
-                olap.erase(buffered.top().qh);
-                buffered.pop();
+            while (!S.buffered.empty() && S.buffered.top().end <= S.last_pos - 1) {
+                S.olap.erase(S.buffered.top().qh);
+                S.buffered.pop();
             }
         }
         const uint64_t qh = hash_qname(r.qname);
-        if (c.pos == last_pos && (int)buffered.size() + 1 > MAXCNT) {
-            olap.erase(qh);
+        if (c.pos == S.last_pos && (int)S.buffered.size() + 1 > MAXCNT) {
+            S.olap.erase(qh);
             ++st.dropped_by_cap;
             continue;
         }
-        last_pos = c.pos;
-        buffered.push(Buffered{end, qh});
-        if (buffered.size() > st.max_buffered) st.max_buffered = (uint32_t)buffered.size();
+        S.last_pos = c.pos;
+        S.buffered.push(Buffered{end, qh});
+        if (S.buffered.size() > st.max_buffered) st.max_buffered = (uint32_t)S.buffered.size();
 
-        const uint32_t idx = (uint32_t)out.pos.size();
+        const uint64_t ordinal = S.n_emitted++;
+        const uint32_t idx = (uint32_t)(ordinal - S.base);          // index in this window's batch
         // ---- overlap_push (Annex A.2)
         int32_t mate_idx = -1;
         if (!(c.flag & FLAG_MUNMAP) && (c.flag & FLAG_PROPER_PAIR) &&
             !((c.mtid >= 0 && c.tid != c.mtid) ||
               ((c.tlen < 0 ? -(int64_t)c.tlen : (int64_t)c.tlen) >= 2 * (int64_t)c.l_seq && c.mpos >= end))) {
-            auto it = olap.find(qh);
-            if (it == olap.end()) {
-                if (c.mpos >= c.pos) olap.emplace(qh, Stored{idx, end});
+            auto it = S.olap.find(qh);
+            if (it == S.olap.end()) {
+                if (c.mpos >= c.pos) S.olap.emplace(qh, Stored{ordinal, end});
             } else {
-                if (it->second.end > c.pos) mate_idx = (int32_t)it->second.index;   // else: no common reference base
-                olap.erase(it);
+                // (a partner that is not part of this batch ended before the window: no common position inside it)
+                if (it->second.end > c.pos && it->second.ordinal >= S.base) mate_idx = (int32_t)(it->second.ordinal - S.base);
+                S.olap.erase(it);
             }
         }
-
         // ---- append to the structure of arrays
-        const ShardLayout::Ctg& ctg = layout.ctgs[slot];
         out.pos.push_back((int32_t)(ctg.offset + (uint32_t)c.pos));
         out.mate.push_back(mate_idx);
         if (mate_idx >= 0) { out.mate[(size_t)mate_idx] = (int32_t)idx; ++st.pairs; }
@@ -302,13 +416,13 @@ bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& la
                                 sq[o >> 2] = (uint8_t)((cf[k] & 3) | (cf[k + 1] & 3) << 2 | (cf[k + 2] & 3) << 4 | (cf[k + 3] & 3) << 6);
                             for (; k < len; ++k, ++o) sq[o >> 2] |= (uint8_t)((cf[k] & 3) << ((o & 3) * 2));
                         }
-                        if ((any & 0x80) && !warned_iupac) {           // rare: is one of the flagged bases something other than N?
+                        if ((any & 0x80) && !S.warned_iupac) {           // rare: is one of the flagged bases something other than N?
                             for (uint32_t k = 0; k < len; ++k) {
                                 const size_t i2 = qy + k;
                                 const uint8_t c4 = (r.seq[i2 >> 1] >> ((~i2 & 1) << 2)) & 0xf;
                                 if ((cf[k] & 0x80) && c4 != 15) {
                                     fprintf(stderr, "[msnv] %s: read %s has a base other than A/C/G/T/N; such bases are not counted\n", bam_path.c_str(), r.qname);
-                                    warned_iupac = true;
+                                    S.warned_iupac = true;
                                     break;
                                 }
                             }
@@ -332,11 +446,20 @@ bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& la
         }
         ++st.accepted;
     }
-    if (rc < 0) { err = bam_path + ": " + rd.error(); return false; }
     if (st.max_buffered + 64u > 65535u) { err = bam_path + ": pileup depth above 65535 is not supported"; return false; }
-    st.compressed_bytes = rd.compressed_size();
-    st.inflate_seconds = rd.inflate_seconds();
-    st.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    st.compressed_bytes = S.rd.compressed_bytes_read();
+    st.inflate_seconds = S.rd.inflate_seconds();
+    st.seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return true;
+}
+
+bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& layout, const std::vector<int64_t>& ref_len_of_tid,
+                              int inflate_threads, SampleReads& out, DecodeStats& st, std::string& err)
+{
+    SampleDecoder d;
+    if (!d.open(bam_path, layout, ref_len_of_tid, inflate_threads, std::string(), err)) return false;
+    if (!d.window(0, layout.n_positions, nullptr, out, err)) return false;
+    st = d.stats();
     return true;
 }
 

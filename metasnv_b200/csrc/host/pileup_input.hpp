@@ -59,6 +59,8 @@ struct SampleReads {
     size_t bytes() const;
 };
 
+struct SampleDecoderState;
+
 struct DecodeStats {
     uint64_t records = 0, accepted = 0, dropped_by_cap = 0, aligned_bases = 0, pairs = 0;
     uint64_t compressed_bytes = 0;
@@ -68,7 +70,32 @@ struct DecodeStats {
     uint32_t max_buffered = 0;
 };
 
-// Decode one BAM into `out` for the contigs of `layout`. `ref_len_of_tid[tid]` is the FASTA length
+// Resumable decoder of one BAM: the shard is handed out window by window (ascending, disjoint ranges of shard
+// coordinates), so neither the host nor the device has to hold a whole shard - the reference's pipe streams the same
+// way (call_vC.cpp:466-479 reads one pileup line at a time). Everything mpileup decides per read in file order
+// (filters, depth cap, mate pairing) carries over from window to window.
+//   window(lo, hi, prev, out): `out` = every accepted read that starts before `hi` and was not finished before `lo`:
+//   first the tail of the previous window's batch `prev` (from its first read that reaches `lo` on; pass nullptr for
+//   the first window), then the reads decoded now. Mate links are indices into `out`; a link whose partner is not in
+//   `out` is dropped (the two then share no position inside the window).
+// With a TidIndex and a -l split the decoder seeks to the runs of contigs the split names instead of inflating the
+// whole file.
+class SampleDecoder {
+public:
+    SampleDecoder();
+    ~SampleDecoder();
+    SampleDecoder(const SampleDecoder&) = delete;
+    SampleDecoder& operator=(const SampleDecoder&) = delete;
+    bool open(const std::string& bam_path, const ShardLayout& layout, const std::vector<int64_t>& ref_len_of_tid, int inflate_threads,
+              const std::string& index_hint, std::string& err);
+    bool window(uint32_t pos_lo, uint32_t pos_hi, const SampleReads* prev, SampleReads& out, std::string& err);
+    const DecodeStats& stats() const;
+    bool used_index() const;
+private:
+    SampleDecoderState* st_;
+};
+
+// Decode one BAM into `out` for the contigs of `layout` (one window over the whole shard). `ref_len_of_tid[tid]` is the FASTA length
 // of the contig or -1 when the FASTA lacks it (mpileup then keeps every read). The BAM's header
 // is not compared with the shard's: like mpileup, the first file's header rules.
 bool decode_sample_for_pileup(const std::string& bam_path, const ShardLayout& layout,

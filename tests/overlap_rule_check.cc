@@ -29,6 +29,16 @@ int main() {
                             }
                             if (((oa >> (8 * k)) & 0xff) != ea || ((ob >> (8 * k)) & 0xff) != eb) ++bad;
                         }
+                        // the threshold form the kernel uses: same flag bits, and "passes Q13" exactly where the full rule does
+                        uint32_t pa, pb;
+                        msnv_overlap_pass4(va, vb, msnv_spread_bases(sa ^ sb), m, pa, pb);
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t fa = (oa >> (8 * k)) & 0xff, fb = (ob >> (8 * k)) & 0xff, ga = (pa >> (8 * k)) & 0xff, gb = (pb >> (8 * k)) & 0xff;
+                            if ((m >> (8 * k)) & 0xff) {
+                                if ((fa & 0x80) != (ga & 0x80) || (fb & 0x80) != (gb & 0x80)) ++bad;
+                                if (((fa & 0x7f) >= 13) != ((ga & 0x7f) >= 13) || ((fb & 0x7f) >= 13) != ((gb & 0x7f) >= 13)) ++bad;
+                            } else if (fa != ga || fb != gb) ++bad;
+                        }
                     }
     for (uint32_t q = 0; q < 256; ++q) if (msnv_q08(q) != (uint32_t)(0.8 * (double)q)) ++bad;
     for (int p0 = 0; p0 < 16; p0 += 4) for (int lo = 0; lo < 20; ++lo) for (int hi = lo + 1; hi < 24; ++hi) {

@@ -201,7 +201,8 @@ def test_empty_inputs(built, tmp_path):
 
 @pytest.mark.parametrize("env", [{"MSNV_INDEX_BITMAP": "1"}, {"MSNV_INDEX_BITMAP": "0"}, {"MSNV_MAX_READS": "16"}, {"MSNV_MAX_READS": "255"},
                                  {"MSNV_CHUNK_Q4": "1280"}, {"MSNV_CHUNK_Q4": "16384"}, {"MSNV_PILEUP_CTAS": "1"},
-                                 {"MSNV_MAX_READS": "40", "MSNV_CHUNK_Q4": "1280", "MSNV_PILEUP_CTAS": "2"}],
+                                 {"MSNV_MAX_READS": "40", "MSNV_CHUNK_Q4": "1280", "MSNV_PILEUP_CTAS": "2"},
+                                 {"MSNV_CONSUMERS": "256"}, {"MSNV_TILE_BUDGET_MB": "1"}],
                          ids=lambda e: "-".join("%s=%s" % kv for kv in e.items()))
 def test_kernel_variants_give_identical_output(env, datasets, tmp_path):
     """Every launch-time choice of the library (occupancy bitmap for sparse shards; reads, quads per staged chunk of the
