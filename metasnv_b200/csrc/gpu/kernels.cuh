@@ -2,10 +2,12 @@
 //
 // Data flow for one shard (all samples of one genome bin):
 //   index_kernel     (tile, sample) pairs that have reads  -> ordered work items (ballot compaction)
+//   mate_kernel      mate-overlap quality rule (SURVEY.md Annex A.2) -> per-base verdict bits
 //   pileup_kernel    persistent CTAs: a producer warp stages the items' position-aligned reads through a
-//                    ring of TMA bulk copies; consumer warps apply the mate-overlap quality correction
-//                    (SURVEY.md Annex A.2) in shared memory and scatter sixteen positions per thread and
-//                    step into byte-lane count planes -> 6 B per sample-position     [dominant kernel]
+//                    ring of TMA bulk copies; consumer warps turn the qualities into one pass bit per base
+//                    (32 positions per thread and step) and count depth with vertical (carry-save) counters
+//                    in registers; only bases that differ from the reference touch shared-memory atomics
+//                    -> 6 B per sample-position                                       [dominant kernel]
 //   call_kernel      per tile: reduce over samples, snpCall thresholds (call_vC.cpp:545-601)
 //   compact_kernel   ordered stream compaction of called positions (warp ballot + block scan)
 //   gather_kernel    per hit: per-sample coverage / allele counts for the host formatter
@@ -32,7 +34,7 @@ struct SampleDev {
     const uint16_t* seg_len;
     const uint8_t*  seq2;
     const uint8_t*  qual;
-    uint8_t*        fix;          // samples with mate links: per quad, the verdict of the mate-overlap rule (mate_kernel), else null
+    uint32_t*       fix;          // samples with mate links: the verdicts of the mate-overlap rule (mate_kernel: two words per eight quads), else null
     uint32_t        n_reads, max_span;
 };
 
@@ -308,21 +310,24 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ v, ui
 // mate overlap (htslib tweak_overlap_quality, SURVEY.md Annex A.2): for every pair the host linked, at every
 // reference position both mates align a base to, the rule decides which of the two bases is still counted
 // (overlap_rule.h: a corrected quality is only ever compared with the threshold, so its verdict is one bit).
-// The uploaded reads are never modified: the verdicts go to a side array `fix`, one byte per quad of the
-// sample - low nibble: positions the rule overrides, high nibble: whether the base passes there - which the
-// pileup kernel stages next to the bases. Cleared and rebuilt by every run (fix_clear_kernel, mate_kernel).
-// One thread per pair: the two mates are a few reads apart in a shallow sample and thousands apart in a deep
-// one; either way every load is an independent global access and millions of pairs are in flight.
+// The uploaded reads are never modified: the verdicts go to a side array `fix` in the geometry the pileup
+// kernel consumes - for every group of eight consecutive quads of the sample (32 staged positions) two
+// words: a mask of the positions the rule overrides and, under that mask, whether the base passes
+// (bit 4 * (quad & 7) + lane in both). Cleared and rebuilt by every run (fix_clear_kernel, mate_kernel).
+// Eight lanes per pair, one quad of both mates per lane and step: the mates are stored position-aligned,
+// so their quads line up word for word and a step is two coalesced loads of up to 32 bytes per mate.
 // ------------------------------------------------------------------------------------------------
 // bit 0 of the four byte lanes -> a nibble, and back
 __device__ __forceinline__ uint32_t lanes_to_nibble(uint32_t x) { return ((x & 0x01010101u) * 0x01020408u) >> 24; }
 __device__ __forceinline__ uint32_t nibble_to_lanes(uint32_t n) { return ((n & 0xfu) * 0x00204081u) & 0x01010101u; }
 
+__host__ __device__ __forceinline__ size_t fix_words(size_t n_q4) { return 2 * ((n_q4 + 7) / 8) + 8; }   // + spare for the 16-byte copies
+
 __global__ void __launch_bounds__(256) fix_clear_kernel(const SampleDev* __restrict__ samples)
 {
     const SampleDev sd = samples[blockIdx.y];
     if (!sd.fix || sd.n_reads == 0) return;
-    const uint32_t n16 = (__ldg(sd.q4_off + sd.n_reads) + 15u) / 16u;        // the array has spare bytes behind it
+    const uint32_t n16 = (uint32_t)((fix_words(__ldg(sd.q4_off + sd.n_reads)) * 4 + 15) / 16);
     uint4* f = reinterpret_cast<uint4*>(sd.fix);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) f[i] = make_uint4(0u, 0u, 0u, 0u);
 }
@@ -332,9 +337,9 @@ __global__ void __launch_bounds__(256) mate_kernel(const SampleDev* __restrict__
     const SampleDev sd = samples[blockIdx.y];
     if (!sd.fix) return;
     const uint32_t* __restrict__ qual32 = reinterpret_cast<const uint32_t*>(sd.qual);
-    uint32_t* __restrict__ fix32 = reinterpret_cast<uint32_t*>(sd.fix);
     const uint32_t nq_total = sd.n_reads ? __ldg(sd.q4_off + sd.n_reads) : 0u;
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < sd.n_reads; r += gridDim.x * blockDim.x) {
+    const uint32_t l8 = threadIdx.x & 7u;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < sd.n_reads; r += (gridDim.x * blockDim.x) >> 3) {
         const int32_t mt = __ldg(sd.mate + r);
         if (mt <= (int32_t)r || (uint32_t)mt >= sd.n_reads) continue;         // the earlier mate (a) handles the pair
         const uint32_t sa0 = __ldg(sd.seg_off + r), sa1 = __ldg(sd.seg_off + r + 1), sb0 = __ldg(sd.seg_off + mt), sb1 = __ldg(sd.seg_off + mt + 1);
@@ -348,8 +353,7 @@ __global__ void __launch_bounds__(256) mate_kernel(const SampleDev* __restrict__
                 const int32_t bx = __ldg(sd.seg_pos + kb);
                 const uint32_t bl = __ldg(sd.seg_len + kb);
                 const int32_t lo = max(ax, bx), hi = min(ax + (int32_t)al, bx + (int32_t)bl);
-                #pragma unroll 4
-                for (int32_t P = lo >> 2; P < ((hi + 3) >> 2); ++P) {         // (empty when the segments share no position)
+                for (int32_t P = (lo >> 2) + (int32_t)l8; P < ((hi + 3) >> 2); P += 8) {      // (empty when the segments share no position)
                     const uint32_t ia = qa + (uint32_t)(P - (ax >> 2)), ib = qb + (uint32_t)(P - (bx >> 2));
                     if (ia >= nq_total || ib >= nq_total) continue;           // segments and offsets disagree (the pileup kernel reports it)
                     const uint32_t va = __ldg(qual32 + ia), vb = __ldg(qual32 + ib);
@@ -358,14 +362,12 @@ __global__ void __launch_bounds__(256) mate_kernel(const SampleDev* __restrict__
                     uint32_t na, nb;
                     msnv_overlap_pass4(va, vb, d, msk, na, nb);               // masked lanes: flag | 16 (passes) or flag | 0
                     const uint32_t ovr = lanes_to_nibble(msk);
-                    const uint32_t fa = ovr | (lanes_to_nibble(na >> 4) & ovr) << 4, fb = ovr | (lanes_to_nibble(nb >> 4) & ovr) << 4;
-                    // a quad the rule covers whole belongs to this segment combination alone: plain byte stores. Two
-                    // combinations can meet in a quad at their ends (with disjoint positions): OR into the byte there.
-                    if (msk == 0xffffffffu) { sd.fix[ia] = (uint8_t)fa; sd.fix[ib] = (uint8_t)fb; }
-                    else {
-                        atomicOr(fix32 + (ia >> 2), fa << (8u * (ia & 3u)));
-                        atomicOr(fix32 + (ib >> 2), fb << (8u * (ib & 3u)));
-                    }
+                    const uint32_t pa = lanes_to_nibble(na >> 4) & ovr, pb = lanes_to_nibble(nb >> 4) & ovr;
+                    // several threads (and, where two segment combinations meet in a quad, several steps) share a word: OR
+                    atomicOr(sd.fix + 2u * (ia >> 3), ovr << (4u * (ia & 7u)));
+                    if (pa) atomicOr(sd.fix + 2u * (ia >> 3) + 1u, pa << (4u * (ia & 7u)));
+                    atomicOr(sd.fix + 2u * (ib >> 3), ovr << (4u * (ib & 7u)));
+                    if (pb) atomicOr(sd.fix + 2u * (ib >> 3) + 1u, pb << (4u * (ib & 7u)));
                 }
                 qb += (((uint32_t)bx & 3u) + bl + 3u) >> 2;
             }
@@ -383,7 +385,8 @@ __global__ void __launch_bounds__(256) mate_kernel(const SampleDev* __restrict__
 //       reference base, A where the reference is not A/C/G/T); the plane of letter e stays 0
 //   N   counted bases that are not A/C/G/T
 // so count[e] = D - (A + C + G + T) and count[x != e] = plane x. Nearly every aligned base equals the
-// reference, so the pileup does ONE shared-memory atomic per four positions instead of four.
+// reference: the pileup counts D on bits (pass words and vertical counters) and touches the letter planes only for
+// the rare base that differs.
 // Narrow items (at most 255 reads touch the tile: no counter can pass 255) store the planes as
 // bytes (6 B per sample-position), wide items (deep coverage) as 16-bit values (12 B).
 // ------------------------------------------------------------------------------------------------
@@ -392,7 +395,7 @@ constexpr int N_PLANES = 6;
 constexpr int PLANE_D = 0, PLANE_A = 1, PLANE_N = 5;
 constexpr uint32_t NARROW_MAX_READS = 255;
 constexpr size_t SLOT_BYTES = 2 * N_PLANES * TILE;
-static_assert(TILE_QUADS == 256, "a staged quad is tagged with one byte");
+static_assert(TILE_QUADS == 256, "32 words of 32 positions per tile");
 
 __host__ __device__ __forceinline__ bool item_is_wide(uint32_t r_lo, uint32_t r_hi) { return r_hi - r_lo > NARROW_MAX_READS; }
 
@@ -411,56 +414,93 @@ __global__ void expect_kernel(const uint8_t* __restrict__ ref, uint32_t n, uint8
     expect[p] = (uint8_t)e;
 }
 
+// The same letters in the geometry of the staged reads (2 bits per position, a byte per quad), four
+// copies per tile: byte i of copy c is the quad i + c of the tile (0 behind the tile's end), so the
+// expected letters of four consecutive quads starting at ANY quad j are one aligned word -
+// copy j & 3, word j >> 2. That is what lets a read-sized XOR run word by word whatever the
+// read's alignment in the staging buffer.
+constexpr int EXP_COPY_BYTES = TILE / 4 + 16;
+constexpr int EXP_BYTES = 4 * EXP_COPY_BYTES;
+static_assert(EXP_BYTES % 16 == 0, "one bulk copy per tile");
+
+__global__ void expect2_kernel(const uint8_t* __restrict__ expect /* of the first tile */, uint32_t n_tiles, uint8_t* __restrict__ expect2 /* [n_tiles][EXP_BYTES] */)
+{
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (uint64_t)n_tiles * EXP_BYTES) return;
+    const uint32_t t = (uint32_t)(g / EXP_BYTES), o = (uint32_t)(g % EXP_BYTES), c = o / EXP_COPY_BYTES, i = o % EXP_COPY_BYTES;
+    const uint32_t q = i + c;
+    uint32_t v = 0;
+    if (q < (uint32_t)(TILE / 4)) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(expect + (size_t)t * TILE + 4u * q);
+        v = (w & 3u) | ((w >> 6) & 0xcu) | ((w >> 12) & 0x30u) | ((w >> 18) & 0xc0u);
+    }
+    expect2[g] = (uint8_t)v;
+}
+
 // ------------------------------------------------------------------------------------------------
-// pileup: persistent CTAs, one producer warp + four consumer warps each, walking the work items
-// blockIdx.x, blockIdx.x + gridDim.x, ... (items are tile-major, so the CTAs resident at any time
-// work on neighbouring tiles and the reads of a sample stream through L2 once).
+// pileup: persistent CTAs, one producer warp + four (or eight) consumer warps each, walking the work
+// items blockIdx.x, blockIdx.x + gridDim.x, ... (items are tile-major, so the CTAs resident at any
+// time work on neighbouring tiles and the reads of a sample stream through L2 once).
 //
 // Producer warp. Item records and the four offsets that size an item are fetched 32 items at a time
 // (one per lane: the dependent global loads of 32 items overlap). An item whose reads fit one stage
 // (the common case) becomes one chunk; otherwise the warp searches the longest prefix of reads that
 // fits (32 probes at a time) and sends several chunks. For a chunk the warp waits for a free stage of
 // the ring, writes a header and issues eight TMA bulk copies (UBLKCP) that complete on the stage's
-// mbarrier: the reads' offsets and mate links, the segment records, the 2-bit bases, the qualities
-// and the tile's expected letters. Consumers therefore never wait for HBM, only for the barrier.
+// mbarrier: the reads' offsets, the segment records, the 2-bit bases, the qualities, the overlap
+// verdicts and the tile's expected letters. Consumers therefore never wait for HBM, only for the barrier.
 //
-// Consumer warps, per chunk (reads arrive as position-aligned segments, include/msnv.h: a staged
-// quad holds four consecutive positions starting at a multiple of four, so a quad is either on the
-// tile or off it and its four bases are handled with byte-lane arithmetic):
-//   1. one thread per read: every staged quad that lies on the tile is tagged with its tile-relative
-//      index (four tags per store), the qualities of the few quads off the tile are zeroed (the
-//      scatter's threshold test then rejects them like any poor base)
-//   2. scatter: a thread takes FOUR consecutive staged quads per step (one 128-bit load of the
-//      qualities, one word each of bases, tags and - for samples with mates - overlap verdicts).
-//      Per quad: quality test on four byte lanes (overridden where mate_kernel left a verdict), one
-//      shared-memory atomic into plane D, and a compare with the expected letters; only lanes that
-//      hold a mismatch loop over their set bits and add to a letter plane.
-//   3. last chunk of an item: narrow items copy the byte planes to HBM (6 KB, 128-bit stores) and
+// Consumer warps, per chunk. Reads arrive as position-aligned segments (include/msnv.h): a staged
+// quad holds four consecutive positions starting at a multiple of four, so the bits of a read line up
+// with the bits of the tile after a shift by whole quads. Counting is done on BITS, not bytes:
+//   1. prep, one thread per read: a record per segment (tile-relative quad of its first staged quad,
+//      where it lies in the staging buffer, its length), the read's first quad (reads are in coordinate
+//      order: the reads that can cover a 32-position word of the tile are an index range), and the
+//      staged bases XORed in place with the tile's expected letters (word by word, see expect2_kernel;
+//      padding and quads off the tile become 0), so "differs from the reference" is "byte != 0".
+//   2. extract, flat over the staging buffer, eight quads (32 positions) per thread and step: two
+//      128-bit loads of qualities -> "quality >= 13 and the base is A/C/G/T" on four byte lanes per
+//      quad (3 instructions), the four bits gathered by one multiply, eight quads chained by funnel
+//      shifts -> ONE 32-bit pass word per 32 staged positions (mate-overlap verdicts, two more words,
+//      override it where mate_kernel spoke). Groups that hold a base differing from the expected
+//      letter or a non-ACGT base (about one in six) are appended to a list by warp ballot.
+//   3. exceptions: one thread per listed group finds the tile position of its quads (bisection over
+//      the reads' offsets) and adds the counted mismatches / N bases to the letter and N planes with
+//      shared-memory atomics - the only atomics per base left, for < 1 % of the bases.
+//   4. depth, gather: a thread owns one 32-position word of the tile and a share of the reads that
+//      can cover it. Per (word, segment): two loads of pass words, one funnel shift to the word's
+//      alignment, a mask for the segment's extent, and a carry-save add into vertical counters held in
+//      registers (plane b = bit b of the 32 per-position counts): ~10 instructions for up to 32 bases.
+//      The lanes that share a word add their counters with shuffles (bit-sliced full adders), expand
+//      them to byte lanes and add them to plane D.
+//   5. last chunk of an item: narrow items copy the byte planes to HBM (6 KB, 128-bit stores) and
 //      clear them; wide items fold every chunk into 16-bit lanes held in registers (a chunk stages
 //      at most 255 reads) and store those.
 // The mate-overlap rule itself runs before this kernel (mate_kernel): no read ever waits for its mate here.
 //
-// Shared memory (dynamic, see pileup_smem_layout): mbarriers | 6 count planes | quad tags |
-// PL_STAGES x { header, q4_off, seg_off, seg_pos, seg_len, expected letters, bases, overlap
-// verdicts, qualities }. Every TMA destination is 16-byte aligned; sources are the 16-byte
-// aligned addresses at or below the first element needed (the arrays are 256-byte aligned and have
-// 32 spare bytes behind them), so a stage holds a few elements in front of and behind the chunk.
+// Shared memory (dynamic, see pileup_smem_layout): mbarriers | 6 count planes | pass words | segment
+// records | first quads | word index | exception list | PL_STAGES x { header, q4_off, seg_off,
+// seg_pos, seg_len, expected letters, bases, overlap verdicts, qualities }. Every TMA destination is
+// 16-byte aligned; sources are the 16-byte aligned addresses at or below the first element needed (the
+// arrays are 256-byte aligned and have spare bytes behind them); the per-quad arrays all start at the
+// sample's quad index rounded down to 16, so a stage holds up to 15 quads in front of the chunk.
 // ------------------------------------------------------------------------------------------------
 // consumer threads per CTA: a template parameter of the kernel (128 or 256; the CTA has one more warp, the producer)
 constexpr int PL_STAGES = 2;
 constexpr uint32_t CHUNK_Q4_MIN = MSNV_MAX_READ_BASES / 4 + 2 * MSNV_MAX_READ_SEGMENTS;   // a single read always fits
 constexpr uint32_t CHUNK_SEGS_MIN = MSNV_MAX_READ_SEGMENTS;
 constexpr uint32_t CHUNK_FIRST = 1u, CHUNK_LAST = 2u, CHUNK_WIDE = 4u, CHUNK_STOP = 8u, CHUNK_FIX = 16u /* the sample has mate verdicts */;
+constexpr uint32_t ABL_EXTRACT = 1u, ABL_PREP_XOR = 2u, ABL_DEPTH = 4u, ABL_STORE = 8u, ABL_EXCEPT = 16u;   // PileupShape::ablate (measurement only)
 
 // limits of one staged chunk, chosen per launch from the shape of the shard
 struct PileupShape { uint32_t max_reads, max_segs, chunk_q4, has_fix /* some sample carries mate verdicts */, wait_hint_ns, ablate /* measurement only: phases to skip */; };
 
-struct ChunkHdr { uint32_t m, nq4, q4_0, sg_0, nseg, c0, item, sample, tile, flags, pad[6]; };
+struct ChunkHdr { uint32_t m, nq4, q4_0, sg_0, nseg, c0, item, sample, tile, flags, spanq /* quads a read of the sample can span */, pad[5]; };
 static_assert(sizeof(ChunkHdr) == 64, "header is one 64-byte block");
 
 struct PileupSmem {
-    uint32_t bar, cnt, tags, stage0, stage_bytes;                               // byte offsets
-    uint32_t o_hdr, o_q4, o_sg, o_sp, o_sl, o_exp, o_seq, o_fix, o_qual;        // within a stage
+    uint32_t bar, cnt, pbits, segtab, jr, wend, list, misc, stage0, stage_bytes;        // byte offsets
+    uint32_t o_hdr, o_q4, o_sg, o_sp, o_sl, o_exp, o_seq, o_fix, o_qual;                // within a stage
     uint32_t total;
 };
 
@@ -469,10 +509,16 @@ __host__ __device__ constexpr uint32_t up_to(uint32_t v, uint32_t a) { return (v
 __host__ __device__ inline PileupSmem pileup_smem_layout(const PileupShape sh)
 {
     PileupSmem L{};
+    const uint32_t cq = up_to(sh.chunk_q4, 16) + 16;          // staged quads: the chunk's + up to 15 in front of it
     uint32_t o = 0;
-    L.bar = o;   o += 128;
-    L.cnt = o;   o += N_PLANES * TILE;
-    L.tags = o;  o += up_to(sh.chunk_q4, 16) + 16;
+    L.bar = o;    o += 128;
+    L.cnt = o;    o += N_PLANES * TILE;
+    L.pbits = o;  o += up_to((cq / 8 + 3) * 4, 16);            // one word in front (a segment may start inside a word), one behind
+    L.segtab = o; o += up_to(sh.max_segs, 2) * 8;
+    L.jr = o;     o += up_to((sh.max_reads + 1) * 2, 16);
+    L.wend = o;   o += 80;
+    L.list = o;   o += up_to((cq / 8 + 1) * 2, 16);
+    L.misc = o;   o += 16;
     L.stage0 = up_to(o, 128);
     uint32_t s = 0;
     const uint32_t mw = up_to(sh.max_reads + 1, 4) + 8;
@@ -481,17 +527,23 @@ __host__ __device__ inline PileupSmem pileup_smem_layout(const PileupShape sh)
     L.o_sg = s;   s += mw * 4;
     L.o_sp = s;   s += (up_to(sh.max_segs, 4) + 8) * 4;
     L.o_sl = s;   s += (up_to(sh.max_segs, 8) + 16) * 2;
-    L.o_exp = s;  s += TILE;
-    L.o_seq = s;  s += up_to(sh.chunk_q4, 16) + 32;
-    L.o_fix = s;  s += sh.has_fix ? up_to(sh.chunk_q4, 16) + 32 : 0;
-    L.o_qual = s; s += 4 * up_to(sh.chunk_q4, 16) + 32;
+    L.o_exp = s;  s += EXP_BYTES;
+    L.o_seq = s;  s += cq + 16;
+    L.o_fix = s;  s += sh.has_fix ? cq + 16 : 0;
+    L.o_qual = s; s += 4 * cq + 64;
     L.stage_bytes = up_to(s, 128);
     L.total = L.stage0 + PL_STAGES * L.stage_bytes;
     return L;
 }
 
-// explicit shared-window accesses (32-bit addresses) for the scatter loop
+// explicit shared-window accesses (32-bit addresses) for the inner loops
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds_v2(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ uint4 lds_v4(uint32_t a)
 {
     uint4 v;
@@ -510,13 +562,13 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 // the arrays of one sample the producer copies from
 struct SrcPtrs {
     const uint32_t* q4_off; const uint32_t* seg_off; const int32_t* seg_pos; const uint16_t* seg_len;
-    const uint8_t* seq2; const uint8_t* qual; const uint8_t* fix;
+    const uint8_t* seq2; const uint8_t* qual; const uint32_t* fix; uint32_t max_span;
 };
 __device__ __forceinline__ SrcPtrs load_src_ptrs(const SampleDev* __restrict__ sd)
 {
     SrcPtrs p;
     p.q4_off = sd->q4_off; p.seg_off = sd->seg_off; p.seg_pos = sd->seg_pos; p.seg_len = sd->seg_len;
-    p.seq2 = sd->seq2; p.qual = sd->qual; p.fix = sd->fix;
+    p.seq2 = sd->seq2; p.qual = sd->qual; p.fix = sd->fix; p.max_span = sd->max_span;
     return p;
 }
 
@@ -525,15 +577,16 @@ __device__ __forceinline__ SrcPtrs load_src_ptrs(const SampleDev* __restrict__ s
 struct ChunkCopies { const void* src[7]; uint32_t bytes[7]; };
 __device__ __forceinline__ ChunkCopies chunk_copies(const SrcPtrs& p, uint32_t c0, uint32_t m, uint32_t q4_0, uint32_t nq4, uint32_t sg_0, uint32_t nseg)
 {
-    const uint32_t dm = c0 & 3u, ds = sg_0 & 3u, dl = sg_0 & 7u, dq = q4_0 & 3u, d16 = q4_0 & 15u;
+    const uint32_t dm = c0 & 3u, ds = sg_0 & 3u, dl = sg_0 & 7u, d16 = q4_0 & 15u;
     ChunkCopies c;
     c.src[0] = p.q4_off + (c0 - dm);             c.bytes[0] = up_to(dm + m + 1u, 4) * 4u;
     c.src[1] = p.seg_off + (c0 - dm);            c.bytes[1] = c.bytes[0];
-    c.src[2] = p.fix ? p.fix + (q4_0 - d16) : nullptr; c.bytes[2] = p.fix ? up_to(d16 + nq4, 16) : 0u;   // same geometry as the bases
+    // verdicts: a byte per quad (two words per eight quads), same geometry as the bases
+    c.src[2] = p.fix ? reinterpret_cast<const uint8_t*>(p.fix) + (q4_0 - d16) : nullptr; c.bytes[2] = p.fix ? up_to(d16 + nq4, 16) : 0u;
     c.src[3] = p.seg_pos + (sg_0 - ds);          c.bytes[3] = up_to(ds + nseg, 4) * 4u;
     c.src[4] = p.seg_len + (sg_0 - dl);          c.bytes[4] = up_to(dl + nseg, 8) * 2u;
     c.src[5] = p.seq2 + (q4_0 - d16);            c.bytes[5] = up_to(d16 + nq4, 16);
-    c.src[6] = p.qual + 4u * (size_t)(q4_0 - dq); c.bytes[6] = up_to(dq + nq4, 4) * 4u;
+    c.src[6] = p.qual + 4u * (size_t)(q4_0 - d16); c.bytes[6] = up_to(d16 + nq4, 4) * 4u;
     return c;
 }
 __device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes)
@@ -551,7 +604,7 @@ __device__ __forceinline__ void prefetch_chunk(const SrcPtrs& p, uint32_t c0, ui
 
 // ---- producer: one chunk into the next stage of the ring (whole warp waits; lane `issuer` writes the header and issues)
 __device__ __forceinline__ void pileup_issue_chunk(uint8_t* smem, const PileupSmem& L, const PileupShape& sh, uint32_t& chunk_no, uint32_t issuer, const SrcPtrs& src,
-                                                   const uint8_t* __restrict__ expect, uint32_t item, uint32_t sample, uint32_t tile, uint32_t c0,
+                                                   const uint8_t* __restrict__ expect2, uint32_t item, uint32_t sample, uint32_t tile, uint32_t c0,
                                                    uint32_t m, uint32_t q4_0, uint32_t nq4, uint32_t sg_0, uint32_t nseg, uint32_t flags)
 {
     uint64_t* full = (uint64_t*)(smem + L.bar);
@@ -563,16 +616,17 @@ __device__ __forceinline__ void pileup_issue_chunk(uint8_t* smem, const PileupSm
         ChunkHdr* h = (ChunkHdr*)(stage + L.o_hdr);
         h->m = m; h->nq4 = nq4; h->q4_0 = q4_0; h->sg_0 = sg_0; h->nseg = nseg; h->c0 = c0;
         h->item = item; h->sample = sample; h->tile = tile; h->flags = flags | (src.fix ? CHUNK_FIX : 0u);
+        h->spanq = (src.max_span + 3u) / 4u + 1u;
         const ChunkCopies c = chunk_copies(src, c0, m, q4_0, nq4, sg_0, nseg);
         const uint32_t dst[7] = {L.o_q4, L.o_sg, L.o_fix, L.o_sp, L.o_sl, L.o_seq, L.o_qual};
-        uint32_t total = (uint32_t)TILE;
+        uint32_t total = (uint32_t)EXP_BYTES;
         #pragma unroll
         for (int i = 0; i < 7; ++i) total += c.bytes[i];
         fence_proxy_async();
         mbar_expect_tx(full + s, total);
         #pragma unroll
         for (int i = 0; i < 7; ++i) if (c.bytes[i]) tma_load_1d(stage + dst[i], c.src[i], c.bytes[i], full + s);
-        tma_load_1d(stage + L.o_exp, expect + (size_t)tile * TILE, TILE, full + s);
+        tma_load_1d(stage + L.o_exp, expect2 + (size_t)tile * EXP_BYTES, EXP_BYTES, full + s);
     }
     __syncwarp();
     ++chunk_no;
@@ -581,7 +635,7 @@ __device__ __forceinline__ void pileup_issue_chunk(uint8_t* smem, const PileupSm
 constexpr uint32_t PREFETCH_AHEAD = 4;       // items between a chunk's L2 prefetch and its copy
 
 __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem& L, const PileupShape sh, const SampleDev* __restrict__ samples,
-                                                const Item* __restrict__ items, uint32_t n_items, const uint8_t* __restrict__ expect,
+                                                const Item* __restrict__ items, uint32_t n_items, const uint8_t* __restrict__ expect2,
                                                 int* __restrict__ err_flag)
 {
     const uint32_t lane = threadIdx.x & 31, G = gridDim.x;
@@ -606,7 +660,7 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
             if (idx >= n_items) break;
             if (lane == k + PREFETCH_AHEAD && whole) prefetch_chunk(src, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo, g_hi - g_lo);
             if (__shfl_sync(0xffffffffu, (int)whole, k)) {                   // the lane that owns the item issues it from its own registers
-                pileup_issue_chunk(smem, L, sh, chunk_no, k, src, expect, (uint32_t)mine, it.x, it.y, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo,
+                pileup_issue_chunk(smem, L, sh, chunk_no, k, src, expect2, (uint32_t)mine, it.x, it.y, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo,
                                    g_hi - g_lo, CHUNK_FIRST | CHUNK_LAST | (item_is_wide(it.z, it.w) ? CHUNK_WIDE : 0u));
                 continue;
             }
@@ -637,7 +691,7 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
                         const uint32_t bk = __shfl_sync(0xffffffffu, b_l, kk), ek = __shfl_sync(0xffffffffu, e_l, kk);
                         if (ek == bk) break;                                             // past the end of the item
                         if (lane == kk + PREFETCH_AHEAD && lane < n_ok && e_l > b_l) prefetch_chunk(sp, b_l, e_l - b_l, qb, qe - qb, gb, ge - gb);
-                        pileup_issue_chunk(smem, L, sh, chunk_no, kk, sp, expect, (uint32_t)idx, sample, tile, b_l, e_l - b_l, qb, qe - qb, gb, ge - gb, fl);
+                        pileup_issue_chunk(smem, L, sh, chunk_no, kk, sp, expect2, (uint32_t)idx, sample, tile, b_l, e_l - b_l, qb, qe - qb, gb, ge - gb, fl);
                         done_to = ek; done_q = __shfl_sync(0xffffffffu, qe, kk); done_g = __shfl_sync(0xffffffffu, ge, kk);
                     }
                     c0 = done_to; qc = done_q; gc = done_g;
@@ -658,11 +712,11 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
                 const uint32_t first = c0 == r_lo ? CHUNK_FIRST : 0u;
                 if (m == 0) {                        // a single read over the documented limits: host validation failed
                     if (lane == 0) atomicExch(err_flag, 1);
-                    pileup_issue_chunk(smem, L, sh, chunk_no, 0u, sp, expect, (uint32_t)idx, sample, tile, c0, 0u, qc, 0u, gc, 0u, first | CHUNK_LAST | wide);
+                    pileup_issue_chunk(smem, L, sh, chunk_no, 0u, sp, expect2, (uint32_t)idx, sample, tile, c0, 0u, qc, 0u, gc, 0u, first | CHUNK_LAST | wide);
                     break;
                 }
                 const uint32_t qn = __ldg(q4p + c0 + m), gn = __ldg(sgp + c0 + m);
-                pileup_issue_chunk(smem, L, sh, chunk_no, 0u, sp, expect, (uint32_t)idx, sample, tile, c0, m, qc, qn - qc, gc, gn - gc,
+                pileup_issue_chunk(smem, L, sh, chunk_no, 0u, sp, expect2, (uint32_t)idx, sample, tile, c0, m, qc, qn - qc, gc, gn - gc,
                                    first | (c0 + m == r_hi ? CHUNK_LAST : 0u) | wide);
                 c0 += m; qc = qn; gc = gn;
             }
@@ -679,13 +733,49 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
     }
 }
 
-// CONSUMERS: consumer threads (128: four CTAs per SM at the standard shape; 256: three larger ones).
+// ---- vertical counters: plane b holds bit b of 32 per-position counts
+// add the 0/1 word `mk` to the counters c[0..8) (a chunk stages at most 255 reads: eight planes never overflow)
+__device__ __forceinline__ void csa_add(uint32_t (&c)[8], uint32_t mk)
+{
+    uint32_t carry = c[0] & mk; c[0] ^= mk;
+    uint32_t t = c[1] & carry; c[1] ^= carry; carry = t;
+    t = c[2] & carry; c[2] ^= carry; carry = t;
+    t = c[3] & carry; c[3] ^= carry; carry = t;
+    if (carry) {                                                            // a count passed 15: rare at ordinary depth
+        #pragma unroll
+        for (int b = 4; b < 8; ++b) { t = c[b] & carry; c[b] ^= carry; carry = t; }
+    }
+}
+// c += the counters of the lane `lane ^ off` (bit-sliced full adders over PLANES planes), every lane of the warp
+template <int PLANES>
+__device__ __forceinline__ void csa_combine(uint32_t (&c)[8], uint32_t off)
+{
+    uint32_t carry = 0;
+    #pragma unroll
+    for (int b = 0; b < PLANES; ++b) {
+        const uint32_t p = __shfl_xor_sync(0xffffffffu, c[b], off);
+        const uint32_t s = c[b] ^ p ^ carry;
+        carry = (c[b] & p) | (carry & (c[b] ^ p));
+        c[b] = s;
+    }
+}
+// byte lanes of quad qi (positions 4 qi .. 4 qi + 3 of the word) from PLANES planes
+template <int PLANES>
+__device__ __forceinline__ uint32_t csa_quad_lanes(const uint32_t (&c)[8], uint32_t qi)
+{
+    uint32_t v = 0;
+    #pragma unroll
+    for (int b = 0; b < PLANES; ++b) v |= (((c[b] >> (4u * qi)) & 15u) * (0x00204081u << b)) & (0x01010101u << b);
+    return v;
+}
+
+// CONSUMERS: consumer threads (128: four CTAs per SM at the standard shape; 256: two larger ones for deep shards).
 // HAS_WIDE: the shard has items with more than 255 reads (deep coverage); without them the 16-bit accumulators and
 // their registers do not exist.
 template <int CONSUMERS, bool HAS_WIDE>
-__global__ void __launch_bounds__(CONSUMERS + 32, CONSUMERS == 128 ? 4 : 3)
+__global__ void __launch_bounds__(CONSUMERS + 32, CONSUMERS == 128 ? 4 : 2)
 pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items, const PileupShape sh,
-              const uint8_t* __restrict__ expect, uint8_t* __restrict__ tiles /*[n_items][SLOT_BYTES]*/, int* __restrict__ err_flag)
+              const uint8_t* __restrict__ expect2, uint8_t* __restrict__ tiles /*[n_items][SLOT_BYTES]*/, int* __restrict__ err_flag)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const PileupSmem L = pileup_smem_layout(sh);
@@ -701,13 +791,19 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     __syncthreads();
 
     if (threadIdx.x >= CONSUMERS) {
-        pileup_producer(smem, L, sh, samples, items, n_items, expect, err_flag);
+        pileup_producer(smem, L, sh, samples, items, n_items, expect2, err_flag);
         return;
     }
 
     // ------------------------------------------------------------------------------------ consumers
-    const uint32_t tid = threadIdx.x;
-    uint8_t* s_tags = smem + L.tags;
+    constexpr uint32_t NWARPS = CONSUMERS / 32;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t* s_pb = (uint32_t*)(smem + L.pbits);                   // pass word of buffer quads 8u .. 8u+7 in s_pb[u + 1]
+    int2* s_seg = (int2*)(smem + L.segtab);                        // per staged segment: tile-relative quad of its first quad | first buffer quad, quads << 16
+    int16_t* s_jr = (int16_t*)(smem + L.jr);                       // per staged read: tile-relative quad of its first segment
+    uint16_t* s_wend = (uint16_t*)(smem + L.wend);                 // per word of the tile: staged reads that start in or before it
+    uint16_t* s_list = (uint16_t*)(smem + L.list);                 // groups with exceptions
+    uint32_t* s_misc = (uint32_t*)(smem + L.misc);                 // [0] length of the list
     // wide items: per plane and owned quad (QPT * tid + k), 16-bit lanes: [0] = positions 0 and 2, [1] = positions 1 and 3
     constexpr int QPT = TILE_QUADS / CONSUMERS;                 // quads a thread folds (2 or 1)
     uint32_t acc[HAS_WIDE ? N_PLANES : 1][QPT][2];
@@ -724,137 +820,235 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
         const uint32_t flags = h->flags;
         if (flags & CHUNK_STOP) break;
         const uint32_t m = h->m, nq4 = h->nq4, q4_0 = h->q4_0, sg_0 = h->sg_0, nseg = h->nseg, c0 = h->c0, item = h->item;
+        const int32_t spanq = (int32_t)h->spanq;
         const int32_t p0 = (int32_t)(h->tile * TILE);
-        const uint32_t dm = c0 & 3u, dq = q4_0 & 3u, c12 = q4_0 & 12u;
+        const uint32_t dm = c0 & 3u, dq = q4_0 & 15u;
         const uint32_t* s_q4 = (const uint32_t*)(stage + L.o_q4) + dm;          // s_q4[t] = q4_off[c0 + t], t <= m
         const uint32_t* s_sgo = (const uint32_t*)(stage + L.o_sg) + dm;
         const int32_t* s_sp = (const int32_t*)(stage + L.o_sp) + (sg_0 & 3u);   // s_sp[k] = seg_pos[sg_0 + k], k < nseg
         const uint16_t* s_sl = (const uint16_t*)(stage + L.o_sl) + (sg_0 & 7u);
-        uint32_t* s_qw = (uint32_t*)(stage + L.o_qual);                         // qualities of buffer quad B in word B
-        uint8_t* s_fx = stage + L.o_fix + c12;                                  // overlap verdicts of buffer quad B (samples with mates)
+        uint8_t* s_x = stage + L.o_seq;                                         // bases of buffer quad B in byte B (prep: XOR expected letters)
+        const uint8_t* s_e = stage + L.o_exp;                                   // expected letters, four shifted copies
         const bool has_fix = (flags & CHUNK_FIX) != 0;
-        const uint32_t nbq = dq + nq4, ngroups = (nbq + 3u) >> 2;               // staged quad g is buffer quad g + dq
-        // a quad that must not count (off the tile, in front of or behind the chunk): no quality passes and no verdict overrides
-        auto mute = [&](uint32_t g) { s_qw[g] = 0; if (has_fix) s_fx[g] = 0; };
+        const uint32_t nbq = dq + nq4, ngroups = (nbq + 7u) >> 3;               // buffer quad g is quad (q4_0 - dq) + g of the sample
+        const uint32_t qbase = q4_0 - dq;                                       // s_q4[t] - qbase = first buffer quad of read t
 
-        // ---- 1. one thread per read: tags of the quads on the tile, zeroed qualities off it
+        // ---- 1. prep: one thread per read
         for (uint32_t t = tid; t < m; t += CONSUMERS) {
             const uint32_t k0 = s_sgo[t] - sg_0, k1 = s_sgo[t + 1] - sg_0;
-            uint32_t B = s_q4[t] - q4_0 + dq;                                   // first buffer quad of the next segment
-            const uint32_t B_end = s_q4[t + 1] - q4_0 + dq;
-            if (k1 < k0 || k1 > nseg || B_end < B || B_end > nbq) { atomicExch(err_flag, 2); continue; }   // offsets not prefix sums
+            uint32_t B = s_q4[t] - qbase;                                       // first buffer quad of the next segment
+            const uint32_t B_end = s_q4[t + 1] - qbase;
+            if (k1 <= k0 || k1 > nseg || B_end < B || B_end > nbq) {            // offsets not prefix sums / a read without segments
+                atomicExch(err_flag, 2);
+                s_jr[t] = t ? s_jr[0] : (int16_t)0;                             // (keeps the walk below inside the tables; the run fails anyway)
+                continue;
+            }
+            int32_t j_first = 0;
             for (uint32_t k = k0; k < k1; ++k) {
                 const int32_t p = s_sp[k];
                 const uint32_t len = s_sl[k];
                 const uint32_t a = (uint32_t)p & 3u;
-                const int32_t nq = (int32_t)((a + len + 3u) >> 2);
+                const uint32_t nq = (a + len + 3u) >> 2;
                 const int32_t jw = (p - (int32_t)a - p0) >> 2;                  // tile-relative index of the segment's first quad
-                if (B + (uint32_t)nq > B_end) break;                            // segments and offsets disagree: flagged below
-                int32_t i_lo = jw < 0 ? -jw : 0; if (i_lo > nq) i_lo = nq;
-                int32_t i_hi = TILE_QUADS - jw; if (i_hi > nq) i_hi = nq; if (i_hi < i_lo) i_hi = i_lo;
-                for (int32_t i = 0; i < i_lo; ++i) mute(B + (uint32_t)i);
-                for (int32_t i = i_hi; i < nq; ++i) mute(B + (uint32_t)i);
-                uint32_t g = B + (uint32_t)i_lo, tv = (uint32_t)(jw + i_lo);
-                const uint32_t e = B + (uint32_t)i_hi;                          // tags tv .. tv + (e - g) - 1 are within 0..255
-                if (!(sh.ablate & 2u)) {   // up to three single tags to a word boundary, words of four consecutive tags, up to three single tags
+                if (B + nq > B_end) break;                                      // segments and offsets disagree: flagged below
+                if (k == k0) j_first = jw;
+                s_seg[k] = make_int2(jw, (int32_t)(B | (nq << 16)));
+                int32_t i_lo = jw < 0 ? -jw : 0; if (i_lo > (int32_t)nq) i_lo = (int32_t)nq;
+                int32_t i_hi = TILE_QUADS - jw; if (i_hi > (int32_t)nq) i_hi = (int32_t)nq; if (i_hi < i_lo) i_hi = i_lo;
+                // bases XOR expected letters; quads off the tile and the padding lanes of the first / last quad become 0
+                for (int32_t i = 0; i < i_lo; ++i) s_x[B + (uint32_t)i] = 0;
+                for (int32_t i = i_hi; i < (int32_t)nq; ++i) s_x[B + (uint32_t)i] = 0;
+                if (!(sh.ablate & ABL_PREP_XOR)) {
+                    uint32_t g = B + (uint32_t)i_lo, j = (uint32_t)(jw + i_lo);
+                    const uint32_t e = B + (uint32_t)i_hi;
+                    // up to three single quads to a word boundary, words of four quads, up to three single quads
                     uint32_t hn = (0u - g) & 3u; if (hn > e - g) hn = e - g;
-                    if (hn > 0u) s_tags[g] = (uint8_t)tv;
-                    if (hn > 1u) s_tags[g + 1] = (uint8_t)(tv + 1u);
-                    if (hn > 2u) s_tags[g + 2] = (uint8_t)(tv + 2u);
-                    g += hn; tv += hn;
-                    uint32_t wv = tv * 0x01010101u + 0x03020100u;                   // no lane passes 255: all four quads are on the tile
-                    uint32_t* tw = reinterpret_cast<uint32_t*>(s_tags + g);
-                    const uint32_t nw = (e - g) >> 2;
-                    uint32_t w = 0;
-                    for (; w + 2u <= nw; w += 2u, wv += 0x08080808u) { tw[w] = wv; tw[w + 1] = wv + 0x04040404u; }
-                    if (w < nw) { tw[w] = wv; ++w; }
-                    g += 4u * nw; tv += 4u * nw;
-                    const uint32_t tn = e - g;
-                    if (tn > 0u) s_tags[g] = (uint8_t)tv;
-                    if (tn > 1u) s_tags[g + 1] = (uint8_t)(tv + 1u);
-                    if (tn > 2u) s_tags[g + 2] = (uint8_t)(tv + 2u);
+                    for (uint32_t i = 0; i < hn; ++i, ++g, ++j) s_x[g] ^= s_e[j];
+                    uint32_t* xw = reinterpret_cast<uint32_t*>(s_x + g);
+                    const uint32_t nw4 = (e - g) >> 2;
+                    // expected letters of quads j .. j+3: copy j & 3, word j >> 2 (the copy stays the same as j advances by four)
+                    const uint32_t* ew = reinterpret_cast<const uint32_t*>(s_e + (j & 3u) * (uint32_t)EXP_COPY_BYTES + (j & ~3u));
+                    for (uint32_t w = 0; w < nw4; ++w) xw[w] ^= ew[w];
+                    g += 4u * nw4; j += 4u * nw4;
+                    for (; g < e; ++g, ++j) s_x[g] ^= s_e[j];
+                    if (i_lo == 0 && i_hi > 0 && a) s_x[B] &= (uint8_t)(0xffu << (2u * a));
+                    const uint32_t tl = (a + len) & 3u;
+                    if (tl && i_hi == (int32_t)nq && i_hi > i_lo) s_x[B + nq - 1u] &= (uint8_t)(0xffu >> (8u - 2u * tl));
                 }
-                B += (uint32_t)nq;
+                B += nq;
             }
             if (B != B_end) {                                                   // quads no segment owns: keep them out of the counts
                 atomicExch(err_flag, 2);
-                for (uint32_t g = B; g < B_end; ++g) mute(g);
+                for (uint32_t g = B; g < B_end; ++g) s_x[g] = 0;
             }
+            s_jr[t] = (int16_t)max(-32768, min(32767, j_first));
+            // reads are in coordinate order: word w of the tile is started in or before by the reads [0, s_wend[w])
+            int32_t wa = j_first >> 3; wa = wa < 0 ? 0 : (wa > 32 ? 32 : wa);
+            int32_t wb = 32;
+            if (t + 1 < m) {
+                const uint32_t kn = s_sgo[t + 1] - sg_0;
+                const int32_t pn = kn < nseg ? s_sp[kn] : p0 + 32 * TILE;
+                wb = ((pn & ~3) - p0) >> 5; wb = wb < 0 ? 0 : (wb > 32 ? 32 : wb);
+            }
+            for (int32_t w = wa; w < wb; ++w) s_wend[w] = (uint16_t)(t + 1);
+            if (t == 0) for (int32_t w = 0; w < wa; ++w) s_wend[w] = 0;
         }
         if (tid == CONSUMERS - 1) {                                             // elements in front of and behind the chunk in the buffer
-            for (uint32_t g = 0; g < dq; ++g) mute(g);
-            for (uint32_t g = nbq; g < 4u * ngroups; ++g) mute(g);
+            for (uint32_t g = 0; g < dq; ++g) s_x[g] = 0;
+            for (uint32_t g = nbq; g < 8u * ngroups; ++g) s_x[g] = 0;
+            s_misc[0] = 0;
         }
         consumer_sync<CONSUMERS>();
 
-        // ---- 2. scatter: four consecutive buffer quads per thread and step
+        // ---- 2. extract: 32 staged positions per thread and step -> one pass word; groups with exceptions -> list
         {
-            const uint32_t a_q = smem_u32(s_qw), a_s = smem_u32(stage + L.o_seq) + c12, a_f = smem_u32(stage + L.o_fix) + c12, a_g = smem_u32(s_tags);
-            const uint32_t a_c = smem_u32(s_cnt), a_e = smem_u32(stage + L.o_exp);
-            for (uint32_t u = tid; u < ((sh.ablate & 1u) ? 0u : ngroups); u += CONSUMERS) {
-                const uint4 qv = lds_v4(a_q + 16u * u);
-                const uint32_t sw = lds_u32(a_s + 4u * u), tw = lds_u32(a_g + 4u * u);
-                const uint32_t qa[4] = {qv.x, qv.y, qv.z, qv.w};
-                uint32_t xs[4], mm[4], ac[4], nn[4], nn_any = 0, mm_any = 0;
-                if (!has_fix) {
+            const uint32_t a_q = smem_u32(stage + L.o_qual), a_x = smem_u32(s_x), a_f = smem_u32(stage + L.o_fix);
+            for (uint32_t u0 = tid & ~31u; u0 < ((sh.ablate & ABL_EXTRACT) ? 0u : ngroups); u0 += CONSUMERS) {
+                const uint32_t u = u0 + lane;
+                bool listed = false;
+                if (u < ngroups) {
+                    const uint4 qa = lds_v4(a_q + 32u * u), qb = lds_v4(a_q + 32u * u + 16u);
+                    const uint32_t q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                    uint32_t pw = 0, orq = 0;
                     #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t q = qa[k];
-                        const uint32_t j = __byte_perm(tw, 0u, 0x4440u + k);                // tile-relative quad
-                        ac[k] = a_c + 4u * j;                                               // its word in plane D
-                        xs[k] = msnv_spread_bases(__byte_perm(sw, 0u, 0x4440u + k));        // one 2-bit base per byte lane
-                        const uint32_t v = (q & 0x7f7f7f7fu) + 0x73737373u;                 // bit 7 of a lane: quality >= 13
-                        uint32_t ok;                                                        // ... and the base is A/C/G/T
-                        asm("lop3.b32 %0, %1, %2, 0x80808080, 0x20;" : "=r"(ok) : "r"(v), "r"(q));    // v & ~q & 0x80808080
-                        ok >>= 7;
-                        const uint32_t d = xs[k] ^ lds_u32(a_e + 4u * j);                   // differs from the expected letter?
-                        red_shared_add(ac[k], ok);
-                        mm[k] = (d | (d >> 1)) & ok;
-                        mm_any |= mm[k];
-                        nn[k] = v & q;                                                      // bit 7: counted base that is not A/C/G/T
-                        nn_any |= nn[k];
+                    for (int k = 7; k >= 0; --k) {
+                        const uint32_t v = (q[k] & 0x7f7f7f7fu) + 0x73737373u;          // bit 7 of a lane: quality >= 13
+                        uint32_t ok;                                                    // ... and the base is A/C/G/T
+                        asm("lop3.b32 %0, %1, %2, 0x80808080, 0x20;" : "=r"(ok) : "r"(v), "r"(q[k]));    // v & ~q & 0x80808080
+                        pw = __funnelshift_l(ok * 0x00204081u, pw, 4);                  // the four bits 7 -> the product's top nibble
+                        orq |= q[k];
                     }
-                } else {
-                    // the sample has mate verdicts: where the overlap rule spoke (low nibble of the quad's fix byte) its verdict
-                    // (high nibble) replaces the quality test
-                    const uint32_t fw = lds_u32(a_f + 4u * u);
-                    #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t q = qa[k];
-                        const uint32_t j = __byte_perm(tw, 0u, 0x4440u + k);
-                        ac[k] = a_c + 4u * j;
-                        xs[k] = msnv_spread_bases(__byte_perm(sw, 0u, 0x4440u + k));
-                        const uint32_t f = __byte_perm(fw, 0u, 0x4440u + k);
-                        const uint32_t ovr = nibble_to_lanes(f), val = nibble_to_lanes(f >> 4);
-                        const uint32_t qp = (((q & 0x7f7f7f7fu) + 0x73737373u) >> 7) & 0x01010101u;   // quality >= 13
-                        const uint32_t pass = (qp & ~ovr) | (val & ovr);
-                        const uint32_t fl = (q >> 7) & 0x01010101u;                         // the base is not A/C/G/T
-                        const uint32_t ok = pass & ~fl;
-                        const uint32_t d = xs[k] ^ lds_u32(a_e + 4u * j);
-                        red_shared_add(ac[k], ok);
-                        mm[k] = (d | (d >> 1)) & ok;
-                        mm_any |= mm[k];
-                        nn[k] = (pass & fl) << 7;
-                        nn_any |= nn[k];
-                    }
-                }
-                if (mm_any && !(sh.ablate & 32u)) {                                     // counted bases that are not the expected letter:
-                    #pragma unroll                                                      // only the lanes that hold one loop over their set bits
-                    for (int k = 0; k < 4; ++k) {
-                        uint32_t r = mm[k];
-                        while (r) {
-                            const uint32_t b = (uint32_t)__ffs((int)r) - 1u;            // 0, 8, 16 or 24
-                            red_shared_add(ac[k] + (PLANE_A + ((xs[k] >> b) & 3u)) * (uint32_t)TILE, 1u << b);
-                            r &= r - 1u;
+                    const uint32_t nf = orq & 0x80808080u;                              // some base of the group is not A/C/G/T
+                    if (has_fix) {
+                        // mate verdicts: where the overlap rule spoke (first word) its verdict (second word) replaces the quality test
+                        const uint2 f = lds_v2(a_f + 8u * u);
+                        uint32_t val = f.y;
+                        if (nf) {                                                       // a flagged base never counts in D, whatever the verdict
+                            uint32_t fl = 0;
+                            #pragma unroll
+                            for (int k = 7; k >= 0; --k) fl = __funnelshift_l((q[k] & 0x80808080u) * 0x00204081u, fl, 4);
+                            val &= ~fl;
                         }
+                        pw = (pw & ~f.x) | (val & f.x);
+                    }
+                    s_pb[u + 1u] = pw;
+                    const uint2 x = lds_v2(a_x + 8u * u);
+                    listed = (x.x | x.y | nf) != 0u;
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, listed);
+                if (bal) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&s_misc[0], (uint32_t)__popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (listed) s_list[base + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = (uint16_t)u;
+                }
+            }
+        }
+        consumer_sync<CONSUMERS>();
+
+        // ---- 3. exceptions: counted bases that differ from the expected letter, counted non-ACGT bases
+        if (!(sh.ablate & ABL_EXCEPT)) {
+            const uint32_t n_listed = s_misc[0];
+            const uint32_t a_c = smem_u32(s_cnt);
+            const uint32_t* s_qw = (const uint32_t*)(stage + L.o_qual);
+            const uint2* s_fx = (const uint2*)(stage + L.o_fix);
+            for (uint32_t li = tid; li < n_listed; li += CONSUMERS) {
+                const uint32_t u = s_list[li];
+                const uint32_t pw = s_pb[u + 1u];
+                const uint32_t x0 = *reinterpret_cast<const uint32_t*>(s_x + 8u * u), x1 = *reinterpret_cast<const uint32_t*>(s_x + 8u * u + 4u);
+                // counted non-ACGT bases of the group, a bit per position
+                uint32_t np = 0;
+                {
+                    uint32_t qp = 0, fl = 0;
+                    #pragma unroll
+                    for (int k = 7; k >= 0; --k) {
+                        const uint32_t qk = s_qw[8u * u + (uint32_t)k];
+                        const uint32_t v = (qk & 0x7f7f7f7fu) + 0x73737373u;
+                        qp = __funnelshift_l((v & 0x80808080u) * 0x00204081u, qp, 4);
+                        fl = __funnelshift_l((qk & 0x80808080u) * 0x00204081u, fl, 4);
+                    }
+                    if (fl) {
+                        if (has_fix) { const uint2 f = s_fx[u]; qp = (qp & ~f.x) | (f.y & f.x); }
+                        np = qp & fl;
                     }
                 }
-                if (nn_any & 0x80808080u) {                                             // rare: counted non-ACGT bases
-                    #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t n7 = nn[k] & 0x80808080u;
-                        if (n7) red_shared_add(ac[k] + PLANE_N * (uint32_t)TILE, n7 >> 7);
+                uint32_t seg_b = 1u, seg_e = 0u; int32_t seg_j = 0;           // cached segment: buffer quads [seg_b, seg_e) start at tile quad seg_j
+                #pragma unroll 1
+                for (uint32_t i8 = 0; i8 < 8u; ++i8) {
+                    const uint32_t xb = ((i8 < 4u ? x0 : x1) >> (8u * (i8 & 3u))) & 0xffu;
+                    const uint32_t pn = (pw >> (4u * i8)) & 15u, nn = (np >> (4u * i8)) & 15u;
+                    uint32_t dz = (xb | (xb >> 1)) & 0x55u;                      // bit 2l: lane l differs from the expected letter
+                    dz = (dz | (dz >> 1)) & 0x33u; dz = (dz | (dz >> 2)) & 0x0fu;   // -> bit l
+                    const uint32_t mm = dz & pn;
+                    if (!(mm | nn)) continue;
+                    const uint32_t g = 8u * u + i8;
+                    if (g < seg_b || g >= seg_e) {
+                        // read that owns buffer quad g (bisection over the reads' offsets), then its segment
+                        if (g < s_q4[0] - qbase || g >= s_q4[m] - qbase) continue;
+                        uint32_t lo = 0, hi = m;
+                        while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_q4[mid] - qbase <= g) lo = mid; else hi = mid; }
+                        const uint32_t k0 = s_sgo[lo] - sg_0, k1 = s_sgo[lo + 1] - sg_0;
+                        bool found = false;
+                        if (k1 <= nseg)
+                            for (uint32_t k = k0; k < k1; ++k) {
+                                const int2 sg = s_seg[k];
+                                const uint32_t b = (uint32_t)sg.y & 0xffffu, nq = (uint32_t)sg.y >> 16;
+                                if (g >= b && g < b + nq) { seg_b = b; seg_e = b + nq; seg_j = sg.x; found = true; break; }
+                            }
+                        if (!found) { seg_b = 1u; seg_e = 0u; continue; }
                     }
+                    const int32_t j = seg_j + (int32_t)(g - seg_b);
+                    if ((uint32_t)j >= (uint32_t)TILE_QUADS) continue;
+                    const uint32_t letters = xb ^ (uint32_t)s_e[j];            // the bases themselves again
+                    const uint32_t ac = a_c + 4u * (uint32_t)j;
+                    #pragma unroll
+                    for (uint32_t l = 0; l < 4u; ++l)
+                        if ((mm >> l) & 1u) red_shared_add(ac + (PLANE_A + ((letters >> (2u * l)) & 3u)) * (uint32_t)TILE, 1u << (8u * l));
+                    if (nn) red_shared_add(ac + PLANE_N * (uint32_t)TILE, nibble_to_lanes(nn));
+                }
+            }
+        }
+
+        // ---- 4. depth: a thread owns one 32-position word of the tile and a share of the reads that can cover it
+        if (m && !(sh.ablate & ABL_DEPTH)) {
+            int32_t w_lo = (int32_t)s_jr[0] >> 3; if (w_lo < 0) w_lo = 0;
+            int32_t w_hi = ((int32_t)s_jr[m - 1] + spanq) >> 3; if (w_hi > 31) w_hi = 31;
+            if (w_hi >= w_lo) {
+                const uint32_t nw = (uint32_t)(w_hi - w_lo + 1);
+                // SL lanes share a word: the largest power of two that still gives every word a slot
+                uint32_t sl_log = 5; while ((32u >> sl_log) * NWARPS < nw) --sl_log;
+                const uint32_t SL = 1u << sl_log, wpw = 32u >> sl_log, nslots = wpw * NWARPS;
+                const uint32_t slot = warp * wpw + (lane >> sl_log);
+                const uint32_t wi = slot % nw, blk = slot / nw, nblk = (nslots - 1u - wi) / nw + 1u;
+                const int32_t sub = (int32_t)(blk * SL + (lane & (SL - 1u))), nsub = (int32_t)(nblk * SL);
+                const int32_t w = w_lo + (int32_t)wi, q0w = 8 * w;                 // first tile quad of the word
+                uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                int32_t r_top = (int32_t)s_wend[w]; if (r_top > (int32_t)m) r_top = (int32_t)m;
+                for (int32_t r = r_top - 1 - sub; r >= 0; r -= nsub) {
+                    if ((int32_t)s_jr[r] + spanq <= q0w) break;                    // this read and all before it end in front of the word
+                    const uint32_t k0 = s_sgo[r] - sg_0; uint32_t k1 = s_sgo[r + 1] - sg_0; if (k1 > nseg) k1 = nseg;
+                    for (uint32_t k = k0; k < k1; ++k) {
+                        const int2 sg = s_seg[k];
+                        const int32_t jw = sg.x, b = (int32_t)((uint32_t)sg.y & 0xffffu), nq = (int32_t)((uint32_t)sg.y >> 16);
+                        int32_t i_lo = jw - q0w; if (i_lo < 0) i_lo = 0;
+                        int32_t i_hi = jw + nq - q0w; if (i_hi > 8) i_hi = 8;
+                        if (i_hi <= i_lo) continue;
+                        const uint32_t bit = (uint32_t)(4 * (b + q0w - jw) + 32);      // the word's first position in the pass bits (one word of slack in front)
+                        const uint32_t lo = s_pb[bit >> 5], hi = s_pb[(bit >> 5) + 1u];
+                        const uint32_t mk = __funnelshift_r(lo, hi, bit & 31u) & (0xffffffffu << (4 * i_lo)) & (0xffffffffu >> (32 - 4 * i_hi));
+                        csa_add(c, mk);
+                    }
+                }
+                __syncwarp();
+                // the SL lanes of a word add their counters, then each expands its share of the word's eight quads
+                const bool hi_any = __any_sync(0xffffffffu, (c[4] | c[5] | c[6] | c[7]) != 0u);
+                const uint32_t a_d = smem_u32(s_cnt) + 4u * (uint32_t)q0w;
+                if (!hi_any && sl_log <= 2u) {
+                    for (uint32_t off = 1; off < SL; off <<= 1) csa_combine<6>(c, off);
+                    for (uint32_t qi = lane & (SL - 1u); qi < 8u; qi += SL) { const uint32_t v = csa_quad_lanes<6>(c, qi); if (v) red_shared_add(a_d + 4u * qi, v); }
+                } else {
+                    for (uint32_t off = 1; off < SL; off <<= 1) csa_combine<8>(c, off);
+                    for (uint32_t qi = lane & (SL - 1u); qi < 8u; qi += SL) { const uint32_t v = csa_quad_lanes<8>(c, qi); if (v) red_shared_add(a_d + 4u * qi, v); }
                 }
             }
         }
@@ -862,7 +1056,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
         consumer_sync<CONSUMERS>();
         if (tid == 0) mbar_arrive(empty + st);
 
-        // ---- 4. counts of the chunk
+        // ---- 5. counts of the chunk
         if (HAS_WIDE && (flags & CHUNK_WIDE)) {
             #pragma unroll
             for (int c = 0; c < (HAS_WIDE ? N_PLANES : 1); ++c)
@@ -884,7 +1078,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                         acc[c][k][0] = acc[c][k][1] = 0;
                     }
             }
-        } else if ((flags & CHUNK_LAST) && !(sh.ablate & 8u)) {
+        } else if ((flags & CHUNK_LAST) && !(sh.ablate & ABL_STORE)) {
             uint4* cnt4 = reinterpret_cast<uint4*>(s_cnt);
             uint4* dst = reinterpret_cast<uint4*>(tiles + (size_t)item * SLOT_BYTES);
             for (uint32_t i = tid; i < (uint32_t)(N_PLANES * TILE / 16); i += CONSUMERS) {
@@ -893,7 +1087,8 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                 dst[i] = w;
             }
         }
-        // no barrier here: the next chunk touches the counters again only after its own barriers
+        // The next chunk's prep writes the segment records, first quads and word index again while slower warps may still
+        // be copying counts out: those are different arrays; the counters are next touched behind the next chunk's barriers.
     }
 }
 

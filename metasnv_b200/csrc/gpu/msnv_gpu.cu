@@ -54,6 +54,7 @@ struct msnv_ctx {
     uint64_t gen = 0;                   // counts msnv_window_begin calls: pool entries unused for a while are freed
     uint8_t* d_ref = nullptr;
     uint8_t* d_expect = nullptr;        // expected letter per position (derived from d_ref)
+    uint8_t* d_expect2 = nullptr;       // the same, 2 bits per position in the pileup kernel's geometry (EXP_BYTES per tile)
 
     // ---- work buffers (grown on demand, kept across windows and shards)
     Item* d_items = nullptr;        uint64_t cap_items = 0;
@@ -396,7 +397,7 @@ static int launch_pileup(msnv_ctx* ctx, const msnv_ctx::Window& w, uint32_t a, u
     int ctas = 1;
     bool has_fix = false;
     for (const SampleDev& sd : w.h_samples) has_fix = has_fix || sd.fix;
-    const PileupShape sh = choose_pileup_shape(w.n_reads, w.n_bases, w.n_segs, n_items_window, item_reads, has_fix, consumers == 256 ? 3 : 4, ctas);   // register-bound CTA counts
+    const PileupShape sh = choose_pileup_shape(w.n_reads, w.n_bases, w.n_segs, n_items_window, item_reads, has_fix, consumers == 256 ? 2 : 4, ctas);   // register-bound CTA counts
     const size_t smem = pileup_smem_layout(sh).total;
     const bool has_wide = item_reads_max > NARROW_MAX_READS;
     const int threads = consumers + 32;
@@ -411,7 +412,7 @@ static int launch_pileup(msnv_ctx* ctx, const msnv_ctx::Window& w, uint32_t a, u
     if (fit < ctas) ctas = fit;
     uint64_t grid = (uint64_t)ctas * (uint64_t)ctx->sm_count;
     if (grid > n) grid = n;
-    MSNV_PILEUP_DISPATCH((K<<<(unsigned)grid, threads, smem, ctx->stream>>>(w.d_samples, ctx->d_items + a, n, sh, ctx->d_expect, ctx->d_tiles, ctx->d_err)));
+    MSNV_PILEUP_DISPATCH((K<<<(unsigned)grid, threads, smem, ctx->stream>>>(w.d_samples, ctx->d_items + a, n, sh, ctx->d_expect2, ctx->d_tiles, ctx->d_err)));
 #undef MSNV_PILEUP_DISPATCH
     ++launches;
     if (getenv("MSNV_VERBOSE"))
@@ -451,8 +452,9 @@ static int run_window(msnv_ctx* ctx, uint32_t slot, const msnv_call_params* prm,
     cudaEvent_t ev_m0 = ctx->ev[2], ev_m1 = ctx->ev[3];
     CU(cudaEventRecord(ev_m0, st));
     if (any_fix) {
+        unsigned gm = (unsigned)((max_reads * 8 + 255) / 256); if (gm < 1) gm = 1; if (gm > 2048) gm = 2048;     // eight lanes per pair
         fix_clear_kernel<<<dim3(gx, S), 256, 0, st>>>(w.d_samples);
-        mate_kernel<<<dim3(gx, S), 256, 0, st>>>(w.d_samples);
+        mate_kernel<<<dim3(gm, S), 256, 0, st>>>(w.d_samples);
         launches += 2;
     }
     CU(cudaEventRecord(ev_m1, st));
@@ -460,7 +462,8 @@ static int run_window(msnv_ctx* ctx, uint32_t slot, const msnv_call_params* prm,
     CU(cudaEventRecord(ctx->ev[0], st));
     // expected letter per position of the window (msnv_shard_mask_position may have changed the reference since the last run)
     expect_kernel<<<(nt * TILE + 255) / 256, 256, 0, st>>>(ctx->d_ref + (size_t)w.t0 * TILE, nt * TILE, ctx->d_expect + (size_t)w.t0 * TILE);
-    ++launches;
+    expect2_kernel<<<(unsigned)(((uint64_t)nt * EXP_BYTES + 255) / 256), 256, 0, st>>>(ctx->d_expect + (size_t)w.t0 * TILE, nt, ctx->d_expect2 + (size_t)w.t0 * EXP_BYTES);
+    launches += 2;
     // ---- index
     const uint64_t n_pairs_idx = (uint64_t)nt * S;
     const uint64_t n_blocks = (n_pairs_idx + 255) / 256;
@@ -613,7 +616,7 @@ void msnv_destroy(msnv_ctx* ctx)
     drop_pool(ctx);
     for (auto& sl : ctx->slabs) cudaFree(sl.base);
     cudaFree(ctx->d_ref);
-    cudaFree(ctx->d_items); cudaFree(ctx->d_tiles); cudaFree(ctx->d_expect); cudaFree(ctx->d_text_acgt); cudaFree(ctx->d_text_match);
+    cudaFree(ctx->d_items); cudaFree(ctx->d_tiles); cudaFree(ctx->d_expect); cudaFree(ctx->d_expect2); cudaFree(ctx->d_text_acgt); cudaFree(ctx->d_text_match);
     cudaFree(ctx->d_tile_begin); cudaFree(ctx->d_tile_hits); cudaFree(ctx->d_flags); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_range_cache); cudaFree(ctx->d_bitmap);
     cudaFree(ctx->d_scalar); cudaFree(ctx->d_err);
     cudaFree(ctx->d_hit_pos); cudaFree(ctx->d_hit_total); cudaFree(ctx->d_hit_pop); cudaFree(ctx->d_hit_ind);
@@ -650,10 +653,11 @@ int msnv_shard_begin(msnv_ctx* ctx, uint32_t n_samples, uint32_t n_positions, co
     for (auto& w : ctx->win) release_window(ctx, w);
     ctx->S = n_samples; ctx->P = n_positions; ctx->n_tiles = n_positions / TILE;
     ctx->has_run = false;
-    cudaFree(ctx->d_ref); cudaFree(ctx->d_expect);
-    ctx->d_ref = nullptr; ctx->d_expect = nullptr;
+    cudaFree(ctx->d_ref); cudaFree(ctx->d_expect); cudaFree(ctx->d_expect2);
+    ctx->d_ref = nullptr; ctx->d_expect = nullptr; ctx->d_expect2 = nullptr;
     CU(cudaMalloc((void**)&ctx->d_ref, n_positions));
     CU(cudaMalloc((void**)&ctx->d_expect, n_positions));
+    CU(cudaMalloc((void**)&ctx->d_expect2, (size_t)(n_positions / TILE) * EXP_BYTES));
     CU(cudaMemcpyAsync(ctx->d_ref, ref, n_positions, cudaMemcpyHostToDevice, ctx->stream));
     ctx->open = true;
     // the whole shard as one window in slot 0 until msnv_window_begin says otherwise
@@ -702,7 +706,7 @@ int msnv_window_add_sample(msnv_ctx* ctx, uint32_t slot, uint32_t sample, const 
     for (size_t i = 0; i < n && !has_mates; ++i) has_mates = r->mate[i] >= 0;
     const size_t o_pos = take(n * 4), o_sgo = take(n1 * 4), o_q4 = take(n1 * 4), o_mate = take(n * 4),
                  o_sp = take(n_seg * 4), o_sl = take(n_seg * 2), o_seq = take(n_q4), o_qual = take(n_q4 * 4),
-                 o_fix = has_mates ? take(n_q4) : 0;       // verdicts of the mate-overlap rule, rebuilt by every run
+                 o_fix = has_mates ? take(fix_words(n_q4) * 4) : 0;       // verdicts of the mate-overlap rule, rebuilt by every run
     uint8_t* base = (uint8_t*)take_block(ctx, w, off);
     if (!base) return fail(ctx, MSNV_E_NOMEM, "sample %u: cannot allocate %zu bytes of device memory; process the shard in smaller windows (msnv_window_begin) or smaller genome bins (metaSNV.py --n_splits)", sample, off);
     cudaStream_t st = ctx->copy_stream;
@@ -720,7 +724,7 @@ int msnv_window_add_sample(msnv_ctx* ctx, uint32_t slot, uint32_t sample, const 
     d.mate = (const int32_t*)(base + o_mate);
     d.seg_pos = (const int32_t*)(base + o_sp);   d.seg_len = (const uint16_t*)(base + o_sl);
     d.seq2 = base + o_seq;                      d.qual = base + o_qual;
-    d.fix = has_mates ? base + o_fix : nullptr;
+    d.fix = has_mates ? (uint32_t*)(base + o_fix) : nullptr;
     d.n_reads = r->n_reads; d.max_span = r->max_span ? r->max_span : 1;
     w.n_reads += n; w.n_bases += 4ull * n_q4; w.n_segs += n_seg;
     uint64_t n_aligned = 0;
@@ -929,7 +933,7 @@ int msnv_window_synth(msnv_ctx* ctx, uint32_t slot, const msnv_synth_desc* d, ui
         const uint32_t q_slots = q4 + 4;          // upper bound of the quads of one read (two segments)
         o = 0;
         const size_t o_sp = take((size_t)n_seg * 4), o_sl = take((size_t)n_seg * 2), o_seq = take(n_q4), o_qual = take(n_q4 * 4),
-                     o_fix = n_mated ? take(n_q4) : 0;
+                     o_fix = n_mated ? take(fix_words(n_q4) * 4) : 0;
         uint8_t* data = (uint8_t*)take_block(ctx, w, o);
         if (!data) return fail(ctx, MSNV_E_NOMEM, "msnv_shard_synth: out of device memory (sample %u)", s);
         synth_fill_kernel<<<(unsigned)((n * q_slots + 255) / 256), 256, 0, st>>>(m, (int)s, paired, d_blocks, d_frag0, (uint32_t)nb, (uint32_t)n, q_slots,
@@ -949,7 +953,7 @@ int msnv_window_synth(msnv_ctx* ctx, uint32_t slot, const msnv_synth_desc* d, ui
         sd.mate = (const int32_t*)(meta + o_mate);
         sd.seg_pos = (const int32_t*)(data + o_sp);  sd.seg_len = (const uint16_t*)(data + o_sl);
         sd.seq2 = data + o_seq;                      sd.qual = data + o_qual;
-        sd.fix = n_mated ? data + o_fix : nullptr;
+        sd.fix = n_mated ? (uint32_t*)(data + o_fix) : nullptr;
         sd.n_reads = (uint32_t)n; sd.max_span = L + 3;
         w.n_reads += n; w.n_bases += 4ull * n_q4; w.n_segs += n_seg;
         w.sizes[s] = msnv_sample_sizes{(uint32_t)n, (uint32_t)n_mated, L + 3, 0, (uint64_t)n_seg, (uint64_t)n_q4, (uint64_t)n_aligned};
