@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <algorithm>
 #include <vector>
 
 #include "../../../include/msnv.h"
@@ -58,8 +60,23 @@ int main(int argc, char* argv[])
     if (argc - optind != 2) { print_usage(); return 1; }
     if (maxCoverage < 1) { fprintf(stderr, "qaCompute: -c must be at least 1\n"); return -1; }
 
+    // BGZF members are independent: inflate them with a few threads (metaSNV.py runs `--threads` of these processes at once,
+    // metaSNV.py:58, so the default stays small; MSNV_THREADS overrides)
+    int inflate_threads = std::min(4u, std::max(1u, std::thread::hardware_concurrency() / 4u));
+    if (const char* e = getenv("MSNV_THREADS")) inflate_threads = std::max(1, atoi(e));
+    // GPU of this process: MSNV_DEVICE, else spread the BAMs over the GPUs by a hash of the path. The CUDA context takes about
+    // half a second to come up: create it in the background while the BAM is being read.
+    const int nd = msnv_device_count();
+    int dev = 0;
+    if (const char* e = getenv("MSNV_DEVICE")) dev = atoi(e);
+    else if (nd > 1) { uint32_t hsh = 2166136261u; for (const char* c = argv[optind]; *c; ++c) hsh = (hsh ^ (unsigned char)*c) * 16777619u; dev = (int)(hsh % (uint32_t)nd); }
+    msnv_ctx* ctx = nullptr;
+    int ctx_rc = MSNV_E_CUDA;
+    std::thread ctx_thread([&]() { if (nd > 0) ctx_rc = msnv_create(dev % nd, &ctx); });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{ctx_thread};
+
     BamReader rd;
-    if (!rd.open(argv[optind], 1)) {
+    if (!rd.open(argv[optind], inflate_threads)) {
         fprintf(stderr, "qaCompute: Failed to open file %s\n", argv[optind]);
         fprintf(stderr, "NULL pointer error (%s)\n", rd.error().c_str());
         return 1;
@@ -89,8 +106,16 @@ int main(int argc, char* argv[])
     bool warned = false;
     BamRecord r;
     int rc;
-    while ((rc = rd.next(r)) > 0) {
+    // where the records of every contig start (BGZF virtual offsets): written next to the coverage file so that the SNV
+    // calling pass can seek to the contigs of its genome bin instead of inflating every BAM once per bin (metaSNV.py:157-165)
+    TidIndex tidx;
+    tidx.first.assign((size_t)n_targets, TidIndex::NONE);
+    int idx_tid = -1;
+    for (;;) {
+        const uint64_t at = rd.tell();
+        if ((rc = rd.next(r)) <= 0) break;
         const BamCore& c = r.core;
+        if (c.tid != idx_tid && c.tid >= 0 && c.tid < n_targets) { if (tidx.first[(size_t)c.tid] == TidIndex::NONE) tidx.first[(size_t)c.tid] = at; idx_tid = c.tid; }
         if (c.flag & FLAG_UNMAP) { ++unmappedReads; ++totalNumberOfReads; continue; }
         if (c.tid != currentTid) {
             if (c.tid == -1) {
@@ -144,11 +169,8 @@ int main(int argc, char* argv[])
     if (K) {
         std::vector<uint32_t> clen(K);
         for (uint32_t k = 0; k < K; ++k) clen[k] = head.lens[seen_tid[k]];
-        int dev = 0;
-        if (const char* e = getenv("MSNV_DEVICE")) dev = atoi(e);
-        const int nd = msnv_device_count();
-        msnv_ctx* ctx = nullptr;
-        if (nd <= 0 || msnv_create(dev % nd, &ctx) != MSNV_OK) {
+        ctx_thread.join();
+        if (nd <= 0 || ctx_rc != MSNV_OK) {
             fprintf(stderr, "qaCompute: no usable CUDA device (%s); this build has no CPU path\n", msnv_last_error(ctx));
             msnv_destroy(ctx);
             return 1;
@@ -163,6 +185,8 @@ int main(int argc, char* argv[])
         }
         if (getenv("MSNV_CLEAN_EXIT")) msnv_destroy(ctx);      // otherwise left to process exit (see snpcall_main.cc)
     }
+
+    if (!getenv("MSNV_NO_TIDX")) tidx.save(std::string(argv[optind + 1]) + ".tidx", rd.compressed_size());     // best effort
 
     // ---- text output, in header order (qaCompute.cpp:214-217,226-263,439,600-602)
     fprintf(outputFile, "Chromosome\tSeq_lem\tAvg_Cov\n");

@@ -12,6 +12,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
+#include <memory>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -66,6 +68,44 @@ static int pick_device(const std::string& indiv_path)
 
 struct Job { std::string ref, bed, list; };
 
+// Pinned staging memory of one window slot: the decoding threads copy their finished batches in (bump allocation),
+// the uploads (cudaMemcpyAsync from pinned memory) then run as DMA while the threads go on decoding.
+struct PinnedSlab {
+    uint8_t* base = nullptr; size_t cap = 0; std::atomic<size_t> used{0};
+    uint8_t* take(size_t bytes) {
+        const size_t need = (bytes + 255) & ~(size_t)255;
+        const size_t at = used.fetch_add(need);
+        return at + need <= cap ? base + at : nullptr;
+    }
+};
+
+// one sample's batch as the library wants it, in pinned memory when the slab had room (else the decoder's own arrays)
+static msnv_sample_reads stage_batch(const SampleReads& r, PinnedSlab& slab, bool& pinned)
+{
+    msnv_sample_reads v = r.view();
+    pinned = false;
+    if (!slab.base || v.n_reads == 0) return v;
+    uint8_t* p = slab.take(r.bytes() + 8 * 256);
+    if (!p) return v;
+    auto put = [&](const void* src, size_t bytes) { uint8_t* d = p; memcpy(d, src, bytes); p += (bytes + 255) & ~(size_t)255; return d; };
+    v.pos = (const int32_t*)put(r.pos.data(), r.pos.size() * 4);
+    v.seg_off = (const uint32_t*)put(r.seg_off.data(), r.seg_off.size() * 4);
+    v.q4_off = (const uint32_t*)put(r.q4_off.data(), r.q4_off.size() * 4);
+    v.mate = (const int32_t*)put(r.mate.data(), r.mate.size() * 4);
+    v.seg_pos = (const int32_t*)put(r.seg_pos.data(), r.seg_pos.size() * 4);
+    v.seg_len = (const uint16_t*)put(r.seg_len.data(), r.seg_len.size() * 2);
+    v.seq2 = put(r.seq2.data(), r.seq2.size());
+    v.qual = put(r.qual.data(), r.qual.size());
+    pinned = true;
+    return v;
+}
+
+static std::string dir_of(const std::string& p) { size_t k = p.rfind('/'); return k == std::string::npos ? std::string(".") : p.substr(0, k); }
+static std::string base_of(const std::string& p) { size_t k = p.rfind('/'); return k == std::string::npos ? p : p.substr(k + 1); }
+
+// Direct mode. The shard is cut into position windows (msnv_window_*): while the GPU runs window k the decoding threads
+// are already on window k+1, and every finished batch of k+1 is copied to pinned memory and queued for upload at once,
+// so inflate / parse, the host link and the kernels overlap and neither the host nor the device holds a whole shard.
 static int run_direct(const Job& job, const msnv_call_params& prm, const std::string& fasta_opt, const std::string& genes_opt,
                       FILE* indiv, const std::string& indiv_path)
 {
@@ -84,31 +124,36 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     fprintf(stderr, "Identified %d samples\n", (int)S);
     if (S == 0) return 0;
 
+    // the CUDA context takes half a second to come up: create it while the reference is being read
+    const int dev = pick_device(indiv_path);
+    msnv_ctx* ctx = nullptr;
+    int ctx_rc = MSNV_E_CUDA;
+    std::thread ctx_thread([&]() { if (dev >= 0) ctx_rc = msnv_create(dev, &ctx); });
+
     std::string err;
     BamHeader hdr;
-    { BamReader r; if (!r.open(bams[0])) { fprintf(stderr, "snpCall: %s\n", r.error().c_str()); return 1; } hdr = r.header(); }
+    uint64_t bam_bytes_total = 0;
+    { BamReader r; if (!r.open(bams[0])) { fprintf(stderr, "snpCall: %s\n", r.error().c_str()); ctx_thread.join(); return 1; } hdr = r.header(); }
+    for (const std::string& b : bams) { FILE* f = fopen(b.c_str(), "rb"); if (f) { fseek(f, 0, SEEK_END); bam_bytes_total += (uint64_t)ftell(f); fclose(f); } }
     Bed bed; bool has_bed = job.bed != "-";
-    if (has_bed && !bed.load(job.bed, err)) { fprintf(stderr, "snpCall: %s\n", err.c_str()); return 1; }
     ShardLayout layout;
-    if (!layout.build(hdr, has_bed ? &bed : nullptr, err)) { fprintf(stderr, "snpCall: %s\n", err.c_str()); return 1; }
     Fasta fa;
-    if (!fa.load(job.ref, err)) { fprintf(stderr, "snpCall: %s\n", err.c_str()); return 1; }
+    bool ok = (!has_bed || bed.load(job.bed, err)) && layout.build(hdr, has_bed ? &bed : nullptr, err) && fa.load(job.ref, err);
+    if (!ok) { fprintf(stderr, "snpCall: %s\n", err.c_str()); ctx_thread.join(); return 1; }
     std::vector<int64_t> ref_len(hdr.names.size(), -1);
     for (size_t t = 0; t < hdr.names.size(); ++t) { int fi = fa.find(hdr.names[t]); if (fi >= 0) ref_len[t] = (int64_t)fa.seqs[fi].size(); }
-    if (layout.n_positions == 0) return 0;
+    if (layout.n_positions == 0) { ctx_thread.join(); return 0; }
     std::vector<uint8_t> ref = shard_reference(layout, hdr, fa);
 
     Annotation ann;
     if (!fasta_opt.empty() && !genes_opt.empty()) {
         fprintf(stderr, "Found reference genomes and annotation file.\nLoading Genomes...\n");
-        if (!ann.load(genes_opt, fasta_opt, err)) { fprintf(stderr, "%s\n", err.c_str()); return 255; }
+        if (!ann.load(genes_opt, fasta_opt, err)) { fprintf(stderr, "%s\n", err.c_str()); ctx_thread.join(); return 255; }
         fprintf(stderr, "Genomes loaded!\n");
     }
-
     stage("reference and annotation loaded");
-    const int dev = pick_device(indiv_path);
-    msnv_ctx* ctx = nullptr;
-    if (dev < 0 || msnv_create(dev, &ctx) != MSNV_OK) {
+    ctx_thread.join();
+    if (dev < 0 || ctx_rc != MSNV_OK) {
         fprintf(stderr, "snpCall: no usable CUDA device (%s); this build has no CPU calling path\n", msnv_last_error(ctx));
         msnv_destroy(ctx);
         return 1;
@@ -118,125 +163,212 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
         fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); msnv_destroy(ctx); return 1;
     }
 
-    // ---- decode all BAMs (one thread per file at a time), upload each as soon as it is ready
+    // ---- windows: ranges of tiles sized so that one window's decoded reads are about MSNV_WINDOW_MB (default 4096)
+    const uint32_t n_tiles = layout.n_positions / MSNV_TILE;
+    uint64_t header_len = 0; for (uint32_t l : hdr.lens) header_len += l;
+    // decoded batches take ~4x the BAM bytes (1.5 B per aligned base against ~0.4); a split reads its share of the files
+    const double share = header_len ? std::min(1.0, (double)layout.n_positions / (double)header_len) : 1.0;
+    const double est_bytes = 4.0 * (double)bam_bytes_total * share + 1.0;
+    const double win_mb = getenv("MSNV_WINDOW_MB") ? atof(getenv("MSNV_WINDOW_MB")) : 4096.0;
+    uint32_t n_windows = (uint32_t)std::ceil(est_bytes / (std::max(1.0, win_mb) * 1048576.0));
+    if (getenv("MSNV_WINDOWS")) n_windows = (uint32_t)atoi(getenv("MSNV_WINDOWS"));
+    const char* dump = getenv("MSNV_DUMP_COUNTS");               // (test hook below: wants the whole shard in one window)
+    if (dump) n_windows = 1;
+    if (n_windows < 1) n_windows = 1;
+    if (n_windows > n_tiles) n_windows = n_tiles;
+    const uint32_t tiles_per_window = (n_tiles + n_windows - 1) / n_windows;
+    n_windows = (n_tiles + tiles_per_window - 1) / tiles_per_window;
+
+    // ---- decoders (one per BAM, resumable) and the thread pool
     int n_threads = (int)std::thread::hardware_concurrency();
     if (const char* e = getenv("MSNV_THREADS")) n_threads = atoi(e);
     if (n_threads < 1) n_threads = 1;
     int inflate_threads = 1;
     if ((int)S < n_threads) { inflate_threads = n_threads / (int)S; n_threads = (int)S; }
-    std::vector<SampleReads> reads(S);
-    std::vector<DecodeStats> stats(S);
-    std::vector<char> done(S, 0);
-    std::atomic<uint32_t> next(0);
-    std::atomic<bool> failed(false);
-    std::mutex mu; std::string first_err;
-    const double t_dec0 = now_s();
-    std::vector<std::thread> pool;
-    for (int t = 0; t < n_threads; ++t)
-        pool.emplace_back([&]() {
-            for (;;) {
-                uint32_t s = next.fetch_add(1);
-                if (s >= S || failed) break;
-                std::string e;
-                if (!decode_sample_for_pileup(bams[s], layout, ref_len, inflate_threads, reads[s], stats[s], e)) {
-                    std::lock_guard<std::mutex> lk(mu);
-                    if (first_err.empty()) first_err = e;
-                    failed = true;
+    // the coverage pass leaves "<project>/cov/<bam>.cov.tidx" (this repository's qaCompute): lets a split seek to its contigs
+    const std::string cov_dir = indiv_path.empty() ? std::string() : dir_of(dir_of(indiv_path)) + "/cov/";
+    std::vector<std::unique_ptr<SampleDecoder>> dec(S);
+    {
+        std::atomic<uint32_t> nx(0); std::atomic<bool> bad(false); std::mutex mu; std::string first_err;
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_threads; ++t)
+            pool.emplace_back([&]() {
+                for (;;) {
+                    const uint32_t s = nx.fetch_add(1);
+                    if (s >= S || bad) break;
+                    dec[s].reset(new SampleDecoder());
+                    std::string e;
+                    const std::string hint = cov_dir.empty() ? std::string() : cov_dir + base_of(bams[s]) + ".cov.tidx";
+                    if (!dec[s]->open(bams[s], layout, ref_len, inflate_threads, hint, e)) {
+                        std::lock_guard<std::mutex> lk(mu);
+                        if (first_err.empty()) first_err = e;
+                        bad = true;
+                    }
                 }
-                std::lock_guard<std::mutex> lk(mu);
-                done[s] = 1;
-            }
-        });
-    // the context is single-threaded: uploads happen here, in sample order
-    double t_h2d = 0; uint64_t h2d_bytes = 0;
-    int rc = 0;
-    for (uint32_t s = 0; s < S && !failed; ++s) {
-        for (;;) { { std::lock_guard<std::mutex> lk(mu); if (done[s]) break; } std::this_thread::sleep_for(std::chrono::microseconds(200)); }
-        if (failed) break;
-        const double a = now_s();
-        msnv_sample_reads v = reads[s].view();
-        if (msnv_shard_add_sample(ctx, s, &v) != MSNV_OK || msnv_shard_sync(ctx) != MSNV_OK) {
-            fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); rc = 1; failed = true; break;
-        }
-        h2d_bytes += reads[s].bytes();
-        reads[s] = SampleReads();                          // release the host copy
-        t_h2d += now_s() - a;
+            });
+        for (auto& th : pool) th.join();
+        if (bad) { fprintf(stderr, "snpCall: %s\n", first_err.c_str()); msnv_destroy(ctx); return 1; }
     }
-    for (auto& th : pool) th.join();
-    const double t_dec1 = now_s();
-    stage("BAMs decoded and uploaded");
-    if (failed) {
-        if (!first_err.empty()) fprintf(stderr, "snpCall: %s\n", first_err.c_str());
-        msnv_destroy(ctx);
-        return rc ? rc : 1;
+    PinnedSlab slab[2];
+    {
+        const double per_window = est_bytes / n_windows * 1.3 + (double)S * 4096.0 + (1 << 20);
+        const size_t cap = (size_t)std::min(per_window, 1.5 * std::max(1.0, win_mb) * 1048576.0 + (double)S * 4096.0);
+        for (int i = 0; i < (n_windows > 1 ? 2 : 1); ++i) { slab[i].base = (uint8_t*)msnv_pinned_alloc(cap); slab[i].cap = slab[i].base ? cap : 0; }
     }
-    // the reference consumes the first pileup line without calling it (call_vC.cpp:423-434)
-    int64_t first_col = -1;
-    DecodeStats tot;
-    for (uint32_t s = 0; s < S; ++s) {
-        if (stats[s].first_column >= 0 && (first_col < 0 || stats[s].first_column < first_col)) first_col = stats[s].first_column;
-        tot.records += stats[s].records; tot.accepted += stats[s].accepted; tot.dropped_by_cap += stats[s].dropped_by_cap;
-        tot.aligned_bases += stats[s].aligned_bases; tot.pairs += stats[s].pairs; tot.compressed_bytes += stats[s].compressed_bytes;
-        tot.seconds += stats[s].seconds; tot.inflate_seconds += stats[s].inflate_seconds;
-    }
-    if (first_col >= 0 && msnv_shard_mask_position(ctx, (uint32_t)first_col) != MSNV_OK) {
-        fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); msnv_destroy(ctx); return 1;
-    }
+    stage("decoders open");
 
-    msnv_hits hits;
-    const double t_run0 = now_s();
-    if (msnv_shard_run(ctx, &prm, &hits) != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); msnv_destroy(ctx); return 1; }
-    const double t_run1 = now_s();
-    stage("kernels done");
-
-    // test hook: per-sample, per-position A,C,G,T,N counts of the whole shard (msnv_shard_counts)
-    if (const char* dump = getenv("MSNV_DUMP_COUNTS")) {
-        FILE* f = fopen(dump, "wb");
-        FILE* g = fopen((std::string(dump) + ".layout").c_str(), "w");
-        if (f && g) {
-            std::vector<uint16_t> buf((size_t)layout.n_positions * 5);
-            for (uint32_t s = 0; s < S; ++s) {
-                if (msnv_shard_counts(ctx, s, 0, layout.n_positions, buf.data()) != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); break; }
-                fwrite(buf.data(), 2, buf.size(), f);
-            }
-            fprintf(g, "%u\t%u\t%lld\n", S, layout.n_positions, (long long)first_col);
-            for (const auto& c : layout.ctgs) fprintf(g, "%s\t%u\t%u\n", hdr.names[c.tid].c_str(), c.offset, c.len);
-        }
-        if (f) fclose(f);
-        if (g) fclose(g);
-    }
+    std::vector<SampleReads> batch[2];
+    batch[0].resize(S); batch[1].resize(S);
+    struct WindowJob {
+        std::vector<std::thread> pool; std::atomic<uint32_t> next{0}; std::atomic<bool> failed{false};
+        std::mutex mu; std::vector<uint32_t> ready; std::string err; uint32_t n_done = 0;
+    };
+    auto start_window = [&](WindowJob& J, uint32_t k) {
+        const uint32_t lo = k * tiles_per_window * MSNV_TILE, hi = std::min<uint64_t>((uint64_t)(k + 1) * tiles_per_window * MSNV_TILE, layout.n_positions);
+        J.next = 0; J.failed = false; J.ready.clear(); J.err.clear(); J.n_done = 0;
+        for (int t = 0; t < n_threads; ++t)
+            J.pool.emplace_back([&J, &dec, &batch, k, lo, hi, S]() {
+                for (;;) {
+                    const uint32_t s = J.next.fetch_add(1);
+                    if (s >= S) break;
+                    std::string e;
+                    bool good = true;
+                    if (!J.failed) good = dec[s]->window(lo, (uint32_t)hi, k ? &batch[(k - 1) & 1][s] : nullptr, batch[k & 1][s], e);
+                    std::lock_guard<std::mutex> lk(J.mu);
+                    if (!good) { if (J.err.empty()) J.err = e; J.failed = true; }
+                    J.ready.push_back(s);
+                }
+            });
+    };
 
     HitWriter w;
     w.pop_out = stdout; w.indiv_out = indiv; w.ann = ann.active() ? &ann : nullptr;
     std::vector<HitWriter::Contig> ctgs;
     for (const auto& c : layout.ctgs) ctgs.push_back(HitWriter::Contig{hdr.names[c.tid], c.offset, c.len});
-    w.write(hits, HitWriter::shard_locator(ctgs, ref.data()));
+    const HitWriter::Locator locate = HitWriter::shard_locator(ctgs, ref.data());
+
+    double t_add = 0, t_wait_upload = 0, t_run = 0, t_format = 0, t_decode_wait = 0;
+    uint64_t h2d_bytes = 0, pageable_bytes = 0, n_hits_total = 0, items_total = 0;
+    msnv_timings tm_sum; memset(&tm_sum, 0, sizeof tm_sum);
+    bool masked = false;
+    int64_t first_col = -1;
+    int rc = 0;
+    const double t_dec0 = now_s();
+    std::unique_ptr<WindowJob> cur(new WindowJob()), nxt;
+    start_window(*cur, 0);
+    for (uint32_t k = 0; k < n_windows && !rc; ++k) {
+        const uint32_t slot = k & 1u;
+        const uint32_t lo = k * tiles_per_window * MSNV_TILE, hi = (uint32_t)std::min<uint64_t>((uint64_t)(k + 1) * tiles_per_window * MSNV_TILE, layout.n_positions);
+        if (n_windows > 1 && msnv_window_begin(ctx, slot, lo, hi) != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); rc = 1; }
+        slab[slot].used = 0;
+        // drain: queue the upload of every batch of this window as soon as its thread is through
+        uint32_t taken = 0;
+        while (taken < S && !rc) {
+            std::vector<uint32_t> got;
+            { std::lock_guard<std::mutex> lk(cur->mu); got.assign(cur->ready.begin() + taken, cur->ready.end()); }
+            if (got.empty()) { const double a = now_s(); std::this_thread::sleep_for(std::chrono::microseconds(100)); t_decode_wait += now_s() - a; continue; }
+            taken += (uint32_t)got.size();
+            if (cur->failed) continue;
+            for (uint32_t s : got) {
+                const double a = now_s();
+                bool pinned = false;
+                const msnv_sample_reads v = stage_batch(batch[slot][s], slab[slot], pinned);
+                const int arc = n_windows > 1 ? msnv_window_add_sample(ctx, slot, s, &v) : msnv_shard_add_sample(ctx, s, &v);
+                if (arc != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); rc = 1; break; }
+                (pinned ? h2d_bytes : pageable_bytes) += batch[slot][s].bytes();
+                t_add += now_s() - a;
+            }
+        }
+        for (auto& th : cur->pool) th.join();
+        cur->pool.clear();
+        if (cur->failed) { fprintf(stderr, "snpCall: %s\n", cur->err.c_str()); rc = 1; }
+        if (rc) break;
+        // the next window decodes while this one runs
+        if (k + 1 < n_windows) { nxt.reset(new WindowJob()); start_window(*nxt, k + 1); }
+        // the reference consumes the first pileup line without calling it (call_vC.cpp:423-434): the smallest first column over the samples
+        if (!masked) {
+            for (uint32_t s = 0; s < S; ++s) { const int64_t c = dec[s]->stats().first_column; if (c >= 0 && (first_col < 0 || c < first_col)) first_col = c; }
+            if (first_col >= 0) {
+                if (msnv_shard_mask_position(ctx, (uint32_t)first_col) != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); rc = 1; break; }
+                masked = true;
+            }
+        }
+        double a = now_s();
+        if (msnv_shard_sync(ctx) != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); rc = 1; break; }     // uploads that the decoding did not hide
+        t_wait_upload += now_s() - a;
+        a = now_s();
+        msnv_hits hits;
+        const int rrc = n_windows > 1 ? msnv_window_run(ctx, slot, &prm, &hits) : msnv_shard_run(ctx, &prm, &hits);
+        if (rrc != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); rc = 1; break; }
+        t_run += now_s() - a;
+        msnv_timings tm; msnv_get_timings(ctx, &tm);
+        tm_sum.ms_index += tm.ms_index; tm_sum.ms_pileup += tm.ms_pileup; tm_sum.ms_call += tm.ms_call; tm_sum.ms_compact += tm.ms_compact;
+        tm_sum.ms_gather += tm.ms_gather; tm_sum.kernel_launches += tm.kernel_launches; items_total += tm.n_items;
+
+        // test hook: per-sample, per-position A,C,G,T,N counts of the whole shard (msnv_shard_counts)
+        if (dump) {
+            FILE* f = fopen(dump, "wb");
+            FILE* g = fopen((std::string(dump) + ".layout").c_str(), "w");
+            if (f && g) {
+                std::vector<uint16_t> buf((size_t)layout.n_positions * 5);
+                for (uint32_t s = 0; s < S; ++s) {
+                    if (msnv_shard_counts(ctx, s, 0, layout.n_positions, buf.data()) != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); break; }
+                    fwrite(buf.data(), 2, buf.size(), f);
+                }
+                fprintf(g, "%u\t%u\t%lld\n", S, layout.n_positions, (long long)first_col);
+                for (const auto& c : layout.ctgs) fprintf(g, "%s\t%u\t%u\n", hdr.names[c.tid].c_str(), c.offset, c.len);
+            }
+            if (f) fclose(f);
+            if (g) fclose(g);
+        }
+        a = now_s();
+        w.write(hits, locate);
+        n_hits_total += hits.n_hits;
+        t_format += now_s() - a;
+        if (k + 1 < n_windows) cur = std::move(nxt);
+    }
+    if (nxt) { for (auto& th : nxt->pool) th.join(); }
+    if (cur) { for (auto& th : cur->pool) th.join(); }
+    const double t_dec1 = now_s();
+    if (rc) { msnv_destroy(ctx); return rc; }
     fflush(stdout);
     const double t_end = now_s();
+    stage("kernels done, output written");
 
-    msnv_timings tm; msnv_get_timings(ctx, &tm);
+    DecodeStats tot;
+    uint32_t n_indexed = 0;
+    for (uint32_t s = 0; s < S; ++s) {
+        const DecodeStats& d = dec[s]->stats();
+        tot.records += d.records; tot.accepted += d.accepted; tot.dropped_by_cap += d.dropped_by_cap;
+        tot.aligned_bases += d.aligned_bases; tot.pairs += d.pairs; tot.compressed_bytes += d.compressed_bytes;
+        tot.seconds += d.seconds; tot.inflate_seconds += d.inflate_seconds;
+        n_indexed += dec[s]->used_index() ? 1u : 0u;
+    }
     if (const char* pj = getenv("MSNV_PERF_JSON")) {
         FILE* f = fopen(pj, "a");
         if (f) {
             fprintf(f,
-                    "{\"tool\": \"snpCall\", \"device\": %d, \"samples\": %u, \"positions\": %u, \"records\": %llu, \"reads\": %llu, "
-                    "\"aligned_bases\": %llu, \"pairs\": %llu, \"dropped_by_cap\": %llu, \"bam_bytes\": %llu, \"h2d_bytes\": %llu, \"hits\": %u, "
-                    "\"decode_threads\": %d, \"decode_wall_s\": %.6f, \"decode_cpu_s\": %.6f, \"inflate_cpu_s\": %.6f, \"h2d_s\": %.6f, "
+                    "{\"tool\": \"snpCall\", \"device\": %d, \"samples\": %u, \"positions\": %u, \"windows\": %u, \"bams_read_through_index\": %u, "
+                    "\"records\": %llu, \"reads\": %llu, \"aligned_bases\": %llu, \"pairs\": %llu, \"dropped_by_cap\": %llu, "
+                    "\"bam_bytes\": %llu, \"bam_bytes_inflated\": %llu, \"h2d_bytes\": %llu, \"h2d_pageable_bytes\": %llu, \"hits\": %llu, "
+                    "\"decode_threads\": %d, \"decode_wall_s\": %.6f, \"decode_cpu_s\": %.6f, \"inflate_cpu_s\": %.6f, "
+                    "\"h2d_s\": %.6f, \"h2d_not_hidden_s\": %.6f, \"waiting_for_decode_s\": %.6f, "
                     "\"gpu_run_wall_s\": %.6f, \"format_s\": %.6f, \"total_s\": %.6f, "
                     "\"ms_index\": %.4f, \"ms_pileup\": %.4f, \"ms_call\": %.4f, \"ms_compact\": %.4f, \"ms_gather\": %.4f, "
                     "\"items\": %llu, \"launches\": %u}\n",
-                    dev, S, layout.n_positions, (unsigned long long)tot.records, (unsigned long long)tot.accepted,
+                    dev, S, layout.n_positions, n_windows, n_indexed, (unsigned long long)tot.records, (unsigned long long)tot.accepted,
                     (unsigned long long)tot.aligned_bases, (unsigned long long)tot.pairs, (unsigned long long)tot.dropped_by_cap,
-                    (unsigned long long)tot.compressed_bytes, (unsigned long long)h2d_bytes, hits.n_hits, n_threads * inflate_threads,
-                    t_dec1 - t_dec0, tot.seconds, tot.inflate_seconds, t_h2d, t_run1 - t_run0, t_end - t_run1, t_end - t_start, tm.ms_index,
-                    tm.ms_pileup, tm.ms_call, tm.ms_compact, tm.ms_gather, (unsigned long long)tm.n_items, tm.kernel_launches);
+                    (unsigned long long)bam_bytes_total, (unsigned long long)tot.compressed_bytes, (unsigned long long)h2d_bytes,
+                    (unsigned long long)pageable_bytes, (unsigned long long)n_hits_total, n_threads * inflate_threads,
+                    t_dec1 - t_dec0, tot.seconds, tot.inflate_seconds, t_add, t_wait_upload, t_decode_wait, t_run, t_format, t_end - t_start,
+                    tm_sum.ms_index, tm_sum.ms_pileup, tm_sum.ms_call, tm_sum.ms_compact, tm_sum.ms_gather, (unsigned long long)items_total,
+                    tm_sum.kernel_launches);
             fclose(f);
         }
     }
-    stage("output written");
     // the process is about to exit: the driver reclaims the device; freeing every block one by one
     // (each cudaFree is a device-wide synchronisation) would only add seconds
-    if (getenv("MSNV_CLEAN_EXIT")) msnv_destroy(ctx);
+    if (getenv("MSNV_CLEAN_EXIT")) { for (auto& sl : slab) msnv_pinned_free(sl.base); msnv_destroy(ctx); }
     return 0;
 }
 

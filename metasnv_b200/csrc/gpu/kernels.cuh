@@ -414,21 +414,17 @@ __global__ void expect_kernel(const uint8_t* __restrict__ ref, uint32_t n, uint8
     expect[p] = (uint8_t)e;
 }
 
-// The same letters in the geometry of the staged reads (2 bits per position, a byte per quad), four
-// copies per tile: byte i of copy c is the quad i + c of the tile (0 behind the tile's end), so the
-// expected letters of four consecutive quads starting at ANY quad j are one aligned word -
-// copy j & 3, word j >> 2. That is what lets a read-sized XOR run word by word whatever the
-// read's alignment in the staging buffer.
-constexpr int EXP_COPY_BYTES = TILE / 4 + 16;
-constexpr int EXP_BYTES = 4 * EXP_COPY_BYTES;
+// The same letters in the geometry of the staged reads: 2 bits per position, a byte per quad, EXP_BYTES per tile
+// (the tile's 256 quads and 16 bytes of zeros). A staged read is cut along the tile's 32-position words, so the
+// expected letters of a word are one aligned 8-byte load.
+constexpr int EXP_BYTES = TILE / 4 + 16;
 static_assert(EXP_BYTES % 16 == 0, "one bulk copy per tile");
 
 __global__ void expect2_kernel(const uint8_t* __restrict__ expect /* of the first tile */, uint32_t n_tiles, uint8_t* __restrict__ expect2 /* [n_tiles][EXP_BYTES] */)
 {
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (uint64_t)n_tiles * EXP_BYTES) return;
-    const uint32_t t = (uint32_t)(g / EXP_BYTES), o = (uint32_t)(g % EXP_BYTES), c = o / EXP_COPY_BYTES, i = o % EXP_COPY_BYTES;
-    const uint32_t q = i + c;
+    const uint32_t t = (uint32_t)(g / EXP_BYTES), q = (uint32_t)(g % EXP_BYTES);
     uint32_t v = 0;
     if (q < (uint32_t)(TILE / 4)) {
         const uint32_t w = *reinterpret_cast<const uint32_t*>(expect + (size_t)t * TILE + 4u * q);
@@ -486,38 +482,44 @@ __global__ void expect2_kernel(const uint8_t* __restrict__ expect /* of the firs
 // sample's quad index rounded down to 16, so a stage holds up to 15 quads in front of the chunk.
 // ------------------------------------------------------------------------------------------------
 // consumer threads per CTA: a template parameter of the kernel (128 or 256; the CTA has one more warp, the producer)
-constexpr int PL_STAGES = 2;
+constexpr int PL_STAGES_MAX = 4;        // stages of the ring: PileupShape::n_stages (2 .. PL_STAGES_MAX)
 constexpr uint32_t CHUNK_Q4_MIN = MSNV_MAX_READ_BASES / 4 + 2 * MSNV_MAX_READ_SEGMENTS;   // a single read always fits
 constexpr uint32_t CHUNK_SEGS_MIN = MSNV_MAX_READ_SEGMENTS;
 constexpr uint32_t CHUNK_FIRST = 1u, CHUNK_LAST = 2u, CHUNK_WIDE = 4u, CHUNK_STOP = 8u, CHUNK_FIX = 16u /* the sample has mate verdicts */;
-constexpr uint32_t ABL_EXTRACT = 1u, ABL_PREP_XOR = 2u, ABL_DEPTH = 4u, ABL_STORE = 8u, ABL_EXCEPT = 16u;   // PileupShape::ablate (measurement only)
+constexpr uint32_t ABL_EXTRACT = 1u, ABL_DEPTH = 4u, ABL_STORE = 8u, ABL_EXCEPT = 16u, ABL_READS = 32u, ABL_PREFETCH = 64u;   // PileupShape::ablate (measurement only)
 
 // limits of one staged chunk, chosen per launch from the shape of the shard
-struct PileupShape { uint32_t max_reads, max_segs, chunk_q4, has_fix /* some sample carries mate verdicts */, wait_hint_ns, ablate /* measurement only: phases to skip */; };
+struct PileupShape { uint32_t max_reads, max_segs, chunk_q4, has_fix /* some sample carries mate verdicts */, wait_hint_ns, ablate /* measurement only: phases to skip */, n_stages; };
 
 struct ChunkHdr { uint32_t m, nq4, q4_0, sg_0, nseg, c0, item, sample, tile, flags, spanq /* quads a read of the sample can span */, pad[5]; };
 static_assert(sizeof(ChunkHdr) == 64, "header is one 64-byte block");
 
 struct PileupSmem {
-    uint32_t bar, cnt, pbits, segtab, jr, wend, list, misc, stage0, stage_bytes;        // byte offsets
+    uint32_t bar, cnt, fill, bucket, segtab, list, misc, stage0, stage_bytes;           // byte offsets
     uint32_t o_hdr, o_q4, o_sg, o_sp, o_sl, o_exp, o_seq, o_fix, o_qual;                // within a stage
-    uint32_t total;
+    uint32_t bucket_words, list_cap, total;
 };
 
 __host__ __device__ constexpr uint32_t up_to(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
+// buffer quad g of a chunk is stored PADQ quads into the stage's per-quad arrays: a piece that starts inside a word of the
+// tile is loaded from the word's first quad, up to seven quads in front of the segment
+constexpr uint32_t PADQ = 16;
+
 __host__ __device__ inline PileupSmem pileup_smem_layout(const PileupShape sh)
 {
     PileupSmem L{};
-    const uint32_t cq = up_to(sh.chunk_q4, 16) + 16;          // staged quads: the chunk's + up to 15 in front of it
+    const uint32_t cq = up_to(sh.chunk_q4, 16) + 16 + PADQ;   // staged quads: the chunk's, up to 15 in front of it, the pad
     uint32_t o = 0;
     L.bar = o;    o += 128;
     L.cnt = o;    o += N_PLANES * TILE;
-    L.pbits = o;  o += up_to((cq / 8 + 3) * 4, 16);            // one word in front (a segment may start inside a word), one behind
+    L.fill = o;   o += 2 * 32 * 4;                             // entries per word of the tile, for this chunk and the next
+    // pass words of the chunk's pieces, bucketed by word of the tile (a piece = what a segment has on one word)
+    L.bucket_words = up_to((sh.chunk_q4 / 8 + 2 * sh.max_reads) * 9 / 8, 32);
+    L.bucket = o; o += L.bucket_words * 4;
     L.segtab = o; o += up_to(sh.max_segs, 2) * 8;
-    L.jr = o;     o += up_to((sh.max_reads + 1) * 2, 16);
-    L.wend = o;   o += 80;
-    L.list = o;   o += up_to((cq / 8 + 1) * 2, 16);
+    L.list_cap = 160;
+    L.list = o;   o += L.list_cap * 8;
     L.misc = o;   o += 16;
     L.stage0 = up_to(o, 128);
     uint32_t s = 0;
@@ -528,11 +530,11 @@ __host__ __device__ inline PileupSmem pileup_smem_layout(const PileupShape sh)
     L.o_sp = s;   s += (up_to(sh.max_segs, 4) + 8) * 4;
     L.o_sl = s;   s += (up_to(sh.max_segs, 8) + 16) * 2;
     L.o_exp = s;  s += EXP_BYTES;
-    L.o_seq = s;  s += cq + 16;
-    L.o_fix = s;  s += sh.has_fix ? cq + 16 : 0;
+    L.o_seq = s;  s += cq + 32;                                // (a piece is read as three words)
+    L.o_fix = s;  s += sh.has_fix ? cq + 32 : 0;
     L.o_qual = s; s += 4 * cq + 64;
     L.stage_bytes = up_to(s, 128);
-    L.total = L.stage0 + PL_STAGES * L.stage_bytes;
+    L.total = L.stage0 + sh.n_stages * L.stage_bytes;
     return L;
 }
 
@@ -608,8 +610,8 @@ __device__ __forceinline__ void pileup_issue_chunk(uint8_t* smem, const PileupSm
                                                    uint32_t m, uint32_t q4_0, uint32_t nq4, uint32_t sg_0, uint32_t nseg, uint32_t flags)
 {
     uint64_t* full = (uint64_t*)(smem + L.bar);
-    uint64_t* empty = full + PL_STAGES;
-    const uint32_t s = chunk_no % PL_STAGES, ph = (chunk_no / PL_STAGES) & 1u;
+    uint64_t* empty = full + PL_STAGES_MAX;
+    const uint32_t s = chunk_no % sh.n_stages, ph = (chunk_no / sh.n_stages) & 1u;
     mbar_wait(empty + s, ph ^ 1u, sh.wait_hint_ns);
     if ((threadIdx.x & 31) == issuer) {
         uint8_t* stage = smem + L.stage0 + s * L.stage_bytes;
@@ -618,7 +620,7 @@ __device__ __forceinline__ void pileup_issue_chunk(uint8_t* smem, const PileupSm
         h->item = item; h->sample = sample; h->tile = tile; h->flags = flags | (src.fix ? CHUNK_FIX : 0u);
         h->spanq = (src.max_span + 3u) / 4u + 1u;
         const ChunkCopies c = chunk_copies(src, c0, m, q4_0, nq4, sg_0, nseg);
-        const uint32_t dst[7] = {L.o_q4, L.o_sg, L.o_fix, L.o_sp, L.o_sl, L.o_seq, L.o_qual};
+        const uint32_t dst[7] = {L.o_q4, L.o_sg, L.o_fix + PADQ, L.o_sp, L.o_sl, L.o_seq + PADQ, L.o_qual + 4u * PADQ};
         uint32_t total = (uint32_t)EXP_BYTES;
         #pragma unroll
         for (int i = 0; i < 7; ++i) total += c.bytes[i];
@@ -653,12 +655,12 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
             q_lo = __ldg(src.q4_off + it.z); q_hi = __ldg(src.q4_off + it.w);
             g_lo = __ldg(src.seg_off + it.z); g_hi = __ldg(src.seg_off + it.w);
             whole = it.w - it.z <= sh.max_reads && q_hi - q_lo <= sh.chunk_q4 && g_hi - g_lo <= sh.max_segs;
-            if (whole && lane < PREFETCH_AHEAD) prefetch_chunk(src, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo, g_hi - g_lo);
+            if (whole && lane < PREFETCH_AHEAD && !(sh.ablate & ABL_PREFETCH)) prefetch_chunk(src, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo, g_hi - g_lo);
         }
         for (uint32_t k = 0; k < 32u; ++k) {
             const uint64_t idx = base + (uint64_t)k * G;
             if (idx >= n_items) break;
-            if (lane == k + PREFETCH_AHEAD && whole) prefetch_chunk(src, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo, g_hi - g_lo);
+            if (lane == k + PREFETCH_AHEAD && whole && !(sh.ablate & ABL_PREFETCH)) prefetch_chunk(src, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo, g_hi - g_lo);
             if (__shfl_sync(0xffffffffu, (int)whole, k)) {                   // the lane that owns the item issues it from its own registers
                 pileup_issue_chunk(smem, L, sh, chunk_no, k, src, expect2, (uint32_t)mine, it.x, it.y, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo,
                                    g_hi - g_lo, CHUNK_FIRST | CHUNK_LAST | (item_is_wide(it.z, it.w) ? CHUNK_WIDE : 0u));
@@ -724,8 +726,8 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
     }
     // ---- no more items: tell the consumers
     uint64_t* full = (uint64_t*)(smem + L.bar);
-    uint64_t* empty = full + PL_STAGES;
-    const uint32_t s = chunk_no % PL_STAGES, ph = (chunk_no / PL_STAGES) & 1u;
+    uint64_t* empty = full + PL_STAGES_MAX;
+    const uint32_t s = chunk_no % sh.n_stages, ph = (chunk_no / sh.n_stages) & 1u;
     mbar_wait(empty + s, ph ^ 1u, sh.wait_hint_ns);
     if (lane == 0) {
         ((ChunkHdr*)(smem + L.stage0 + s * L.stage_bytes + L.o_hdr))->flags = CHUNK_STOP;
@@ -769,25 +771,40 @@ __device__ __forceinline__ uint32_t csa_quad_lanes(const uint32_t (&c)[8], uint3
     return v;
 }
 
-// CONSUMERS: consumer threads (128: four CTAs per SM at the standard shape; 256: two larger ones for deep shards).
+// shifts that give 0 for counts of 32 and more (plain C++ shifts are undefined there)
+__device__ __forceinline__ uint32_t shl_c(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
+// byte lanes [lo, hi) of a word, 0 <= lo, hi <= 4
+__device__ __forceinline__ uint32_t byte_range(uint32_t lo, uint32_t hi) { return shl_c(0xffffffffu, 8u * lo) & ~shl_c(0xffffffffu, 8u * hi); }
+// bit 7 of the four byte lanes of a word -> a nibble in the top four bits of the product; quads are chained with funnel
+// shifts (the quad chained last ends up in bits 0..3)
+__device__ __forceinline__ uint32_t chain_nibble(uint32_t lanes7, uint32_t acc) { return __funnelshift_l(lanes7 * 0x00204081u, acc, 4); }
+
+// A PIECE is what one staged segment has on one 32-position word of the tile: quads [i_lo, i_hi) of the word. It is loaded
+// as the eight staged quads that line up with the word (the segment is stored position-aligned, so that is a plain offset);
+// quads outside the segment belong to a neighbour in the buffer and are masked.
+struct PieceOut { uint32_t pw /* counted bases, bit 4 quad + lane */, xnz /* != 0: some base of the piece differs from the expected letter */, nf /* != 0: a base is not A/C/G/T */; };
+
+// CONSUMERS: consumer threads (128: up to four CTAs per SM; 256: two larger ones for deep shards).
 // HAS_WIDE: the shard has items with more than 255 reads (deep coverage); without them the 16-bit accumulators and
 // their registers do not exist.
 template <int CONSUMERS, bool HAS_WIDE>
-__global__ void __launch_bounds__(CONSUMERS + 32, CONSUMERS == 128 ? 4 : 2)
+__global__ void __launch_bounds__(CONSUMERS + 32, CONSUMERS == 128 ? 3 : 2)
 pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items, const PileupShape sh,
               const uint8_t* __restrict__ expect2, uint8_t* __restrict__ tiles /*[n_items][SLOT_BYTES]*/, int* __restrict__ err_flag)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const PileupSmem L = pileup_smem_layout(sh);
     uint64_t* full = (uint64_t*)(smem + L.bar);
-    uint64_t* empty = full + PL_STAGES;
+    uint64_t* empty = full + PL_STAGES_MAX;
     uint32_t* s_cnt = (uint32_t*)(smem + L.cnt);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < PL_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        // a stage is full when its copies have landed (one arrival + bytes), empty when every consumer warp is through with it
+        for (int s = 0; s < PL_STAGES_MAX; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ((uint32_t*)(smem + L.misc))[0] = 0; ((uint32_t*)(smem + L.misc))[1] = 0;
     }
-    for (uint32_t k = threadIdx.x; k < (uint32_t)(N_PLANES * TILE_QUADS); k += CONSUMERS + 32) s_cnt[k] = 0;
+    for (uint32_t k = threadIdx.x; k < (uint32_t)(N_PLANES * TILE_QUADS) + 64u; k += CONSUMERS + 32) s_cnt[k] = 0;     // the planes and the fill counters behind them
     __syncthreads();
 
     if (threadIdx.x >= CONSUMERS) {
@@ -798,12 +815,12 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     // ------------------------------------------------------------------------------------ consumers
     constexpr uint32_t NWARPS = CONSUMERS / 32;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    uint32_t* s_pb = (uint32_t*)(smem + L.pbits);                   // pass word of buffer quads 8u .. 8u+7 in s_pb[u + 1]
+    uint32_t* s_fill = (uint32_t*)(smem + L.fill);                 // [chunk & 1][32]: pieces per word of the tile
+    uint32_t* s_bucket = (uint32_t*)(smem + L.bucket);             // pass words of the pieces, `cap` slots per word of the chunk's range
     int2* s_seg = (int2*)(smem + L.segtab);                        // per staged segment: tile-relative quad of its first quad | first buffer quad, quads << 16
-    int16_t* s_jr = (int16_t*)(smem + L.jr);                       // per staged read: tile-relative quad of its first segment
-    uint16_t* s_wend = (uint16_t*)(smem + L.wend);                 // per word of the tile: staged reads that start in or before it
-    uint16_t* s_list = (uint16_t*)(smem + L.list);                 // groups with exceptions
-    uint32_t* s_misc = (uint32_t*)(smem + L.misc);                 // [0] length of the list
+    uint2* s_list = (uint2*)(smem + L.list);                       // pieces with exceptions: segment | word << 16 | non-ACGT << 31, pass word
+    uint32_t* s_misc = (uint32_t*)(smem + L.misc);                 // [chunk & 1] length of the list
+    const uint32_t a_c = smem_u32(s_cnt);
     // wide items: per plane and owned quad (QPT * tid + k), 16-bit lanes: [0] = positions 0 and 2, [1] = positions 1 and 3
     constexpr int QPT = TILE_QUADS / CONSUMERS;                 // quads a thread folds (2 or 1)
     uint32_t acc[HAS_WIDE ? N_PLANES : 1][QPT][2];
@@ -813,7 +830,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
         for (int k = 0; k < QPT; ++k) acc[c][k][0] = acc[c][k][1] = 0;
 
     for (uint32_t chunk_no = 0;; ++chunk_no) {
-        const uint32_t st = chunk_no % PL_STAGES, ph = (chunk_no / PL_STAGES) & 1u;
+        const uint32_t st = chunk_no % sh.n_stages, ph = (chunk_no / sh.n_stages) & 1u;
         uint8_t* stage = smem + L.stage0 + st * L.stage_bytes;
         mbar_wait(full + st, ph, sh.wait_hint_ns);
         const ChunkHdr* h = (const ChunkHdr*)(stage + L.o_hdr);
@@ -827,236 +844,232 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
         const uint32_t* s_sgo = (const uint32_t*)(stage + L.o_sg) + dm;
         const int32_t* s_sp = (const int32_t*)(stage + L.o_sp) + (sg_0 & 3u);   // s_sp[k] = seg_pos[sg_0 + k], k < nseg
         const uint16_t* s_sl = (const uint16_t*)(stage + L.o_sl) + (sg_0 & 7u);
-        uint8_t* s_x = stage + L.o_seq;                                         // bases of buffer quad B in byte B (prep: XOR expected letters)
-        const uint8_t* s_e = stage + L.o_exp;                                   // expected letters, four shifted copies
+        uint8_t* s_x = stage + L.o_seq + PADQ;                                  // bases of buffer quad B in byte B
+        const uint8_t* s_e = stage + L.o_exp;                                   // expected letters of tile quad j in byte j
+        const uint32_t* s_qw = (const uint32_t*)(stage + L.o_qual) + PADQ;      // qualities of buffer quad B in word B
+        const uint2* s_fx = (const uint2*)(stage + L.o_fix);                    // mate verdicts of buffer quads 8 G - PADQ .. + 7 in s_fx[G]
         const bool has_fix = (flags & CHUNK_FIX) != 0;
-        const uint32_t nbq = dq + nq4, ngroups = (nbq + 7u) >> 3;               // buffer quad g is quad (q4_0 - dq) + g of the sample
+        const uint32_t nbq = dq + nq4;                                          // buffer quad g is quad (q4_0 - dq) + g of the sample
         const uint32_t qbase = q4_0 - dq;                                       // s_q4[t] - qbase = first buffer quad of read t
+        uint32_t* list_n = s_misc + (chunk_no & 1u);
+        uint32_t* fill = s_fill + 32u * (chunk_no & 1u);
+        // words of the tile this chunk can touch (reads are in coordinate order) and the bucket slots each gets
+        int32_t w_lo = 0, w_hi = -1;
+        if (m) {
+            const uint32_t kl = s_sgo[m - 1] - sg_0;
+            const int32_t j_a = ((s_sp[0] & ~3) - p0) >> 2, j_b = ((s_sp[kl < nseg ? kl : 0u] & ~3) - p0) >> 2;
+            w_lo = j_a >> 3; w_lo = w_lo < 0 ? 0 : (w_lo > 31 ? 31 : w_lo);
+            w_hi = (j_b + spanq) >> 3; w_hi = w_hi > 31 ? 31 : (w_hi < w_lo ? w_lo : w_hi);
+        }
+        const uint32_t nw = (uint32_t)(w_hi - w_lo + 1);
+        const uint32_t cap = m ? L.bucket_words / nw : 0u;
 
-        // ---- 1. prep: one thread per read
-        for (uint32_t t = tid; t < m; t += CONSUMERS) {
+        // one piece: pass word, does-any-base-differ, is-any-base-not-ACGT
+        auto piece = [&](int32_t jw, uint32_t B, uint32_t nq, int32_t w, bool exact) -> PieceOut {
+            const int32_t q0w = 8 * w;
+            const int32_t d = (int32_t)B + q0w - jw;                                // buffer quad that lines up with the word's first quad
+            const uint32_t* qp = s_qw + d;
+            uint32_t q[8];
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) q[i] = qp[i];
+            uint32_t lo = 0, hi = 0, orq = 0;
+            #pragma unroll
+            for (int i = 3; i >= 0; --i) {                                          // two independent chains of four quads
+                const uint32_t va = (q[i] & 0x7f7f7f7fu) + 0x73737373u, vb = (q[i + 4] & 0x7f7f7f7fu) + 0x73737373u;   // bit 7 of a lane: quality >= 13
+                uint32_t oa, ob;                                                    // ... and the base is A/C/G/T
+                asm("lop3.b32 %0, %1, %2, 0x80808080, 0x20;" : "=r"(oa) : "r"(va), "r"(q[i]));        // v & ~q & 0x80808080
+                asm("lop3.b32 %0, %1, %2, 0x80808080, 0x20;" : "=r"(ob) : "r"(vb), "r"(q[i + 4]));
+                lo = chain_nibble(oa, lo); hi = chain_nibble(ob, hi);
+                orq |= q[i] | q[i + 4];
+            }
+            uint32_t pw = __byte_perm(lo, hi, 0x5410);
+            int32_t i_lo = jw - q0w; if (i_lo < 0) i_lo = 0;
+            int32_t i_hi = jw + (int32_t)nq - q0w; if (i_hi > 8) i_hi = 8;
+            const uint32_t msk = (0xffffffffu << (4 * i_lo)) & (0xffffffffu >> (32 - 4 * i_hi));      // (a piece has at least one quad)
+            PieceOut o;
+            o.nf = orq & 0x80808080u;
+            const uint32_t dp = (uint32_t)(d + (int32_t)PADQ);                      // the same quad in the stage's padded arrays
+            if (has_fix) {
+                // mate verdicts: where the overlap rule spoke (first word) its verdict (second word) replaces the quality test
+                const uint32_t G = dp >> 3, fs = 4u * (dp & 7u);
+                const uint2 f0 = s_fx[G], f1 = s_fx[G + 1u];
+                const uint32_t ovr = __funnelshift_r(f0.x, f1.x, fs);
+                uint32_t val = __funnelshift_r(f0.y, f1.y, fs);
+                if (o.nf) {                                                         // a flagged base never counts in D, whatever the verdict
+                    uint32_t fl = 0;
+                    #pragma unroll
+                    for (int i = 7; i >= 0; --i) fl = chain_nibble(q[i] & 0x80808080u, fl);
+                    val &= ~fl;
+                }
+                pw = (pw & ~ovr) | (val & ovr);
+            }
+            o.pw = pw & msk;
+            // bases of the eight quads XOR the word's expected letters
+            const uint32_t* xw = reinterpret_cast<const uint32_t*>(stage + L.o_seq + (dp & ~3u));
+            const uint32_t w0 = xw[0], w1 = xw[1], w2 = xw[2], sft = 8u * (dp & 3u);
+            const uint2 e = *reinterpret_cast<const uint2*>(s_e + q0w);
+            uint32_t x0 = __funnelshift_r(w0, w1, sft) ^ e.x, x1 = __funnelshift_r(w1, w2, sft) ^ e.y;
+            if (exact || i_lo != 0 || i_hi != 8) {                                  // first / last piece of a segment: drop the neighbours' quads
+                const uint32_t a0 = (uint32_t)min(i_lo, 4), a1 = (uint32_t)min(i_hi, 4);
+                x0 &= byte_range(a0, a1);
+                x1 &= byte_range((uint32_t)i_lo - a0, (uint32_t)i_hi - a1);
+            }
+            o.xnz = x0 | x1;
+            if (exact) { o.xnz = x0; o.nf = x1; }                                   // (the exception pass wants the two words themselves)
+            return o;
+        };
+        // a pass word that found no slot in its word's bucket (very uneven depth, or a read longer than the sample's span says)
+        auto spill = [&](int32_t w, uint32_t pw) {
+            for (uint32_t i = 0; i < 8u; ++i) { const uint32_t nb = (pw >> (4u * i)) & 15u; if (nb) red_shared_add(a_c + 4u * (8u * (uint32_t)w + i), nibble_to_lanes(nb)); }
+        };
+        // the counted bases of a piece that differ from the expected letter -> letter planes; its counted non-ACGT bases -> N plane
+        auto exceptions = [&](uint32_t k, int32_t w, uint32_t pw, bool any_n) {
+            const int2 sg = s_seg[k];
+            const int32_t jw = sg.x;
+            const uint32_t B = (uint32_t)sg.y & 0xffffu, nq = (uint32_t)sg.y >> 16;
+            const PieceOut x = piece(jw, B, nq, w, true);                          // .xnz / .nf: the two XOR words, neighbours masked
+            uint32_t nz[2];
+            #pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {                                        // lanes that differ, a bit per position: even bits of (x | x >> 1), compressed
+                uint32_t z = hh ? x.nf : x.xnz;
+                z = (z | (z >> 1)) & 0x55555555u;
+                z = (z | (z >> 1)) & 0x33333333u;
+                z = (z | (z >> 2)) & 0x0f0f0f0fu;
+                z = (z | (z >> 4)) & 0x00ff00ffu;
+                nz[hh] = (z | (z >> 8)) & 0xffffu;
+            }
+            uint32_t mm = (nz[0] | (nz[1] << 16)) & pw;
+            const uint32_t q0w = 8u * (uint32_t)w;
+            while (mm) {
+                const uint32_t b = (uint32_t)__ffs((int)mm) - 1u; mm &= mm - 1u;
+                const uint32_t i = b >> 2, l = b & 3u;
+                const uint32_t xb = ((i < 4u ? x.xnz : x.nf) >> (8u * (i & 3u))) & 0xffu;
+                const uint32_t letter = ((xb ^ (uint32_t)s_e[q0w + i]) >> (2u * l)) & 3u;          // the base itself again
+                red_shared_add(a_c + 4u * (q0w + i) + (PLANE_A + letter) * (uint32_t)TILE, 1u << (8u * l));
+            }
+            if (any_n) {
+                const int32_t d = (int32_t)B + 8 * w - jw;
+                int32_t i_lo = jw - 8 * w; if (i_lo < 0) i_lo = 0;
+                int32_t i_hi = jw + (int32_t)nq - 8 * w; if (i_hi > 8) i_hi = 8;
+                uint32_t qp = 0, fl = 0;
+                #pragma unroll
+                for (int i = 7; i >= 0; --i) {
+                    const uint32_t qk = s_qw[d + i];
+                    fl = chain_nibble(qk & 0x80808080u, fl);
+                    qp = chain_nibble(((qk & 0x7f7f7f7fu) + 0x73737373u) & 0x80808080u, qp);
+                }
+                if (has_fix) {
+                    const uint32_t dp = (uint32_t)(d + (int32_t)PADQ), G = dp >> 3, fs = 4u * (dp & 7u);
+                    const uint2 f0 = s_fx[G], f1 = s_fx[G + 1u];
+                    const uint32_t ovr = __funnelshift_r(f0.x, f1.x, fs), val = __funnelshift_r(f0.y, f1.y, fs);
+                    qp = (qp & ~ovr) | (val & ovr);
+                }
+                uint32_t np = qp & fl & (0xffffffffu << (4 * i_lo)) & (0xffffffffu >> (32 - 4 * i_hi));
+                while (np) {
+                    const uint32_t b = (uint32_t)__ffs((int)np) - 1u; np &= np - 1u;
+                    red_shared_add(a_c + 4u * (q0w + (b >> 2)) + PLANE_N * (uint32_t)TILE, 1u << (8u * (b & 3u)));
+                }
+            }
+        };
+        // pass word -> its word's bucket; the piece -> the exception list when it has any
+        auto commit = [&](uint32_t k, int32_t w, const PieceOut& o) {
+            if (o.pw) {
+                const uint32_t wi = (uint32_t)(w - w_lo);
+                uint32_t pos = cap;
+                if (wi < nw) pos = atomicAdd(fill + w, 1u);
+                if (pos < cap) s_bucket[wi * cap + pos] = o.pw; else spill(w, o.pw);
+            }
+            if ((o.xnz && o.pw) || o.nf) {
+                if (sh.ablate & ABL_EXCEPT) return;
+                const uint32_t at = atomicAdd(list_n, 1u);
+                if (at < L.list_cap) s_list[at] = make_uint2(k | ((uint32_t)w << 16) | (o.nf ? 0x80000000u : 0u), o.pw);
+                else exceptions(k, w, o.pw, o.nf != 0u);
+            }
+        };
+
+        // ---- 1. one thread per read: segment records, pass words into the buckets of the tile's words, exception list
+        if (tid < 32u) s_fill[32u * ((chunk_no + 1u) & 1u) + tid] = 0;          // the next chunk's counters
+        if (tid == CONSUMERS - 1) s_misc[(chunk_no + 1u) & 1u] = 0;
+        for (uint32_t t = tid; t < ((sh.ablate & ABL_READS) ? 0u : m); t += CONSUMERS) {
             const uint32_t k0 = s_sgo[t] - sg_0, k1 = s_sgo[t + 1] - sg_0;
             uint32_t B = s_q4[t] - qbase;                                       // first buffer quad of the next segment
             const uint32_t B_end = s_q4[t + 1] - qbase;
-            if (k1 <= k0 || k1 > nseg || B_end < B || B_end > nbq) {            // offsets not prefix sums / a read without segments
-                atomicExch(err_flag, 2);
-                s_jr[t] = t ? s_jr[0] : (int16_t)0;                             // (keeps the walk below inside the tables; the run fails anyway)
-                continue;
-            }
-            int32_t j_first = 0;
+            if (k1 <= k0 || k1 > nseg || B_end < B || B_end > nbq) { atomicExch(err_flag, 2); continue; }   // offsets not prefix sums / a read without segments
             for (uint32_t k = k0; k < k1; ++k) {
-                const int32_t p = s_sp[k];
+                const int32_t ps = s_sp[k];
                 const uint32_t len = s_sl[k];
-                const uint32_t a = (uint32_t)p & 3u;
+                const uint32_t a = (uint32_t)ps & 3u;
                 const uint32_t nq = (a + len + 3u) >> 2;
-                const int32_t jw = (p - (int32_t)a - p0) >> 2;                  // tile-relative index of the segment's first quad
+                const int32_t jw = (ps - (int32_t)a - p0) >> 2;                 // tile-relative index of the segment's first quad
                 if (B + nq > B_end) break;                                      // segments and offsets disagree: flagged below
-                if (k == k0) j_first = jw;
                 s_seg[k] = make_int2(jw, (int32_t)(B | (nq << 16)));
-                int32_t i_lo = jw < 0 ? -jw : 0; if (i_lo > (int32_t)nq) i_lo = (int32_t)nq;
-                int32_t i_hi = TILE_QUADS - jw; if (i_hi > (int32_t)nq) i_hi = (int32_t)nq; if (i_hi < i_lo) i_hi = i_lo;
-                // bases XOR expected letters; quads off the tile and the padding lanes of the first / last quad become 0
-                for (int32_t i = 0; i < i_lo; ++i) s_x[B + (uint32_t)i] = 0;
-                for (int32_t i = i_hi; i < (int32_t)nq; ++i) s_x[B + (uint32_t)i] = 0;
-                if (!(sh.ablate & ABL_PREP_XOR)) {
-                    uint32_t g = B + (uint32_t)i_lo, j = (uint32_t)(jw + i_lo);
-                    const uint32_t e = B + (uint32_t)i_hi;
-                    // up to three single quads to a word boundary, words of four quads, up to three single quads
-                    uint32_t hn = (0u - g) & 3u; if (hn > e - g) hn = e - g;
-                    for (uint32_t i = 0; i < hn; ++i, ++g, ++j) s_x[g] ^= s_e[j];
-                    uint32_t* xw = reinterpret_cast<uint32_t*>(s_x + g);
-                    const uint32_t nw4 = (e - g) >> 2;
-                    // expected letters of quads j .. j+3: copy j & 3, word j >> 2 (the copy stays the same as j advances by four)
-                    const uint32_t* ew = reinterpret_cast<const uint32_t*>(s_e + (j & 3u) * (uint32_t)EXP_COPY_BYTES + (j & ~3u));
-                    for (uint32_t w = 0; w < nw4; ++w) xw[w] ^= ew[w];
-                    g += 4u * nw4; j += 4u * nw4;
-                    for (; g < e; ++g, ++j) s_x[g] ^= s_e[j];
-                    if (i_lo == 0 && i_hi > 0 && a) s_x[B] &= (uint8_t)(0xffu << (2u * a));
-                    const uint32_t tl = (a + len) & 3u;
-                    if (tl && i_hi == (int32_t)nq && i_hi > i_lo) s_x[B + nq - 1u] &= (uint8_t)(0xffu >> (8u - 2u * tl));
+                // the padding lanes of the first and last quad take the expected letters: padding then never looks like a mismatch
+                const uint32_t tl = (a + len) & 3u;
+                const int32_t jl = jw + (int32_t)nq - 1;
+                if (a && (uint32_t)jw < (uint32_t)TILE_QUADS) s_x[B] |= (uint8_t)(s_e[jw] & ((1u << (2u * a)) - 1u));
+                if (tl && (uint32_t)jl < (uint32_t)TILE_QUADS) s_x[B + nq - 1u] |= (uint8_t)(s_e[jl] & (0xffu << (2u * tl)));
+                if (jl >= 0 && jw < TILE_QUADS && !(sh.ablate & ABL_EXTRACT)) {
+                    const int32_t w_first = (jw < 0 ? 0 : jw) >> 3, w_last = (jl > TILE_QUADS - 1 ? TILE_QUADS - 1 : jl) >> 3;
+                    for (int32_t w = w_first; w <= w_last; w += 2) {            // two pieces per step: independent work for the pipelines
+                        const bool two = w + 1 <= w_last;
+                        const PieceOut oa = piece(jw, B, nq, w, false);
+                        PieceOut ob = piece(jw, B, nq, two ? w + 1 : w, false);
+                        commit(k, w, oa);
+                        if (two) commit(k, w + 1, ob);
+                    }
                 }
                 B += nq;
             }
-            if (B != B_end) {                                                   // quads no segment owns: keep them out of the counts
-                atomicExch(err_flag, 2);
-                for (uint32_t g = B; g < B_end; ++g) s_x[g] = 0;
-            }
-            s_jr[t] = (int16_t)max(-32768, min(32767, j_first));
-            // reads are in coordinate order: word w of the tile is started in or before by the reads [0, s_wend[w])
-            int32_t wa = j_first >> 3; wa = wa < 0 ? 0 : (wa > 32 ? 32 : wa);
-            int32_t wb = 32;
-            if (t + 1 < m) {
-                const uint32_t kn = s_sgo[t + 1] - sg_0;
-                const int32_t pn = kn < nseg ? s_sp[kn] : p0 + 32 * TILE;
-                wb = ((pn & ~3) - p0) >> 5; wb = wb < 0 ? 0 : (wb > 32 ? 32 : wb);
-            }
-            for (int32_t w = wa; w < wb; ++w) s_wend[w] = (uint16_t)(t + 1);
-            if (t == 0) for (int32_t w = 0; w < wa; ++w) s_wend[w] = 0;
-        }
-        if (tid == CONSUMERS - 1) {                                             // elements in front of and behind the chunk in the buffer
-            for (uint32_t g = 0; g < dq; ++g) s_x[g] = 0;
-            for (uint32_t g = nbq; g < 8u * ngroups; ++g) s_x[g] = 0;
-            s_misc[0] = 0;
+            if (B != B_end) atomicExch(err_flag, 2);                            // quads no segment owns
         }
         consumer_sync<CONSUMERS>();
 
-        // ---- 2. extract: 32 staged positions per thread and step -> one pass word; groups with exceptions -> list
+        // ---- 2. exceptions: the listed pieces
         {
-            const uint32_t a_q = smem_u32(stage + L.o_qual), a_x = smem_u32(s_x), a_f = smem_u32(stage + L.o_fix);
-            for (uint32_t u0 = tid & ~31u; u0 < ((sh.ablate & ABL_EXTRACT) ? 0u : ngroups); u0 += CONSUMERS) {
-                const uint32_t u = u0 + lane;
-                bool listed = false;
-                if (u < ngroups) {
-                    const uint4 qa = lds_v4(a_q + 32u * u), qb = lds_v4(a_q + 32u * u + 16u);
-                    const uint32_t q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-                    uint32_t pw = 0, orq = 0;
-                    #pragma unroll
-                    for (int k = 7; k >= 0; --k) {
-                        const uint32_t v = (q[k] & 0x7f7f7f7fu) + 0x73737373u;          // bit 7 of a lane: quality >= 13
-                        uint32_t ok;                                                    // ... and the base is A/C/G/T
-                        asm("lop3.b32 %0, %1, %2, 0x80808080, 0x20;" : "=r"(ok) : "r"(v), "r"(q[k]));    // v & ~q & 0x80808080
-                        pw = __funnelshift_l(ok * 0x00204081u, pw, 4);                  // the four bits 7 -> the product's top nibble
-                        orq |= q[k];
-                    }
-                    const uint32_t nf = orq & 0x80808080u;                              // some base of the group is not A/C/G/T
-                    if (has_fix) {
-                        // mate verdicts: where the overlap rule spoke (first word) its verdict (second word) replaces the quality test
-                        const uint2 f = lds_v2(a_f + 8u * u);
-                        uint32_t val = f.y;
-                        if (nf) {                                                       // a flagged base never counts in D, whatever the verdict
-                            uint32_t fl = 0;
-                            #pragma unroll
-                            for (int k = 7; k >= 0; --k) fl = __funnelshift_l((q[k] & 0x80808080u) * 0x00204081u, fl, 4);
-                            val &= ~fl;
-                        }
-                        pw = (pw & ~f.x) | (val & f.x);
-                    }
-                    s_pb[u + 1u] = pw;
-                    const uint2 x = lds_v2(a_x + 8u * u);
-                    listed = (x.x | x.y | nf) != 0u;
-                }
-                const uint32_t bal = __ballot_sync(0xffffffffu, listed);
-                if (bal) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&s_misc[0], (uint32_t)__popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (listed) s_list[base + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = (uint16_t)u;
-                }
-            }
-        }
-        consumer_sync<CONSUMERS>();
-
-        // ---- 3. exceptions: counted bases that differ from the expected letter, counted non-ACGT bases
-        if (!(sh.ablate & ABL_EXCEPT)) {
-            const uint32_t n_listed = s_misc[0];
-            const uint32_t a_c = smem_u32(s_cnt);
-            const uint32_t* s_qw = (const uint32_t*)(stage + L.o_qual);
-            const uint2* s_fx = (const uint2*)(stage + L.o_fix);
+            uint32_t n_listed = *list_n; if (n_listed > L.list_cap) n_listed = L.list_cap;
             for (uint32_t li = tid; li < n_listed; li += CONSUMERS) {
-                const uint32_t u = s_list[li];
-                const uint32_t pw = s_pb[u + 1u];
-                const uint32_t x0 = *reinterpret_cast<const uint32_t*>(s_x + 8u * u), x1 = *reinterpret_cast<const uint32_t*>(s_x + 8u * u + 4u);
-                // counted non-ACGT bases of the group, a bit per position
-                uint32_t np = 0;
-                {
-                    uint32_t qp = 0, fl = 0;
-                    #pragma unroll
-                    for (int k = 7; k >= 0; --k) {
-                        const uint32_t qk = s_qw[8u * u + (uint32_t)k];
-                        const uint32_t v = (qk & 0x7f7f7f7fu) + 0x73737373u;
-                        qp = __funnelshift_l((v & 0x80808080u) * 0x00204081u, qp, 4);
-                        fl = __funnelshift_l((qk & 0x80808080u) * 0x00204081u, fl, 4);
-                    }
-                    if (fl) {
-                        if (has_fix) { const uint2 f = s_fx[u]; qp = (qp & ~f.x) | (f.y & f.x); }
-                        np = qp & fl;
-                    }
-                }
-                uint32_t seg_b = 1u, seg_e = 0u; int32_t seg_j = 0;           // cached segment: buffer quads [seg_b, seg_e) start at tile quad seg_j
-                #pragma unroll 1
-                for (uint32_t i8 = 0; i8 < 8u; ++i8) {
-                    const uint32_t xb = ((i8 < 4u ? x0 : x1) >> (8u * (i8 & 3u))) & 0xffu;
-                    const uint32_t pn = (pw >> (4u * i8)) & 15u, nn = (np >> (4u * i8)) & 15u;
-                    uint32_t dz = (xb | (xb >> 1)) & 0x55u;                      // bit 2l: lane l differs from the expected letter
-                    dz = (dz | (dz >> 1)) & 0x33u; dz = (dz | (dz >> 2)) & 0x0fu;   // -> bit l
-                    const uint32_t mm = dz & pn;
-                    if (!(mm | nn)) continue;
-                    const uint32_t g = 8u * u + i8;
-                    if (g < seg_b || g >= seg_e) {
-                        // read that owns buffer quad g (bisection over the reads' offsets), then its segment
-                        if (g < s_q4[0] - qbase || g >= s_q4[m] - qbase) continue;
-                        uint32_t lo = 0, hi = m;
-                        while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_q4[mid] - qbase <= g) lo = mid; else hi = mid; }
-                        const uint32_t k0 = s_sgo[lo] - sg_0, k1 = s_sgo[lo + 1] - sg_0;
-                        bool found = false;
-                        if (k1 <= nseg)
-                            for (uint32_t k = k0; k < k1; ++k) {
-                                const int2 sg = s_seg[k];
-                                const uint32_t b = (uint32_t)sg.y & 0xffffu, nq = (uint32_t)sg.y >> 16;
-                                if (g >= b && g < b + nq) { seg_b = b; seg_e = b + nq; seg_j = sg.x; found = true; break; }
-                            }
-                        if (!found) { seg_b = 1u; seg_e = 0u; continue; }
-                    }
-                    const int32_t j = seg_j + (int32_t)(g - seg_b);
-                    if ((uint32_t)j >= (uint32_t)TILE_QUADS) continue;
-                    const uint32_t letters = xb ^ (uint32_t)s_e[j];            // the bases themselves again
-                    const uint32_t ac = a_c + 4u * (uint32_t)j;
-                    #pragma unroll
-                    for (uint32_t l = 0; l < 4u; ++l)
-                        if ((mm >> l) & 1u) red_shared_add(ac + (PLANE_A + ((letters >> (2u * l)) & 3u)) * (uint32_t)TILE, 1u << (8u * l));
-                    if (nn) red_shared_add(ac + PLANE_N * (uint32_t)TILE, nibble_to_lanes(nn));
-                }
+                const uint2 ent = s_list[li];
+                exceptions(ent.x & 0xffffu, (int32_t)((ent.x >> 16) & 0x7fffu), ent.y, (ent.x >> 31) != 0u);
             }
         }
 
-        // ---- 4. depth: a thread owns one 32-position word of the tile and a share of the reads that can cover it
-        if (m && !(sh.ablate & ABL_DEPTH)) {
-            int32_t w_lo = (int32_t)s_jr[0] >> 3; if (w_lo < 0) w_lo = 0;
-            int32_t w_hi = ((int32_t)s_jr[m - 1] + spanq) >> 3; if (w_hi > 31) w_hi = 31;
-            if (w_hi >= w_lo) {
-                const uint32_t nw = (uint32_t)(w_hi - w_lo + 1);
-                // SL lanes share a word: the largest power of two that still gives every word a slot
-                uint32_t sl_log = 5; while ((32u >> sl_log) * NWARPS < nw) --sl_log;
-                const uint32_t SL = 1u << sl_log, wpw = 32u >> sl_log, nslots = wpw * NWARPS;
-                const uint32_t slot = warp * wpw + (lane >> sl_log);
-                const uint32_t wi = slot % nw, blk = slot / nw, nblk = (nslots - 1u - wi) / nw + 1u;
-                const int32_t sub = (int32_t)(blk * SL + (lane & (SL - 1u))), nsub = (int32_t)(nblk * SL);
-                const int32_t w = w_lo + (int32_t)wi, q0w = 8 * w;                 // first tile quad of the word
-                uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                int32_t r_top = (int32_t)s_wend[w]; if (r_top > (int32_t)m) r_top = (int32_t)m;
-                for (int32_t r = r_top - 1 - sub; r >= 0; r -= nsub) {
-                    if ((int32_t)s_jr[r] + spanq <= q0w) break;                    // this read and all before it end in front of the word
-                    const uint32_t k0 = s_sgo[r] - sg_0; uint32_t k1 = s_sgo[r + 1] - sg_0; if (k1 > nseg) k1 = nseg;
-                    for (uint32_t k = k0; k < k1; ++k) {
-                        const int2 sg = s_seg[k];
-                        const int32_t jw = sg.x, b = (int32_t)((uint32_t)sg.y & 0xffffu), nq = (int32_t)((uint32_t)sg.y >> 16);
-                        int32_t i_lo = jw - q0w; if (i_lo < 0) i_lo = 0;
-                        int32_t i_hi = jw + nq - q0w; if (i_hi > 8) i_hi = 8;
-                        if (i_hi <= i_lo) continue;
-                        const uint32_t bit = (uint32_t)(4 * (b + q0w - jw) + 32);      // the word's first position in the pass bits (one word of slack in front)
-                        const uint32_t lo = s_pb[bit >> 5], hi = s_pb[(bit >> 5) + 1u];
-                        const uint32_t mk = __funnelshift_r(lo, hi, bit & 31u) & (0xffffffffu << (4 * i_lo)) & (0xffffffffu >> (32 - 4 * i_hi));
-                        csa_add(c, mk);
-                    }
-                }
-                __syncwarp();
-                // the SL lanes of a word add their counters, then each expands its share of the word's eight quads
-                const bool hi_any = __any_sync(0xffffffffu, (c[4] | c[5] | c[6] | c[7]) != 0u);
-                const uint32_t a_d = smem_u32(s_cnt) + 4u * (uint32_t)q0w;
-                if (!hi_any && sl_log <= 2u) {
-                    for (uint32_t off = 1; off < SL; off <<= 1) csa_combine<6>(c, off);
-                    for (uint32_t qi = lane & (SL - 1u); qi < 8u; qi += SL) { const uint32_t v = csa_quad_lanes<6>(c, qi); if (v) red_shared_add(a_d + 4u * qi, v); }
-                } else {
-                    for (uint32_t off = 1; off < SL; off <<= 1) csa_combine<8>(c, off);
-                    for (uint32_t qi = lane & (SL - 1u); qi < 8u; qi += SL) { const uint32_t v = csa_quad_lanes<8>(c, qi); if (v) red_shared_add(a_d + 4u * qi, v); }
-                }
-            }
-        }
+        // the stage is not needed any more (the depth pass works on the buckets): every warp hands it back on its own, so the
+        // copies of the chunk after next run while the depth pass, the barrier and the copy of the counts are still under way
         fence_proxy_async();                // this thread's writes to the stage are ordered before the copies that refill it
-        consumer_sync<CONSUMERS>();
-        if (tid == 0) mbar_arrive(empty + st);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + st);
 
-        // ---- 5. counts of the chunk
+        // ---- 3. depth: a thread owns one 32-position word of the tile and a share of its bucket
+        if (m && !(sh.ablate & ABL_DEPTH)) {
+            // SL lanes share a word: the largest power of two that still gives every word a slot
+            const uint32_t per_warp = (nw + NWARPS - 1u) / NWARPS;                  // words a warp must hold
+            const uint32_t wpw_log = per_warp > 1u ? 32u - (uint32_t)__clz((int)(per_warp - 1u)) : 0u, sl_log = 5u - wpw_log;
+            const uint32_t SL = 1u << sl_log, nslots = NWARPS << wpw_log;
+            const uint32_t slot = (warp << wpw_log) + (lane >> sl_log);
+            const uint32_t blk = slot / nw, wi = slot - blk * nw, nblk = (nslots - 1u - wi) / nw + 1u;
+            const uint32_t sub = blk * SL + (lane & (SL - 1u)), nsub = nblk * SL;
+            uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            uint32_t n = fill[(uint32_t)w_lo + wi]; if (n > cap) n = cap;
+            const uint32_t* bk = s_bucket + wi * cap;
+            for (uint32_t e = sub; e < n; e += 2u * nsub) {                         // two entries per step
+                const uint32_t ma = bk[e], mb = e + nsub < n ? bk[e + nsub] : 0u;
+                csa_add(c, ma); csa_add(c, mb);
+            }
+            __syncwarp();
+            // the SL lanes of a word add their counters, then each expands its share of the word's eight quads
+            const bool hi_any = __any_sync(0xffffffffu, (c[4] | c[5] | c[6] | c[7]) != 0u);
+            const uint32_t a_d = a_c + 32u * ((uint32_t)w_lo + wi);
+            if (!hi_any && sl_log <= 2u) {
+                for (uint32_t off = 1; off < SL; off <<= 1) csa_combine<6>(c, off);
+                for (uint32_t qi = lane & (SL - 1u); qi < 8u; qi += SL) { const uint32_t v = csa_quad_lanes<6>(c, qi); if (v) red_shared_add(a_d + 4u * qi, v); }
+            } else {
+                for (uint32_t off = 1; off < SL; off <<= 1) csa_combine<8>(c, off);
+                for (uint32_t qi = lane & (SL - 1u); qi < 8u; qi += SL) { const uint32_t v = csa_quad_lanes<8>(c, qi); if (v) red_shared_add(a_d + 4u * qi, v); }
+            }
+        }
+        consumer_sync<CONSUMERS>();
+
+        // ---- 4. counts of the chunk
         if (HAS_WIDE && (flags & CHUNK_WIDE)) {
             #pragma unroll
             for (int c = 0; c < (HAS_WIDE ? N_PLANES : 1); ++c)
@@ -1087,8 +1100,8 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                 dst[i] = w;
             }
         }
-        // The next chunk's prep writes the segment records, first quads and word index again while slower warps may still
-        // be copying counts out: those are different arrays; the counters are next touched behind the next chunk's barriers.
+        // Warps that are through start the next chunk while slower ones still copy counts out: step 1 writes the segment records,
+        // the buckets and the list (none of which a copy touches), and the counters are next written behind the next chunk's barrier.
     }
 }
 

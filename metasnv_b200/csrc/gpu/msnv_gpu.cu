@@ -281,6 +281,8 @@ static PileupShape choose_pileup_shape(uint64_t n_reads, uint64_t n_bases, uint6
     sh.has_fix = has_fix ? 1u : 0u;
     sh.wait_hint_ns = getenv("MSNV_WAIT_HINT_NS") ? (uint32_t)atoi(getenv("MSNV_WAIT_HINT_NS")) : 0u;
     sh.ablate = getenv("MSNV_ABLATE") ? (uint32_t)atoi(getenv("MSNV_ABLATE")) : 0u;
+    sh.n_stages = 2;
+    if (const char* e = getenv("MSNV_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= PL_STAGES_MAX) sh.n_stages = (uint32_t)v; }
     uint32_t mr = deep ? (max_ctas <= 3 ? NARROW_MAX_READS : 96u) : (uint32_t)(reads_per_item * 1.3 + 24.0);
     if (const char* e = getenv("MSNV_MAX_READS")) mr = (uint32_t)atoi(e);
     if (mr < 16) mr = 16;

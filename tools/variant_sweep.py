@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Tuning aid: one device-generated shard, msnv_shard_run under several staging settings of the pileup kernel
-(MSNV_PILEUP_CTAS : MSNV_CHUNK_Q4 : MSNV_MAX_READS : MSNV_WAIT_HINT_NS : MSNV_CONSUMERS : MSNV_ABLATE, empty = the library's own choice)."""
+(MSNV_PILEUP_CTAS : MSNV_CHUNK_Q4 : MSNV_MAX_READS : MSNV_WAIT_HINT_NS : MSNV_CONSUMERS : MSNV_ABLATE : MSNV_STAGES, empty = the library's own choice)."""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from metasnv_b200 import abi, harness as H
@@ -18,8 +18,8 @@ if first >= 0:
     ctx.shard_mask_position(first)
 ref_hits = None
 for setting in a.settings.split(","):
-    fields = (setting.split(":") + ["", "", "", "", "", ""])[:6]
-    for k, v in zip(("MSNV_PILEUP_CTAS", "MSNV_CHUNK_Q4", "MSNV_MAX_READS", "MSNV_WAIT_HINT_NS", "MSNV_CONSUMERS", "MSNV_ABLATE"), fields):
+    fields = (setting.split(":") + ["", "", "", "", "", "", ""])[:7]
+    for k, v in zip(("MSNV_PILEUP_CTAS", "MSNV_CHUNK_Q4", "MSNV_MAX_READS", "MSNV_WAIT_HINT_NS", "MSNV_CONSUMERS", "MSNV_ABLATE", "MSNV_STAGES"), fields):
         os.environ.pop(k, None)
         if v:
             os.environ[k] = v
@@ -31,4 +31,4 @@ for setting in a.settings.split(","):
         ms.append(ctx.timings()["ms_pileup"])
     if ref_hits is None:
         ref_hits = h.n_hits
-    print(json.dumps({"setting": setting, "ms_pileup": sum(ms) / len(ms), "min": min(ms), "hits_equal": h.n_hits == ref_hits}), flush=True)
+    print(json.dumps({"setting": setting, "ms_pileup": sum(ms) / len(ms), "min": min(ms), "ms_mate": ctx.timings().get("ms_mate"), "hits_equal": h.n_hits == ref_hits}), flush=True)
