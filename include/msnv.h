@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MSNV_ABI_VERSION 4
+#define MSNV_ABI_VERSION 5
 
 /* Positions per tile: contigs of a shard are laid out back to back in a "shard coordinate" space,
  * each starting at a multiple of MSNV_TILE, so a tile never spans two contigs. The kernels are written
@@ -125,6 +125,10 @@ typedef struct {
     uint32_t kernel_launches;
     uint32_t n_ranges;          /* ranges of tiles the run was split into to fit the tile budget (1 = none) */
     float    ms_mate;           /* the mate-overlap pass alone (included in ms_pileup) */
+    /* last msnv_cov_run(): device time of its two kernels (difference scatter; prefix sum + histogram), what they processed */
+    float    ms_cov_scatter, ms_cov_scan;
+    uint32_t reserved;
+    uint64_t cov_positions, cov_blocks;
 } msnv_timings;
 
 int         msnv_abi_version(void);

@@ -40,7 +40,9 @@ class Timings(C.Structure):
     _fields_ = [("ms_index", C.c_float), ("ms_d2h", C.c_float), ("ms_pileup", C.c_float), ("ms_call", C.c_float),
                 ("ms_compact", C.c_float), ("ms_gather", C.c_float), ("ms_total", C.c_float),
                 ("n_items", C.c_uint64), ("n_reads", C.c_uint64), ("n_bases", C.c_uint64),
-                ("n_tiles", C.c_uint32), ("kernel_launches", C.c_uint32), ("n_ranges", C.c_uint32), ("ms_mate", C.c_float)]
+                ("n_tiles", C.c_uint32), ("kernel_launches", C.c_uint32), ("n_ranges", C.c_uint32), ("ms_mate", C.c_float),
+                ("ms_cov_scatter", C.c_float), ("ms_cov_scan", C.c_float), ("reserved", C.c_uint32),
+                ("cov_positions", C.c_uint64), ("cov_blocks", C.c_uint64)]
 
 
 class CovBlocks(C.Structure):
@@ -174,6 +176,11 @@ class HitsView:
         self.cov = arr(h.cov, (n, s), np.uint16)
         self.allele = arr(h.allele, (n, 4, s), np.uint16)
         self.total = arr(h.total, (n, 5), np.uint32)
+
+
+def device_count():
+    """CUDA devices the library sees (0 without a GPU)."""
+    return int(load().msnv_device_count())
 
 
 class Context:

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <memory>
 #include <chrono>
 #include <cstdio>
@@ -68,25 +69,39 @@ static int pick_device(const std::string& indiv_path)
 
 struct Job { std::string ref, bed, list; };
 
-// Pinned staging memory of one window slot: the decoding threads copy their finished batches in (bump allocation),
-// the uploads (cudaMemcpyAsync from pinned memory) then run as DMA while the threads go on decoding.
-struct PinnedSlab {
-    uint8_t* base = nullptr; size_t cap = 0; std::atomic<size_t> used{0};
-    uint8_t* take(size_t bytes) {
-        const size_t need = (bytes + 255) & ~(size_t)255;
-        const size_t at = used.fetch_add(need);
-        return at + need <= cap ? base + at : nullptr;
+// Pinned bounce buffers between the decoding threads and the device. Page-locking memory costs about a second per two
+// gigabytes, so the pool is small (a few chunks, locked in the background while the reference is being read) and
+// recycled: a decoding thread copies its finished batch into a free chunk, the main thread queues the upload from
+// there (DMA at the host link's rate, it overlaps the decoding) and hands the chunks back once the copies have run.
+struct BouncePool {
+    static constexpr size_t CHUNK = (size_t)128 << 20;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<uint8_t*> free_chunks, all_chunks;
+    size_t wanted = 0;
+    bool closed = false;                                   // no more chunks will ever come (allocation failed or stopped)
+    void add(uint8_t* p) { { std::lock_guard<std::mutex> lk(mu); free_chunks.push_back(p); all_chunks.push_back(p); } cv.notify_all(); }
+    void close() { { std::lock_guard<std::mutex> lk(mu); closed = true; } cv.notify_all(); }
+    // a free chunk; waits while chunks are in flight or still being locked. nullptr: there is no pool (use pageable memory)
+    uint8_t* acquire() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !free_chunks.empty() || (closed && all_chunks.empty()); });
+        if (free_chunks.empty()) return nullptr;
+        uint8_t* p = free_chunks.back(); free_chunks.pop_back();
+        return p;
     }
+    void release(const std::vector<uint8_t*>& v) { { std::lock_guard<std::mutex> lk(mu); free_chunks.insert(free_chunks.end(), v.begin(), v.end()); } cv.notify_all(); }
 };
 
-// one sample's batch as the library wants it, in pinned memory when the slab had room (else the decoder's own arrays)
-static msnv_sample_reads stage_batch(const SampleReads& r, PinnedSlab& slab, bool& pinned)
+// one sample's batch as the library wants it: copied into a bounce chunk when it fits one (else the decoder's own arrays)
+static msnv_sample_reads stage_batch(const SampleReads& r, BouncePool& pool, uint8_t*& chunk)
 {
     msnv_sample_reads v = r.view();
-    pinned = false;
-    if (!slab.base || v.n_reads == 0) return v;
-    uint8_t* p = slab.take(r.bytes() + 8 * 256);
+    chunk = nullptr;
+    if (v.n_reads == 0 || r.bytes() + 8 * 256 > BouncePool::CHUNK) return v;
+    uint8_t* p = pool.acquire();
     if (!p) return v;
+    chunk = p;
     auto put = [&](const void* src, size_t bytes) { uint8_t* d = p; memcpy(d, src, bytes); p += (bytes + 255) & ~(size_t)255; return d; };
     v.pos = (const int32_t*)put(r.pos.data(), r.pos.size() * 4);
     v.seg_off = (const uint32_t*)put(r.seg_off.data(), r.seg_off.size() * 4);
@@ -96,7 +111,6 @@ static msnv_sample_reads stage_batch(const SampleReads& r, PinnedSlab& slab, boo
     v.seg_len = (const uint16_t*)put(r.seg_len.data(), r.seg_len.size() * 2);
     v.seq2 = put(r.seq2.data(), r.seq2.size());
     v.qual = put(r.qual.data(), r.qual.size());
-    pinned = true;
     return v;
 }
 
@@ -209,12 +223,19 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
         for (auto& th : pool) th.join();
         if (bad) { fprintf(stderr, "snpCall: %s\n", first_err.c_str()); msnv_destroy(ctx); return 1; }
     }
-    PinnedSlab slab[2];
-    {
-        const double per_window = est_bytes / n_windows * 1.3 + (double)S * 4096.0 + (1 << 20);
-        const size_t cap = (size_t)std::min(per_window, 1.5 * std::max(1.0, win_mb) * 1048576.0 + (double)S * 4096.0);
-        for (int i = 0; i < (n_windows > 1 ? 2 : 1); ++i) { slab[i].base = (uint8_t*)msnv_pinned_alloc(cap); slab[i].cap = slab[i].base ? cap : 0; }
-    }
+    BouncePool pool;
+    std::atomic<bool> stop_pinning(false);
+    std::thread pinner([&]() {
+        size_t n = (size_t)std::min(8.0, std::max(2.0, est_bytes / (double)BouncePool::CHUNK));
+        if (const char* e = getenv("MSNV_BOUNCE_CHUNKS")) n = (size_t)std::max(0, atoi(e));
+        for (size_t i = 0; i < n && !stop_pinning; ++i) {
+            uint8_t* p = (uint8_t*)msnv_pinned_alloc(BouncePool::CHUNK);
+            if (!p) break;
+            pool.add(p);
+        }
+        pool.close();
+    });
+    struct PinJoin { std::atomic<bool>& stop; std::thread& t; ~PinJoin() { stop = true; if (t.joinable()) t.join(); } } pin_join{stop_pinning, pinner};
     stage("decoders open");
 
     std::vector<SampleReads> batch[2];
@@ -222,18 +243,21 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     struct WindowJob {
         std::vector<std::thread> pool; std::atomic<uint32_t> next{0}; std::atomic<bool> failed{false};
         std::mutex mu; std::vector<uint32_t> ready; std::string err; uint32_t n_done = 0;
+        std::vector<msnv_sample_reads> view; std::vector<uint8_t*> chunk;       // per sample: the staged batch
     };
     auto start_window = [&](WindowJob& J, uint32_t k) {
         const uint32_t lo = k * tiles_per_window * MSNV_TILE, hi = std::min<uint64_t>((uint64_t)(k + 1) * tiles_per_window * MSNV_TILE, layout.n_positions);
         J.next = 0; J.failed = false; J.ready.clear(); J.err.clear(); J.n_done = 0;
+        J.view.assign(S, msnv_sample_reads{}); J.chunk.assign(S, nullptr);
         for (int t = 0; t < n_threads; ++t)
-            J.pool.emplace_back([&J, &dec, &batch, k, lo, hi, S]() {
+            J.pool.emplace_back([&J, &dec, &batch, &pool, k, lo, hi, S]() {
                 for (;;) {
                     const uint32_t s = J.next.fetch_add(1);
                     if (s >= S) break;
                     std::string e;
                     bool good = true;
                     if (!J.failed) good = dec[s]->window(lo, (uint32_t)hi, k ? &batch[(k - 1) & 1][s] : nullptr, batch[k & 1][s], e);
+                    if (good && !J.failed) J.view[s] = stage_batch(batch[k & 1][s], pool, J.chunk[s]);
                     std::lock_guard<std::mutex> lk(J.mu);
                     if (!good) { if (J.err.empty()) J.err = e; J.failed = true; }
                     J.ready.push_back(s);
@@ -260,25 +284,40 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
         const uint32_t slot = k & 1u;
         const uint32_t lo = k * tiles_per_window * MSNV_TILE, hi = (uint32_t)std::min<uint64_t>((uint64_t)(k + 1) * tiles_per_window * MSNV_TILE, layout.n_positions);
         if (n_windows > 1 && msnv_window_begin(ctx, slot, lo, hi) != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); rc = 1; }
-        slab[slot].used = 0;
-        // drain: queue the upload of every batch of this window as soon as its thread is through
+        // drain: queue the upload of every batch of this window as soon as its thread is through, hand bounce chunks back
         uint32_t taken = 0;
+        std::vector<uint8_t*> in_flight;
+        auto recycle = [&]() {
+            if (in_flight.empty()) return true;
+            const double a = now_s();
+            if (msnv_shard_sync(ctx) != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); return false; }
+            t_add += now_s() - a;
+            pool.release(in_flight); in_flight.clear();
+            return true;
+        };
         while (taken < S && !rc) {
             std::vector<uint32_t> got;
             { std::lock_guard<std::mutex> lk(cur->mu); got.assign(cur->ready.begin() + taken, cur->ready.end()); }
-            if (got.empty()) { const double a = now_s(); std::this_thread::sleep_for(std::chrono::microseconds(100)); t_decode_wait += now_s() - a; continue; }
+            if (got.empty()) {
+                if (!recycle()) { rc = 1; break; }                 // (threads may be waiting for a chunk)
+                const double a = now_s(); std::this_thread::sleep_for(std::chrono::microseconds(100)); t_decode_wait += now_s() - a;
+                continue;
+            }
             taken += (uint32_t)got.size();
-            if (cur->failed) continue;
+            if (cur->failed) { for (uint32_t s : got) if (cur->chunk[s]) in_flight.push_back(cur->chunk[s]); recycle(); continue; }
             for (uint32_t s : got) {
                 const double a = now_s();
-                bool pinned = false;
-                const msnv_sample_reads v = stage_batch(batch[slot][s], slab[slot], pinned);
+                const msnv_sample_reads& v = cur->view[s];
                 const int arc = n_windows > 1 ? msnv_window_add_sample(ctx, slot, s, &v) : msnv_shard_add_sample(ctx, s, &v);
                 if (arc != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); rc = 1; break; }
-                (pinned ? h2d_bytes : pageable_bytes) += batch[slot][s].bytes();
+                if (cur->chunk[s]) in_flight.push_back(cur->chunk[s]);
+                (cur->chunk[s] ? h2d_bytes : pageable_bytes) += batch[slot][s].bytes();
                 t_add += now_s() - a;
             }
+            if (in_flight.size() >= 3 && !recycle()) { rc = 1; break; }
         }
+        if (!recycle()) rc = 1;
+        if (rc) { cur->failed = true; pool.close(); }
         for (auto& th : cur->pool) th.join();
         cur->pool.clear();
         if (cur->failed) { fprintf(stderr, "snpCall: %s\n", cur->err.c_str()); rc = 1; }
@@ -368,7 +407,9 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     }
     // the process is about to exit: the driver reclaims the device; freeing every block one by one
     // (each cudaFree is a device-wide synchronisation) would only add seconds
-    if (getenv("MSNV_CLEAN_EXIT")) { for (auto& sl : slab) msnv_pinned_free(sl.base); msnv_destroy(ctx); }
+    stop_pinning = true;
+    if (pinner.joinable()) pinner.join();
+    if (getenv("MSNV_CLEAN_EXIT")) { for (uint8_t* p : pool.all_chunks) msnv_pinned_free(p); msnv_destroy(ctx); }
     return 0;
 }
 

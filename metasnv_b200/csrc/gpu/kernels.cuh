@@ -2,12 +2,10 @@
 //
 // Data flow for one shard (all samples of one genome bin):
 //   index_kernel     (tile, sample) pairs that have reads  -> ordered work items (ballot compaction)
-//   mate_kernel      mate-overlap quality rule (SURVEY.md Annex A.2) -> per-base verdict bits
 //   pileup_kernel    persistent CTAs: a producer warp stages the items' position-aligned reads through a
-//                    ring of TMA bulk copies; consumer warps turn the qualities into one pass bit per base
-//                    (32 positions per thread and step) and count depth with vertical (carry-save) counters
-//                    in registers; only bases that differ from the reference touch shared-memory atomics
-//                    -> 6 B per sample-position                                       [dominant kernel]
+//                    ring of TMA bulk copies; consumer warps apply the mate-overlap quality correction
+//                    (SURVEY.md Annex A.2) in shared memory and scatter sixteen positions per thread and
+//                    step into byte-lane count planes -> 6 B per sample-position     [dominant kernel]
 //   call_kernel      per tile: reduce over samples, snpCall thresholds (call_vC.cpp:545-601)
 //   compact_kernel   ordered stream compaction of called positions (warp ballot + block scan)
 //   gather_kernel    per hit: per-sample coverage / allele counts for the host formatter
@@ -34,7 +32,7 @@ struct SampleDev {
     const uint16_t* seg_len;
     const uint8_t*  seq2;
     const uint8_t*  qual;
-    uint32_t*       fix;          // samples with mate links: the verdicts of the mate-overlap rule (mate_kernel: two words per eight quads), else null
+    uint8_t*        fix;          // samples with mate links: per quad, the verdict of the mate-overlap rule (mate_kernel), else null
     uint32_t        n_reads, max_span;
 };
 
@@ -310,68 +308,83 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ v, ui
 // mate overlap (htslib tweak_overlap_quality, SURVEY.md Annex A.2): for every pair the host linked, at every
 // reference position both mates align a base to, the rule decides which of the two bases is still counted
 // (overlap_rule.h: a corrected quality is only ever compared with the threshold, so its verdict is one bit).
-// The uploaded reads are never modified: the verdicts go to a side array `fix` in the geometry the pileup
-// kernel consumes - for every group of eight consecutive quads of the sample (32 staged positions) two
-// words: a mask of the positions the rule overrides and, under that mask, whether the base passes
-// (bit 4 * (quad & 7) + lane in both). Cleared and rebuilt by every run (fix_clear_kernel, mate_kernel).
-// Eight lanes per pair, one quad of both mates per lane and step: the mates are stored position-aligned,
-// so their quads line up word for word and a step is two coalesced loads of up to 32 bytes per mate.
+// The uploaded reads are never modified: the verdicts go to a side array `fix`, one byte per quad of the
+// sample - low nibble: positions the rule overrides, high nibble: whether the base passes there - which the
+// pileup kernel stages next to the bases. Cleared and rebuilt by every run (fix_clear_kernel, mate_kernel).
 // ------------------------------------------------------------------------------------------------
 // bit 0 of the four byte lanes -> a nibble, and back
 __device__ __forceinline__ uint32_t lanes_to_nibble(uint32_t x) { return ((x & 0x01010101u) * 0x01020408u) >> 24; }
 __device__ __forceinline__ uint32_t nibble_to_lanes(uint32_t n) { return ((n & 0xfu) * 0x00204081u) & 0x01010101u; }
 
-__host__ __device__ __forceinline__ size_t fix_words(size_t n_q4) { return 2 * ((n_q4 + 7) / 8) + 8; }   // + spare for the 16-byte copies
-
-__global__ void __launch_bounds__(256) fix_clear_kernel(const SampleDev* __restrict__ samples)
+// `which`: the samples that have mate links (blockIdx.y indexes it)
+__global__ void __launch_bounds__(256) fix_clear_kernel(const SampleDev* __restrict__ samples, const uint32_t* __restrict__ which)
 {
-    const SampleDev sd = samples[blockIdx.y];
+    const SampleDev sd = samples[which[blockIdx.y]];
     if (!sd.fix || sd.n_reads == 0) return;
-    const uint32_t n16 = (uint32_t)((fix_words(__ldg(sd.q4_off + sd.n_reads)) * 4 + 15) / 16);
+    const uint32_t n16 = (__ldg(sd.q4_off + sd.n_reads) + 15u) / 16u;        // the array has spare bytes behind it
     uint4* f = reinterpret_cast<uint4*>(sd.fix);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) f[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-__global__ void __launch_bounds__(256) mate_kernel(const SampleDev* __restrict__ samples)
+// A warp takes 32 consecutive reads, picks the ones that open a pair (the earlier mate) by ballot and hands them out four
+// at a time to its four groups of eight lanes: every lane works on a pair, one quad of both mates per lane and step. The
+// mates are stored position-aligned, so their quads line up word for word; a step of a pair is two coalesced loads of up
+// to 32 bytes per mate and one coalesced store of up to 8 verdict bytes per mate.
+__global__ void __launch_bounds__(256) mate_kernel(const SampleDev* __restrict__ samples, const uint32_t* __restrict__ which)
 {
-    const SampleDev sd = samples[blockIdx.y];
+    const SampleDev sd = samples[which[blockIdx.y]];
     if (!sd.fix) return;
     const uint32_t* __restrict__ qual32 = reinterpret_cast<const uint32_t*>(sd.qual);
+    uint32_t* __restrict__ fix32 = reinterpret_cast<uint32_t*>(sd.fix);
     const uint32_t nq_total = sd.n_reads ? __ldg(sd.q4_off + sd.n_reads) : 0u;
-    const uint32_t l8 = threadIdx.x & 7u;
-    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < sd.n_reads; r += (gridDim.x * blockDim.x) >> 3) {
-        const int32_t mt = __ldg(sd.mate + r);
-        if (mt <= (int32_t)r || (uint32_t)mt >= sd.n_reads) continue;         // the earlier mate (a) handles the pair
-        const uint32_t sa0 = __ldg(sd.seg_off + r), sa1 = __ldg(sd.seg_off + r + 1), sb0 = __ldg(sd.seg_off + mt), sb1 = __ldg(sd.seg_off + mt + 1);
-        uint32_t qa = __ldg(sd.q4_off + r);                                   // first quad of a's next segment
-        const uint32_t qb0 = __ldg(sd.q4_off + mt);
-        for (uint32_t ka = sa0; ka < sa1; ++ka) {
-            const int32_t ax = __ldg(sd.seg_pos + ka);
-            const uint32_t al = __ldg(sd.seg_len + ka);
-            uint32_t qb = qb0;
-            for (uint32_t kb = sb0; kb < sb1; ++kb) {
-                const int32_t bx = __ldg(sd.seg_pos + kb);
-                const uint32_t bl = __ldg(sd.seg_len + kb);
-                const int32_t lo = max(ax, bx), hi = min(ax + (int32_t)al, bx + (int32_t)bl);
-                for (int32_t P = (lo >> 2) + (int32_t)l8; P < ((hi + 3) >> 2); P += 8) {      // (empty when the segments share no position)
-                    const uint32_t ia = qa + (uint32_t)(P - (ax >> 2)), ib = qb + (uint32_t)(P - (bx >> 2));
-                    if (ia >= nq_total || ib >= nq_total) continue;           // segments and offsets disagree (the pileup kernel reports it)
-                    const uint32_t va = __ldg(qual32 + ia), vb = __ldg(qual32 + ib);
-                    const uint32_t d = msnv_spread_bases((uint32_t)__ldg(sd.seq2 + ia) ^ (uint32_t)__ldg(sd.seq2 + ib));
-                    const uint32_t msk = ((P << 2) >= lo && (P << 2) + 4 <= hi) ? 0xffffffffu : msnv_quad_mask(P << 2, lo, hi);
-                    uint32_t na, nb;
-                    msnv_overlap_pass4(va, vb, d, msk, na, nb);               // masked lanes: flag | 16 (passes) or flag | 0
-                    const uint32_t ovr = lanes_to_nibble(msk);
-                    const uint32_t pa = lanes_to_nibble(na >> 4) & ovr, pb = lanes_to_nibble(nb >> 4) & ovr;
-                    // several threads (and, where two segment combinations meet in a quad, several steps) share a word: OR
-                    atomicOr(sd.fix + 2u * (ia >> 3), ovr << (4u * (ia & 7u)));
-                    if (pa) atomicOr(sd.fix + 2u * (ia >> 3) + 1u, pa << (4u * (ia & 7u)));
-                    atomicOr(sd.fix + 2u * (ib >> 3), ovr << (4u * (ib & 7u)));
-                    if (pb) atomicOr(sd.fix + 2u * (ib >> 3) + 1u, pb << (4u * (ib & 7u)));
+    const uint32_t lane = threadIdx.x & 31u, l8 = lane & 7u, grp = lane >> 3;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5, warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (uint32_t base = warp0 * 32u; base < sd.n_reads; base += warps * 32u) {
+        const uint32_t r_l = base + lane;
+        const int32_t mt_l = r_l < sd.n_reads ? __ldg(sd.mate + r_l) : -1;
+        uint32_t open = __ballot_sync(0xffffffffu, mt_l > (int32_t)r_l && (uint32_t)mt_l < sd.n_reads);     // the earlier mate (a) handles the pair
+        while (open) {
+            // the grp-th of the next (up to) four pairs
+            const uint32_t src = __fns(open, 0u, grp + 1u);                                                   // 0xffffffff when there are fewer
+            const bool have = src < 32u;
+            const int32_t mt = __shfl_sync(0xffffffffu, mt_l, have ? src : 0u);
+            const uint32_t r = base + (have ? src : 0u);
+            { uint32_t k = __popc(open); k = k < 4u ? k : 4u; for (uint32_t i = 0; i < k; ++i) open &= open - 1u; }
+            if (!have) continue;
+            const uint32_t sa0 = __ldg(sd.seg_off + r), sa1 = __ldg(sd.seg_off + r + 1), sb0 = __ldg(sd.seg_off + mt), sb1 = __ldg(sd.seg_off + mt + 1);
+            uint32_t qa = __ldg(sd.q4_off + r);                                   // first quad of a's next segment
+            const uint32_t qb0 = __ldg(sd.q4_off + mt);
+            for (uint32_t ka = sa0; ka < sa1; ++ka) {
+                const int32_t ax = __ldg(sd.seg_pos + ka);
+                const uint32_t al = __ldg(sd.seg_len + ka);
+                uint32_t qb = qb0;
+                for (uint32_t kb = sb0; kb < sb1; ++kb) {
+                    const int32_t bx = __ldg(sd.seg_pos + kb);
+                    const uint32_t bl = __ldg(sd.seg_len + kb);
+                    const int32_t lo = max(ax, bx), hi = min(ax + (int32_t)al, bx + (int32_t)bl);
+                    for (int32_t P = (lo >> 2) + (int32_t)l8; P < ((hi + 3) >> 2); P += 8) {      // (empty when the segments share no position)
+                        const uint32_t ia = qa + (uint32_t)(P - (ax >> 2)), ib = qb + (uint32_t)(P - (bx >> 2));
+                        if (ia >= nq_total || ib >= nq_total) continue;           // segments and offsets disagree (the pileup kernel reports it)
+                        const uint32_t va = __ldg(qual32 + ia), vb = __ldg(qual32 + ib);
+                        const uint32_t d = msnv_spread_bases((uint32_t)__ldg(sd.seq2 + ia) ^ (uint32_t)__ldg(sd.seq2 + ib));
+                        const bool whole = (P << 2) >= lo && (P << 2) + 4 <= hi;
+                        const uint32_t msk = whole ? 0xffffffffu : msnv_quad_mask(P << 2, lo, hi);
+                        uint32_t na, nb;
+                        msnv_overlap_pass4(va, vb, d, msk, na, nb);               // masked lanes: flag | 16 (passes) or flag | 0
+                        const uint32_t ovr = lanes_to_nibble(msk);
+                        const uint32_t fa = ovr | (lanes_to_nibble(na >> 4) & ovr) << 4, fb = ovr | (lanes_to_nibble(nb >> 4) & ovr) << 4;
+                        // a quad the rule covers whole belongs to this segment combination alone: plain byte stores. Two
+                        // combinations can meet in a quad at their ends (with disjoint positions): OR into the byte there.
+                        if (whole) { sd.fix[ia] = (uint8_t)fa; sd.fix[ib] = (uint8_t)fb; }
+                        else {
+                            atomicOr(fix32 + (ia >> 2), fa << (8u * (ia & 3u)));
+                            atomicOr(fix32 + (ib >> 2), fb << (8u * (ib & 3u)));
+                        }
+                    }
+                    qb += (((uint32_t)bx & 3u) + bl + 3u) >> 2;
                 }
-                qb += (((uint32_t)bx & 3u) + bl + 3u) >> 2;
+                qa += (((uint32_t)ax & 3u) + al + 3u) >> 2;
             }
-            qa += (((uint32_t)ax & 3u) + al + 3u) >> 2;
         }
     }
 }
@@ -385,8 +398,7 @@ __global__ void __launch_bounds__(256) mate_kernel(const SampleDev* __restrict__
 //       reference base, A where the reference is not A/C/G/T); the plane of letter e stays 0
 //   N   counted bases that are not A/C/G/T
 // so count[e] = D - (A + C + G + T) and count[x != e] = plane x. Nearly every aligned base equals the
-// reference: the pileup counts D on bits (pass words and vertical counters) and touches the letter planes only for
-// the rare base that differs.
+// reference, so the pileup does ONE shared-memory atomic per four positions instead of four.
 // Narrow items (at most 255 reads touch the tile: no counter can pass 255) store the planes as
 // bytes (6 B per sample-position), wide items (deep coverage) as 16-bit values (12 B).
 // ------------------------------------------------------------------------------------------------
@@ -395,7 +407,7 @@ constexpr int N_PLANES = 6;
 constexpr int PLANE_D = 0, PLANE_A = 1, PLANE_N = 5;
 constexpr uint32_t NARROW_MAX_READS = 255;
 constexpr size_t SLOT_BYTES = 2 * N_PLANES * TILE;
-static_assert(TILE_QUADS == 256, "32 words of 32 positions per tile");
+static_assert(TILE_QUADS == 256, "a staged quad is tagged with one byte");
 
 __host__ __device__ __forceinline__ bool item_is_wide(uint32_t r_lo, uint32_t r_hi) { return r_hi - r_lo > NARROW_MAX_READS; }
 
@@ -414,113 +426,68 @@ __global__ void expect_kernel(const uint8_t* __restrict__ ref, uint32_t n, uint8
     expect[p] = (uint8_t)e;
 }
 
-// The same letters in the geometry of the staged reads: 2 bits per position, a byte per quad, EXP_BYTES per tile
-// (the tile's 256 quads and 16 bytes of zeros). A staged read is cut along the tile's 32-position words, so the
-// expected letters of a word are one aligned 8-byte load.
-constexpr int EXP_BYTES = TILE / 4 + 16;
-static_assert(EXP_BYTES % 16 == 0, "one bulk copy per tile");
-
-__global__ void expect2_kernel(const uint8_t* __restrict__ expect /* of the first tile */, uint32_t n_tiles, uint8_t* __restrict__ expect2 /* [n_tiles][EXP_BYTES] */)
-{
-    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (uint64_t)n_tiles * EXP_BYTES) return;
-    const uint32_t t = (uint32_t)(g / EXP_BYTES), q = (uint32_t)(g % EXP_BYTES);
-    uint32_t v = 0;
-    if (q < (uint32_t)(TILE / 4)) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(expect + (size_t)t * TILE + 4u * q);
-        v = (w & 3u) | ((w >> 6) & 0xcu) | ((w >> 12) & 0x30u) | ((w >> 18) & 0xc0u);
-    }
-    expect2[g] = (uint8_t)v;
-}
-
 // ------------------------------------------------------------------------------------------------
-// pileup: persistent CTAs, one producer warp + four (or eight) consumer warps each, walking the work
-// items blockIdx.x, blockIdx.x + gridDim.x, ... (items are tile-major, so the CTAs resident at any
-// time work on neighbouring tiles and the reads of a sample stream through L2 once).
+// pileup: persistent CTAs, one producer warp + four consumer warps each, walking the work items
+// blockIdx.x, blockIdx.x + gridDim.x, ... (items are tile-major, so the CTAs resident at any time
+// work on neighbouring tiles and the reads of a sample stream through L2 once).
 //
 // Producer warp. Item records and the four offsets that size an item are fetched 32 items at a time
 // (one per lane: the dependent global loads of 32 items overlap). An item whose reads fit one stage
 // (the common case) becomes one chunk; otherwise the warp searches the longest prefix of reads that
 // fits (32 probes at a time) and sends several chunks. For a chunk the warp waits for a free stage of
 // the ring, writes a header and issues eight TMA bulk copies (UBLKCP) that complete on the stage's
-// mbarrier: the reads' offsets, the segment records, the 2-bit bases, the qualities, the overlap
-// verdicts and the tile's expected letters. Consumers therefore never wait for HBM, only for the barrier.
+// mbarrier: the reads' offsets and mate links, the segment records, the 2-bit bases, the qualities
+// and the tile's expected letters. Consumers therefore never wait for HBM, only for the barrier.
 //
-// Consumer warps, per chunk. Reads arrive as position-aligned segments (include/msnv.h): a staged
-// quad holds four consecutive positions starting at a multiple of four, so the bits of a read line up
-// with the bits of the tile after a shift by whole quads. Counting is done on BITS, not bytes:
-//   1. prep, one thread per read: a record per segment (tile-relative quad of its first staged quad,
-//      where it lies in the staging buffer, its length), the read's first quad (reads are in coordinate
-//      order: the reads that can cover a 32-position word of the tile are an index range), and the
-//      staged bases XORed in place with the tile's expected letters (word by word, see expect2_kernel;
-//      padding and quads off the tile become 0), so "differs from the reference" is "byte != 0".
-//   2. extract, flat over the staging buffer, eight quads (32 positions) per thread and step: two
-//      128-bit loads of qualities -> "quality >= 13 and the base is A/C/G/T" on four byte lanes per
-//      quad (3 instructions), the four bits gathered by one multiply, eight quads chained by funnel
-//      shifts -> ONE 32-bit pass word per 32 staged positions (mate-overlap verdicts, two more words,
-//      override it where mate_kernel spoke). Groups that hold a base differing from the expected
-//      letter or a non-ACGT base (about one in six) are appended to a list by warp ballot.
-//   3. exceptions: one thread per listed group finds the tile position of its quads (bisection over
-//      the reads' offsets) and adds the counted mismatches / N bases to the letter and N planes with
-//      shared-memory atomics - the only atomics per base left, for < 1 % of the bases.
-//   4. depth, gather: a thread owns one 32-position word of the tile and a share of the reads that
-//      can cover it. Per (word, segment): two loads of pass words, one funnel shift to the word's
-//      alignment, a mask for the segment's extent, and a carry-save add into vertical counters held in
-//      registers (plane b = bit b of the 32 per-position counts): ~10 instructions for up to 32 bases.
-//      The lanes that share a word add their counters with shuffles (bit-sliced full adders), expand
-//      them to byte lanes and add them to plane D.
-//   5. last chunk of an item: narrow items copy the byte planes to HBM (6 KB, 128-bit stores) and
+// Consumer warps, per chunk (reads arrive as position-aligned segments, include/msnv.h: a staged
+// quad holds four consecutive positions starting at a multiple of four, so a quad is either on the
+// tile or off it and its four bases are handled with byte-lane arithmetic):
+//   1. one thread per read: every staged quad that lies on the tile is tagged with its tile-relative
+//      index (four tags per store), the qualities of the few quads off the tile are zeroed (the
+//      scatter's threshold test then rejects them like any poor base)
+//   2. scatter: a thread takes FOUR consecutive staged quads per step (one 128-bit load of the
+//      qualities, one word each of bases, tags and - for samples with mates - overlap verdicts).
+//      Per quad: quality test on four byte lanes (overridden where mate_kernel left a verdict), one
+//      shared-memory atomic into plane D, and a compare with the expected letters; only lanes that
+//      hold a mismatch loop over their set bits and add to a letter plane.
+//   3. last chunk of an item: narrow items copy the byte planes to HBM (6 KB, 128-bit stores) and
 //      clear them; wide items fold every chunk into 16-bit lanes held in registers (a chunk stages
 //      at most 255 reads) and store those.
 // The mate-overlap rule itself runs before this kernel (mate_kernel): no read ever waits for its mate here.
 //
-// Shared memory (dynamic, see pileup_smem_layout): mbarriers | 6 count planes | pass words | segment
-// records | first quads | word index | exception list | PL_STAGES x { header, q4_off, seg_off,
-// seg_pos, seg_len, expected letters, bases, overlap verdicts, qualities }. Every TMA destination is
-// 16-byte aligned; sources are the 16-byte aligned addresses at or below the first element needed (the
-// arrays are 256-byte aligned and have spare bytes behind them); the per-quad arrays all start at the
-// sample's quad index rounded down to 16, so a stage holds up to 15 quads in front of the chunk.
+// Shared memory (dynamic, see pileup_smem_layout): mbarriers | 6 count planes | quad tags |
+// PL_STAGES x { header, q4_off, seg_off, seg_pos, seg_len, expected letters, bases, overlap
+// verdicts, qualities }. Every TMA destination is 16-byte aligned; sources are the 16-byte
+// aligned addresses at or below the first element needed (the arrays are 256-byte aligned and have
+// 32 spare bytes behind them), so a stage holds a few elements in front of and behind the chunk.
 // ------------------------------------------------------------------------------------------------
 // consumer threads per CTA: a template parameter of the kernel (128 or 256; the CTA has one more warp, the producer)
-constexpr int PL_STAGES_MAX = 4;        // stages of the ring: PileupShape::n_stages (2 .. PL_STAGES_MAX)
+constexpr int PL_STAGES = 2;
 constexpr uint32_t CHUNK_Q4_MIN = MSNV_MAX_READ_BASES / 4 + 2 * MSNV_MAX_READ_SEGMENTS;   // a single read always fits
 constexpr uint32_t CHUNK_SEGS_MIN = MSNV_MAX_READ_SEGMENTS;
 constexpr uint32_t CHUNK_FIRST = 1u, CHUNK_LAST = 2u, CHUNK_WIDE = 4u, CHUNK_STOP = 8u, CHUNK_FIX = 16u /* the sample has mate verdicts */;
-constexpr uint32_t ABL_EXTRACT = 1u, ABL_DEPTH = 4u, ABL_STORE = 8u, ABL_EXCEPT = 16u, ABL_READS = 32u, ABL_PREFETCH = 64u;   // PileupShape::ablate (measurement only)
 
 // limits of one staged chunk, chosen per launch from the shape of the shard
-struct PileupShape { uint32_t max_reads, max_segs, chunk_q4, has_fix /* some sample carries mate verdicts */, wait_hint_ns, ablate /* measurement only: phases to skip */, n_stages; };
+struct PileupShape { uint32_t max_reads, max_segs, chunk_q4, has_fix /* some sample carries mate verdicts */, wait_hint_ns, ablate /* measurement only: phases to skip */; };
 
-struct ChunkHdr { uint32_t m, nq4, q4_0, sg_0, nseg, c0, item, sample, tile, flags, spanq /* quads a read of the sample can span */, pad[5]; };
+struct ChunkHdr { uint32_t m, nq4, q4_0, sg_0, nseg, c0, item, sample, tile, flags, pad[6]; };
 static_assert(sizeof(ChunkHdr) == 64, "header is one 64-byte block");
 
 struct PileupSmem {
-    uint32_t bar, cnt, fill, bucket, segtab, list, misc, stage0, stage_bytes;           // byte offsets
-    uint32_t o_hdr, o_q4, o_sg, o_sp, o_sl, o_exp, o_seq, o_fix, o_qual;                // within a stage
-    uint32_t bucket_words, list_cap, total;
+    uint32_t bar, cnt, tags, stage0, stage_bytes;                               // byte offsets
+    uint32_t o_hdr, o_q4, o_sg, o_sp, o_sl, o_exp, o_seq, o_fix, o_qual;        // within a stage
+    uint32_t total;
 };
 
 __host__ __device__ constexpr uint32_t up_to(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-// buffer quad g of a chunk is stored PADQ quads into the stage's per-quad arrays: a piece that starts inside a word of the
-// tile is loaded from the word's first quad, up to seven quads in front of the segment
-constexpr uint32_t PADQ = 16;
-
 __host__ __device__ inline PileupSmem pileup_smem_layout(const PileupShape sh)
 {
     PileupSmem L{};
-    const uint32_t cq = up_to(sh.chunk_q4, 16) + 16 + PADQ;   // staged quads: the chunk's, up to 15 in front of it, the pad
     uint32_t o = 0;
-    L.bar = o;    o += 128;
-    L.cnt = o;    o += N_PLANES * TILE;
-    L.fill = o;   o += 2 * 32 * 4;                             // entries per word of the tile, for this chunk and the next
-    // pass words of the chunk's pieces, bucketed by word of the tile (a piece = what a segment has on one word)
-    L.bucket_words = up_to((sh.chunk_q4 / 8 + 2 * sh.max_reads) * 9 / 8, 32);
-    L.bucket = o; o += L.bucket_words * 4;
-    L.segtab = o; o += up_to(sh.max_segs, 2) * 8;
-    L.list_cap = 160;
-    L.list = o;   o += L.list_cap * 8;
-    L.misc = o;   o += 16;
+    L.bar = o;   o += 128;
+    L.cnt = o;   o += N_PLANES * TILE;
+    L.tags = o;  o += up_to(sh.chunk_q4, 16) + 16;
     L.stage0 = up_to(o, 128);
     uint32_t s = 0;
     const uint32_t mw = up_to(sh.max_reads + 1, 4) + 8;
@@ -529,23 +496,17 @@ __host__ __device__ inline PileupSmem pileup_smem_layout(const PileupShape sh)
     L.o_sg = s;   s += mw * 4;
     L.o_sp = s;   s += (up_to(sh.max_segs, 4) + 8) * 4;
     L.o_sl = s;   s += (up_to(sh.max_segs, 8) + 16) * 2;
-    L.o_exp = s;  s += EXP_BYTES;
-    L.o_seq = s;  s += cq + 32;                                // (a piece is read as three words)
-    L.o_fix = s;  s += sh.has_fix ? cq + 32 : 0;
-    L.o_qual = s; s += 4 * cq + 64;
+    L.o_exp = s;  s += TILE;
+    L.o_seq = s;  s += up_to(sh.chunk_q4, 16) + 32;
+    L.o_fix = s;  s += sh.has_fix ? up_to(sh.chunk_q4, 16) + 32 : 0;
+    L.o_qual = s; s += 4 * up_to(sh.chunk_q4, 16) + 32;
     L.stage_bytes = up_to(s, 128);
-    L.total = L.stage0 + sh.n_stages * L.stage_bytes;
+    L.total = L.stage0 + PL_STAGES * L.stage_bytes;
     return L;
 }
 
-// explicit shared-window accesses (32-bit addresses) for the inner loops
+// explicit shared-window accesses (32-bit addresses) for the scatter loop
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint2 lds_v2(uint32_t a)
-{
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
-    return v;
-}
 __device__ __forceinline__ uint4 lds_v4(uint32_t a)
 {
     uint4 v;
@@ -564,13 +525,13 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 // the arrays of one sample the producer copies from
 struct SrcPtrs {
     const uint32_t* q4_off; const uint32_t* seg_off; const int32_t* seg_pos; const uint16_t* seg_len;
-    const uint8_t* seq2; const uint8_t* qual; const uint32_t* fix; uint32_t max_span;
+    const uint8_t* seq2; const uint8_t* qual; const uint8_t* fix;
 };
 __device__ __forceinline__ SrcPtrs load_src_ptrs(const SampleDev* __restrict__ sd)
 {
     SrcPtrs p;
     p.q4_off = sd->q4_off; p.seg_off = sd->seg_off; p.seg_pos = sd->seg_pos; p.seg_len = sd->seg_len;
-    p.seq2 = sd->seq2; p.qual = sd->qual; p.fix = sd->fix; p.max_span = sd->max_span;
+    p.seq2 = sd->seq2; p.qual = sd->qual; p.fix = sd->fix;
     return p;
 }
 
@@ -579,16 +540,15 @@ __device__ __forceinline__ SrcPtrs load_src_ptrs(const SampleDev* __restrict__ s
 struct ChunkCopies { const void* src[7]; uint32_t bytes[7]; };
 __device__ __forceinline__ ChunkCopies chunk_copies(const SrcPtrs& p, uint32_t c0, uint32_t m, uint32_t q4_0, uint32_t nq4, uint32_t sg_0, uint32_t nseg)
 {
-    const uint32_t dm = c0 & 3u, ds = sg_0 & 3u, dl = sg_0 & 7u, d16 = q4_0 & 15u;
+    const uint32_t dm = c0 & 3u, ds = sg_0 & 3u, dl = sg_0 & 7u, dq = q4_0 & 3u, d16 = q4_0 & 15u;
     ChunkCopies c;
     c.src[0] = p.q4_off + (c0 - dm);             c.bytes[0] = up_to(dm + m + 1u, 4) * 4u;
     c.src[1] = p.seg_off + (c0 - dm);            c.bytes[1] = c.bytes[0];
-    // verdicts: a byte per quad (two words per eight quads), same geometry as the bases
-    c.src[2] = p.fix ? reinterpret_cast<const uint8_t*>(p.fix) + (q4_0 - d16) : nullptr; c.bytes[2] = p.fix ? up_to(d16 + nq4, 16) : 0u;
+    c.src[2] = p.fix ? p.fix + (q4_0 - d16) : nullptr; c.bytes[2] = p.fix ? up_to(d16 + nq4, 16) : 0u;   // same geometry as the bases
     c.src[3] = p.seg_pos + (sg_0 - ds);          c.bytes[3] = up_to(ds + nseg, 4) * 4u;
     c.src[4] = p.seg_len + (sg_0 - dl);          c.bytes[4] = up_to(dl + nseg, 8) * 2u;
     c.src[5] = p.seq2 + (q4_0 - d16);            c.bytes[5] = up_to(d16 + nq4, 16);
-    c.src[6] = p.qual + 4u * (size_t)(q4_0 - d16); c.bytes[6] = up_to(d16 + nq4, 4) * 4u;
+    c.src[6] = p.qual + 4u * (size_t)(q4_0 - dq); c.bytes[6] = up_to(dq + nq4, 4) * 4u;
     return c;
 }
 __device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes)
@@ -606,29 +566,28 @@ __device__ __forceinline__ void prefetch_chunk(const SrcPtrs& p, uint32_t c0, ui
 
 // ---- producer: one chunk into the next stage of the ring (whole warp waits; lane `issuer` writes the header and issues)
 __device__ __forceinline__ void pileup_issue_chunk(uint8_t* smem, const PileupSmem& L, const PileupShape& sh, uint32_t& chunk_no, uint32_t issuer, const SrcPtrs& src,
-                                                   const uint8_t* __restrict__ expect2, uint32_t item, uint32_t sample, uint32_t tile, uint32_t c0,
+                                                   const uint8_t* __restrict__ expect, uint32_t item, uint32_t sample, uint32_t tile, uint32_t c0,
                                                    uint32_t m, uint32_t q4_0, uint32_t nq4, uint32_t sg_0, uint32_t nseg, uint32_t flags)
 {
     uint64_t* full = (uint64_t*)(smem + L.bar);
-    uint64_t* empty = full + PL_STAGES_MAX;
-    const uint32_t s = chunk_no % sh.n_stages, ph = (chunk_no / sh.n_stages) & 1u;
+    uint64_t* empty = full + PL_STAGES;
+    const uint32_t s = chunk_no % PL_STAGES, ph = (chunk_no / PL_STAGES) & 1u;
     mbar_wait(empty + s, ph ^ 1u, sh.wait_hint_ns);
     if ((threadIdx.x & 31) == issuer) {
         uint8_t* stage = smem + L.stage0 + s * L.stage_bytes;
         ChunkHdr* h = (ChunkHdr*)(stage + L.o_hdr);
         h->m = m; h->nq4 = nq4; h->q4_0 = q4_0; h->sg_0 = sg_0; h->nseg = nseg; h->c0 = c0;
         h->item = item; h->sample = sample; h->tile = tile; h->flags = flags | (src.fix ? CHUNK_FIX : 0u);
-        h->spanq = (src.max_span + 3u) / 4u + 1u;
         const ChunkCopies c = chunk_copies(src, c0, m, q4_0, nq4, sg_0, nseg);
-        const uint32_t dst[7] = {L.o_q4, L.o_sg, L.o_fix + PADQ, L.o_sp, L.o_sl, L.o_seq + PADQ, L.o_qual + 4u * PADQ};
-        uint32_t total = (uint32_t)EXP_BYTES;
+        const uint32_t dst[7] = {L.o_q4, L.o_sg, L.o_fix, L.o_sp, L.o_sl, L.o_seq, L.o_qual};
+        uint32_t total = (uint32_t)TILE;
         #pragma unroll
         for (int i = 0; i < 7; ++i) total += c.bytes[i];
         fence_proxy_async();
         mbar_expect_tx(full + s, total);
         #pragma unroll
         for (int i = 0; i < 7; ++i) if (c.bytes[i]) tma_load_1d(stage + dst[i], c.src[i], c.bytes[i], full + s);
-        tma_load_1d(stage + L.o_exp, expect2 + (size_t)tile * EXP_BYTES, EXP_BYTES, full + s);
+        tma_load_1d(stage + L.o_exp, expect + (size_t)tile * TILE, TILE, full + s);
     }
     __syncwarp();
     ++chunk_no;
@@ -637,7 +596,7 @@ __device__ __forceinline__ void pileup_issue_chunk(uint8_t* smem, const PileupSm
 constexpr uint32_t PREFETCH_AHEAD = 4;       // items between a chunk's L2 prefetch and its copy
 
 __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem& L, const PileupShape sh, const SampleDev* __restrict__ samples,
-                                                const Item* __restrict__ items, uint32_t n_items, const uint8_t* __restrict__ expect2,
+                                                const Item* __restrict__ items, uint32_t n_items, const uint8_t* __restrict__ expect,
                                                 int* __restrict__ err_flag)
 {
     const uint32_t lane = threadIdx.x & 31, G = gridDim.x;
@@ -655,14 +614,14 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
             q_lo = __ldg(src.q4_off + it.z); q_hi = __ldg(src.q4_off + it.w);
             g_lo = __ldg(src.seg_off + it.z); g_hi = __ldg(src.seg_off + it.w);
             whole = it.w - it.z <= sh.max_reads && q_hi - q_lo <= sh.chunk_q4 && g_hi - g_lo <= sh.max_segs;
-            if (whole && lane < PREFETCH_AHEAD && !(sh.ablate & ABL_PREFETCH)) prefetch_chunk(src, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo, g_hi - g_lo);
+            if (whole && lane < PREFETCH_AHEAD) prefetch_chunk(src, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo, g_hi - g_lo);
         }
         for (uint32_t k = 0; k < 32u; ++k) {
             const uint64_t idx = base + (uint64_t)k * G;
             if (idx >= n_items) break;
-            if (lane == k + PREFETCH_AHEAD && whole && !(sh.ablate & ABL_PREFETCH)) prefetch_chunk(src, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo, g_hi - g_lo);
+            if (lane == k + PREFETCH_AHEAD && whole) prefetch_chunk(src, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo, g_hi - g_lo);
             if (__shfl_sync(0xffffffffu, (int)whole, k)) {                   // the lane that owns the item issues it from its own registers
-                pileup_issue_chunk(smem, L, sh, chunk_no, k, src, expect2, (uint32_t)mine, it.x, it.y, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo,
+                pileup_issue_chunk(smem, L, sh, chunk_no, k, src, expect, (uint32_t)mine, it.x, it.y, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo,
                                    g_hi - g_lo, CHUNK_FIRST | CHUNK_LAST | (item_is_wide(it.z, it.w) ? CHUNK_WIDE : 0u));
                 continue;
             }
@@ -693,7 +652,7 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
                         const uint32_t bk = __shfl_sync(0xffffffffu, b_l, kk), ek = __shfl_sync(0xffffffffu, e_l, kk);
                         if (ek == bk) break;                                             // past the end of the item
                         if (lane == kk + PREFETCH_AHEAD && lane < n_ok && e_l > b_l) prefetch_chunk(sp, b_l, e_l - b_l, qb, qe - qb, gb, ge - gb);
-                        pileup_issue_chunk(smem, L, sh, chunk_no, kk, sp, expect2, (uint32_t)idx, sample, tile, b_l, e_l - b_l, qb, qe - qb, gb, ge - gb, fl);
+                        pileup_issue_chunk(smem, L, sh, chunk_no, kk, sp, expect, (uint32_t)idx, sample, tile, b_l, e_l - b_l, qb, qe - qb, gb, ge - gb, fl);
                         done_to = ek; done_q = __shfl_sync(0xffffffffu, qe, kk); done_g = __shfl_sync(0xffffffffu, ge, kk);
                     }
                     c0 = done_to; qc = done_q; gc = done_g;
@@ -714,11 +673,11 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
                 const uint32_t first = c0 == r_lo ? CHUNK_FIRST : 0u;
                 if (m == 0) {                        // a single read over the documented limits: host validation failed
                     if (lane == 0) atomicExch(err_flag, 1);
-                    pileup_issue_chunk(smem, L, sh, chunk_no, 0u, sp, expect2, (uint32_t)idx, sample, tile, c0, 0u, qc, 0u, gc, 0u, first | CHUNK_LAST | wide);
+                    pileup_issue_chunk(smem, L, sh, chunk_no, 0u, sp, expect, (uint32_t)idx, sample, tile, c0, 0u, qc, 0u, gc, 0u, first | CHUNK_LAST | wide);
                     break;
                 }
                 const uint32_t qn = __ldg(q4p + c0 + m), gn = __ldg(sgp + c0 + m);
-                pileup_issue_chunk(smem, L, sh, chunk_no, 0u, sp, expect2, (uint32_t)idx, sample, tile, c0, m, qc, qn - qc, gc, gn - gc,
+                pileup_issue_chunk(smem, L, sh, chunk_no, 0u, sp, expect, (uint32_t)idx, sample, tile, c0, m, qc, qn - qc, gc, gn - gc,
                                    first | (c0 + m == r_hi ? CHUNK_LAST : 0u) | wide);
                 c0 += m; qc = qn; gc = gn;
             }
@@ -726,8 +685,8 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
     }
     // ---- no more items: tell the consumers
     uint64_t* full = (uint64_t*)(smem + L.bar);
-    uint64_t* empty = full + PL_STAGES_MAX;
-    const uint32_t s = chunk_no % sh.n_stages, ph = (chunk_no / sh.n_stages) & 1u;
+    uint64_t* empty = full + PL_STAGES;
+    const uint32_t s = chunk_no % PL_STAGES, ph = (chunk_no / PL_STAGES) & 1u;
     mbar_wait(empty + s, ph ^ 1u, sh.wait_hint_ns);
     if (lane == 0) {
         ((ChunkHdr*)(smem + L.stage0 + s * L.stage_bytes + L.o_hdr))->flags = CHUNK_STOP;
@@ -735,92 +694,35 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
     }
 }
 
-// ---- vertical counters: plane b holds bit b of 32 per-position counts
-// add the 0/1 word `mk` to the counters c[0..8) (a chunk stages at most 255 reads: eight planes never overflow)
-__device__ __forceinline__ void csa_add(uint32_t (&c)[8], uint32_t mk)
-{
-    uint32_t carry = c[0] & mk; c[0] ^= mk;
-    uint32_t t = c[1] & carry; c[1] ^= carry; carry = t;
-    t = c[2] & carry; c[2] ^= carry; carry = t;
-    t = c[3] & carry; c[3] ^= carry; carry = t;
-    if (carry) {                                                            // a count passed 15: rare at ordinary depth
-        #pragma unroll
-        for (int b = 4; b < 8; ++b) { t = c[b] & carry; c[b] ^= carry; carry = t; }
-    }
-}
-// c += the counters of the lane `lane ^ off` (bit-sliced full adders over PLANES planes), every lane of the warp
-template <int PLANES>
-__device__ __forceinline__ void csa_combine(uint32_t (&c)[8], uint32_t off)
-{
-    uint32_t carry = 0;
-    #pragma unroll
-    for (int b = 0; b < PLANES; ++b) {
-        const uint32_t p = __shfl_xor_sync(0xffffffffu, c[b], off);
-        const uint32_t s = c[b] ^ p ^ carry;
-        carry = (c[b] & p) | (carry & (c[b] ^ p));
-        c[b] = s;
-    }
-}
-// byte lanes of quad qi (positions 4 qi .. 4 qi + 3 of the word) from PLANES planes
-template <int PLANES>
-__device__ __forceinline__ uint32_t csa_quad_lanes(const uint32_t (&c)[8], uint32_t qi)
-{
-    uint32_t v = 0;
-    #pragma unroll
-    for (int b = 0; b < PLANES; ++b) v |= (((c[b] >> (4u * qi)) & 15u) * (0x00204081u << b)) & (0x01010101u << b);
-    return v;
-}
-
-// shifts that give 0 for counts of 32 and more (plain C++ shifts are undefined there)
-__device__ __forceinline__ uint32_t shl_c(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
-// byte lanes [lo, hi) of a word, 0 <= lo, hi <= 4
-__device__ __forceinline__ uint32_t byte_range(uint32_t lo, uint32_t hi) { return shl_c(0xffffffffu, 8u * lo) & ~shl_c(0xffffffffu, 8u * hi); }
-// bit 7 of the four byte lanes of a word -> a nibble in the top four bits of the product; quads are chained with funnel
-// shifts (the quad chained last ends up in bits 0..3)
-__device__ __forceinline__ uint32_t chain_nibble(uint32_t lanes7, uint32_t acc) { return __funnelshift_l(lanes7 * 0x00204081u, acc, 4); }
-
-// A PIECE is what one staged segment has on one 32-position word of the tile: quads [i_lo, i_hi) of the word. It is loaded
-// as the eight staged quads that line up with the word (the segment is stored position-aligned, so that is a plain offset);
-// quads outside the segment belong to a neighbour in the buffer and are masked.
-struct PieceOut { uint32_t pw /* counted bases, bit 4 quad + lane */, xnz /* != 0: some base of the piece differs from the expected letter */, nf /* != 0: a base is not A/C/G/T */; };
-
-// CONSUMERS: consumer threads (128: up to four CTAs per SM; 256: two larger ones for deep shards).
+// CONSUMERS: consumer threads (128: four CTAs per SM at the standard shape; 256: three larger ones).
 // HAS_WIDE: the shard has items with more than 255 reads (deep coverage); without them the 16-bit accumulators and
 // their registers do not exist.
 template <int CONSUMERS, bool HAS_WIDE>
-__global__ void __launch_bounds__(CONSUMERS + 32, CONSUMERS == 128 ? 3 : 2)
+__global__ void __launch_bounds__(CONSUMERS + 32, CONSUMERS == 128 ? 4 : 3)
 pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items, const PileupShape sh,
-              const uint8_t* __restrict__ expect2, uint8_t* __restrict__ tiles /*[n_items][SLOT_BYTES]*/, int* __restrict__ err_flag)
+              const uint8_t* __restrict__ expect, uint8_t* __restrict__ tiles /*[n_items][SLOT_BYTES]*/, int* __restrict__ err_flag)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const PileupSmem L = pileup_smem_layout(sh);
     uint64_t* full = (uint64_t*)(smem + L.bar);
-    uint64_t* empty = full + PL_STAGES_MAX;
+    uint64_t* empty = full + PL_STAGES;
     uint32_t* s_cnt = (uint32_t*)(smem + L.cnt);
 
     if (threadIdx.x == 0) {
-        // a stage is full when its copies have landed (one arrival + bytes), empty when every consumer warp is through with it
-        for (int s = 0; s < PL_STAGES_MAX; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CONSUMERS / 32); }
+        for (int s = 0; s < PL_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        ((uint32_t*)(smem + L.misc))[0] = 0; ((uint32_t*)(smem + L.misc))[1] = 0;
     }
-    for (uint32_t k = threadIdx.x; k < (uint32_t)(N_PLANES * TILE_QUADS) + 64u; k += CONSUMERS + 32) s_cnt[k] = 0;     // the planes and the fill counters behind them
+    for (uint32_t k = threadIdx.x; k < (uint32_t)(N_PLANES * TILE_QUADS); k += CONSUMERS + 32) s_cnt[k] = 0;
     __syncthreads();
 
     if (threadIdx.x >= CONSUMERS) {
-        pileup_producer(smem, L, sh, samples, items, n_items, expect2, err_flag);
+        pileup_producer(smem, L, sh, samples, items, n_items, expect, err_flag);
         return;
     }
 
     // ------------------------------------------------------------------------------------ consumers
-    constexpr uint32_t NWARPS = CONSUMERS / 32;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    uint32_t* s_fill = (uint32_t*)(smem + L.fill);                 // [chunk & 1][32]: pieces per word of the tile
-    uint32_t* s_bucket = (uint32_t*)(smem + L.bucket);             // pass words of the pieces, `cap` slots per word of the chunk's range
-    int2* s_seg = (int2*)(smem + L.segtab);                        // per staged segment: tile-relative quad of its first quad | first buffer quad, quads << 16
-    uint2* s_list = (uint2*)(smem + L.list);                       // pieces with exceptions: segment | word << 16 | non-ACGT << 31, pass word
-    uint32_t* s_misc = (uint32_t*)(smem + L.misc);                 // [chunk & 1] length of the list
-    const uint32_t a_c = smem_u32(s_cnt);
+    const uint32_t tid = threadIdx.x;
+    uint8_t* s_tags = smem + L.tags;
     // wide items: per plane and owned quad (QPT * tid + k), 16-bit lanes: [0] = positions 0 and 2, [1] = positions 1 and 3
     constexpr int QPT = TILE_QUADS / CONSUMERS;                 // quads a thread folds (2 or 1)
     uint32_t acc[HAS_WIDE ? N_PLANES : 1][QPT][2];
@@ -830,244 +732,150 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
         for (int k = 0; k < QPT; ++k) acc[c][k][0] = acc[c][k][1] = 0;
 
     for (uint32_t chunk_no = 0;; ++chunk_no) {
-        const uint32_t st = chunk_no % sh.n_stages, ph = (chunk_no / sh.n_stages) & 1u;
+        const uint32_t st = chunk_no % PL_STAGES, ph = (chunk_no / PL_STAGES) & 1u;
         uint8_t* stage = smem + L.stage0 + st * L.stage_bytes;
         mbar_wait(full + st, ph, sh.wait_hint_ns);
         const ChunkHdr* h = (const ChunkHdr*)(stage + L.o_hdr);
         const uint32_t flags = h->flags;
         if (flags & CHUNK_STOP) break;
         const uint32_t m = h->m, nq4 = h->nq4, q4_0 = h->q4_0, sg_0 = h->sg_0, nseg = h->nseg, c0 = h->c0, item = h->item;
-        const int32_t spanq = (int32_t)h->spanq;
         const int32_t p0 = (int32_t)(h->tile * TILE);
-        const uint32_t dm = c0 & 3u, dq = q4_0 & 15u;
+        const uint32_t dm = c0 & 3u, dq = q4_0 & 3u, c12 = q4_0 & 12u;
         const uint32_t* s_q4 = (const uint32_t*)(stage + L.o_q4) + dm;          // s_q4[t] = q4_off[c0 + t], t <= m
         const uint32_t* s_sgo = (const uint32_t*)(stage + L.o_sg) + dm;
         const int32_t* s_sp = (const int32_t*)(stage + L.o_sp) + (sg_0 & 3u);   // s_sp[k] = seg_pos[sg_0 + k], k < nseg
         const uint16_t* s_sl = (const uint16_t*)(stage + L.o_sl) + (sg_0 & 7u);
-        uint8_t* s_x = stage + L.o_seq + PADQ;                                  // bases of buffer quad B in byte B
-        const uint8_t* s_e = stage + L.o_exp;                                   // expected letters of tile quad j in byte j
-        const uint32_t* s_qw = (const uint32_t*)(stage + L.o_qual) + PADQ;      // qualities of buffer quad B in word B
-        const uint2* s_fx = (const uint2*)(stage + L.o_fix);                    // mate verdicts of buffer quads 8 G - PADQ .. + 7 in s_fx[G]
+        uint32_t* s_qw = (uint32_t*)(stage + L.o_qual);                         // qualities of buffer quad B in word B
+        uint8_t* s_fx = stage + L.o_fix + c12;                                  // overlap verdicts of buffer quad B (samples with mates)
         const bool has_fix = (flags & CHUNK_FIX) != 0;
-        const uint32_t nbq = dq + nq4;                                          // buffer quad g is quad (q4_0 - dq) + g of the sample
-        const uint32_t qbase = q4_0 - dq;                                       // s_q4[t] - qbase = first buffer quad of read t
-        uint32_t* list_n = s_misc + (chunk_no & 1u);
-        uint32_t* fill = s_fill + 32u * (chunk_no & 1u);
-        // words of the tile this chunk can touch (reads are in coordinate order) and the bucket slots each gets
-        int32_t w_lo = 0, w_hi = -1;
-        if (m) {
-            const uint32_t kl = s_sgo[m - 1] - sg_0;
-            const int32_t j_a = ((s_sp[0] & ~3) - p0) >> 2, j_b = ((s_sp[kl < nseg ? kl : 0u] & ~3) - p0) >> 2;
-            w_lo = j_a >> 3; w_lo = w_lo < 0 ? 0 : (w_lo > 31 ? 31 : w_lo);
-            w_hi = (j_b + spanq) >> 3; w_hi = w_hi > 31 ? 31 : (w_hi < w_lo ? w_lo : w_hi);
-        }
-        const uint32_t nw = (uint32_t)(w_hi - w_lo + 1);
-        const uint32_t cap = m ? L.bucket_words / nw : 0u;
+        const uint32_t nbq = dq + nq4, ngroups = (nbq + 3u) >> 2;               // staged quad g is buffer quad g + dq
+        // a quad that must not count (off the tile, in front of or behind the chunk): no quality passes and no verdict overrides
+        auto mute = [&](uint32_t g) { s_qw[g] = 0; if (has_fix) s_fx[g] = 0; };
 
-        // one piece: pass word, does-any-base-differ, is-any-base-not-ACGT
-        auto piece = [&](int32_t jw, uint32_t B, uint32_t nq, int32_t w, bool exact) -> PieceOut {
-            const int32_t q0w = 8 * w;
-            const int32_t d = (int32_t)B + q0w - jw;                                // buffer quad that lines up with the word's first quad
-            const uint32_t* qp = s_qw + d;
-            uint32_t q[8];
-            #pragma unroll
-            for (int i = 0; i < 8; ++i) q[i] = qp[i];
-            uint32_t lo = 0, hi = 0, orq = 0;
-            #pragma unroll
-            for (int i = 3; i >= 0; --i) {                                          // two independent chains of four quads
-                const uint32_t va = (q[i] & 0x7f7f7f7fu) + 0x73737373u, vb = (q[i + 4] & 0x7f7f7f7fu) + 0x73737373u;   // bit 7 of a lane: quality >= 13
-                uint32_t oa, ob;                                                    // ... and the base is A/C/G/T
-                asm("lop3.b32 %0, %1, %2, 0x80808080, 0x20;" : "=r"(oa) : "r"(va), "r"(q[i]));        // v & ~q & 0x80808080
-                asm("lop3.b32 %0, %1, %2, 0x80808080, 0x20;" : "=r"(ob) : "r"(vb), "r"(q[i + 4]));
-                lo = chain_nibble(oa, lo); hi = chain_nibble(ob, hi);
-                orq |= q[i] | q[i + 4];
-            }
-            uint32_t pw = __byte_perm(lo, hi, 0x5410);
-            int32_t i_lo = jw - q0w; if (i_lo < 0) i_lo = 0;
-            int32_t i_hi = jw + (int32_t)nq - q0w; if (i_hi > 8) i_hi = 8;
-            const uint32_t msk = (0xffffffffu << (4 * i_lo)) & (0xffffffffu >> (32 - 4 * i_hi));      // (a piece has at least one quad)
-            PieceOut o;
-            o.nf = orq & 0x80808080u;
-            const uint32_t dp = (uint32_t)(d + (int32_t)PADQ);                      // the same quad in the stage's padded arrays
-            if (has_fix) {
-                // mate verdicts: where the overlap rule spoke (first word) its verdict (second word) replaces the quality test
-                const uint32_t G = dp >> 3, fs = 4u * (dp & 7u);
-                const uint2 f0 = s_fx[G], f1 = s_fx[G + 1u];
-                const uint32_t ovr = __funnelshift_r(f0.x, f1.x, fs);
-                uint32_t val = __funnelshift_r(f0.y, f1.y, fs);
-                if (o.nf) {                                                         // a flagged base never counts in D, whatever the verdict
-                    uint32_t fl = 0;
-                    #pragma unroll
-                    for (int i = 7; i >= 0; --i) fl = chain_nibble(q[i] & 0x80808080u, fl);
-                    val &= ~fl;
-                }
-                pw = (pw & ~ovr) | (val & ovr);
-            }
-            o.pw = pw & msk;
-            // bases of the eight quads XOR the word's expected letters
-            const uint32_t* xw = reinterpret_cast<const uint32_t*>(stage + L.o_seq + (dp & ~3u));
-            const uint32_t w0 = xw[0], w1 = xw[1], w2 = xw[2], sft = 8u * (dp & 3u);
-            const uint2 e = *reinterpret_cast<const uint2*>(s_e + q0w);
-            uint32_t x0 = __funnelshift_r(w0, w1, sft) ^ e.x, x1 = __funnelshift_r(w1, w2, sft) ^ e.y;
-            if (exact || i_lo != 0 || i_hi != 8) {                                  // first / last piece of a segment: drop the neighbours' quads
-                const uint32_t a0 = (uint32_t)min(i_lo, 4), a1 = (uint32_t)min(i_hi, 4);
-                x0 &= byte_range(a0, a1);
-                x1 &= byte_range((uint32_t)i_lo - a0, (uint32_t)i_hi - a1);
-            }
-            o.xnz = x0 | x1;
-            if (exact) { o.xnz = x0; o.nf = x1; }                                   // (the exception pass wants the two words themselves)
-            return o;
-        };
-        // a pass word that found no slot in its word's bucket (very uneven depth, or a read longer than the sample's span says)
-        auto spill = [&](int32_t w, uint32_t pw) {
-            for (uint32_t i = 0; i < 8u; ++i) { const uint32_t nb = (pw >> (4u * i)) & 15u; if (nb) red_shared_add(a_c + 4u * (8u * (uint32_t)w + i), nibble_to_lanes(nb)); }
-        };
-        // the counted bases of a piece that differ from the expected letter -> letter planes; its counted non-ACGT bases -> N plane
-        auto exceptions = [&](uint32_t k, int32_t w, uint32_t pw, bool any_n) {
-            const int2 sg = s_seg[k];
-            const int32_t jw = sg.x;
-            const uint32_t B = (uint32_t)sg.y & 0xffffu, nq = (uint32_t)sg.y >> 16;
-            const PieceOut x = piece(jw, B, nq, w, true);                          // .xnz / .nf: the two XOR words, neighbours masked
-            uint32_t nz[2];
-            #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {                                        // lanes that differ, a bit per position: even bits of (x | x >> 1), compressed
-                uint32_t z = hh ? x.nf : x.xnz;
-                z = (z | (z >> 1)) & 0x55555555u;
-                z = (z | (z >> 1)) & 0x33333333u;
-                z = (z | (z >> 2)) & 0x0f0f0f0fu;
-                z = (z | (z >> 4)) & 0x00ff00ffu;
-                nz[hh] = (z | (z >> 8)) & 0xffffu;
-            }
-            uint32_t mm = (nz[0] | (nz[1] << 16)) & pw;
-            const uint32_t q0w = 8u * (uint32_t)w;
-            while (mm) {
-                const uint32_t b = (uint32_t)__ffs((int)mm) - 1u; mm &= mm - 1u;
-                const uint32_t i = b >> 2, l = b & 3u;
-                const uint32_t xb = ((i < 4u ? x.xnz : x.nf) >> (8u * (i & 3u))) & 0xffu;
-                const uint32_t letter = ((xb ^ (uint32_t)s_e[q0w + i]) >> (2u * l)) & 3u;          // the base itself again
-                red_shared_add(a_c + 4u * (q0w + i) + (PLANE_A + letter) * (uint32_t)TILE, 1u << (8u * l));
-            }
-            if (any_n) {
-                const int32_t d = (int32_t)B + 8 * w - jw;
-                int32_t i_lo = jw - 8 * w; if (i_lo < 0) i_lo = 0;
-                int32_t i_hi = jw + (int32_t)nq - 8 * w; if (i_hi > 8) i_hi = 8;
-                uint32_t qp = 0, fl = 0;
-                #pragma unroll
-                for (int i = 7; i >= 0; --i) {
-                    const uint32_t qk = s_qw[d + i];
-                    fl = chain_nibble(qk & 0x80808080u, fl);
-                    qp = chain_nibble(((qk & 0x7f7f7f7fu) + 0x73737373u) & 0x80808080u, qp);
-                }
-                if (has_fix) {
-                    const uint32_t dp = (uint32_t)(d + (int32_t)PADQ), G = dp >> 3, fs = 4u * (dp & 7u);
-                    const uint2 f0 = s_fx[G], f1 = s_fx[G + 1u];
-                    const uint32_t ovr = __funnelshift_r(f0.x, f1.x, fs), val = __funnelshift_r(f0.y, f1.y, fs);
-                    qp = (qp & ~ovr) | (val & ovr);
-                }
-                uint32_t np = qp & fl & (0xffffffffu << (4 * i_lo)) & (0xffffffffu >> (32 - 4 * i_hi));
-                while (np) {
-                    const uint32_t b = (uint32_t)__ffs((int)np) - 1u; np &= np - 1u;
-                    red_shared_add(a_c + 4u * (q0w + (b >> 2)) + PLANE_N * (uint32_t)TILE, 1u << (8u * (b & 3u)));
-                }
-            }
-        };
-        // pass word -> its word's bucket; the piece -> the exception list when it has any
-        auto commit = [&](uint32_t k, int32_t w, const PieceOut& o) {
-            if (o.pw) {
-                const uint32_t wi = (uint32_t)(w - w_lo);
-                uint32_t pos = cap;
-                if (wi < nw) pos = atomicAdd(fill + w, 1u);
-                if (pos < cap) s_bucket[wi * cap + pos] = o.pw; else spill(w, o.pw);
-            }
-            if ((o.xnz && o.pw) || o.nf) {
-                if (sh.ablate & ABL_EXCEPT) return;
-                const uint32_t at = atomicAdd(list_n, 1u);
-                if (at < L.list_cap) s_list[at] = make_uint2(k | ((uint32_t)w << 16) | (o.nf ? 0x80000000u : 0u), o.pw);
-                else exceptions(k, w, o.pw, o.nf != 0u);
-            }
-        };
-
-        // ---- 1. one thread per read: segment records, pass words into the buckets of the tile's words, exception list
-        if (tid < 32u) s_fill[32u * ((chunk_no + 1u) & 1u) + tid] = 0;          // the next chunk's counters
-        if (tid == CONSUMERS - 1) s_misc[(chunk_no + 1u) & 1u] = 0;
-        for (uint32_t t = tid; t < ((sh.ablate & ABL_READS) ? 0u : m); t += CONSUMERS) {
+        // ---- 1. one thread per read: tags of the quads on the tile, zeroed qualities off it
+        for (uint32_t t = tid; t < m; t += CONSUMERS) {
             const uint32_t k0 = s_sgo[t] - sg_0, k1 = s_sgo[t + 1] - sg_0;
-            uint32_t B = s_q4[t] - qbase;                                       // first buffer quad of the next segment
-            const uint32_t B_end = s_q4[t + 1] - qbase;
-            if (k1 <= k0 || k1 > nseg || B_end < B || B_end > nbq) { atomicExch(err_flag, 2); continue; }   // offsets not prefix sums / a read without segments
+            uint32_t B = s_q4[t] - q4_0 + dq;                                   // first buffer quad of the next segment
+            const uint32_t B_end = s_q4[t + 1] - q4_0 + dq;
+            if (k1 < k0 || k1 > nseg || B_end < B || B_end > nbq) { atomicExch(err_flag, 2); continue; }   // offsets not prefix sums
             for (uint32_t k = k0; k < k1; ++k) {
-                const int32_t ps = s_sp[k];
+                const int32_t p = s_sp[k];
                 const uint32_t len = s_sl[k];
-                const uint32_t a = (uint32_t)ps & 3u;
-                const uint32_t nq = (a + len + 3u) >> 2;
-                const int32_t jw = (ps - (int32_t)a - p0) >> 2;                 // tile-relative index of the segment's first quad
-                if (B + nq > B_end) break;                                      // segments and offsets disagree: flagged below
-                s_seg[k] = make_int2(jw, (int32_t)(B | (nq << 16)));
-                // the padding lanes of the first and last quad take the expected letters: padding then never looks like a mismatch
-                const uint32_t tl = (a + len) & 3u;
-                const int32_t jl = jw + (int32_t)nq - 1;
-                if (a && (uint32_t)jw < (uint32_t)TILE_QUADS) s_x[B] |= (uint8_t)(s_e[jw] & ((1u << (2u * a)) - 1u));
-                if (tl && (uint32_t)jl < (uint32_t)TILE_QUADS) s_x[B + nq - 1u] |= (uint8_t)(s_e[jl] & (0xffu << (2u * tl)));
-                if (jl >= 0 && jw < TILE_QUADS && !(sh.ablate & ABL_EXTRACT)) {
-                    const int32_t w_first = (jw < 0 ? 0 : jw) >> 3, w_last = (jl > TILE_QUADS - 1 ? TILE_QUADS - 1 : jl) >> 3;
-                    for (int32_t w = w_first; w <= w_last; w += 2) {            // two pieces per step: independent work for the pipelines
-                        const bool two = w + 1 <= w_last;
-                        const PieceOut oa = piece(jw, B, nq, w, false);
-                        PieceOut ob = piece(jw, B, nq, two ? w + 1 : w, false);
-                        commit(k, w, oa);
-                        if (two) commit(k, w + 1, ob);
+                const uint32_t a = (uint32_t)p & 3u;
+                const int32_t nq = (int32_t)((a + len + 3u) >> 2);
+                const int32_t jw = (p - (int32_t)a - p0) >> 2;                  // tile-relative index of the segment's first quad
+                if (B + (uint32_t)nq > B_end) break;                            // segments and offsets disagree: flagged below
+                int32_t i_lo = jw < 0 ? -jw : 0; if (i_lo > nq) i_lo = nq;
+                int32_t i_hi = TILE_QUADS - jw; if (i_hi > nq) i_hi = nq; if (i_hi < i_lo) i_hi = i_lo;
+                for (int32_t i = 0; i < i_lo; ++i) mute(B + (uint32_t)i);
+                for (int32_t i = i_hi; i < nq; ++i) mute(B + (uint32_t)i);
+                uint32_t g = B + (uint32_t)i_lo, tv = (uint32_t)(jw + i_lo);
+                const uint32_t e = B + (uint32_t)i_hi;                          // tags tv .. tv + (e - g) - 1 are within 0..255
+                if (!(sh.ablate & 2u)) {   // up to three single tags to a word boundary, words of four consecutive tags, up to three single tags
+                    uint32_t hn = (0u - g) & 3u; if (hn > e - g) hn = e - g;
+                    if (hn > 0u) s_tags[g] = (uint8_t)tv;
+                    if (hn > 1u) s_tags[g + 1] = (uint8_t)(tv + 1u);
+                    if (hn > 2u) s_tags[g + 2] = (uint8_t)(tv + 2u);
+                    g += hn; tv += hn;
+                    uint32_t wv = tv * 0x01010101u + 0x03020100u;                   // no lane passes 255: all four quads are on the tile
+                    uint32_t* tw = reinterpret_cast<uint32_t*>(s_tags + g);
+                    const uint32_t nw = (e - g) >> 2;
+                    uint32_t w = 0;
+                    for (; w + 2u <= nw; w += 2u, wv += 0x08080808u) { tw[w] = wv; tw[w + 1] = wv + 0x04040404u; }
+                    if (w < nw) { tw[w] = wv; ++w; }
+                    g += 4u * nw; tv += 4u * nw;
+                    const uint32_t tn = e - g;
+                    if (tn > 0u) s_tags[g] = (uint8_t)tv;
+                    if (tn > 1u) s_tags[g + 1] = (uint8_t)(tv + 1u);
+                    if (tn > 2u) s_tags[g + 2] = (uint8_t)(tv + 2u);
+                }
+                B += (uint32_t)nq;
+            }
+            if (B != B_end) {                                                   // quads no segment owns: keep them out of the counts
+                atomicExch(err_flag, 2);
+                for (uint32_t g = B; g < B_end; ++g) mute(g);
+            }
+        }
+        if (tid == CONSUMERS - 1) {                                             // elements in front of and behind the chunk in the buffer
+            for (uint32_t g = 0; g < dq; ++g) mute(g);
+            for (uint32_t g = nbq; g < 4u * ngroups; ++g) mute(g);
+        }
+        consumer_sync<CONSUMERS>();
+
+        // ---- 2. scatter: four consecutive buffer quads per thread and step
+        {
+            const uint32_t a_q = smem_u32(s_qw), a_s = smem_u32(stage + L.o_seq) + c12, a_f = smem_u32(stage + L.o_fix) + c12, a_g = smem_u32(s_tags);
+            const uint32_t a_c = smem_u32(s_cnt), a_e = smem_u32(stage + L.o_exp);
+            for (uint32_t u = tid; u < ((sh.ablate & 1u) ? 0u : ngroups); u += CONSUMERS) {
+                const uint4 qv = lds_v4(a_q + 16u * u);
+                const uint32_t sw = lds_u32(a_s + 4u * u), tw = lds_u32(a_g + 4u * u);
+                const uint32_t qa[4] = {qv.x, qv.y, qv.z, qv.w};
+                uint32_t xs[4], mm[4], ac[4], nn[4], nn_any = 0, mm_any = 0;
+                if (!has_fix) {
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t q = qa[k];
+                        const uint32_t j = __byte_perm(tw, 0u, 0x4440u + k);                // tile-relative quad
+                        ac[k] = a_c + 4u * j;                                               // its word in plane D
+                        xs[k] = msnv_spread_bases(__byte_perm(sw, 0u, 0x4440u + k));        // one 2-bit base per byte lane
+                        const uint32_t v = (q & 0x7f7f7f7fu) + 0x73737373u;                 // bit 7 of a lane: quality >= 13
+                        uint32_t ok;                                                        // ... and the base is A/C/G/T
+                        asm("lop3.b32 %0, %1, %2, 0x80808080, 0x20;" : "=r"(ok) : "r"(v), "r"(q));    // v & ~q & 0x80808080
+                        ok >>= 7;
+                        const uint32_t d = xs[k] ^ lds_u32(a_e + 4u * j);                   // differs from the expected letter?
+                        red_shared_add(ac[k], ok);
+                        mm[k] = (d | (d >> 1)) & ok;
+                        mm_any |= mm[k];
+                        nn[k] = v & q;                                                      // bit 7: counted base that is not A/C/G/T
+                        nn_any |= nn[k];
+                    }
+                } else {
+                    // the sample has mate verdicts: where the overlap rule spoke (low nibble of the quad's fix byte) its verdict
+                    // (high nibble) replaces the quality test
+                    const uint32_t fw = lds_u32(a_f + 4u * u);
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t q = qa[k];
+                        const uint32_t j = __byte_perm(tw, 0u, 0x4440u + k);
+                        ac[k] = a_c + 4u * j;
+                        xs[k] = msnv_spread_bases(__byte_perm(sw, 0u, 0x4440u + k));
+                        const uint32_t f = __byte_perm(fw, 0u, 0x4440u + k);
+                        const uint32_t ovr = nibble_to_lanes(f), val = nibble_to_lanes(f >> 4);
+                        const uint32_t qp = (((q & 0x7f7f7f7fu) + 0x73737373u) >> 7) & 0x01010101u;   // quality >= 13
+                        const uint32_t pass = (qp & ~ovr) | (val & ovr);
+                        const uint32_t fl = (q >> 7) & 0x01010101u;                         // the base is not A/C/G/T
+                        const uint32_t ok = pass & ~fl;
+                        const uint32_t d = xs[k] ^ lds_u32(a_e + 4u * j);
+                        red_shared_add(ac[k], ok);
+                        mm[k] = (d | (d >> 1)) & ok;
+                        mm_any |= mm[k];
+                        nn[k] = (pass & fl) << 7;
+                        nn_any |= nn[k];
                     }
                 }
-                B += nq;
+                if (mm_any && !(sh.ablate & 32u)) {                                     // counted bases that are not the expected letter:
+                    #pragma unroll                                                      // only the lanes that hold one loop over their set bits
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t r = mm[k];
+                        while (r) {
+                            const uint32_t b = (uint32_t)__ffs((int)r) - 1u;            // 0, 8, 16 or 24
+                            red_shared_add(ac[k] + (PLANE_A + ((xs[k] >> b) & 3u)) * (uint32_t)TILE, 1u << b);
+                            r &= r - 1u;
+                        }
+                    }
+                }
+                if (nn_any & 0x80808080u) {                                             // rare: counted non-ACGT bases
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t n7 = nn[k] & 0x80808080u;
+                        if (n7) red_shared_add(ac[k] + PLANE_N * (uint32_t)TILE, n7 >> 7);
+                    }
+                }
             }
-            if (B != B_end) atomicExch(err_flag, 2);                            // quads no segment owns
         }
-        consumer_sync<CONSUMERS>();
-
-        // ---- 2. exceptions: the listed pieces
-        {
-            uint32_t n_listed = *list_n; if (n_listed > L.list_cap) n_listed = L.list_cap;
-            for (uint32_t li = tid; li < n_listed; li += CONSUMERS) {
-                const uint2 ent = s_list[li];
-                exceptions(ent.x & 0xffffu, (int32_t)((ent.x >> 16) & 0x7fffu), ent.y, (ent.x >> 31) != 0u);
-            }
-        }
-
-        // the stage is not needed any more (the depth pass works on the buckets): every warp hands it back on its own, so the
-        // copies of the chunk after next run while the depth pass, the barrier and the copy of the counts are still under way
         fence_proxy_async();                // this thread's writes to the stage are ordered before the copies that refill it
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + st);
-
-        // ---- 3. depth: a thread owns one 32-position word of the tile and a share of its bucket
-        if (m && !(sh.ablate & ABL_DEPTH)) {
-            // SL lanes share a word: the largest power of two that still gives every word a slot
-            const uint32_t per_warp = (nw + NWARPS - 1u) / NWARPS;                  // words a warp must hold
-            const uint32_t wpw_log = per_warp > 1u ? 32u - (uint32_t)__clz((int)(per_warp - 1u)) : 0u, sl_log = 5u - wpw_log;
-            const uint32_t SL = 1u << sl_log, nslots = NWARPS << wpw_log;
-            const uint32_t slot = (warp << wpw_log) + (lane >> sl_log);
-            const uint32_t blk = slot / nw, wi = slot - blk * nw, nblk = (nslots - 1u - wi) / nw + 1u;
-            const uint32_t sub = blk * SL + (lane & (SL - 1u)), nsub = nblk * SL;
-            uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            uint32_t n = fill[(uint32_t)w_lo + wi]; if (n > cap) n = cap;
-            const uint32_t* bk = s_bucket + wi * cap;
-            for (uint32_t e = sub; e < n; e += 2u * nsub) {                         // two entries per step
-                const uint32_t ma = bk[e], mb = e + nsub < n ? bk[e + nsub] : 0u;
-                csa_add(c, ma); csa_add(c, mb);
-            }
-            __syncwarp();
-            // the SL lanes of a word add their counters, then each expands its share of the word's eight quads
-            const bool hi_any = __any_sync(0xffffffffu, (c[4] | c[5] | c[6] | c[7]) != 0u);
-            const uint32_t a_d = a_c + 32u * ((uint32_t)w_lo + wi);
-            if (!hi_any && sl_log <= 2u) {
-                for (uint32_t off = 1; off < SL; off <<= 1) csa_combine<6>(c, off);
-                for (uint32_t qi = lane & (SL - 1u); qi < 8u; qi += SL) { const uint32_t v = csa_quad_lanes<6>(c, qi); if (v) red_shared_add(a_d + 4u * qi, v); }
-            } else {
-                for (uint32_t off = 1; off < SL; off <<= 1) csa_combine<8>(c, off);
-                for (uint32_t qi = lane & (SL - 1u); qi < 8u; qi += SL) { const uint32_t v = csa_quad_lanes<8>(c, qi); if (v) red_shared_add(a_d + 4u * qi, v); }
-            }
-        }
         consumer_sync<CONSUMERS>();
+        if (tid == 0) mbar_arrive(empty + st);
 
         // ---- 4. counts of the chunk
         if (HAS_WIDE && (flags & CHUNK_WIDE)) {
@@ -1091,7 +899,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                         acc[c][k][0] = acc[c][k][1] = 0;
                     }
             }
-        } else if ((flags & CHUNK_LAST) && !(sh.ablate & ABL_STORE)) {
+        } else if ((flags & CHUNK_LAST) && !(sh.ablate & 8u)) {
             uint4* cnt4 = reinterpret_cast<uint4*>(s_cnt);
             uint4* dst = reinterpret_cast<uint4*>(tiles + (size_t)item * SLOT_BYTES);
             for (uint32_t i = tid; i < (uint32_t)(N_PLANES * TILE / 16); i += CONSUMERS) {
@@ -1100,8 +908,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
                 dst[i] = w;
             }
         }
-        // Warps that are through start the next chunk while slower ones still copy counts out: step 1 writes the segment records,
-        // the buckets and the list (none of which a copy touches), and the counters are next written behind the next chunk's barrier.
+        // no barrier here: the next chunk touches the counters again only after its own barriers
     }
 }
 
@@ -1403,7 +1210,7 @@ __global__ void text_tiles_kernel(const uint64_t* __restrict__ acgt, const uint1
 // chunk is prefix-summed independently by one CTA: no carries between CTAs, one pass over HBM.
 // ------------------------------------------------------------------------------------------------
 constexpr int COV_CHUNK = 4096;
-constexpr int COV_THREADS = 1024;
+constexpr int COV_THREADS = 256;              // x 16 positions per thread = one chunk
 constexpr int COV_MAX_BINS = 1024;
 
 __global__ void __launch_bounds__(256)
@@ -1429,7 +1236,10 @@ cov_scan_kernel(const int32_t* __restrict__ diff, const uint32_t* __restrict__ c
                 const uint32_t* __restrict__ contig_len, uint32_t max_cov, unsigned long long* __restrict__ cov_sum,
                 unsigned long long* __restrict__ hist /*[n_contigs][max_cov+1]*/)
 {
-    __shared__ int32_t s_warp[32];
+    // 256 threads x 16 consecutive positions: many small CTAs per SM (the scan needs two barriers, and a CTA of 1024
+    // threads spent most of its life in them), four 16-byte loads in flight per thread
+    static_assert(COV_THREADS * 16 == COV_CHUNK, "a CTA scans one chunk");
+    __shared__ int32_t s_warp[COV_THREADS / 32];
     __shared__ uint32_t s_hist[COV_MAX_BINS];
     __shared__ unsigned long long s_sum;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1438,31 +1248,30 @@ cov_scan_kernel(const int32_t* __restrict__ diff, const uint32_t* __restrict__ c
     const uint32_t len = contig_len[k];
     for (uint32_t i = tid; i <= max_cov; i += COV_THREADS) s_hist[i] = 0;
     if (tid == 0) s_sum = 0;
-    const int4 v = reinterpret_cast<const int4*>(diff + (size_t)blockIdx.x * COV_CHUNK)[tid];
-    int32_t c0 = v.x, c1 = c0 + v.y, c2 = c1 + v.z, c3 = c2 + v.w;
-    int32_t incl = c3;
+    const int4* src = reinterpret_cast<const int4*>(diff + (size_t)blockIdx.x * COV_CHUNK) + 4 * tid;
+    const int4 v[4] = {src[0], src[1], src[2], src[3]};
+    int32_t c[16];
+    int32_t run = 0;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) { c[4 * i] = run += v[i].x; c[4 * i + 1] = run += v[i].y; c[4 * i + 2] = run += v[i].z; c[4 * i + 3] = run += v[i].w; }
+    int32_t incl = run;
     #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
-        int32_t w = s_warp[lane], wi = w;
-        #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int32_t o = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += o; }
-        s_warp[lane] = wi - w;
-    }
-    __syncthreads();
-    const int32_t base = s_warp[warp] + incl - c3;
-    int32_t cv[4] = {base + c0, base + c1, base + c2, base + c3};
+    int32_t base = incl - run;
+    #pragma unroll
+    for (int w = 0; w < COV_THREADS / 32; ++w) if ((uint32_t)w < warp) base += s_warp[w];
     unsigned long long local = 0;
     #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t p = first + tid * 4 + j;
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t p = first + tid * 16 + j;
         const bool valid = p < len;
+        const int32_t cv = base + c[j];
         // negative coverage cannot occur for blocks that satisfy the ABI contract (beg < end)
-        uint32_t bin = cv[j] < 0 ? 0u : ((uint32_t)cv[j] > max_cov ? max_cov : (uint32_t)cv[j]);
+        uint32_t bin = cv < 0 ? 0u : ((uint32_t)cv > max_cov ? max_cov : (uint32_t)cv);
         if (!valid) bin = 0xffffffffu;
-        else local += (unsigned long long)(cv[j] < 0 ? 0 : cv[j]);
+        else local += (unsigned long long)(cv < 0 ? 0 : cv);
         const uint32_t peers = __match_any_sync(0xffffffffu, bin);
         if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[bin], (uint32_t)__popc(peers));
     }

@@ -54,7 +54,6 @@ struct msnv_ctx {
     uint64_t gen = 0;                   // counts msnv_window_begin calls: pool entries unused for a while are freed
     uint8_t* d_ref = nullptr;
     uint8_t* d_expect = nullptr;        // expected letter per position (derived from d_ref)
-    uint8_t* d_expect2 = nullptr;       // the same, 2 bits per position in the pileup kernel's geometry (EXP_BYTES per tile)
 
     // ---- work buffers (grown on demand, kept across windows and shards)
     Item* d_items = nullptr;        uint64_t cap_items = 0;
@@ -67,6 +66,7 @@ struct msnv_ctx {
     uint2* d_range_cache = nullptr;   uint64_t cap_range = 0;
     uint32_t* d_bitmap = nullptr;     uint64_t cap_bitmap = 0;
     uint32_t* d_scalar = nullptr;   int* d_err = nullptr;
+    uint32_t* d_fix_list = nullptr;   uint64_t cap_fix_list = 0;        // samples with mate links
     // what msnv_shard_counts can still look at: the last range of the last run
     uint32_t last_slot = 0, last_item0 = 0, last_ta = 0, last_tb = 0;
 
@@ -78,6 +78,11 @@ struct msnv_ctx {
     uint16_t *h_hit_cov = nullptr, *h_hit_allele = nullptr;
     uint32_t* h_scalar = nullptr;   // pinned, 8 words
 
+    // coverage pass: work buffers grown on demand and kept (one call per BAM, hundreds of calls per job)
+    int32_t* d_cov_diff = nullptr; uint64_t cap_cov_diff = 0;
+    uint32_t* d_cov_beg = nullptr; uint32_t* d_cov_end = nullptr; uint64_t cap_cov_blocks = 0;
+    uint32_t* d_cov_meta = nullptr; uint64_t cap_cov_meta = 0;          // chunk0 | chunk_contig | contig_len | blk_off (as 2 words each)
+    unsigned long long* d_cov_out = nullptr; uint64_t cap_cov_out = 0;  // cov_sum | hist
     cudaEvent_t ev[8] = {};
     msnv_timings tm = {};
 };
@@ -229,8 +234,9 @@ uint64_t tile_budget_slots(msnv_ctx* ctx)
         size_t fr = 0, tot = 0;
         if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); fr = (size_t)8 << 30; }
         fr += (size_t)ctx->cap_tile_slots * SLOT_BYTES;        // what the buffer holds already is ours to use
+        // the called positions of a range need buffers too (10 bytes per hit and sample): a third of what is free stays for them
         const size_t reserve = (size_t)2 << 30;
-        budget = fr > 2 * reserve ? fr - reserve : fr / 2;
+        budget = fr > 3 * reserve ? (fr - reserve) / 3 * 2 : fr / 2;
     }
     return budget / SLOT_BYTES;
 }
@@ -281,8 +287,6 @@ static PileupShape choose_pileup_shape(uint64_t n_reads, uint64_t n_bases, uint6
     sh.has_fix = has_fix ? 1u : 0u;
     sh.wait_hint_ns = getenv("MSNV_WAIT_HINT_NS") ? (uint32_t)atoi(getenv("MSNV_WAIT_HINT_NS")) : 0u;
     sh.ablate = getenv("MSNV_ABLATE") ? (uint32_t)atoi(getenv("MSNV_ABLATE")) : 0u;
-    sh.n_stages = 2;
-    if (const char* e = getenv("MSNV_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= PL_STAGES_MAX) sh.n_stages = (uint32_t)v; }
     uint32_t mr = deep ? (max_ctas <= 3 ? NARROW_MAX_READS : 96u) : (uint32_t)(reads_per_item * 1.3 + 24.0);
     if (const char* e = getenv("MSNV_MAX_READS")) mr = (uint32_t)atoi(e);
     if (mr < 16) mr = 16;
@@ -399,7 +403,7 @@ static int launch_pileup(msnv_ctx* ctx, const msnv_ctx::Window& w, uint32_t a, u
     int ctas = 1;
     bool has_fix = false;
     for (const SampleDev& sd : w.h_samples) has_fix = has_fix || sd.fix;
-    const PileupShape sh = choose_pileup_shape(w.n_reads, w.n_bases, w.n_segs, n_items_window, item_reads, has_fix, consumers == 256 ? 2 : 4, ctas);   // register-bound CTA counts
+    const PileupShape sh = choose_pileup_shape(w.n_reads, w.n_bases, w.n_segs, n_items_window, item_reads, has_fix, consumers == 256 ? 3 : 4, ctas);   // register-bound CTA counts
     const size_t smem = pileup_smem_layout(sh).total;
     const bool has_wide = item_reads_max > NARROW_MAX_READS;
     const int threads = consumers + 32;
@@ -414,7 +418,7 @@ static int launch_pileup(msnv_ctx* ctx, const msnv_ctx::Window& w, uint32_t a, u
     if (fit < ctas) ctas = fit;
     uint64_t grid = (uint64_t)ctas * (uint64_t)ctx->sm_count;
     if (grid > n) grid = n;
-    MSNV_PILEUP_DISPATCH((K<<<(unsigned)grid, threads, smem, ctx->stream>>>(w.d_samples, ctx->d_items + a, n, sh, ctx->d_expect2, ctx->d_tiles, ctx->d_err)));
+    MSNV_PILEUP_DISPATCH((K<<<(unsigned)grid, threads, smem, ctx->stream>>>(w.d_samples, ctx->d_items + a, n, sh, ctx->d_expect, ctx->d_tiles, ctx->d_err)));
 #undef MSNV_PILEUP_DISPATCH
     ++launches;
     if (getenv("MSNV_VERBOSE"))
@@ -448,15 +452,26 @@ static int run_window(msnv_ctx* ctx, uint32_t slot, const msnv_call_params* prm,
     if (ensure_window_buffers(ctx, nt)) return MSNV_E_CUDA;
 
     // ---- mate overlap: verdicts per quad for the samples that have pairs (read by the pileup kernel)
-    uint64_t max_reads = 0; bool any_fix = false;
-    for (uint32_t s = 0; s < S; ++s) { if (w.h_samples[s].n_reads > max_reads) max_reads = w.h_samples[s].n_reads; any_fix = any_fix || w.h_samples[s].fix; }
+    uint64_t max_reads = 0, max_fix_reads = 0;
+    std::vector<uint32_t> fix_samples;
+    for (uint32_t s = 0; s < S; ++s) {
+        if (w.h_samples[s].n_reads > max_reads) max_reads = w.h_samples[s].n_reads;
+        if (w.h_samples[s].fix) { fix_samples.push_back(s); if (w.h_samples[s].n_reads > max_fix_reads) max_fix_reads = w.h_samples[s].n_reads; }
+    }
     unsigned gx = (unsigned)((max_reads + 256 * 8 - 1) / (256 * 8)); if (gx < 1) gx = 1; if (gx > 1024) gx = 1024;
     cudaEvent_t ev_m0 = ctx->ev[2], ev_m1 = ctx->ev[3];
     CU(cudaEventRecord(ev_m0, st));
-    if (any_fix) {
-        unsigned gm = (unsigned)((max_reads * 8 + 255) / 256); if (gm < 1) gm = 1; if (gm > 2048) gm = 2048;     // eight lanes per pair
-        fix_clear_kernel<<<dim3(gx, S), 256, 0, st>>>(w.d_samples);
-        mate_kernel<<<dim3(gm, S), 256, 0, st>>>(w.d_samples);
+    if (!fix_samples.empty()) {
+        if (fix_samples.size() > ctx->cap_fix_list) {
+            if (grow(ctx, ctx->d_fix_list, fix_samples.size() + 64)) return MSNV_E_CUDA;
+            ctx->cap_fix_list = fix_samples.size() + 64;
+        }
+        // (pageable source: the copy is staged before the call returns)
+        CU(cudaMemcpyAsync(ctx->d_fix_list, fix_samples.data(), fix_samples.size() * 4, cudaMemcpyHostToDevice, st));
+        unsigned gc = (unsigned)((max_fix_reads * 2 + 255) / 256); if (gc < 1) gc = 1; if (gc > 1024) gc = 1024;          // ~27 bytes per read, 16 per thread
+        unsigned gm = (unsigned)((max_fix_reads + 255) / 256); if (gm < 1) gm = 1; if (gm > 4096) gm = 4096;              // a warp per 32 reads
+        fix_clear_kernel<<<dim3(gc, (unsigned)fix_samples.size()), 256, 0, st>>>(w.d_samples, ctx->d_fix_list);
+        mate_kernel<<<dim3(gm, (unsigned)fix_samples.size()), 256, 0, st>>>(w.d_samples, ctx->d_fix_list);
         launches += 2;
     }
     CU(cudaEventRecord(ev_m1, st));
@@ -464,8 +479,7 @@ static int run_window(msnv_ctx* ctx, uint32_t slot, const msnv_call_params* prm,
     CU(cudaEventRecord(ctx->ev[0], st));
     // expected letter per position of the window (msnv_shard_mask_position may have changed the reference since the last run)
     expect_kernel<<<(nt * TILE + 255) / 256, 256, 0, st>>>(ctx->d_ref + (size_t)w.t0 * TILE, nt * TILE, ctx->d_expect + (size_t)w.t0 * TILE);
-    expect2_kernel<<<(unsigned)(((uint64_t)nt * EXP_BYTES + 255) / 256), 256, 0, st>>>(ctx->d_expect + (size_t)w.t0 * TILE, nt, ctx->d_expect2 + (size_t)w.t0 * EXP_BYTES);
-    launches += 2;
+    ++launches;
     // ---- index
     const uint64_t n_pairs_idx = (uint64_t)nt * S;
     const uint64_t n_blocks = (n_pairs_idx + 255) / 256;
@@ -618,9 +632,10 @@ void msnv_destroy(msnv_ctx* ctx)
     drop_pool(ctx);
     for (auto& sl : ctx->slabs) cudaFree(sl.base);
     cudaFree(ctx->d_ref);
-    cudaFree(ctx->d_items); cudaFree(ctx->d_tiles); cudaFree(ctx->d_expect); cudaFree(ctx->d_expect2); cudaFree(ctx->d_text_acgt); cudaFree(ctx->d_text_match);
+    cudaFree(ctx->d_items); cudaFree(ctx->d_tiles); cudaFree(ctx->d_expect); cudaFree(ctx->d_text_acgt); cudaFree(ctx->d_text_match);
     cudaFree(ctx->d_tile_begin); cudaFree(ctx->d_tile_hits); cudaFree(ctx->d_flags); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_range_cache); cudaFree(ctx->d_bitmap);
-    cudaFree(ctx->d_scalar); cudaFree(ctx->d_err);
+    cudaFree(ctx->d_scalar); cudaFree(ctx->d_err); cudaFree(ctx->d_fix_list);
+    cudaFree(ctx->d_cov_diff); cudaFree(ctx->d_cov_beg); cudaFree(ctx->d_cov_end); cudaFree(ctx->d_cov_meta); cudaFree(ctx->d_cov_out);
     cudaFree(ctx->d_hit_pos); cudaFree(ctx->d_hit_total); cudaFree(ctx->d_hit_pop); cudaFree(ctx->d_hit_ind);
     cudaFree(ctx->d_hit_cov); cudaFree(ctx->d_hit_allele);
     cudaFreeHost(ctx->h_hit_pos); cudaFreeHost(ctx->h_hit_total); cudaFreeHost(ctx->h_hit_pop); cudaFreeHost(ctx->h_hit_ind);
@@ -655,11 +670,10 @@ int msnv_shard_begin(msnv_ctx* ctx, uint32_t n_samples, uint32_t n_positions, co
     for (auto& w : ctx->win) release_window(ctx, w);
     ctx->S = n_samples; ctx->P = n_positions; ctx->n_tiles = n_positions / TILE;
     ctx->has_run = false;
-    cudaFree(ctx->d_ref); cudaFree(ctx->d_expect); cudaFree(ctx->d_expect2);
-    ctx->d_ref = nullptr; ctx->d_expect = nullptr; ctx->d_expect2 = nullptr;
+    cudaFree(ctx->d_ref); cudaFree(ctx->d_expect);
+    ctx->d_ref = nullptr; ctx->d_expect = nullptr;
     CU(cudaMalloc((void**)&ctx->d_ref, n_positions));
     CU(cudaMalloc((void**)&ctx->d_expect, n_positions));
-    CU(cudaMalloc((void**)&ctx->d_expect2, (size_t)(n_positions / TILE) * EXP_BYTES));
     CU(cudaMemcpyAsync(ctx->d_ref, ref, n_positions, cudaMemcpyHostToDevice, ctx->stream));
     ctx->open = true;
     // the whole shard as one window in slot 0 until msnv_window_begin says otherwise
@@ -708,7 +722,7 @@ int msnv_window_add_sample(msnv_ctx* ctx, uint32_t slot, uint32_t sample, const 
     for (size_t i = 0; i < n && !has_mates; ++i) has_mates = r->mate[i] >= 0;
     const size_t o_pos = take(n * 4), o_sgo = take(n1 * 4), o_q4 = take(n1 * 4), o_mate = take(n * 4),
                  o_sp = take(n_seg * 4), o_sl = take(n_seg * 2), o_seq = take(n_q4), o_qual = take(n_q4 * 4),
-                 o_fix = has_mates ? take(fix_words(n_q4) * 4) : 0;       // verdicts of the mate-overlap rule, rebuilt by every run
+                 o_fix = has_mates ? take(n_q4) : 0;       // verdicts of the mate-overlap rule, rebuilt by every run
     uint8_t* base = (uint8_t*)take_block(ctx, w, off);
     if (!base) return fail(ctx, MSNV_E_NOMEM, "sample %u: cannot allocate %zu bytes of device memory; process the shard in smaller windows (msnv_window_begin) or smaller genome bins (metaSNV.py --n_splits)", sample, off);
     cudaStream_t st = ctx->copy_stream;
@@ -726,7 +740,7 @@ int msnv_window_add_sample(msnv_ctx* ctx, uint32_t slot, uint32_t sample, const 
     d.mate = (const int32_t*)(base + o_mate);
     d.seg_pos = (const int32_t*)(base + o_sp);   d.seg_len = (const uint16_t*)(base + o_sl);
     d.seq2 = base + o_seq;                      d.qual = base + o_qual;
-    d.fix = has_mates ? (uint32_t*)(base + o_fix) : nullptr;
+    d.fix = has_mates ? base + o_fix : nullptr;
     d.n_reads = r->n_reads; d.max_span = r->max_span ? r->max_span : 1;
     w.n_reads += n; w.n_bases += 4ull * n_q4; w.n_segs += n_seg;
     uint64_t n_aligned = 0;
@@ -935,7 +949,7 @@ int msnv_window_synth(msnv_ctx* ctx, uint32_t slot, const msnv_synth_desc* d, ui
         const uint32_t q_slots = q4 + 4;          // upper bound of the quads of one read (two segments)
         o = 0;
         const size_t o_sp = take((size_t)n_seg * 4), o_sl = take((size_t)n_seg * 2), o_seq = take(n_q4), o_qual = take(n_q4 * 4),
-                     o_fix = n_mated ? take(fix_words(n_q4) * 4) : 0;
+                     o_fix = n_mated ? take(n_q4) : 0;
         uint8_t* data = (uint8_t*)take_block(ctx, w, o);
         if (!data) return fail(ctx, MSNV_E_NOMEM, "msnv_shard_synth: out of device memory (sample %u)", s);
         synth_fill_kernel<<<(unsigned)((n * q_slots + 255) / 256), 256, 0, st>>>(m, (int)s, paired, d_blocks, d_frag0, (uint32_t)nb, (uint32_t)n, q_slots,
@@ -955,7 +969,7 @@ int msnv_window_synth(msnv_ctx* ctx, uint32_t slot, const msnv_synth_desc* d, ui
         sd.mate = (const int32_t*)(meta + o_mate);
         sd.seg_pos = (const int32_t*)(data + o_sp);  sd.seg_len = (const uint16_t*)(data + o_sl);
         sd.seq2 = data + o_seq;                      sd.qual = data + o_qual;
-        sd.fix = n_mated ? (uint32_t*)(data + o_fix) : nullptr;
+        sd.fix = n_mated ? data + o_fix : nullptr;
         sd.n_reads = (uint32_t)n; sd.max_span = L + 3;
         w.n_reads += n; w.n_bases += 4ull * n_q4; w.n_segs += n_seg;
         w.sizes[s] = msnv_sample_sizes{(uint32_t)n, (uint32_t)n_mated, L + 3, 0, (uint64_t)n_seg, (uint64_t)n_q4, (uint64_t)n_aligned};
@@ -1074,31 +1088,29 @@ int msnv_cov_run(msnv_ctx* ctx, const msnv_cov_blocks* b, uint32_t max_cov, uint
     chunk_contig.resize(n_chunks);
     for (uint32_t k = 0; k < K; ++k) for (uint32_t c = chunk0[k]; c < chunk0[k + 1]; ++c) chunk_contig[c] = k;
 
-    int32_t* d_diff = nullptr; uint32_t *d_beg = nullptr, *d_end = nullptr, *d_chunk0 = nullptr, *d_cc = nullptr, *d_len = nullptr;
-    uint64_t* d_off = nullptr; unsigned long long *d_sum = nullptr, *d_hist = nullptr;
     int rc = MSNV_OK;
-    auto cleanup = [&]() {
-        cudaFree(d_diff); cudaFree(d_beg); cudaFree(d_end); cudaFree(d_chunk0); cudaFree(d_cc); cudaFree(d_len);
-        cudaFree(d_off); cudaFree(d_sum); cudaFree(d_hist);
-    };
 #define CUC(call)                                                                                                   \
     do {                                                                                                            \
         cudaError_t e_ = (call);                                                                                    \
-        if (e_ != cudaSuccess) { rc = fail(ctx, MSNV_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); cleanup(); return rc; } \
+        if (e_ != cudaSuccess) { rc = fail(ctx, MSNV_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return rc; } \
     } while (0)
     const size_t hist_n = (size_t)K * (max_cov + 1);
-    CUC(cudaMalloc((void**)&d_diff, n_chunks * COV_CHUNK * 4));
-    CUC(cudaMalloc((void**)&d_beg, (n_blocks ? n_blocks : 1) * 4));
-    CUC(cudaMalloc((void**)&d_end, (n_blocks ? n_blocks : 1) * 4));
-    CUC(cudaMalloc((void**)&d_chunk0, ((size_t)K + 1) * 4));
-    CUC(cudaMalloc((void**)&d_cc, n_chunks * 4));
-    CUC(cudaMalloc((void**)&d_len, (size_t)K * 4));
-    CUC(cudaMalloc((void**)&d_off, ((size_t)K + 1) * 8));
-    CUC(cudaMalloc((void**)&d_sum, (size_t)K * 8));
-    CUC(cudaMalloc((void**)&d_hist, hist_n * 8));
-    CUC(cudaMemsetAsync(d_diff, 0, n_chunks * COV_CHUNK * 4, st));
-    CUC(cudaMemsetAsync(d_sum, 0, (size_t)K * 8, st));
-    CUC(cudaMemsetAsync(d_hist, 0, hist_n * 8, st));
+    const uint64_t n_diff = n_chunks * COV_CHUNK, n_meta = ((uint64_t)K + 1) + n_chunks + K + 2 * ((uint64_t)K + 1), n_out = K + hist_n;
+    if (n_diff > ctx->cap_cov_diff) { if (grow(ctx, ctx->d_cov_diff, n_diff + n_diff / 8)) return MSNV_E_CUDA; ctx->cap_cov_diff = n_diff + n_diff / 8; }
+    if (n_blocks > ctx->cap_cov_blocks) {
+        const uint64_t cap = n_blocks + n_blocks / 8 + 1024;
+        if (grow(ctx, ctx->d_cov_beg, cap) || grow(ctx, ctx->d_cov_end, cap)) return MSNV_E_CUDA;
+        ctx->cap_cov_blocks = cap;
+    }
+    if (n_meta > ctx->cap_cov_meta) { if (grow(ctx, ctx->d_cov_meta, n_meta + 1024)) return MSNV_E_CUDA; ctx->cap_cov_meta = n_meta + 1024; }
+    if (n_out > ctx->cap_cov_out) { if (grow(ctx, ctx->d_cov_out, n_out + 1024)) return MSNV_E_CUDA; ctx->cap_cov_out = n_out + 1024; }
+    int32_t* d_diff = ctx->d_cov_diff;
+    uint32_t *d_beg = ctx->d_cov_beg, *d_end = ctx->d_cov_end;
+    uint32_t *d_chunk0 = ctx->d_cov_meta, *d_cc = d_chunk0 + (K + 1), *d_len = d_cc + n_chunks;
+    uint64_t* d_off = reinterpret_cast<uint64_t*>(ctx->d_cov_meta + (((uint64_t)K + 1) + n_chunks + K + 1) / 2 * 2);     // 8-byte aligned
+    unsigned long long *d_sum = ctx->d_cov_out, *d_hist = d_sum + K;
+    CUC(cudaMemsetAsync(d_diff, 0, n_diff * 4, st));
+    CUC(cudaMemsetAsync(d_sum, 0, n_out * 8, st));
     if (n_blocks) {
         CUC(cudaMemcpyAsync(d_beg, b->beg, n_blocks * 4, cudaMemcpyHostToDevice, st));
         CUC(cudaMemcpyAsync(d_end, b->end, n_blocks * 4, cudaMemcpyHostToDevice, st));
@@ -1107,15 +1119,22 @@ int msnv_cov_run(msnv_ctx* ctx, const msnv_cov_blocks* b, uint32_t max_cov, uint
     CUC(cudaMemcpyAsync(d_cc, chunk_contig.data(), n_chunks * 4, cudaMemcpyHostToDevice, st));
     CUC(cudaMemcpyAsync(d_len, b->contig_len, (size_t)K * 4, cudaMemcpyHostToDevice, st));
     CUC(cudaMemcpyAsync(d_off, b->blk_off, ((size_t)K + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUC(cudaEventRecord(ctx->ev[0], st));
     if (n_blocks)
         cov_scatter_kernel<<<(unsigned)((n_blocks + 255) / 256), 256, 0, st>>>(d_beg, d_end, d_off, d_chunk0, K, n_blocks, d_diff);
+    CUC(cudaEventRecord(ctx->ev[1], st));
     cov_scan_kernel<<<(unsigned)n_chunks, COV_THREADS, 0, st>>>(d_diff, d_cc, d_chunk0, d_len, max_cov, d_sum, d_hist);
+    CUC(cudaEventRecord(ctx->ev[2], st));
     CUC(cudaMemcpyAsync(cov_sum, d_sum, (size_t)K * 8, cudaMemcpyDeviceToHost, st));
     CUC(cudaMemcpyAsync(hist, d_hist, hist_n * 8, cudaMemcpyDeviceToHost, st));
     CUC(cudaStreamSynchronize(st));
     CUC(cudaGetLastError());
+    ctx->tm = msnv_timings{};
+    cudaEventElapsedTime(&ctx->tm.ms_cov_scatter, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->tm.ms_cov_scan, ctx->ev[1], ctx->ev[2]);
+    ctx->tm.cov_blocks = n_blocks; ctx->tm.kernel_launches = n_blocks ? 2u : 1u;
+    for (uint32_t k = 0; k < K; ++k) ctx->tm.cov_positions += b->contig_len[k];
 #undef CUC
-    cleanup();
     return rc;
 }
 

@@ -7,7 +7,12 @@
  * PARITY UNPINNED: samtools/htslib is an un-vendored, un-pinned external dependency of the
  * reference (README.md:19, DEVELOPER.md:46, .github/workflows/main.yml:33-34) and is absent from
  * this image, and the reference holds no test vectors for it. This
- * file restates the published algorithm of samtools/htslib >= 1.9 (bam_plcmd.c: mplp_func,
+ * file restates the published algorithm of samtools 1.9 / htslib 1.9 (released 2018-07-18; the
+ * first release with `-d 8000` per file, Annex A; the pileup iterator and the overlap rule are
+ * the same in 1.10). Whether later releases changed the overlap rule's handling of two mates that
+ * disagree with EQUAL qualities (here, as in 1.9: the earlier read keeps 0.8 x its quality, the
+ * later one drops to 0) could not be checked in this image: treat that case as version dependent.
+ * The restated functions (bam_plcmd.c: mplp_func,
  * mpileup, pileup_seq; htslib sam.c: bam_plp_push / bam_plp_next / bam_plp_auto / bam_mplp_auto,
  * resolve_cigar2, overlap_push / tweak_overlap_quality) as summarised in SURVEY.md Annex A.
  * It is written as htslib writes it -- a per-file buffered pileup iterator that renders text --

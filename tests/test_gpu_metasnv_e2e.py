@@ -2,6 +2,7 @@
 oracle/_ref/metaSNV) drives the product binaries exactly as it drives its own: qaCompute per BAM, `samtools view -H`,
 createOptimumSplit, one `samtools mpileup | snpCall` pipe per split. Every file of the project directory must be
 byte-identical to the run with the oracle's binaries."""
+import json
 import os
 import subprocess
 import sys
@@ -20,20 +21,36 @@ def test_metasnv_py_drives_the_gpu_path(threads, splits, ann, built, tmp_path):
         pytest.skip("oracle/_ref/metaSNV not staged (needs /root/reference at build time)")
     data = str(tmp_path / "data")
     if ann:
-        H.synth(data, "c5", 0.002, 5, annotation=True)
+        st = H.synth(data, "c5", 0.002, 5, annotation=True)
     else:
-        H.synth(data, "c1", 0.03, 9)
+        st = H.synth(data, "c1", 0.03, 9)
     lst, ref = os.path.join(data, "all_samples"), os.path.join(data, "ref.fa")
     db_ann = os.path.join(data, "annotation.txt") if ann else None
     outs = {}
     for mode in ("oracle", "gpu"):
         script, env = H.stage_metasnv(str(tmp_path / ("tree_" + mode)), mode)
         out = str(tmp_path / "proj")          # same project name in both runs: it appears in file names
+        perf = str(tmp_path / ("perf_" + mode + ".jsonl"))
+        env["MSNV_PERF_JSON"] = perf
         r = H.run_metasnv(script, env, out, lst, ref, threads=threads, n_splits=splits, db_ann=db_ann)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         keep = str(tmp_path / ("proj_" + mode))
         os.rename(out, keep)
         outs[mode] = H.tree_files(keep)
+    # the product's coverage pass leaves one extra file per BAM: where every contig starts in it (cov/<bam>.cov.tidx) ...
+    tidx = [f for f in outs["gpu"] if f.endswith(".tidx")]
+    assert len(tidx) == sum(1 for _ in open(lst))
+    for f in tidx:
+        del outs["gpu"][f]
+    # ... which lets every split's snpCall seek to its contigs instead of inflating whole files (metaSNV.py:157-165)
+    runs = [json.loads(l) for l in open(str(tmp_path / "perf_gpu.jsonl"))]
+    calls = [x for x in runs if x.get("tool") == "snpCall"]
+    assert len(calls) == splits
+    if splits > 1:
+        assert all(x["bams_read_through_index"] == x["samples"] for x in calls)
+        # every record is parsed by the one split that owns its contig (plus the record that ends a run), not by every split
+        n_records = st["reads"] + st["junk"] + st["unmapped"]
+        assert sum(x["records"] for x in calls) <= n_records + 2 * splits * calls[0]["samples"]
     assert sorted(outs["oracle"]) == sorted(outs["gpu"])
     assert any(f.startswith("snpCaller/called_SNPs") for f in outs["gpu"])
     n_lines = 0

@@ -69,6 +69,42 @@ def test_hand_written_case(built, tmp_path):
             _same(os.path.join(GOLDEN, "hand", "expected_%s.cov%s" % (s, ext)), o + ext)
 
 
+def test_hand_written_pairing_rules(built, tmp_path):
+    """tests/golden/hand/s5_rules.sam (supplementary read, unpaired later mate, the distant-mate exit, equal-quality
+    disagreement; expectations derived by hand in tests/test_oracle_cpu.py) through the product, whole and with a BED that
+    has two intervals on one contig."""
+    tmp = str(tmp_path)
+    bams = []
+    for s in ("s5_rules", "s2"):
+        out = os.path.join(tmp, s + ".bam")
+        subprocess.run([bin_path("msnv_synth"), "--sam", os.path.join(GOLDEN, "hand", s + ".sam"), "--bam", out], check=True)
+        bams.append(out)
+    open(os.path.join(tmp, "all_samples"), "w").write("\n".join(bams) + "\n")
+    os.symlink(os.path.join(GOLDEN, "hand", "ref.fa"), os.path.join(tmp, "ref.fa"))
+    for mode, bed in (("whole", None), ("bed", os.path.join(GOLDEN, "hand", "rules.bed"))):
+        o, g = os.path.join(tmp, "oracle_" + mode), os.path.join(tmp, "gpu_" + mode)
+        rc, err = H.run_oracle_snpcall(tmp, o, bed=bed, c=1, t=1)
+        assert rc == 0, err
+        rc, err = H.run_product_snpcall(tmp, g, bed=bed, c=1, t=1)
+        assert rc == 0, err
+        for ext in (".called", ".indiv"):
+            _same(o + ext, g + ext)
+        assert os.path.getsize(o + ".called") + os.path.getsize(o + ".indiv") > 0
+    # per-position counts of the first sample against the hand-derived pileup: position 27 of ctgB counts one C (the earlier mate), no A
+    dump = os.path.join(tmp, "counts.bin")
+    rc, err = H.run_product_snpcall(tmp, os.path.join(tmp, "gpu_counts"), c=1, t=1, env=dict(os.environ, MSNV_DUMP_COUNTS=dump))
+    assert rc == 0, err
+    hdr = open(dump + ".layout").read().split("\n")
+    S, P = int(hdr[0].split("\t")[0]), int(hdr[0].split("\t")[1])
+    off = {l.split("\t")[0]: int(l.split("\t")[1]) for l in hdr[1:] if l}
+    cnt = np.fromfile(dump, np.uint16).reshape(S, P, 5)
+    b = off["ctgB"]
+    assert cnt[0, b + 26].tolist() == [0, 1, 0, 0, 0]             # 27 (1-based): C from the earlier mate only
+    assert cnt[0, b + 5].tolist() == [0, 0, 0, 3, 0]              # 6: three T (supplementary + both p2 mates, never paired)
+    assert cnt[0, b + 12].tolist() == [0, 0, 0, 0, 0]             # 13: nothing
+    assert cnt[0, b + 30].tolist() == [1, 0, 0, 0, 0]             # 31: A from the later mate, behind the overlap
+
+
 # ---------------------------------------------------------------- live oracle on larger seeded inputs
 LIVE = [
     ("c1", 0.2, 40, {}, dict()),
@@ -215,3 +251,87 @@ def test_kernel_variants_give_identical_output(env, datasets, tmp_path):
         assert rc == 0, err
         for ext in (".called", ".indiv"):
             _same(os.path.join(GOLDEN, name, "unsplit" + ext), out + ext)
+
+
+# ---------------------------------------------------------------- the reference's own vectors through the product's classic mode
+_VECTORS = json.load(open(os.path.join(GOLDEN, "snpcall_vectors.json")))
+
+
+@pytest.mark.parametrize("case", _VECTORS, ids=[c["name"] for c in _VECTORS])
+def test_reference_vectors_through_classic_mode(case, built, tmp_path):
+    """tests/golden/snpcall_vectors.json (made by the unmodified reference build, SURVEY.md Annex E: token truncation at 10000
+    characters, lower-case reference skip, -p, no -i file, annotation, empty input) fed as mpileup TEXT to the product's snpCall:
+    host tokeniser (csrc/host/text_pileup.cc) + the GPU call / compaction / gather kernels. Cases the reference answers by
+    crashing (negative return codes: abort / segfault on malformed columns) are outside the contract."""
+    if case["rc"] != 0:
+        pytest.skip("the reference itself fails on this input (rc %d)" % case["rc"])
+    tmp = str(tmp_path)
+    for fn, txt in case.get("files", {}).items():
+        open(os.path.join(tmp, fn), "w").write(txt)
+    indiv = os.path.join(tmp, "indiv.txt")
+    args = [a if a != "@INDIV" else indiv for a in case["args"]]
+    r = subprocess.run([bin_path("snpCall")] + args, input=case["stdin"].encode(), capture_output=True, cwd=tmp)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    assert r.stdout.decode() == case["stdout"]
+    assert (open(indiv).read() if os.path.exists(indiv) else None) == case["indiv"]
+
+
+# ---------------------------------------------------------------- position windows through the product
+@pytest.mark.parametrize("preset,scale,samples,windows", [("c1", 0.1, 12, 5), ("c4", 0.005, 3, 4), ("c3", 0.0005, 10, 7)])
+def test_snpcall_in_windows_equals_oracle(preset, scale, samples, windows, datasets, tmp_path):
+    """snpCall cut into position windows (decoders resume from window to window, reads that straddle a boundary go to both,
+    uploads overlap decoding, two window slots on the device) writes the same bytes as the oracle's single pass - also when the
+    count planes of a window must be produced in several ranges of tiles (tiny tile budget)."""
+    data = datasets(preset, scale, samples)
+    bed = H.bed_header(data, os.path.join(data, "bed_header"))
+    for mode, b in (("unsplit", None), ("split", bed)):
+        o, g = str(tmp_path / ("oracle_" + mode)), str(tmp_path / ("gpu_" + mode))
+        rc, err = H.run_oracle_snpcall(data, o, bed=b)
+        assert rc == 0, err
+        perf = str(tmp_path / ("perf_" + mode))
+        env = dict(os.environ, MSNV_WINDOWS=str(windows), MSNV_TILE_BUDGET_MB="2", MSNV_PERF_JSON=perf)
+        rc, err = H.run_product_snpcall(data, g, bed=b, env=env)
+        assert rc == 0, err
+        for ext in (".called", ".indiv"):
+            _same(o + ext, g + ext)
+        assert json.loads(open(perf).readline())["windows"] > 1
+
+
+# ---------------------------------------------------------------- two splits on two GPUs (the shipped multi-GPU path)
+def test_two_splits_on_two_gpus(datasets, tmp_path):
+    """metaSNV.py's own sharding: one `samtools mpileup -l best_split_k | snpCall -i ...best_split_k` pipe per genome bin, started
+    at the same time; snpCall takes GPU k mod #GPUs from the name of its -i file. Needs two GPUs."""
+    from metasnv_b200 import abi
+    if abi.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import threading
+    data = datasets("c1", 0.1, 12)
+    beds = []
+    for k, line in enumerate(open(H.bed_header(data, os.path.join(data, "bed_header")))):
+        genome = line.split(".")[0]
+        p = str(tmp_path / ("best_split_%d" % (k % 2)))
+        open(p, "a").write(line)
+        if p not in beds:
+            beds.append(p)
+    res = {}
+
+    def one(k, bed):
+        perf = str(tmp_path / ("perf_%d" % k))
+        out = str(tmp_path / ("gpu.best_split_%d" % k))
+        ref = os.path.join(data, "ref.fa")
+        prod = [bin_path("samtools"), "mpileup", "-f", ref, "-l", bed, "-B", "-b", os.path.join(data, "all_samples")]
+        cons = [bin_path("snpCall"), "-f", ref, "-i", str(tmp_path / ("indiv_called.best_split_%d" % k)), "-c", "4", "-t", "4"]
+        res[k] = H._pipe(prod, cons, out, env=dict(os.environ, MSNV_PERF_JSON=perf)) + (json.loads(open(perf).readline()) if os.path.exists(perf) else {},)
+
+    th = [threading.Thread(target=one, args=(k, b)) for k, b in enumerate(beds)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for k, bed in enumerate(beds):
+        rc, err, perf = res[k]
+        assert rc == 0, err
+        assert perf["device"] == k % abi.device_count()
+        o = str(tmp_path / ("oracle_%d" % k))
+        rc, err = H.run_oracle_snpcall(data, o, bed=bed)
+        assert rc == 0, err
+        _same(o + ".called", str(tmp_path / ("gpu.best_split_%d" % k)))
+        _same(o + ".indiv", str(tmp_path / ("indiv_called.best_split_%d" % k)))

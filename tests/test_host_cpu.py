@@ -28,7 +28,7 @@ def test_abi_exports_every_declared_symbol(built):
     for n in sorted(names):
         assert hasattr(lib, n), "libmsnv_gpu.so does not export %s" % n
     lib.msnv_abi_version.restype = ctypes.c_int
-    assert lib.msnv_abi_version() == 4
+    assert lib.msnv_abi_version() == 5
 
 
 def test_abi_python_binding_matches_struct_sizes(built):
@@ -37,7 +37,7 @@ def test_abi_python_binding_matches_struct_sizes(built):
     assert ctypes.sizeof(abi.CallParams) == 16
     assert ctypes.sizeof(abi.Hits) == 8 + 6 * 8
     assert ctypes.sizeof(abi.CovBlocks) == 8 + 4 * 8
-    assert ctypes.sizeof(abi.Timings) == 7 * 4 + 4 + 3 * 8 + 4 * 4
+    assert ctypes.sizeof(abi.Timings) == 7 * 4 + 4 + 3 * 8 + 4 * 4 + 4 * 4 + 2 * 8
 
 
 def test_library_contains_sm100a_code_and_tma(built):

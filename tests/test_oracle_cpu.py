@@ -91,6 +91,33 @@ def test_mpileup_restatement_hand_case(built, tmp_path):
     assert b"<" in txt3
 
 
+def test_mpileup_restatement_pairing_rules(built, tmp_path):
+    """Hand-derived case for the per-read rules of SURVEY.md Annex A.1 / A.2 that the first hand case does not reach:
+    a supplementary read is kept; a later mate whose partner was filtered (duplicate) is never paired (mpos < pos: not
+    stored); a pair whose first mate claims a distant mate (|isize| >= 2 l_qseq and mpos >= its end) is not paired even
+    though the mates overlap; mates that disagree with EQUAL qualities: the earlier read keeps int(0.8 q), the later drops
+    to 0; a BED with two intervals on one contig."""
+    tmp = str(tmp_path)
+    lst = os.path.join(tmp, "list")
+    open(lst, "w").write("%s\n" % _bam_from_sam("s5_rules", tmp))
+    ref = os.path.join(GOLDEN, "hand", "ref.fa")
+    txt = subprocess.check_output([H.oracle_bin("mpileup_oracle"), "mpileup", "-f", ref, "-B", "-b", lst])
+    assert txt == open(os.path.join(GOLDEN, "hand", "expected_rules.pileup"), "rb").read()
+    ln = {l.split("\t")[1]: l for l in txt.decode().split("\n") if l}
+    assert ln["1"] == "ctgB\t1\tT\t2\t^].^].\tII"            # the supplementary read (0x800) is piled up like any other
+    assert ln["6"] == "ctgB\t6\tT\t3\t..,\tIII"               # p2: mate 1 says its mate is far away -> not paired -> both mates counted at 5..8
+    assert ln["11"] == "ctgB\t11\tG\t1\t,\tI"                 # p1 mate 1 is a duplicate: filtered; 13 and 14 have no line at all
+    assert "13" not in ln and "14" not in ln
+    assert ln["16"] == "ctgB\t16\tG\t1\t,\tI"                 # p1 mate 2 (mpos < pos, partner never stored): full quality
+    assert ln["26"] == "ctgB\t26\tC\t1\t.\tI"                 # p3 agree: 20 + 20 = 40 for the earlier mate, the later one drops out
+    assert ln["27"] == "ctgB\t27\tC\t1\t.\t1"                 # p3 disagree, equal qualities: the earlier mate keeps int(0.8 * 20) = 16
+    assert ln["31"] == "ctgB\t31\tA\t1\t,\t5"                 # behind the overlap the later mate counts again (no '^': its first column was 25)
+    bed = os.path.join(GOLDEN, "hand", "rules.bed")
+    txt = subprocess.check_output([H.oracle_bin("mpileup_oracle"), "mpileup", "-f", ref, "-l", bed, "-B", "-b", lst])
+    assert txt == open(os.path.join(GOLDEN, "hand", "expected_rules_bed.pileup"), "rb").read()
+    assert [l.split("\t")[1] for l in txt.decode().split("\n") if l] == ["3", "4", "5", "6", "21", "22", "23", "24"]     # BED is 0-based half open
+
+
 def test_view_header(built, tmp_path):
     bam = _bam_from_sam("s1", str(tmp_path))
     a = subprocess.check_output([H.oracle_bin("mpileup_oracle"), "view", "-H", bam])
