@@ -219,6 +219,7 @@ def e2e_from_bam(a, work, local, rank):
             raise RuntimeError("snpCall failed: " + err[-2000:])
         last = json.loads(open(perf).readline())
         last["wall_s"] = dt
+        last["trace"] = [l for l in err.splitlines() if l.startswith("[msnv")][-12:]       # stage times (MSNV_VERBOSE)
     last.update(scale=scale, bam_bytes_on_disk=bam_bytes, synth_s=t_synth, reads_written=st["reads"])
     shutil.rmtree(data, ignore_errors=True)
     return last
@@ -464,7 +465,7 @@ def run_ours(a):
                        "breakdown_s": {k: e2e_bam[k] for k in ("decode_wall_s", "decode_cpu_s", "inflate_cpu_s", "h2d_s", "h2d_not_hidden_s",
                                                                "waiting_for_decode_s", "gpu_run_wall_s", "format_s", "total_s")},
                        "kernels_ms": {k: e2e_bam[k] for k in ("ms_index", "ms_pileup", "ms_call", "ms_compact", "ms_gather")},
-                       "windows": e2e_bam["windows"]}
+                       "windows": e2e_bam["windows"], "trace": e2e_bam.get("trace")}
     if e2e_h2d:
         if "ms" in e2e_h2d:
             line["e2e_h2d"] = {"value": tot_aligned / (h2d_ms / 1000.0), "unit": "aligned bases/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,

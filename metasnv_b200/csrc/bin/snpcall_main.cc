@@ -277,6 +277,7 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     bool masked = false;
     int64_t first_col = -1;
     int rc = 0;
+    stage("first window starts");
     const double t_dec0 = now_s();
     std::unique_ptr<WindowJob> cur(new WindowJob()), nxt;
     start_window(*cur, 0);
@@ -340,6 +341,7 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
         const int rrc = n_windows > 1 ? msnv_window_run(ctx, slot, &prm, &hits) : msnv_shard_run(ctx, &prm, &hits);
         if (rrc != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); rc = 1; break; }
         t_run += now_s() - a;
+        if (verbose()) fprintf(stderr, "[msnv %8.3f s] window %u of %u done (%u hits)\n", now_s() - g_t0, k + 1, n_windows, hits.n_hits);
         msnv_timings tm; msnv_get_timings(ctx, &tm);
         tm_sum.ms_index += tm.ms_index; tm_sum.ms_pileup += tm.ms_pileup; tm_sum.ms_call += tm.ms_call; tm_sum.ms_compact += tm.ms_compact;
         tm_sum.ms_gather += tm.ms_gather; tm_sum.kernel_launches += tm.kernel_launches; items_total += tm.n_items;

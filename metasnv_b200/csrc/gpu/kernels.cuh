@@ -555,8 +555,9 @@ __device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
-// bring a chunk's source bytes into L2 ahead of the copy that stages them (the copy then takes an L2 round trip
-// instead of an HBM one: with two stages per CTA the time from "stage free" to "stage full" bounds the CTA's rate)
+// bring a chunk's source bytes into L2 ahead of the copy that stages them. Measured (profiles/r02_pileup_ablations.txt): it
+// buys nothing - the consumers, not the refill, bound a CTA's rate - and costs DRAM reads (lines evicted before their copy
+// are fetched twice), so it is OFF; MSNV_ABLATE bit 64 switches it on for measurements.
 __device__ __forceinline__ void prefetch_chunk(const SrcPtrs& p, uint32_t c0, uint32_t m, uint32_t q4_0, uint32_t nq4, uint32_t sg_0, uint32_t nseg)
 {
     const ChunkCopies c = chunk_copies(p, c0, m, q4_0, nq4, sg_0, nseg);
@@ -614,12 +615,12 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
             q_lo = __ldg(src.q4_off + it.z); q_hi = __ldg(src.q4_off + it.w);
             g_lo = __ldg(src.seg_off + it.z); g_hi = __ldg(src.seg_off + it.w);
             whole = it.w - it.z <= sh.max_reads && q_hi - q_lo <= sh.chunk_q4 && g_hi - g_lo <= sh.max_segs;
-            if (whole && lane < PREFETCH_AHEAD) prefetch_chunk(src, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo, g_hi - g_lo);
+            if (whole && lane < PREFETCH_AHEAD && (sh.ablate & 64u)) prefetch_chunk(src, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo, g_hi - g_lo);
         }
         for (uint32_t k = 0; k < 32u; ++k) {
             const uint64_t idx = base + (uint64_t)k * G;
             if (idx >= n_items) break;
-            if (lane == k + PREFETCH_AHEAD && whole) prefetch_chunk(src, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo, g_hi - g_lo);
+            if (lane == k + PREFETCH_AHEAD && whole && (sh.ablate & 64u)) prefetch_chunk(src, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo, g_hi - g_lo);
             if (__shfl_sync(0xffffffffu, (int)whole, k)) {                   // the lane that owns the item issues it from its own registers
                 pileup_issue_chunk(smem, L, sh, chunk_no, k, src, expect, (uint32_t)mine, it.x, it.y, it.z, it.w - it.z, q_lo, q_hi - q_lo, g_lo,
                                    g_hi - g_lo, CHUNK_FIRST | CHUNK_LAST | (item_is_wide(it.z, it.w) ? CHUNK_WIDE : 0u));
@@ -646,12 +647,12 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
                 const uint32_t n_ok = okmask == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~okmask) - 1u;      // leading chunks that fit
                 if (n_ok) {
                     const uint32_t fl = (b_l == r_lo ? CHUNK_FIRST : 0u) | (e_l == r_hi ? CHUNK_LAST : 0u) | wide;
-                    if (lane < PREFETCH_AHEAD && lane < n_ok && e_l > b_l) prefetch_chunk(sp, b_l, e_l - b_l, qb, qe - qb, gb, ge - gb);
+                    if (lane < PREFETCH_AHEAD && lane < n_ok && e_l > b_l && (sh.ablate & 64u)) prefetch_chunk(sp, b_l, e_l - b_l, qb, qe - qb, gb, ge - gb);
                     uint32_t done_to = c0, done_q = qc, done_g = gc;
                     for (uint32_t kk = 0; kk < n_ok; ++kk) {
                         const uint32_t bk = __shfl_sync(0xffffffffu, b_l, kk), ek = __shfl_sync(0xffffffffu, e_l, kk);
                         if (ek == bk) break;                                             // past the end of the item
-                        if (lane == kk + PREFETCH_AHEAD && lane < n_ok && e_l > b_l) prefetch_chunk(sp, b_l, e_l - b_l, qb, qe - qb, gb, ge - gb);
+                        if (lane == kk + PREFETCH_AHEAD && lane < n_ok && e_l > b_l && (sh.ablate & 64u)) prefetch_chunk(sp, b_l, e_l - b_l, qb, qe - qb, gb, ge - gb);
                         pileup_issue_chunk(smem, L, sh, chunk_no, kk, sp, expect, (uint32_t)idx, sample, tile, b_l, e_l - b_l, qb, qe - qb, gb, ge - gb, fl);
                         done_to = ek; done_q = __shfl_sync(0xffffffffu, qe, kk); done_g = __shfl_sync(0xffffffffu, ge, kk);
                     }
@@ -978,7 +979,7 @@ __device__ __forceinline__ uint32_t call_position(uint32_t rc, uint32_t ch, cons
 constexpr int CALL_THREADS = TILE_QUADS;
 
 template <bool HI_THR>
-__global__ void __launch_bounds__(CALL_THREADS)
+__global__ void __launch_bounds__(CALL_THREADS, 3)
 call_kernel(const uint8_t* __restrict__ tiles /* slot of item `item0` first */, const Item* __restrict__ items, uint32_t item0,
             const uint32_t* __restrict__ tile_begin /* of this launch's first tile */, uint32_t tile_abs0 /* its shard tile index */,
             const uint8_t* __restrict__ ref, const uint8_t* __restrict__ expect, CallParamsDev prm, int text_mode,
