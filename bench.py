@@ -125,11 +125,37 @@ def cpu_sample(workload, work, samples, scale):
     return data, st
 
 
+def metasnv_part1(data, work, mode, threads, n_splits):
+    """Part I of the workflow through the reference's UNCHANGED metaSNV.py (coverage pass, header, createOptimumSplit, one
+    mpileup | snpCall pipe per split) with either the CPU programs (mode "oracle") or the GPU ones (mode "gpu"); seconds."""
+    from metasnv_b200 import harness as H
+    script, env = H.stage_metasnv(os.path.join(work, "tree_" + mode), mode)
+    t0 = time.perf_counter()
+    r = H.run_metasnv(script, env, os.path.join(work, "proj_" + mode), os.path.join(data, "all_samples"), os.path.join(data, "ref.fa"),
+                      threads=threads, n_splits=n_splits)
+    dt = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise RuntimeError("metaSNV.py (%s) failed: %s" % (mode, (r.stdout + r.stderr)[-2000:]))
+    return dt
+
+
 def cpu_baseline(workload, work, steps=1, scale=None, samples=None):
     # about 3e8 aligned bases: 10-30 s of the CPU pipe
+    from metasnv_b200 import harness as H
     samples = samples or {"c2": 1000, "c1": 160, "c4": 20, "c3": 500, "c5": 200}[workload]
     scale = scale or {"c2": 0.003, "c1": 0.12, "c4": 0.0012, "c3": 0.0004, "c5": 0.0012}[workload]
     data, st = cpu_sample(workload, work, samples, scale)
+    if workload in ("c1", "c3", "c5") and os.path.exists(os.path.join(H.ORACLE_BIN, "metaSNV", "metaSNV.py")):
+        # several genomes: the reference parallelises over genome bins, so it is driven the way its users drive it:
+        # unchanged metaSNV.py --threads <host cores> (n_splits = threads, metaSNV.py:275-276), coverage pass included
+        cores = os.cpu_count() or 1
+        n_splits = max(1, min(cores, 100))
+        times = [metasnv_part1(data, work, "oracle", cores, n_splits) for _ in range(steps)]
+        best = min(times)
+        desc = "%s at scale %g (%d samples, %d aligned bases in %d reads) through the unchanged metaSNV.py --threads %d --n_splits %d with `oracle mpileup`, the reference's snpCall and qaCompute (Part I: coverage pass + SNV calling)" % (
+            workload, scale, samples, st["aligned_bases"], st["reads"], cores, n_splits)
+        return {"value": st["aligned_bases"] / best, "unit": "aligned bases/s", "cores": cores, "kind": "port", "sample": desc, "seconds": best,
+                "host_cores_available": cores, "data_dir": data}, st, times
     times = []
     caller = ""
     for i in range(steps):
@@ -149,6 +175,7 @@ def run_reference(a):
     work = tempfile.mkdtemp(prefix="msnv_bench_ref_")
     try:
         base, st, times = cpu_baseline(a.workload, work, steps=a.warmup + a.steps if a.ref_full_steps else max(1, min(a.steps, 3)))
+        base.pop("data_dir", None)
         used = times[-min(len(times), a.steps):]
         ms = 1000.0 * sum(used) / len(used)
         value = st["aligned_bases"] / (ms / 1000.0)
@@ -476,7 +503,14 @@ def run_ours(a):
     if world == 1 and not a.no_cpu_baseline:
         work = tempfile.mkdtemp(prefix="msnv_bench_cpu_")
         try:
-            line["cpu_baseline"], _, _ = cpu_baseline(a.workload, work)
+            line["cpu_baseline"], st_cpu, _ = cpu_baseline(a.workload, work)
+            data_dir = line["cpu_baseline"].pop("data_dir", None)
+            if data_dir:
+                # the same data set and the same driver with the GPU programs in place of the CPU ones
+                cores = os.cpu_count() or 1
+                dt = min(metasnv_part1(data_dir, work, "gpu", cores, max(1, min(cores, 100))) for _ in range(2))
+                line["e2e_metasnv"] = {"value": st_cpu["aligned_bases"] / dt, "unit": "aligned bases/s", "seconds": dt, "threads": cores,
+                                       "what": "unchanged metaSNV.py --threads %d on the cpu_baseline's data set with this repository's qaCompute, samtools stand-in and snpCall (Part I)" % cores}
         finally:
             shutil.rmtree(work, ignore_errors=True)
     emit(line)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MSNV_ABI_VERSION 5
+#define MSNV_ABI_VERSION 6
 
 /* Positions per tile: contigs of a shard are laid out back to back in a "shard coordinate" space,
  * each starting at a multiple of MSNV_TILE, so a tile never spans two contigs. The kernels are written
@@ -85,6 +85,31 @@ typedef struct {
     const uint8_t*  seq2;
     const uint8_t*  qual;
 } msnv_sample_reads;
+
+/* The same reads as BAM stores them: the device walks the CIGARs, packs the bases and lays the aligned segments out
+ * (what `samtools mpileup`'s resolve_cigar2 / pileup_seq do per column upstream of snpCall, metaSNV.py:160-165); the host
+ * only supplies what it has after filtering anyway. Per read:
+ *   pos       shard coordinate of the first reference base
+ *   mate      as in msnv_sample_reads
+ *   seg_off, q4_off   prefix sums (n_reads + 1) of the read's aligned segments (M/=/X operations of non-zero length) and of the
+ *             quads they occupy in the position-aligned layout (a segment at shard coordinate x of length l: ((x & 3) + l + 3) / 4)
+ *   raw_off   prefix sums (n_reads + 1) of the reads' blobs in `raw`, in units of 4 bytes
+ *   n_cigar, l_seq   as in the BAM record
+ *   raw       per read, 4-byte aligned: n_cigar little-endian u32 CIGAR operations (len << 4 | op), (l_seq + 1) / 2 bytes
+ *             of 4-bit bases, l_seq phred qualities - the record's own bytes, BAM section 4.2 */
+typedef struct {
+    uint32_t        n_reads;
+    uint32_t        max_span;
+    uint32_t        reserved0, reserved1;
+    const int32_t*  pos;
+    const int32_t*  mate;
+    const uint32_t* seg_off;
+    const uint32_t* q4_off;
+    const uint32_t* raw_off;
+    const uint16_t* n_cigar;
+    const uint16_t* l_seq;
+    const uint8_t*  raw;
+} msnv_raw_reads;
 
 /* snpCall's thresholds (call_vC.cpp:26-36, options -c -t -p). */
 typedef struct {
@@ -174,6 +199,11 @@ int msnv_shard_run(msnv_ctx* ctx, const msnv_call_params* params, msnv_hits* hit
 int msnv_window_begin(msnv_ctx* ctx, uint32_t slot, uint32_t pos_lo, uint32_t pos_hi);
 int msnv_window_add_sample(msnv_ctx* ctx, uint32_t slot, uint32_t sample, const msnv_sample_reads* reads);
 int msnv_window_run(msnv_ctx* ctx, uint32_t slot, const msnv_call_params* params, msnv_hits* hits);
+/* The same as msnv_window_add_sample() from BAM-shaped records: copied to the device and expanded there (expand_kernel:
+ * CIGAR walk, 4-bit -> 2-bit bases, quality capping, position alignment). Slot 0 after msnv_shard_begin() is the whole shard.
+ * msnv_expand_stats(): bases seen so far that are neither A/C/G/T nor N (IUPAC codes; they are counted as "other"). */
+int msnv_window_add_sample_raw(msnv_ctx* ctx, uint32_t slot, uint32_t sample, const msnv_raw_reads* reads);
+int msnv_expand_stats(msnv_ctx* ctx, uint64_t* iupac_bases);
 
 /* Test/inspection hook: per-position A,C,G,T,N counts ([n][5], uint16) of one sample after the last
  * run, for shard coordinates [first, first+n). */

@@ -26,6 +26,15 @@ class SampleReads(C.Structure):
                 ("seg_pos", C.c_void_p), ("seg_len", C.c_void_p), ("seq2", C.c_void_p), ("qual", C.c_void_p)]
 
 
+class RawReads(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("max_span", C.c_uint32), ("reserved0", C.c_uint32), ("reserved1", C.c_uint32),
+                ("pos", C.c_void_p), ("mate", C.c_void_p), ("seg_off", C.c_void_p), ("q4_off", C.c_void_p), ("raw_off", C.c_void_p),
+                ("n_cigar", C.c_void_p), ("l_seq", C.c_void_p), ("raw", C.c_void_p)]
+
+
+RAW_ARRAYS = ("pos", "mate", "seg_off", "q4_off", "raw_off", "n_cigar", "l_seq", "raw")
+
+
 class CallParams(C.Structure):
     _fields_ = [("min_coverage", C.c_int32), ("calling_threshold", C.c_int32), ("min_fraction", C.c_double)]
 
@@ -91,6 +100,8 @@ def load():
     lib.msnv_window_begin.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
     lib.msnv_window_add_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(SampleReads)]
     lib.msnv_window_run.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(CallParams), C.POINTER(Hits)]
+    lib.msnv_window_add_sample_raw.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(RawReads)]
+    lib.msnv_expand_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.msnv_shard_counts.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.msnv_get_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
     lib.msnv_call_counts.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -242,6 +253,23 @@ class Context:
         for k in SAMPLE_ARRAYS:
             setattr(r, k, _ptr(a[k]))
         self._check(self.lib.msnv_window_add_sample(self.h, slot, sample, C.byref(r)), "msnv_window_add_sample")
+
+    def window_add_sample_raw(self, slot, sample, arrays):
+        """arrays: pos, mate, seg_off, q4_off, raw_off, n_cigar, l_seq, raw (+ max_span): reads as BAM stores them; the device expands them."""
+        a = {k: np.ascontiguousarray(arrays[k]) for k in RAW_ARRAYS}
+        self._keep_win = getattr(self, "_keep_win", {})
+        self._keep_win.setdefault(slot, []).append(a)
+        r = RawReads()
+        r.n_reads = a["pos"].size
+        r.max_span = int(arrays["max_span"])
+        for k in RAW_ARRAYS:
+            setattr(r, k, _ptr(a[k]))
+        self._check(self.lib.msnv_window_add_sample_raw(self.h, slot, sample, C.byref(r)), "msnv_window_add_sample_raw")
+
+    def expand_stats(self):
+        v = C.c_uint64(0)
+        self._check(self.lib.msnv_expand_stats(self.h, C.byref(v)), "msnv_expand_stats")
+        return int(v.value)
 
     def window_run(self, slot, min_coverage=4, calling_threshold=4, min_fraction=0.01, copy=True):
         p = CallParams(min_coverage, calling_threshold, min_fraction)

@@ -114,6 +114,27 @@ static msnv_sample_reads stage_batch(const SampleReads& r, BouncePool& pool, uin
     return v;
 }
 
+// the same for a BAM-shaped batch (the device expands it)
+static msnv_raw_reads stage_raw(const RawReads& r, BouncePool& pool, uint8_t*& chunk)
+{
+    msnv_raw_reads v = r.view();
+    chunk = nullptr;
+    if (v.n_reads == 0 || r.bytes() + 8 * 256 > BouncePool::CHUNK) return v;
+    uint8_t* p = pool.acquire();
+    if (!p) return v;
+    chunk = p;
+    auto put = [&](const void* src, size_t bytes) { uint8_t* d = p; memcpy(d, src, bytes); p += (bytes + 255) & ~(size_t)255; return d; };
+    v.pos = (const int32_t*)put(r.pos.data(), r.pos.size() * 4);
+    v.mate = (const int32_t*)put(r.mate.data(), r.mate.size() * 4);
+    v.seg_off = (const uint32_t*)put(r.seg_off.data(), r.seg_off.size() * 4);
+    v.q4_off = (const uint32_t*)put(r.q4_off.data(), r.q4_off.size() * 4);
+    v.raw_off = (const uint32_t*)put(r.raw_off.data(), r.raw_off.size() * 4);
+    v.n_cigar = (const uint16_t*)put(r.n_cigar.data(), r.n_cigar.size() * 2);
+    v.l_seq = (const uint16_t*)put(r.l_seq.data(), r.l_seq.size() * 2);
+    v.raw = put(r.raw.data(), r.raw.size() * 4);
+    return v;
+}
+
 static std::string dir_of(const std::string& p) { size_t k = p.rfind('/'); return k == std::string::npos ? std::string(".") : p.substr(0, k); }
 static std::string base_of(const std::string& p) { size_t k = p.rfind('/'); return k == std::string::npos ? p : p.substr(k + 1); }
 
@@ -238,26 +259,35 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     struct PinJoin { std::atomic<bool>& stop; std::thread& t; ~PinJoin() { stop = true; if (t.joinable()) t.join(); } } pin_join{stop_pinning, pinner};
     stage("decoders open");
 
+    // MSNV_RAW=0: build the position-aligned layout on the host (the C ABI's other input form) instead of on the device
+    const bool raw_mode = !(getenv("MSNV_RAW") && atoi(getenv("MSNV_RAW")) == 0);
     std::vector<SampleReads> batch[2];
-    batch[0].resize(S); batch[1].resize(S);
+    std::vector<RawReads> rbatch[2];
+    if (raw_mode) { rbatch[0].resize(S); rbatch[1].resize(S); } else { batch[0].resize(S); batch[1].resize(S); }
     struct WindowJob {
         std::vector<std::thread> pool; std::atomic<uint32_t> next{0}; std::atomic<bool> failed{false};
         std::mutex mu; std::vector<uint32_t> ready; std::string err; uint32_t n_done = 0;
-        std::vector<msnv_sample_reads> view; std::vector<uint8_t*> chunk;       // per sample: the staged batch
+        std::vector<msnv_sample_reads> view; std::vector<msnv_raw_reads> rview; std::vector<uint8_t*> chunk;       // per sample: the staged batch
     };
     auto start_window = [&](WindowJob& J, uint32_t k) {
         const uint32_t lo = k * tiles_per_window * MSNV_TILE, hi = std::min<uint64_t>((uint64_t)(k + 1) * tiles_per_window * MSNV_TILE, layout.n_positions);
         J.next = 0; J.failed = false; J.ready.clear(); J.err.clear(); J.n_done = 0;
-        J.view.assign(S, msnv_sample_reads{}); J.chunk.assign(S, nullptr);
+        J.view.assign(raw_mode ? 0 : S, msnv_sample_reads{}); J.rview.assign(raw_mode ? S : 0, msnv_raw_reads{}); J.chunk.assign(S, nullptr);
         for (int t = 0; t < n_threads; ++t)
-            J.pool.emplace_back([&J, &dec, &batch, &pool, k, lo, hi, S]() {
+            J.pool.emplace_back([&J, &dec, &batch, &rbatch, &pool, raw_mode, k, lo, hi, S]() {
                 for (;;) {
                     const uint32_t s = J.next.fetch_add(1);
                     if (s >= S) break;
                     std::string e;
                     bool good = true;
-                    if (!J.failed) good = dec[s]->window(lo, (uint32_t)hi, k ? &batch[(k - 1) & 1][s] : nullptr, batch[k & 1][s], e);
-                    if (good && !J.failed) J.view[s] = stage_batch(batch[k & 1][s], pool, J.chunk[s]);
+                    if (!J.failed) {
+                        if (raw_mode) good = dec[s]->window_raw(lo, (uint32_t)hi, k ? &rbatch[(k - 1) & 1][s] : nullptr, rbatch[k & 1][s], e);
+                        else good = dec[s]->window(lo, (uint32_t)hi, k ? &batch[(k - 1) & 1][s] : nullptr, batch[k & 1][s], e);
+                    }
+                    if (good && !J.failed) {
+                        if (raw_mode) J.rview[s] = stage_raw(rbatch[k & 1][s], pool, J.chunk[s]);
+                        else J.view[s] = stage_batch(batch[k & 1][s], pool, J.chunk[s]);
+                    }
                     std::lock_guard<std::mutex> lk(J.mu);
                     if (!good) { if (J.err.empty()) J.err = e; J.failed = true; }
                     J.ready.push_back(s);
@@ -308,11 +338,11 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
             if (cur->failed) { for (uint32_t s : got) if (cur->chunk[s]) in_flight.push_back(cur->chunk[s]); recycle(); continue; }
             for (uint32_t s : got) {
                 const double a = now_s();
-                const msnv_sample_reads& v = cur->view[s];
-                const int arc = n_windows > 1 ? msnv_window_add_sample(ctx, slot, s, &v) : msnv_shard_add_sample(ctx, s, &v);
+                const uint32_t lib_slot = n_windows > 1 ? slot : 0u;          // (one window: the whole shard, opened by msnv_shard_begin in slot 0)
+                const int arc = raw_mode ? msnv_window_add_sample_raw(ctx, lib_slot, s, &cur->rview[s]) : msnv_window_add_sample(ctx, lib_slot, s, &cur->view[s]);
                 if (arc != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); rc = 1; break; }
                 if (cur->chunk[s]) in_flight.push_back(cur->chunk[s]);
-                (cur->chunk[s] ? h2d_bytes : pageable_bytes) += batch[slot][s].bytes();
+                (cur->chunk[s] ? h2d_bytes : pageable_bytes) += raw_mode ? rbatch[slot][s].bytes() : batch[slot][s].bytes();
                 t_add += now_s() - a;
             }
             if (in_flight.size() >= 3 && !recycle()) { rc = 1; break; }
@@ -376,6 +406,11 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     const double t_end = now_s();
     stage("kernels done, output written");
 
+    if (raw_mode) {
+        uint64_t iupac = 0;
+        if (msnv_expand_stats(ctx, &iupac) == MSNV_OK && iupac)
+            fprintf(stderr, "[msnv] %llu read bases are neither A/C/G/T nor N; such bases are not counted\n", (unsigned long long)iupac);
+    }
     DecodeStats tot;
     uint32_t n_indexed = 0;
     for (uint32_t s = 0; s < S; ++s) {
@@ -392,7 +427,7 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
                     "{\"tool\": \"snpCall\", \"device\": %d, \"samples\": %u, \"positions\": %u, \"windows\": %u, \"bams_read_through_index\": %u, "
                     "\"records\": %llu, \"reads\": %llu, \"aligned_bases\": %llu, \"pairs\": %llu, \"dropped_by_cap\": %llu, "
                     "\"bam_bytes\": %llu, \"bam_bytes_inflated\": %llu, \"h2d_bytes\": %llu, \"h2d_pageable_bytes\": %llu, \"hits\": %llu, "
-                    "\"decode_threads\": %d, \"decode_wall_s\": %.6f, \"decode_cpu_s\": %.6f, \"inflate_cpu_s\": %.6f, "
+                    "\"records_expanded_on_device\": %d, \"decode_threads\": %d, \"decode_wall_s\": %.6f, \"decode_cpu_s\": %.6f, \"inflate_cpu_s\": %.6f, "
                     "\"h2d_s\": %.6f, \"h2d_not_hidden_s\": %.6f, \"waiting_for_decode_s\": %.6f, "
                     "\"gpu_run_wall_s\": %.6f, \"format_s\": %.6f, \"total_s\": %.6f, "
                     "\"ms_index\": %.4f, \"ms_pileup\": %.4f, \"ms_call\": %.4f, \"ms_compact\": %.4f, \"ms_gather\": %.4f, "
@@ -400,7 +435,7 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
                     dev, S, layout.n_positions, n_windows, n_indexed, (unsigned long long)tot.records, (unsigned long long)tot.accepted,
                     (unsigned long long)tot.aligned_bases, (unsigned long long)tot.pairs, (unsigned long long)tot.dropped_by_cap,
                     (unsigned long long)bam_bytes_total, (unsigned long long)tot.compressed_bytes, (unsigned long long)h2d_bytes,
-                    (unsigned long long)pageable_bytes, (unsigned long long)n_hits_total, n_threads * inflate_threads,
+                    (unsigned long long)pageable_bytes, (unsigned long long)n_hits_total, raw_mode ? 1 : 0, n_threads * inflate_threads,
                     t_dec1 - t_dec0, tot.seconds, tot.inflate_seconds, t_add, t_wait_upload, t_decode_wait, t_run, t_format, t_end - t_start,
                     tm_sum.ms_index, tm_sum.ms_pileup, tm_sum.ms_call, tm_sum.ms_compact, tm_sum.ms_gather, (unsigned long long)items_total,
                     tm_sum.kernel_launches);

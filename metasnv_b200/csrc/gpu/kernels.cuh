@@ -305,6 +305,74 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ v, ui
 }
 
 // ------------------------------------------------------------------------------------------------
+// expand: reads as BAM stores them -> position-aligned segments (include/msnv.h). This is the column builder's
+// per-read half - the CIGAR walk of htslib's resolve_cigar2 and the base / quality look-up of pileup_seq,
+// which `samtools mpileup` performs once per COLUMN upstream of snpCall (metaSNV.py:160-165) - done once per
+// read: every M/=/X operation becomes a segment whose bases (4-bit -> 2-bit, anything but A/C/G/T flagged) and
+// qualities (capped at 127) are stored at their reference position modulo four.
+// One warp per read: every lane walks the (short) CIGAR, lane 0 writes the segment records, the lanes share the
+// segment's quads - consecutive lanes write consecutive bytes / words.
+// ------------------------------------------------------------------------------------------------
+struct RawDev {
+    const int32_t* pos; const uint32_t* seg_off; const uint32_t* q4_off;      // in the sample's block
+    const uint32_t* raw_off; const uint16_t* n_cigar; const uint16_t* l_seq; const uint32_t* raw;      // staged
+    uint32_t n_reads;
+};
+
+// xstat: [0] bases that are neither A/C/G/T nor N, [1] != 0: a record is inconsistent (CIGAR longer than the sequence, blob
+// shorter than the record, more segments or quads than the offsets say); aligned: the sample's aligned bases (statistics)
+__global__ void __launch_bounds__(256) expand_kernel(const RawDev in, int32_t* __restrict__ seg_pos, uint16_t* __restrict__ seg_len,
+                                                     uint8_t* __restrict__ seq2, uint32_t* __restrict__ qual32, unsigned long long* __restrict__ xstat,
+                                                     unsigned long long* __restrict__ aligned)
+{
+    const uint32_t lane = threadIdx.x & 31u, r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= in.n_reads) return;
+    const uint32_t b0 = __ldg(in.raw_off + r), b1 = __ldg(in.raw_off + r + 1);
+    const uint32_t* blob = in.raw + b0;
+    const uint32_t nc = __ldg(in.n_cigar + r), ls = __ldg(in.l_seq + r);
+    const uint8_t* seq4 = reinterpret_cast<const uint8_t*>(blob + nc);
+    const uint8_t* ql = seq4 + (ls + 1u) / 2u;
+    uint32_t rx = (uint32_t)__ldg(in.pos + r), qy = 0, k = __ldg(in.seg_off + r), Q = __ldg(in.q4_off + r);
+    const uint32_t k_end = __ldg(in.seg_off + r + 1), Q_end = __ldg(in.q4_off + r + 1);
+    uint32_t n_iupac = 0, n_al = 0;
+    if (b1 < b0 || (size_t)(b1 - b0) * 4u < 4u * (size_t)nc + (ls + 1u) / 2u + ls) { if (lane == 0) atomicExch(xstat + 1, 1ull); return; }
+    for (uint32_t c = 0; c < nc; ++c) {
+        const uint32_t w = __ldg(blob + c), op = w & 15u, len = w >> 4;
+        if (op == 0u || op == 7u || op == 8u) {                                  // M, =, X: aligned bases
+            if (len) {
+                const uint32_t a = rx & 3u, nq = (a + len + 3u) >> 2;
+                if (qy + len > ls || k >= k_end || Q + nq > Q_end) { if (lane == 0) atomicExch(xstat + 1, 1ull); return; }
+                n_al += len;
+                if (lane == 0) { seg_pos[k] = (int32_t)rx; seg_len[k] = (uint16_t)len; }
+                for (uint32_t i = lane; i < nq; i += 32u) {
+                    uint32_t sb = 0, qw = 0;
+                    #pragma unroll
+                    for (uint32_t j = 0; j < 4u; ++j) {
+                        const int32_t o = (int32_t)(4u * i + j) - (int32_t)a;    // offset in the segment (padding in front of / behind it stays 0)
+                        if (o >= 0 && (uint32_t)o < len) {
+                            const uint32_t q = qy + (uint32_t)o;
+                            const uint32_t b4 = (__ldg(seq4 + (q >> 1)) >> ((~q & 1u) << 2)) & 15u;    // "=ACMGRSVTWYHKDBN": A, C, G, T are the one-hot codes
+                            const bool other = __popc(b4) != 1;
+                            const uint32_t ph = __ldg(ql + q);
+                            sb |= (other ? 0u : (uint32_t)__ffs((int)b4) - 1u) << (2u * j);
+                            qw |= ((ph < 127u ? ph : 127u) | (other ? 0x80u : 0u)) << (8u * j);
+                            n_iupac += (other && b4 != 15u) ? 1u : 0u;
+                        }
+                    }
+                    seq2[Q + i] = (uint8_t)sb;
+                    qual32[Q + i] = qw;
+                }
+                ++k; Q += nq;
+            }
+            rx += len; qy += len;
+        } else if (op == 2u || op == 3u) rx += len;                              // D, N: reference only
+        else if (op == 1u || op == 4u) qy += len;                                // I, S: query only (H, P: neither)
+    }
+    if (n_iupac) atomicAdd(xstat, (unsigned long long)n_iupac);
+    if (lane == 0 && n_al) atomicAdd(aligned, (unsigned long long)n_al);
+}
+
+// ------------------------------------------------------------------------------------------------
 // mate overlap (htslib tweak_overlap_quality, SURVEY.md Annex A.2): for every pair the host linked, at every
 // reference position both mates align a base to, the rule decides which of the two bases is still counted
 // (overlap_rule.h: a corrected quality is only ever compared with the threshold, so its verdict is one bit).

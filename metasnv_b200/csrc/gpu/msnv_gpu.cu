@@ -42,6 +42,7 @@ struct msnv_ctx {
         std::vector<Block> allocs;                  // device blocks holding the samples
         uint64_t n_reads = 0, n_bases = 0, n_segs = 0;
         SampleDev* d_samples = nullptr; uint32_t cap_samples = 0;
+        unsigned long long* d_aligned = nullptr; uint32_t cap_aligned = 0; bool has_raw = false;     // aligned bases per sample (samples expanded on the device)
         cudaEvent_t uploaded = nullptr;
     };
 
@@ -67,6 +68,9 @@ struct msnv_ctx {
     uint32_t* d_bitmap = nullptr;     uint64_t cap_bitmap = 0;
     uint32_t* d_scalar = nullptr;   int* d_err = nullptr;
     uint32_t* d_fix_list = nullptr;   uint64_t cap_fix_list = 0;        // samples with mate links
+    // raw (BAM-shaped) reads of the sample being expanded: one staging buffer, reused in stream order
+    uint8_t* d_raw = nullptr;         uint64_t cap_raw = 0;
+    unsigned long long* d_xstat = nullptr;       // [0] IUPAC bases seen by expand_kernel, [1] inconsistent record flag
     // what msnv_shard_counts can still look at: the last range of the last run
     uint32_t last_slot = 0, last_item0 = 0, last_ta = 0, last_tb = 0;
 
@@ -127,7 +131,7 @@ void release_window(msnv_ctx* ctx, msnv_ctx::Window& w)
     w.allocs.clear();
     w.h_samples.clear(); w.sizes.clear();
     w.n_reads = w.n_bases = w.n_segs = 0;
-    w.open = false;
+    w.open = false; w.has_raw = false;
     // plain blocks nobody has reused for a few windows are returned to the driver
     size_t k = 0;
     for (size_t i = 0; i < ctx->pool.size(); ++i) {
@@ -514,7 +518,9 @@ static int run_window(msnv_ctx* ctx, uint32_t slot, const msnv_call_params* prm,
     launches += 2;
     CU(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, 24, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(ctx->h_scalar + 6, ctx->d_err, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_scalar + 7, reinterpret_cast<const uint32_t*>(ctx->d_xstat + 1), 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (ctx->h_scalar[7]) return fail(ctx, MSNV_E_ARG, "a BAM-shaped record is inconsistent: CIGAR longer than the sequence, blob shorter than the record, or offsets that disagree with the CIGAR");
     float ms_mate = 0;
     cudaEventElapsedTime(&ms_mate, ev_m0, ev_m1);          // (the events are reused by the ranges below)
     if (ctx->h_scalar[6] == 3) return fail(ctx, MSNV_E_ARG, "the reads of a sample are not in coordinate order (pos must be ascending)");
@@ -613,6 +619,8 @@ int msnv_create(int device, msnv_ctx** out)
     for (auto& w : ctx->win) CU(cudaEventCreateWithFlags(&w.uploaded, cudaEventDisableTiming));
     CU(cudaMalloc((void**)&ctx->d_scalar, 32));
     CU(cudaMalloc((void**)&ctx->d_err, 4));
+    CU(cudaMalloc((void**)&ctx->d_xstat, 16));
+    CU(cudaMemset(ctx->d_xstat, 0, 16));
     CU(cudaMallocHost((void**)&ctx->h_scalar, 32));
     CU(cudaFuncSetAttribute(pileup_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PER_CTA_MAX));
     CU(cudaFuncSetAttribute(pileup_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PER_CTA_MAX));
@@ -628,13 +636,13 @@ void msnv_destroy(msnv_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (auto& w : ctx->win) { release_window(ctx, w); cudaFree(w.d_samples); if (w.uploaded) cudaEventDestroy(w.uploaded); }
+    for (auto& w : ctx->win) { release_window(ctx, w); cudaFree(w.d_samples); cudaFree(w.d_aligned); if (w.uploaded) cudaEventDestroy(w.uploaded); }
     drop_pool(ctx);
     for (auto& sl : ctx->slabs) cudaFree(sl.base);
     cudaFree(ctx->d_ref);
     cudaFree(ctx->d_items); cudaFree(ctx->d_tiles); cudaFree(ctx->d_expect); cudaFree(ctx->d_text_acgt); cudaFree(ctx->d_text_match);
     cudaFree(ctx->d_tile_begin); cudaFree(ctx->d_tile_hits); cudaFree(ctx->d_flags); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_range_cache); cudaFree(ctx->d_bitmap);
-    cudaFree(ctx->d_scalar); cudaFree(ctx->d_err); cudaFree(ctx->d_fix_list);
+    cudaFree(ctx->d_scalar); cudaFree(ctx->d_err); cudaFree(ctx->d_fix_list); cudaFree(ctx->d_raw); cudaFree(ctx->d_xstat);
     cudaFree(ctx->d_cov_diff); cudaFree(ctx->d_cov_beg); cudaFree(ctx->d_cov_end); cudaFree(ctx->d_cov_meta); cudaFree(ctx->d_cov_out);
     cudaFree(ctx->d_hit_pos); cudaFree(ctx->d_hit_total); cudaFree(ctx->d_hit_pop); cudaFree(ctx->d_hit_ind);
     cudaFree(ctx->d_hit_cov); cudaFree(ctx->d_hit_allele);
@@ -746,6 +754,84 @@ int msnv_window_add_sample(msnv_ctx* ctx, uint32_t slot, uint32_t sample, const 
     uint64_t n_aligned = 0;
     for (size_t k = 0; k < n_seg; ++k) n_aligned += r->seg_len[k];
     w.sizes[sample] = msnv_sample_sizes{r->n_reads, 0, d.max_span, 0, (uint64_t)n_seg, (uint64_t)n_q4, n_aligned};
+    return MSNV_OK;
+}
+
+int msnv_window_add_sample_raw(msnv_ctx* ctx, uint32_t slot, uint32_t sample, const msnv_raw_reads* r)
+{
+    if (!ctx || !r) return MSNV_E_ARG;
+    if (!ctx->open || slot >= (uint32_t)N_SLOTS || !ctx->win[slot].open) return fail(ctx, MSNV_E_STATE, "msnv_window_add_sample_raw: no open window in this slot");
+    msnv_ctx::Window& w = ctx->win[slot];
+    if (sample >= ctx->S) return fail(ctx, MSNV_E_ARG, "msnv_window_add_sample_raw: sample %u out of range", sample);
+    if (w.h_samples[sample].n_reads) return fail(ctx, MSNV_E_STATE, "msnv_window_add_sample_raw: sample %u added twice", sample);
+    if (r->n_reads == 0) return MSNV_OK;
+    if (r->max_span > 8u * MSNV_MAX_READ_BASES) return fail(ctx, MSNV_E_LIMIT, "sample %u: reference span %u exceeds the limit", sample, r->max_span);
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = r->n_reads, n1 = n + 1;
+    if (r->seg_off[0] != 0 || r->q4_off[0] != 0 || r->raw_off[0] != 0) return fail(ctx, MSNV_E_ARG, "sample %u: seg_off / q4_off / raw_off must start at 0", sample);
+    const size_t n_seg = r->seg_off[n], n_q4 = r->q4_off[n], raw_words = r->raw_off[n];
+    if (n_seg < n || n_q4 < n_seg) return fail(ctx, MSNV_E_ARG, "sample %u: inconsistent offsets (%zu reads, %zu segments, %zu quads)", sample, n, n_seg, n_q4);
+    // (the records themselves are checked by expand_kernel: CIGAR against sequence length, blob size, offsets)
+    bool has_mates = false;
+    for (size_t i = 0; i < n && !has_mates; ++i) has_mates = r->mate[i] >= 0;
+    if (w.cap_aligned < ctx->S) {
+        cudaFree(w.d_aligned); w.d_aligned = nullptr; w.cap_aligned = 0;
+        CU(cudaMalloc((void**)&w.d_aligned, (size_t)ctx->S * 8));
+        w.cap_aligned = ctx->S;
+    }
+    if (!w.has_raw) { CU(cudaMemsetAsync(w.d_aligned, 0, (size_t)ctx->S * 8, ctx->copy_stream)); w.has_raw = true; }
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes + 32, 256); return o; };
+    const size_t o_pos = take(n * 4), o_sgo = take(n1 * 4), o_q4 = take(n1 * 4), o_mate = take(n * 4),
+                 o_sp = take(n_seg * 4), o_sl = take(n_seg * 2), o_seq = take(n_q4), o_qual = take(n_q4 * 4),
+                 o_fix = has_mates ? take(n_q4) : 0;
+    uint8_t* base = (uint8_t*)take_block(ctx, w, off);
+    if (!base) return fail(ctx, MSNV_E_NOMEM, "sample %u: cannot allocate %zu bytes of device memory; process the shard in smaller windows (msnv_window_begin) or smaller genome bins (metaSNV.py --n_splits)", sample, off);
+    // staging of the BAM-shaped arrays: raw_off | raw | n_cigar | l_seq
+    const size_t s_off = 0, s_raw = align_up(n1 * 4, 256), s_nc = align_up(s_raw + raw_words * 4, 256), s_ls = align_up(s_nc + n * 2, 256), s_end = s_ls + n * 2;
+    if (s_end > ctx->cap_raw) {
+        const uint64_t cap = s_end + s_end / 4 + (1u << 20);
+        if (grow(ctx, ctx->d_raw, cap)) return MSNV_E_CUDA;
+        ctx->cap_raw = cap;
+    }
+    cudaStream_t st = ctx->copy_stream;
+    CU(cudaMemcpyAsync(base + o_pos, r->pos, n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_sgo, r->seg_off, n1 * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_q4, r->q4_off, n1 * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_mate, r->mate, n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_raw + s_off, r->raw_off, n1 * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_raw + s_raw, r->raw, raw_words * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_raw + s_nc, r->n_cigar, n * 2, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_raw + s_ls, r->l_seq, n * 2, cudaMemcpyHostToDevice, st));
+    // the aligned arrays are built in place: padding bytes must be 0
+    CU(cudaMemsetAsync(base + o_seq, 0, n_q4 + 32, st));
+    RawDev in;
+    in.pos = (const int32_t*)(base + o_pos); in.seg_off = (const uint32_t*)(base + o_sgo); in.q4_off = (const uint32_t*)(base + o_q4);
+    in.raw_off = (const uint32_t*)(ctx->d_raw + s_off); in.raw = (const uint32_t*)(ctx->d_raw + s_raw);
+    in.n_cigar = (const uint16_t*)(ctx->d_raw + s_nc); in.l_seq = (const uint16_t*)(ctx->d_raw + s_ls); in.n_reads = r->n_reads;
+    expand_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(in, (int32_t*)(base + o_sp), (uint16_t*)(base + o_sl), base + o_seq, (uint32_t*)(base + o_qual), ctx->d_xstat, w.d_aligned + sample);
+    CU(cudaGetLastError());
+    SampleDev& d = w.h_samples[sample];
+    d.pos = (const int32_t*)(base + o_pos);
+    d.seg_off = (const uint32_t*)(base + o_sgo); d.q4_off = (const uint32_t*)(base + o_q4);
+    d.mate = (const int32_t*)(base + o_mate);
+    d.seg_pos = (const int32_t*)(base + o_sp);   d.seg_len = (const uint16_t*)(base + o_sl);
+    d.seq2 = base + o_seq;                      d.qual = base + o_qual;
+    d.fix = has_mates ? base + o_fix : nullptr;
+    d.n_reads = r->n_reads; d.max_span = r->max_span ? r->max_span : 1;
+    w.n_reads += n; w.n_bases += 4ull * n_q4; w.n_segs += n_seg;
+    w.sizes[sample] = msnv_sample_sizes{r->n_reads, 0, d.max_span, 0, (uint64_t)n_seg, (uint64_t)n_q4, 0};      // n_aligned: see msnv_window_sample_sizes
+    return MSNV_OK;
+}
+
+int msnv_expand_stats(msnv_ctx* ctx, uint64_t* iupac_bases)
+{
+    if (!ctx || !iupac_bases) return MSNV_E_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    unsigned long long v = 0;
+    CU(cudaMemcpy(&v, ctx->d_xstat, 8, cudaMemcpyDeviceToHost));
+    *iupac_bases = v;
     return MSNV_OK;
 }
 
@@ -983,18 +1069,21 @@ int msnv_shard_synth(msnv_ctx* ctx, const msnv_synth_desc* d, int64_t* first_col
     return msnv_window_synth(ctx, 0, d, 0, d->n_contigs);
 }
 
-int msnv_shard_sample_sizes(msnv_ctx* ctx, uint32_t sample, msnv_sample_sizes* sizes)
-{
-    if (!ctx || !sizes) return MSNV_E_ARG;
-    if (!ctx->open || sample >= ctx->S) return fail(ctx, MSNV_E_ARG, "msnv_shard_sample_sizes: no such sample");
-    *sizes = ctx->win[0].sizes[sample];
-    return MSNV_OK;
-}
+int msnv_window_sample_sizes(msnv_ctx* ctx, uint32_t slot, uint32_t sample, msnv_sample_sizes* sizes);
+int msnv_shard_sample_sizes(msnv_ctx* ctx, uint32_t sample, msnv_sample_sizes* sizes) { return msnv_window_sample_sizes(ctx, 0, sample, sizes); }
 
 int msnv_window_sample_sizes(msnv_ctx* ctx, uint32_t slot, uint32_t sample, msnv_sample_sizes* sizes)
 {
     if (!ctx || !sizes) return MSNV_E_ARG;
     if (!ctx->open || slot >= (uint32_t)N_SLOTS || !ctx->win[slot].open || sample >= ctx->S) return fail(ctx, MSNV_E_ARG, "msnv_window_sample_sizes: no such sample");
+    msnv_ctx::Window& w = ctx->win[slot];
+    if (w.has_raw && w.sizes[sample].n_reads && w.sizes[sample].n_aligned == 0) {        // expanded on the device: its count is there
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaStreamSynchronize(ctx->copy_stream));
+        unsigned long long v = 0;
+        CU(cudaMemcpy(&v, w.d_aligned + sample, 8, cudaMemcpyDeviceToHost));
+        w.sizes[sample].n_aligned = v;
+    }
     *sizes = ctx->win[slot].sizes[sample];
     return MSNV_OK;
 }

@@ -132,6 +132,22 @@ msnv_sample_reads SampleReads::view() const
     return v;
 }
 
+msnv_raw_reads RawReads::view() const
+{
+    msnv_raw_reads v;
+    memset(&v, 0, sizeof v);
+    v.n_reads = (uint32_t)pos.size();
+    v.max_span = max_span;
+    v.pos = pos.data(); v.mate = mate.data(); v.seg_off = seg_off.data(); v.q4_off = q4_off.data(); v.raw_off = raw_off.data();
+    v.n_cigar = n_cigar.data(); v.l_seq = l_seq.data(); v.raw = reinterpret_cast<const uint8_t*>(raw.data());
+    return v;
+}
+
+size_t RawReads::bytes() const
+{
+    return pos.size() * 8 + seg_off.size() * 4 + q4_off.size() * 4 + raw_off.size() * 4 + n_cigar.size() * 2 + l_seq.size() * 2 + raw.size() * 4;
+}
+
 size_t SampleReads::bytes() const
 {
     return pos.size() * 4 + seg_off.size() * 4 + q4_off.size() * 4 + mate.size() * 4 + seg_pos.size() * 4 +
@@ -234,7 +250,20 @@ static int next_record(SampleDecoderState& S, BamRecord& r)
 
 bool SampleDecoder::window(uint32_t pos_lo, uint32_t pos_hi, const SampleReads* prev, SampleReads& out, std::string& err)
 {
+    return window_impl(pos_lo, pos_hi, prev, &out, nullptr, nullptr, err);
+}
+
+bool SampleDecoder::window_raw(uint32_t pos_lo, uint32_t pos_hi, const RawReads* prev, RawReads& out, std::string& err)
+{
+    return window_impl(pos_lo, pos_hi, nullptr, nullptr, prev, &out, err);
+}
+
+bool SampleDecoder::window_impl(uint32_t pos_lo, uint32_t pos_hi, const SampleReads* prev, SampleReads* out_p, const RawReads* prev_raw, RawReads* out_raw,
+                                std::string& err)
+{
     SampleDecoderState& S = *st_;
+    SampleReads dummy;
+    SampleReads& out = out_p ? *out_p : dummy;
     const ShardLayout& layout = *S.layout;
     const std::vector<int64_t>& ref_len_of_tid = *S.ref_len;
     DecodeStats& st = S.st;
@@ -267,6 +296,35 @@ bool SampleDecoder::window(uint32_t pos_lo, uint32_t pos_hi, const SampleReads* 
         S.base = S.n_emitted - (n - first);
     } else {
         S.base = S.n_emitted;
+    }
+
+    if (out_raw) {
+        RawReads& o = *out_raw;
+        o = RawReads();
+        if (prev_raw && !prev_raw->pos.empty()) {
+            const RawReads& p = *prev_raw;
+            const size_t n = p.pos.size();
+            size_t first = n;
+            for (size_t i = n; i-- > 0;) {
+                if ((int64_t)p.pos[i] + (int64_t)p.max_span <= (int64_t)pos_lo) break;          // no earlier read can reach the window either
+                if ((int64_t)p.end[i] > (int64_t)pos_lo) first = i;
+            }
+            if (first < n) {
+                const uint32_t s0 = p.seg_off[first], q0 = p.q4_off[first], r0 = p.raw_off[first];
+                o.pos.assign(p.pos.begin() + first, p.pos.end());
+                o.end.assign(p.end.begin() + first, p.end.end());
+                o.n_cigar.assign(p.n_cigar.begin() + first, p.n_cigar.end());
+                o.l_seq.assign(p.l_seq.begin() + first, p.l_seq.end());
+                o.seg_off.resize(n - first + 1); o.q4_off.resize(n - first + 1); o.raw_off.resize(n - first + 1); o.mate.resize(n - first);
+                for (size_t i = first; i <= n; ++i) { o.seg_off[i - first] = p.seg_off[i] - s0; o.q4_off[i - first] = p.q4_off[i] - q0; o.raw_off[i - first] = p.raw_off[i] - r0; }
+                for (size_t i = first; i < n; ++i) { const int64_t m = (int64_t)p.mate[i] - (int64_t)first; o.mate[i - first] = m >= 0 ? (int32_t)m : -1; }
+                o.raw.assign(p.raw.begin() + r0, p.raw.end());
+                o.max_span = p.max_span;
+            }
+            S.base = S.n_emitted - (n - first);
+        } else {
+            S.base = S.n_emitted;
+        }
     }
 
     BamRecord r;
@@ -371,6 +429,42 @@ bool SampleDecoder::window(uint32_t pos_lo, uint32_t pos_hi, const SampleReads* 
                 if (it->second.end > c.pos && it->second.ordinal >= S.base) mate_idx = (int32_t)(it->second.ordinal - S.base);
                 S.olap.erase(it);
             }
+        }
+        if (out_raw) {
+            // ---- BAM-shaped batch: offsets of the aligned layout (the device fills it) and the record's own bytes
+            RawReads& o = *out_raw;
+            size_t quads = 0, q_len = 0;
+            {
+                uint32_t rx = ctg.offset + (uint32_t)c.pos;
+                for (int i = 0; i < c.n_cigar; ++i) {
+                    const uint32_t w = r.cigar_at(i), op = w & 0xf, len = w >> 4;
+                    if (op == CIG_M || op == CIG_EQ || op == CIG_X) { if (len) { quads += ((rx & 3u) + len + 3u) >> 2; st.aligned_bases += len; } rx += len; q_len += len; }
+                    else if (op == CIG_D || op == CIG_N) rx += len;
+                    else if (op == CIG_I || op == CIG_S) q_len += len;
+                }
+            }
+            if (q_len > (size_t)c.l_seq) { err = bam_path + ": read " + r.qname + ": CIGAR longer than the sequence"; return false; }
+            if (o.q4_off.back() + quads > 0xffffffffull) { err = bam_path + ": more than 2^34 bases in one shard of one sample"; return false; }
+            o.pos.push_back((int32_t)(ctg.offset + (uint32_t)c.pos));
+            o.end.push_back((int32_t)(ctg.offset + (uint32_t)end));
+            o.mate.push_back(mate_idx);
+            if (mate_idx >= 0) { o.mate[(size_t)mate_idx] = (int32_t)idx; ++st.pairs; }
+            o.seg_off.push_back(o.seg_off.back() + n_seg);
+            o.q4_off.push_back((uint32_t)(o.q4_off.back() + quads));
+            o.n_cigar.push_back((uint16_t)c.n_cigar);
+            o.l_seq.push_back((uint16_t)c.l_seq);
+            const size_t nb = 4 * (size_t)c.n_cigar + (size_t)((c.l_seq + 1) / 2) + (size_t)c.l_seq, nw = (nb + 3) / 4;
+            const size_t w0 = o.raw.size();
+            o.raw.resize(w0 + nw, 0);
+            memcpy(o.raw.data() + w0, r.cigar, nb);                      // CIGAR, bases and qualities are contiguous in the record
+            o.raw_off.push_back((uint32_t)(w0 + nw));
+            if ((uint32_t)rlen > o.max_span) o.max_span = (uint32_t)rlen;
+            if (st.first_column < 0) {
+                int64_t p = layout.first_inside(slot, c.pos, end);
+                if (p >= 0) st.first_column = (int64_t)ctg.offset + p;
+            }
+            ++st.accepted;
+            continue;
         }
         // ---- append to the structure of arrays
         out.pos.push_back((int32_t)(ctg.offset + (uint32_t)c.pos));

@@ -59,6 +59,19 @@ struct SampleReads {
     size_t bytes() const;
 };
 
+// The same batch as BAM stores it (msnv_raw_reads): the device walks the CIGARs and packs the bases (expand_kernel), the
+// decoding thread only copies the record's own bytes. `end` (one past the last reference base, shard coordinate) is the
+// host's: it decides which reads a later window still needs.
+struct RawReads {
+    std::vector<int32_t>  pos, end, mate;
+    std::vector<uint32_t> seg_off{0}, q4_off{0}, raw_off{0};
+    std::vector<uint16_t> n_cigar, l_seq;
+    std::vector<uint32_t> raw;
+    uint32_t max_span = 0;
+    msnv_raw_reads view() const;
+    size_t bytes() const;
+};
+
 struct SampleDecoderState;
 
 struct DecodeStats {
@@ -89,9 +102,12 @@ public:
     bool open(const std::string& bam_path, const ShardLayout& layout, const std::vector<int64_t>& ref_len_of_tid, int inflate_threads,
               const std::string& index_hint, std::string& err);
     bool window(uint32_t pos_lo, uint32_t pos_hi, const SampleReads* prev, SampleReads& out, std::string& err);
+    // the same window as BAM-shaped records (the aligned layout is then built on the device)
+    bool window_raw(uint32_t pos_lo, uint32_t pos_hi, const RawReads* prev, RawReads& out, std::string& err);
     const DecodeStats& stats() const;
     bool used_index() const;
 private:
+    bool window_impl(uint32_t pos_lo, uint32_t pos_hi, const SampleReads* prev, SampleReads* out, const RawReads* prev_raw, RawReads* out_raw, std::string& err);
     SampleDecoderState* st_;
 };
 

@@ -56,6 +56,15 @@ int main(int argc, char** argv)
             !dump(p + "seg_pos.bin", r.seg_pos) || !dump(p + "seg_len.bin", r.seg_len) || !dump(p + "seq2.bin", r.seq2) || !dump(p + "qual.bin", r.qual)) {
             fprintf(stderr, "msnv_decode_dump: cannot write to %s\n", out.c_str()); return 1;
         }
+        if (getenv("MSNV_DUMP_RAW")) {
+            // the same sample as BAM-shaped records (what snpCall uploads when the device expands them)
+            SampleDecoder d2; RawReads rr;
+            if (!d2.open(bams[s], layout, ref_len, 1, std::string(), err) || !d2.window_raw(0, layout.n_positions, nullptr, rr, err)) { fprintf(stderr, "msnv_decode_dump: %s\n", err.c_str()); return 1; }
+            if (!dump(p + "raw_pos.bin", rr.pos) || !dump(p + "raw_mate.bin", rr.mate) || !dump(p + "raw_seg_off.bin", rr.seg_off) || !dump(p + "raw_q4_off.bin", rr.q4_off) ||
+                !dump(p + "raw_off.bin", rr.raw_off) || !dump(p + "raw_n_cigar.bin", rr.n_cigar) || !dump(p + "raw_l_seq.bin", rr.l_seq) || !dump(p + "raw.bin", rr.raw)) {
+                fprintf(stderr, "msnv_decode_dump: cannot write to %s\n", out.c_str()); return 1;
+            }
+        }
         fprintf(js, "%s{\"n_reads\": %zu, \"n_segs\": %zu, \"n_q4\": %zu, \"max_span\": %u, \"first_column\": %lld, \"records\": %llu, \"accepted\": %llu, "
                     "\"dropped_by_cap\": %llu, \"aligned_bases\": %llu, \"pairs\": %llu, \"decode_s\": %.6f, \"inflate_s\": %.6f}",
                 s ? ", " : "", r.pos.size(), r.seg_pos.size(), r.seq2.size(), r.max_span, (long long)st.first_column, (unsigned long long)st.records,

@@ -122,3 +122,48 @@ def numpy_counts(e, P):
     flat = np.bincount((pos * 5 + ch)[ok], minlength=P * 5)
     assert flat.size == P * 5, "a base lies outside the shard"
     return flat.reshape(P, 5).astype(np.uint16)
+
+
+RAW_ARRAYS = (("raw_pos", np.int32), ("raw_mate", np.int32), ("raw_seg_off", np.uint32), ("raw_q4_off", np.uint32),
+              ("raw_off", np.uint32), ("raw_n_cigar", np.uint16), ("raw_l_seq", np.uint16), ("raw", np.uint32))
+
+
+def expand_raw(r):
+    """Plain-Python restatement of expand_kernel (csrc/gpu/kernels.cuh): reads as BAM stores them (msnv_raw_reads) -> the
+    position-aligned arrays of msnv_sample_reads. Slow on purpose (one base at a time); for small batches only."""
+    n = r["raw_pos"].size
+    raw8 = r["raw"].view(np.uint8)
+    n_seg, n_q4 = int(r["raw_seg_off"][-1]), int(r["raw_q4_off"][-1])
+    seg_pos = np.zeros(n_seg, np.int32); seg_len = np.zeros(n_seg, np.uint16)
+    seq2 = np.zeros(n_q4, np.uint8); qual = np.zeros(4 * n_q4, np.uint8)
+    code = {1: 0, 2: 1, 4: 2, 8: 3}                       # "=ACMGRSVTWYHKDBN": the one-hot codes are A, C, G, T
+    for i in range(n):
+        b0 = 4 * int(r["raw_off"][i])
+        nc, ls = int(r["raw_n_cigar"][i]), int(r["raw_l_seq"][i])
+        cig = r["raw"][int(r["raw_off"][i]):int(r["raw_off"][i]) + nc]
+        seq4 = raw8[b0 + 4 * nc:b0 + 4 * nc + (ls + 1) // 2]
+        ql = raw8[b0 + 4 * nc + (ls + 1) // 2:b0 + 4 * nc + (ls + 1) // 2 + ls]
+        rx, qy, k, Q = int(r["raw_pos"][i]), 0, int(r["raw_seg_off"][i]), int(r["raw_q4_off"][i])
+        for w in cig:
+            op, ln = int(w) & 15, int(w) >> 4
+            if op in (0, 7, 8):
+                if ln:
+                    a = rx & 3
+                    seg_pos[k], seg_len[k] = rx, ln
+                    for o in range(ln):
+                        q = qy + o
+                        b4 = (int(seq4[q >> 1]) >> (4 if q % 2 == 0 else 0)) & 15
+                        other = b4 not in code
+                        at = 4 * Q + a + o
+                        qual[at] = min(int(ql[q]), 127) | (0x80 if other else 0)
+                        if not other:
+                            seq2[at >> 2] |= code[b4] << (2 * (at & 3))
+                    k += 1; Q += (a + ln + 3) >> 2
+                rx += ln; qy += ln
+            elif op in (2, 3):
+                rx += ln
+            elif op in (1, 4):
+                qy += ln
+        assert k == int(r["raw_seg_off"][i + 1]) and Q == int(r["raw_q4_off"][i + 1]) and qy <= ls
+    return {"pos": r["raw_pos"], "mate": r["raw_mate"], "seg_off": r["raw_seg_off"], "q4_off": r["raw_q4_off"],
+            "seg_pos": seg_pos, "seg_len": seg_len, "seq2": seq2, "qual": qual}

@@ -13,18 +13,22 @@ import pytest
 from conftest import GOLDEN
 from metasnv_b200 import harness as H
 from metasnv_b200.paths import bin_path
-from pileup_counts import ARRAYS, check_layout, numpy_counts, oracle_counts
+from pileup_counts import ARRAYS, RAW_ARRAYS, check_layout, expand_raw, numpy_counts, oracle_counts
 
 
-def _decode(ref, lst, out):
+def _decode(ref, lst, out, raw=False):
     os.makedirs(out, exist_ok=True)
-    r = subprocess.run([bin_path("msnv_decode_dump"), ref, lst, out], capture_output=True, text=True)
+    env = dict(os.environ, MSNV_DUMP_RAW="1") if raw else None
+    r = subprocess.run([bin_path("msnv_decode_dump"), ref, lst, out], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr
     lay = json.load(open(os.path.join(out, "layout.json")))
     samples = []
     for s, meta in enumerate(lay["samples"]):
         e = {k: np.fromfile(os.path.join(out, "s%d.%s.bin" % (s, k)), dt) for k, dt in ARRAYS}
         e["max_span"] = meta["max_span"]
+        if raw:
+            for k, dt in RAW_ARRAYS:
+                e[k] = np.fromfile(os.path.join(out, "s%d.%s.bin" % (s, k)), dt)
         assert e["pos"].size == meta["n_reads"] and e["seg_pos"].size == meta["n_segs"] and e["seq2"].size == meta["n_q4"]
         samples.append(e)
     return lay, samples
@@ -76,3 +80,33 @@ def test_decoder_hand_written_cases(sams, pile, built, tmp_path):
     lay, batches = _decode(os.path.join(GOLDEN, "hand", "ref.fa"), lst, os.path.join(tmp, "dump"))
     assert lay["tile"] == 1024 and lay["n_positions"] == 2048          # two 40-base contigs, one tile each
     assert _compare(lay, batches, os.path.join(GOLDEN, "hand", pile)) > 50
+
+
+def test_bam_shaped_batches_expand_to_the_aligned_layout(built, tmp_path):
+    """The decoder's other output form - reads as BAM stores them, expanded on the device by expand_kernel - against the
+    aligned layout the decoder builds itself, through a plain-Python restatement of the expansion: hand-written cases
+    (indels, clips, =/X/P/N/H operations, N bases, one-base segments) and a small synthetic set."""
+    tmp = str(tmp_path)
+    bams = []
+    for s in ("s1", "s2", "s4_ops", "s3_refskip", "s5_rules"):
+        out = os.path.join(tmp, s + ".bam")
+        subprocess.run([bin_path("msnv_synth"), "--sam", os.path.join(GOLDEN, "hand", s + ".sam"), "--bam", out], check=True)
+        bams.append(out)
+    lst = os.path.join(tmp, "list")
+    open(lst, "w").write("\n".join(bams) + "\n")
+    sets = [(os.path.join(GOLDEN, "hand", "ref.fa"), lst)]
+    data = os.path.join(tmp, "c1")
+    H.synth(data, "c1", 0.004, 3)
+    sets.append((os.path.join(data, "ref.fa"), os.path.join(data, "all_samples")))
+    n_reads = 0
+    for i, (ref, l) in enumerate(sets):
+        lay, batches = _decode(ref, l, os.path.join(tmp, "dump%d" % i), raw=True)
+        for e in batches:
+            if not e["pos"].size:
+                assert e["raw_pos"].size == 0
+                continue
+            x = expand_raw(e)
+            for k, _ in ARRAYS:
+                assert np.array_equal(x[k], e[k]), k
+            n_reads += e["pos"].size
+    assert n_reads > 1000

@@ -198,3 +198,65 @@ def test_full_size_shard_counts_recount_with_numpy(built):
         for a in ("pos", "pop_mask", "ind_mask", "cov", "allele", "total"):
             assert np.array_equal(getattr(h, a), getattr(h2, a)), a
         assert h.n_hits > 10000
+
+
+def test_expand_kernel_builds_the_aligned_layout(built, tmp_path):
+    """Reads handed over as BAM stores them (msnv_window_add_sample_raw): expand_kernel must build, byte for byte, the
+    position-aligned arrays the host decoder builds itself (and that tests/test_decode_cpu.py pins against the oracle):
+    hand-written CIGAR cases and a synthetic set with indels, clips and N bases. Then the calls must be the same too."""
+    import json
+    from metasnv_b200 import abi
+    from metasnv_b200.paths import bin_path
+    from conftest import GOLDEN
+    from pileup_counts import ARRAYS, RAW_ARRAYS
+    tmp = str(tmp_path)
+    bams = []
+    for s in ("s1", "s2", "s4_ops", "s3_refskip", "s5_rules"):
+        out = os.path.join(tmp, s + ".bam")
+        subprocess.run([bin_path("msnv_synth"), "--sam", os.path.join(GOLDEN, "hand", s + ".sam"), "--bam", out], check=True)
+        bams.append(out)
+    lst = os.path.join(tmp, "list")
+    open(lst, "w").write("\n".join(bams) + "\n")
+    data = os.path.join(tmp, "c1")
+    H.synth(data, "c1", 0.05, 6)
+    ctx = abi.Context(0)
+    for i, (ref, l) in enumerate([(os.path.join(GOLDEN, "hand", "ref.fa"), lst), (os.path.join(data, "ref.fa"), os.path.join(data, "all_samples"))]):
+        out = os.path.join(tmp, "dump%d" % i)
+        os.makedirs(out)
+        r = subprocess.run([bin_path("msnv_decode_dump"), ref, l, out], capture_output=True, text=True, env=dict(os.environ, MSNV_DUMP_RAW="1"))
+        assert r.returncode == 0, r.stderr
+        lay = json.load(open(os.path.join(out, "layout.json")))
+        S, P = len(lay["samples"]), lay["n_positions"]
+        refc = np.fromfile(os.path.join(out, "ref.bin"), np.uint8)
+        host, raw = [], []
+        for s, meta in enumerate(lay["samples"]):
+            e = {k: np.fromfile(os.path.join(out, "s%d.%s.bin" % (s, k)), dt) for k, dt in ARRAYS}
+            e["max_span"] = meta["max_span"]
+            x = {k[4:] if k.startswith("raw_") and k != "raw_off" else k: np.fromfile(os.path.join(out, "s%d.%s.bin" % (s, k)), dt) for k, dt in RAW_ARRAYS}
+            x["max_span"] = meta["max_span"]
+            host.append(e); raw.append(x)
+        # (a) device expansion == host layout
+        ctx.shard_begin(S, refc)
+        for s in range(S):
+            if raw[s]["pos"].size:
+                ctx.window_add_sample_raw(0, s, raw[s])
+        n = 0
+        for s in range(S):
+            d = ctx.export_sample(s)
+            for k, _ in ARRAYS:
+                assert np.array_equal(d[k], host[s][k]), (i, s, k)
+            n += d["pos"].size
+        assert n > 20
+        assert ctx.sample_sizes(0).n_aligned == int(host[0]["seg_len"].sum())
+        h_raw = ctx.shard_run(min_coverage=2, calling_threshold=2)
+        # (b) the same calls from either input form
+        ctx.shard_begin(S, refc)
+        for s in range(S):
+            if host[s]["pos"].size:
+                ctx.shard_add_sample(s, host[s])
+        h_host = ctx.shard_run(min_coverage=2, calling_threshold=2)
+        assert h_raw.n_hits == h_host.n_hits and h_raw.n_hits > 0
+        for k in ("pos", "pop_mask", "ind_mask", "cov", "allele", "total"):
+            assert np.array_equal(getattr(h_raw, k), getattr(h_host, k)), k
+    assert ctx.expand_stats() == 0
+    ctx.close()

@@ -28,7 +28,7 @@ def test_abi_exports_every_declared_symbol(built):
     for n in sorted(names):
         assert hasattr(lib, n), "libmsnv_gpu.so does not export %s" % n
     lib.msnv_abi_version.restype = ctypes.c_int
-    assert lib.msnv_abi_version() == 5
+    assert lib.msnv_abi_version() == 6
 
 
 def test_abi_python_binding_matches_struct_sizes(built):
