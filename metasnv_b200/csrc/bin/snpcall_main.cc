@@ -69,69 +69,102 @@ static int pick_device(const std::string& indiv_path)
 
 struct Job { std::string ref, bed, list; };
 
-// Pinned bounce buffers between the decoding threads and the device. Page-locking memory costs about a second per two
-// gigabytes, so the pool is small (a few chunks, locked in the background while the reference is being read) and
-// recycled: a decoding thread copies its finished batch into a free chunk, the main thread queues the upload from
-// there (DMA at the host link's rate, it overlaps the decoding) and hands the chunks back once the copies have run.
+// Pinned bounce buffers between the decoding threads and the device. Page-locking memory costs about a second per
+// gigabyte, so the pool is small (a few chunks, locked in the background while the reference is being read) and
+// recycled: a decoding thread copies its finished batch into the chunk that is being filled (several batches share a
+// chunk), the main thread queues the upload from there (DMA at the host link's rate, it overlaps the decoding) and a
+// chunk goes back to the pool once it is full and the copies of all its batches have run.
 struct BouncePool {
     static constexpr size_t CHUNK = (size_t)128 << 20;
+    struct Chunk { uint8_t* base; size_t used; int pending; bool sealed; };
     std::mutex mu;
     std::condition_variable cv;
-    std::vector<uint8_t*> free_chunks, all_chunks;
-    size_t wanted = 0;
-    bool closed = false;                                   // no more chunks will ever come (allocation failed or stopped)
-    void add(uint8_t* p) { { std::lock_guard<std::mutex> lk(mu); free_chunks.push_back(p); all_chunks.push_back(p); } cv.notify_all(); }
+    std::vector<Chunk> chunks;
+    std::vector<int> free_ids;
+    int cur = -1;                                          // the chunk being filled
+    bool closed = false;                                   // no more chunks will come (allocation failed or stopped)
+    void add(uint8_t* p) { { std::lock_guard<std::mutex> lk(mu); chunks.push_back(Chunk{p, 0, 0, false}); free_ids.push_back((int)chunks.size() - 1); } cv.notify_all(); }
     void close() { { std::lock_guard<std::mutex> lk(mu); closed = true; } cv.notify_all(); }
-    // a free chunk; waits while chunks are in flight or still being locked. nullptr: there is no pool (use pageable memory)
-    uint8_t* acquire() {
+    // room for one batch: (pointer, chunk id), or (nullptr, -1) when the batch is larger than a chunk or there is no pool
+    uint8_t* acquire(size_t bytes, int& id) {
+        const size_t need = (bytes + 255) & ~(size_t)255;
+        id = -1;
+        if (need > CHUNK) return nullptr;
         std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return !free_chunks.empty() || (closed && all_chunks.empty()); });
-        if (free_chunks.empty()) return nullptr;
-        uint8_t* p = free_chunks.back(); free_chunks.pop_back();
+        for (;;) {
+            if (cur >= 0 && chunks[cur].used + need <= CHUNK) break;
+            if (cur >= 0) { chunks[cur].sealed = true; maybe_free(cur); cur = -1; }
+            if (!free_ids.empty()) { cur = free_ids.back(); free_ids.pop_back(); chunks[cur].used = 0; chunks[cur].sealed = false; break; }
+            if (closed && chunks.empty()) return nullptr;
+            cv.wait(lk);
+        }
+        Chunk& c = chunks[cur];
+        uint8_t* p = c.base + c.used;
+        c.used += need; ++c.pending;
+        id = cur;
         return p;
     }
-    void release(const std::vector<uint8_t*>& v) { { std::lock_guard<std::mutex> lk(mu); free_chunks.insert(free_chunks.end(), v.begin(), v.end()); } cv.notify_all(); }
+    // the copies of these batches have run
+    void release(const std::vector<int>& ids) {
+        { std::lock_guard<std::mutex> lk(mu); for (int id : ids) { --chunks[id].pending; maybe_free(id); } }
+        cv.notify_all();
+    }
+private:
+    void maybe_free(int id) { if (chunks[id].sealed && chunks[id].pending == 0) { chunks[id].sealed = false; chunks[id].used = 0; free_ids.push_back(id); } }
 };
 
+// offsets of consecutive arrays inside one block: the rule the library uses for its device blocks (msnv_gpu.cu), so that a batch
+// packed this way goes up in one or two copies instead of eight
+static size_t pack_step(size_t& off, size_t bytes) { const size_t o = off; off = (off + bytes + 32 + 255) & ~(size_t)255; return o; }
+
 // one sample's batch as the library wants it: copied into a bounce chunk when it fits one (else the decoder's own arrays)
-static msnv_sample_reads stage_batch(const SampleReads& r, BouncePool& pool, uint8_t*& chunk)
+static msnv_sample_reads stage_batch(const SampleReads& r, BouncePool& pool, int& chunk)
 {
     msnv_sample_reads v = r.view();
-    chunk = nullptr;
-    if (v.n_reads == 0 || r.bytes() + 8 * 256 > BouncePool::CHUNK) return v;
-    uint8_t* p = pool.acquire();
+    chunk = -1;
+    if (v.n_reads == 0) return v;
+    size_t off = 0;
+    const size_t o_pos = pack_step(off, r.pos.size() * 4), o_sgo = pack_step(off, r.seg_off.size() * 4), o_q4 = pack_step(off, r.q4_off.size() * 4),
+                 o_mate = pack_step(off, r.mate.size() * 4), o_sp = pack_step(off, r.seg_pos.size() * 4), o_sl = pack_step(off, r.seg_len.size() * 2),
+                 o_seq = pack_step(off, r.seq2.size()), o_qual = pack_step(off, r.qual.size());
+    uint8_t* p = pool.acquire(off, chunk);
     if (!p) return v;
-    chunk = p;
-    auto put = [&](const void* src, size_t bytes) { uint8_t* d = p; memcpy(d, src, bytes); p += (bytes + 255) & ~(size_t)255; return d; };
-    v.pos = (const int32_t*)put(r.pos.data(), r.pos.size() * 4);
-    v.seg_off = (const uint32_t*)put(r.seg_off.data(), r.seg_off.size() * 4);
-    v.q4_off = (const uint32_t*)put(r.q4_off.data(), r.q4_off.size() * 4);
-    v.mate = (const int32_t*)put(r.mate.data(), r.mate.size() * 4);
-    v.seg_pos = (const int32_t*)put(r.seg_pos.data(), r.seg_pos.size() * 4);
-    v.seg_len = (const uint16_t*)put(r.seg_len.data(), r.seg_len.size() * 2);
-    v.seq2 = put(r.seq2.data(), r.seq2.size());
-    v.qual = put(r.qual.data(), r.qual.size());
+    auto put = [&](size_t o, const void* src, size_t bytes) { memcpy(p + o, src, bytes); return p + o; };
+    v.pos = (const int32_t*)put(o_pos, r.pos.data(), r.pos.size() * 4);
+    v.seg_off = (const uint32_t*)put(o_sgo, r.seg_off.data(), r.seg_off.size() * 4);
+    v.q4_off = (const uint32_t*)put(o_q4, r.q4_off.data(), r.q4_off.size() * 4);
+    v.mate = (const int32_t*)put(o_mate, r.mate.data(), r.mate.size() * 4);
+    v.seg_pos = (const int32_t*)put(o_sp, r.seg_pos.data(), r.seg_pos.size() * 4);
+    v.seg_len = (const uint16_t*)put(o_sl, r.seg_len.data(), r.seg_len.size() * 2);
+    v.seq2 = put(o_seq, r.seq2.data(), r.seq2.size());
+    v.qual = put(o_qual, r.qual.data(), r.qual.size());
     return v;
 }
 
 // the same for a BAM-shaped batch (the device expands it)
-static msnv_raw_reads stage_raw(const RawReads& r, BouncePool& pool, uint8_t*& chunk)
+static msnv_raw_reads stage_raw(const RawReads& r, BouncePool& pool, int& chunk)
 {
     msnv_raw_reads v = r.view();
-    chunk = nullptr;
-    if (v.n_reads == 0 || r.bytes() + 8 * 256 > BouncePool::CHUNK) return v;
-    uint8_t* p = pool.acquire();
+    chunk = -1;
+    if (v.n_reads == 0) return v;
+    size_t off = 0;
+    const size_t o_pos = pack_step(off, r.pos.size() * 4), o_sgo = pack_step(off, r.seg_off.size() * 4), o_q4 = pack_step(off, r.q4_off.size() * 4),
+                 o_mate = pack_step(off, r.mate.size() * 4);
+    size_t off2 = 0;                                       // second group: what the library stages for expand_kernel
+    const size_t s_off = pack_step(off2, r.raw_off.size() * 4), s_raw = pack_step(off2, r.raw.size() * 4), s_nc = pack_step(off2, r.n_cigar.size() * 2),
+                 s_ls = pack_step(off2, r.l_seq.size() * 2);
+    uint8_t* p = pool.acquire(off + off2, chunk);
     if (!p) return v;
-    chunk = p;
-    auto put = [&](const void* src, size_t bytes) { uint8_t* d = p; memcpy(d, src, bytes); p += (bytes + 255) & ~(size_t)255; return d; };
-    v.pos = (const int32_t*)put(r.pos.data(), r.pos.size() * 4);
-    v.mate = (const int32_t*)put(r.mate.data(), r.mate.size() * 4);
-    v.seg_off = (const uint32_t*)put(r.seg_off.data(), r.seg_off.size() * 4);
-    v.q4_off = (const uint32_t*)put(r.q4_off.data(), r.q4_off.size() * 4);
-    v.raw_off = (const uint32_t*)put(r.raw_off.data(), r.raw_off.size() * 4);
-    v.n_cigar = (const uint16_t*)put(r.n_cigar.data(), r.n_cigar.size() * 2);
-    v.l_seq = (const uint16_t*)put(r.l_seq.data(), r.l_seq.size() * 2);
-    v.raw = put(r.raw.data(), r.raw.size() * 4);
+    uint8_t* p2 = p + off;
+    auto put = [&](uint8_t* base, size_t o, const void* src, size_t bytes) { memcpy(base + o, src, bytes); return base + o; };
+    v.pos = (const int32_t*)put(p, o_pos, r.pos.data(), r.pos.size() * 4);
+    v.seg_off = (const uint32_t*)put(p, o_sgo, r.seg_off.data(), r.seg_off.size() * 4);
+    v.q4_off = (const uint32_t*)put(p, o_q4, r.q4_off.data(), r.q4_off.size() * 4);
+    v.mate = (const int32_t*)put(p, o_mate, r.mate.data(), r.mate.size() * 4);
+    v.raw_off = (const uint32_t*)put(p2, s_off, r.raw_off.data(), r.raw_off.size() * 4);
+    v.raw = put(p2, s_raw, r.raw.data(), r.raw.size() * 4);
+    v.n_cigar = (const uint16_t*)put(p2, s_nc, r.n_cigar.data(), r.n_cigar.size() * 2);
+    v.l_seq = (const uint16_t*)put(p2, s_ls, r.l_seq.data(), r.l_seq.size() * 2);
     return v;
 }
 
@@ -267,12 +300,12 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     struct WindowJob {
         std::vector<std::thread> pool; std::atomic<uint32_t> next{0}; std::atomic<bool> failed{false};
         std::mutex mu; std::vector<uint32_t> ready; std::string err; uint32_t n_done = 0;
-        std::vector<msnv_sample_reads> view; std::vector<msnv_raw_reads> rview; std::vector<uint8_t*> chunk;       // per sample: the staged batch
+        std::vector<msnv_sample_reads> view; std::vector<msnv_raw_reads> rview; std::vector<int> chunk;       // per sample: the staged batch
     };
     auto start_window = [&](WindowJob& J, uint32_t k) {
         const uint32_t lo = k * tiles_per_window * MSNV_TILE, hi = std::min<uint64_t>((uint64_t)(k + 1) * tiles_per_window * MSNV_TILE, layout.n_positions);
         J.next = 0; J.failed = false; J.ready.clear(); J.err.clear(); J.n_done = 0;
-        J.view.assign(raw_mode ? 0 : S, msnv_sample_reads{}); J.rview.assign(raw_mode ? S : 0, msnv_raw_reads{}); J.chunk.assign(S, nullptr);
+        J.view.assign(raw_mode ? 0 : S, msnv_sample_reads{}); J.rview.assign(raw_mode ? S : 0, msnv_raw_reads{}); J.chunk.assign(S, -1);
         for (int t = 0; t < n_threads; ++t)
             J.pool.emplace_back([&J, &dec, &batch, &rbatch, &pool, raw_mode, k, lo, hi, S]() {
                 for (;;) {
@@ -317,7 +350,7 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
         if (n_windows > 1 && msnv_window_begin(ctx, slot, lo, hi) != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); rc = 1; }
         // drain: queue the upload of every batch of this window as soon as its thread is through, hand bounce chunks back
         uint32_t taken = 0;
-        std::vector<uint8_t*> in_flight;
+        std::vector<int> in_flight;
         auto recycle = [&]() {
             if (in_flight.empty()) return true;
             const double a = now_s();
@@ -335,17 +368,17 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
                 continue;
             }
             taken += (uint32_t)got.size();
-            if (cur->failed) { for (uint32_t s : got) if (cur->chunk[s]) in_flight.push_back(cur->chunk[s]); recycle(); continue; }
+            if (cur->failed) { for (uint32_t s : got) if (cur->chunk[s] >= 0) in_flight.push_back(cur->chunk[s]); recycle(); continue; }
             for (uint32_t s : got) {
                 const double a = now_s();
                 const uint32_t lib_slot = n_windows > 1 ? slot : 0u;          // (one window: the whole shard, opened by msnv_shard_begin in slot 0)
                 const int arc = raw_mode ? msnv_window_add_sample_raw(ctx, lib_slot, s, &cur->rview[s]) : msnv_window_add_sample(ctx, lib_slot, s, &cur->view[s]);
                 if (arc != MSNV_OK) { fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); rc = 1; break; }
-                if (cur->chunk[s]) in_flight.push_back(cur->chunk[s]);
-                (cur->chunk[s] ? h2d_bytes : pageable_bytes) += raw_mode ? rbatch[slot][s].bytes() : batch[slot][s].bytes();
+                if (cur->chunk[s] >= 0) in_flight.push_back(cur->chunk[s]);
+                (cur->chunk[s] >= 0 ? h2d_bytes : pageable_bytes) += raw_mode ? rbatch[slot][s].bytes() : batch[slot][s].bytes();
                 t_add += now_s() - a;
             }
-            if (in_flight.size() >= 3 && !recycle()) { rc = 1; break; }
+            if (in_flight.size() >= 48 && !recycle()) { rc = 1; break; }
         }
         if (!recycle()) rc = 1;
         if (rc) { cur->failed = true; pool.close(); }
@@ -446,7 +479,7 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     // (each cudaFree is a device-wide synchronisation) would only add seconds
     stop_pinning = true;
     if (pinner.joinable()) pinner.join();
-    if (getenv("MSNV_CLEAN_EXIT")) { for (uint8_t* p : pool.all_chunks) msnv_pinned_free(p); msnv_destroy(ctx); }
+    if (getenv("MSNV_CLEAN_EXIT")) { for (auto& c : pool.chunks) msnv_pinned_free(c.base); msnv_destroy(ctx); }
     return 0;
 }
 

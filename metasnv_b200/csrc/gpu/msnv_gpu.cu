@@ -734,14 +734,23 @@ int msnv_window_add_sample(msnv_ctx* ctx, uint32_t slot, uint32_t sample, const 
     uint8_t* base = (uint8_t*)take_block(ctx, w, off);
     if (!base) return fail(ctx, MSNV_E_NOMEM, "sample %u: cannot allocate %zu bytes of device memory; process the shard in smaller windows (msnv_window_begin) or smaller genome bins (metaSNV.py --n_splits)", sample, off);
     cudaStream_t st = ctx->copy_stream;
-    CU(cudaMemcpyAsync(base + o_pos, r->pos, n * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_sgo, r->seg_off, n1 * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_q4, r->q4_off, n1 * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_mate, r->mate, n * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_sp, r->seg_pos, n_seg * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_sl, r->seg_len, n_seg * 2, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_seq, r->seq2, n_q4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_qual, r->qual, n_q4 * 4, cudaMemcpyHostToDevice, st));
+    {
+        // a caller that packed the arrays the way this block is laid out (same order, same spacing) gets ONE copy instead of eight
+        const uint8_t* h0 = reinterpret_cast<const uint8_t*>(r->pos);
+        auto at = [&](const void* p, size_t o) { return reinterpret_cast<const uint8_t*>(p) == h0 + (o - o_pos); };
+        if (at(r->seg_off, o_sgo) && at(r->q4_off, o_q4) && at(r->mate, o_mate) && at(r->seg_pos, o_sp) && at(r->seg_len, o_sl) && at(r->seq2, o_seq) && at(r->qual, o_qual)) {
+            CU(cudaMemcpyAsync(base + o_pos, h0, o_qual + n_q4 * 4 - o_pos, cudaMemcpyHostToDevice, st));
+        } else {
+            CU(cudaMemcpyAsync(base + o_pos, r->pos, n * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(base + o_sgo, r->seg_off, n1 * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(base + o_q4, r->q4_off, n1 * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(base + o_mate, r->mate, n * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(base + o_sp, r->seg_pos, n_seg * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(base + o_sl, r->seg_len, n_seg * 2, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(base + o_seq, r->seq2, n_q4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(base + o_qual, r->qual, n_q4 * 4, cudaMemcpyHostToDevice, st));
+        }
+    }
     SampleDev& d = w.h_samples[sample];
     d.pos = (const int32_t*)(base + o_pos);
     d.seg_off = (const uint32_t*)(base + o_sgo); d.q4_off = (const uint32_t*)(base + o_q4);
@@ -788,21 +797,37 @@ int msnv_window_add_sample_raw(msnv_ctx* ctx, uint32_t slot, uint32_t sample, co
     uint8_t* base = (uint8_t*)take_block(ctx, w, off);
     if (!base) return fail(ctx, MSNV_E_NOMEM, "sample %u: cannot allocate %zu bytes of device memory; process the shard in smaller windows (msnv_window_begin) or smaller genome bins (metaSNV.py --n_splits)", sample, off);
     // staging of the BAM-shaped arrays: raw_off | raw | n_cigar | l_seq
-    const size_t s_off = 0, s_raw = align_up(n1 * 4, 256), s_nc = align_up(s_raw + raw_words * 4, 256), s_ls = align_up(s_nc + n * 2, 256), s_end = s_ls + n * 2;
+    size_t soff = 0;
+    auto stake = [&](size_t bytes) { size_t o = soff; soff = align_up(soff + bytes + 32, 256); return o; };
+    const size_t s_off = stake(n1 * 4), s_raw = stake(raw_words * 4), s_nc = stake(n * 2), s_ls = stake(n * 2), s_end = soff;
     if (s_end > ctx->cap_raw) {
         const uint64_t cap = s_end + s_end / 4 + (1u << 20);
         if (grow(ctx, ctx->d_raw, cap)) return MSNV_E_CUDA;
         ctx->cap_raw = cap;
     }
     cudaStream_t st = ctx->copy_stream;
-    CU(cudaMemcpyAsync(base + o_pos, r->pos, n * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_sgo, r->seg_off, n1 * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_q4, r->q4_off, n1 * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_mate, r->mate, n * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->d_raw + s_off, r->raw_off, n1 * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->d_raw + s_raw, r->raw, raw_words * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->d_raw + s_nc, r->n_cigar, n * 2, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->d_raw + s_ls, r->l_seq, n * 2, cudaMemcpyHostToDevice, st));
+    {
+        // packed callers (same order and spacing as the device side): two copies instead of eight
+        const uint8_t* h0 = reinterpret_cast<const uint8_t*>(r->pos);
+        const uint8_t* g0 = reinterpret_cast<const uint8_t*>(r->raw_off);
+        auto at = [](const void* p, const uint8_t* b, size_t o) { return reinterpret_cast<const uint8_t*>(p) == b + o; };
+        if (at(r->seg_off, h0, o_sgo - o_pos) && at(r->q4_off, h0, o_q4 - o_pos) && at(r->mate, h0, o_mate - o_pos)) {
+            CU(cudaMemcpyAsync(base + o_pos, h0, o_mate + n * 4 - o_pos, cudaMemcpyHostToDevice, st));
+        } else {
+            CU(cudaMemcpyAsync(base + o_pos, r->pos, n * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(base + o_sgo, r->seg_off, n1 * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(base + o_q4, r->q4_off, n1 * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(base + o_mate, r->mate, n * 4, cudaMemcpyHostToDevice, st));
+        }
+        if (at(r->raw, g0, s_raw - s_off) && at(r->n_cigar, g0, s_nc - s_off) && at(r->l_seq, g0, s_ls - s_off)) {
+            CU(cudaMemcpyAsync(ctx->d_raw + s_off, g0, s_ls + n * 2 - s_off, cudaMemcpyHostToDevice, st));
+        } else {
+            CU(cudaMemcpyAsync(ctx->d_raw + s_off, r->raw_off, n1 * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(ctx->d_raw + s_raw, r->raw, raw_words * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(ctx->d_raw + s_nc, r->n_cigar, n * 2, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(ctx->d_raw + s_ls, r->l_seq, n * 2, cudaMemcpyHostToDevice, st));
+        }
+    }
     // the aligned arrays are built in place: padding bytes must be 0
     CU(cudaMemsetAsync(base + o_seq, 0, n_q4 + 32, st));
     RawDev in;
