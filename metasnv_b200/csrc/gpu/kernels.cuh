@@ -394,10 +394,13 @@ __global__ void __launch_bounds__(256) fix_clear_kernel(const SampleDev* __restr
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) f[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// A warp takes 32 consecutive reads, picks the ones that open a pair (the earlier mate) by ballot and hands them out four
-// at a time to its four groups of eight lanes: every lane works on a pair, one quad of both mates per lane and step. The
-// mates are stored position-aligned, so their quads line up word for word; a step of a pair is two coalesced loads of up
-// to 32 bytes per mate and one coalesced store of up to 8 verdict bytes per mate.
+// A warp takes 32 consecutive reads, picks the ones that open a pair (the earlier mate) by ballot and hands them out eight
+// at a time to its eight groups of four lanes: every lane works on a pair, one quad of both mates per lane and step. The
+// mates are stored position-aligned, so their quads line up word for word; a step of a pair is two coalesced 16-byte loads
+// per mate and one 4-byte store of verdicts per mate. (Four lanes rather than eight per pair: a 100-base overlap is 18 quads,
+// and the per-pair set-up - offsets, segment records - is paid once per warp pass however many pairs share it.)
+constexpr uint32_t MATE_LANES = 4;
+
 __global__ void __launch_bounds__(256) mate_kernel(const SampleDev* __restrict__ samples, const uint32_t* __restrict__ which)
 {
     const SampleDev sd = samples[which[blockIdx.y]];
@@ -405,23 +408,52 @@ __global__ void __launch_bounds__(256) mate_kernel(const SampleDev* __restrict__
     const uint32_t* __restrict__ qual32 = reinterpret_cast<const uint32_t*>(sd.qual);
     uint32_t* __restrict__ fix32 = reinterpret_cast<uint32_t*>(sd.fix);
     const uint32_t nq_total = sd.n_reads ? __ldg(sd.q4_off + sd.n_reads) : 0u;
-    const uint32_t lane = threadIdx.x & 31u, l8 = lane & 7u, grp = lane >> 3;
+    constexpr uint32_t GROUPS = 32u / MATE_LANES;
+    const uint32_t lane = threadIdx.x & 31u, lg = lane % MATE_LANES, grp = lane / MATE_LANES;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5, warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // the quads [lo, hi) (positions) that a segment of a at (ax, first quad qa) and one of b at (bx, qb) share
+    auto overlap = [&](int32_t ax, uint32_t qa, int32_t bx, uint32_t qb, int32_t lo, int32_t hi) {
+        for (int32_t P = (lo >> 2) + (int32_t)lg; P < ((hi + 3) >> 2); P += (int32_t)MATE_LANES) {      // (empty when the segments share no position)
+            const uint32_t ia = qa + (uint32_t)(P - (ax >> 2)), ib = qb + (uint32_t)(P - (bx >> 2));
+            if (ia >= nq_total || ib >= nq_total) continue;           // segments and offsets disagree (the pileup kernel reports it)
+            const uint32_t va = __ldg(qual32 + ia), vb = __ldg(qual32 + ib);
+            const uint32_t d = msnv_spread_bases((uint32_t)__ldg(sd.seq2 + ia) ^ (uint32_t)__ldg(sd.seq2 + ib));
+            const bool whole = (P << 2) >= lo && (P << 2) + 4 <= hi;
+            const uint32_t msk = whole ? 0xffffffffu : msnv_quad_mask(P << 2, lo, hi);
+            uint32_t na, nb;
+            msnv_overlap_pass4(va, vb, d, msk, na, nb);               // masked lanes: flag | 16 (passes) or flag | 0
+            const uint32_t ovr = lanes_to_nibble(msk);
+            const uint32_t fa = ovr | (lanes_to_nibble(na >> 4) & ovr) << 4, fb = ovr | (lanes_to_nibble(nb >> 4) & ovr) << 4;
+            // a quad the rule covers whole belongs to this segment combination alone: plain byte stores. Two
+            // combinations can meet in a quad at their ends (with disjoint positions): OR into the byte there.
+            if (whole) { sd.fix[ia] = (uint8_t)fa; sd.fix[ib] = (uint8_t)fb; }
+            else {
+                atomicOr(fix32 + (ia >> 2), fa << (8u * (ia & 3u)));
+                atomicOr(fix32 + (ib >> 2), fb << (8u * (ib & 3u)));
+            }
+        }
+    };
     for (uint32_t base = warp0 * 32u; base < sd.n_reads; base += warps * 32u) {
         const uint32_t r_l = base + lane;
         const int32_t mt_l = r_l < sd.n_reads ? __ldg(sd.mate + r_l) : -1;
         uint32_t open = __ballot_sync(0xffffffffu, mt_l > (int32_t)r_l && (uint32_t)mt_l < sd.n_reads);     // the earlier mate (a) handles the pair
         while (open) {
-            // the grp-th of the next (up to) four pairs
+            // the grp-th of the next (up to) GROUPS pairs
             const uint32_t src = __fns(open, 0u, grp + 1u);                                                   // 0xffffffff when there are fewer
             const bool have = src < 32u;
             const int32_t mt = __shfl_sync(0xffffffffu, mt_l, have ? src : 0u);
             const uint32_t r = base + (have ? src : 0u);
-            { uint32_t k = __popc(open); k = k < 4u ? k : 4u; for (uint32_t i = 0; i < k; ++i) open &= open - 1u; }
+            { uint32_t k = __popc(open); k = k < GROUPS ? k : GROUPS; for (uint32_t i = 0; i < k; ++i) open &= open - 1u; }
             if (!have) continue;
             const uint32_t sa0 = __ldg(sd.seg_off + r), sa1 = __ldg(sd.seg_off + r + 1), sb0 = __ldg(sd.seg_off + mt), sb1 = __ldg(sd.seg_off + mt + 1);
             uint32_t qa = __ldg(sd.q4_off + r);                                   // first quad of a's next segment
             const uint32_t qb0 = __ldg(sd.q4_off + mt);
+            if (sa1 - sa0 == 1u && sb1 - sb0 == 1u) {                             // the common case: both mates are one segment
+                const int32_t ax = __ldg(sd.seg_pos + sa0), bx = __ldg(sd.seg_pos + sb0);
+                const int32_t ae = ax + (int32_t)__ldg(sd.seg_len + sa0), be = bx + (int32_t)__ldg(sd.seg_len + sb0);
+                overlap(ax, qa, bx, qb0, max(ax, bx), min(ae, be));
+                continue;
+            }
             for (uint32_t ka = sa0; ka < sa1; ++ka) {
                 const int32_t ax = __ldg(sd.seg_pos + ka);
                 const uint32_t al = __ldg(sd.seg_len + ka);
@@ -429,26 +461,7 @@ __global__ void __launch_bounds__(256) mate_kernel(const SampleDev* __restrict__
                 for (uint32_t kb = sb0; kb < sb1; ++kb) {
                     const int32_t bx = __ldg(sd.seg_pos + kb);
                     const uint32_t bl = __ldg(sd.seg_len + kb);
-                    const int32_t lo = max(ax, bx), hi = min(ax + (int32_t)al, bx + (int32_t)bl);
-                    for (int32_t P = (lo >> 2) + (int32_t)l8; P < ((hi + 3) >> 2); P += 8) {      // (empty when the segments share no position)
-                        const uint32_t ia = qa + (uint32_t)(P - (ax >> 2)), ib = qb + (uint32_t)(P - (bx >> 2));
-                        if (ia >= nq_total || ib >= nq_total) continue;           // segments and offsets disagree (the pileup kernel reports it)
-                        const uint32_t va = __ldg(qual32 + ia), vb = __ldg(qual32 + ib);
-                        const uint32_t d = msnv_spread_bases((uint32_t)__ldg(sd.seq2 + ia) ^ (uint32_t)__ldg(sd.seq2 + ib));
-                        const bool whole = (P << 2) >= lo && (P << 2) + 4 <= hi;
-                        const uint32_t msk = whole ? 0xffffffffu : msnv_quad_mask(P << 2, lo, hi);
-                        uint32_t na, nb;
-                        msnv_overlap_pass4(va, vb, d, msk, na, nb);               // masked lanes: flag | 16 (passes) or flag | 0
-                        const uint32_t ovr = lanes_to_nibble(msk);
-                        const uint32_t fa = ovr | (lanes_to_nibble(na >> 4) & ovr) << 4, fb = ovr | (lanes_to_nibble(nb >> 4) & ovr) << 4;
-                        // a quad the rule covers whole belongs to this segment combination alone: plain byte stores. Two
-                        // combinations can meet in a quad at their ends (with disjoint positions): OR into the byte there.
-                        if (whole) { sd.fix[ia] = (uint8_t)fa; sd.fix[ib] = (uint8_t)fb; }
-                        else {
-                            atomicOr(fix32 + (ia >> 2), fa << (8u * (ia & 3u)));
-                            atomicOr(fix32 + (ib >> 2), fb << (8u * (ib & 3u)));
-                        }
-                    }
+                    overlap(ax, qa, bx, qb, max(ax, bx), min(ax + (int32_t)al, bx + (int32_t)bl));
                     qb += (((uint32_t)bx & 3u) + bl + 3u) >> 2;
                 }
                 qa += (((uint32_t)ax & 3u) + al + 3u) >> 2;
