@@ -537,19 +537,22 @@ __global__ void expect_kernel(const uint8_t* __restrict__ ref, uint32_t n, uint8
 // The mate-overlap rule itself runs before this kernel (mate_kernel): no read ever waits for its mate here.
 //
 // Shared memory (dynamic, see pileup_smem_layout): mbarriers | 6 count planes | quad tags |
-// PL_STAGES x { header, q4_off, seg_off, seg_pos, seg_len, expected letters, bases, overlap
+// stages x { header, q4_off, seg_off, seg_pos, seg_len, expected letters, bases, overlap
 // verdicts, qualities }. Every TMA destination is 16-byte aligned; sources are the 16-byte
 // aligned addresses at or below the first element needed (the arrays are 256-byte aligned and have
 // 32 spare bytes behind them), so a stage holds a few elements in front of and behind the chunk.
 // ------------------------------------------------------------------------------------------------
 // consumer threads per CTA: a template parameter of the kernel (128 or 256; the CTA has one more warp, the producer)
-constexpr int PL_STAGES = 2;
+constexpr uint32_t PL_STAGES_MAX = 8;          // stages of the ring: PileupShape::stages (2 unless the host chose otherwise)
 constexpr uint32_t CHUNK_Q4_MIN = MSNV_MAX_READ_BASES / 4 + 2 * MSNV_MAX_READ_SEGMENTS;   // a single read always fits
 constexpr uint32_t CHUNK_SEGS_MIN = MSNV_MAX_READ_SEGMENTS;
 constexpr uint32_t CHUNK_FIRST = 1u, CHUNK_LAST = 2u, CHUNK_WIDE = 4u, CHUNK_STOP = 8u, CHUNK_FIX = 16u /* the sample has mate verdicts */;
 
 // limits of one staged chunk, chosen per launch from the shape of the shard
-struct PileupShape { uint32_t max_reads, max_segs, chunk_q4, has_fix /* some sample carries mate verdicts */, wait_hint_ns, ablate /* measurement only: phases to skip */; };
+struct PileupShape { uint32_t max_reads, max_segs, chunk_q4, has_fix /* some sample carries mate verdicts */, wait_hint_ns, ablate /* measurement only: phases to skip */,
+                     gather /* stages carry the gather kernel's segment records and ranges instead of the scatter kernel's tags */,
+                     stages /* of the ring, 2 .. PL_STAGES_MAX */,
+                     producer_hint_ns /* how long the producer warp may be parked while it waits for a free stage */; };
 
 struct ChunkHdr { uint32_t m, nq4, q4_0, sg_0, nseg, c0, item, sample, tile, flags, pad[6]; };
 static_assert(sizeof(ChunkHdr) == 64, "header is one 64-byte block");
@@ -557,6 +560,7 @@ static_assert(sizeof(ChunkHdr) == 64, "header is one 64-byte block");
 struct PileupSmem {
     uint32_t bar, cnt, tags, stage0, stage_bytes;                               // byte offsets
     uint32_t o_hdr, o_q4, o_sg, o_sp, o_sl, o_exp, o_seq, o_fix, o_qual;        // within a stage
+    uint32_t o_set, o_rec, o_lohi;                                              // within a stage, gather kernel only (written by its consumers)
     uint32_t total;
 };
 
@@ -568,7 +572,7 @@ __host__ __device__ inline PileupSmem pileup_smem_layout(const PileupShape sh)
     uint32_t o = 0;
     L.bar = o;   o += 128;
     L.cnt = o;   o += N_PLANES * TILE;
-    L.tags = o;  o += up_to(sh.chunk_q4, 16) + 16;
+    L.tags = o;  o += sh.gather ? 0u : up_to(sh.chunk_q4, 16) + 16;
     L.stage0 = up_to(o, 128);
     uint32_t s = 0;
     const uint32_t mw = up_to(sh.max_reads + 1, 4) + 8;
@@ -581,8 +585,13 @@ __host__ __device__ inline PileupSmem pileup_smem_layout(const PileupShape sh)
     L.o_seq = s;  s += up_to(sh.chunk_q4, 16) + 32;
     L.o_fix = s;  s += sh.has_fix ? up_to(sh.chunk_q4, 16) + 32 : 0;
     L.o_qual = s; s += 4 * up_to(sh.chunk_q4, 16) + 32;
+    if (sh.gather) {
+        L.o_set = s;  s += 64;
+        L.o_rec = s;  s += (up_to(sh.max_segs, 4) + 8) * 8;
+        L.o_lohi = s; s += TILE_QUADS * 4;
+    }
     L.stage_bytes = up_to(s, 128);
-    L.total = L.stage0 + PL_STAGES * L.stage_bytes;
+    L.total = L.stage0 + sh.stages * L.stage_bytes;
     return L;
 }
 
@@ -652,9 +661,9 @@ __device__ __forceinline__ void pileup_issue_chunk(uint8_t* smem, const PileupSm
                                                    uint32_t m, uint32_t q4_0, uint32_t nq4, uint32_t sg_0, uint32_t nseg, uint32_t flags)
 {
     uint64_t* full = (uint64_t*)(smem + L.bar);
-    uint64_t* empty = full + PL_STAGES;
-    const uint32_t s = chunk_no % PL_STAGES, ph = (chunk_no / PL_STAGES) & 1u;
-    mbar_wait(empty + s, ph ^ 1u, sh.wait_hint_ns);
+    uint64_t* empty = full + sh.stages;
+    const uint32_t s = chunk_no % sh.stages, ph = (chunk_no / sh.stages) & 1u;
+    mbar_wait(empty + s, ph ^ 1u, sh.producer_hint_ns);
     if ((threadIdx.x & 31) == issuer) {
         uint8_t* stage = smem + L.stage0 + s * L.stage_bytes;
         ChunkHdr* h = (ChunkHdr*)(stage + L.o_hdr);
@@ -767,9 +776,9 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
     }
     // ---- no more items: tell the consumers
     uint64_t* full = (uint64_t*)(smem + L.bar);
-    uint64_t* empty = full + PL_STAGES;
-    const uint32_t s = chunk_no % PL_STAGES, ph = (chunk_no / PL_STAGES) & 1u;
-    mbar_wait(empty + s, ph ^ 1u, sh.wait_hint_ns);
+    uint64_t* empty = full + sh.stages;
+    const uint32_t s = chunk_no % sh.stages, ph = (chunk_no / sh.stages) & 1u;
+    mbar_wait(empty + s, ph ^ 1u, sh.producer_hint_ns);
     if (lane == 0) {
         ((ChunkHdr*)(smem + L.stage0 + s * L.stage_bytes + L.o_hdr))->flags = CHUNK_STOP;
         mbar_arrive(full + s);
@@ -787,11 +796,11 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
     extern __shared__ __align__(128) uint8_t smem[];
     const PileupSmem L = pileup_smem_layout(sh);
     uint64_t* full = (uint64_t*)(smem + L.bar);
-    uint64_t* empty = full + PL_STAGES;
+    uint64_t* empty = full + sh.stages;
     uint32_t* s_cnt = (uint32_t*)(smem + L.cnt);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < PL_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (uint32_t s = 0; s < sh.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t k = threadIdx.x; k < (uint32_t)(N_PLANES * TILE_QUADS); k += CONSUMERS + 32) s_cnt[k] = 0;
@@ -814,7 +823,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
         for (int k = 0; k < QPT; ++k) acc[c][k][0] = acc[c][k][1] = 0;
 
     for (uint32_t chunk_no = 0;; ++chunk_no) {
-        const uint32_t st = chunk_no % PL_STAGES, ph = (chunk_no / PL_STAGES) & 1u;
+        const uint32_t st = chunk_no % sh.stages, ph = (chunk_no / sh.stages) & 1u;
         uint8_t* stage = smem + L.stage0 + st * L.stage_bytes;
         mbar_wait(full + st, ph, sh.wait_hint_ns);
         const ChunkHdr* h = (const ChunkHdr*)(stage + L.o_hdr);
@@ -991,6 +1000,337 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
             }
         }
         // no barrier here: the next chunk touches the counters again only after its own barriers
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pileup, gather form. Same ring, same stages, same count planes as pileup_kernel; what differs is who adds what:
+// a consumer thread OWNS tile quads (four positions each) and walks the aligned segments that cover them, so the counts
+// live in registers - no shared-memory atomics, no tags, no cleared planes - and go straight from the registers to HBM.
+// A consumer warp releases the stage on its own when it has read it (the stage's "empty" barrier counts warps).
+//
+// The geometry the consumers need is built per chunk by the consumers themselves, a thread per read (gather_setup, two
+// CTA-wide barriers: a single warp doing it - tried first, in the producer - takes longer than the counting):
+//   * a record per segment, clipped to the tile: first and last+1 tile quad, and the buffer quad that holds tile quad 0
+//   * per tile quad j the range [lo_j, hi_j) of segments that can cover it. Reads are in coordinate order, so
+//     hi_j = first segment of the first read that starts behind j, and lo_j = first segment of the first read r whose
+//     running maximum of read ends (a warp scan, block maxima through shared memory) passes j. Both are written as runs
+//     by the thread that owns the read.
+// For a read that covers j the segments in between are its neighbours in the file: at 10x and 100-base reads a thread
+// looks at ~12 records to find its ~10.
+//
+// Per (quad, segment) step: one 64-bit record, the quad's four qualities and its base byte; quality test on byte lanes;
+// D += pass; the letters are counted as three bit-plane sums (bit 0 set, bit 1 set, both set) from which the four letter
+// counts follow at the end of the item by subtraction - the expected letter is not needed inside the loop at all. With 128
+// consumers a thread owns two neighbouring quads, which share the record and its range test.
+//
+// Narrow items (at most 255 reads: a byte lane cannot overflow) stay in the registers of the threads that own their quads
+// over as many chunks as the item takes. Deep items (cut into chunks of 255 reads that start within a few positions of each
+// other): a chunk then spans only part of the tile, so the 256 quad slots are dealt out as G groups of W quads (W = the
+// chunk's span rounded up to a power of two), group g taking every G-th segment; the partial sums are added to the shared
+// planes (one atomic per non-zero word instead of one per staged quad) and the planes are folded as in pileup_kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t clamp_quad(int32_t v) { return v < 0 ? 0 : (v > TILE_QUADS ? TILE_QUADS : v); }
+
+// Layout of a stage's "set" block (16 words): [0] jmin, [1] jmax (quads [jmin, jmax) can be covered), [2..9] maximum of the
+// read ends per block of 32 reads.
+template <int CONSUMERS>
+__device__ __forceinline__ void gather_setup(uint8_t* stage, const PileupSmem& L, int* __restrict__ err_flag)
+{
+    constexpr int RPT = (int)(NARROW_MAX_READS + CONSUMERS) / CONSUMERS;    // reads per thread (a chunk stages at most 255)
+    constexpr int N_WARPS = CONSUMERS / 32;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const ChunkHdr* h = (const ChunkHdr*)(stage + L.o_hdr);
+    const uint32_t m = h->m, nq4 = h->nq4, q4_0 = h->q4_0, sg_0 = h->sg_0, nseg = h->nseg, c0 = h->c0;
+    const int32_t p0 = (int32_t)(h->tile * TILE);
+    const uint32_t dm = c0 & 3u, dq = q4_0 & 3u;
+    const uint32_t* s_q4 = (const uint32_t*)(stage + L.o_q4) + dm;          // s_q4[t] = q4_off[c0 + t], t <= m
+    const uint32_t* s_sgo = (const uint32_t*)(stage + L.o_sg) + dm;
+    const int32_t* s_sp = (const int32_t*)(stage + L.o_sp) + (sg_0 & 3u);   // s_sp[k] = seg_pos[sg_0 + k], k < nseg
+    const uint16_t* s_sl = (const uint16_t*)(stage + L.o_sl) + (sg_0 & 7u);
+    uint2* recs = (uint2*)(stage + L.o_rec);
+    uint16_t* lohi = (uint16_t*)(stage + L.o_lohi);                         // [2 j] = lo_j, [2 j + 1] = hi_j
+    int32_t* set = (int32_t*)(stage + L.o_set);
+    const uint32_t nbq = dq + nq4;
+    // first tile quad (clipped) of read t's first segment; 256 behind the last read
+    auto read_start = [&](uint32_t t) -> int32_t {
+        if (t >= m) return TILE_QUADS;
+        const uint32_t k = s_sgo[t] - sg_0;
+        if (k >= nseg) return TILE_QUADS;
+        return clamp_quad((s_sp[k] - p0) >> 2);
+    };
+    int32_t aq[RPT], pb[RPT];
+    uint32_t k0[RPT], k1[RPT];
+    // ---- records; per block of 32 reads the maximum of the read ends
+    #pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const uint32_t t = tid + (uint32_t)i * CONSUMERS;
+        int32_t eq = 0;
+        aq[i] = TILE_QUADS; k0[i] = k1[i] = 0;
+        if (t < m) {
+            k0[i] = s_sgo[t] - sg_0; k1[i] = s_sgo[t + 1] - sg_0;
+            uint32_t B = s_q4[t] - q4_0 + dq;                                   // first buffer quad of the next segment
+            const uint32_t B_end = s_q4[t + 1] - q4_0 + dq;
+            if (k1[i] < k0[i] || k1[i] > nseg || B_end < B || B_end > nbq) { atomicExch(err_flag, 2); k0[i] = k1[i] = 0; }   // offsets not prefix sums
+            aq[i] = read_start(t);
+            for (uint32_t k = k0[i]; k < k1[i]; ++k) {
+                const int32_t p = s_sp[k];
+                const uint32_t len = s_sl[k];
+                const uint32_t a = (uint32_t)p & 3u;
+                const int32_t nq = (int32_t)((a + len + 3u) >> 2);
+                const int32_t jw = (p - (int32_t)a - p0) >> 2;                  // tile-relative index of the segment's first quad
+                int32_t lo = clamp_quad(jw), hi = clamp_quad(jw + nq);
+                if (B + (uint32_t)nq > B_end) { atomicExch(err_flag, 2); lo = hi = 0; }    // segments and offsets disagree: the run fails
+                recs[k] = make_uint2((uint32_t)((int32_t)B - jw), hi > lo ? (uint32_t)lo | (uint32_t)hi << 16 : 0u);
+                if (hi > lo && hi > eq) eq = hi;
+                B += (uint32_t)nq;
+            }
+            if (B != B_end) atomicExch(err_flag, 2);                            // quads no segment owns
+            if (t == 0) set[0] = aq[i];                                         // jmin
+        }
+        if ((uint32_t)i * CONSUMERS < m) {                                      // (uniform)
+            int32_t v = eq;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int32_t o = __shfl_up_sync(0xffffffffu, v, d); if ((int)lane >= d && o > v) v = o; }
+            pb[i] = v;
+            if (lane == 31) set[2 + i * N_WARPS + (int)warp] = v;
+        } else pb[i] = 0;
+    }
+    if (m == 0 && tid == 0) { set[0] = 0; set[1] = 0; }
+    consumer_sync<CONSUMERS>();
+    // ---- running maximum over the blocks in front, then the two ranges as runs
+    const int32_t jmin = m ? set[0] : 0;
+    #pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const uint32_t t = tid + (uint32_t)i * CONSUMERS;
+        if ((uint32_t)i * CONSUMERS >= m) break;                                // (uniform)
+        const int b = i * N_WARPS + (int)warp;
+        int32_t carry = jmin;
+        for (int bb = 0; bb < b; ++bb) { const int32_t v = set[2 + bb]; if (v > carry) carry = v; }
+        int32_t p = pb[i] > carry ? pb[i] : carry;
+        int32_t p_prev = __shfl_up_sync(0xffffffffu, p, 1);
+        if (lane == 0) p_prev = carry;
+        if (t < m) {
+            for (int32_t j = p_prev; j < p; ++j) lohi[2 * j] = (uint16_t)k0[i];
+            const int32_t upper = t + 1 < m ? read_start(t + 1) : p;
+            for (int32_t j = aq[i]; j < upper; ++j) lohi[2 * j + 1] = (uint16_t)k1[i];
+            if (t + 1 == m) set[1] = p;                                         // jmax (>= jmin)
+        }
+    }
+    consumer_sync<CONSUMERS>();
+}
+
+__device__ __forceinline__ uint2 lds_v2(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+template <int OFF> __device__ __forceinline__ uint32_t lds_u32_at(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF)); return v; }
+template <int OFF> __device__ __forceinline__ uint32_t lds_u8_at(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF)); return v; }
+__device__ __forceinline__ uint32_t and3(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+
+// The records at shared addresses a_rec, a_rec + stride, ... < a_end against the NQ consecutive tile quads j0, j0 + 1, ...
+// of this thread (FIX: the sample carries mate verdicts). a_qj / a_sj / a_fj: shared addresses of the qualities / bases /
+// verdicts of "buffer quad j0". One record fetch and one range test serve all NQ quads (neighbouring quads are covered by
+// the same segments except at a segment's ends, where the quad outside is read - the byte in front of or behind the
+// segment is inside the stage - and then ignored).
+template <bool FIX, int NQ>
+__device__ __forceinline__ void gather_quads(uint32_t j0, uint32_t a_rec, uint32_t a_end, uint32_t stride, uint32_t a_qj, uint32_t a_sj, uint32_t a_fj,
+                                             uint32_t (&D)[NQ], uint32_t (&N)[NQ], uint32_t (&X0)[NQ], uint32_t (&X1)[NQ], uint32_t (&X01)[NQ])
+{
+    static_assert(NQ == 1 || NQ == 2, "one or two quads per thread");
+    // No branch inside: a record that covers none of this thread's quads is read at offset 0 (inside the stage) and its
+    // qualities are replaced by 0, which no test passes. Some lane of the warp is covered in nearly every step anyway.
+    #pragma unroll 2
+    for (; a_rec < a_end; a_rec += stride) {
+        const uint2 rec = lds_v2(a_rec);
+        const uint32_t a = rec.y & 0xffffu, len = (rec.y >> 16) - a, t0 = j0 - a;   // quad q is covered iff t0 + q < len (an empty record has len = 0)
+        const bool in0 = t0 < len, in1 = NQ > 1 && t0 + 1u < len;
+        const uint32_t x = (in0 || in1) ? rec.x : 0u;                               // rec.x + j = buffer quad of tile quad j
+        const uint32_t aq = a_qj + 4u * x, as = a_sj + x, af = a_fj + x;
+        uint32_t q[NQ], sv[NQ], f[NQ];
+        q[0] = lds_u32_at<0>(aq); sv[0] = lds_u8_at<0>(as);
+        if (NQ > 1) { q[NQ - 1] = lds_u32_at<4>(aq); sv[NQ - 1] = lds_u8_at<1>(as); }
+        if (FIX) { f[0] = lds_u8_at<0>(af); if (NQ > 1) f[NQ - 1] = lds_u8_at<1>(af); }
+        if (!in0) { q[0] = 0; if (FIX) f[0] = 0; }                                  // quality 0 and no verdict: nothing counts
+        if (NQ > 1 && !in1) { q[NQ - 1] = 0; if (FIX) f[NQ - 1] = 0; }
+        #pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            const uint32_t xs = msnv_spread_bases(sv[i]);                           // one 2-bit base per byte lane
+            uint32_t ok, nn;
+            if (!FIX) {
+                const uint32_t v = (q[i] & 0x7f7f7f7fu) + 0x73737373u;              // bit 7 of a lane: quality >= 13
+                asm("lop3.b32 %0, %1, %2, 0x80808080, 0x20;" : "=r"(ok) : "r"(v), "r"(q[i]));        // ... and the base is A/C/G/T
+                ok >>= 7;
+                nn = and3(v, q[i], 0x80808080u) >> 7;                               // counted base that is not A/C/G/T
+            } else {
+                // where the overlap rule spoke (low nibble of the quad's fix byte) its verdict (high nibble) replaces the quality test
+                const uint32_t ovr = nibble_to_lanes(f[i]), val = nibble_to_lanes(f[i] >> 4);
+                const uint32_t qp = (((q[i] & 0x7f7f7f7fu) + 0x73737373u) >> 7) & 0x01010101u;
+                const uint32_t pass = (qp & ~ovr) | (val & ovr);
+                const uint32_t fl = (q[i] >> 7) & 0x01010101u;
+                ok = pass & ~fl;
+                nn = pass & fl;
+            }
+            const uint32_t s1 = xs >> 1;
+            D[i] += ok; N[i] += nn;
+            X0[i] += xs & ok; X1[i] += s1 & ok; X01[i] += and3(xs, s1, ok);
+        }
+    }
+}
+
+template <int CONSUMERS, bool HAS_WIDE>
+__global__ void __launch_bounds__(CONSUMERS + 32, CONSUMERS == 128 ? 4 : 3)
+pileup_gather_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ items, uint32_t n_items, const PileupShape sh,
+                     const uint8_t* __restrict__ expect, uint8_t* __restrict__ tiles /*[n_items][SLOT_BYTES]*/, int* __restrict__ err_flag)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const PileupSmem L = pileup_smem_layout(sh);
+    uint64_t* full = (uint64_t*)(smem + L.bar);
+    uint64_t* empty = full + sh.stages;
+    uint32_t* s_cnt = (uint32_t*)(smem + L.cnt);
+    constexpr int N_WARPS = CONSUMERS / 32;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < sh.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, N_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (uint32_t k = threadIdx.x; k < (uint32_t)(N_PLANES * TILE_QUADS); k += CONSUMERS + 32) s_cnt[k] = 0;
+    // records and ranges start out empty: a failed consistency check (which fails the run) must not leave wild indices behind
+    for (uint32_t s = 0; s < sh.stages; ++s) {
+        uint32_t* z = (uint32_t*)(smem + L.stage0 + s * L.stage_bytes + L.o_set);
+        for (uint32_t k = threadIdx.x; k < (L.stage_bytes - L.o_set) / 4u; k += CONSUMERS + 32) z[k] = 0;
+    }
+    __syncthreads();
+
+    if (threadIdx.x >= CONSUMERS) {
+        pileup_producer(smem, L, sh, samples, items, n_items, expect, err_flag);
+        return;
+    }
+
+    // ------------------------------------------------------------------------------------ consumers
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    constexpr int QPT = TILE_QUADS / CONSUMERS;                 // quad slots per thread (2 or 1): slots QPT * tid, QPT * tid + 1
+    // wide items: per plane and owned quad (QPT * tid + k), 16-bit lanes: [0] = positions 0 and 2, [1] = positions 1 and 3
+    uint32_t acc[HAS_WIDE ? N_PLANES : 1][QPT][2];
+    #pragma unroll
+    for (int c = 0; c < (HAS_WIDE ? N_PLANES : 1); ++c)
+        #pragma unroll
+        for (int k = 0; k < QPT; ++k) acc[c][k][0] = acc[c][k][1] = 0;
+    uint32_t D[QPT], N[QPT], X0[QPT], X1[QPT], X01[QPT];        // counts of this thread's quads (see gather_quads)
+    #pragma unroll
+    for (int i = 0; i < QPT; ++i) D[i] = N[i] = X0[i] = X1[i] = X01[i] = 0;
+
+    for (uint32_t chunk_no = 0;; ++chunk_no) {
+        const uint32_t st = chunk_no % sh.stages, ph = (chunk_no / sh.stages) & 1u;
+        uint8_t* stage = smem + L.stage0 + st * L.stage_bytes;
+        mbar_wait(full + st, ph, sh.wait_hint_ns);
+        const ChunkHdr* h = (const ChunkHdr*)(stage + L.o_hdr);
+        const uint32_t flags = h->flags;
+        if (flags & CHUNK_STOP) break;
+        if (!(sh.ablate & 2u)) gather_setup<CONSUMERS>(stage, L, err_flag);
+        const uint32_t nseg = h->nseg, item = h->item, c12 = h->q4_0 & 12u;
+        const uint2* recs = (const uint2*)(stage + L.o_rec);
+        const uint32_t* lohi = (const uint32_t*)(stage + L.o_lohi);
+        const uint32_t* s_qw = (const uint32_t*)(stage + L.o_qual);            // qualities of buffer quad B in word B
+        const uint8_t* s_sq = stage + L.o_seq + c12;
+        const uint8_t* s_fx = stage + L.o_fix + c12;
+        const uint32_t* s_exp = (const uint32_t*)(stage + L.o_exp);
+        const uint32_t* set = (const uint32_t*)(stage + L.o_set);
+        const uint32_t jmin = set[0], jmax = set[1];
+        const bool has_fix = (flags & CHUNK_FIX) != 0;
+        // narrow items (at most 255 reads: a byte lane cannot overflow) stay in the registers of the threads that own their
+        // quads, over as many chunks as the item takes, and go from there to HBM; deep items go through the shared planes
+        const bool direct = !(flags & CHUNK_WIDE);
+        uint32_t wsh = 8;                                                       // log2 of the quads per group of slots
+        if (!direct) { const uint32_t span = jmax - jmin; wsh = span <= 32u ? 5u : span <= 64u ? 6u : span <= 128u ? 7u : 8u; }
+        const uint32_t G = (uint32_t)TILE_QUADS >> wsh;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tiles + (size_t)item * SLOT_BYTES);
+        const uint32_t a_recs = smem_u32(recs), a_q = smem_u32(s_qw), a_s = smem_u32(s_sq), a_f = smem_u32(s_fx);
+
+        // this thread's QPT consecutive quad slots
+        const uint32_t v0 = (uint32_t)QPT * tid;
+        const uint32_t j0 = direct ? v0 : jmin + (v0 & ((1u << wsh) - 1u)), grp = direct ? 0u : v0 >> wsh;
+        if (!direct || (flags & CHUNK_FIRST)) {
+            #pragma unroll
+            for (int i = 0; i < QPT; ++i) D[i] = N[i] = X0[i] = X1[i] = X01[i] = 0;
+        }
+        {
+            // the quads of this thread that a segment of the chunk can cover: [ja, jb)
+            const uint32_t ja = j0 > jmin ? j0 : jmin, jb = j0 + QPT < jmax ? j0 + QPT : jmax;
+            if (ja < jb && !(sh.ablate & 1u)) {
+                const uint32_t lo = lohi[ja] & 0xffffu;
+                uint32_t hi = lohi[jb - 1u] >> 16;
+                if (hi > nseg) hi = nseg;
+                const uint32_t k = lo + ((grp - lo) & (G - 1u));                // first segment of this group at or behind lo
+                if (has_fix) gather_quads<true, QPT>(j0, a_recs + 8u * k, a_recs + 8u * hi, 8u * G, a_q + 4u * j0, a_s + j0, a_f + j0, D, N, X0, X1, X01);
+                else         gather_quads<false, QPT>(j0, a_recs + 8u * k, a_recs + 8u * hi, 8u * G, a_q + 4u * j0, a_s + j0, a_f + j0, D, N, X0, X1, X01);
+            }
+        }
+        uint32_t out[QPT][N_PLANES];
+        if (!direct || (flags & CHUNK_LAST)) {
+            // letter counts from the bit-plane sums; the planes hold only the bases that DIFFER from the expected letter
+            #pragma unroll
+            for (int i = 0; i < QPT; ++i) {
+                const uint32_t e = j0 + i < (uint32_t)TILE_QUADS ? s_exp[j0 + i] : 0u;
+                const uint32_t cnt[4] = {D[i] - X0[i] - X1[i] + X01[i], X0[i] - X01[i], X1[i] - X01[i], X01[i]};
+                out[i][PLANE_D] = D[i];
+                #pragma unroll
+                for (uint32_t l = 0; l < 4u; ++l) {
+                    const uint32_t x = e ^ (l * 0x01010101u);
+                    const uint32_t nz = (x | (x >> 1)) & 0x01010101u;           // lanes whose expected letter is not l
+                    out[i][PLANE_A + l] = cnt[l] & (nz * 255u);
+                }
+                out[i][PLANE_N] = N[i];
+            }
+        }
+        // ---- the stage is read: hand it back (per warp, no CTA-wide barrier)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + st);
+
+        if (direct) {
+            if ((flags & CHUNK_LAST) && !(sh.ablate & 8u)) {
+                #pragma unroll
+                for (int c = 0; c < N_PLANES; ++c) {
+                    if (QPT == 2) reinterpret_cast<uint2*>(dst)[(c * TILE_QUADS + j0) >> 1] = make_uint2(out[0][c], out[QPT - 1][c]);     // (j0 is even)
+                    else dst[c * TILE_QUADS + j0] = out[0][c];
+                }
+            }
+            continue;
+        }
+        // ---- deep items: partial sums into the shared planes, folded into 16-bit lanes held in registers
+        #pragma unroll
+        for (int i = 0; i < QPT; ++i)
+            if (j0 + i < (uint32_t)TILE_QUADS) {
+                #pragma unroll
+                for (int c = 0; c < N_PLANES; ++c)
+                    if (out[i][c]) red_shared_add(smem_u32(s_cnt) + 4u * (uint32_t)(c * TILE_QUADS + j0 + i), out[i][c]);
+            }
+        consumer_sync<CONSUMERS>();
+        if (HAS_WIDE) {
+            #pragma unroll
+            for (int c = 0; c < (HAS_WIDE ? N_PLANES : 1); ++c)
+                #pragma unroll
+                for (int k = 0; k < QPT; ++k) {
+                    const uint32_t slot = c * TILE_QUADS + QPT * tid + k;
+                    const uint32_t w = s_cnt[slot];
+                    s_cnt[slot] = 0;
+                    acc[c][k][0] += w & 0x00ff00ffu; acc[c][k][1] += (w >> 8) & 0x00ff00ffu;
+                }
+            if (flags & CHUNK_LAST) {
+                uint2* dst2 = reinterpret_cast<uint2*>(tiles + (size_t)item * SLOT_BYTES);
+                #pragma unroll
+                for (int c = 0; c < (HAS_WIDE ? N_PLANES : 1); ++c)
+                    #pragma unroll
+                    for (int k = 0; k < QPT; ++k) {
+                        // 16-bit plane c, positions 4 * (QPT * tid + k) .. + 3
+                        dst2[c * (TILE / 4) + QPT * tid + k] = make_uint2((acc[c][k][0] & 0xffffu) | (acc[c][k][1] << 16), (acc[c][k][0] >> 16) | (acc[c][k][1] & 0xffff0000u));
+                        acc[c][k][0] = acc[c][k][1] = 0;
+                    }
+            }
+        }
+        consumer_sync<CONSUMERS>();             // the planes are folded and cleared before the next chunk adds to them
     }
 }
 

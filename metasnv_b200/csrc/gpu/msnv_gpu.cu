@@ -281,17 +281,35 @@ int ensure_window_buffers(msnv_ctx* ctx, uint32_t n_tiles_w)
 constexpr size_t SMEM_PER_SM = 233472, SMEM_PER_CTA_MAX = 232448, SMEM_CTA_RESERVED = 1024;
 constexpr uint32_t CHUNK_Q4_CAP = 16384;
 
-static PileupShape choose_pileup_shape(uint64_t n_reads, uint64_t n_bases, uint64_t n_segs, uint64_t n_items, uint64_t item_reads, bool has_fix, int max_ctas, int& ctas)
+// Which pileup kernel: the gather form (counts in registers, kernels.cuh) for ordinary depth, the scatter form for deep shards
+// (hundreds of reads per position: a chunk of 255 reads then covers ~30 quads and the scatter's one atomic per staged quad
+// costs less than the gather's record per (quad, segment) step; measured at C4, profiles/r02_pileup_ablations.txt).
+// MSNV_PILEUP=gather|scatter overrides.
+static bool pileup_gather_mode(bool deep)
+{
+    if (const char* e = getenv("MSNV_PILEUP")) {
+        if (!strcmp(e, "scatter")) return false;
+        if (!strcmp(e, "gather")) return true;
+    }
+    return !deep;
+}
+
+static PileupShape choose_pileup_shape(uint64_t n_reads, uint64_t n_bases, uint64_t n_segs, uint64_t n_items, uint64_t item_reads, uint32_t item_reads_max, bool has_fix, int max_ctas, int& ctas)
 {
     const double reads_per_item = (double)item_reads / (double)(n_items ? n_items : 1);
     const double q4_per_read = (double)n_bases / 4.0 / (double)(n_reads ? n_reads : 1);
     const double segs_per_read = (double)n_segs / (double)(n_reads ? n_reads : 1);
     const bool deep = reads_per_item > 200.0;          // items take several chunks whatever the limits
     PileupShape sh{};
+    sh.gather = pileup_gather_mode(deep) ? 1u : 0u;
     sh.has_fix = has_fix ? 1u : 0u;
     sh.wait_hint_ns = getenv("MSNV_WAIT_HINT_NS") ? (uint32_t)atoi(getenv("MSNV_WAIT_HINT_NS")) : 0u;
     sh.ablate = getenv("MSNV_ABLATE") ? (uint32_t)atoi(getenv("MSNV_ABLATE")) : 0u;
+    sh.stages = 2;
+    sh.producer_hint_ns = getenv("MSNV_PRODUCER_HINT_NS") ? (uint32_t)atoi(getenv("MSNV_PRODUCER_HINT_NS")) : 1000u;
+    if (const char* e = getenv("MSNV_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= (int)PL_STAGES_MAX) sh.stages = (uint32_t)v; }
     uint32_t mr = deep ? (max_ctas <= 3 ? NARROW_MAX_READS : 96u) : (uint32_t)(reads_per_item * 1.3 + 24.0);
+    if (!deep && item_reads_max && mr > item_reads_max) mr = item_reads_max;      // no item has more reads than this
     if (const char* e = getenv("MSNV_MAX_READS")) mr = (uint32_t)atoi(e);
     if (mr < 16) mr = 16;
     if (mr > NARROW_MAX_READS) mr = NARROW_MAX_READS;
@@ -304,6 +322,7 @@ static PileupShape choose_pileup_shape(uint64_t n_reads, uint64_t n_bases, uint6
     auto clampq = [](double q) { uint32_t v = q < 0 ? 0u : (uint32_t)q; if (v < CHUNK_Q4_MIN) v = CHUNK_Q4_MIN; if (v > CHUNK_Q4_CAP) v = CHUNK_Q4_CAP; return up_to(v, 16); };
     uint32_t want = deep ? clampq(mr * q4_per_read * 1.15 + 64.0) : clampq((reads_per_item * 1.25 + 4.0) * q4_per_read + 64.0);
     uint32_t least = deep ? want : clampq(reads_per_item * 1.12 * q4_per_read);
+    if (!deep && item_reads_max) least = std::min(least, clampq((item_reads_max + 1.0) * q4_per_read + 32.0));      // (the largest item, with a little slack)
     if (const char* e = getenv("MSNV_CHUNK_Q4")) want = least = clampq((double)atoi(e));
     auto total_at = [&](uint32_t cq) { PileupShape t = sh; t.chunk_q4 = cq; return (size_t)pileup_smem_layout(t).total; };
     if (const char* e = getenv("MSNV_PILEUP_CTAS")) { const int v = atoi(e); if (v >= 1 && v < max_ctas) max_ctas = v; }
@@ -407,15 +426,20 @@ static int launch_pileup(msnv_ctx* ctx, const msnv_ctx::Window& w, uint32_t a, u
     int ctas = 1;
     bool has_fix = false;
     for (const SampleDev& sd : w.h_samples) has_fix = has_fix || sd.fix;
-    const PileupShape sh = choose_pileup_shape(w.n_reads, w.n_bases, w.n_segs, n_items_window, item_reads, has_fix, consumers == 256 ? 3 : 4, ctas);   // register-bound CTA counts
+    const PileupShape sh = choose_pileup_shape(w.n_reads, w.n_bases, w.n_segs, n_items_window, item_reads, item_reads_max, has_fix, consumers == 256 ? 3 : 4, ctas);   // register-bound CTA counts
     const size_t smem = pileup_smem_layout(sh).total;
     const bool has_wide = item_reads_max > NARROW_MAX_READS;
     const int threads = consumers + 32;
     int fit = 0;
 #define MSNV_PILEUP_DISPATCH(EXPR)                                                                  \
     do {                                                                                            \
-        if (consumers == 256) { if (has_wide) { auto K = pileup_kernel<256, true>; EXPR; } else { auto K = pileup_kernel<256, false>; EXPR; } } \
-        else                  { if (has_wide) { auto K = pileup_kernel<128, true>; EXPR; } else { auto K = pileup_kernel<128, false>; EXPR; } } \
+        if (sh.gather) {                                                                            \
+            if (consumers == 256) { if (has_wide) { auto K = pileup_gather_kernel<256, true>; EXPR; } else { auto K = pileup_gather_kernel<256, false>; EXPR; } } \
+            else                  { if (has_wide) { auto K = pileup_gather_kernel<128, true>; EXPR; } else { auto K = pileup_gather_kernel<128, false>; EXPR; } } \
+        } else {                                                                                    \
+            if (consumers == 256) { if (has_wide) { auto K = pileup_kernel<256, true>; EXPR; } else { auto K = pileup_kernel<256, false>; EXPR; } } \
+            else                  { if (has_wide) { auto K = pileup_kernel<128, true>; EXPR; } else { auto K = pileup_kernel<128, false>; EXPR; } } \
+        }                                                                                           \
     } while (0)
     MSNV_PILEUP_DISPATCH(CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, K, threads, smem)));
     if (fit < 1) return fail(ctx, MSNV_E_CUDA, "pileup kernel does not fit an SM (%zu bytes of shared memory)", smem);
@@ -426,8 +450,8 @@ static int launch_pileup(msnv_ctx* ctx, const msnv_ctx::Window& w, uint32_t a, u
 #undef MSNV_PILEUP_DISPATCH
     ++launches;
     if (getenv("MSNV_VERBOSE"))
-        fprintf(stderr, "msnv: pileup %u items (%.1f reads each, at most %u), %u CTAs (%d per SM) x %d threads%s, stage limits %u reads / %u segments / %u quads, %zu B shared memory\n",
-                n, (double)item_reads / (double)n_items_window, item_reads_max, (unsigned)grid, ctas, threads, has_wide ? " (wide items)" : "", sh.max_reads,
+        fprintf(stderr, "msnv: pileup (%s) %u items (%.1f reads each, at most %u), %u CTAs (%d per SM) x %d threads%s, stage limits %u reads / %u segments / %u quads, %zu B shared memory\n",
+                sh.gather ? "gather" : "scatter", n, (double)item_reads / (double)n_items_window, item_reads_max, (unsigned)grid, ctas, threads, has_wide ? " (wide items)" : "", sh.max_reads,
                 sh.max_segs, sh.chunk_q4, smem);
     return MSNV_OK;
 }
@@ -626,6 +650,10 @@ int msnv_create(int device, msnv_ctx** out)
     CU(cudaFuncSetAttribute(pileup_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PER_CTA_MAX));
     CU(cudaFuncSetAttribute(pileup_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PER_CTA_MAX));
     CU(cudaFuncSetAttribute(pileup_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PER_CTA_MAX));
+    CU(cudaFuncSetAttribute(pileup_gather_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PER_CTA_MAX));
+    CU(cudaFuncSetAttribute(pileup_gather_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PER_CTA_MAX));
+    CU(cudaFuncSetAttribute(pileup_gather_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PER_CTA_MAX));
+    CU(cudaFuncSetAttribute(pileup_gather_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PER_CTA_MAX));
     CU(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     return MSNV_OK;
 }

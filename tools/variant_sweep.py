@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Tuning aid: one device-generated shard, msnv_shard_run under several staging settings of the pileup kernel
-(MSNV_PILEUP_CTAS : MSNV_CHUNK_Q4 : MSNV_MAX_READS : MSNV_WAIT_HINT_NS : MSNV_CONSUMERS : MSNV_ABLATE, empty = the library's own choice)."""
+(MSNV_PILEUP_CTAS : MSNV_CHUNK_Q4 : MSNV_MAX_READS : MSNV_WAIT_HINT_NS : MSNV_CONSUMERS : MSNV_ABLATE : MSNV_PILEUP : MSNV_STAGES : MSNV_PRODUCER_HINT_NS, empty = the library's own choice)."""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from metasnv_b200 import abi, harness as H
@@ -18,8 +18,8 @@ if first >= 0:
     ctx.shard_mask_position(first)
 ref_hits = None
 for setting in a.settings.split(","):
-    fields = (setting.split(":") + ["", "", "", "", "", ""])[:6]
-    for k, v in zip(("MSNV_PILEUP_CTAS", "MSNV_CHUNK_Q4", "MSNV_MAX_READS", "MSNV_WAIT_HINT_NS", "MSNV_CONSUMERS", "MSNV_ABLATE"), fields):
+    fields = (setting.split(":") + [""] * 9)[:9]
+    for k, v in zip(("MSNV_PILEUP_CTAS", "MSNV_CHUNK_Q4", "MSNV_MAX_READS", "MSNV_WAIT_HINT_NS", "MSNV_CONSUMERS", "MSNV_ABLATE", "MSNV_PILEUP", "MSNV_STAGES", "MSNV_PRODUCER_HINT_NS"), fields):
         os.environ.pop(k, None)
         if v:
             os.environ[k] = v
