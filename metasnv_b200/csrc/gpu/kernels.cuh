@@ -76,6 +76,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
         } while (!done);
     }
 }
+// the producer's wait for a free stage: it is long (the consumers work on an item for microseconds) and a warp that polls
+// takes issue slots from them (a tenth of all executed instructions in the profile), so sleep between polls
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t sleep_ns)
+{
+    if (!sleep_ns) { mbar_wait(bar, parity); return; }
+    while (true) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(sleep_ns);
+    }
+}
 // global -> shared bulk copy (TMA, SASS UBLKCP); dst/src 16-byte aligned, bytes a multiple of 16
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
 {
@@ -552,7 +568,7 @@ constexpr uint32_t CHUNK_FIRST = 1u, CHUNK_LAST = 2u, CHUNK_WIDE = 4u, CHUNK_STO
 struct PileupShape { uint32_t max_reads, max_segs, chunk_q4, has_fix /* some sample carries mate verdicts */, wait_hint_ns, ablate /* measurement only: phases to skip */,
                      gather /* stages carry the gather kernel's segment records and ranges instead of the scatter kernel's tags */,
                      stages /* of the ring, 2 .. PL_STAGES_MAX */,
-                     producer_hint_ns /* how long the producer warp may be parked while it waits for a free stage */; };
+                     producer_hint_ns /* the producer warp sleeps this long between polls for a free stage (0: it spins) */; };
 
 struct ChunkHdr { uint32_t m, nq4, q4_0, sg_0, nseg, c0, item, sample, tile, flags, pad[6]; };
 static_assert(sizeof(ChunkHdr) == 64, "header is one 64-byte block");
@@ -663,7 +679,7 @@ __device__ __forceinline__ void pileup_issue_chunk(uint8_t* smem, const PileupSm
     uint64_t* full = (uint64_t*)(smem + L.bar);
     uint64_t* empty = full + sh.stages;
     const uint32_t s = chunk_no % sh.stages, ph = (chunk_no / sh.stages) & 1u;
-    mbar_wait(empty + s, ph ^ 1u, sh.producer_hint_ns);
+    mbar_wait_parked(empty + s, ph ^ 1u, sh.producer_hint_ns);
     if ((threadIdx.x & 31) == issuer) {
         uint8_t* stage = smem + L.stage0 + s * L.stage_bytes;
         ChunkHdr* h = (ChunkHdr*)(stage + L.o_hdr);
@@ -778,7 +794,7 @@ __device__ __forceinline__ void pileup_producer(uint8_t* smem, const PileupSmem&
     uint64_t* full = (uint64_t*)(smem + L.bar);
     uint64_t* empty = full + sh.stages;
     const uint32_t s = chunk_no % sh.stages, ph = (chunk_no / sh.stages) & 1u;
-    mbar_wait(empty + s, ph ^ 1u, sh.producer_hint_ns);
+    mbar_wait_parked(empty + s, ph ^ 1u, sh.producer_hint_ns);
     if (lane == 0) {
         ((ChunkHdr*)(smem + L.stage0 + s * L.stage_bytes + L.o_hdr))->flags = CHUNK_STOP;
         mbar_arrive(full + s);
@@ -1141,35 +1157,38 @@ __device__ __forceinline__ void gather_quads(uint32_t j0, uint32_t a_rec, uint32
 {
     static_assert(NQ == 1 || NQ == 2, "one or two quads per thread");
     // No branch inside: a record that covers none of this thread's quads is read at offset 0 (inside the stage) and its
-    // qualities are replaced by 0, which no test passes. Some lane of the warp is covered in nearly every step anyway.
-    #pragma unroll 2
-    for (; a_rec < a_end; a_rec += stride) {
-        const uint2 rec = lds_v2(a_rec);
+    // qualities are replaced by 0, which no test passes (some lane of the warp is covered in nearly every step anyway).
+    // Software pipeline, two deep: the record of step i + 2 and the quads of step i + 1 are on their way while step i is
+    // counted - a thread's steps are otherwise one chain of dependent shared-memory round trips.
+    struct Step { uint32_t q[NQ], sv[NQ], f[NQ]; };
+    auto fetch_rec = [&](uint32_t addr) { uint2 r = make_uint2(0u, 0u); if (addr < a_end) r = lds_v2(addr); return r; };       // behind the end: an empty record
+    auto issue = [&](const uint2 rec, Step& st) {
         const uint32_t a = rec.y & 0xffffu, len = (rec.y >> 16) - a, t0 = j0 - a;   // quad q is covered iff t0 + q < len (an empty record has len = 0)
         const bool in0 = t0 < len, in1 = NQ > 1 && t0 + 1u < len;
         const uint32_t x = (in0 || in1) ? rec.x : 0u;                               // rec.x + j = buffer quad of tile quad j
         const uint32_t aq = a_qj + 4u * x, as = a_sj + x, af = a_fj + x;
-        uint32_t q[NQ], sv[NQ], f[NQ];
-        q[0] = lds_u32_at<0>(aq); sv[0] = lds_u8_at<0>(as);
-        if (NQ > 1) { q[NQ - 1] = lds_u32_at<4>(aq); sv[NQ - 1] = lds_u8_at<1>(as); }
-        if (FIX) { f[0] = lds_u8_at<0>(af); if (NQ > 1) f[NQ - 1] = lds_u8_at<1>(af); }
-        if (!in0) { q[0] = 0; if (FIX) f[0] = 0; }                                  // quality 0 and no verdict: nothing counts
-        if (NQ > 1 && !in1) { q[NQ - 1] = 0; if (FIX) f[NQ - 1] = 0; }
+        st.q[0] = lds_u32_at<0>(aq); st.sv[0] = lds_u8_at<0>(as);
+        if (NQ > 1) { st.q[NQ - 1] = lds_u32_at<4>(aq); st.sv[NQ - 1] = lds_u8_at<1>(as); }
+        if (FIX) { st.f[0] = lds_u8_at<0>(af); if (NQ > 1) st.f[NQ - 1] = lds_u8_at<1>(af); }
+        if (!in0) { st.q[0] = 0; if (FIX) st.f[0] = 0; }                            // quality 0 and no verdict: nothing counts
+        if (NQ > 1 && !in1) { st.q[NQ - 1] = 0; if (FIX) st.f[NQ - 1] = 0; }
+    };
+    auto count = [&](const Step& st) {
         #pragma unroll
         for (int i = 0; i < NQ; ++i) {
-            const uint32_t xs = msnv_spread_bases(sv[i]);                           // one 2-bit base per byte lane
+            const uint32_t xs = msnv_spread_bases(st.sv[i]);                        // one 2-bit base per byte lane
             uint32_t ok, nn;
             if (!FIX) {
-                const uint32_t v = (q[i] & 0x7f7f7f7fu) + 0x73737373u;              // bit 7 of a lane: quality >= 13
-                asm("lop3.b32 %0, %1, %2, 0x80808080, 0x20;" : "=r"(ok) : "r"(v), "r"(q[i]));        // ... and the base is A/C/G/T
+                const uint32_t v = (st.q[i] & 0x7f7f7f7fu) + 0x73737373u;           // bit 7 of a lane: quality >= 13
+                asm("lop3.b32 %0, %1, %2, 0x80808080, 0x20;" : "=r"(ok) : "r"(v), "r"(st.q[i]));        // ... and the base is A/C/G/T
                 ok >>= 7;
-                nn = and3(v, q[i], 0x80808080u) >> 7;                               // counted base that is not A/C/G/T
+                nn = and3(v, st.q[i], 0x80808080u) >> 7;                            // counted base that is not A/C/G/T
             } else {
                 // where the overlap rule spoke (low nibble of the quad's fix byte) its verdict (high nibble) replaces the quality test
-                const uint32_t ovr = nibble_to_lanes(f[i]), val = nibble_to_lanes(f[i] >> 4);
-                const uint32_t qp = (((q[i] & 0x7f7f7f7fu) + 0x73737373u) >> 7) & 0x01010101u;
+                const uint32_t ovr = nibble_to_lanes(st.f[i]), val = nibble_to_lanes(st.f[i] >> 4);
+                const uint32_t qp = (((st.q[i] & 0x7f7f7f7fu) + 0x73737373u) >> 7) & 0x01010101u;
                 const uint32_t pass = (qp & ~ovr) | (val & ovr);
-                const uint32_t fl = (q[i] >> 7) & 0x01010101u;
+                const uint32_t fl = (st.q[i] >> 7) & 0x01010101u;
                 ok = pass & ~fl;
                 nn = pass & fl;
             }
@@ -1177,6 +1196,18 @@ __device__ __forceinline__ void gather_quads(uint32_t j0, uint32_t a_rec, uint32
             D[i] += ok; N[i] += nn;
             X0[i] += xs & ok; X1[i] += s1 & ok; X01[i] += and3(xs, s1, ok);
         }
+    };
+    if (a_rec >= a_end) return;
+    Step cur, nxt;
+    uint2 r1;
+    { const uint2 r0 = fetch_rec(a_rec); r1 = fetch_rec(a_rec + stride); issue(r0, cur); }
+    uint32_t a_next = a_rec + 2u * stride;                                          // record of the step after next
+    #pragma unroll 2
+    for (; a_rec < a_end; a_rec += stride, a_next += stride) {
+        issue(r1, nxt);                     // (behind the end: the empty record, offset 0, counted by nobody)
+        r1 = fetch_rec(a_next);
+        count(cur);
+        cur = nxt;
     }
 }
 
