@@ -306,7 +306,8 @@ static PileupShape choose_pileup_shape(uint64_t n_reads, uint64_t n_bases, uint6
     sh.wait_hint_ns = getenv("MSNV_WAIT_HINT_NS") ? (uint32_t)atoi(getenv("MSNV_WAIT_HINT_NS")) : 0u;
     sh.ablate = getenv("MSNV_ABLATE") ? (uint32_t)atoi(getenv("MSNV_ABLATE")) : 0u;
     sh.stages = 2;
-    sh.producer_hint_ns = getenv("MSNV_PRODUCER_HINT_NS") ? (uint32_t)atoi(getenv("MSNV_PRODUCER_HINT_NS")) : 1000u;
+    // (measured: sleeping 200 / 1000 ns between the producer's polls changes nothing, 3000 ns costs 5 %; the plain try_wait executes fewer instructions)
+    sh.producer_hint_ns = getenv("MSNV_PRODUCER_HINT_NS") ? (uint32_t)atoi(getenv("MSNV_PRODUCER_HINT_NS")) : 0u;
     if (const char* e = getenv("MSNV_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= (int)PL_STAGES_MAX) sh.stages = (uint32_t)v; }
     uint32_t mr = deep ? (max_ctas <= 3 ? NARROW_MAX_READS : 96u) : (uint32_t)(reads_per_item * 1.3 + 24.0);
     if (!deep && item_reads_max && mr > item_reads_max) mr = item_reads_max;      // no item has more reads than this

@@ -154,6 +154,51 @@ def test_device_synth_equals_bam_pipeline(preset, scale, samples, built, tmp_pat
         assert np.array_equal(getattr(h, a), getattr(h3, a)), a
 
 
+_FORM_KEYS = ("MSNV_PILEUP", "MSNV_MAX_READS", "MSNV_CHUNK_Q4", "MSNV_STAGES", "MSNV_CONSUMERS", "MSNV_PILEUP_CTAS")
+
+
+@pytest.mark.parametrize("preset,scale,samples", [("c2", 0.003, 12), ("c4", 0.004, 4), ("c3", 0.0005, 12)])
+def test_pileup_kernel_forms_agree(preset, scale, samples, built, monkeypatch):
+    """The two forms of the pileup kernel (gather: counts in registers; scatter: shared-memory atomics) and their staging
+    variants - items cut into several chunks, three stages, 256 consumers, deep items through the gather form's shared
+    planes - give identical per-sample counts and identical hits on the same shard (ordinary depth with mate pairs, deep
+    coverage with > 255 reads per tile, sparse multi-genome)."""
+    from metasnv_b200 import abi
+    desc = H.describe(preset, scale, samples)
+    variants = [
+        {},                                                                    # the library's own choice
+        {"MSNV_PILEUP": "scatter"},
+        {"MSNV_PILEUP": "gather"},
+        {"MSNV_PILEUP": "gather", "MSNV_MAX_READS": "16", "MSNV_CHUNK_Q4": "1280"},          # narrow items in several chunks
+        {"MSNV_PILEUP": "gather", "MSNV_STAGES": "3", "MSNV_PILEUP_CTAS": "2"},
+        {"MSNV_PILEUP": "gather", "MSNV_CONSUMERS": "256"},
+        {"MSNV_PILEUP": "scatter", "MSNV_MAX_READS": "16", "MSNV_CHUNK_Q4": "1280"},
+    ]
+    with abi.Context(0) as ctx:
+        n_pos, first = ctx.shard_synth(desc)
+        if first >= 0:
+            ctx.shard_mask_position(first)
+        S = desc["n_samples"]
+        ref_hits = ref_counts = None
+        for v in variants:
+            for k in _FORM_KEYS:
+                monkeypatch.delenv(k, raising=False)
+            for k, val in v.items():
+                monkeypatch.setenv(k, val)
+            h = ctx.shard_run()
+            hits = {a: np.array(getattr(h, a), copy=True) for a in ("pos", "pop_mask", "ind_mask", "cov", "allele", "total")}
+            counts = [np.array(ctx.shard_counts(s, 0, n_pos), copy=True) for s in range(S)]
+            if ref_hits is None:
+                ref_hits, ref_counts = hits, counts
+                assert sum(int(c.sum()) for c in counts) > 0
+                continue
+            for s, (a, b) in enumerate(zip(ref_counts, counts)):
+                bad = np.argwhere(a != b)
+                assert bad.size == 0, "%s: sample %d first mismatch at %s: %s against %s" % (v, s, bad[0], b[tuple(bad[0])], a[tuple(bad[0])])
+            for a in ref_hits:
+                assert np.array_equal(ref_hits[a], hits[a]), "%s: %s" % (v, a)
+
+
 def test_full_size_shard_counts_recount_with_numpy(built):
     """BASELINE.json's headline shape at FULL size (5 Mb genome, 1000 samples at ~10x: 5e8 reads, 125 GB resident):
     the oracle cannot run at this size, so the device counts of whole samples are checked against the independent
