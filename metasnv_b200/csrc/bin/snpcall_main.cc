@@ -83,6 +83,10 @@ struct BouncePool {
     std::vector<int> free_ids;
     int cur = -1;                                          // the chunk being filled
     bool closed = false;                                   // no more chunks will come (allocation failed or stopped)
+    bool started = false;                                  // chunks are being page-locked (needs the CUDA context); batches decoded before that are staged afterwards
+    void start() { { std::lock_guard<std::mutex> lk(mu); started = true; } cv.notify_all(); }
+    bool is_started() { std::lock_guard<std::mutex> lk(mu); return started; }
+    void wait_started() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return started || closed; }); }
     void add(uint8_t* p) { { std::lock_guard<std::mutex> lk(mu); chunks.push_back(Chunk{p, 0, 0, false}); free_ids.push_back((int)chunks.size() - 1); } cv.notify_all(); }
     void close() { { std::lock_guard<std::mutex> lk(mu); closed = true; } cv.notify_all(); }
     // room for one batch: (pointer, chunk id), or (nullptr, -1) when the batch is larger than a chunk or there is no pool
@@ -220,17 +224,6 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
         fprintf(stderr, "Genomes loaded!\n");
     }
     stage("reference and annotation loaded");
-    ctx_thread.join();
-    if (dev < 0 || ctx_rc != MSNV_OK) {
-        fprintf(stderr, "snpCall: no usable CUDA device (%s); this build has no CPU calling path\n", msnv_last_error(ctx));
-        msnv_destroy(ctx);
-        return 1;
-    }
-    stage("CUDA context created");
-    if (msnv_shard_begin(ctx, S, layout.n_positions, ref.data()) != MSNV_OK) {
-        fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx)); msnv_destroy(ctx); return 1;
-    }
-
     // ---- windows: ranges of tiles sized so that one window's decoded reads are about MSNV_WINDOW_MB (default 4096)
     const uint32_t n_tiles = layout.n_positions / MSNV_TILE;
     uint64_t header_len = 0; for (uint32_t l : hdr.lens) header_len += l;
@@ -246,6 +239,9 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     if (n_windows > n_tiles) n_windows = n_tiles;
     const uint32_t tiles_per_window = (n_tiles + n_windows - 1) / n_windows;
     n_windows = (n_tiles + tiles_per_window - 1) / tiles_per_window;
+
+    // MSNV_EARLY_DECODE=0: wait for the CUDA context before anything is decoded (measurement switch; default: decode meanwhile)
+    if (getenv("MSNV_EARLY_DECODE") && atoi(getenv("MSNV_EARLY_DECODE")) == 0 && ctx_thread.joinable()) ctx_thread.join();
 
     // ---- decoders (one per BAM, resumable) and the thread pool
     int n_threads = (int)std::thread::hardware_concurrency();
@@ -275,21 +271,9 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
                 }
             });
         for (auto& th : pool) th.join();
-        if (bad) { fprintf(stderr, "snpCall: %s\n", first_err.c_str()); msnv_destroy(ctx); return 1; }
+        if (bad) { fprintf(stderr, "snpCall: %s\n", first_err.c_str()); if (ctx_thread.joinable()) ctx_thread.join(); msnv_destroy(ctx); return 1; }
     }
     BouncePool pool;
-    std::atomic<bool> stop_pinning(false);
-    std::thread pinner([&]() {
-        size_t n = (size_t)std::min(8.0, std::max(2.0, est_bytes / (double)BouncePool::CHUNK));
-        if (const char* e = getenv("MSNV_BOUNCE_CHUNKS")) n = (size_t)std::max(0, atoi(e));
-        for (size_t i = 0; i < n && !stop_pinning; ++i) {
-            uint8_t* p = (uint8_t*)msnv_pinned_alloc(BouncePool::CHUNK);
-            if (!p) break;
-            pool.add(p);
-        }
-        pool.close();
-    });
-    struct PinJoin { std::atomic<bool>& stop; std::thread& t; ~PinJoin() { stop = true; if (t.joinable()) t.join(); } } pin_join{stop_pinning, pinner};
     stage("decoders open");
 
     // MSNV_RAW=0: build the position-aligned layout on the host (the C ABI's other input form) instead of on the device
@@ -308,6 +292,11 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
         J.view.assign(raw_mode ? 0 : S, msnv_sample_reads{}); J.rview.assign(raw_mode ? S : 0, msnv_raw_reads{}); J.chunk.assign(S, -1);
         for (int t = 0; t < n_threads; ++t)
             J.pool.emplace_back([&J, &dec, &batch, &rbatch, &pool, raw_mode, k, lo, hi, S]() {
+                auto stage_one = [&](uint32_t s) {
+                    if (raw_mode) J.rview[s] = stage_raw(rbatch[k & 1][s], pool, J.chunk[s]);
+                    else J.view[s] = stage_batch(batch[k & 1][s], pool, J.chunk[s]);
+                };
+                std::vector<uint32_t> deferred;           // decoded while the CUDA context was still coming up: no bounce chunk to copy into yet
                 for (;;) {
                     const uint32_t s = J.next.fetch_add(1);
                     if (s >= S) break;
@@ -318,16 +307,57 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
                         else good = dec[s]->window(lo, (uint32_t)hi, k ? &batch[(k - 1) & 1][s] : nullptr, batch[k & 1][s], e);
                     }
                     if (good && !J.failed) {
-                        if (raw_mode) J.rview[s] = stage_raw(rbatch[k & 1][s], pool, J.chunk[s]);
-                        else J.view[s] = stage_batch(batch[k & 1][s], pool, J.chunk[s]);
+                        if (!pool.is_started()) { deferred.push_back(s); continue; }
+                        stage_one(s);
                     }
                     std::lock_guard<std::mutex> lk(J.mu);
                     if (!good) { if (J.err.empty()) J.err = e; J.failed = true; }
                     J.ready.push_back(s);
                 }
+                for (uint32_t s : deferred) {
+                    pool.wait_started();                  // (or closed: then the batch goes up from the decoder's own arrays)
+                    if (!J.failed) stage_one(s);
+                    std::lock_guard<std::mutex> lk(J.mu);
+                    J.ready.push_back(s);
+                }
             });
     };
 
+    // the first window is decoded while the CUDA context comes up (0.5 - 0.9 s); what is decoded before bounce chunks can be
+    // page-locked is copied into them afterwards
+    stage("first window starts");
+    const double t_dec0 = now_s();
+    std::unique_ptr<WindowJob> cur(new WindowJob()), nxt;
+    start_window(*cur, 0);
+    if (ctx_thread.joinable()) ctx_thread.join();
+    if (dev < 0 || ctx_rc != MSNV_OK) {
+        fprintf(stderr, "snpCall: no usable CUDA device (%s); this build has no CPU calling path\n", msnv_last_error(ctx));
+        cur->failed = true; pool.close();
+        for (auto& th : cur->pool) th.join();
+        msnv_destroy(ctx);
+        return 1;
+    }
+    stage("CUDA context created");
+    if (msnv_shard_begin(ctx, S, layout.n_positions, ref.data()) != MSNV_OK) {
+        fprintf(stderr, "snpCall: %s\n", msnv_last_error(ctx));
+        cur->failed = true; pool.close();
+        for (auto& th : cur->pool) th.join();
+        msnv_destroy(ctx); return 1;
+    }
+
+    std::atomic<bool> stop_pinning(false);
+    pool.start();
+    std::thread pinner([&]() {
+        size_t n = (size_t)std::min(8.0, std::max(2.0, est_bytes / (double)BouncePool::CHUNK));
+        if (const char* e = getenv("MSNV_BOUNCE_CHUNKS")) n = (size_t)std::max(0, atoi(e));
+        for (size_t i = 0; i < n && !stop_pinning; ++i) {
+            uint8_t* p = (uint8_t*)msnv_pinned_alloc(BouncePool::CHUNK);
+            if (!p) break;
+            pool.add(p);
+        }
+        pool.close();
+    });
+    struct PinJoin { std::atomic<bool>& stop; std::thread& t; ~PinJoin() { stop = true; if (t.joinable()) t.join(); } } pin_join{stop_pinning, pinner};
     HitWriter w;
     w.pop_out = stdout; w.indiv_out = indiv; w.ann = ann.active() ? &ann : nullptr;
     std::vector<HitWriter::Contig> ctgs;
@@ -340,10 +370,6 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     bool masked = false;
     int64_t first_col = -1;
     int rc = 0;
-    stage("first window starts");
-    const double t_dec0 = now_s();
-    std::unique_ptr<WindowJob> cur(new WindowJob()), nxt;
-    start_window(*cur, 0);
     for (uint32_t k = 0; k < n_windows && !rc; ++k) {
         const uint32_t slot = k & 1u;
         const uint32_t lo = k * tiles_per_window * MSNV_TILE, hi = (uint32_t)std::min<uint64_t>((uint64_t)(k + 1) * tiles_per_window * MSNV_TILE, layout.n_positions);

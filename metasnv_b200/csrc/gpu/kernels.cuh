@@ -429,23 +429,22 @@ __global__ void __launch_bounds__(256) mate_kernel(const SampleDev* __restrict__
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5, warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     // the quads [lo, hi) (positions) that a segment of a at (ax, first quad qa) and one of b at (bx, qb) share
     auto overlap = [&](int32_t ax, uint32_t qa, int32_t bx, uint32_t qb, int32_t lo, int32_t hi) {
+        const uint32_t ia0 = qa - (uint32_t)(ax >> 2), ib0 = qb - (uint32_t)(bx >> 2);                  // quad index of position quad P: i0 + P
         for (int32_t P = (lo >> 2) + (int32_t)lg; P < ((hi + 3) >> 2); P += (int32_t)MATE_LANES) {      // (empty when the segments share no position)
-            const uint32_t ia = qa + (uint32_t)(P - (ax >> 2)), ib = qb + (uint32_t)(P - (bx >> 2));
+            const uint32_t ia = ia0 + (uint32_t)P, ib = ib0 + (uint32_t)P;
             if (ia >= nq_total || ib >= nq_total) continue;           // segments and offsets disagree (the pileup kernel reports it)
             const uint32_t va = __ldg(qual32 + ia), vb = __ldg(qual32 + ib);
             const uint32_t d = msnv_spread_bases((uint32_t)__ldg(sd.seq2 + ia) ^ (uint32_t)__ldg(sd.seq2 + ib));
-            const bool whole = (P << 2) >= lo && (P << 2) + 4 <= hi;
-            const uint32_t msk = whole ? 0xffffffffu : msnv_quad_mask(P << 2, lo, hi);
-            uint32_t na, nb;
-            msnv_overlap_pass4(va, vb, d, msk, na, nb);               // masked lanes: flag | 16 (passes) or flag | 0
-            const uint32_t ovr = lanes_to_nibble(msk);
-            const uint32_t fa = ovr | (lanes_to_nibble(na >> 4) & ovr) << 4, fb = ovr | (lanes_to_nibble(nb >> 4) & ovr) << 4;
+            uint32_t pa7, pb7;
+            msnv_overlap_verdict4(va, vb, d, pa7, pb7);               // bit 7 of a lane: that mate's base still passes
+            const uint32_t na = ((pa7 >> 7) * 0x01020408u) >> 24, nb = ((pb7 >> 7) * 0x01020408u) >> 24;     // ... as nibbles
             // a quad the rule covers whole belongs to this segment combination alone: plain byte stores. Two
             // combinations can meet in a quad at their ends (with disjoint positions): OR into the byte there.
-            if (whole) { sd.fix[ia] = (uint8_t)fa; sd.fix[ib] = (uint8_t)fb; }
+            if ((P << 2) >= lo && (P << 2) + 4 <= hi) { sd.fix[ia] = (uint8_t)(0xfu | na << 4); sd.fix[ib] = (uint8_t)(0xfu | nb << 4); }
             else {
-                atomicOr(fix32 + (ia >> 2), fa << (8u * (ia & 3u)));
-                atomicOr(fix32 + (ib >> 2), fb << (8u * (ib & 3u)));
+                const uint32_t ovr = lanes_to_nibble(msnv_quad_mask(P << 2, lo, hi));
+                atomicOr(fix32 + (ia >> 2), (ovr | (na & ovr) << 4) << (8u * (ia & 3u)));
+                atomicOr(fix32 + (ib >> 2), (ovr | (nb & ovr) << 4) << (8u * (ib & 3u)));
             }
         }
     };

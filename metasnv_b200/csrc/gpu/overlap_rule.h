@@ -84,6 +84,22 @@ MSNV_RULE_HD void msnv_overlap_pass4(uint32_t va, uint32_t vb, uint32_t d, uint3
     ob = (vb & ~m) | ((fb | (pb >> 3)) & m);
 }
 
+// The verdicts alone, for all four lanes: bit 7 of a lane of pa7 / pb7 = the base of mate a / b still passes Q13 after the
+// rule (what msnv_overlap_pass4 encodes as quality 16). The caller masks the lanes the rule does not apply to.
+MSNV_RULE_HD void msnv_overlap_verdict4(uint32_t va, uint32_t vb, uint32_t d, uint32_t& pa7, uint32_t& pb7)
+{
+    const uint32_t H = 0x80808080u;
+    const uint32_t fa = va & H, fb = vb & H, qa = va & ~H, qb = vb & ~H;
+    const uint32_t diff7 = (d | (d << 1)) << 6;                                  // bit 7: the 2-bit codes differ
+    const uint32_t same7 = (fa & fb) | ~(fa | fb | diff7);                       // bit 7: "bases equal"
+    const uint32_t sum = qa + qb;                                                // <= 254 per lane: no carry between lanes
+    const uint32_t s13 = ((sum & ~H) + 0x73737373u) | sum;                       // bit 7: qa + qb >= 13
+    const uint32_t ge7 = (qa | H) - qb;                                          // bit 7: qa >= qb (no borrow between lanes)
+    const uint32_t a17 = qa + 0x6f6f6f6fu, b17 = qb + 0x6f6f6f6fu;               // bit 7: quality >= 17
+    pa7 = ((same7 & s13) | (~same7 & ge7 & a17)) & H;
+    pb7 = ~same7 & ~ge7 & b17 & H;
+}
+
 // byte-lane mask of the positions p0 .. p0+3 that lie in [lo, hi); the quad must intersect the range
 MSNV_RULE_HD uint32_t msnv_quad_mask(int32_t p0, int32_t lo, int32_t hi)
 {

@@ -39,6 +39,15 @@ int main() {
                                 if (((fa & 0x7f) >= 13) != ((ga & 0x7f) >= 13) || ((fb & 0x7f) >= 13) != ((gb & 0x7f) >= 13)) ++bad;
                             } else if (fa != ga || fb != gb) ++bad;
                         }
+                        // the verdicts alone (what mate_kernel stores): bit 7 of a lane = "passes Q13" of the threshold form
+                        uint32_t qa7, qb7;
+                        msnv_overlap_verdict4(va, vb, msnv_spread_bases(sa ^ sb), qa7, qb7);
+                        for (int k = 0; k < 4; ++k)
+                            if ((m >> (8 * k)) & 0xff) {
+                                if (((qa7 >> (8 * k + 7)) & 1u) != ((((pa >> (8 * k)) & 0x7f) >= 13) ? 1u : 0u)) ++bad;
+                                if (((qb7 >> (8 * k + 7)) & 1u) != ((((pb >> (8 * k)) & 0x7f) >= 13) ? 1u : 0u)) ++bad;
+                            }
+                        if ((qa7 | qb7) & 0x7f7f7f7fu) ++bad;
                     }
     for (uint32_t q = 0; q < 256; ++q) if (msnv_q08(q) != (uint32_t)(0.8 * (double)q)) ++bad;
     for (int p0 = 0; p0 < 16; p0 += 4) for (int lo = 0; lo < 20; ++lo) for (int hi = lo + 1; hi < 24; ++hi) {
