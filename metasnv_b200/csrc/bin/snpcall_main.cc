@@ -505,8 +505,12 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     // (each cudaFree is a device-wide synchronisation) would only add seconds
     stop_pinning = true;
     if (pinner.joinable()) pinner.join();
-    if (getenv("MSNV_CLEAN_EXIT")) { for (auto& c : pool.chunks) msnv_pinned_free(c.base); msnv_destroy(ctx); }
-    return 0;
+    if (getenv("MSNV_CLEAN_EXIT")) { for (auto& c : pool.chunks) msnv_pinned_free(c.base); msnv_destroy(ctx); return 0; }
+    // nor are the decoded batches and decoders (gigabytes of vectors) worth freeing one by one: everything is written, leave
+    if (indiv) fclose(indiv);
+    fflush(stdout); fflush(stderr);
+    stage("exit");
+    _exit(0);
 }
 
 int main(int argc, char** argv)
