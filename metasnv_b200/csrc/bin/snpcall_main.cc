@@ -240,8 +240,11 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
     const uint32_t tiles_per_window = (n_tiles + n_windows - 1) / n_windows;
     n_windows = (n_tiles + tiles_per_window - 1) / tiles_per_window;
 
-    // MSNV_EARLY_DECODE=0: wait for the CUDA context before anything is decoded (measurement switch; default: decode meanwhile)
-    if (getenv("MSNV_EARLY_DECODE") && atoi(getenv("MSNV_EARLY_DECODE")) == 0 && ctx_thread.joinable()) ctx_thread.join();
+    // MSNV_EARLY_DECODE=1: decode the first window while the CUDA context comes up (batches are staged into bounce chunks once they
+    // can be page-locked). Default: wait for the context first - 21 interleaved runs on four boxes show no difference in the mean
+    // (4.1 s against 4.0 s on 2 GB of BAM): the early decode hides a slow context (1 - 3 s) but decodes slower while the driver maps
+    // memory (the decoders' page faults and the driver's mappings contend for the address-space lock); BASELINE.md section 4.
+    if (!(getenv("MSNV_EARLY_DECODE") && atoi(getenv("MSNV_EARLY_DECODE")) != 0) && ctx_thread.joinable()) ctx_thread.join();
 
     // ---- decoders (one per BAM, resumable) and the thread pool
     int n_threads = (int)std::thread::hardware_concurrency();
@@ -323,8 +326,8 @@ static int run_direct(const Job& job, const msnv_call_params& prm, const std::st
             });
     };
 
-    // the first window is decoded while the CUDA context comes up (0.5 - 0.9 s); what is decoded before bounce chunks can be
-    // page-locked is copied into them afterwards
+    // (MSNV_EARLY_DECODE=1: the context may still be coming up here; what is decoded before bounce chunks can be page-locked is
+    // copied into them afterwards)
     stage("first window starts");
     const double t_dec0 = now_s();
     std::unique_ptr<WindowJob> cur(new WindowJob()), nxt;

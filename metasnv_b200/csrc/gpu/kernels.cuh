@@ -1048,7 +1048,7 @@ pileup_kernel(const SampleDev* __restrict__ samples, const Item* __restrict__ it
 __device__ __forceinline__ int32_t clamp_quad(int32_t v) { return v < 0 ? 0 : (v > TILE_QUADS ? TILE_QUADS : v); }
 
 // Layout of a stage's "set" block (16 words): [0] jmin, [1] jmax (quads [jmin, jmax) can be covered), [2..9] maximum of the
-// read ends per block of 32 reads.
+// read ends per block of 32 reads, [10] != 0: the ranges are not usable (see below).
 template <int CONSUMERS>
 __device__ __forceinline__ void gather_setup(uint8_t* stage, const PileupSmem& L, int* __restrict__ err_flag)
 {
@@ -1101,7 +1101,7 @@ __device__ __forceinline__ void gather_setup(uint8_t* stage, const PileupSmem& L
                 B += (uint32_t)nq;
             }
             if (B != B_end) atomicExch(err_flag, 2);                            // quads no segment owns
-            if (t == 0) set[0] = aq[i];                                         // jmin
+            if (t == 0) { set[0] = aq[i]; set[10] = 0; }                        // jmin; "ranges are valid"
         }
         if ((uint32_t)i * CONSUMERS < m) {                                      // (uniform)
             int32_t v = eq;
@@ -1128,6 +1128,9 @@ __device__ __forceinline__ void gather_setup(uint8_t* stage, const PileupSmem& L
         if (t < m) {
             for (int32_t j = p_prev; j < p; ++j) lohi[2 * j] = (uint16_t)k0[i];
             const int32_t upper = t + 1 < m ? read_start(t + 1) : p;
+            // first segments out of coordinate order (the reads are in order of `pos`, but a CIGAR may open with a deletion): the
+            // runs of hi would overlap. Such a chunk is counted with every record offered to every quad instead.
+            if (t + 1 < m && upper < aq[i]) set[10] = 1;
             for (int32_t j = aq[i]; j < upper; ++j) lohi[2 * j + 1] = (uint16_t)k1[i];
             if (t + 1 == m) set[1] = p;                                         // jmax (>= jmin)
         }
@@ -1268,7 +1271,8 @@ pileup_gather_kernel(const SampleDev* __restrict__ samples, const Item* __restri
         const uint8_t* s_fx = stage + L.o_fix + c12;
         const uint32_t* s_exp = (const uint32_t*)(stage + L.o_exp);
         const uint32_t* set = (const uint32_t*)(stage + L.o_set);
-        const uint32_t jmin = set[0], jmax = set[1];
+        const bool no_ranges = set[10] != 0;                                    // (rare: see gather_setup)
+        const uint32_t jmin = no_ranges ? 0u : set[0], jmax = set[1];
         const bool has_fix = (flags & CHUNK_FIX) != 0;
         // narrow items (at most 255 reads: a byte lane cannot overflow) stay in the registers of the threads that own their
         // quads, over as many chunks as the item takes, and go from there to HBM; deep items go through the shared planes
@@ -1290,8 +1294,8 @@ pileup_gather_kernel(const SampleDev* __restrict__ samples, const Item* __restri
             // the quads of this thread that a segment of the chunk can cover: [ja, jb)
             const uint32_t ja = j0 > jmin ? j0 : jmin, jb = j0 + QPT < jmax ? j0 + QPT : jmax;
             if (ja < jb && !(sh.ablate & 1u)) {
-                const uint32_t lo = lohi[ja] & 0xffffu;
-                uint32_t hi = lohi[jb - 1u] >> 16;
+                const uint32_t lo = no_ranges ? 0u : lohi[ja] & 0xffffu;
+                uint32_t hi = no_ranges ? nseg : lohi[jb - 1u] >> 16;
                 if (hi > nseg) hi = nseg;
                 const uint32_t k = lo + ((grp - lo) & (G - 1u));                // first segment of this group at or behind lo
                 if (has_fix) gather_quads<true, QPT>(j0, a_recs + 8u * k, a_recs + 8u * hi, 8u * G, a_q + 4u * j0, a_s + j0, a_f + j0, D, N, X0, X1, X01);

@@ -62,7 +62,8 @@ def check_layout(e):
     nq = ((sp & 3) + sl + 3) >> 2
     per_read = np.add.reduceat(nq, seg_off[:-1]) if n else np.zeros(0, np.int64)
     assert np.array_equal(per_read, np.diff(q4_off)), "a read owns exactly the quads of its segments"
-    assert np.array_equal(sp[seg_off[:-1]], e["pos"].astype(np.int64)), "pos is the first segment's start"
+    # pos is the first reference base the read covers: the first segment's start unless the CIGAR opens with a deletion / skip
+    assert np.all(sp[seg_off[:-1]] >= e["pos"].astype(np.int64)), "no segment starts in front of the read"
     span = np.maximum.reduceat(sp + sl, seg_off[:-1]) - e["pos"].astype(np.int64) if n else np.zeros(0, np.int64)
     assert n == 0 or span.max() <= int(e["max_span"])
     m = e["mate"].astype(np.int64)

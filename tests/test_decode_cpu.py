@@ -65,10 +65,10 @@ def test_decoder_batches_recount_to_the_oracle_text(preset, scale, samples, data
 
 
 @pytest.mark.parametrize("sams,pile", [(("s1", "s2"), "expected.pileup"), (("s4_ops", "s1"), "expected_ops.pileup"),
-                                       (("s3_refskip",), "expected_refskip.pileup")])
+                                       (("s3_refskip",), "expected_refskip.pileup"), (("s6_leading_del", "s1"), "expected_leading_del.pileup")])
 def test_decoder_hand_written_cases(sams, pile, built, tmp_path):
     """The hand-written SAM files (indels, clips, =/X/P/N operations, overlapping mates with indels, filtered flags,
-    orphans, N bases) against the pinned pileup text."""
+    orphans, N bases, CIGARs that open with a deletion) against the pinned pileup text."""
     tmp = str(tmp_path)
     bams = []
     for s in sams:
@@ -88,7 +88,7 @@ def test_bam_shaped_batches_expand_to_the_aligned_layout(built, tmp_path):
     (indels, clips, =/X/P/N/H operations, N bases, one-base segments) and a small synthetic set."""
     tmp = str(tmp_path)
     bams = []
-    for s in ("s1", "s2", "s4_ops", "s3_refskip", "s5_rules"):
+    for s in ("s1", "s2", "s4_ops", "s3_refskip", "s5_rules", "s6_leading_del"):
         out = os.path.join(tmp, s + ".bam")
         subprocess.run([bin_path("msnv_synth"), "--sam", os.path.join(GOLDEN, "hand", s + ".sam"), "--bam", out], check=True)
         bams.append(out)

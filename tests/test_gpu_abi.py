@@ -256,7 +256,7 @@ def test_expand_kernel_builds_the_aligned_layout(built, tmp_path):
     from pileup_counts import ARRAYS, RAW_ARRAYS
     tmp = str(tmp_path)
     bams = []
-    for s in ("s1", "s2", "s4_ops", "s3_refskip", "s5_rules"):
+    for s in ("s1", "s2", "s4_ops", "s3_refskip", "s5_rules", "s6_leading_del"):
         out = os.path.join(tmp, s + ".bam")
         subprocess.run([bin_path("msnv_synth"), "--sam", os.path.join(GOLDEN, "hand", s + ".sam"), "--bam", out], check=True)
         bams.append(out)

@@ -213,6 +213,42 @@ def test_exotic_cigar_operations_counts_match_pinned_oracle_text(built, tmp_path
     assert int(got[0].sum()) > 60
 
 
+@pytest.mark.parametrize("form", ["gather", "scatter"])
+def test_cigars_that_open_with_a_deletion(form, built, tmp_path):
+    """tests/golden/hand/s6_leading_del.sam: reads in order of POS whose first aligned bases are NOT in order (6D10M at 5,
+    12M at 6, 2D8M at 7, ...). The gather form of the pileup kernel derives its per-quad segment ranges from coordinate
+    order and must notice (it then offers every record to every quad); both forms must give the pinned counts and the
+    oracle's calls."""
+    tmp = str(tmp_path)
+    bams = []
+    for s in ("s6_leading_del", "s1"):
+        out = os.path.join(tmp, s + ".bam")
+        subprocess.run([bin_path("msnv_synth"), "--sam", os.path.join(GOLDEN, "hand", s + ".sam"), "--bam", out], check=True)
+        bams.append(out)
+    open(os.path.join(tmp, "all_samples"), "w").write("\n".join(bams) + "\n")
+    os.symlink(os.path.join(GOLDEN, "hand", "ref.fa"), os.path.join(tmp, "ref.fa"))
+    env = dict(os.environ, MSNV_PILEUP=form)
+    o, g = os.path.join(tmp, "oracle"), os.path.join(tmp, "gpu")
+    rc, err = H.run_oracle_snpcall(tmp, o, c=1, t=1)
+    assert rc == 0, err
+    rc, err = H.run_product_snpcall(tmp, g, c=1, t=1, env=env)
+    assert rc == 0, err
+    for ext in (".called", ".indiv"):
+        _same(o + ext, g + ext)
+    assert os.path.getsize(o + ".called") + os.path.getsize(o + ".indiv") > 0
+    dump = os.path.join(tmp, "counts.bin")
+    rc, err = H.run_product_snpcall(tmp, os.path.join(tmp, "gpu_counts"), c=1, t=1, env=dict(env, MSNV_DUMP_COUNTS=dump))
+    assert rc == 0, err
+    lay = [l.rstrip("\n").split("\t") for l in open(dump + ".layout")]
+    S, P = int(lay[0][0]), int(lay[0][1])
+    layout = [(n, int(o_), int(l)) for n, o_, l in lay[1:]]
+    got = np.fromfile(dump, np.uint16).reshape(S, P, 5)
+    want = _oracle_counts(os.path.join(GOLDEN, "hand", "expected_leading_del.pileup"), S, layout, P)
+    bad = np.argwhere(want != got)
+    assert bad.size == 0, "first mismatch (sample,pos,channel)=%s want %s got %s" % (bad[0], want[tuple(bad[0])], got[tuple(bad[0])])
+    assert int(got[0].sum()) > 60
+
+
 def test_empty_inputs(built, tmp_path):
     """BAMs with a header but no reads, alone and next to a populated one."""
     d = str(tmp_path)

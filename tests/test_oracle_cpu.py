@@ -83,6 +83,16 @@ def test_mpileup_restatement_hand_case(built, tmp_path):
     l4 = txt4.decode().split("\n")
     assert l4[5].startswith("ctgA\t6\tC\t4\tA.,.\t")                  # the X of 5=1X4= is a mismatch like any other
     assert l4[11].startswith("ctgA\t12\tt\t2\t*^]a\tA5\t")             # q1's deletion meets its mate's first base: no overlap rule on '*'
+    # CIGARs that open with a deletion: the reads are in order of POS, their first aligned bases are not (hand-derived:
+    # column 11 sees d1 . d2 C d3 . d4 . d5 T d6 . in file order; a read shows '*' with its start marker in its first column)
+    lst6 = os.path.join(tmp, "list6")
+    open(lst6, "w").write("%s\n%s\n" % (_bam_from_sam("s6_leading_del", tmp), _bam_from_sam("s1", tmp)))
+    txt6 = subprocess.check_output([H.oracle_bin("mpileup_oracle"), "mpileup", "-f", ref, "-B", "-b", lst6])
+    assert txt6 == open(os.path.join(GOLDEN, "hand", "expected_leading_del.pileup"), "rb").read()
+    l6 = txt6.decode().split("\n")
+    assert l6[4].startswith("ctgA\t5\tA\t2\t.^]*\tII\t")               # d1 opens with a deleted base
+    assert l6[10].startswith("ctgA\t11\tg\t6\t.C..T.\tIIIIII\t")
+    assert l6[16].startswith("ctgA\t17\tN\t5\tAA$.$GC\tIIIII\t")         # d4's last base is N on an N reference: '.'; d5's second segment (after its inner deletion) shows G
     # N operations render '>' / '<'
     lst3 = os.path.join(tmp, "list3")
     open(lst3, "w").write("%s\n" % _bam_from_sam("s3_refskip", tmp))
